@@ -1,0 +1,338 @@
+"""Generate tests/golden/*.npz from the LIVE reference (dev container only).
+
+Run:  python oracle/gen_golden.py
+Needs /root/reference (numba path, fastmath=False).  The reference ships no
+golden vectors of its own, so these files -- outputs of the
+reference itself on seeded inputs -- are what pins oracle/vs_oracle.c and,
+through it, the CUDA path.  Everything is seeded; re-running reproduces the
+files bit for bit on the same numpy/numba/libm.
+"""
+import os
+import sys
+from itertools import repeat
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def cloud(rng, n, extent, central_mass=1e6, vscale=1.0):
+    """Small random 2-D system: heavy body 0 at origin + light bodies on roughly
+    circular orbits (distinct masses)."""
+    mass = rng.uniform(0.5, 2.0, n)
+    mass[0] = central_mass
+    r = rng.uniform(0.05, 1.0, n) * extent
+    th = rng.uniform(0, 2 * np.pi, n)
+    pos = np.stack([r * np.cos(th), r * np.sin(th)], axis=1)
+    sp = np.sqrt(central_mass / r) * rng.normal(1.0, 0.1, n) * vscale
+    vel = np.stack([-sp * np.sin(th), sp * np.cos(th)], axis=1)
+    pos[0] = 0
+    vel[0] = 0
+    den = np.full(n, 3000.0)
+    return mass, den, pos, vel
+
+
+def snap(ph, prefix):
+    return {prefix + k: np.array(getattr(ph, k)) for k in
+            ("mass", "rad", "pos", "vel", "rel_vel", "coi", "parents", "focus", "ecc_v",
+             "semi_major", "semi_minor", "periapsis_arg")}
+
+
+def gen_solar(ns):
+    gd, conf, bd, bod, vd, vod = ns.peripherals.load_file(ns.solar_system_ini)
+    out = dict(mass=bd["mass"].copy(), den=bd["den"].copy(), pos0=bod["pos"].copy(),
+               vel0=bod["vel"].copy(), gc=conf["gc"], rad_mult=conf["rad_mult"],
+               coi_coef=conf["coi_coef"])
+    ph = ns.phys_editor.Physics()
+    ph.load_system(conf, bd, bod)
+    out.update(load_coi=ph.coi.copy(), load_parents=np.array(ph.parents),
+               load_rel_vel=ph.rel_vel.copy(), load_rad=ph.rad.copy(),
+               load_largest=int(ph.largest))
+    ph.kepler_basic(); ph.temp_color(); ph.classify()
+    out.update(snap(ph, "f0_"))
+    rh.set_curve_points(ns, ph, 64)
+    frames = 0
+    for target in (1, 2, 100, 1000, 10000):
+        while frames < target:
+            rh.editor_frame(ph)
+            frames += 1
+        out.update(snap(ph, "f%d_" % target))
+        if target == 100:
+            out["f100_curve64"] = ph.curve()
+    save("solar_editor", **out)
+    return conf, bd, bod
+
+
+def gen_editor_clouds(ns):
+    """MODE_REF frames with parent changes and merges on small seeded clouds."""
+    rng = np.random.default_rng(20240611)
+    out = {}
+    # case A: 48-body hierarchical system (moons inside planet COIs), no overlap
+    n = 48
+    mass, den, pos, vel = cloud(rng, n, 2.0e4, central_mass=1e4)
+    mass[1:7] = rng.uniform(50, 400, 6)                 # planets
+    for k in range(7, 19):                               # moons near planets
+        p = 1 + (k % 6)
+        d = rng.uniform(40, 120)
+        th = rng.uniform(0, 2 * np.pi)
+        pos[k] = pos[p] + d * np.array([np.cos(th), np.sin(th)])
+        sp = np.sqrt(mass[p] / d)
+        vel[k] = vel[p] + sp * np.array([-np.sin(th), np.cos(th)])
+        mass[k] = rng.uniform(0.01, 0.5)
+    for k in range(19, 33):                              # COI crossers: fly-bys and escapers
+        p = 1 + (k % 6)
+        coi_est = np.hypot(*pos[p]) * (mass[p] / mass[0]) ** 0.7
+        th = rng.uniform(0, 2 * np.pi)
+        d = coi_est * (rng.uniform(1.02, 1.2) if k % 2 else rng.uniform(0.5, 0.9))
+        u = np.array([np.cos(th), np.sin(th)])
+        pos[k] = pos[p] + d * u
+        sp = np.sqrt(mass[p] / d) * (rng.uniform(0.3, 1.2) if k % 2 else rng.uniform(1.5, 2.5))
+        vel[k] = vel[p] - sp * u * (1 if k % 2 else -1) + 0.3 * sp * np.array([-u[1], u[0]])
+        mass[k] = rng.uniform(0.01, 0.5)
+    den[:] = 3.0e7                                       # tiny radii: case A is about COI crossings
+    ph = rh.editor_from_arrays(ns, mass, den, pos, vel)
+    out.update(A_mass=mass, A_den=den, A_pos0=pos, A_vel0=vel)
+    out.update(snap(ph, "A_f0_"))
+    dels, plog = [], []
+    for fr in range(1, 601):
+        d = rh.editor_frame(ph)
+        dels.append(d[0] if d else -1)
+        plog.append(np.array(ph.parents) if len(ph.parents) == n else np.full(n, -1))
+        if fr in (1, 50, 300, 600):
+            out.update(snap(ph, "A_f%d_" % fr))
+    out["A_deleted"] = np.array(dels)
+    out["A_parents_log"] = np.array([p if len(p) == n else np.full(n, -1) for p in plog])
+
+    # case B: dense 40-body clump => merges (incl. index shifts)
+    n = 40
+    mass, den, pos, vel = cloud(rng, n, 600.0, central_mass=5e3, vscale=0.6)
+    den[:] = 300.0
+    ph = rh.editor_from_arrays(ns, mass, den, pos, vel)
+    out.update(B_mass=mass, B_den=den, B_pos0=pos, B_vel0=vel)
+    dels, counts = [], []
+    for fr in range(1, 121):
+        d = rh.editor_frame(ph)
+        dels.append(d[0] if d else -1)
+        counts.append(len(ph.mass))
+        if fr in (1, 10, 40, 120):
+            out.update(snap(ph, "B_f%d_" % fr))
+    out["B_deleted"] = np.array(dels)
+    out["B_counts"] = np.array(counts)
+
+    # case C: the 5-body toy of SURVEY 8(c): two simultaneous overlaps (1,4),(2,3)
+    mass = np.array([1e4, 5.0, 7.0, 3.0, 9.0])
+    den = np.full(5, 1.0)
+    pos = np.array([[0, 0], [5000.0, 0], [0, 8000.0], [0, 8010.0], [5010.0, 0]])
+    vel = np.array([[0, 0], [0, 1.4], [-1.1, 0], [-1.0, 0], [0, 1.5]])
+    ph = rh.editor_from_arrays(ns, mass, den, pos, vel)
+    out.update(C_mass=mass, C_den=den, C_pos0=pos, C_vel0=vel)
+    out["C_check0"] = np.array(ph.check_collision())
+    d1 = ph.inelastic_collision()
+    out["C_del1"] = np.array(d1)
+    out.update(snap(ph, "C_m1_"))
+    out["C_check1"] = np.array(ph.check_collision())
+    save("editor_clouds", **out)
+
+
+def gen_pair_kernels(ns):
+    """Direct calls of the jitted per-body kernels on seeded clouds."""
+    rng = np.random.default_rng(20240612)
+    pe = ns.phys_editor
+    out = {}
+    n = 384
+    mass, den, pos, vel = cloud(rng, n, 3.0e3, central_mass=1e4)
+    coi = rng.uniform(0, 400, n) * (rng.uniform(0, 1, n) < 0.5)
+    coi[0] = 0
+    order = np.argsort(mass)[-1::-1]
+    parents = np.array(list(map(pe.find_parent_one, list(range(n)), repeat(order), repeat(pos),
+                                repeat(coi))))
+    out.update(fp_mass=mass, fp_pos=pos, fp_coi=coi, fp_order=order, fp_parents=parents)
+    rel_pos = pos[parents] - pos
+    acc = np.array(list(map(pe.gravity_one, list(range(n)), parents, repeat(mass), rel_pos,
+                            repeat(0.75))))
+    out.update(g1_acc=acc, g1_gc=0.75)
+    vals = list(map(pe.kepler_basic_one, list(range(n)), parents, repeat(mass), repeat(pos),
+                    repeat(vel), repeat(0.75), repeat(0.7)))
+    f, ev, a, b, w, c = list(map(np.array, zip(*vals)))
+    out.update(kb_vel=vel, kb_focus=f, kb_ecc_v=ev, kb_semi_major=a, kb_semi_minor=b,
+               kb_periapsis_arg=w, kb_coi=c)
+    # collision predicate incl. exact-touch and one-ulp cases
+    m = 256
+    cm, cden, cpos, cvel = cloud(rng, m, 9.0e4, central_mass=50.0)
+    cpos += 7.0e4                                   # off-origin: no exact zeros
+    rad = rng.uniform(2.0, 9.0, m)
+    cases = []
+    for trial in range(24):
+        p = cpos.copy()
+        r = rad.copy()
+        for extra in range(trial if trial < 4 else 0):   # plain overlaps (several at once)
+            i, j = sorted(rng.choice(m, 2, replace=False))
+            p[j] = p[i] + 0.5 * (r[i] + r[j]) * np.array([0.6, 0.8])
+        if trial >= 4:   # engineer a near-threshold pair
+            i, j = sorted(rng.choice(m, 2, replace=False))
+            th = rng.uniform(0, 2 * np.pi)
+            dist = r[i] + r[j]
+            p[j] = p[i] + dist * np.array([np.cos(th), np.sin(th)])
+            if trial % 3 == 0:
+                p[j, 0] = np.nextafter(p[j, 0], np.inf)
+            if trial % 3 == 1:
+                p[j, 0] = np.nextafter(p[j, 0], -np.inf)
+        val = list(map(pe.check_collision_one, list(range(m - 1)), repeat(cm), repeat(p),
+                       repeat(r)))
+        b1, b2 = next((it for it in val if it is not None), (-1, -1))
+        cases.append((p, r, b1, b2))
+    out.update(cc_mass=cm, cc_pos=np.array([c[0] for c in cases]),
+               cc_rad=np.array([c[1] for c in cases]),
+               cc_del=np.array([c[2] for c in cases]), cc_add=np.array([c[3] for c in cases]))
+    # simplified_orbit_coi through the reference object
+    ph = rh.editor_from_arrays(ns, mass[:96], den[:96], pos[:96], vel[:96])
+    ph.pos, ph.vel = pos[:96].copy(), vel[:96].copy()
+    ph.simplified_orbit_coi()
+    out.update(soc_coi=ph.coi.copy(), soc_largest=int(ph.largest))
+    save("pair_kernels", **out)
+
+
+def gen_allpairs(ns):
+    """All-pairs model: njit driver that calls the reference's own jitted
+    gravity_one per pair + documented v+=a; P+=v."""
+    from numba import njit
+    g1 = ns.phys_editor.gravity_one
+
+    @njit
+    def accel(mass, pos, gc):
+        n = mass.shape[0]
+        acc = np.zeros((n, 2))
+        m2 = np.empty(2)
+        for i in range(n):
+            for j in range(n):
+                if j != i:
+                    # body index 1 => "not root"; mass looked up via a 2-vector
+                    m2[0] = mass[j]
+                    m2[1] = mass[i]
+                    a = g1(1, 0, m2, pos[j] - pos[i], gc)
+                    acc[i, 0] += a[0]
+                    acc[i, 1] += a[1]
+        return acc
+
+    rng = np.random.default_rng(20240613)
+    n = 256
+    mass, den, pos, vel = cloud(rng, n, 5.0e3, central_mass=1e4)
+    gc = 1.0
+    out = dict(mass=mass, pos0=pos, vel0=vel, gc=gc, acc0=accel(mass, pos, gc))
+    p, v = pos.copy(), vel.copy()
+    for s in range(1, 17):
+        v += accel(mass, p, gc)
+        p += v
+        if s in (1, 16):
+            out["pos%d" % s] = p.copy()
+            out["vel%d" % s] = v.copy()
+    save("allpairs_small", **out)
+
+
+def gen_kepler_solvers(ns):
+    rng = np.random.default_rng(20240614)
+    ske = ns.enhanced_kepler_solver.solve_kepler_ell
+    nrh = ns.phys_shared.newton_root_kepler_hyp
+    ecc = np.concatenate([rng.uniform(0, 0.999, 600), rng.uniform(0.9901, 0.99999, 100),
+                          [0.0, 0.1, 0.5, 0.9, 0.0167, 0.7, 0.995, 0.99, 0.9900001]])
+    ma = np.concatenate([rng.uniform(0, 2 * np.pi, 500), rng.uniform(-1, 9, 100),
+                         rng.uniform(0, 0.0045, 60), 2 * np.pi - rng.uniform(0, 0.0045, 40),
+                         [0.0, 1.0, 3.0, 0.1, 4.5, 6.0, 0.001, 0.004, np.pi]])
+    ell = np.array([ske(e, m, 1e-10) for e, m in zip(ecc, ma)])
+    ell_tol6 = np.array([ske(e, m, 1e-6) for e, m in zip(ecc, ma)])
+    hecc = np.concatenate([rng.uniform(1.0001, 4.0, 400), [1.5, 3.0, 1.01, 1.0]])
+    hma = np.concatenate([rng.uniform(-6, 6, 400), [2.0, -4.0, 0.5, 0.3]])
+    hguess = np.concatenate([hma[:200], rng.uniform(-3, 3, 200), [2.0, 0.0, 0.5, 0.3]])
+    hyp = np.array([nrh(e, m, g) for e, m, g in zip(hecc, hma, hguess)])
+    save("kepler_solvers", ecc=ecc, ma=ma, ell=ell, ell_tol6=ell_tol6, hecc=hecc, hma=hma,
+         hguess=hguess, hyp=hyp)
+
+
+def gen_game(ns, conf, bd, bod):
+    """Game mode: Solar System -> convert.to_kepler -> phys_body (C1,C5,C6,C8);
+    synthetic vessels through phys_vessel.Physics.move (C4)."""
+    import copy
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    from volatilespace.physics import convert
+    sys.path.remove(rh.REFERENCE_ROOT)
+    P = 32
+    korb = convert.to_kepler(bd["mass"], copy.deepcopy(bod), conf["gc"], conf["coi_coef"])
+    pb = ns.phys_body.Physics()
+    rh.set_curve_points(ns, pb, P)
+    pb.load(conf, copy.deepcopy(bd), copy.deepcopy(korb))
+    out = dict(P=P, gc=conf["gc"], coi_coef=conf["coi_coef"], mass=bd["mass"].copy(),
+               a=korb["a"].copy(), ecc=korb["ecc"].copy(), pea=korb["pe_arg"].copy(),
+               ma0=korb["ma"].copy(), ref=korb["ref"].copy(), dr=korb["dir"].copy())
+    body_data, body_orb, pos, ma, ea, cm = pb.initial(1)
+    for k in ("b", "f", "coi", "pe_d", "ap_d", "n", "per", "u"):
+        out["orb_" + k] = np.array(body_orb[k])
+    out.update(i_pos=pos.copy(), i_ma=ma.copy(), i_ea=ea.copy(), i_curves=pb.curves.copy(),
+               i_curves_mov=cm.copy())
+    for k in range(1, 1001):
+        pos, ma, ea = pb.move(3 if k % 2 else 1)
+        if k in (1, 1000):
+            out.update({"m%d_pos" % k: pos.copy(), "m%d_ma" % k: ma.copy(),
+                        "m%d_ea" % k: ea.copy(), "m%d_curves_mov" % k: pb.curve_move().copy()})
+    body_pos_final = pos.copy()
+
+    # synthetic vessels around the solar-system bodies (mixed elliptic/hyperbolic)
+    rng = np.random.default_rng(20240615)
+    nv = 200
+    pv = ns.phys_vessel.Physics()
+    rh.set_curve_points(ns, pv, P)
+    v_ref = rng.integers(0, len(bd["mass"]), nv)
+    hypm = rng.uniform(0, 1, nv) < 0.3
+    v_ecc = np.where(hypm, rng.uniform(1.02, 3.0, nv), rng.uniform(0.0, 0.97, nv))
+    v_ecc[:6] = [0.0, 0.995, 0.999, 1.0, 0.9905, 0.5]
+    hypm = v_ecc >= 1
+    v_a = rng.uniform(50, 4000, nv) * np.where(v_ecc > 1, -1, 1)
+    v_pea = rng.uniform(0, 2 * np.pi, nv)
+    v_ma = np.where(hypm, rng.uniform(-3, 3, nv), rng.uniform(0, 2 * np.pi, nv))
+    v_ma[1:3] = [0.001, 2 * np.pi - 0.002]     # ENRKE quirk region (F8b)
+    v_dr = rng.choice([-1.0, 1.0], nv)
+    vals = list(map(ns.phys_vessel.calc_orb_one, v_ref, repeat(bd["mass"]), repeat(conf["gc"]),
+                    v_a, v_ecc))
+    vb, vf, vpe, vap, vper, vn, vu = list(map(np.array, zip(*vals)))
+    pv.names = np.array(["v%d" % i for i in range(nv)])
+    pv.a, pv.ecc, pv.pea, pv.ma, pv.ref, pv.dr = v_a, v_ecc, v_pea, v_ma.copy(), v_ref, v_dr
+    pv.b, pv.f, pv.n, pv.u = vb, vf, vn, vu
+    pv.pos = np.zeros((nv, 2))
+    pv.ea = np.where(hypm, v_ma, 0.0)
+    pv.curves = np.zeros((nv, P, 2))
+    out.update(v_ref=v_ref, v_ecc=v_ecc, v_a=v_a, v_pea=v_pea, v_ma0=v_ma, v_dr=v_dr,
+               v_ea0=pv.ea.copy(), v_b=vb, v_f=vf, v_n=vn, v_u=vu, v_pe_d=vpe, v_ap_d=vap,
+               v_per=vper, v_body_pos=body_pos_final)
+    for k in range(1, 51):
+        vpos, vma = pv.move(2, body_pos_final, ma, ea)
+        if k in (1, 50):
+            out.update({"v%d_pos" % k: vpos.copy(), "v%d_ma" % k: vma.copy(),
+                        "v%d_ea" % k: pv.ea.copy()})
+    for v in range(nv):
+        pv.curve(v)
+    out.update(v_curves=pv.curves.copy(), v_curves_mov=pv.curve_move().copy())
+    save("game_mode", **out)
+
+
+def main():
+    ns = rh.load()
+    conf, bd, bod = gen_solar(ns)
+    gen_editor_clouds(ns)
+    gen_pair_kernels(ns)
+    gen_allpairs(ns)
+    gen_kepler_solvers(ns)
+    gen_game(ns, conf, bd, bod)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,415 @@
+"""Python face of the CPU parity oracle (TEST INFRASTRUCTURE ONLY).
+
+Loads oracle/libvs_oracle.so (built from vs_oracle.c by `make -C oracle`) and
+adds numpy-level restatements of the reference's O(N) host logic (merge
+bookkeeping, root swap) that sits between the O(N^2) loops.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; the product package
+volatilespace_b200 never does.
+
+Pinning status: pinned against outputs of the live reference (numba path)
+committed under tests/golden/ by oracle/gen_golden.py -- the reference has no
+golden vectors or tests of its own.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libvs_oracle.so")
+_lib = None
+
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "--no-print-directory"],
+                          stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        build()
+    L = C.CDLL(_LIB_PATH)
+    i64, f64 = C.c_int64, C.c_double
+    sigs = {
+        "vso_num_threads": (C.c_int, []),
+        "vso_set_num_threads": (None, [C.c_int]),
+        "vso_find_parents": (None, [i64, _i64p, _f64p, _f64p, _i64p]),
+        "vso_gravity_one": (None, [i64, i64, _f64p, f64, f64, f64, _f64p]),
+        "vso_gravity_ref": (None, [i64, _i64p, _f64p, _f64p, f64, _f64p, _f64p, _f64p, _i64p]),
+        "vso_allpairs_accel": (None, [i64, _f64p, _f64p, f64, i64, i64, _f64p]),
+        "vso_allpairs_step": (None, [i64, _f64p, _f64p, _f64p, f64, i64]),
+        "vso_kepler_basic": (None, [i64, _i64p, _f64p, _f64p, _f64p, f64, f64,
+                                    _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]),
+        "vso_simplified_orbit_coi": (i64, [i64, _i64p, _f64p, _f64p, _f64p, f64, f64, _f64p]),
+        "vso_check_collision": (None, [i64, _f64p, _f64p, _f64p,
+                                       C.POINTER(i64), C.POINTER(i64)]),
+        "vso_solve_kepler_ell": (f64, [f64, f64, f64]),
+        "vso_newton_root_kepler_hyp": (f64, [f64, f64, f64]),
+        "vso_newton_root_kepler_ell": (f64, [f64, f64, f64]),
+        "vso_solve_kepler_ell_batch": (None, [i64, _f64p, _f64p, f64, _f64p]),
+        "vso_newton_root_kepler_hyp_batch": (None, [i64, _f64p, _f64p, _f64p, _f64p]),
+        "vso_calc_orb_one": (None, [C.c_int, i64, i64, _f64p, f64, f64, f64, f64, f64, _f64p]),
+        "vso_body_move": (None, [i64, f64, _i64p, _i64p] + [_f64p] * 10),
+        "vso_vessel_move": (None, [i64, f64, _i64p, _f64p] + [_f64p] * 10),
+        "vso_curve_points": (None, [f64, f64, f64, f64, _f64p, i64, _f64p]),
+        "vso_curves_all": (None, [i64, _f64p, _f64p, _f64p, _f64p, _f64p, i64, _f64p]),
+        "vso_curve_move_to": (None, [i64, i64, _f64p, _f64p, _i64p, _f64p, _f64p, _f64p]),
+        "vso_editor_curve": (None, [i64, i64, _f64p, _f64p, _f64p, _f64p, _f64p, _i64p,
+                                    _f64p, _f64p, _f64p, _f64p]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def mass_order(mass):
+    """argsort(mass)[-1::-1] exactly as phys_editor.py:353,375 computes it."""
+    return _i(np.argsort(mass)[-1::-1])
+
+
+# ---------------------------------------------------------------- free functions
+def find_parents(mass, pos, coi, order=None):
+    n = len(mass)
+    order = mass_order(mass) if order is None else _i(order)
+    out = np.zeros(n, dtype=np.int64)
+    lib().vso_find_parents(n, order, _f(pos), _f(coi), out)
+    return out
+
+
+def gravity_one(body, parent, mass, rel_pos, gc):
+    out = np.zeros(2)
+    lib().vso_gravity_one(int(body), int(parent), _f(mass), float(rel_pos[0]),
+                          float(rel_pos[1]), float(gc), out)
+    return out
+
+
+def allpairs_accel(mass, pos, gc, row0=0, row1=None):
+    n = len(mass)
+    row1 = n if row1 is None else row1
+    acc = np.zeros((row1 - row0, 2))
+    lib().vso_allpairs_accel(n, _f(mass), _f(pos), float(gc), row0, row1, acc)
+    return acc
+
+
+def allpairs_step(mass, pos, vel, gc, nsteps=1):
+    """Returns new (pos, vel) after nsteps ticks of v += a; P += v."""
+    pos = _f(pos).copy()
+    vel = _f(vel).copy()
+    lib().vso_allpairs_step(len(mass), _f(mass), pos, vel, float(gc), int(nsteps))
+    return pos, vel
+
+
+def check_collision(mass, pos, rad):
+    d, a = C.c_int64(-1), C.c_int64(-1)
+    lib().vso_check_collision(len(mass), _f(mass), _f(pos), _f(rad), C.byref(d), C.byref(a))
+    if d.value < 0:
+        return None, None
+    return int(d.value), int(a.value)
+
+
+def kepler_basic(parents, mass, pos, vel, gc, coi_coef):
+    n = len(mass)
+    focus, sma, smi, pea, coi = (np.zeros(n) for _ in range(5))
+    ecc_v = np.zeros((n, 2))
+    lib().vso_kepler_basic(n, _i(parents), _f(mass), _f(pos), _f(vel), float(gc),
+                           float(coi_coef), focus, ecc_v, sma, smi, pea, coi)
+    return focus, ecc_v, sma, smi, pea, coi
+
+
+def simplified_orbit_coi(mass, pos, vel, gc, coi_coef, order=None):
+    n = len(mass)
+    order = mass_order(mass) if order is None else _i(order)
+    coi = np.zeros(n)
+    largest = lib().vso_simplified_orbit_coi(n, order, _f(mass), _f(pos), _f(vel),
+                                             float(gc), float(coi_coef), coi)
+    return int(largest), coi
+
+
+def solve_kepler_ell(ecc, ma, tol=1e-10):
+    if np.ndim(ecc) == 0 and np.ndim(ma) == 0:
+        return lib().vso_solve_kepler_ell(float(ecc), float(ma), float(tol))
+    ecc, ma = np.broadcast_arrays(_f(ecc), _f(ma))
+    ecc, ma = _f(ecc), _f(ma)
+    out = np.zeros(ecc.shape)
+    lib().vso_solve_kepler_ell_batch(ecc.size, ecc.ravel(), ma.ravel(), float(tol), out.ravel())
+    return out
+
+
+def newton_root_kepler_hyp(ecc, ma, guess):
+    if np.ndim(ecc) == 0 and np.ndim(ma) == 0:
+        return lib().vso_newton_root_kepler_hyp(float(ecc), float(ma), float(guess))
+    ecc, ma, guess = (_f(x) for x in np.broadcast_arrays(_f(ecc), _f(ma), _f(guess)))
+    out = np.zeros(ecc.shape)
+    lib().vso_newton_root_kepler_hyp_batch(ecc.size, ecc.ravel(), ma.ravel(), guess.ravel(),
+                                           out.ravel())
+    return out
+
+
+def calc_orb(kind, ref, mass_ref_table, body_mass, gc, coi_coef, a, ecc):
+    """Vectorised C8.  kind='body' (phys_body.py:27-60) or 'vessel'
+    (phys_vessel.py:82-110).  Returns dict of arrays b,f,coi,pe_d,ap_d,period,n,u."""
+    n = len(a)
+    out = np.zeros((n, 8))
+    tmp = np.zeros(8)
+    mt = _f(mass_ref_table)
+    with_coi = 1 if kind == "body" else 0
+    for i in range(n):
+        bm = float(body_mass[i]) if with_coi else 0.0
+        lib().vso_calc_orb_one(with_coi, i, int(ref[i]), mt, bm, float(gc), float(coi_coef),
+                               float(a[i]), float(ecc[i]), tmp)
+        out[i] = tmp
+    keys = ["b", "f", "coi", "pe_d", "ap_d", "period", "n", "u"]
+    return {k: np.ascontiguousarray(out[:, j]) for j, k in enumerate(keys)}
+
+
+def body_move(warp, ref, coi, a, b, f, ecc, pea, n, dr, ma, ea, pos):
+    """C1; returns new (pos, ma, ea)."""
+    order = _i(np.argsort(coi)[-1::-1])
+    ma, ea, pos = _f(ma).copy(), _f(ea).copy(), _f(pos).copy()
+    lib().vso_body_move(len(a), float(warp), order, _i(ref), _f(a), _f(b), _f(f), _f(ecc),
+                        _f(pea), _f(n), _f(dr), ma, ea, pos)
+    return pos, ma, ea
+
+
+def vessel_move(warp, ref, body_pos, a, b, f, ecc, pea, n, dr, ma, ea):
+    """C4; returns new (pos, ma, ea)."""
+    ma, ea = _f(ma).copy(), _f(ea).copy()
+    pos = np.zeros((len(a), 2))
+    lib().vso_vessel_move(len(a), float(warp), _i(ref), _f(body_pos), _f(a), _f(b), _f(f),
+                          _f(ecc), _f(pea), _f(n), _f(dr), ma, ea, pos)
+    return pos, ma, ea
+
+
+def curve_points(ecc, a, b, pea, t):
+    t = _f(t)
+    out = np.zeros((len(t), 2))
+    lib().vso_curve_points(float(ecc), float(a), float(b), float(pea), t, len(t), out)
+    return out
+
+
+def curves_all(ecc, a, b, pea, t):
+    t = _f(t)
+    out = np.zeros((len(a), len(t), 2))
+    lib().vso_curves_all(len(a), _f(ecc), _f(a), _f(b), _f(pea), t, len(t), out)
+    return out
+
+
+def curve_move_to(curves, body_pos, ref, f, pea):
+    curves = _f(curves)
+    out = np.zeros_like(curves)
+    lib().vso_curve_move_to(curves.shape[0], curves.shape[1], curves, _f(body_pos), _i(ref),
+                            _f(f), _f(pea), out)
+    return out
+
+
+def editor_curve(ecc_v, semi_major, semi_minor, focus, periapsis_arg, parents, pos, P):
+    n = len(semi_major)
+    ell_t = np.linspace(-np.pi, np.pi, P)
+    par_t = np.linspace(-np.pi - 1, np.pi + 1, P)
+    out = np.zeros((2, n, P))
+    lib().vso_editor_curve(n, P, _f(ecc_v), _f(semi_major), _f(semi_minor), _f(focus),
+                           _f(periapsis_arg), _i(parents), _f(pos), ell_t, par_t, out)
+    return out
+
+
+def body_radius(mass, den, rad_mult):
+    """A5 radius only, phys_editor.py:580-581 (host numpy on both sides)."""
+    volume = mass / den
+    return rad_mult * np.cbrt(3 * volume / (4 * np.pi))
+
+
+# ---------------------------------------------------------------- editor state
+class EditorOracle:
+    """Restatement of phys_editor.Physics restricted to the arrays the hot path
+    reads or writes (phys_editor.py:112-149): mass, den, rad, pos, vel, rel_vel,
+    coi, parents, largest and the kepler_basic outputs."""
+
+    def __init__(self, mass, den, pos, vel, gc=1.0, rad_mult=179.0, coi_coef=0.7):
+        self.gc, self.rad_mult, self.coi_coef = float(gc), float(rad_mult), float(coi_coef)
+        # load_system, phys_editor.py:169-201
+        self.mass = _f(mass).copy()
+        self.den = _f(den).copy()
+        self.rad = body_radius(self.mass, self.den, self.rad_mult)
+        self.pos = _f(pos).copy()
+        self.vel = _f(vel).copy()
+        self.parents = np.array([], dtype=np.int64)
+        self.simplified_orbit_coi()
+        self.find_parents()
+        self.rel_vel = self.vel - self.vel[self.parents]
+        n = len(self.mass)
+        self.focus = np.zeros(n)
+        self.semi_major = np.zeros(n)
+        self.semi_minor = np.zeros(n)
+        self.periapsis_arg = np.zeros(n)
+        self.ecc_v = np.zeros((n, 2))
+        self.body()
+
+    # phys_editor.py:325-346
+    def simplified_orbit_coi(self):
+        self.largest, self.coi = simplified_orbit_coi(self.mass, self.pos, self.vel, self.gc,
+                                                      self.coi_coef)
+
+    # phys_editor.py:350-354
+    def find_parents(self):
+        self.parents = find_parents(self.mass, self.pos, self.coi)
+
+    # phys_editor.py:357-378
+    def gravity(self):
+        n = len(self.mass)
+        order = mass_order(self.mass)
+        parents = self.parents.copy() if len(self.parents) == n else np.zeros(n, np.int64)
+        lib().vso_gravity_ref(n, order, self.mass, self.coi, self.gc, self.pos, self.vel,
+                              self.rel_vel, parents)
+        self.parents = parents
+
+    # phys_editor.py:577-581 (radius part)
+    def body(self):
+        self.rad = body_radius(self.mass, self.den, self.rad_mult)
+
+    # phys_editor.py:547-551
+    def check_collision(self):
+        return check_collision(self.mass, self.pos, self.rad)
+
+    # phys_editor.py:381-384
+    def kepler_basic(self):
+        (self.focus, self.ecc_v, self.semi_major, self.semi_minor, self.periapsis_arg,
+         self.coi) = kepler_basic(self.parents, self.mass, self.pos, self.vel, self.gc,
+                                  self.coi_coef)
+
+    # phys_editor.py:519-544
+    def curve(self, P):
+        return editor_curve(self.ecc_v, self.semi_major, self.semi_minor, self.focus,
+                            self.periapsis_arg, self.parents, self.pos, P)
+
+    # phys_editor.py:554-565
+    def inelastic_collision(self):
+        body_del, body_add = self.check_collision()
+        if body_del is not None:
+            mass_r = self.mass[body_del] + self.mass[body_add]
+            mom1 = self.vel[body_add] * self.mass[body_add]
+            mom2 = self.vel[body_del] * self.mass[body_del]
+            velr = (mom1 + mom2) / mass_r
+            self.rel_vel[body_add] = velr - self.rel_vel[self.parents[body_add]]
+            self.set_body_mass(body_add, mass_r)
+            self.del_body(body_del)
+        return body_del
+
+    # phys_editor.py:844-857
+    def set_body_mass(self, body, mass):
+        self.mass[body] = mass
+        old_largest = int(self.largest)
+        self.find_parents()
+        self.simplified_orbit_coi()
+        if self.largest != old_largest:
+            diff = self.pos[self.largest].copy()
+            self.pos -= diff
+            self.rel_vel[old_largest] = self.rel_vel[self.largest] * -1
+            self.vel[self.largest] = [0, 0]
+            if self.largest != 0:
+                self.set_root(self.largest)
+
+    # phys_editor.py:293-313 (arrays on the hot path only; coi and the orbit
+    # arrays are NOT swapped there either)
+    def set_root(self, body):
+        for arr in (self.mass, self.den, self.rad, self.parents):
+            arr[0], arr[body] = arr[body], arr[0]
+        for arr in (self.pos, self.vel, self.rel_vel):
+            arr[[0, body]] = arr[[body, 0]]
+        self.simplified_orbit_coi()
+        self.find_parents()
+        self.largest = 0
+
+    # phys_editor.py:250-290
+    def del_body(self, delete):
+        if len(self.mass) > 1:
+            for name in ("mass", "den", "rad", "parents"):
+                setattr(self, name, np.delete(getattr(self, name), delete))
+            for name in ("pos", "vel", "rel_vel"):
+                setattr(self, name, np.delete(getattr(self, name), delete, axis=0))
+            self.simplified_orbit_coi()
+            self.find_parents()
+            for name in ("focus", "semi_major", "semi_minor", "periapsis_arg"):
+                setattr(self, name, np.delete(getattr(self, name), delete))
+            self.ecc_v = np.delete(self.ecc_v, delete, axis=0)
+            if self.largest == delete:
+                self.find_parents()
+                self.simplified_orbit_coi()
+                diff = self.pos[self.largest].copy()
+                self.pos -= diff
+                self.vel[self.largest] = [0, 0]
+                if self.largest != 0:
+                    self.set_root(self.largest)
+            return 0
+        return 1
+
+    # editor.py:1503-1523
+    def frame(self, warp=1):
+        deleted = []
+        for _ in range(warp):
+            self.gravity()
+            self.body()
+            d = self.inelastic_collision()
+            if d is not None:
+                deleted.append(int(d))
+        self.kepler_basic()
+        return deleted
+
+
+class AllPairsOracle:
+    """MODE_ALLPAIRS: documented complex model (01-complex-orbit-model.txt:4-12)
+    + B1 detection + the documented merge (09-collisions.txt:3-6): survivor gets
+    summed mass and momentum-weighted velocity, keeps its own position and
+    density; the deleted row is removed np.delete-style (order preserved);
+    rad is refreshed by body() at the start of the next tick's collision phase
+    exactly like the editor order gravity(); body(); inelastic_collision()."""
+
+    def __init__(self, mass, den, pos, vel, gc=1.0, rad_mult=179.0):
+        self.gc, self.rad_mult = float(gc), float(rad_mult)
+        self.mass, self.den = _f(mass).copy(), _f(den).copy()
+        self.pos, self.vel = _f(pos).copy(), _f(vel).copy()
+        self.rad = body_radius(self.mass, self.den, self.rad_mult)
+
+    def gravity(self):
+        self.pos, self.vel = allpairs_step(self.mass, self.pos, self.vel, self.gc, 1)
+
+    def body(self):
+        self.rad = body_radius(self.mass, self.den, self.rad_mult)
+
+    def inelastic_collision(self):
+        d, a = check_collision(self.mass, self.pos, self.rad)
+        if d is None:
+            return None, None
+        mass_r = self.mass[d] + self.mass[a]
+        velr = (self.vel[a] * self.mass[a] + self.vel[d] * self.mass[d]) / mass_r
+        self.vel[a] = velr
+        self.mass[a] = mass_r
+        for name in ("mass", "den", "rad"):
+            setattr(self, name, np.delete(getattr(self, name), d))
+        for name in ("pos", "vel"):
+            setattr(self, name, np.delete(getattr(self, name), d, axis=0))
+        return d, a
+
+    def tick(self):
+        self.gravity()
+        self.body()
+        return self.inelastic_collision()

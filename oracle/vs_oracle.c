@@ -1,0 +1,554 @@
+/*
+ * vs_oracle.c -- CPU restatement of VolatileSpace's physics hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle for the CUDA path
+ * in volatilespace_b200/csrc.  It may be imported / linked / executed only by
+ * tests/, by __graft_entry__.smoke() and by bench.py's cpu_baseline /
+ * --impl reference legs, and there only as the checker or as the timed CPU
+ * baseline -- never by the product path (volatilespace_b200/ has no CPU
+ * fallback and fails loudly without its CUDA library).
+ *
+ * Every function cites the reference lines (relative to the reference repo,
+ * mzivic7/VolatileSpace v0.5.2) whose arithmetic it restates.  The reference
+ * runs these as numba @njit (fastmath=False: no FMA contraction, libm
+ * transcendentals) or as plain numpy; this file is compiled with
+ * -ffp-contract=off so every a*b+c is two IEEE roundings exactly as there.
+ *
+ * Pinning: the reference ships no tests or golden vectors.
+ * The oracle is pinned against outputs of the reference itself, generated in
+ * the dev container by oracle/gen_golden.py (imports /root/reference live)
+ * and committed under tests/golden/; tests/test_oracle_golden.py checks every
+ * function below against them.
+ *
+ * Build: make -C oracle   (gcc -O2 -ffp-contract=off -fopenmp -shared)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define VSO_PI 3.141592653589793 /* math.pi == np.pi */
+
+int vso_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void vso_set_num_threads(int t)
+{
+#ifdef _OPENMP
+    if (t > 0) omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}
+
+/* Python float % for a positive divisor (numba lowers `%` on floats this way). */
+static double py_mod(double a, double b)
+{
+    double r = fmod(a, b);
+    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+    return r;
+}
+
+/* ------------------------------------------------------------------ */
+/* Part A -- body-sim step                                            */
+/* ------------------------------------------------------------------ */
+
+/* A1: find_parent_one, phys_editor.py:36-48, driven by find_parents :350-354.
+ * order = argsort(mass)[::-1] is computed by the caller with numpy (mass-tie
+ * order is whatever numpy's introsort gives). */
+void vso_find_parents(int64_t n, const int64_t *order, const double *pos,
+                      const double *coi, int64_t *parents)
+{
+    int64_t *rank = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    for (int64_t k = 0; k < n; ++k) rank[order[k]] = k;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t parent = 0;
+        if (i != 0) {
+            for (int64_t l = 0; l < rank[i]; ++l) {
+                int64_t p = order[l];
+                double rx = pos[2 * i] - pos[2 * p];
+                double ry = pos[2 * i + 1] - pos[2 * p + 1];
+                if (rx * rx + ry * ry < coi[p] * coi[p]) parent = p;
+            }
+        }
+        parents[i] = parent;
+    }
+    free(rank);
+}
+
+/* A2: gravity_one, phys_editor.py:51-60.  rel_pos = pos[parent] - pos[body]. */
+void vso_gravity_one(int64_t body, int64_t parent, const double *mass, double rx,
+                     double ry, double gc, double *out)
+{
+    if (body) {
+        double distance = sqrt(rx * rx + ry * ry);
+        double force = gc * mass[body] * mass[parent] / (distance * distance);
+        double angle = atan2(ry, rx);
+        double acc = force / mass[body];
+        out[0] = acc * cos(angle);
+        out[1] = acc * sin(angle);
+    } else {
+        out[0] = 0.0;
+        out[1] = 0.0;
+    }
+}
+
+/* A3: Physics.gravity, phys_editor.py:357-378 (one tick of the parent/COI
+ * "simplified n-body" model, in place).  parents holds last tick's parents on
+ * entry and this tick's on exit. */
+void vso_gravity_ref(int64_t n, const int64_t *order, const double *mass,
+                     const double *coi, double gc, double *pos, double *vel,
+                     double *rel_vel, int64_t *parents)
+{
+    int64_t *parents_old = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    memcpy(parents_old, parents, sizeof(int64_t) * (size_t)n);
+    vso_find_parents(n, order, pos, coi, parents);
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t p = parents[i];
+        double a[2];
+        vso_gravity_one(i, p, mass, pos[2 * p] - pos[2 * i],
+                        pos[2 * p + 1] - pos[2 * i + 1], gc, a);
+        rel_vel[2 * i] += a[0];
+        rel_vel[2 * i + 1] += a[1];
+    }
+    /* leaving / entering a COI, sequential in index order (:366-373) */
+    for (int64_t b = 0; b < n; ++b) {
+        if (parents[b] != parents_old[b] && b != 0) {
+            int64_t parent = parents[b], old = parents_old[b];
+            if (mass[parent] > mass[old]) {
+                rel_vel[2 * b] += rel_vel[2 * old];
+                rel_vel[2 * b + 1] += rel_vel[2 * old + 1];
+            }
+            if (mass[parent] < mass[old]) {
+                rel_vel[2 * b] -= rel_vel[2 * parent];
+                rel_vel[2 * b + 1] -= rel_vel[2 * parent + 1];
+            }
+        }
+    }
+    for (int64_t k = 1; k < n; ++k) { /* descending mass, root skipped (:375-377) */
+        int64_t b = order[k], p = parents[b];
+        vel[2 * b] = rel_vel[2 * b] + vel[2 * p];
+        vel[2 * b + 1] = rel_vel[2 * b + 1] + vel[2 * p + 1];
+    }
+    for (int64_t i = 0; i < 2 * n; ++i) pos[i] += vel[i];
+    free(parents_old);
+}
+
+/* A4: the documented all-pairs model, documentation/orbital-physics/
+ * 01-complex-orbit-model.txt:4-12, evaluated with the reference's own pair
+ * formula gravity_one (phys_editor.py:51-60; its result depends only on
+ * mass[parent], rel_pos and gc when body != 0).  acc rows [row0,row1) only;
+ * source order j ascending, j != i. */
+void vso_allpairs_accel(int64_t n, const double *mass, const double *pos, double gc,
+                        int64_t row0, int64_t row1, double *acc)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = row0; i < row1; ++i) {
+        double ax = 0.0, ay = 0.0;
+        double xi = pos[2 * i], yi = pos[2 * i + 1], mi = mass[i];
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i) continue;
+            double rx = pos[2 * j] - xi, ry = pos[2 * j + 1] - yi;
+            double distance = sqrt(rx * rx + ry * ry);
+            double force = gc * mi * mass[j] / (distance * distance);
+            double angle = atan2(ry, rx);
+            double a = force / mi;
+            ax += a * cos(angle);
+            ay += a * sin(angle);
+        }
+        acc[2 * (i - row0)] = ax;
+        acc[2 * (i - row0) + 1] = ay;
+    }
+}
+
+/* A4 integrator: v = v + av ; P = P + v  (01-complex-orbit-model.txt:11-12). */
+void vso_allpairs_step(int64_t n, const double *mass, double *pos, double *vel,
+                       double gc, int64_t nsteps)
+{
+    double *acc = (double *)malloc(sizeof(double) * 2 * (size_t)(n > 0 ? n : 1));
+    for (int64_t s = 0; s < nsteps; ++s) {
+        vso_allpairs_accel(n, mass, pos, gc, 0, n, acc);
+        for (int64_t i = 0; i < 2 * n; ++i) {
+            vel[i] += acc[i];
+            pos[i] += vel[i];
+        }
+    }
+    free(acc);
+}
+
+/* A6: kepler_basic_one, phys_editor.py:63-83, over all bodies (:381-384). */
+void vso_kepler_basic(int64_t n, const int64_t *parents, const double *mass,
+                      const double *pos, const double *vel, double gc, double coi_coef,
+                      double *focus, double *ecc_v, double *semi_major,
+                      double *semi_minor, double *periapsis_arg, double *coi)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < n; ++b) {
+        if (!b) {
+            focus[0] = 0.0; ecc_v[0] = 0.0; ecc_v[1] = 0.0; semi_major[0] = 0.0;
+            semi_minor[0] = 0.0; periapsis_arg[0] = 0.0; coi[0] = 0.0;
+            continue;
+        }
+        int64_t p = parents[b];
+        double rpx = pos[2 * b] - pos[2 * p], rpy = pos[2 * b + 1] - pos[2 * p + 1];
+        double rvx = vel[2 * b] - vel[2 * p], rvy = vel[2 * b + 1] - vel[2 * p + 1];
+        double u = gc * mass[p];
+        double magp = sqrt(rpx * rpx + rpy * rpy);
+        double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / magp));
+        double momentum = rpx * rvy - rpy * rvx;
+        double sx = rvy, sy = -rvx; /* swap axes and -y (:73) */
+        double ex = (sx * momentum / u) - rpx / magp;
+        double ey = (sy * momentum / u) - rpy / magp;
+        double ecc = sqrt(ex * ex + ey * ey);
+        double pea = py_mod((3 * VSO_PI / 2) + atan2(-ex, ey), 2 * VSO_PI);
+        double f = a * ecc;
+        double bm = sqrt(fabs(f * f - a * a));
+        double c = 0.0;
+        if (a > 0) c = a * pow(mass[b] / mass[p], coi_coef);
+        focus[b] = f; ecc_v[2 * b] = ex; ecc_v[2 * b + 1] = ey; semi_major[b] = a;
+        semi_minor[b] = bm; periapsis_arg[b] = pea; coi[b] = c;
+    }
+}
+
+/* A7: simplified_orbit_coi, phys_editor.py:325-346.  order as for A1; returns
+ * largest = argmax(mass) (first maximum). */
+int64_t vso_simplified_orbit_coi(int64_t n, const int64_t *order, const double *mass,
+                                 const double *pos, const double *vel, double gc,
+                                 double coi_coef, double *coi)
+{
+    int64_t largest = 0;
+    for (int64_t i = 1; i < n; ++i)
+        if (mass[i] > mass[largest]) largest = i;
+    for (int64_t i = 0; i < n; ++i) coi[i] = 0.0;
+    for (int64_t num = 0; num + 1 < n; ++num) {
+        int64_t body = order[num + 1];
+        double body_mass = mass[body];
+        int64_t parent = largest;
+        for (int64_t l = 0; l <= num; ++l) {
+            int64_t pot = order[l];
+            double dx = pos[2 * body] - pos[2 * pot], dy = pos[2 * body + 1] - pos[2 * pot + 1];
+            if (dx * dx + dy * dy < coi[pot] * coi[pot]) parent = pot;
+        }
+        double rpx = pos[2 * parent] - pos[2 * body], rpy = pos[2 * parent + 1] - pos[2 * body + 1];
+        double rvx = vel[2 * parent] - vel[2 * body], rvy = vel[2 * parent + 1] - vel[2 * body + 1];
+        double u = gc * mass[parent];
+        double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / sqrt(rpx * rpx + rpy * rpy)));
+        if (a > 0)
+            coi[body] = a * pow(body_mass / mass[parent], coi_coef);
+        else
+            coi[body] = 0.0;
+    }
+    return largest;
+}
+
+/* ------------------------------------------------------------------ */
+/* Part B -- collisions                                               */
+/* ------------------------------------------------------------------ */
+
+/* B1: check_collision_one (phys_editor.py:86-97) for every i, first non-None
+ * result (:547-551) == lexicographically smallest colliding (i<j).  Writes
+ * (body_del, body_add), or (-1,-1) for (None, None). */
+void vso_check_collision(int64_t n, const double *mass, const double *pos,
+                         const double *rad, int64_t *del, int64_t *add)
+{
+    int64_t best_i = -1, best_j = -1;
+#pragma omp parallel
+    {
+        int64_t li = -1, lj = -1;
+#pragma omp for schedule(dynamic, 64) nowait
+        for (int64_t i = 0; i < n - 1; ++i) {
+            if (li >= 0 && li < i) continue; /* a smaller i already hit */
+            for (int64_t j = i + 1; j < n; ++j) {
+                double rx = pos[2 * i] - pos[2 * j], ry = pos[2 * i + 1] - pos[2 * j + 1];
+                double distance = sqrt(rx * rx + ry * ry);
+                if (distance <= rad[i] + rad[j]) {
+                    if (li < 0 || i < li) { li = i; lj = j; }
+                    break;
+                }
+            }
+        }
+#pragma omp critical
+        {
+            if (li >= 0 && (best_i < 0 || li < best_i)) { best_i = li; best_j = lj; }
+        }
+    }
+    if (best_i < 0) { *del = -1; *add = -1; return; }
+    if (mass[best_i] <= mass[best_j]) { *del = best_i; *add = best_j; }
+    else { *del = best_j; *add = best_i; }
+}
+
+/* Number of predicate tests the reference algorithm performs for a tick with
+ * no hit (N(N-1)/2); helper for the CPU-baseline bookkeeping. */
+int64_t vso_collision_tests(int64_t n) { return n * (n - 1) / 2; }
+
+/* ------------------------------------------------------------------ */
+/* Part C -- Keplerian propagation and orbit curves                   */
+/* ------------------------------------------------------------------ */
+
+/* C2: solve_kepler_ell, enhanced_kepler_solver.py:18-69 (ENRKE). */
+double vso_solve_kepler_ell(double ecc, double ma, double tol)
+{
+    double mr = ma, flip;
+    if (mr > VSO_PI) { mr = 2 * VSO_PI - mr; flip = 1; }
+    else flip = -1;
+
+    if (ecc > 0.99 && mr < 0.0045) {
+        double al = tol / 1e7, be = tol / 0.3, fp = 2.7 * mr, fpp = 0.301, f = 0.154;
+        for (int i = 0; i < 1000; ++i) { /* midpoint update is outside the loop (F8b) */
+            if ((fpp - fp) <= (al + be * f)) break;
+            if ((f - ecc * sin(f) - mr) > 0) fpp = f;
+            else fp = f;
+        }
+        f = 0.5 * (fp + fpp);
+        return ma + flip * (mr - f);
+    }
+
+    double tol2s = 2 * tol / (ecc + 2.2e-16);
+    double eapp = mr + 0.999999 * mr * (VSO_PI - mr) /
+                           (2. * mr + ecc - VSO_PI + 2.4674011002723395 / (ecc + 2.2e-16));
+    double fpp = ecc * sin(eapp);
+    double fppp = ecc * cos(eapp);
+    double fp = 1 - fppp;
+    double f = eapp - fpp - mr;
+    double delta = -f / fp;
+    double fp3 = fp * fp * fp;
+    double ffpfpp = f * fp * fpp;
+    double f2fppp = f * f * fppp;
+    delta = delta * (fp3 - 0.5 * ffpfpp + f2fppp / 3) / (fp3 - ffpfpp + 0.5 * f2fppp);
+    for (int i = 0; i < 30; ++i) {
+        if (delta * delta < fp * tol2s) break;
+        eapp = eapp + delta;
+        fp = 1 - ecc * cos(eapp);
+        delta = (mr - eapp + ecc * sin(eapp)) / fp;
+    }
+    eapp = eapp + delta;
+    return ma + flip * (mr - eapp);
+}
+
+/* C3: newton_root_kepler_hyp, phys_shared.py:114-122 (negated convention). */
+double vso_newton_root_kepler_hyp(double ecc, double ma, double ea_guess)
+{
+    double ea = ea_guess;
+    for (int i = 0; i < 50; ++i) {
+        double delta_x = (ea - ecc * sinh(ea) - ma) / (1.0 - ecc * cosh(ea));
+        ea -= delta_x;
+        if (fabs(delta_x) < 1e-10) return ea;
+    }
+    return ea;
+}
+
+/* newton_root_kepler_ell, phys_shared.py:103-111 (plain twin, off the hot path). */
+double vso_newton_root_kepler_ell(double ecc, double ma, double ea_guess)
+{
+    double ea = ea_guess;
+    for (int i = 0; i < 50; ++i) {
+        double delta_x = (ea - ecc * sin(ea) - ma) / (1.0 - ecc * cos(ea));
+        ea -= delta_x;
+        if (fabs(delta_x) < 1e-10) return ea;
+    }
+    return ea;
+}
+
+void vso_solve_kepler_ell_batch(int64_t n, const double *ecc, const double *ma, double tol,
+                                double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) out[i] = vso_solve_kepler_ell(ecc[i], ma[i], tol);
+}
+
+void vso_newton_root_kepler_hyp_batch(int64_t n, const double *ecc, const double *ma,
+                                      const double *guess, double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = vso_newton_root_kepler_hyp(ecc[i], ma[i], guess[i]);
+}
+
+/* C8: calc_orb_one, phys_body.py:27-60 (with_coi=1: bodies, root -> zeros) and
+ * phys_vessel.py:82-110 (with_coi=0: vessels, no root special case).
+ * out8 = b, f, coi, pe_d, ap_d, period, n, u. */
+void vso_calc_orb_one(int with_coi, int64_t body, int64_t ref, const double *mass,
+                      double body_mass, double gc, double coi_coef, double a, double ecc,
+                      double *out8)
+{
+    if (with_coi && !body) {
+        for (int k = 0; k < 8; ++k) out8[k] = 0.0;
+        return;
+    }
+    double u = gc * mass[ref];
+    double f = a * ecc;
+    double b = sqrt(fabs(f * f - a * a));
+    double coi = 0.0, pe_d, ap_d, period, n;
+    if (with_coi && a > 0) coi = a * pow(body_mass / mass[ref], coi_coef);
+    if (ecc != 0) {
+        pe_d = a * (1 - ecc);
+        if (ecc < 1) {
+            period = 2 * VSO_PI * sqrt(a * a * a / u);
+            ap_d = a * (1 + ecc);
+            n = 2 * VSO_PI / period;
+        } else {
+            if (ecc > 1) pe_d = a * (1 - ecc);
+            else pe_d = a;
+            period = 0;
+            ap_d = 0;
+            double aa = fabs(a);
+            n = sqrt(u / (aa * aa * aa));
+        }
+    } else {
+        period = (2 * VSO_PI * sqrt(a * a * a / u)) / 10;
+        pe_d = a * (1 - ecc);
+        ap_d = 0;
+        n = 2 * VSO_PI / period;
+    }
+    out8[0] = b; out8[1] = f; out8[2] = coi; out8[3] = pe_d; out8[4] = ap_d;
+    out8[5] = period; out8[6] = n; out8[7] = u;
+}
+
+/* C1: phys_body.Physics.move, phys_body.py:323-346.  order = argsort(coi)[::-1]
+ * from the caller (numpy).  In place on ma, ea, pos. */
+void vso_body_move(int64_t n, double warp, const int64_t *order, const int64_t *ref,
+                   const double *a, const double *b, const double *f, const double *ecc,
+                   const double *pea, const double *nmot, const double *dr, double *ma,
+                   double *ea, double *pos)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        double m = ma[i] + dr[i] * nmot[i] * warp;
+        if (m > 2 * VSO_PI) m = m - 2 * VSO_PI;
+        if (m < 0) m = m + 2 * VSO_PI;
+        ma[i] = m;
+    }
+    for (int64_t k = 0; k < n; ++k) {
+        int64_t body = order[k];
+        double e, prx, pry;
+        if (ecc[body] < 1) {
+            e = vso_solve_kepler_ell(ecc[body], ma[body], 1e-10);
+            prx = a[body] * cos(e) - f[body];
+            pry = b[body] * sin(e);
+        } else {
+            e = vso_newton_root_kepler_hyp(ecc[body], ma[body], ea[body]);
+            prx = a[body] * cosh(e) - f[body];
+            pry = b[body] * sinh(e);
+        }
+        double ang = pea[body] - VSO_PI;
+        double x = prx * cos(ang) - pry * sin(ang);
+        double y = prx * sin(ang) + pry * cos(ang);
+        int64_t r = ref[body];
+        double rx = pos[2 * r], ry = pos[2 * r + 1];
+        pos[2 * body] = rx + x;
+        pos[2 * body + 1] = ry + y;
+        ea[body] = e;
+    }
+}
+
+/* C4: phys_vessel.Physics.move (phys_vessel.py:477-494) with ea2coord (:247-255)
+ * and orb2xy (phys_shared.py:187-199).  In place on ma, ea; writes pos. */
+void vso_vessel_move(int64_t n, double warp, const int64_t *ref, const double *body_pos,
+                     const double *a, const double *b, const double *f, const double *ecc,
+                     const double *pea, const double *nmot, const double *dr, double *ma,
+                     double *ea, double *pos)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double hyp = ecc[i] > 1 ? -1.0 : 1.0;
+        double m = ma[i] + dr[i] * nmot[i] * warp * hyp;
+        if (ecc[i] < 1 && m > 2 * VSO_PI) m = m - 2 * VSO_PI;
+        if (ecc[i] < 1 && m < 0) m = m + 2 * VSO_PI;
+        ma[i] = m;
+        double e;
+        if (ecc[i] < 1) e = vso_solve_kepler_ell(ecc[i], m, 1e-10);
+        else e = vso_newton_root_kepler_hyp(ecc[i], m, ea[i]);
+        double x = 0.0, y = 0.0;
+        if (e != 0.0) {
+            double xn, yn;
+            if (ecc[i] < 1) { xn = a[i] * cos(e) - f[i]; yn = b[i] * sin(e); }
+            else { xn = a[i] * cosh(e) - f[i]; yn = b[i] * sinh(e); }
+            double ang = pea[i] - VSO_PI;
+            int64_t r = ref[i];
+            x = (xn * cos(ang) - yn * sin(ang)) + body_pos[2 * r];
+            y = (xn * sin(ang) + yn * cos(ang)) + body_pos[2 * r + 1];
+        }
+        pos[2 * i] = x;
+        pos[2 * i + 1] = y;
+        ea[i] = e;
+    }
+}
+
+/* C5: curve_points, phys_shared.py:202-216.  out is (P,2). */
+void vso_curve_points(double ecc, double a, double b, double pea, const double *t,
+                      int64_t P, double *out)
+{
+    double sin_p = sin(pea), cos_p = cos(pea);
+    for (int64_t k = 0; k < P; ++k) {
+        double x, y;
+        if (ecc < 1) { x = a * cos(t[k]); y = b * sin(t[k]); }
+        else { x = -a * cosh(t[k]); y = b * sinh(t[k]); }
+        out[2 * k] = x * cos_p - y * sin_p;
+        out[2 * k + 1] = y * cos_p + x * sin_p;
+    }
+}
+
+/* C5 over all objects: Physics.curve(i) for every i (phys_body.py:315-320,
+ * phys_vessel.py:364-369).  curves is (N,P,2). */
+void vso_curves_all(int64_t n, const double *ecc, const double *a, const double *b,
+                    const double *pea, const double *t, int64_t P, double *curves)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i)
+        vso_curve_points(ecc[i], a[i], b[i], pea[i], t, P, curves + 2 * P * i);
+}
+
+/* C6: curve_move_to, phys_shared.py:219-222.  (N,P,2) -> (N,P,2). */
+void vso_curve_move_to(int64_t n, int64_t P, const double *curves, const double *body_pos,
+                       const int64_t *ref, const double *f, const double *pea, double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double fx = f[i] * cos(pea[i]), fy = f[i] * sin(pea[i]);
+        double bx = body_pos[2 * ref[i]], by = body_pos[2 * ref[i] + 1];
+        const double *c = curves + 2 * P * i;
+        double *o = out + 2 * P * i;
+        for (int64_t k = 0; k < P; ++k) {
+            o[2 * k] = c[2 * k] + fx + bx;
+            o[2 * k + 1] = c[2 * k + 1] + fy + by;
+        }
+    }
+}
+
+/* C7: editor Physics.curve, phys_editor.py:519-544.  out is (2,N,P).
+ * ell_t = linspace(-pi,pi,P), par_t = linspace(-pi-1,pi+1,P) (:155-157). */
+void vso_editor_curve(int64_t n, int64_t P, const double *ecc_v, const double *semi_major,
+                      const double *semi_minor, const double *focus,
+                      const double *periapsis_arg, const int64_t *parents,
+                      const double *pos, const double *ell_t, const double *par_t,
+                      double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double ex = ecc_v[2 * i], ey = ecc_v[2 * i + 1];
+        double ecc = sqrt(ex * ex + ey * ey);
+        double cp = cos(periapsis_arg[i]), sp = sin(periapsis_arg[i]);
+        double fx = focus[i] * cp, fy = focus[i] * sp;
+        double px = pos[2 * parents[i]], py = pos[2 * parents[i] + 1];
+        double a = semi_major[i], b = semi_minor[i];
+        for (int64_t k = 0; k < P; ++k) {
+            double x = 0.0, y = 0.0;
+            if (ecc < 1) { x = a * cos(ell_t[k]); y = b * sin(ell_t[k]); }
+            else if (ecc == 1) { x = a * (par_t[k] * par_t[k]) - a; y = 2 * a * par_t[k]; }
+            else if (ecc > 1) { x = -a * cosh(ell_t[k]); y = b * sinh(ell_t[k]); }
+            double xr = cp * x + (-sp) * y;
+            double yr = sp * x + cp * y;
+            out[(0 * n + i) * P + k] = xr + fx + px;
+            out[(1 * n + i) * P + k] = yr + fy + py;
+        }
+    }
+}
