@@ -1,0 +1,228 @@
+/*
+ * vsb200.h -- C ABI of libvsb200.so, the B200 (sm_100a) implementation of
+ * VolatileSpace's data-parallel physics hot path.
+ *
+ * The reference (mzivic7/VolatileSpace v0.5.2, pure Python + numba) has no FFI
+ * of its own: its seam is the `Physics` classes in
+ * volatilespace/physics/{phys_editor,phys_body,phys_vessel}.py and a few free
+ * functions.  Each entry point below names the reference interface
+ * (file:line, relative to the reference repo) it stands behind; the ctypes
+ * binding a maintainer adds on the reference side is shown in INTEGRATION.md
+ * and shipped as volatilespace_b200/_lib.py.
+ *
+ * Conventions: every function returns VSB_OK (0) or a negative VSB_ERR_* code,
+ * with a message available from vsb_last_error(); nothing throws; host pointers
+ * are never retained past the call; all floating point is IEEE float64, index
+ * arrays are int64, 2-vectors are interleaved (N,2) C-order exactly like the
+ * reference's numpy arrays; calls are blocking (the result is visible in the
+ * host buffers on return) and expected from one host thread per context.
+ * There is no CPU fallback anywhere: without a CUDA device vsb_ctx_create fails.
+ */
+#ifndef VSB200_H
+#define VSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSB_ABI_VERSION 1
+
+#define VSB_OK 0
+#define VSB_ERR_CUDA (-1)  /* CUDA runtime error, no device, launch failure */
+#define VSB_ERR_ARG (-2)   /* bad argument (null pointer, negative size, index out of range) */
+#define VSB_ERR_STATE (-3) /* call order violated (e.g. step before upload) */
+#define VSB_ERR_NOMEM (-4) /* device or pinned allocation failed */
+
+typedef struct vsb_ctx vsb_ctx;
+
+/* ------------------------------------------------------------------ library */
+int vsb_abi_version(void);
+const char *vsb_last_error(void);
+int vsb_device_count(int *count_out);
+
+/* One context per GPU (one per process under torch.distributed). */
+int vsb_ctx_create(int device, vsb_ctx **ctx_out);
+int vsb_ctx_destroy(vsb_ctx *ctx);
+int vsb_ctx_sync(vsb_ctx *ctx);
+/* cudaStream_t every kernel of this context is launched on (for event timing /
+ * torch.cuda.ExternalStream interop). */
+int vsb_ctx_stream(vsb_ctx *ctx, void **cuda_stream_out);
+/* Number of kernels this library has launched on the context so far. */
+int vsb_ctx_kernel_launches(vsb_ctx *ctx, int64_t *count_out);
+/* Measured FP64 FMA peak of this device in FLOP/s (DFMA-chain microbenchmark,
+ * 2 flop per DFMA); the roofline denominator for the gravity kernel. */
+int vsb_measure_fp64_peak(vsb_ctx *ctx, double *flops_out, double *pipe_ops_out);
+/* Pin / unpin a caller-owned host buffer (cudaHostRegister) so the host-buffer entry
+ * points below copy at full PCIe rate; optional. */
+int vsb_host_register(void *ptr, int64_t bytes);
+int vsb_host_unregister(void *ptr);
+
+/* ------------------------------------------------- body-sim state (editor mode)
+ * Device mirror of phys_editor.Physics' SoA arrays, phys_editor.py:112-149. */
+enum vsb_body_field {
+    VSB_F_MASS = 0,      /* (N,)   f64 */
+    VSB_F_DEN = 1,       /* (N,)   f64 */
+    VSB_F_RAD = 2,       /* (N,)   f64  host-computed np.cbrt radius, phys_editor.py:580-581 */
+    VSB_F_COI = 3,       /* (N,)   f64 */
+    VSB_F_POS = 4,       /* (N,2)  f64 */
+    VSB_F_VEL = 5,       /* (N,2)  f64 */
+    VSB_F_REL_VEL = 6,   /* (N,2)  f64 */
+    VSB_F_ACC = 7,       /* (N,2)  f64  last all-pairs acceleration (owned rows valid) */
+    VSB_F_PARENTS = 8,   /* (N,)   i64 */
+    VSB_F_FOCUS = 9,     /* (N,)   f64  kepler_basic outputs, phys_editor.py:381-384 */
+    VSB_F_ECC_V = 10,    /* (N,2)  f64 */
+    VSB_F_SEMI_MAJOR = 11,
+    VSB_F_SEMI_MINOR = 12,
+    VSB_F_PERIAPSIS_ARG = 13,
+    VSB_F_COUNT_ = 14
+};
+
+/* load_system / add_body resize, phys_editor.py:169-201: (re)allocate for n bodies.
+ * Contents are undefined until set. */
+int vsb_bodies_resize(vsb_ctx *ctx, int64_t n);
+int vsb_bodies_count(vsb_ctx *ctx, int64_t *n_out);
+/* Copy `count` bodies starting at row `first` host->device / device->host. */
+int vsb_bodies_set(vsb_ctx *ctx, int field, const void *src, int64_t first, int64_t count);
+int vsb_bodies_get(vsb_ctx *ctx, int field, void *dst, int64_t first, int64_t count);
+/* Raw device pointer of a field (zero-copy plumbing for the NCCL all-gather). */
+int vsb_bodies_device_ptr(vsb_ctx *ctx, int field, void **dptr_out);
+/* Rows [row0,row1) are the target rows this rank computes and integrates
+ * (SURVEY 8e row sharding).  Default after resize: [0,n). */
+int vsb_bodies_set_rows(vsb_ctx *ctx, int64_t row0, int64_t row1);
+
+/* A1  Physics.find_parents, phys_editor.py:350-354 (find_parent_one :36-48).
+ * order_desc_mass = np.argsort(mass)[-1::-1] from the host.
+ * Result stays in VSB_F_PARENTS; parents_out may be NULL. */
+int vsb_find_parents(vsb_ctx *ctx, const int64_t *order_desc_mass, int64_t *parents_out);
+
+/* A3  Physics.gravity, phys_editor.py:357-378: one tick of the parent/COI model
+ * (find_parents, gravity_one :51-60, rel_vel fix-up, vel compose, pos += vel). */
+int vsb_gravity_ref(vsb_ctx *ctx, double gc, const int64_t *order_desc_mass);
+
+/* A4  documented all-pairs model, documentation/orbital-physics/
+ * 01-complex-orbit-model.txt:4-12, pair formula of gravity_one phys_editor.py:51-60.
+ * accel: VSB_F_ACC[rows] = gc * sum_{j!=i} m_j (r_j-r_i)/|r_j-r_i|^3 (no softening).
+ * integrate: v += a ; P += v on the owned rows.  step = nsteps x (accel, integrate),
+ * single GPU (rows must be [0,n)). */
+int vsb_allpairs_accel(vsb_ctx *ctx, double gc);
+int vsb_allpairs_integrate(vsb_ctx *ctx);
+int vsb_allpairs_step(vsb_ctx *ctx, double gc, int64_t nsteps);
+/* One tick on the owned rows (accel + reduce + integrate), enqueued on the context
+ * stream WITHOUT a host sync: the multi-GPU driver all-gathers VSB_F_POS after it. */
+int vsb_allpairs_tick_async(vsb_ctx *ctx, double gc);
+/* Acceleration only (accel + reduce into VSB_F_ACC), enqueued without a host sync. */
+int vsb_allpairs_accel_async(vsb_ctx *ctx, double gc);
+
+/* A6  Physics.kepler_basic, phys_editor.py:381-384 (kepler_basic_one :63-83):
+ * fills FOCUS, ECC_V, SEMI_MAJOR, SEMI_MINOR, PERIAPSIS_ARG and COI. */
+int vsb_kepler_basic(vsb_ctx *ctx, double gc, double coi_coef);
+
+/* A7  Physics.simplified_orbit_coi, phys_editor.py:325-346: recompute every COI
+ * hierarchically in descending-mass order; largest_out = argmax(mass). */
+int vsb_simplified_orbit_coi(vsb_ctx *ctx, double gc, double coi_coef,
+                             const int64_t *order_desc_mass, int64_t *largest_out);
+
+/* B1  Physics.check_collision, phys_editor.py:547-551 (check_collision_one :86-97):
+ * lexicographically smallest colliding pair, returned as (body_del, body_add);
+ * (-1,-1) stands for the reference's (None, None).  Bit-exact predicate. */
+int vsb_check_collision(vsb_ctx *ctx, int64_t *body_del_out, int64_t *body_add_out);
+
+/* B3  structural pieces of del_body :250-290 / set_root :293-313 /
+ * set_body_mass :844-857 on the device arrays.
+ * delete_row: np.delete(row) on every body array (order preserved, n -> n-1).
+ * swap_rows : swap_with_first-style swap of rows a,b in mass, den, rad, pos, vel,
+ *             rel_vel, parents (coi and the orbit arrays are not swapped, as there).
+ * translate_to: pos[:] -= pos[row]  (re-rooting, :848-850). */
+int vsb_delete_row(vsb_ctx *ctx, int64_t row);
+int vsb_swap_rows(vsb_ctx *ctx, int64_t a, int64_t b);
+int vsb_translate_to(vsb_ctx *ctx, int64_t row);
+
+/* C7  editor Physics.curve, phys_editor.py:519-544: all conic curves, layout
+ * (2,N,P) f64, from the kepler_basic outputs.  ell_t/par_t as :155-157. */
+int vsb_editor_curve(vsb_ctx *ctx, int64_t P, const double *ell_t, const double *par_t,
+                     double *out_2NP);
+
+/* ------------------------------------------- stateless host-buffer entry points
+ * Same operators over caller-owned numpy buffers: upload, run, download inside
+ * the call (this is the end-to-end path bench.py times as `e2e`). */
+/* A4 over host arrays, in place on pos/vel. */
+int vsb_host_allpairs_step(vsb_ctx *ctx, int64_t n, const double *mass, double *pos, double *vel,
+                           double gc, int64_t nsteps);
+/* A4 acceleration only, acc_out (n,2). */
+int vsb_host_allpairs_accel(vsb_ctx *ctx, int64_t n, const double *mass, const double *pos,
+                            double gc, double *acc_out);
+/* A1 */
+int vsb_host_find_parents(vsb_ctx *ctx, int64_t n, const int64_t *order_desc_mass,
+                          const double *pos, const double *coi, int64_t *parents_out);
+/* B1 */
+int vsb_host_check_collision(vsb_ctx *ctx, int64_t n, const double *mass, const double *pos,
+                             const double *rad, int64_t *body_del_out, int64_t *body_add_out);
+/* C2  enhanced_kepler_solver.solve_kepler_ell, enhanced_kepler_solver.py:18-69 (batched). */
+int vsb_host_solve_kepler_ell(vsb_ctx *ctx, int64_t n, const double *ecc, const double *ma,
+                              double tol, double *ea_out);
+/* C3  phys_shared.newton_root_kepler_hyp, phys_shared.py:114-122 (batched). */
+int vsb_host_newton_root_kepler_hyp(vsb_ctx *ctx, int64_t n, const double *ecc, const double *ma,
+                                    const double *ea_guess, double *ea_out);
+/* C5  phys_shared.curve_points, phys_shared.py:202-216, for n objects: out (n,P,2). */
+int vsb_host_curve_points(vsb_ctx *ctx, int64_t n, int64_t P, const double *ecc, const double *a,
+                          const double *b, const double *pea, const double *t, double *out);
+/* C6  phys_shared.curve_move_to, phys_shared.py:219-222. */
+int vsb_host_curve_move_to(vsb_ctx *ctx, int64_t n, int64_t P, int64_t nref, const double *curves,
+                           const double *body_pos, const int64_t *ref, const double *f,
+                           const double *pea, double *out);
+
+/* ------------------------------------------------ game-mode Keplerian state
+ * Device mirror of phys_body.Physics (kind BODY, phys_body.py:122-157) or
+ * phys_vessel.Physics (kind VESSEL, phys_vessel.py:139-173) orbit arrays. */
+#define VSB_KIND_BODY 0
+#define VSB_KIND_VESSEL 1
+
+enum vsb_kepler_field {
+    VSB_K_A = 0, VSB_K_B = 1, VSB_K_F = 2, VSB_K_ECC = 3, VSB_K_PEA = 4, VSB_K_N = 5,
+    VSB_K_DR = 6, VSB_K_MA = 7, VSB_K_EA = 8, VSB_K_POS = 9 /* (N,2) */, VSB_K_REF = 10 /* i64 */,
+    VSB_K_COUNT_ = 11
+};
+
+/* Physics.load + the orbit part of initial(): phys_body.py:177-198,221-312 /
+ * phys_vessel.py:198-240.  t = np.linspace(-pi, pi, P) (phys_body.py:165).
+ * The derived elements b, f, n come from calc_orb_one (C8, host side). */
+int vsb_kepler_load(vsb_ctx *ctx, int kind, int64_t n, int64_t P, const double *a,
+                    const double *b, const double *f, const double *ecc, const double *pea,
+                    const double *n_motion, const double *dr, const double *ma, const double *ea,
+                    const int64_t *ref, const double *t);
+/* kind BODY only: processing order np.argsort(coi)[-1::-1] of phys_body.py:328; the
+ * library turns it into dependency levels (a body whose ref comes earlier in the order
+ * sees the ref's NEW position, otherwise last tick's). */
+int vsb_kepler_set_order(vsb_ctx *ctx, const int64_t *order_desc_coi);
+int vsb_kepler_set(vsb_ctx *ctx, int kind, int field, const void *src, int64_t first, int64_t count);
+int vsb_kepler_get(vsb_ctx *ctx, int kind, int field, void *dst, int64_t first, int64_t count);
+int vsb_kepler_device_ptr(vsb_ctx *ctx, int kind, int field, void **dptr_out);
+
+/* C1  phys_body.Physics.move(warp), phys_body.py:323-346           (kind BODY;  body_pos NULL)
+ * C4  phys_vessel.Physics.move(warp, body_pos, ..), phys_vessel.py:477-494 (kind VESSEL;
+ *     body_pos = (nref,2) host array of parent-body positions, or NULL to use the
+ *     device-resident BODY state's positions).
+ * Includes C2/C3.  Results stay on the device (fetch with vsb_kepler_get). */
+int vsb_kepler_move(vsb_ctx *ctx, int kind, double warp, const double *body_pos, int64_t nref);
+
+/* C5+C6 fused: Physics.curve(i) for all i + Physics.curve_move() (phys_body.py:315-320,
+ * 405-411; phys_vessel.py:364-369,497-503): writes the moved curves (N,P,2) into the
+ * device-resident buffer straight from the elements (write-only traffic). */
+int vsb_kepler_curves(vsb_ctx *ctx, int kind);
+/* One game tick for kind VESSEL in a single kernel: move + curves (the bench path). */
+int vsb_kepler_tick(vsb_ctx *ctx, int kind, double warp, const double *body_pos, int64_t nref);
+/* Same tick enqueued without a host sync, parent positions already resident
+ * (device-timed benchmarking). */
+int vsb_kepler_tick_async(vsb_ctx *ctx, int kind, double warp);
+int vsb_kepler_free(vsb_ctx *ctx, int kind);
+/* Copy curves of objects [first, first+count) to the host, layout (count,P,2);
+ * only visible curves are ever consumed by the caller (game.py:1403-1407). */
+int vsb_kepler_curves_get(vsb_ctx *ctx, int kind, int64_t first, int64_t count, double *out);
+int vsb_kepler_curves_device_ptr(vsb_ctx *ctx, int kind, void **dptr_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSB200_H */

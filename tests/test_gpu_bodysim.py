@@ -1,0 +1,343 @@
+"""GPU parity tests for parts A and B (body-sim step, collisions): the CUDA path,
+called through the C ABI, against the CPU oracle and the committed golden
+vectors of the live reference.
+
+Bars: parents, merge pairs and indices bit-exact; positions and
+velocities within the relative FP64 tolerance written at each assert.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from volatilespace_b200.device import Device
+    d = Device(0)
+    yield d
+    d.close()
+
+
+def small_cloud(n, seed, extent=5.0e3, central=1.0e4):
+    rng = np.random.default_rng(seed)
+    mass = rng.uniform(0.5, 2.0, n)
+    mass[0] = central
+    r = rng.uniform(0.05, 1.0, n) * extent
+    th = rng.uniform(0, 2 * np.pi, n)
+    pos = np.stack([r * np.cos(th), r * np.sin(th)], axis=1)
+    sp = np.sqrt(central / r) * rng.normal(1.0, 0.1, n)
+    vel = np.stack([-sp * np.sin(th), sp * np.cos(th)], axis=1)
+    pos[0] = 0
+    vel[0] = 0
+    return mass, np.ascontiguousarray(pos), np.ascontiguousarray(vel)
+
+
+def row_rel_err(got, want):
+    """max over rows of |got-want|_2 / |want|_2"""
+    num = np.linalg.norm(got - want, axis=1)
+    den = np.maximum(np.linalg.norm(want, axis=1), 1e-300)
+    return float(np.max(num / den))
+
+
+# ------------------------------------------------------------------ A4 all-pairs
+def test_allpairs_accel_golden(dev):
+    g = golden("allpairs_small")
+    acc = dev.host_allpairs_accel(g["mass"], g["pos0"], float(g["gc"]))
+    assert row_rel_err(acc, g["acc0"]) < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 127, 128, 129, 1000, 1024, 1025, 4096, 5000])
+def test_allpairs_accel_vs_oracle(dev, oracle, n):
+    mass, pos, _ = small_cloud(n, 100 + n)
+    acc = dev.host_allpairs_accel(mass, pos, 0.75)
+    want = oracle.allpairs_accel(mass, pos, 0.75)
+    assert acc.shape == (n, 2)
+    assert np.all(np.isfinite(acc))
+    if n == 1:
+        assert np.all(acc == 0)
+    else:
+        assert row_rel_err(acc, want) < 1e-12
+
+
+def test_allpairs_plummer_sampled_rows(dev, oracle):
+    """64k-body config: acceleration parity on 256 sampled target rows."""
+    from volatilespace_b200 import synth
+    s = synth.plummer2d(65536)
+    acc = dev.host_allpairs_accel(s["mass"], s["pos"], s["gc"])
+    rows = np.random.default_rng(7).choice(65536, 256, replace=False)
+    for r in rows[:256]:
+        want = oracle.allpairs_accel(s["mass"], s["pos"], s["gc"], int(r), int(r) + 1)[0]
+        err = np.linalg.norm(acc[r] - want) / np.linalg.norm(want)
+        assert err < 1e-11, (r, err)
+
+
+def test_allpairs_steps_vs_oracle_and_golden(dev, oracle):
+    g = golden("allpairs_small")
+    pos, vel = g["pos0"].copy(), g["vel0"].copy()
+    dev.host_allpairs_step(g["mass"], pos, vel, float(g["gc"]), 16)
+    # K=16 ticks: rel 1e-10 on positions and velocities (north star "stated tolerance")
+    np.testing.assert_allclose(pos, g["pos16"], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(vel, g["vel16"], rtol=1e-10, atol=1e-12)
+    mass, pos, vel = small_cloud(4096, 5)
+    p0, v0 = pos.copy(), vel.copy()
+    dev.host_allpairs_step(mass, pos, vel, 1.0, 16)
+    wp, wv = oracle.allpairs_step(mass, p0, v0, 1.0, 16)
+    np.testing.assert_allclose(pos, wp, rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(vel, wv, rtol=1e-10, atol=1e-11)
+
+
+def test_allpairs_deterministic_and_shard_invariant(dev):
+    """Bit-identical run to run, and row-sharded accelerations equal the unsharded ones."""
+    from volatilespace_b200._lib import F_ACC
+    mass, pos, vel = small_cloud(6000, 11)
+    dev.upload_bodies(mass, pos, vel)
+    dev.allpairs_accel(1.0)
+    full = dev.get(F_ACC)
+    dev.allpairs_accel(1.0)
+    assert np.array_equal(full, dev.get(F_ACC))
+    for (r0, r1) in ((0, 1500), (1500, 3000), (3000, 4501), (4501, 6000)):
+        dev.set_rows(r0, r1)
+        dev.allpairs_accel(1.0)
+        part = dev.get(F_ACC, first=r0, count=r1 - r0)
+        assert np.array_equal(part, full[r0:r1])
+    dev.set_rows(0, 6000)
+
+
+def test_allpairs_momentum_conservation(dev):
+    """Size-independent property at a larger N: sum_i m_i a_i = 0 for pairwise forces."""
+    from volatilespace_b200 import synth
+    s = synth.plummer2d(32768, seed=3)
+    acc = dev.host_allpairs_accel(s["mass"], s["pos"], 1.0)
+    f = (acc * s["mass"][:, None])
+    scale = np.abs(f).sum(axis=0)
+    assert np.all(np.abs(f.sum(axis=0)) < 1e-11 * scale)
+
+
+# ------------------------------------------------------------------ A1 find_parents
+def test_find_parents_golden(dev):
+    g = golden("pair_kernels")
+    got = dev.host_find_parents(g["fp_order"], g["fp_pos"], g["fp_coi"])
+    assert np.array_equal(got, g["fp_parents"])
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 513, 3000, 8192])
+def test_find_parents_vs_oracle(dev, oracle, n):
+    rng = np.random.default_rng(n)
+    mass, pos, _ = small_cloud(n, 200 + n, extent=3.0e3)
+    coi = rng.uniform(0, 300, n) * (rng.uniform(0, 1, n) < 0.5)
+    order = np.argsort(mass)[-1::-1]
+    got = dev.host_find_parents(order, pos, coi)
+    want = oracle.find_parents(mass, pos, coi, order)
+    assert np.array_equal(got, want)
+    if n >= 513:
+        assert (want != 0).sum() > 10
+
+
+# ------------------------------------------------------------------ B1 collisions
+def test_check_collision_golden(dev):
+    g = golden("pair_kernels")
+    for p, r, d, a in zip(g["cc_pos"], g["cc_rad"], g["cc_del"], g["cc_add"]):
+        got = dev.host_check_collision(g["cc_mass"], p, r)
+        want = (None, None) if d < 0 else (int(d), int(a))
+        assert got == want
+
+
+@pytest.mark.parametrize("n", [2, 3, 100, 1024, 4097])
+def test_check_collision_vs_oracle_teacher_forced(dev, oracle, n):
+    rng = np.random.default_rng(300 + n)
+    for trial in range(8):
+        mass = rng.uniform(0.5, 2.0, n)
+        if trial == 7:
+            mass[:] = 1.0                                 # mass ties: lower index is deleted
+        pos = rng.uniform(-1, 1, (n, 2)) * 40.0 * np.sqrt(n) + 1.0e4
+        rad = rng.uniform(1.0, 3.0, n)
+        if trial in (1, 2) and n > 2:                     # exact-touch and +-1 ulp pairs
+            i, j = sorted(rng.choice(n, 2, replace=False))
+            d = rad[i] + rad[j]
+            pos[j] = pos[i] + np.array([d, 0.0])
+            if trial == 2:
+                pos[j, 0] = np.nextafter(pos[j, 0], np.inf)
+        if trial == 3:
+            rad[:] = 1e-3                                  # nothing collides
+        got = dev.host_check_collision(mass, pos, rad)
+        want = oracle.check_collision(mass, pos, rad)
+        assert got == want, (n, trial)
+
+
+def test_collision_full_size_property(dev, oracle):
+    """256k bodies (config 5 size): planted pair must be found; a no-overlap cloud returns None."""
+    n = 262144
+    rng = np.random.default_rng(9)
+    side = 512
+    gx, gy = np.meshgrid(np.arange(side), np.arange(side))
+    pos = np.stack([gx.ravel(), gy.ravel()], axis=1) * 40.0 + rng.uniform(-5, 5, (n, 2))
+    pos = np.ascontiguousarray(pos[rng.permutation(n)])
+    mass = rng.uniform(0.5, 2.0, n)
+    rad = np.full(n, 10.0)                                 # min spacing 30 > 20: no overlap
+    assert dev.host_check_collision(mass, pos, rad) == (None, None)
+    i, j = 201234, 255000
+    pos[j] = pos[i] + np.array([12.0, 9.0])                # distance 15 <= 20
+    got = dev.host_check_collision(mass, pos, rad)
+    assert got == ((i, j) if mass[i] <= mass[j] else (j, i))
+    i2, j2 = 777, 99999                                    # a lexicographically smaller pair wins
+    pos[j2] = pos[i2] + np.array([0.0, 20.0])              # exactly touching
+    got = dev.host_check_collision(mass, pos, rad)
+    assert got == ((i2, j2) if mass[i2] <= mass[j2] else (j2, i2))
+
+
+# ------------------------------------------------------------------ editor frames (MODE_REF)
+KEYS = ("mass", "rad", "pos", "vel", "rel_vel", "coi", "parents", "focus", "ecc_v",
+        "semi_major", "semi_minor", "periapsis_arg")
+
+
+def make_editor(dev, mass, den, pos, vel, gc=1.0, rad_mult=179.0, coi_coef=0.7, P=64):
+    from volatilespace_b200.phys_editor import Physics
+    ph = Physics(dev, curve_points=P)
+    conf = {"gc": gc, "rad_mult": rad_mult, "coi_coef": coi_coef}
+    ph.load_system(conf, {"mass": mass, "den": den}, {"pos": pos, "vel": vel})
+    ph.kepler_basic()
+    return ph
+
+
+def check_snapshot(ph, g, prefix, rtol):
+    ph.pull()
+    for k in KEYS:
+        want = g[prefix + k]
+        got = getattr(ph, k)
+        assert got.shape == want.shape, (prefix, k)
+        if k == "parents":
+            assert np.array_equal(got, want), (prefix, k)
+        else:
+            np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-300, err_msg=prefix + k)
+
+
+def test_solar_system_frames(dev):
+    """BASELINE config 1: built-in map, MODE_REF, 10 000 faithful editor frames."""
+    g = golden("solar_editor")
+    ph = make_editor(dev, g["mass"], g["den"], g["pos0"], g["vel0"], float(g["gc"]),
+                     float(g["rad_mult"]), float(g["coi_coef"]))
+    assert ph.largest == int(g["load_largest"])
+    check_snapshot(ph, g, "f0_", 1e-13)
+    frames = 0
+    for target in (1, 2, 100, 1000, 10000):
+        while frames < target:
+            assert ph.frame() == []
+            frames += 1
+        # rel 1e-9 on pos/vel after 10k frames, parents bit-exact
+        check_snapshot(ph, g, "f%d_" % target, 1e-12 if target <= 100 else 1e-9)
+        if target == 100:
+            np.testing.assert_allclose(ph.curve(), g["f100_curve64"], rtol=1e-11, atol=1e-8)
+    assert np.array_equal(ph.parents, [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 5, 5, 5, 6])
+
+
+def test_editor_cloud_coi_crossings(dev):
+    g = golden("editor_clouds")
+    ph = make_editor(dev, g["A_mass"], g["A_den"], g["A_pos0"], g["A_vel0"])
+    check_snapshot(ph, g, "A_f0_", 1e-13)
+    log = g["A_parents_log"]
+    for fr in range(1, 601):
+        assert ph.frame() == []
+        assert np.array_equal(ph.parents, log[fr - 1]), fr
+        if fr in (1, 50, 300, 600):
+            check_snapshot(ph, g, "A_f%d_" % fr, 1e-9)
+
+
+def test_editor_cloud_merges(dev):
+    """Free-running merges on the dense clump: deleted-index sequence bit-exact."""
+    g = golden("editor_clouds")
+    ph = make_editor(dev, g["B_mass"], g["B_den"], g["B_pos0"], g["B_vel0"])
+    for fr in range(1, 121):
+        d = ph.frame()
+        assert (d[0] if d else -1) == g["B_deleted"][fr - 1], fr
+        assert len(ph.mass) == g["B_counts"][fr - 1]
+        if fr in (1, 10, 40, 120):
+            check_snapshot(ph, g, "B_f%d_" % fr, 1e-9)
+
+
+def test_toy_collision_semantics(dev):
+    g = golden("editor_clouds")
+    ph = make_editor(dev, g["C_mass"], g["C_den"], g["C_pos0"], g["C_vel0"])
+    assert ph.check_collision() == (1, 4)
+    assert ph.inelastic_collision() == int(g["C_del1"])
+    ph.pull()
+    for k in ("mass", "pos", "vel", "rel_vel", "coi", "parents", "rad"):
+        np.testing.assert_allclose(getattr(ph, k), g["C_m1_" + k], rtol=1e-14, err_msg=k)
+    assert ph.check_collision() == (2, 1)
+
+
+def test_editor_vs_oracle_random_cloud(dev, oracle):
+    """A 700-body hierarchical cloud, 40 frames, against the CPU oracle state."""
+    rng = np.random.default_rng(42)
+    n = 700
+    mass, pos, vel = small_cloud(n, 77, extent=4.0e4, central=1.0e5)
+    mass[1:20] = rng.uniform(100, 2000, 19)
+    den = np.full(n, 3.0e6)
+    ph = make_editor(dev, mass, den, pos, vel)
+    ed = oracle.EditorOracle(mass, den, pos, vel)
+    ed.kepler_basic()
+    for fr in range(40):
+        assert ph.frame() == ed.frame()
+        ph.pull()
+        assert np.array_equal(ph.parents, ed.parents), fr
+    for k in ("pos", "vel", "rel_vel", "coi", "semi_major"):
+        np.testing.assert_allclose(getattr(ph, k), getattr(ed, k), rtol=1e-9, atol=1e-300,
+                                   err_msg=k)
+    assert (ed.parents != 0).sum() > 5
+
+
+def test_simplified_orbit_coi_multi_slab(dev, oracle):
+    """A7 across several 1024-rank slabs."""
+    from volatilespace_b200._lib import F_COI
+    n = 3000
+    mass, pos, vel = small_cloud(n, 91, extent=2.0e4, central=1.0e6)
+    mass[1:40] = np.random.default_rng(1).uniform(500, 5000, 39)
+    dev.upload_bodies(mass, pos, vel)
+    order = np.argsort(mass)[-1::-1]
+    largest = dev.simplified_orbit_coi(1.0, 0.7, order)
+    wl, wcoi = oracle.simplified_orbit_coi(mass, pos, vel, 1.0, 0.7, order)
+    assert largest == wl
+    np.testing.assert_allclose(dev.get(F_COI), wcoi, rtol=1e-13)
+
+
+def test_allpairs_merge_sequence(dev, oracle):
+    """MODE_ALLPAIRS free-running: (tick, del, add) list bit-exact over a short horizon
+    on a dense cold clump (non-borderline margins), final state within tolerance."""
+    from volatilespace_b200.phys_editor import AllPairsPhysics
+    rng = np.random.default_rng(5)
+    n = 600
+    mass = rng.uniform(0.5, 2.0, n)
+    mass[0] = 5.0e3
+    r = 900.0 * np.sqrt(rng.uniform(0, 1, n))
+    th = rng.uniform(0, 2 * np.pi, n)
+    pos = np.ascontiguousarray(np.stack([r * np.cos(th), r * np.sin(th)], axis=1))
+    pos[0] = 0
+    vel = np.zeros((n, 2))
+    den = np.full(n, 3000.0)
+    ph = AllPairsPhysics(dev)
+    ph.load_system({"gc": 1.0, "rad_mult": 179.0}, {"mass": mass, "den": den},
+                   {"pos": pos, "vel": vel})
+    orc = oracle.AllPairsOracle(mass, den, pos, vel)
+    got, want = [], []
+    for t in range(48):
+        got.append(ph.tick())
+        want.append(orc.tick())
+    assert got == [w if w[0] is not None else None for w in want]
+    assert sum(1 for w in want if w[0] is not None) >= 10
+    ph.pull("pos", "vel")
+    np.testing.assert_allclose(ph.pos, orc.pos, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(ph.mass, orc.mass, rtol=0)
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors_are_reported(dev):
+    from volatilespace_b200._lib import VsbError, F_POS
+    with pytest.raises(VsbError):
+        dev.set_rows(5, 2)
+    dev.upload_bodies(np.ones(4), np.zeros((4, 2)))
+    with pytest.raises(VsbError):
+        dev.get(F_POS, first=3, count=5)
+    with pytest.raises(VsbError):
+        dev.delete_row(17)

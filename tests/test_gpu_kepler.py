@@ -1,0 +1,220 @@
+"""GPU parity tests for part C (game-mode Keplerian propagation + orbit curves).
+
+Tolerances: ea, ma, pos rel 1e-12 (iteration counts may
+differ by one near the solver tolerance -> 1e-10 on ea where stated), curve
+points rel 1e-12 of the curve's scale.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from volatilespace_b200.device import Device
+    d = Device(0)
+    yield d
+    d.close()
+
+
+def test_solve_kepler_ell_golden_and_known_answers(dev):
+    g = golden("kepler_solvers")
+    got = dev.host_solve_kepler_ell(g["ecc"], g["ma"], 1e-10)
+    # the Newton exit test may fire one iteration apart: both sides are within tol of the root
+    np.testing.assert_allclose(got, g["ell"], rtol=1e-9, atol=1e-10)
+    close = np.isclose(got, g["ell"], rtol=1e-13, atol=1e-14)
+    assert close.mean() > 0.97
+    got6 = dev.host_solve_kepler_ell(g["ecc"], g["ma"], 1e-6)
+    np.testing.assert_allclose(got6, g["ell_tol6"], rtol=1e-5, atol=1e-6)
+    known = {(0.1, 1.0): 1.0885977523978936, (0.5, 3.0): 3.0471507747023945,
+             (0.9, 0.1): 0.6308435275631534, (0.0167, 4.5): 4.4837346626129175,
+             (0.7, 6.0): 5.512220917883771, (0.995, 0.001): 0.07835}
+    e = np.array([k[0] for k in known])
+    m = np.array([k[1] for k in known])
+    np.testing.assert_allclose(dev.host_solve_kepler_ell(e, m, 1e-10), list(known.values()),
+                               rtol=1e-12)
+
+
+def test_enrke_quirk_branch_exact(dev, oracle):
+    """ecc > 0.99 and folded ma < 0.0045: the reference's non-converging bisection (F8b)."""
+    rng = np.random.default_rng(1)
+    ecc = rng.uniform(0.9901, 0.99999, 4000)
+    m = rng.uniform(0.0, 0.0045, 4000)
+    ma = np.where(rng.uniform(0, 1, 4000) < 0.5, m, 2 * np.pi - m)
+    got = dev.host_solve_kepler_ell(ecc, ma, 1e-10)
+    want = oracle.solve_kepler_ell(ecc, ma, 1e-10)
+    np.testing.assert_allclose(got, want, rtol=1e-14, atol=1e-16)
+
+
+def test_newton_hyp_golden(dev):
+    g = golden("kepler_solvers")
+    got = dev.host_newton_root_kepler_hyp(g["hecc"], g["hma"], g["hguess"])
+    want = g["hyp"]
+    ok = np.isfinite(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(
+        dev.host_newton_root_kepler_hyp([1.5, 3.0, 1.01], [2.0, -4.0, 0.5], [2.0, 0.0, 0.5]),
+        [-1.6126858097584946, 1.3408203817380824, -1.379754746227187], rtol=1e-12)
+
+
+def test_curve_points_and_move_to_golden(dev):
+    g = golden("game_mode")
+    P = int(g["P"])
+    t = np.linspace(-np.pi, np.pi, P)
+    curves = dev.host_curve_points(g["v_ecc"], g["v_a"], g["v_b"], g["v_pea"], t)
+    scale = np.abs(g["v_curves"]).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(curves - g["v_curves"]) <= 1e-12 * scale)
+    moved = dev.host_curve_move_to(g["v_curves"], g["v_body_pos"], g["v_ref"], g["v_f"],
+                                   g["v_pea"])
+    scale = np.abs(g["v_curves_mov"]).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(moved - g["v_curves_mov"]) <= 1e-12 * scale)
+
+
+def test_game_body_path_golden(dev):
+    """phys_body drop-in on the Solar System: initial(1) + 1000 moves + curve_move."""
+    from volatilespace_b200.phys_body import Physics
+    g = golden("game_mode")
+    pb = Physics(dev, curve_points=int(g["P"]))
+    pb.load({"gc": float(g["gc"]), "coi_coef": float(g["coi_coef"])}, {"mass": g["mass"]},
+            {"a": g["a"], "ecc": g["ecc"], "pe_arg": g["pea"], "ma": g["ma0"], "ref": g["ref"],
+             "dir": g["dr"]})
+    body_orb, pos, ma, ea, cm = pb.initial(1)
+    for k, gk in (("b", "orb_b"), ("f", "orb_f"), ("coi", "orb_coi"), ("n", "orb_n"),
+                  ("per", "orb_per"), ("u", "orb_u"), ("pe_d", "orb_pe_d"), ("ap_d", "orb_ap_d")):
+        np.testing.assert_allclose(body_orb[k], g[gk], rtol=1e-14, err_msg=k)
+    np.testing.assert_allclose(pos, g["i_pos"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(ea, g["i_ea"], rtol=1e-10)
+    scale = np.abs(g["i_curves_mov"]).max()
+    assert np.abs(cm - g["i_curves_mov"]).max() <= 1e-12 * scale
+    for k in range(1, 1001):
+        pos, ma, ea = pb.move(3 if k % 2 else 1)
+        if k in (1, 1000):
+            np.testing.assert_allclose(pos, g["m%d_pos" % k], rtol=1e-10, atol=1e-7)
+            np.testing.assert_allclose(ma, g["m%d_ma" % k], rtol=1e-11)
+            np.testing.assert_allclose(ea, g["m%d_ea" % k], rtol=1e-10)
+            cmv = pb.curve_move()
+            assert np.abs(cmv - g["m%d_curves_mov" % k]).max() <= 1e-10 * scale
+    one = pb.curve(3)
+    assert np.abs(one - g["i_curves"][3]).max() <= 1e-12 * np.abs(g["i_curves"][3]).max()
+    vis = pb.curve_move(visible=[2, 5])
+    assert set(vis) == {2, 5} and np.array_equal(vis[5], cmv[5])
+
+
+def test_game_vessel_path_golden(dev):
+    """phys_vessel drop-in: 50 moves of 200 mixed elliptic/hyperbolic vessels (incl. ecc 0, 1,
+    and the ENRKE quirk region), then curves."""
+    from volatilespace_b200.phys_vessel import Physics
+    g = golden("game_mode")
+    pv = Physics(dev, curve_points=int(g["P"]))
+    pv.load({"gc": float(g["gc"])}, {"mass": g["mass"]}, None, None,
+            {"a": g["v_a"], "ecc": g["v_ecc"], "pe_arg": g["v_pea"], "ma": g["v_ma0"],
+             "ref": g["v_ref"], "dir": g["v_dr"], "ea": g["v_ea0"]})
+    from volatilespace_b200.synth import calc_orb
+    from volatilespace_b200._lib import KIND_VESSEL
+    orb = calc_orb("vessel", pv.ref, pv.body_mass, None, pv.gc, 0.0, pv.a, pv.ecc)
+    for k, gk in (("b", "v_b"), ("f", "v_f"), ("n", "v_n"), ("u", "v_u")):
+        np.testing.assert_allclose(orb[k], g[gk], rtol=1e-14, err_msg=k)
+    pv.b, pv.f, pv.n = orb["b"], orb["f"], orb["n"]
+    dev.kepler_load(KIND_VESSEL, pv.curve_points, pv.a, pv.b, pv.f, pv.ecc, pv.pea, pv.n, pv.dr,
+                    pv.ma, pv.ea, pv.ref, pv.t)
+    for k in range(1, 51):
+        pos, ma = pv.move(2, g["v_body_pos"])
+        if k in (1, 50):
+            np.testing.assert_allclose(ma, g["v%d_ma" % k], rtol=1e-13)
+            np.testing.assert_allclose(pv.ea, g["v%d_ea" % k], rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(pos, g["v%d_pos" % k], rtol=1e-9, atol=1e-6)
+    cm = pv.curve_move()
+    scale = np.abs(g["v_curves_mov"]).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(cm - g["v_curves_mov"]) <= 1e-12 * scale)
+
+
+def test_vessel_tick_fused_equals_split_and_oracle(dev, oracle):
+    """Config-4 shaped input at a size the oracle finishes in seconds: the fused
+    move+curves kernel must equal move followed by curves bit for bit, and match the
+    oracle (ragged N, not a multiple of 32)."""
+    from volatilespace_b200 import synth
+    from volatilespace_b200._lib import KIND_VESSEL, K_EA, K_MA, K_POS
+    n, P = 20011, 128
+    s = synth.kepler_objects(n, seed=5, quirk=500)
+    t = np.linspace(-np.pi, np.pi, P)
+
+    def load():
+        dev.kepler_load(KIND_VESSEL, P, s["a"], s["b"], s["f"], s["ecc"], s["pea"], s["n"],
+                        s["dr"], s["ma"], s["ea"], s["ref"], t)
+    load()
+    for _ in range(3):
+        dev.kepler_move(KIND_VESSEL, 1.0, s["body_pos"])
+    dev.kepler_curves(KIND_VESSEL)
+    pos_a = dev.kepler_get(KIND_VESSEL, K_POS, n)
+    ea_a = dev.kepler_get(KIND_VESSEL, K_EA, n)
+    cur_a = dev.kepler_curves_get(KIND_VESSEL, 0, n, P)
+    load()
+    for _ in range(3):
+        dev.kepler_tick(KIND_VESSEL, 1.0, s["body_pos"])
+    assert np.array_equal(pos_a, dev.kepler_get(KIND_VESSEL, K_POS, n))
+    assert np.array_equal(ea_a, dev.kepler_get(KIND_VESSEL, K_EA, n))
+    assert np.array_equal(cur_a, dev.kepler_curves_get(KIND_VESSEL, 0, n, P))
+    ma, ea = s["ma"].copy(), s["ea"].copy()
+    for _ in range(3):
+        pos, ma, ea = oracle.vessel_move(1.0, s["ref"], s["body_pos"], s["a"], s["b"], s["f"],
+                                         s["ecc"], s["pea"], s["n"], s["dr"], ma, ea)
+    np.testing.assert_allclose(dev.kepler_get(KIND_VESSEL, K_MA, n), ma, rtol=1e-14)
+    np.testing.assert_allclose(ea_a, ea, rtol=1e-9, atol=1e-10)
+    rscale = np.maximum(np.abs(s["a"]) * (1 + s["ecc"]), 1.0)[:, None]
+    assert np.all(np.abs(pos_a - pos) <= 1e-9 * rscale * np.cosh(np.minimum(np.abs(ea), 20))[:, None])
+    want = oracle.curve_move_to(oracle.curves_all(s["ecc"], s["a"], s["b"], s["pea"], t),
+                                s["body_pos"], s["ref"], s["f"], s["pea"])
+    cscale = np.abs(want).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(cur_a - want) <= 1e-12 * cscale)
+
+
+def test_kepler_full_size_properties(dev):
+    """Config 4 at 1/4 size (1M objects, P=512 = 8 GiB of curves): residual of Kepler's
+    equation, curve closure and slice consistency -- size-independent properties."""
+    from volatilespace_b200 import synth
+    from volatilespace_b200._lib import KIND_VESSEL, K_EA, K_MA, K_POS
+    n, P = 1 << 20, 512
+    s = synth.kepler_objects(n, seed=20240603)
+    dev.kepler_load(KIND_VESSEL, P, s["a"], s["b"], s["f"], s["ecc"], s["pea"], s["n"], s["dr"],
+                    s["ma"], s["ea"], s["ref"])
+    dev.kepler_tick(KIND_VESSEL, 1.0, s["body_pos"])
+    ma = dev.kepler_get(KIND_VESSEL, K_MA, n)
+    ea = dev.kepler_get(KIND_VESSEL, K_EA, n)
+    ell = s["ecc"] < 1
+    res_ell = ea[ell] - s["ecc"][ell] * np.sin(ea[ell]) - ma[ell]
+    assert np.abs(res_ell).max() < 1e-9
+    hyp = ~ell
+    res_hyp = ea[hyp] - s["ecc"][hyp] * np.sinh(ea[hyp]) - ma[hyp]     # negated convention (F8a)
+    assert np.abs(res_hyp).max() < 1e-8 * np.maximum(1, np.abs(ma[hyp])).max()
+    for first in (0, n // 2 + 17, n - 64):
+        cur = dev.kepler_curves_get(KIND_VESSEL, first, 64, P)
+        sl = slice(first, first + 64)
+        e = s["ecc"][sl] < 1
+        # ellipses close on themselves: t = -pi and t = +pi give the same point
+        closure = np.abs(cur[e, 0] - cur[e, -1]).max(axis=1)
+        assert np.all(closure <= 1e-9 * np.abs(s["a"][sl][e]))
+        # every point satisfies the conic equation about its centre
+        cp, sp = np.cos(s["pea"][sl]), np.sin(s["pea"][sl])
+        cx = s["f"][sl] * cp + s["body_pos"][0, 0]
+        cy = s["f"][sl] * sp + s["body_pos"][0, 1]
+        x = cur[:, :, 0] - cx[:, None]
+        y = cur[:, :, 1] - cy[:, None]
+        xr = x * cp[:, None] + y * sp[:, None]
+        yr = -x * sp[:, None] + y * cp[:, None]
+        sign = np.where(e, 1.0, -1.0)[:, None]
+        val = (xr / s["a"][sl][:, None])**2 + sign * (yr / s["b"][sl][:, None])**2
+        np.testing.assert_allclose(val[:, ::37], 1.0, rtol=1e-9)
+    dev.kepler_free(KIND_VESSEL)
+
+
+def test_kepler_errors(dev):
+    from volatilespace_b200._lib import VsbError, KIND_BODY, KIND_VESSEL
+    dev.kepler_free(KIND_BODY)
+    dev.kepler_free(KIND_VESSEL)
+    with pytest.raises(VsbError):
+        dev.kepler_move(KIND_BODY, 1.0)
+    with pytest.raises(VsbError):
+        dev.kepler_curves_get(KIND_VESSEL, 0, 1, 8)

@@ -1,0 +1,965 @@
+// vsb_api.cu -- C ABI of libvsb200.so (see include/vsb200.h for the contract and
+// the reference interfaces each entry point stands behind).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+
+#include "vsb_common.cuh"
+
+int vsb_kepler_tables(vsb_ctx *c, vsb_kepler_state &k, const double *d_t);
+int vsb_launch_vessel_tick(vsb_ctx *c, vsb_kepler_state &k, double warp, double *d_out);
+
+// ---------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+void vsb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int vsb_buf_reserve(vsb_buf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return VSB_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        vsb_set_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e));
+        b.p = nullptr;
+        return VSB_ERR_NOMEM;
+    }
+    b.cap = want;
+    return VSB_OK;
+}
+
+void vsb_buf_free(vsb_buf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+#define CTX(c)                                                                      \
+    do {                                                                            \
+        VSB_CHECK((c) != nullptr, VSB_ERR_ARG, "%s: null context", __func__);       \
+        VSB_CUDA(cudaSetDevice((c)->device));                                       \
+    } while (0)
+
+static int h2d(vsb_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return VSB_OK;
+    VSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+static int d2h(vsb_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (bytes == 0) return VSB_OK;
+    VSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+// ---------------------------------------------------------------- library / context
+extern "C" int vsb_abi_version(void) { return VSB_ABI_VERSION; }
+
+extern "C" const char *vsb_last_error(void) { return g_err; }
+
+extern "C" int vsb_device_count(int *count_out)
+{
+    VSB_CHECK(count_out, VSB_ERR_ARG, "vsb_device_count: null output");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count_out = 0;
+        vsb_set_error("cudaGetDeviceCount -> %s", cudaGetErrorString(e));
+        return VSB_ERR_CUDA;
+    }
+    *count_out = n;
+    return VSB_OK;
+}
+
+extern "C" int vsb_ctx_create(int device, vsb_ctx **ctx_out)
+{
+    VSB_CHECK(ctx_out, VSB_ERR_ARG, "vsb_ctx_create: null output");
+    *ctx_out = nullptr;
+    int ndev = 0;
+    VSB_TRY(vsb_device_count(&ndev));
+    VSB_CHECK(ndev > 0, VSB_ERR_CUDA, "vsb_ctx_create: no CUDA device (there is no CPU fallback)");
+    VSB_CHECK(device >= 0 && device < ndev, VSB_ERR_ARG, "vsb_ctx_create: device %d of %d", device,
+              ndev);
+    VSB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VSB_CUDA(cudaGetDeviceProperties(&prop, device));
+    VSB_CHECK(prop.major >= 10, VSB_ERR_CUDA,
+              "vsb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+              prop.major, prop.minor);
+    vsb_ctx *c = new (std::nothrow) vsb_ctx();
+    VSB_CHECK(c, VSB_ERR_NOMEM, "vsb_ctx_create: out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->kep[0].kind = VSB_KIND_BODY;
+    c->kep[1].kind = VSB_KIND_VESSEL;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_key, 64);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_key, 64);
+    if (e != cudaSuccess) {
+        vsb_set_error("vsb_ctx_create: %s", cudaGetErrorString(e));
+        delete c;
+        return VSB_ERR_CUDA;
+    }
+    *ctx_out = c;
+    return VSB_OK;
+}
+
+static void free_bodies(vsb_ctx *c)
+{
+    if (c->mass) cudaFree(c->mass);  // one slab, mass is its base
+    c->mass = nullptr;
+    c->cap = 0;
+}
+
+static void free_kepler(vsb_kepler_state &k)
+{
+    if (k.a) cudaFree(k.a);  // one slab
+    if (k.ref_pos && !k.ref_pos_borrowed) cudaFree(k.ref_pos);
+    vsb_buf_free(k.curves);
+    vsb_buf_free(k.quirk_idx);
+    free(k.h_ref);
+    int kind = k.kind;
+    k = vsb_kepler_state();
+    k.kind = kind;
+}
+
+extern "C" int vsb_ctx_destroy(vsb_ctx *c)
+{
+    if (!c) return VSB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_bodies(c);
+    free_kepler(c->kep[0]);
+    free_kepler(c->kep[1]);
+    vsb_buf_free(c->part);
+    vsb_buf_free(c->order);
+    vsb_buf_free(c->sorted);
+    vsb_buf_free(c->scratch);
+    vsb_buf_free(c->host_stage);
+    if (c->d_key) cudaFree(c->d_key);
+    if (c->h_key) cudaFreeHost(c->h_key);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return VSB_OK;
+}
+
+extern "C" int vsb_ctx_sync(vsb_ctx *c)
+{
+    CTX(c);
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_ctx_stream(vsb_ctx *c, void **out)
+{
+    CTX(c);
+    VSB_CHECK(out, VSB_ERR_ARG, "vsb_ctx_stream: null output");
+    *out = (void *)c->stream;
+    return VSB_OK;
+}
+
+extern "C" int vsb_ctx_kernel_launches(vsb_ctx *c, int64_t *out)
+{
+    VSB_CHECK(c && out, VSB_ERR_ARG, "vsb_ctx_kernel_launches: null argument");
+    *out = c->launches;
+    return VSB_OK;
+}
+
+extern "C" int vsb_host_register(void *ptr, int64_t bytes)
+{
+    VSB_CHECK(ptr && bytes > 0, VSB_ERR_ARG, "vsb_host_register: bad argument");
+    VSB_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return VSB_OK;
+}
+
+extern "C" int vsb_host_unregister(void *ptr)
+{
+    VSB_CHECK(ptr, VSB_ERR_ARG, "vsb_host_unregister: null pointer");
+    VSB_CUDA(cudaHostUnregister(ptr));
+    return VSB_OK;
+}
+
+extern "C" int vsb_measure_fp64_peak(vsb_ctx *c, double *flops_out, double *pipe_ops_out)
+{
+    CTX(c);
+    const int iters = 1 << 15, blocks = c->sm_count * 8;
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        float ms = 0;
+        VSB_TRY(vsb_launch_dfma_peak(c, iters, blocks, &ms));
+        if (ms < best) best = ms;
+    }
+    const double dfma = (double)blocks * 256.0 * 8.0 * (double)iters;
+    if (pipe_ops_out) *pipe_ops_out = dfma / (best * 1e-3);
+    if (flops_out) *flops_out = 2.0 * dfma / (best * 1e-3);
+    return VSB_OK;
+}
+
+// ---------------------------------------------------------------- body-sim state
+struct field_info {
+    int width;  // 8-byte words per row
+};
+static const field_info k_fields[VSB_F_COUNT_] = {{1}, {1}, {1}, {1}, {2}, {2}, {2},
+                                                  {2}, {1}, {1}, {2}, {1}, {1}, {1}};
+
+static void *field_ptr(vsb_ctx *c, int field)
+{
+    switch (field) {
+        case VSB_F_MASS: return c->mass;
+        case VSB_F_DEN: return c->den;
+        case VSB_F_RAD: return c->rad;
+        case VSB_F_COI: return c->coi;
+        case VSB_F_POS: return c->pos;
+        case VSB_F_VEL: return c->vel;
+        case VSB_F_REL_VEL: return c->rel_vel;
+        case VSB_F_ACC: return c->acc;
+        case VSB_F_PARENTS: return c->parents;
+        case VSB_F_FOCUS: return c->focus;
+        case VSB_F_ECC_V: return c->ecc_v;
+        case VSB_F_SEMI_MAJOR: return c->semi_major;
+        case VSB_F_SEMI_MINOR: return c->semi_minor;
+        case VSB_F_PERIAPSIS_ARG: return c->periapsis_arg;
+        default: return nullptr;
+    }
+}
+
+extern "C" int vsb_bodies_resize(vsb_ctx *c, int64_t n)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && n < (1ll << 31), VSB_ERR_ARG, "vsb_bodies_resize: n=%lld out of range",
+              (long long)n);
+    const int64_t npad = vsb_round_up(n > 0 ? n : 1, VSB_PAD);
+    if (npad > c->cap) {
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        free_bodies(c);
+        // one slab: 20 words per row (9 one-word fields incl. parents + 5 two-word) + parents_old
+        const size_t words = 20;
+        double *slab = nullptr;
+        cudaError_t e = cudaMalloc((void **)&slab, sizeof(double) * words * (size_t)npad);
+        VSB_CHECK(e == cudaSuccess, VSB_ERR_NOMEM, "vsb_bodies_resize: cudaMalloc for %lld bodies -> %s",
+                  (long long)n, cudaGetErrorString(e));
+        size_t o = 0;
+        auto take = [&](int w) { double *p = slab + o; o += (size_t)w * npad; return p; };
+        c->mass = take(1); c->den = take(1); c->rad = take(1); c->coi = take(1);
+        c->focus = take(1); c->semi_major = take(1); c->semi_minor = take(1);
+        c->periapsis_arg = take(1);
+        c->parents = (int64_t *)take(1);
+        c->parents_old = (int64_t *)take(1);
+        c->pos = take(2); c->vel = take(2); c->rel_vel = take(2); c->acc = take(2);
+        c->ecc_v = take(2);
+        c->cap = npad;
+        VSB_CUDA(cudaMemsetAsync(slab, 0, sizeof(double) * words * (size_t)npad, c->stream));
+    }
+    c->n = n;
+    c->npad = npad;
+    c->row0 = 0;
+    c->row1 = n;
+    VSB_TRY(vsb_launch_pad_tail(c));
+    return VSB_OK;
+}
+
+extern "C" int vsb_bodies_count(vsb_ctx *c, int64_t *n_out)
+{
+    VSB_CHECK(c && n_out, VSB_ERR_ARG, "vsb_bodies_count: null argument");
+    *n_out = c->n;
+    return VSB_OK;
+}
+
+static int field_range(vsb_ctx *c, const char *who, int field, const void *p, int64_t first,
+                       int64_t count)
+{
+    VSB_CHECK(field >= 0 && field < VSB_F_COUNT_, VSB_ERR_ARG, "%s: unknown field %d", who, field);
+    VSB_CHECK(c->mass != nullptr, VSB_ERR_STATE, "%s: no bodies (call vsb_bodies_resize)", who);
+    VSB_CHECK(first >= 0 && count >= 0 && first + count <= c->n, VSB_ERR_ARG,
+              "%s: rows [%lld,%lld) outside [0,%lld)", who, (long long)first,
+              (long long)(first + count), (long long)c->n);
+    VSB_CHECK(p != nullptr || count == 0, VSB_ERR_ARG, "%s: null buffer", who);
+    return VSB_OK;
+}
+
+extern "C" int vsb_bodies_set(vsb_ctx *c, int field, const void *src, int64_t first, int64_t count)
+{
+    CTX(c);
+    VSB_TRY(field_range(c, "vsb_bodies_set", field, src, first, count));
+    const size_t w = 8 * (size_t)k_fields[field].width;
+    return h2d(c, (char *)field_ptr(c, field) + w * first, src, w * count);
+}
+
+extern "C" int vsb_bodies_get(vsb_ctx *c, int field, void *dst, int64_t first, int64_t count)
+{
+    CTX(c);
+    VSB_TRY(field_range(c, "vsb_bodies_get", field, dst, first, count));
+    const size_t w = 8 * (size_t)k_fields[field].width;
+    return d2h(c, dst, (char *)field_ptr(c, field) + w * first, w * count);
+}
+
+extern "C" int vsb_bodies_device_ptr(vsb_ctx *c, int field, void **out)
+{
+    CTX(c);
+    VSB_CHECK(out && field >= 0 && field < VSB_F_COUNT_, VSB_ERR_ARG,
+              "vsb_bodies_device_ptr: bad argument");
+    VSB_CHECK(c->mass != nullptr, VSB_ERR_STATE, "vsb_bodies_device_ptr: no bodies");
+    *out = field_ptr(c, field);
+    return VSB_OK;
+}
+
+extern "C" int vsb_bodies_set_rows(vsb_ctx *c, int64_t row0, int64_t row1)
+{
+    VSB_CHECK(c, VSB_ERR_ARG, "vsb_bodies_set_rows: null context");
+    VSB_CHECK(row0 >= 0 && row0 <= row1 && row1 <= c->n, VSB_ERR_ARG,
+              "vsb_bodies_set_rows: [%lld,%lld) outside [0,%lld]", (long long)row0,
+              (long long)row1, (long long)c->n);
+    c->row0 = row0;
+    c->row1 = row1;
+    return VSB_OK;
+}
+
+static int need_bodies(vsb_ctx *c, const char *who)
+{
+    VSB_CHECK(c->mass != nullptr && c->n > 0, VSB_ERR_STATE, "%s: no bodies uploaded", who);
+    return VSB_OK;
+}
+
+static int upload_order(vsb_ctx *c, const char *who, const int64_t *order)
+{
+    VSB_CHECK(order, VSB_ERR_ARG, "%s: null order", who);
+    VSB_TRY(vsb_buf_reserve(c->order, sizeof(int64_t) * (size_t)c->npad));
+    return h2d(c, c->order.p, order, sizeof(int64_t) * (size_t)c->n);
+}
+
+extern "C" int vsb_find_parents(vsb_ctx *c, const int64_t *order, int64_t *parents_out)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_find_parents"));
+    VSB_TRY(upload_order(c, "vsb_find_parents", order));
+    VSB_TRY(vsb_launch_find_parents(c, (const int64_t *)c->order.p));
+    if (parents_out) return d2h(c, parents_out, c->parents, sizeof(int64_t) * (size_t)c->n);
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_gravity_ref(vsb_ctx *c, double gc, const int64_t *order)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_gravity_ref"));
+    VSB_TRY(upload_order(c, "vsb_gravity_ref", order));
+    return vsb_launch_gravity_ref(c, gc, (const int64_t *)c->order.p);
+}
+
+extern "C" int vsb_allpairs_accel(vsb_ctx *c, double gc)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_allpairs_accel"));
+    VSB_TRY(vsb_launch_allpairs_accel(c, gc));
+    VSB_TRY(vsb_launch_allpairs_reduce(c, gc, 0));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_allpairs_integrate(vsb_ctx *c)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_allpairs_integrate"));
+    VSB_TRY(vsb_launch_allpairs_integrate(c));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+// asynchronous variants used by the multi-GPU driver (no host sync inside)
+extern "C" int vsb_allpairs_tick_async(vsb_ctx *c, double gc)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_allpairs_tick_async"));
+    VSB_TRY(vsb_launch_allpairs_accel(c, gc));
+    return vsb_launch_allpairs_reduce(c, gc, 1);
+}
+
+extern "C" int vsb_allpairs_accel_async(vsb_ctx *c, double gc)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_allpairs_accel_async"));
+    VSB_TRY(vsb_launch_allpairs_accel(c, gc));
+    return vsb_launch_allpairs_reduce(c, gc, 0);
+}
+
+extern "C" int vsb_allpairs_step(vsb_ctx *c, double gc, int64_t nsteps)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_allpairs_step"));
+    VSB_CHECK(c->row0 == 0 && c->row1 == c->n, VSB_ERR_STATE,
+              "vsb_allpairs_step: rows are sharded [%lld,%lld); step per tick and all-gather "
+              "positions between ticks instead",
+              (long long)c->row0, (long long)c->row1);
+    for (int64_t s = 0; s < nsteps; ++s) {
+        VSB_TRY(vsb_launch_allpairs_accel(c, gc));
+        VSB_TRY(vsb_launch_allpairs_reduce(c, gc, 1));
+    }
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_kepler_basic(vsb_ctx *c, double gc, double coi_coef)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_kepler_basic"));
+    VSB_TRY(vsb_launch_kepler_basic(c, gc, coi_coef));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_simplified_orbit_coi(vsb_ctx *c, double gc, double coi_coef,
+                                        const int64_t *order, int64_t *largest_out)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_simplified_orbit_coi"));
+    VSB_TRY(upload_order(c, "vsb_simplified_orbit_coi", order));
+    VSB_TRY(vsb_launch_simplified_orbit_coi(c, gc, coi_coef, (const int64_t *)c->order.p));
+    int64_t largest = 0;
+    VSB_TRY(d2h(c, &largest, c->scratch.p, sizeof(int64_t)));
+    if (largest_out) *largest_out = largest;
+    return VSB_OK;
+}
+
+extern "C" int vsb_check_collision(vsb_ctx *c, int64_t *del_out, int64_t *add_out)
+{
+    CTX(c);
+    VSB_CHECK(del_out && add_out, VSB_ERR_ARG, "vsb_check_collision: null output");
+    VSB_TRY(need_bodies(c, "vsb_check_collision"));
+    VSB_TRY(vsb_launch_check_collision(c));
+    VSB_CUDA(cudaMemcpyAsync(c->h_key, c->scratch.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                             c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    *del_out = ((int64_t *)c->h_key)[0];
+    *add_out = ((int64_t *)c->h_key)[1];
+    return VSB_OK;
+}
+
+extern "C" int vsb_delete_row(vsb_ctx *c, int64_t row)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_delete_row"));
+    VSB_CHECK(row >= 0 && row < c->n, VSB_ERR_ARG, "vsb_delete_row: row %lld of %lld",
+              (long long)row, (long long)c->n);
+    VSB_CHECK(c->n > 1, VSB_ERR_STATE, "vsb_delete_row: the last body cannot be deleted");
+    VSB_TRY(vsb_launch_delete_row(c, row));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_swap_rows(vsb_ctx *c, int64_t a, int64_t b)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_swap_rows"));
+    VSB_CHECK(a >= 0 && a < c->n && b >= 0 && b < c->n, VSB_ERR_ARG,
+              "vsb_swap_rows: rows %lld,%lld of %lld", (long long)a, (long long)b, (long long)c->n);
+    if (a != b) VSB_TRY(vsb_launch_swap_rows(c, a, b));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_translate_to(vsb_ctx *c, int64_t row)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_translate_to"));
+    VSB_CHECK(row >= 0 && row < c->n, VSB_ERR_ARG, "vsb_translate_to: row %lld of %lld",
+              (long long)row, (long long)c->n);
+    VSB_TRY(vsb_launch_translate(c, row));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_editor_curve(vsb_ctx *c, int64_t P, const double *ell_t, const double *par_t,
+                                double *out)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_editor_curve"));
+    VSB_CHECK(P > 0 && ell_t && par_t && out, VSB_ERR_ARG, "vsb_editor_curve: bad argument");
+    const size_t out_bytes = sizeof(double) * 2 * (size_t)c->n * (size_t)P;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, out_bytes + sizeof(double) * 2 * (size_t)P));
+    double *d_out = (double *)c->host_stage.p;
+    double *d_tabs = (double *)((char *)c->host_stage.p + out_bytes);
+    VSB_TRY(h2d(c, d_tabs, ell_t, sizeof(double) * (size_t)P));
+    VSB_TRY(h2d(c, d_tabs + P, par_t, sizeof(double) * (size_t)P));
+    VSB_TRY(vsb_launch_editor_curve(c, P, d_tabs, d_out));
+    return d2h(c, out, d_out, out_bytes);
+}
+
+// ---------------------------------------------------------------- stateless host-buffer calls
+// They stage through the context's own body arrays: resident body state is overwritten.
+static int stage_bodies(vsb_ctx *c, int64_t n)
+{
+    if (c->n != n || c->mass == nullptr) VSB_TRY(vsb_bodies_resize(c, n));
+    c->row0 = 0;
+    c->row1 = n;
+    return VSB_OK;
+}
+
+extern "C" int vsb_host_allpairs_step(vsb_ctx *c, int64_t n, const double *mass, double *pos,
+                                      double *vel, double gc, int64_t nsteps)
+{
+    CTX(c);
+    VSB_CHECK(n > 0 && mass && pos && vel && nsteps >= 0, VSB_ERR_ARG,
+              "vsb_host_allpairs_step: bad argument");
+    VSB_TRY(stage_bodies(c, n));
+    VSB_CUDA(cudaMemcpyAsync(c->mass, mass, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(c->pos, pos, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(c->vel, vel, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    for (int64_t s = 0; s < nsteps; ++s) {
+        VSB_TRY(vsb_launch_allpairs_accel(c, gc));
+        VSB_TRY(vsb_launch_allpairs_reduce(c, gc, 1));
+    }
+    VSB_CUDA(cudaMemcpyAsync(pos, c->pos, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(vel, c->vel, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_host_allpairs_accel(vsb_ctx *c, int64_t n, const double *mass,
+                                       const double *pos, double gc, double *acc_out)
+{
+    CTX(c);
+    VSB_CHECK(n > 0 && mass && pos && acc_out, VSB_ERR_ARG, "vsb_host_allpairs_accel: bad argument");
+    VSB_TRY(stage_bodies(c, n));
+    VSB_CUDA(cudaMemcpyAsync(c->mass, mass, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(c->pos, pos, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_allpairs_accel(c, gc));
+    VSB_TRY(vsb_launch_allpairs_reduce(c, gc, 0));
+    return d2h(c, acc_out, c->acc, 16 * (size_t)n);
+}
+
+extern "C" int vsb_host_find_parents(vsb_ctx *c, int64_t n, const int64_t *order,
+                                     const double *pos, const double *coi, int64_t *parents_out)
+{
+    CTX(c);
+    VSB_CHECK(n > 0 && order && pos && coi && parents_out, VSB_ERR_ARG,
+              "vsb_host_find_parents: bad argument");
+    VSB_TRY(stage_bodies(c, n));
+    VSB_CUDA(cudaMemcpyAsync(c->pos, pos, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(c->coi, coi, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    return vsb_find_parents(c, order, parents_out);
+}
+
+extern "C" int vsb_host_check_collision(vsb_ctx *c, int64_t n, const double *mass,
+                                        const double *pos, const double *rad, int64_t *del_out,
+                                        int64_t *add_out)
+{
+    CTX(c);
+    VSB_CHECK(n > 0 && mass && pos && rad, VSB_ERR_ARG, "vsb_host_check_collision: bad argument");
+    VSB_TRY(stage_bodies(c, n));
+    VSB_CUDA(cudaMemcpyAsync(c->mass, mass, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(c->pos, pos, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(c->rad, rad, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    return vsb_check_collision(c, del_out, add_out);
+}
+
+extern "C" int vsb_host_solve_kepler_ell(vsb_ctx *c, int64_t n, const double *ecc,
+                                         const double *ma, double tol, double *out)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && (n == 0 || (ecc && ma && out)), VSB_ERR_ARG,
+              "vsb_host_solve_kepler_ell: bad argument");
+    if (n == 0) return VSB_OK;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 24 * (size_t)n));
+    double *d = (double *)c->host_stage.p;
+    VSB_CUDA(cudaMemcpyAsync(d, ecc, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d + n, ma, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_solve_ell(c, n, d, d + n, tol, d + 2 * n));
+    return d2h(c, out, d + 2 * n, 8 * (size_t)n);
+}
+
+extern "C" int vsb_host_newton_root_kepler_hyp(vsb_ctx *c, int64_t n, const double *ecc,
+                                               const double *ma, const double *guess, double *out)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && (n == 0 || (ecc && ma && guess && out)), VSB_ERR_ARG,
+              "vsb_host_newton_root_kepler_hyp: bad argument");
+    if (n == 0) return VSB_OK;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 32 * (size_t)n));
+    double *d = (double *)c->host_stage.p;
+    VSB_CUDA(cudaMemcpyAsync(d, ecc, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d + n, ma, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d + 2 * n, guess, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_solve_hyp(c, n, d, d + n, d + 2 * n, d + 3 * n));
+    return d2h(c, out, d + 3 * n, 8 * (size_t)n);
+}
+
+extern "C" int vsb_host_curve_points(vsb_ctx *c, int64_t n, int64_t P, const double *ecc,
+                                     const double *a, const double *b, const double *pea,
+                                     const double *t, double *out)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && P > 0 && (n == 0 || (ecc && a && b && pea && t && out)), VSB_ERR_ARG,
+              "vsb_host_curve_points: bad argument");
+    if (n == 0) return VSB_OK;
+    const size_t out_bytes = 16 * (size_t)n * (size_t)P;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, out_bytes + 8 * (4 * (size_t)n + 5 * (size_t)P)));
+    double *d_out = (double *)c->host_stage.p;
+    double *d = (double *)((char *)c->host_stage.p + out_bytes);
+    vsb_kepler_state k;
+    k.kind = VSB_KIND_VESSEL;
+    k.n = n;
+    k.P = P;
+    k.ecc = d; k.a = d + n; k.b = d + 2 * n; k.pea = d + 3 * n;
+    k.tab = d + 4 * n;          // 4P doubles
+    double *d_t = d + 4 * n + 4 * P;
+    VSB_CUDA(cudaMemcpyAsync(k.ecc, ecc, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(k.a, a, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(k.b, b, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(k.pea, pea, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_t, t, 8 * (size_t)P, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_kepler_tables(c, k, d_t));
+    VSB_TRY(vsb_launch_kepler_curves(c, k, 0, n, d_out, 0));
+    return d2h(c, out, d_out, out_bytes);
+}
+
+extern "C" int vsb_host_curve_move_to(vsb_ctx *c, int64_t n, int64_t P, int64_t nref,
+                                      const double *curves, const double *body_pos,
+                                      const int64_t *ref, const double *f, const double *pea,
+                                      double *out)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && P > 0 && nref > 0 && (n == 0 || (curves && body_pos && ref && f && pea && out)),
+              VSB_ERR_ARG, "vsb_host_curve_move_to: bad argument");
+    if (n == 0) return VSB_OK;
+    const size_t cb = 16 * (size_t)n * (size_t)P;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 2 * cb + 16 * (size_t)nref + 24 * (size_t)n));
+    char *base = (char *)c->host_stage.p;
+    double *d_in = (double *)base, *d_out = (double *)(base + cb);
+    double *d_bp = (double *)(base + 2 * cb);
+    int64_t *d_ref = (int64_t *)(base + 2 * cb + 16 * (size_t)nref);
+    double *d_f = (double *)(d_ref + n), *d_pea = d_f + n;
+    VSB_CUDA(cudaMemcpyAsync(d_in, curves, cb, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_bp, body_pos, 16 * (size_t)nref, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_ref, ref, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_f, f, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_pea, pea, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_curve_move_to(c, n, P, d_in, d_bp, d_ref, d_f, d_pea, d_out));
+    return d2h(c, out, d_out, cb);
+}
+
+// ---------------------------------------------------------------- game-mode Kepler state
+static int kep_of(vsb_ctx *c, const char *who, int kind, vsb_kepler_state **k)
+{
+    VSB_CHECK(kind == VSB_KIND_BODY || kind == VSB_KIND_VESSEL, VSB_ERR_ARG, "%s: unknown kind %d",
+              who, kind);
+    *k = &c->kep[kind];
+    return VSB_OK;
+}
+
+static void *kep_field_ptr(vsb_kepler_state &k, int field, int *width, int *is_int)
+{
+    *width = 1;
+    *is_int = 0;
+    switch (field) {
+        case VSB_K_A: return k.a;
+        case VSB_K_B: return k.b;
+        case VSB_K_F: return k.f;
+        case VSB_K_ECC: return k.ecc;
+        case VSB_K_PEA: return k.pea;
+        case VSB_K_N: return k.nmot;
+        case VSB_K_DR: return k.dr;
+        case VSB_K_MA: return k.ma;
+        case VSB_K_EA: return k.ea;
+        case VSB_K_POS: *width = 2; return k.pos;
+        case VSB_K_REF: *is_int = 1; return k.ref;
+        default: return nullptr;
+    }
+}
+
+extern "C" int vsb_kepler_load(vsb_ctx *c, int kind, int64_t n, int64_t P, const double *a,
+                               const double *b, const double *f, const double *ecc,
+                               const double *pea, const double *nmot, const double *dr,
+                               const double *ma, const double *ea, const int64_t *ref,
+                               const double *t)
+{
+    CTX(c);
+    vsb_kepler_state *kp;
+    VSB_TRY(kep_of(c, "vsb_kepler_load", kind, &kp));
+    VSB_CHECK(n > 0 && P > 0 && a && b && f && ecc && pea && nmot && dr && ma && ea && ref && t,
+              VSB_ERR_ARG, "vsb_kepler_load: bad argument");
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    free_kepler(*kp);
+    vsb_kepler_state &k = *kp;
+    // slab (8-byte words): 9 element arrays + pos(2) + pr(2) + ref + lvl_idx = 15n, tab 4P, t P
+    const size_t words = 15 * (size_t)n + 5 * (size_t)P;
+    double *slab = nullptr;
+    cudaError_t e = cudaMalloc((void **)&slab, 8 * words);
+    VSB_CHECK(e == cudaSuccess, VSB_ERR_NOMEM, "vsb_kepler_load: cudaMalloc -> %s",
+              cudaGetErrorString(e));
+    size_t o = 0;
+    auto take = [&](size_t w) { double *p = slab + o; o += w; return p; };
+    k.a = take(n); k.b = take(n); k.f = take(n); k.ecc = take(n); k.pea = take(n);
+    k.nmot = take(n); k.dr = take(n); k.ma = take(n); k.ea = take(n);
+    k.pos = take(2 * n); k.pr = take(2 * n);
+    k.ref = (int64_t *)take(n); k.lvl_idx = (int64_t *)take(n);
+    k.tab = take(4 * P);
+    double *d_t = take(P);
+    k.n = n; k.P = P; k.kind = kind; k.nlevels = 0;
+    k.h_ref = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    VSB_CHECK(k.h_ref, VSB_ERR_NOMEM, "vsb_kepler_load: out of host memory");
+    memcpy(k.h_ref, ref, sizeof(int64_t) * (size_t)n);
+    const double *src[9] = {a, b, f, ecc, pea, nmot, dr, ma, ea};
+    double *dst[9] = {k.a, k.b, k.f, k.ecc, k.pea, k.nmot, k.dr, k.ma, k.ea};
+    for (int i = 0; i < 9; ++i)
+        VSB_CUDA(cudaMemcpyAsync(dst[i], src[i], 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(k.ref, ref, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemsetAsync(k.pos, 0, 16 * (size_t)n, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_t, t, 8 * (size_t)P, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_kepler_tables(c, k, d_t));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_kepler_set_order(vsb_ctx *c, const int64_t *order)
+{
+    CTX(c);
+    vsb_kepler_state &k = c->kep[VSB_KIND_BODY];
+    VSB_CHECK(k.n > 0, VSB_ERR_STATE, "vsb_kepler_set_order: no BODY state loaded");
+    VSB_CHECK(order, VSB_ERR_ARG, "vsb_kepler_set_order: null order");
+    const int64_t n = k.n;
+    int64_t *rank = (int64_t *)malloc(sizeof(int64_t) * 3 * (size_t)n);
+    VSB_CHECK(rank, VSB_ERR_NOMEM, "vsb_kepler_set_order: out of host memory");
+    int64_t *level = rank + n, *idx = rank + 2 * n;
+    for (int64_t r = 0; r < n; ++r) {
+        if (order[r] < 0 || order[r] >= n) {
+            free(rank);
+            VSB_CHECK(false, VSB_ERR_ARG, "vsb_kepler_set_order: order[%lld] out of range",
+                      (long long)r);
+        }
+        rank[order[r]] = r;
+    }
+    int64_t nlevels = 0;
+    int64_t counts[65] = {0};
+    for (int64_t r = 0; r < n; ++r) {  // ascending rank: a "new" ref is already levelled
+        const int64_t body = order[r], rf = k.h_ref[body];
+        const bool dep_new = rf >= 0 && rf < n && rank[rf] < r;
+        level[body] = dep_new ? level[rf] + 1 : 0;
+        if (level[body] >= 64) {
+            free(rank);
+            VSB_CHECK(false, VSB_ERR_ARG, "vsb_kepler_set_order: hierarchy deeper than 64 levels");
+        }
+        counts[level[body]]++;
+        if (level[body] + 1 > nlevels) nlevels = level[body] + 1;
+    }
+    k.lvl_off[0] = 0;
+    for (int64_t l = 0; l < nlevels; ++l) k.lvl_off[l + 1] = k.lvl_off[l] + counts[l];
+    int64_t fill[65];
+    for (int64_t l = 0; l <= nlevels; ++l) fill[l] = k.lvl_off[l];
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t body = order[r], rf = k.h_ref[body];
+        const bool dep_new = rf >= 0 && rf < n && rank[rf] < r;
+        idx[fill[level[body]]++] = body | ((int64_t)(dep_new ? 1 : 0) << 62);
+    }
+    k.nlevels = nlevels;
+    int rc = h2d(c, k.lvl_idx, idx, sizeof(int64_t) * (size_t)n);
+    free(rank);
+    return rc;
+}
+
+static int kep_range(vsb_kepler_state &k, const char *who, int field, const void *p, int64_t first,
+                     int64_t count)
+{
+    VSB_CHECK(k.n > 0, VSB_ERR_STATE, "%s: no state loaded for this kind", who);
+    VSB_CHECK(field >= 0 && field < VSB_K_COUNT_, VSB_ERR_ARG, "%s: unknown field %d", who, field);
+    VSB_CHECK(first >= 0 && count >= 0 && first + count <= k.n, VSB_ERR_ARG,
+              "%s: objects [%lld,%lld) outside [0,%lld)", who, (long long)first,
+              (long long)(first + count), (long long)k.n);
+    VSB_CHECK(p != nullptr || count == 0, VSB_ERR_ARG, "%s: null buffer", who);
+    return VSB_OK;
+}
+
+extern "C" int vsb_kepler_set(vsb_ctx *c, int kind, int field, const void *src, int64_t first,
+                              int64_t count)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_set", kind, &k));
+    VSB_TRY(kep_range(*k, "vsb_kepler_set", field, src, first, count));
+    int w, is_int;
+    char *p = (char *)kep_field_ptr(*k, field, &w, &is_int);
+    if (field == VSB_K_REF) memcpy(k->h_ref + first, src, 8 * (size_t)count);
+    return h2d(c, p + 8 * (size_t)w * first, src, 8 * (size_t)w * count);
+}
+
+extern "C" int vsb_kepler_get(vsb_ctx *c, int kind, int field, void *dst, int64_t first,
+                              int64_t count)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_get", kind, &k));
+    VSB_TRY(kep_range(*k, "vsb_kepler_get", field, dst, first, count));
+    int w, is_int;
+    char *p = (char *)kep_field_ptr(*k, field, &w, &is_int);
+    return d2h(c, dst, p + 8 * (size_t)w * first, 8 * (size_t)w * count);
+}
+
+extern "C" int vsb_kepler_device_ptr(vsb_ctx *c, int kind, int field, void **out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_device_ptr", kind, &k));
+    VSB_CHECK(out && k->n > 0 && field >= 0 && field < VSB_K_COUNT_, VSB_ERR_ARG,
+              "vsb_kepler_device_ptr: bad argument or no state");
+    int w, is_int;
+    *out = kep_field_ptr(*k, field, &w, &is_int);
+    return VSB_OK;
+}
+
+static int vessel_ref_pos(vsb_ctx *c, vsb_kepler_state &k, const double *body_pos, int64_t nref)
+{
+    if (body_pos) {
+        VSB_CHECK(nref > 0, VSB_ERR_ARG, "kepler(VESSEL): nref must be positive");
+        if (k.ref_pos_borrowed) {
+            k.ref_pos = nullptr;
+            k.ref_pos_borrowed = 0;
+            k.nref = 0;
+        }
+        if (nref > k.nref || !k.ref_pos) {
+            VSB_CUDA(cudaStreamSynchronize(c->stream));
+            if (k.ref_pos) cudaFree(k.ref_pos);
+            k.ref_pos = nullptr;
+            cudaError_t e = cudaMalloc((void **)&k.ref_pos, 16 * (size_t)nref);
+            VSB_CHECK(e == cudaSuccess, VSB_ERR_NOMEM, "kepler(VESSEL): cudaMalloc -> %s",
+                      cudaGetErrorString(e));
+        }
+        k.nref = nref;
+        VSB_CUDA(cudaMemcpyAsync(k.ref_pos, body_pos, 16 * (size_t)nref, cudaMemcpyHostToDevice,
+                                 c->stream));
+    } else {
+        // NULL: borrow the resident BODY state's device positions (no copy)
+        vsb_kepler_state &b = c->kep[VSB_KIND_BODY];
+        VSB_CHECK(b.n > 0, VSB_ERR_STATE,
+                  "kepler(VESSEL): body_pos is NULL and no BODY state is resident");
+        if (k.ref_pos && !k.ref_pos_borrowed) {
+            VSB_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(k.ref_pos);
+        }
+        k.ref_pos = b.pos;
+        k.ref_pos_borrowed = 1;
+        k.nref = b.n;
+    }
+    return VSB_OK;
+}
+
+extern "C" int vsb_kepler_move(vsb_ctx *c, int kind, double warp, const double *body_pos,
+                               int64_t nref)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_move", kind, &k));
+    VSB_CHECK(k->n > 0, VSB_ERR_STATE, "vsb_kepler_move: no state loaded for this kind");
+    if (kind == VSB_KIND_VESSEL) VSB_TRY(vessel_ref_pos(c, *k, body_pos, nref));
+    VSB_TRY(vsb_launch_kepler_move(c, *k, warp));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+static int reserve_curves(vsb_kepler_state &k)
+{
+    return vsb_buf_reserve(k.curves, 16 * (size_t)k.n * (size_t)k.P);
+}
+
+extern "C" int vsb_kepler_curves(vsb_ctx *c, int kind)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_curves", kind, &k));
+    VSB_CHECK(k->n > 0, VSB_ERR_STATE, "vsb_kepler_curves: no state loaded for this kind");
+    if (kind == VSB_KIND_VESSEL)
+        VSB_CHECK(k->ref_pos != nullptr, VSB_ERR_STATE,
+                  "vsb_kepler_curves(VESSEL): call vsb_kepler_move first (parent positions)");
+    VSB_TRY(reserve_curves(*k));
+    VSB_TRY(vsb_launch_kepler_curves(c, *k, 0, k->n, (double *)k->curves.p, 1));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_kepler_tick(vsb_ctx *c, int kind, double warp, const double *body_pos,
+                               int64_t nref)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_tick", kind, &k));
+    VSB_CHECK(k->n > 0, VSB_ERR_STATE, "vsb_kepler_tick: no state loaded for this kind");
+    VSB_TRY(reserve_curves(*k));
+    if (kind == VSB_KIND_VESSEL) {
+        VSB_TRY(vessel_ref_pos(c, *k, body_pos, nref));
+        VSB_TRY(vsb_launch_vessel_tick(c, *k, warp, (double *)k->curves.p));
+    } else {
+        VSB_TRY(vsb_launch_kepler_move(c, *k, warp));
+        VSB_TRY(vsb_launch_kepler_curves(c, *k, 0, k->n, (double *)k->curves.p, 1));
+    }
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+// asynchronous tick for device-timed benchmarking (no host sync)
+extern "C" int vsb_kepler_tick_async(vsb_ctx *c, int kind, double warp)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_tick_async", kind, &k));
+    VSB_CHECK(k->n > 0, VSB_ERR_STATE, "vsb_kepler_tick_async: no state loaded for this kind");
+    VSB_TRY(reserve_curves(*k));
+    if (kind == VSB_KIND_VESSEL) {
+        VSB_CHECK(k->ref_pos != nullptr, VSB_ERR_STATE,
+                  "vsb_kepler_tick_async(VESSEL): parent positions not resident");
+        return vsb_launch_vessel_tick(c, *k, warp, (double *)k->curves.p);
+    }
+    VSB_TRY(vsb_launch_kepler_move(c, *k, warp));
+    return vsb_launch_kepler_curves(c, *k, 0, k->n, (double *)k->curves.p, 1);
+}
+
+extern "C" int vsb_kepler_curves_get(vsb_ctx *c, int kind, int64_t first, int64_t count,
+                                     double *out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_curves_get", kind, &k));
+    VSB_CHECK(k->n > 0 && k->curves.p, VSB_ERR_STATE,
+              "vsb_kepler_curves_get: no curves generated yet");
+    VSB_CHECK(first >= 0 && count >= 0 && first + count <= k->n && (out || count == 0), VSB_ERR_ARG,
+              "vsb_kepler_curves_get: objects [%lld,%lld) outside [0,%lld)", (long long)first,
+              (long long)(first + count), (long long)k->n);
+    const size_t stride = 16 * (size_t)k->P;
+    return d2h(c, out, (char *)k->curves.p + stride * first, stride * count);
+}
+
+extern "C" int vsb_kepler_curves_device_ptr(vsb_ctx *c, int kind, void **out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_curves_device_ptr", kind, &k));
+    VSB_CHECK(out && k->curves.p, VSB_ERR_STATE, "vsb_kepler_curves_device_ptr: no curves yet");
+    *out = k->curves.p;
+    return VSB_OK;
+}
+
+extern "C" int vsb_kepler_free(vsb_ctx *c, int kind)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_free", kind, &k));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    free_kepler(*k);
+    return VSB_OK;
+}

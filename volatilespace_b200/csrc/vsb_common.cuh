@@ -1,0 +1,220 @@
+// vsb_common.cuh -- shared device/host helpers for libvsb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vsb200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libvsb200 is written for sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------- errors
+void vsb_set_error(const char *fmt, ...);
+
+#define VSB_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            vsb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,              \
+                          cudaGetErrorString(e__));                                 \
+            return VSB_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define VSB_CHECK(cond, code, ...)                                                  \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            vsb_set_error(__VA_ARGS__);                                             \
+            return (code);                                                          \
+        }                                                                           \
+    } while (0)
+
+#define VSB_TRY(expr)                                                               \
+    do {                                                                            \
+        int r__ = (expr);                                                           \
+        if (r__ != VSB_OK) return r__;                                              \
+    } while (0)
+
+// ---------------------------------------------------------------- context
+// All body arrays are padded to a multiple of VSB_PAD entries; padding rows hold
+// mass 0 and a far-away position so pair kernels can run whole tiles unmasked.
+#define VSB_PAD 1024
+#define VSB_FAR 3.0e150
+
+struct vsb_buf {
+    void *p = nullptr;
+    size_t cap = 0;  // bytes
+};
+
+struct vsb_kepler_state {
+    int64_t n = 0, npad = 0, P = 0, nref = 0;
+    int kind = 0;  // VSB_KIND_BODY / VSB_KIND_VESSEL
+    double *a = nullptr, *b = nullptr, *f = nullptr, *ecc = nullptr, *pea = nullptr,
+           *nmot = nullptr, *dr = nullptr, *ma = nullptr, *ea = nullptr, *pos = nullptr;
+    int64_t *ref = nullptr;
+    double *ref_pos = nullptr;      // (nref,2) parent-body positions (vessel kind)
+    int ref_pos_borrowed = 0;       // ref_pos aliases the BODY state's pos (not owned)
+    int64_t *h_ref = nullptr;       // host copy of ref (level computation)
+    double *tab = nullptr;          // 4*P: cos t, sin t, cosh t, sinh t
+    double *pr = nullptr;           // (n,2) relative position scratch (body kind)
+    int64_t *lvl_idx = nullptr;     // body kind: bodies grouped by dependency level
+    int64_t nlevels = 0;
+    int64_t lvl_off[66] = {0};
+    vsb_buf curves;                 // (n,P,2) moved curves, device resident
+    vsb_buf quirk_idx;              // compacted ENRKE quirk-branch indices
+    size_t bytes_alloc = 0;
+};
+
+struct vsb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+
+    // body-sim state
+    int64_t n = 0, npad = 0, cap = 0;
+    int64_t row0 = 0, row1 = 0;  // target rows owned by this rank
+    double *mass = nullptr, *den = nullptr, *rad = nullptr, *coi = nullptr;
+    double *pos = nullptr, *vel = nullptr, *rel_vel = nullptr, *acc = nullptr;
+    int64_t *parents = nullptr, *parents_old = nullptr;
+    double *focus = nullptr, *ecc_v = nullptr, *semi_major = nullptr, *semi_minor = nullptr,
+           *periapsis_arg = nullptr;
+
+    // scratch
+    vsb_buf part;        // all-pairs partial sums [C][rows][2]
+    vsb_buf order;       // int64 order (descending mass) + rank
+    vsb_buf sorted;      // sorted-source staging for find_parents
+    vsb_buf scratch;     // generic
+    vsb_buf host_stage;  // device staging for the stateless host-buffer calls
+    unsigned long long *d_key = nullptr;   // collision key (device)
+    unsigned long long *h_key = nullptr;   // pinned mirror
+    double *h_pin = nullptr;               // pinned scratch (small)
+    size_t h_pin_bytes = 0;
+
+    vsb_kepler_state kep[2];
+};
+
+int vsb_buf_reserve(vsb_buf &b, size_t bytes);
+void vsb_buf_free(vsb_buf &b);
+
+static inline int64_t vsb_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    // make the inits visible to the async (TMA) proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1-D TMA bulk copy global -> shared (SASS: UBLKCP), completion on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                             uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// MUFU.RSQ64H: ~2^-22 relative seed for x^-1/2 (low word zero).
+__device__ __forceinline__ double rsqrt_seed(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
+__device__ __forceinline__ long long warp_max_i64(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------- internal launchers
+// gravity (vsb_gravity.cu)
+int vsb_launch_allpairs_accel(vsb_ctx *c, double gc);
+int vsb_launch_allpairs_integrate(vsb_ctx *c);
+int vsb_launch_allpairs_reduce(vsb_ctx *c, double gc, int integrate);
+int vsb_launch_dfma_peak(vsb_ctx *c, int iters, int blocks, float *ms_out);
+int vsb_allpairs_chunks(int64_t n, int64_t *chunk_out);
+// pair predicates (vsb_pairs.cu)
+int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order);
+int vsb_launch_check_collision(vsb_ctx *c);
+// editor step pieces (vsb_editor.cu)
+int vsb_launch_gravity_ref(vsb_ctx *c, double gc, const int64_t *d_order);
+int vsb_launch_kepler_basic(vsb_ctx *c, double gc, double coi_coef);
+int vsb_launch_simplified_orbit_coi(vsb_ctx *c, double gc, double coi_coef,
+                                    const int64_t *d_order);
+int vsb_launch_delete_row(vsb_ctx *c, int64_t row);
+int vsb_launch_swap_rows(vsb_ctx *c, int64_t a, int64_t b);
+int vsb_launch_translate(vsb_ctx *c, int64_t ref_row);
+int vsb_launch_pad_tail(vsb_ctx *c);
+int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double *d_out);
+// kepler (vsb_kepler.cu)
+int vsb_launch_kepler_move(vsb_ctx *c, vsb_kepler_state &k, double warp);
+int vsb_launch_kepler_curves(vsb_ctx *c, vsb_kepler_state &k, int64_t first, int64_t count,
+                             double *d_out, int translate);
+int vsb_launch_solve_ell(vsb_ctx *c, int64_t n, const double *ecc, const double *ma, double tol,
+                         double *out);
+int vsb_launch_solve_hyp(vsb_ctx *c, int64_t n, const double *ecc, const double *ma,
+                         const double *guess, double *out);
+int vsb_launch_curve_move_to(vsb_ctx *c, int64_t n, int64_t P, const double *curves,
+                             const double *body_pos, const int64_t *ref, const double *f,
+                             const double *pea, double *out);

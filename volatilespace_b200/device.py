@@ -1,0 +1,279 @@
+"""Thin object layer over the C ABI: one `Device` per GPU context.
+
+Nothing here computes physics; every method forwards numpy buffers to
+libvsb200.so (see include/vsb200.h) and raises VsbError on failure.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (F_ACC, F_COI, F_DEN, F_MASS, F_PARENTS, F_POS, F_RAD, F_REL_VEL, F_VEL,
+                   KIND_BODY, KIND_VESSEL, check, f64, i64, ptr)
+
+_default = None
+
+
+def default_device():
+    """Process-wide context on cuda:LOCAL_RANK (cuda:0 when not distributed)."""
+    global _default
+    if _default is None:
+        import os
+        _default = Device(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default
+
+
+class Device:
+    def __init__(self, device=0):
+        self.L = _lib.load()
+        self.index = int(device)
+        h = C.c_void_p()
+        check(self.L.vsb_ctx_create(self.index, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vsb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------ misc
+    def sync(self):
+        check(self.L.vsb_ctx_sync(self.h))
+
+    def stream_handle(self):
+        s = C.c_void_p()
+        check(self.L.vsb_ctx_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def kernel_launches(self):
+        n = C.c_int64()
+        check(self.L.vsb_ctx_kernel_launches(self.h, C.byref(n)))
+        return n.value
+
+    def fp64_peak(self):
+        """(FLOP/s, DFMA lane-ops/s) measured by a DFMA-chain microbenchmark."""
+        a, b = C.c_double(), C.c_double()
+        check(self.L.vsb_measure_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ------------------------------------------------------------ body-sim state
+    def bodies_resize(self, n):
+        check(self.L.vsb_bodies_resize(self.h, int(n)))
+
+    def bodies_count(self):
+        n = C.c_int64()
+        check(self.L.vsb_bodies_count(self.h, C.byref(n)))
+        return n.value
+
+    def set(self, field, arr, first=0):
+        w = _lib.BODY_FIELD_WIDTH[field]
+        a = i64(arr) if field == F_PARENTS else f64(arr)
+        count = a.size // w
+        check(self.L.vsb_bodies_set(self.h, field, ptr(a), int(first), count))
+
+    def get(self, field, first=0, count=None, out=None):
+        w = _lib.BODY_FIELD_WIDTH[field]
+        if count is None:
+            count = self.bodies_count() - first
+        dt = np.int64 if field == F_PARENTS else np.float64
+        if out is None:
+            out = np.empty((count, 2) if w == 2 else (count,), dtype=dt)
+        assert out.dtype == dt and out.flags.c_contiguous and out.size == count * w
+        check(self.L.vsb_bodies_get(self.h, field, ptr(out), int(first), int(count)))
+        return out
+
+    def device_ptr(self, field):
+        p = C.c_void_p()
+        check(self.L.vsb_bodies_device_ptr(self.h, field, C.byref(p)))
+        return p.value
+
+    def set_rows(self, row0, row1):
+        check(self.L.vsb_bodies_set_rows(self.h, int(row0), int(row1)))
+
+    def upload_bodies(self, mass, pos, vel=None, rad=None, coi=None, rel_vel=None, den=None,
+                      parents=None):
+        n = len(mass)
+        self.bodies_resize(n)
+        self.set(F_MASS, mass)
+        self.set(F_POS, pos)
+        for field, arr in ((F_VEL, vel), (F_RAD, rad), (F_COI, coi), (F_REL_VEL, rel_vel),
+                           (F_DEN, den), (F_PARENTS, parents)):
+            if arr is not None:
+                self.set(field, arr)
+
+    def find_parents(self, order, want=True):
+        order = i64(order)
+        out = np.empty(len(order), dtype=np.int64) if want else None
+        check(self.L.vsb_find_parents(self.h, ptr(order), ptr(out)))
+        return out
+
+    def gravity_ref(self, gc, order):
+        order = i64(order)
+        check(self.L.vsb_gravity_ref(self.h, float(gc), ptr(order)))
+
+    def allpairs_accel(self, gc):
+        check(self.L.vsb_allpairs_accel(self.h, float(gc)))
+
+    def allpairs_integrate(self):
+        check(self.L.vsb_allpairs_integrate(self.h))
+
+    def allpairs_step(self, gc, nsteps=1):
+        check(self.L.vsb_allpairs_step(self.h, float(gc), int(nsteps)))
+
+    def allpairs_tick_async(self, gc):
+        check(self.L.vsb_allpairs_tick_async(self.h, float(gc)))
+
+    def kepler_basic(self, gc, coi_coef):
+        check(self.L.vsb_kepler_basic(self.h, float(gc), float(coi_coef)))
+
+    def simplified_orbit_coi(self, gc, coi_coef, order):
+        order = i64(order)
+        largest = C.c_int64()
+        check(self.L.vsb_simplified_orbit_coi(self.h, float(gc), float(coi_coef), ptr(order),
+                                              C.byref(largest)))
+        return largest.value
+
+    def check_collision(self):
+        d, a = C.c_int64(), C.c_int64()
+        check(self.L.vsb_check_collision(self.h, C.byref(d), C.byref(a)))
+        if d.value < 0:
+            return None, None
+        return d.value, a.value
+
+    def delete_row(self, row):
+        check(self.L.vsb_delete_row(self.h, int(row)))
+
+    def swap_rows(self, a, b):
+        check(self.L.vsb_swap_rows(self.h, int(a), int(b)))
+
+    def translate_to(self, row):
+        check(self.L.vsb_translate_to(self.h, int(row)))
+
+    def editor_curve(self, P, ell_t, par_t):
+        n = self.bodies_count()
+        out = np.empty((2, n, int(P)))
+        ell_t, par_t = f64(ell_t), f64(par_t)
+        check(self.L.vsb_editor_curve(self.h, int(P), ptr(ell_t), ptr(par_t), ptr(out)))
+        return out
+
+    # ------------------------------------------------------------ host-buffer calls
+    def host_allpairs_step(self, mass, pos, vel, gc, nsteps=1):
+        """In place on pos / vel (must be C-contiguous float64)."""
+        assert pos.dtype == np.float64 and pos.flags.c_contiguous
+        assert vel.dtype == np.float64 and vel.flags.c_contiguous
+        mass = f64(mass)
+        check(self.L.vsb_host_allpairs_step(self.h, len(mass), ptr(mass), ptr(pos), ptr(vel),
+                                            float(gc), int(nsteps)))
+
+    def host_allpairs_accel(self, mass, pos, gc):
+        mass, pos = f64(mass), f64(pos)
+        acc = np.empty((len(mass), 2))
+        check(self.L.vsb_host_allpairs_accel(self.h, len(mass), ptr(mass), ptr(pos), float(gc),
+                                             ptr(acc)))
+        return acc
+
+    def host_find_parents(self, order, pos, coi):
+        order, pos, coi = i64(order), f64(pos), f64(coi)
+        out = np.empty(len(order), dtype=np.int64)
+        check(self.L.vsb_host_find_parents(self.h, len(order), ptr(order), ptr(pos), ptr(coi),
+                                           ptr(out)))
+        return out
+
+    def host_check_collision(self, mass, pos, rad):
+        mass, pos, rad = f64(mass), f64(pos), f64(rad)
+        d, a = C.c_int64(), C.c_int64()
+        check(self.L.vsb_host_check_collision(self.h, len(mass), ptr(mass), ptr(pos), ptr(rad),
+                                              C.byref(d), C.byref(a)))
+        if d.value < 0:
+            return None, None
+        return d.value, a.value
+
+    def host_solve_kepler_ell(self, ecc, ma, tol=1e-10):
+        ecc, ma = np.broadcast_arrays(f64(ecc), f64(ma))
+        ecc, ma = f64(ecc), f64(ma)
+        out = np.empty(ecc.shape)
+        check(self.L.vsb_host_solve_kepler_ell(self.h, ecc.size, ptr(ecc), ptr(ma), float(tol),
+                                               ptr(out)))
+        return out
+
+    def host_newton_root_kepler_hyp(self, ecc, ma, guess):
+        ecc, ma, guess = (f64(x) for x in np.broadcast_arrays(f64(ecc), f64(ma), f64(guess)))
+        out = np.empty(ecc.shape)
+        check(self.L.vsb_host_newton_root_kepler_hyp(self.h, ecc.size, ptr(ecc), ptr(ma),
+                                                     ptr(guess), ptr(out)))
+        return out
+
+    def host_curve_points(self, ecc, a, b, pea, t):
+        ecc, a, b, pea, t = (f64(np.atleast_1d(x)) for x in (ecc, a, b, pea, t))
+        out = np.empty((len(a), len(t), 2))
+        check(self.L.vsb_host_curve_points(self.h, len(a), len(t), ptr(ecc), ptr(a), ptr(b),
+                                           ptr(pea), ptr(t), ptr(out)))
+        return out
+
+    def host_curve_move_to(self, curves, body_pos, ref, f, pea):
+        curves, body_pos, ref, f, pea = f64(curves), f64(body_pos), i64(ref), f64(f), f64(pea)
+        out = np.empty_like(curves)
+        check(self.L.vsb_host_curve_move_to(self.h, curves.shape[0], curves.shape[1],
+                                            len(body_pos), ptr(curves), ptr(body_pos), ptr(ref),
+                                            ptr(f), ptr(pea), ptr(out)))
+        return out
+
+    # ------------------------------------------------------------ Kepler state
+    def kepler_load(self, kind, P, a, b, f, ecc, pea, n, dr, ma, ea, ref, t=None):
+        arrs = [f64(x) for x in (a, b, f, ecc, pea, n, dr, ma, ea)]
+        ref = i64(ref)
+        t = np.linspace(-np.pi, np.pi, int(P)) if t is None else f64(t)
+        check(self.L.vsb_kepler_load(self.h, kind, len(arrs[0]), int(P), *[ptr(x) for x in arrs],
+                                     ptr(ref), ptr(t)))
+
+    def kepler_set_order(self, order):
+        order = i64(order)
+        check(self.L.vsb_kepler_set_order(self.h, ptr(order)))
+
+    def kepler_set(self, kind, field, arr, first=0):
+        a = i64(arr) if field == _lib.K_REF else f64(arr)
+        w = 2 if field == _lib.K_POS else 1
+        check(self.L.vsb_kepler_set(self.h, kind, field, ptr(a), int(first), a.size // w))
+
+    def kepler_get(self, kind, field, count, first=0, out=None):
+        w = 2 if field == _lib.K_POS else 1
+        dt = np.int64 if field == _lib.K_REF else np.float64
+        if out is None:
+            out = np.empty((count, 2) if w == 2 else (count,), dtype=dt)
+        check(self.L.vsb_kepler_get(self.h, kind, field, ptr(out), int(first), int(count)))
+        return out
+
+    def kepler_move(self, kind, warp, body_pos=None):
+        bp = None if body_pos is None else f64(body_pos)
+        check(self.L.vsb_kepler_move(self.h, kind, float(warp), ptr(bp),
+                                     0 if bp is None else len(bp)))
+
+    def kepler_curves(self, kind):
+        check(self.L.vsb_kepler_curves(self.h, kind))
+
+    def kepler_tick(self, kind, warp, body_pos=None):
+        bp = None if body_pos is None else f64(body_pos)
+        check(self.L.vsb_kepler_tick(self.h, kind, float(warp), ptr(bp),
+                                     0 if bp is None else len(bp)))
+
+    def kepler_tick_async(self, kind, warp):
+        check(self.L.vsb_kepler_tick_async(self.h, kind, float(warp)))
+
+    def kepler_curves_get(self, kind, first, count, P, out=None):
+        if out is None:
+            out = np.empty((count, P, 2))
+        check(self.L.vsb_kepler_curves_get(self.h, kind, int(first), int(count), ptr(out)))
+        return out
+
+    def kepler_free(self, kind):
+        check(self.L.vsb_kepler_free(self.h, kind))
+
+
+__all__ = ["Device", "default_device", "KIND_BODY", "KIND_VESSEL", "F_MASS", "F_POS", "F_VEL",
+           "F_RAD", "F_COI", "F_REL_VEL", "F_ACC", "F_DEN", "F_PARENTS"]

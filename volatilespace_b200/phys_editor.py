@@ -1,0 +1,384 @@
+"""Drop-in for volatilespace/physics/phys_editor.py's hot path on a B200.
+
+`Physics` keeps the reference's method names, argument meaning and return
+conventions (phys_editor.py:112-857) so editor.py can bind
+`physics = volatilespace_b200.phys_editor.Physics()` instead of the numba class;
+the O(N^2) loops (find_parents, check_collision, simplified_orbit_coi) and the
+per-tick O(N) kernels run in libvsb200.so.  `AllPairsPhysics` is the north-star
+MODE_ALLPAIRS variant (documentation/orbital-physics/01-complex-orbit-model.txt).
+
+Host numpy arrays with the reference's attribute names mirror the device state:
+hot calls refresh them IN PLACE (callers hold aliases between calls,
+editor.py:1517) -- eagerly by default, or on `pull()` with sync="lazy".
+There is no CPU fallback: constructing a Physics without the CUDA library or
+without a GPU raises.
+"""
+import numpy as np
+
+from . import _lib
+from ._lib import (F_ACC, F_COI, F_DEN, F_ECC_V, F_FOCUS, F_MASS, F_PARENTS, F_PERIAPSIS_ARG,
+                   F_POS, F_RAD, F_REL_VEL, F_SEMI_MAJOR, F_SEMI_MINOR, F_VEL)
+from .device import Device, default_device
+
+_FIELDS = {"mass": F_MASS, "den": F_DEN, "rad": F_RAD, "coi": F_COI, "pos": F_POS, "vel": F_VEL,
+           "rel_vel": F_REL_VEL, "parents": F_PARENTS, "focus": F_FOCUS, "ecc_v": F_ECC_V,
+           "semi_major": F_SEMI_MAJOR, "semi_minor": F_SEMI_MINOR,
+           "periapsis_arg": F_PERIAPSIS_ARG}
+_WIDE = ("pos", "vel", "rel_vel", "ecc_v")
+
+DEFAULT_CONF = {"gc": 1.0, "rad_mult": 179.0, "mass_thermal_mult": 2e26, "coi_coef": 0.7,
+                "vessel_scale": 0.1, "min_planet_mass": 200}   # defaults.py:58-65
+
+
+def mass_order(mass):
+    """np.argsort(mass)[-1::-1], phys_editor.py:353,375 (host numpy)."""
+    return np.ascontiguousarray(np.argsort(mass)[-1::-1], dtype=np.int64)
+
+
+def body_radius(mass, den, rad_mult):
+    """phys_editor.py:580-581; stays on the host so `rad` is bit-identical to the
+    reference's np.cbrt path (it feeds the bit-exact collision predicate)."""
+    volume = mass / den
+    return rad_mult * np.cbrt(3 * volume / (4 * np.pi))
+
+
+class _DeviceBodies:
+    """Shared plumbing: host mirrors <-> device fields."""
+
+    def __init__(self, device=None, sync="eager"):
+        assert sync in ("eager", "lazy")
+        self.dev = device if isinstance(device, Device) else (
+            default_device() if device is None else Device(device))
+        self.sync = sync
+        self._stale = set()        # host mirrors older than the device copy
+
+    def _alloc_host(self, n):
+        for name in _FIELDS:
+            if name == "parents":
+                arr = np.zeros(n, dtype=np.int64)
+            elif name in _WIDE:
+                arr = np.zeros((n, 2))
+            else:
+                arr = np.zeros(n)
+            setattr(self, name, arr)
+
+    def _push(self, *names):
+        for name in names or _FIELDS:
+            self.dev.set(_FIELDS[name], getattr(self, name))
+            self._stale.discard(name)
+
+    def pull(self, *names):
+        """Refresh host mirrors in place from the device."""
+        for name in names or tuple(self._stale):
+            self.dev.get(_FIELDS[name], out=getattr(self, name))
+            self._stale.discard(name)
+
+    def _touched(self, *names):
+        self._stale.update(names)
+        if self.sync == "eager":
+            self.pull(*names)
+
+    def _row(self, name, i):
+        """Current value of one row (device is authoritative when the mirror is stale)."""
+        if name in self._stale:
+            return self.dev.get(_FIELDS[name], first=int(i), count=1)[0]
+        return getattr(self, name)[i]
+
+    def _set_row(self, name, i, value):
+        arr = getattr(self, name)
+        if name not in self._stale:
+            arr[i] = value
+        v = np.ascontiguousarray(value, dtype=arr.dtype).reshape(-1)
+        self.dev.set(_FIELDS[name], v, first=int(i))
+
+    def _delete_host_row(self, i):
+        for name in _FIELDS:
+            setattr(self, name, np.delete(getattr(self, name), i, axis=0))
+
+
+class Physics(_DeviceBodies):
+    """Editor physics class (MODE_REF: the reference's parent/COI model)."""
+
+    def __init__(self, device=None, sync="eager", curve_points=300):
+        super().__init__(device, sync)
+        self.gc = DEFAULT_CONF["gc"]
+        self.rad_mult = DEFAULT_CONF["rad_mult"]
+        self.mass_thermal_mult = DEFAULT_CONF["mass_thermal_mult"]
+        self.coi_coef = DEFAULT_CONF["coi_coef"]
+        self.min_mass = DEFAULT_CONF["min_planet_mass"]
+        self.largest = 0
+        self.names = np.array([])
+        self._alloc_host(0)
+        self.reload_settings(curve_points)
+
+    # phys_editor.py:152-157
+    def reload_settings(self, curve_points=None):
+        if curve_points is not None:
+            self.curve_points = int(curve_points)
+        self.ell_t = np.linspace(-np.pi, np.pi, self.curve_points)
+        self.par_t = np.linspace(-np.pi - 1, np.pi + 1, self.curve_points)
+
+    # phys_editor.py:160-166
+    def load_conf(self, conf):
+        self.gc = conf["gc"]
+        self.rad_mult = conf["rad_mult"]
+        self.mass_thermal_mult = conf.get("mass_thermal_mult", self.mass_thermal_mult)
+        self.coi_coef = conf["coi_coef"]
+        self.min_mass = conf.get("min_planet_mass", self.min_mass)
+
+    # phys_editor.py:169-201
+    def load_system(self, conf, body_data, body_orb_data):
+        self.load_conf(conf)
+        mass = np.array(body_data["mass"], dtype=np.float64)
+        n = len(mass)
+        self.names = body_data.get("name", np.array(["body%d" % i for i in range(n)]))
+        self._alloc_host(n)
+        self.mass[:] = mass
+        self.den[:] = body_data["den"]
+        self.rad[:] = body_radius(self.mass, self.den, self.rad_mult)
+        self.pos[:] = body_orb_data["pos"]
+        self.vel[:] = body_orb_data["vel"]
+        self._stale.clear()
+        self.dev.bodies_resize(n)
+        self._push()
+        self.simplified_orbit_coi()
+        self.find_parents()
+        self.pull("parents")
+        self.rel_vel[:] = self.vel - self.vel[self.parents]
+        self._push("rel_vel")
+        self.body()
+
+    # phys_editor.py:325-346
+    def simplified_orbit_coi(self):
+        self.largest = self.dev.simplified_orbit_coi(self.gc, self.coi_coef,
+                                                     mass_order(self.mass))
+        self._touched("coi")
+
+    # phys_editor.py:350-354
+    def find_parents(self):
+        self.dev.find_parents(mass_order(self.mass), want=False)
+        self._touched("parents")
+
+    # phys_editor.py:357-378
+    def gravity(self):
+        self.dev.gravity_ref(self.gc, mass_order(self.mass))
+        self._touched("parents", "rel_vel", "vel", "pos")
+
+    # phys_editor.py:577-599 (radius; the thermal/atmosphere part is UI data, out of scope)
+    def body(self):
+        rad = body_radius(self.mass, self.den, self.rad_mult)
+        if not np.array_equal(rad, self.rad):
+            self.rad[:] = rad
+            self._push("rad")
+
+    # phys_editor.py:547-551
+    def check_collision(self):
+        return self.dev.check_collision()
+
+    # phys_editor.py:381-384
+    def kepler_basic(self):
+        self.dev.kepler_basic(self.gc, self.coi_coef)
+        self._touched("focus", "ecc_v", "semi_major", "semi_minor", "periapsis_arg", "coi")
+
+    # phys_editor.py:519-544  -> ndarray (2, N, P)
+    def curve(self):
+        return self.dev.editor_curve(self.curve_points, self.ell_t, self.par_t)
+
+    # phys_editor.py:554-565
+    def inelastic_collision(self):
+        body_del, body_add = self.check_collision()
+        if body_del is not None:
+            mass_r = self.mass[body_del] + self.mass[body_add]
+            mom1 = self._row("vel", body_add) * self.mass[body_add]
+            mom2 = self._row("vel", body_del) * self.mass[body_del]
+            velr = (mom1 + mom2) / mass_r
+            parent = int(self._row("parents", body_add))
+            self._set_row("rel_vel", body_add, velr - self._row("rel_vel", parent))
+            self.set_body_mass(body_add, mass_r)
+            self.del_body(body_del)
+        return body_del
+
+    # phys_editor.py:844-857
+    def set_body_mass(self, body, mass):
+        self._set_row("mass", body, mass)
+        old_largest = int(self.largest)
+        self.find_parents()
+        self.simplified_orbit_coi()
+        if self.largest != old_largest:
+            self._reroot(old_largest)
+
+    def _reroot(self, old_largest):
+        """:848-857 / :279-289: new root to the origin, first row."""
+        self.dev.translate_to(self.largest)
+        self._touched("pos")
+        if old_largest is not None:
+            self._set_row("rel_vel", old_largest, self._row("rel_vel", self.largest) * -1)
+        self._set_row("vel", self.largest, np.zeros(2))
+        if self.largest != 0:
+            self.set_root(self.largest)
+
+    # phys_editor.py:293-313
+    def set_root(self, body):
+        self.dev.swap_rows(0, body)
+        for name in ("mass", "den", "rad"):
+            arr = getattr(self, name)
+            arr[0], arr[body] = arr[body], arr[0]
+        if len(self.names) > body:
+            self.names[0], self.names[body] = self.names[body], self.names[0]
+        self._touched("pos", "vel", "rel_vel", "parents")
+        self.simplified_orbit_coi()
+        self.find_parents()
+        self.largest = 0
+
+    # phys_editor.py:250-290
+    def del_body(self, delete):
+        if len(self.mass) > 1:
+            self.pull()                      # bring every mirror up to date, then drop the row
+            self.dev.delete_row(delete)
+            self._delete_host_row(delete)
+            if len(self.names) > delete:
+                self.names = np.delete(self.names, delete)
+            self.simplified_orbit_coi()
+            self.find_parents()
+            if self.largest == delete:
+                self.find_parents()
+                self.simplified_orbit_coi()
+                self.dev.translate_to(self.largest)
+                self._touched("pos")
+                self._set_row("vel", self.largest, np.zeros(2))
+                if self.largest != 0:
+                    self.set_root(self.largest)
+            return 0
+        return 1
+
+    # phys_editor.py:204-247
+    def add_body(self, data):
+        self.pull()
+        old_largest = int(self.largest)
+        n = len(self.mass) + 1
+        old = {name: getattr(self, name) for name in _FIELDS}
+        self._alloc_host(n)
+        for name, arr in old.items():
+            getattr(self, name)[:n - 1] = arr
+        self.names = np.append(self.names, data.get("name", "body%d" % (n - 1)))
+        self.mass[-1] = data["mass"]
+        self.den[-1] = data["density"]
+        self.rad[:] = body_radius(self.mass, self.den, self.rad_mult)
+        self.pos[-1] = data["position"]
+        self.dev.bodies_resize(n)
+        self._push()
+        self.simplified_orbit_coi()
+        self.find_parents()
+        self._set_row("rel_vel", n - 1, np.asarray(data["velocity"], dtype=np.float64))
+        if data["mass"] > self.mass[old_largest]:
+            self.largest = n - 1
+            self._reroot(old_largest)
+        self.pull()
+        for body in mass_order(self.mass):       # :245-247
+            self.vel[body] = self.rel_vel[body] + self.vel[self.parents[body]]
+        self._push("vel")
+
+    # phys_editor.py:860-880 (mutators used by the editor UI)
+    def set_body_den(self, body, density):
+        self._set_row("den", body, max(density, 0.05))
+        self.simplified_orbit_coi()
+
+    def set_body_pos(self, body, position):
+        self._set_row("pos", body, np.asarray(position, dtype=np.float64))
+        self.simplified_orbit_coi()
+
+    def set_body_vel(self, body, velocity):
+        parent = int(self._row("parents", body))
+        self._set_row("rel_vel", body,
+                      np.asarray(velocity, dtype=np.float64) - self._row("vel", parent))
+        self.simplified_orbit_coi()
+
+    # phys_editor.py:819-841
+    def get_bodies(self):
+        self.pull()
+        return self.names, self.mass, self.den, self.pos, self.vel, self.rad
+
+    def get_body_orbits(self):
+        self.pull()
+        return self.semi_major, self.semi_minor, self.coi, self.parents
+
+    def frame(self, warp=1):
+        """One editor frame exactly as editor.py:1503-1523 sequences it."""
+        deleted = []
+        for _ in range(warp):
+            self.gravity()
+            self.body()
+            d = self.inelastic_collision()
+            if d is not None:
+                deleted.append(int(d))
+        self.kepler_basic()
+        return deleted
+
+
+class AllPairsPhysics(_DeviceBodies):
+    """MODE_ALLPAIRS: every body attracts every other body
+    (documentation/orbital-physics/01-complex-orbit-model.txt:4-12), integrator
+    v += a; P += v, collisions as check_collision (phys_editor.py:547-551) with the
+    documented inelastic merge (documentation/orbital-physics/09-collisions.txt:3-6).
+    Same call sequence as the editor: gravity(); body(); inelastic_collision()."""
+
+    def __init__(self, device=None, sync="lazy"):
+        super().__init__(device, sync)
+        self.gc, self.rad_mult = 1.0, 179.0
+        self._alloc_host(0)
+
+    def load_system(self, conf, body_data, body_orb_data):
+        self.gc, self.rad_mult = conf["gc"], conf["rad_mult"]
+        mass = np.array(body_data["mass"], dtype=np.float64)
+        n = len(mass)
+        self._alloc_host(n)
+        self.mass[:] = mass
+        self.den[:] = body_data["den"]
+        self.rad[:] = body_radius(self.mass, self.den, self.rad_mult)
+        self.pos[:] = body_orb_data["pos"]
+        self.vel[:] = body_orb_data["vel"]
+        self._stale.clear()
+        self.dev.bodies_resize(n)
+        self._push("mass", "den", "rad", "pos", "vel")
+
+    def gravity(self, nsteps=1):
+        self.dev.allpairs_step(self.gc, nsteps)
+        self._touched("pos", "vel")
+
+    def acceleration(self):
+        self.dev.allpairs_accel(self.gc)
+        return self.dev.get(F_ACC)
+
+    def body(self):
+        rad = body_radius(self.mass, self.den, self.rad_mult)
+        if not np.array_equal(rad, self.rad):
+            changed = np.nonzero(rad != self.rad)[0]
+            self.rad[:] = rad
+            if len(changed) <= 4:
+                for i in changed:
+                    self.dev.set(F_RAD, self.rad[i:i + 1], first=int(i))
+            else:
+                self._push("rad")
+
+    def check_collision(self):
+        return self.dev.check_collision()
+
+    def inelastic_collision(self):
+        body_del, body_add = self.check_collision()
+        if body_del is None:
+            return None
+        mass_r = self.mass[body_del] + self.mass[body_add]
+        velr = (self._row("vel", body_add) * self.mass[body_add]
+                + self._row("vel", body_del) * self.mass[body_del]) / mass_r
+        self._set_row("vel", body_add, velr)
+        self._set_row("mass", body_add, mass_r)
+        self.dev.delete_row(body_del)
+        stale = set(self._stale)
+        self._delete_host_row(body_del)
+        self._stale = stale
+        return body_del, body_add
+
+    def tick(self):
+        self.gravity()
+        self.body()
+        return self.inelastic_collision()
