@@ -1,0 +1,52 @@
+"""Small fixed workloads for ncu captures (see profiles/README.md).
+
+    python tools/profile_run.py gravity64k | kepler1m | collision256k | parents64k | editor15
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from volatilespace_b200 import synth  # noqa: E402
+from volatilespace_b200._lib import KIND_VESSEL  # noqa: E402
+from volatilespace_b200.device import Device  # noqa: E402
+
+
+def main():
+    mode = sys.argv[1]
+    dev = Device(0)
+    t0 = time.perf_counter()
+    if mode == "gravity64k":
+        s = synth.plummer2d(65536)
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"])
+        dev.allpairs_step(s["gc"], 6)
+    elif mode == "kepler1m":
+        k = synth.kepler_objects(1 << 20)
+        dev.kepler_load(KIND_VESSEL, 512, k["a"], k["b"], k["f"], k["ecc"], k["pea"], k["n"],
+                        k["dr"], k["ma"], k["ea"], k["ref"])
+        for _ in range(5):
+            dev.kepler_tick(KIND_VESSEL, 1.0, k["body_pos"])
+    elif mode == "collision256k":
+        from volatilespace_b200.phys_editor import body_radius
+        s = synth.collapsing_cluster(262144)
+        rad = body_radius(s["mass"], s["den"], s["rad_mult"]) * 0.01    # no hit: full scan
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"], rad=rad)
+        for _ in range(4):
+            print(dev.check_collision())
+    elif mode == "parents64k":
+        s = synth.plummer2d(65536)
+        coi = np.where(np.arange(65536) % 7 == 0, 3.0e3, 0.0)
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"], coi=coi)
+        order = np.argsort(s["mass"])[-1::-1]
+        for _ in range(4):
+            dev.find_parents(order, want=False)
+    else:
+        raise SystemExit("unknown mode")
+    dev.sync()
+    print(mode, "done in %.3f s, launches %d" % (time.perf_counter() - t0, dev.kernel_launches()))
+
+
+if __name__ == "__main__":
+    main()

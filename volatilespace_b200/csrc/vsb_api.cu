@@ -611,16 +611,17 @@ extern "C" int vsb_host_curve_points(vsb_ctx *c, int64_t n, int64_t P, const dou
               "vsb_host_curve_points: bad argument");
     if (n == 0) return VSB_OK;
     const size_t out_bytes = 16 * (size_t)n * (size_t)P;
-    VSB_TRY(vsb_buf_reserve(c->host_stage, out_bytes + 8 * (4 * (size_t)n + 5 * (size_t)P)));
+    const size_t na = ((size_t)n + 31) / 32 * 32;   // keep every staged array 256-byte aligned
+    VSB_TRY(vsb_buf_reserve(c->host_stage, out_bytes + 8 * (4 * na + 5 * (size_t)P)));
     double *d_out = (double *)c->host_stage.p;
     double *d = (double *)((char *)c->host_stage.p + out_bytes);
     vsb_kepler_state k;
     k.kind = VSB_KIND_VESSEL;
     k.n = n;
     k.P = P;
-    k.ecc = d; k.a = d + n; k.b = d + 2 * n; k.pea = d + 3 * n;
-    k.tab = d + 4 * n;          // 4P doubles
-    double *d_t = d + 4 * n + 4 * P;
+    k.ecc = d; k.a = d + na; k.b = d + 2 * na; k.pea = d + 3 * na;
+    k.tab = d + 4 * na;         // 4P doubles
+    double *d_t = d + 4 * na + 4 * P;
     VSB_CUDA(cudaMemcpyAsync(k.ecc, ecc, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VSB_CUDA(cudaMemcpyAsync(k.a, a, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VSB_CUDA(cudaMemcpyAsync(k.b, b, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
@@ -699,14 +700,17 @@ extern "C" int vsb_kepler_load(vsb_ctx *c, int kind, int64_t n, int64_t P, const
     VSB_CUDA(cudaStreamSynchronize(c->stream));
     free_kepler(*kp);
     vsb_kepler_state &k = *kp;
-    // slab (8-byte words): 9 element arrays + pos(2) + pr(2) + ref + lvl_idx = 15n, tab 4P, t P
-    const size_t words = 15 * (size_t)n + 5 * (size_t)P;
+    // slab (8-byte words): 9 element arrays + pos(2) + pr(2) + ref + lvl_idx = 15n, tab 4P, t P;
+    // every array starts on a 256-byte boundary (double2 / 128-bit accesses)
+    auto al = [](size_t w) { return (w + 31) / 32 * 32; };
+    const size_t words = 11 * al((size_t)n) + 2 * al(2 * (size_t)n) + al(4 * (size_t)P) +
+                         al((size_t)P);
     double *slab = nullptr;
     cudaError_t e = cudaMalloc((void **)&slab, 8 * words);
     VSB_CHECK(e == cudaSuccess, VSB_ERR_NOMEM, "vsb_kepler_load: cudaMalloc -> %s",
               cudaGetErrorString(e));
     size_t o = 0;
-    auto take = [&](size_t w) { double *p = slab + o; o += w; return p; };
+    auto take = [&](size_t w) { double *p = slab + o; o += al(w); return p; };
     k.a = take(n); k.b = take(n); k.f = take(n); k.ecc = take(n); k.pea = take(n);
     k.nmot = take(n); k.dr = take(n); k.ma = take(n); k.ea = take(n);
     k.pos = take(2 * n); k.pr = take(2 * n);
