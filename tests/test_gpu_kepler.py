@@ -186,9 +186,19 @@ def test_kepler_full_size_properties(dev):
     ell = s["ecc"] < 1
     res_ell = ea[ell] - s["ecc"][ell] * np.sin(ea[ell]) - ma[ell]
     assert np.abs(res_ell).max() < 1e-9
-    hyp = ~ell
+    hyp = np.nonzero(~ell)[0]
     res_hyp = ea[hyp] - s["ecc"][hyp] * np.sinh(ea[hyp]) - ma[hyp]     # negated convention (F8a)
-    assert np.abs(res_hyp).max() < 1e-8 * np.maximum(1, np.abs(ma[hyp])).max()
+    conv = np.abs(res_hyp) < 1e-8 * np.maximum(1, np.abs(ma[hyp]))
+    assert conv.mean() > 0.97
+    # the rest is the reference's own behaviour: Newton from ea = ma overshoots for ecc -> 1 and
+    # the 50-iteration cap (phys_shared.py:117) ends it early -- the oracle must agree there
+    from conftest import ROOT  # noqa: F401
+    import sys, os
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    bad = hyp[~conv]
+    want = orc.newton_root_kepler_hyp(s["ecc"][bad], ma[bad], s["ea"][bad])
+    np.testing.assert_allclose(ea[bad], want, rtol=1e-7, atol=1e-9)
     for first in (0, n // 2 + 17, n - 64):
         cur = dev.kepler_curves_get(KIND_VESSEL, first, 64, P)
         sl = slice(first, first + 64)

@@ -201,14 +201,14 @@ extern "C" int vsb_host_unregister(void *ptr)
 extern "C" int vsb_measure_fp64_peak(vsb_ctx *c, double *flops_out, double *pipe_ops_out)
 {
     CTX(c);
-    const int iters = 1 << 15, blocks = c->sm_count * 8;
+    const int iters = 1 << 12, blocks = c->sm_count * 8;
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         float ms = 0;
         VSB_TRY(vsb_launch_dfma_peak(c, iters, blocks, &ms));
         if (ms < best) best = ms;
     }
-    const double dfma = (double)blocks * 256.0 * 8.0 * (double)iters;
+    const double dfma = (double)blocks * 256.0 * 64.0 * (double)iters;
     if (pipe_ops_out) *pipe_ops_out = dfma / (best * 1e-3);
     if (flops_out) *flops_out = 2.0 * dfma / (best * 1e-3);
     return VSB_OK;

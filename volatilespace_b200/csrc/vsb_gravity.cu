@@ -18,6 +18,8 @@
 // fixed order and the partials are reduced in chunk order by the integrate
 // kernel, so the result is bit-identical run to run and under any row sharding
 // across GPUs (each rank computes only its own rows, same order).
+#include <stdlib.h>
+
 #include "vsb_common.cuh"
 
 namespace {
@@ -28,6 +30,12 @@ constexpr int GR_STAGES = 2;
 constexpr int GR_U = 4;        // independent accumulator chains per target
 
 // m_j * |d|^-3 * d accumulated into (ax, ay).  13 FP64-pipe instructions.
+// MASK: tiles that contain the CTA's own target rows can meet i == j (r2 == 0 ->
+// seed = +inf).  There the seed is zeroed by an integer select on its high word (no
+// FP64-pipe cost) and every later product is an exact 0 contribution; all other
+// tiles skip the two integer instructions (the kernel is issue-bound: an FP64
+// instruction holds the dispatch port for two cycles, everything else for one).
+template <bool MASK>
 __device__ __forceinline__ void pair_accum(double xi, double yi, double2 pj, double mj, double &ax,
                                            double &ay)
 {
@@ -35,11 +43,10 @@ __device__ __forceinline__ void pair_accum(double xi, double yi, double2 pj, dou
     double dy = pj.y - yi;
     double r2 = fma(dx, dx, dy * dy);
     double y = rsqrt_seed(r2);
-    // i == j (or coincident bodies): r2 == 0 -> seed = +inf.  Zero the seed with an
-    // integer select on the high word (no FP64-pipe cost); every later product is
-    // then an exact 0 contribution.
-    int hi = __double2hiint(r2);
-    y = __hiloint2double(hi < 0x00100000 ? 0 : __double2hiint(y), 0);
+    if (MASK) {
+        int hi = __double2hiint(r2);
+        y = __hiloint2double(hi < 0x00100000 ? 0 : __double2hiint(y), 0);
+    }
     double t = y * y;
     double e = fma(-r2, t, 1.0);          // e = 1 - r2*y^2  (|e| <~ 2^-21)
     double ym = y * mj;
@@ -49,6 +56,25 @@ __device__ __forceinline__ void pair_accum(double xi, double yi, double2 pj, dou
     double s = fma(y3m, q, y3m);          // m_j * r^-3
     ax = fma(s, dx, ax);
     ay = fma(s, dy, ay);
+}
+
+template <int TPT, bool MASK>
+__device__ __forceinline__ void tile_accum(const double2 *__restrict__ sp,
+                                           const double *__restrict__ sm, const double (&xi)[TPT],
+                                           const double (&yi)[TPT], double (&ax)[TPT][GR_U],
+                                           double (&ay)[TPT][GR_U])
+{
+#pragma unroll 2
+    for (int j = 0; j < GR_TJ; j += GR_U) {
+#pragma unroll
+        for (int u = 0; u < GR_U; ++u) {
+            double2 pj = sp[j + u];
+            double mj = sm[j + u];
+#pragma unroll
+            for (int k = 0; k < TPT; ++k)
+                pair_accum<MASK>(xi[k], yi[k], pj, mj, ax[k][u], ay[k][u]);
+        }
+    }
 }
 
 template <int TPT>
@@ -87,6 +113,9 @@ allpairs_accel_kernel(const double2 *__restrict__ pos, const double *__restrict_
         }
     }
 
+    // global rows this CTA accumulates (for the diagonal-tile test)
+    const int64_t cta_row0 = row0 + (int64_t)blockIdx.x * TPT * GR_BLOCK;
+    const int64_t cta_row1 = cta_row0 + (int64_t)TPT * GR_BLOCK;
     // targets: row = row0 + (blockIdx.x*TPT + k)*BLOCK + tid
     double xi[TPT], yi[TPT];
     double ax[TPT][GR_U], ay[TPT][GR_U];
@@ -105,18 +134,12 @@ allpairs_accel_kernel(const double2 *__restrict__ pos, const double *__restrict_
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % GR_STAGES;
         mbar_wait(&full[s], (uint32_t)(t / GR_STAGES) & 1u);
-        const double2 *sp = spos[s];
-        const double *sm = smass[s];
-#pragma unroll 2
-        for (int j = 0; j < GR_TJ; j += GR_U) {
-#pragma unroll
-            for (int u = 0; u < GR_U; ++u) {
-                double2 pj = sp[j + u];
-                double mj = sm[j + u];
-#pragma unroll
-                for (int k = 0; k < TPT; ++k) pair_accum(xi[k], yi[k], pj, mj, ax[k][u], ay[k][u]);
-            }
-        }
+        // does this tile hold any of the CTA's own target rows (possible i == j)?
+        const int64_t jt = j0 + (int64_t)t * GR_TJ;
+        if (jt < cta_row1 && jt + GR_TJ > cta_row0)
+            tile_accum<TPT, true>(spos[s], smass[s], xi, yi, ax, ay);
+        else
+            tile_accum<TPT, false>(spos[s], smass[s], xi, yi, ax, ay);
         __syncthreads();  // everyone is done with stage s
         if (tid == 0 && t + GR_STAGES < ntiles) {
             const int64_t jn = j0 + (int64_t)(t + GR_STAGES) * GR_TJ;
@@ -182,16 +205,22 @@ __global__ void integrate_only_kernel(int64_t row0, int64_t rows, const double2 
     pos[g] = p;
 }
 
-// DFMA-chain microbenchmark: 8 independent chains per thread, `iters` x 8 DFMA.
+// DFMA-chain microbenchmark: 16 independent chains per thread, `iters` x 64 DFMA.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b)
 {
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
-           x6 = x0 + 6, x7 = x0 + 7;
+    double x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = threadIdx.x + k;
     for (int i = 0; i < iters; ++i) {
-        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = fma(x[k], a, b);
+        }
     }
-    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += x[k];
     if (s == 123.456) out[0] = s;
 }
 
@@ -217,10 +246,22 @@ int vsb_allpairs_chunks(int64_t n, int64_t *chunk_out)
 
 static int targets_per_thread(int64_t rows, int nchunks, int sm_count)
 {
+    // experiments: VSB_GRAVITY_TPT=1|2|4 forces a variant
+    const char *env = getenv("VSB_GRAVITY_TPT");
+    if (env && (env[0] == '1' || env[0] == '2' || env[0] == '4')) return env[0] - '0';
     // two targets per thread halve the LDS traffic; only worth it when the grid
     // still fills the machine several times over
     int64_t ctas2 = ((rows + 2 * GR_BLOCK - 1) / (2 * GR_BLOCK)) * nchunks;
     return ctas2 >= (int64_t)sm_count * 24 ? 2 : 1;
+}
+
+template <int TPT>
+static void launch_accel(vsb_ctx *c, int64_t rows, int64_t chunk, int nchunks)
+{
+    dim3 grid((unsigned)((rows + (int64_t)TPT * GR_BLOCK - 1) / ((int64_t)TPT * GR_BLOCK)),
+              (unsigned)nchunks);
+    allpairs_accel_kernel<TPT><<<grid, GR_BLOCK, 0, c->stream>>>(
+        (const double2 *)c->pos, c->mass, (double2 *)c->part.p, c->row0, rows, chunk, c->npad);
 }
 
 int vsb_launch_allpairs_accel(vsb_ctx *c, double gc)
@@ -232,14 +273,9 @@ int vsb_launch_allpairs_accel(vsb_ctx *c, double gc)
     const int nchunks = vsb_allpairs_chunks(c->n, &chunk);
     VSB_TRY(vsb_buf_reserve(c->part, sizeof(double2) * (size_t)nchunks * (size_t)rows));
     const int tpt = targets_per_thread(rows, nchunks, c->sm_count);
-    dim3 grid((unsigned)((rows + (int64_t)tpt * GR_BLOCK - 1) / ((int64_t)tpt * GR_BLOCK)),
-              (unsigned)nchunks);
-    if (tpt == 2)
-        allpairs_accel_kernel<2><<<grid, GR_BLOCK, 0, c->stream>>>(
-            (const double2 *)c->pos, c->mass, (double2 *)c->part.p, c->row0, rows, chunk, c->npad);
-    else
-        allpairs_accel_kernel<1><<<grid, GR_BLOCK, 0, c->stream>>>(
-            (const double2 *)c->pos, c->mass, (double2 *)c->part.p, c->row0, rows, chunk, c->npad);
+    if (tpt == 4) launch_accel<4>(c, rows, chunk, nchunks);
+    else if (tpt == 2) launch_accel<2>(c, rows, chunk, nchunks);
+    else launch_accel<1>(c, rows, chunk, nchunks);
     c->launches++;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;
