@@ -193,21 +193,29 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
     ms = time_ticks(torch, stream, lambda: dev.allpairs_tick_async(s["gc"]), 16, nobar) / 16
     pairs = 65536 * 65535
     out["plummer64k"] = {"pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms,
-                         "fp64_pipe_frac": pairs * FLOPS_PER_PAIR / (ms * 1e-3) / fp64_ops_peak}
-    # config 5: collision detection at 256k bodies (exact N^2/2 scan, no hit -> worst case)
+                         "fp64_pipe_frac_at_1965mhz": pairs * FLOPS_PER_PAIR / (ms * 1e-3) /
+                         (148 * 64 * 1965e6)}
+    # config 5: collision detection at 256k bodies, first tick of the collapsing cluster and a
+    # no-hit variant (radii / 100: worst case for the exhaustive scan)
     s = synth.collapsing_cluster(262144)
     from volatilespace_b200.phys_editor import body_radius
     rad = body_radius(s["mass"], s["den"], s["rad_mult"])
-    dev.upload_bodies(s["mass"], s["pos"], s["vel"], rad=rad)
-    dev.check_collision()
-    t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
-        hit = dev.check_collision()
-    dt = (time.perf_counter() - t0) / reps
-    out["cluster256k_collision"] = {"bodies_per_s": 262144 / dt, "ms_per_tick": dt * 1e3,
-                                    "first_hit": None if hit[0] is None else list(hit),
-                                    "timing": "host wall clock incl. 16-byte result read-back"}
+    coll = {}
+    for label, r in (("first_tick", rad), ("no_hit", rad * 0.01)):
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"], rad=r)
+        for mode in ("grid", "brute"):
+            os.environ["VSB_COLLISION"] = mode
+            hit = dev.check_collision()
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                hit = dev.check_collision()
+            dt = (time.perf_counter() - t0) / reps
+            coll[label + "_" + mode] = {"ms_per_tick": dt * 1e3, "bodies_per_s": 262144 / dt,
+                                        "pair": None if hit[0] is None else list(hit)}
+    os.environ.pop("VSB_COLLISION", None)
+    coll["timing"] = "host wall clock per vsb_check_collision call incl. result read-back"
+    out["cluster256k_collision"] = coll
     # config 4: 4M Kepler objects + 512-point curves (fused vessel tick), HBM roofline
     n, P = 4194304, 512
     try:
@@ -228,6 +236,30 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
     except Exception as e:   # e.g. not enough free HBM on a shared device
         out["kepler4m"] = {"error": str(e)[:200]}
     return out
+
+
+def roofline(ops, fp64_flops_microbench, clocks, dev, ms_accel, my_pairs):
+    """FP64-pipe roofline of the gravity kernel.  MEASURED_PEAKS.json has no FP64 figure, so the
+    denominator is the pipe's issue peak -- 64 FP64 lanes/SM/clk (what ncu's
+    sm__inst_executed_pipe_fp64 pct_of_peak is normalised to) x SMs x the SM clock observed
+    during the timed region x 2 flop -- or the DFMA-chain microbenchmark of this run if that is
+    higher (it is not: the all-DFMA microbenchmark runs into the power cap)."""
+    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+    sms = 148
+    nominal = sms * 64 * 2 * sm_clock * 1e6
+    peak = max(nominal, fp64_flops_microbench)
+    return {
+        "bound": "fp64", "achieved": ops * 2 / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+        "frac": ops * 2 / peak, "traffic": None, "kernel": "allpairs_accel_kernel",
+        "ms_per_launch": ms_accel,
+        "peak_source": "64 FP64 lanes/SM/clk x 148 SMs x %.0f MHz observed x 2 (issue peak of the "
+                       "FP64 pipe; not in MEASURED_PEAKS.json)" % sm_clock,
+        "dfma_microbench_tflops": fp64_flops_microbench / 1e12,
+        "frac_of_dfma_microbench": ops * 2 / fp64_flops_microbench,
+        "note": "achieved = 13 FP64-pipe instructions per directed pair x pairs/s, each counted "
+                "as one DFMA slot (2 flop)",
+        "flops13_convention_tflops": my_pairs * 13 / (ms_accel * 1e-3) / 1e12,
+    }
 
 
 def run_b200(args):
@@ -325,15 +357,7 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {
-            "bound": "fp64", "achieved": ops * 2 / 1e12, "peak": fp64_flops_peak / 1e12,
-            "unit": "TFLOP/s", "frac": ops / fp64_ops_peak, "traffic": None,
-            "kernel": "allpairs_accel_kernel", "ms_per_launch": ms_accel,
-            "note": "achieved = 13 FP64-pipe instructions per pair x pairs/s, counted as DFMA "
-                    "slots (2 flop); peak = DFMA-chain microbenchmark measured in this run "
-                    "(MEASURED_PEAKS.json has no FP64 figure)",
-            "flops13_convention_tflops": my_pairs * 13 / (ms_accel * 1e-3) / 1e12,
-        },
+        "roofline": roofline(ops, fp64_flops_peak, clocks, dev, ms_accel, my_pairs),
         "peaks_source": peaks_src,
     }
     if not args.no_extra and world == 1:

@@ -137,7 +137,15 @@ def test_find_parents_vs_oracle(dev, oracle, n):
 
 
 # ------------------------------------------------------------------ B1 collisions
-def test_check_collision_golden(dev):
+@pytest.fixture(params=["brute", "grid"])
+def collision_mode(request, monkeypatch):
+    """Both implementations of B1: the exhaustive N^2/2 scan and the sort-based candidate
+    pass (default from 4096 bodies up) must return the reference's pair."""
+    monkeypatch.setenv("VSB_COLLISION", request.param)
+    return request.param
+
+
+def test_check_collision_golden(dev, collision_mode):
     g = golden("pair_kernels")
     for p, r, d, a in zip(g["cc_pos"], g["cc_rad"], g["cc_del"], g["cc_add"]):
         got = dev.host_check_collision(g["cc_mass"], p, r)
@@ -145,8 +153,54 @@ def test_check_collision_golden(dev):
         assert got == want
 
 
+def test_check_collision_mixed_sizes(dev, oracle, collision_mode):
+    """Wildly different radii (root radius 166 vs moons ~13): big bodies go through
+    the large-body list of the candidate pass; clustered and degenerate layouts included."""
+    rng = np.random.default_rng(77)
+    for trial in range(10):
+        n = int(rng.integers(300, 6000))
+        mass = rng.uniform(0.5, 2.0, n)
+        pos = rng.uniform(-1, 1, (n, 2)) * 60.0 * np.sqrt(n)
+        rad = rng.uniform(1.0, 3.0, n)
+        big = rng.choice(n, 5, replace=False)
+        rad[big] = rng.uniform(50.0, 400.0, 5)              # a few giants
+        if trial % 3 == 1:
+            pos[: n // 2] = pos[: n // 2] * 0.05 + 3.0e4    # dense clump far from the rest
+        if trial % 3 == 2:
+            rad[big] = 2.0                                   # no giants
+            pos[:, 1] = 0.0                                  # collinear
+        if trial == 9:
+            pos[n // 2] = [1.0e300, -1.0e300]               # absurd extent -> exhaustive fallback
+        got = dev.host_check_collision(mass, pos, rad)
+        want = oracle.check_collision(mass, pos, rad)
+        assert got == want, (trial, n)
+
+
+def test_check_collision_grid_equals_brute_dense(dev, monkeypatch):
+    """64k bodies, thousands of overlapping pairs: both paths return the same first pair."""
+    rng = np.random.default_rng(123)
+    n = 65536
+    mass = rng.uniform(0.5, 2.0, n)
+    pos = rng.uniform(0, 1, (n, 2)) * 2.0e4
+    rad = rng.uniform(5.0, 15.0, n)
+    rad[7] = 900.0
+    res = {}
+    for mode in ("brute", "grid"):
+        monkeypatch.setenv("VSB_COLLISION", mode)
+        res[mode] = dev.host_check_collision(mass, pos, rad)
+    assert res["brute"] == res["grid"] and res["grid"][0] is not None
+    # push the first hits away one by one: the sequence of answers stays identical
+    for _ in range(5):
+        d, a = res["grid"]
+        pos[min(d, a)] += 1.0e6 + rng.uniform(0, 1e5, 2)
+        for mode in ("brute", "grid"):
+            monkeypatch.setenv("VSB_COLLISION", mode)
+            res[mode] = dev.host_check_collision(mass, pos, rad)
+        assert res["brute"] == res["grid"]
+
+
 @pytest.mark.parametrize("n", [2, 3, 100, 1024, 4097])
-def test_check_collision_vs_oracle_teacher_forced(dev, oracle, n):
+def test_check_collision_vs_oracle_teacher_forced(dev, oracle, n, collision_mode):
     rng = np.random.default_rng(300 + n)
     for trial in range(8):
         mass = rng.uniform(0.5, 2.0, n)

@@ -24,6 +24,7 @@ SOURCES = {
     "vsb_api.cu": [],
     "vsb_gravity.cu": [],
     "vsb_pairs.cu": ["-fmad=false"],
+    "vsb_broadphase.cu": ["-fmad=false"],
     "vsb_editor.cu": ["-fmad=false"],
     "vsb_kepler.cu": ["-fmad=false"],
 }

@@ -439,17 +439,39 @@ extern "C" int vsb_simplified_orbit_coi(vsb_ctx *c, double gc, double coi_coef,
     return VSB_OK;
 }
 
+// VSB_COLLISION=brute|grid forces one path (tests); default: grid from 4096 bodies up
+static int collision_use_grid(int64_t n)
+{
+    const char *env = getenv("VSB_COLLISION");
+    if (env && env[0] == 'b') return 0;
+    if (env && env[0] == 'g') return n >= 2;
+    return n >= 4096;
+}
+
 extern "C" int vsb_check_collision(vsb_ctx *c, int64_t *del_out, int64_t *add_out)
 {
     CTX(c);
     VSB_CHECK(del_out && add_out, VSB_ERR_ARG, "vsb_check_collision: null output");
     VSB_TRY(need_bodies(c, "vsb_check_collision"));
+    int64_t *h = (int64_t *)c->h_key;
+    if (collision_use_grid(c->n)) {
+        VSB_TRY(vsb_launch_broadphase(c));
+        VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                 c->stream));
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        if (h[2] == 0) {
+            *del_out = h[0];
+            *add_out = h[1];
+            return VSB_OK;
+        }
+        // grid unsuitable for this input: exhaustive scan below
+    }
     VSB_TRY(vsb_launch_check_collision(c));
-    VSB_CUDA(cudaMemcpyAsync(c->h_key, c->scratch.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+    VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost,
                              c->stream));
     VSB_CUDA(cudaStreamSynchronize(c->stream));
-    *del_out = ((int64_t *)c->h_key)[0];
-    *add_out = ((int64_t *)c->h_key)[1];
+    *del_out = h[0];
+    *add_out = h[1];
     return VSB_OK;
 }
 

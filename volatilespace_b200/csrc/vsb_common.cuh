@@ -197,6 +197,8 @@ int vsb_allpairs_chunks(int64_t n, int64_t *chunk_out);
 // pair predicates (vsb_pairs.cu)
 int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order);
 int vsb_launch_check_collision(vsb_ctx *c);
+// sort-based candidate pass (vsb_broadphase.cu); result {del, add, fallback} in c->scratch
+int vsb_launch_broadphase(vsb_ctx *c);
 // editor step pieces (vsb_editor.cu)
 int vsb_launch_gravity_ref(vsb_ctx *c, double gc, const int64_t *d_order);
 int vsb_launch_kepler_basic(vsb_ctx *c, double gc, double coi_coef);
