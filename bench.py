@@ -114,7 +114,8 @@ def pinned_copy(a):
 
 # ---------------------------------------------------------------------- CPU legs
 def cpu_pairs_per_s(s, budget_s, threads=None):
-    """Oracle port on a bounded sample: R target rows x all N sources, all host cores."""
+    """Oracle port on a bounded sample: R target rows x all N sources, all host cores.
+    R is grown until one run takes about budget_s seconds."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     L = orc.lib()
@@ -122,15 +123,15 @@ def cpu_pairs_per_s(s, budget_s, threads=None):
         L.vso_set_num_threads(int(threads))
     cores = L.vso_num_threads()
     n = len(s["mass"])
-    probe = max(cores * 2, 16)
-    t0 = time.perf_counter()
-    orc.allpairs_accel(s["mass"], s["pos"], s["gc"], 0, probe)
-    dt = time.perf_counter() - t0
-    rows = int(min(n, max(probe, budget_s / max(dt / probe, 1e-9))))
-    rows = max(cores, rows // cores * cores)
-    t0 = time.perf_counter()
-    orc.allpairs_accel(s["mass"], s["pos"], s["gc"], 0, rows)
-    dt = time.perf_counter() - t0
+    rows = max(cores * 4, 32)
+    while True:
+        rows = min(n, max(cores, rows // cores * cores))
+        t0 = time.perf_counter()
+        orc.allpairs_accel(s["mass"], s["pos"], s["gc"], 0, rows)
+        dt = time.perf_counter() - t0
+        if dt >= 0.6 * budget_s or rows >= n:
+            break
+        rows = int(rows * min(8.0, 1.05 * budget_s / max(dt, 1e-6)))
     return rows * (n - 1) / dt, cores, rows, dt
 
 
@@ -185,6 +186,41 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
     from volatilespace_b200._lib import KIND_VESSEL
     out = {}
     nobar = lambda: None
+    # config 1: built-in Solar System map (15 bodies), MODE_REF editor frames, host wall clock
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "solar_editor.npz"))
+        from volatilespace_b200.phys_editor import Physics
+        res = {}
+        for name in ("frame", "frame_calls"):
+            ph = Physics(dev, curve_points=64)
+            ph.load_system({"gc": float(g["gc"]), "rad_mult": float(g["rad_mult"]),
+                            "coi_coef": float(g["coi_coef"])},
+                           {"mass": g["mass"], "den": g["den"]},
+                           {"pos": g["pos0"], "vel": g["vel0"]})
+            ph.kepler_basic()
+            fn = getattr(ph, name)
+            for _ in range(50):
+                fn()
+            nfr = 2000 if name == "frame" else 300
+            t0 = time.perf_counter()
+            for _ in range(nfr):
+                fn()
+            res[name + "_per_s"] = nfr / (time.perf_counter() - t0)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as orc
+        ed = orc.EditorOracle(g["mass"], g["den"], g["pos0"], g["vel0"], float(g["gc"]),
+                              float(g["rad_mult"]), float(g["coi_coef"]))
+        orc.lib().vso_set_num_threads(1)
+        t0 = time.perf_counter()
+        for _ in range(2000):
+            ed.frame()
+        res["cpu_port_frames_per_s_1thread"] = 2000 / (time.perf_counter() - t0)
+        orc.lib().vso_set_num_threads(os.cpu_count() or 1)
+        res["note"] = ("frame = fused vsb_editor_ticks driver (1 launch + 1 packed read-back), "
+                       "frame_calls = per-method calls; eager host mirrors in both")
+        out["solar_system_editor"] = res
+    except Exception as e:
+        out["solar_system_editor"] = {"error": str(e)[:200]}
     # config 2: 64k Plummer
     s = synth.plummer2d(65536)
     dev.upload_bodies(s["mass"], s["pos"], s["vel"])

@@ -115,6 +115,20 @@ int vsb_allpairs_tick_async(vsb_ctx *ctx, double gc);
 /* Acceleration only (accel + reduce into VSB_F_ACC), enqueued without a host sync. */
 int vsb_allpairs_accel_async(vsb_ctx *ctx, double gc);
 
+/* Editor frame driver, editor.py:1503-1523: up to max_ticks x (gravity(); check_collision())
+ * -- body() only changes `rad` after a merge, which the host applies -- stopping after the
+ * tick in which a collision is found: *ticks_done ticks were executed and (*body_del_out,
+ * *body_add_out) is that tick's pair ((-1,-1): none).  When every tick ran undisturbed and
+ * do_kepler_basic != 0, kepler_basic (phys_editor.py:381-384) runs at the end.  Up to 1024
+ * bodies the whole call is ONE kernel launch (one CTA, state in shared memory) and one
+ * 32-byte read-back; results are bit-identical to the per-call path. */
+int vsb_editor_ticks(vsb_ctx *ctx, double gc, double coi_coef, const int64_t *order_desc_mass,
+                     int64_t max_ticks, int do_kepler_basic, int64_t *ticks_done,
+                     int64_t *body_del_out, int64_t *body_add_out);
+/* Download several fields with one device->host copy: dst receives the fields concatenated
+ * in the order given (each n x width 8-byte words; VSB_F_PARENTS as int64). */
+int vsb_bodies_get_many(vsb_ctx *ctx, const int *fields, int nfields, void *dst);
+
 /* A6  Physics.kepler_basic, phys_editor.py:381-384 (kepler_basic_one :63-83):
  * fills FOCUS, ECC_V, SEMI_MAJOR, SEMI_MINOR, PERIAPSIS_ARG and COI. */
 int vsb_kepler_basic(vsb_ctx *ctx, double gc, double coi_coef);

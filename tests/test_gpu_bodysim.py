@@ -268,7 +268,36 @@ def check_snapshot(ph, g, prefix, rtol):
             np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-300, err_msg=prefix + k)
 
 
-def test_solar_system_frames(dev):
+@pytest.fixture(params=["fused", "calls"])
+def frame_fn(request):
+    """Physics.frame (fused vsb_editor_ticks driver) and Physics.frame_calls (the individual
+    gravity(); body(); inelastic_collision(); kepler_basic() calls of editor.py:1503-1523)."""
+    name = "frame" if request.param == "fused" else "frame_calls"
+    return lambda ph, warp=1: getattr(ph, name)(warp)
+
+
+def test_fused_frame_is_bit_identical_to_per_call_path(dev):
+    g = golden("editor_clouds")
+    for case, frames, warp in (("A", 120, 1), ("B", 60, 1), ("B", 20, 3), ("A", 30, 5)):
+        args = (g[case + "_mass"], g[case + "_den"], g[case + "_pos0"], g[case + "_vel0"])
+        a = make_editor(dev, *args)
+        sa = []
+        for _ in range(frames):
+            d = a.frame(warp)
+            a.pull()
+            sa.append((d, a.pos.copy(), a.vel.copy(), a.rel_vel.copy(), a.parents.copy(),
+                       a.coi.copy(), a.semi_major.copy(), a.rad.copy(), a.mass.copy()))
+        b = make_editor(dev, *args)
+        for fr in range(frames):
+            d = b.frame_calls(warp)
+            b.pull()
+            assert d == sa[fr][0], (case, fr)
+            for x, y in zip((b.pos, b.vel, b.rel_vel, b.parents, b.coi, b.semi_major, b.rad,
+                             b.mass), sa[fr][1:]):
+                assert np.array_equal(x, y), (case, fr)
+
+
+def test_solar_system_frames(dev, frame_fn):
     """BASELINE config 1: built-in map, MODE_REF, 10 000 faithful editor frames."""
     g = golden("solar_editor")
     ph = make_editor(dev, g["mass"], g["den"], g["pos0"], g["vel0"], float(g["gc"]),
@@ -278,7 +307,7 @@ def test_solar_system_frames(dev):
     frames = 0
     for target in (1, 2, 100, 1000, 10000):
         while frames < target:
-            assert ph.frame() == []
+            assert frame_fn(ph) == []
             frames += 1
         # rel 1e-9 on pos/vel after 10k frames, parents bit-exact
         check_snapshot(ph, g, "f%d_" % target, 1e-12 if target <= 100 else 1e-9)
@@ -287,24 +316,24 @@ def test_solar_system_frames(dev):
     assert np.array_equal(ph.parents, [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 5, 5, 5, 6])
 
 
-def test_editor_cloud_coi_crossings(dev):
+def test_editor_cloud_coi_crossings(dev, frame_fn):
     g = golden("editor_clouds")
     ph = make_editor(dev, g["A_mass"], g["A_den"], g["A_pos0"], g["A_vel0"])
     check_snapshot(ph, g, "A_f0_", 1e-13)
     log = g["A_parents_log"]
     for fr in range(1, 601):
-        assert ph.frame() == []
+        assert frame_fn(ph) == []
         assert np.array_equal(ph.parents, log[fr - 1]), fr
         if fr in (1, 50, 300, 600):
             check_snapshot(ph, g, "A_f%d_" % fr, 1e-9)
 
 
-def test_editor_cloud_merges(dev):
+def test_editor_cloud_merges(dev, frame_fn):
     """Free-running merges on the dense clump: deleted-index sequence bit-exact."""
     g = golden("editor_clouds")
     ph = make_editor(dev, g["B_mass"], g["B_den"], g["B_pos0"], g["B_vel0"])
     for fr in range(1, 121):
-        d = ph.frame()
+        d = frame_fn(ph)
         assert (d[0] if d else -1) == g["B_deleted"][fr - 1], fr
         assert len(ph.mass) == g["B_counts"][fr - 1]
         if fr in (1, 10, 40, 120):

@@ -417,6 +417,74 @@ extern "C" int vsb_allpairs_step(vsb_ctx *c, double gc, int64_t nsteps)
     return VSB_OK;
 }
 
+extern "C" int vsb_editor_ticks(vsb_ctx *c, double gc, double coi_coef, const int64_t *order,
+                                int64_t max_ticks, int do_kepler_basic, int64_t *ticks_done,
+                                int64_t *del_out, int64_t *add_out)
+{
+    CTX(c);
+    VSB_CHECK(ticks_done && del_out && add_out && max_ticks >= 0, VSB_ERR_ARG,
+              "vsb_editor_ticks: bad argument");
+    VSB_TRY(need_bodies(c, "vsb_editor_ticks"));
+    VSB_TRY(upload_order(c, "vsb_editor_ticks", order));
+    const int64_t *d_order = (const int64_t *)c->order.p;
+    *ticks_done = 0;
+    *del_out = -1;
+    *add_out = -1;
+    int64_t *h = (int64_t *)c->h_key;
+    if (c->n <= 1024 && !getenv("VSB_NO_FUSED_FRAME")) {
+        VSB_CHECK(max_ticks < (1ll << 30), VSB_ERR_ARG, "vsb_editor_ticks: max_ticks too large");
+        VSB_TRY(vsb_launch_editor_frame_small(c, gc, coi_coef, d_order, (int)max_ticks,
+                                              do_kepler_basic));
+        VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                 c->stream));
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        VSB_CHECK(h[3] == 0, VSB_ERR_STATE, "vsb_editor_ticks: parent chain deeper than 48 levels");
+        *ticks_done = h[0];
+        *del_out = h[1];
+        *add_out = h[2];
+        return VSB_OK;
+    }
+    for (int64_t t = 0; t < max_ticks; ++t) {
+        VSB_TRY(vsb_launch_gravity_ref(c, gc, d_order));
+        *ticks_done = t + 1;
+        int64_t d, a;
+        VSB_TRY(vsb_check_collision(c, &d, &a));
+        if (d >= 0) {
+            *del_out = d;
+            *add_out = a;
+            return VSB_OK;
+        }
+    }
+    if (do_kepler_basic) {
+        VSB_TRY(vsb_launch_kepler_basic(c, gc, coi_coef));
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return VSB_OK;
+}
+
+extern "C" int vsb_bodies_get_many(vsb_ctx *c, const int *fields, int nfields, void *dst)
+{
+    CTX(c);
+    VSB_CHECK(fields && dst && nfields > 0 && nfields <= 16, VSB_ERR_ARG,
+              "vsb_bodies_get_many: bad argument");
+    VSB_TRY(need_bodies(c, "vsb_bodies_get_many"));
+    const void *ptrs[16];
+    int widths[16];
+    size_t words = 0;
+    for (int f = 0; f < nfields; ++f) {
+        VSB_CHECK(fields[f] >= 0 && fields[f] < VSB_F_COUNT_, VSB_ERR_ARG,
+                  "vsb_bodies_get_many: unknown field %d", fields[f]);
+        ptrs[f] = field_ptr(c, fields[f]);
+        widths[f] = k_fields[fields[f]].width;
+        words += (size_t)c->n * widths[f];
+    }
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * words));
+    int64_t total = 0;
+    VSB_TRY(vsb_launch_pack_fields(c, fields, ptrs, widths, nfields, (double *)c->host_stage.p,
+                                   &total));
+    return d2h(c, dst, c->host_stage.p, 8 * (size_t)total);
+}
+
 extern "C" int vsb_kepler_basic(vsb_ctx *c, double gc, double coi_coef)
 {
     CTX(c);

@@ -208,6 +208,10 @@ int vsb_launch_delete_row(vsb_ctx *c, int64_t row);
 int vsb_launch_swap_rows(vsb_ctx *c, int64_t a, int64_t b);
 int vsb_launch_translate(vsb_ctx *c, int64_t ref_row);
 int vsb_launch_pad_tail(vsb_ctx *c);
+int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order,
+                                  int max_ticks, int do_kepler_basic);
+int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptrs,
+                           const int *widths, int nfields, double *d_out, int64_t *words_out);
 int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double *d_out);
 // kepler (vsb_kepler.cu)
 int vsb_launch_kepler_move(vsb_ctx *c, vsb_kepler_state &k, double warp);

@@ -19,6 +19,20 @@ __device__ __forceinline__ double py_mod(double a, double b)
 }
 
 // ------------------------------------------------------------------ A2/A3
+// gravity_one, phys_editor.py:51-60 (body != 0): acceleration of `pi` toward `pp`.
+__device__ __forceinline__ double2 gravity_one_dev(double2 pi, double2 pp, double mb, double mp,
+                                                   double gc)
+{
+    double rx = pp.x - pi.x, ry = pp.y - pi.y;
+    double distance = sqrt(rx * rx + ry * ry);
+    double force = gc * mb * mp / (distance * distance);
+    double angle = atan2(ry, rx);
+    double acc = force / mb;
+    double sn, cs;
+    sincos(angle, &sn, &cs);
+    return make_double2(acc * cs, acc * sn);
+}
+
 // rel_vel += gravity_one(body, parents[body], ...) for every body (:361-363).
 __global__ void ref_accel_kernel(int64_t n, const double *__restrict__ mass,
                                  const double2 *__restrict__ pos,
@@ -28,18 +42,10 @@ __global__ void ref_accel_kernel(int64_t n, const double *__restrict__ mass,
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || i == 0) return;  // root: acceleration [0,0] (:60)
     int64_t p = parents[i];
-    double2 pi = pos[i], pp = pos[p];
-    double rx = pp.x - pi.x, ry = pp.y - pi.y;
-    double distance = sqrt(rx * rx + ry * ry);
-    double mb = mass[i];
-    double force = gc * mb * mass[p] / (distance * distance);
-    double angle = atan2(ry, rx);
-    double acc = force / mb;
-    double sn, cs;
-    sincos(angle, &sn, &cs);
+    double2 a = gravity_one_dev(pos[i], pos[p], mass[i], mass[p], gc);
     double2 rv = rel_vel[i];
-    rv.x += acc * cs;
-    rv.y += acc * sn;
+    rv.x += a.x;
+    rv.y += a.y;
     rel_vel[i] = rv;
 }
 
@@ -125,6 +131,36 @@ __global__ void ref_compose_kernel(int64_t n, const int64_t *__restrict__ rank,
 }
 
 // ------------------------------------------------------------------ A6
+struct kb_out {
+    double focus, semi_major, semi_minor, periapsis_arg, coi;
+    double2 ecc_v;
+};
+
+// kepler_basic_one, phys_editor.py:63-83 (body != 0)
+__device__ __forceinline__ kb_out kepler_basic_one_dev(double2 pb, double2 pp, double2 vb,
+                                                       double2 vp, double mb, double mp, double gc,
+                                                       double coi_coef)
+{
+    double rpx = pb.x - pp.x, rpy = pb.y - pp.y;
+    double rvx = vb.x - vp.x, rvy = vb.y - vp.y;
+    double u = gc * mp;
+    double magp = sqrt(rpx * rpx + rpy * rpy);
+    double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / magp));
+    double momentum = rpx * rvy - rpy * rvx;
+    double sx = rvy, sy = -rvx;
+    double ex = (sx * momentum / u) - rpx / magp;
+    double ey = (sy * momentum / u) - rpy / magp;
+    double ecc = sqrt(ex * ex + ey * ey);
+    kb_out o;
+    o.periapsis_arg = py_mod((3 * PI_D / 2) + atan2(-ex, ey), 2 * PI_D);
+    o.focus = a * ecc;
+    o.semi_minor = sqrt(fabs(o.focus * o.focus - a * a));
+    o.coi = a > 0 ? a * pow(mb / mp, coi_coef) : 0.0;
+    o.semi_major = a;
+    o.ecc_v = make_double2(ex, ey);
+    return o;
+}
+
 __global__ void kepler_basic_kernel(int64_t n, const int64_t *__restrict__ parents,
                                     const double *__restrict__ mass,
                                     const double2 *__restrict__ pos,
@@ -145,29 +181,14 @@ __global__ void kepler_basic_kernel(int64_t n, const int64_t *__restrict__ paren
         coi[0] = 0.0;
         return;
     }
-    int64_t p = parents[b];
-    double2 pb = pos[b], pp = pos[p], vb = vel[b], vp = vel[p];
-    double rpx = pb.x - pp.x, rpy = pb.y - pp.y;
-    double rvx = vb.x - vp.x, rvy = vb.y - vp.y;
-    double u = gc * mass[p];
-    double magp = sqrt(rpx * rpx + rpy * rpy);
-    double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / magp));
-    double momentum = rpx * rvy - rpy * rvx;
-    double sx = rvy, sy = -rvx;
-    double ex = (sx * momentum / u) - rpx / magp;
-    double ey = (sy * momentum / u) - rpy / magp;
-    double ecc = sqrt(ex * ex + ey * ey);
-    double pea = py_mod((3 * PI_D / 2) + atan2(-ex, ey), 2 * PI_D);
-    double f = a * ecc;
-    double bm = sqrt(fabs(f * f - a * a));
-    double c = 0.0;
-    if (a > 0) c = a * pow(mass[b] / mass[p], coi_coef);
-    focus[b] = f;
-    ecc_v[b] = make_double2(ex, ey);
-    semi_major[b] = a;
-    semi_minor[b] = bm;
-    periapsis_arg[b] = pea;
-    coi[b] = c;
+    kb_out o = kepler_basic_one_dev(pos[b], pos[parents[b]], vel[b], vel[parents[b]], mass[b],
+                                    mass[parents[b]], gc, coi_coef);
+    focus[b] = o.focus;
+    ecc_v[b] = o.ecc_v;
+    semi_major[b] = o.semi_major;
+    semi_minor[b] = o.semi_minor;
+    periapsis_arg[b] = o.periapsis_arg;
+    coi[b] = o.coi;
 }
 
 // ------------------------------------------------------------------ A7
@@ -444,6 +465,226 @@ editor_curve_kernel(int64_t n, int64_t P, const double2 *__restrict__ ecc_v,
     }
 }
 
+// ------------------------------------------------------------------ fused small-N frame
+// Up to `max_ticks` editor ticks (gravity(); [body();] check_collision()) for n <= 1024 in ONE
+// launch of ONE CTA, all state in shared memory; stops after the tick in which a collision is
+// found (the host applies the merge, phys_editor.py:554-565, and calls again for the remaining
+// ticks) and runs kepler_basic at the end of an undisturbed frame (editor.py:1503-1523).
+// Same device functions and operation order as the per-kernel path above: results are
+// bit-identical to it.  hdr = {ticks_done, body_del, body_add, chain_overflow}.
+constexpr int FR_MAX = 1024;
+
+__global__ void __launch_bounds__(FR_MAX)
+editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int do_kepler_basic,
+                          const int64_t *__restrict__ order, const double *__restrict__ g_mass,
+                          double2 *g_pos, double2 *g_vel, double2 *g_rel_vel, double *g_coi,
+                          const double *__restrict__ g_rad, int64_t *g_parents, double *g_focus,
+                          double2 *g_ecc_v, double *g_semi_major, double *g_semi_minor,
+                          double *g_periapsis_arg, int64_t *hdr)
+{
+    extern __shared__ double2 fr_smem[];
+    double2 *s_pos = fr_smem, *s_vel = s_pos + n, *s_rv = s_vel + n, *s_spos = s_rv + n;
+    double *s_mass = (double *)(s_spos + n), *s_rad = s_mass + n, *s_scoi2 = s_rad + n;
+    int *s_par = (int *)(s_scoi2 + n), *s_rank = s_par + n, *s_ord = s_rank + n,
+        *s_changed = s_ord + n;
+    __shared__ unsigned long long s_key[32];
+    __shared__ int s_overflow;
+
+    const int t = threadIdx.x;
+    const bool live = t < n;
+    if (t == 0) s_overflow = 0;
+    if (live) {
+        s_pos[t] = g_pos[t];
+        s_vel[t] = g_vel[t];
+        s_rv[t] = g_rel_vel[t];
+        s_mass[t] = g_mass[t];
+        s_rad[t] = g_rad[t];
+        s_par[t] = (int)g_parents[t];
+        const int body = (int)order[t];   // t plays the role of a rank here
+        s_ord[t] = body;
+        s_rank[body] = t;
+        const double c = g_coi[body];
+        s_scoi2[t] = c * c;
+    }
+    __syncthreads();
+
+    int ticks = 0;
+    long long hit_del = -1, hit_add = -1;
+    for (; ticks < max_ticks;) {
+        // ---- find_parents (:350-354): thread <-> rank
+        const int par_old = live ? s_par[t] : 0;
+        if (live) s_spos[t] = s_pos[s_ord[t]];
+        __syncthreads();
+        if (live) {
+            const double2 me = s_spos[t];
+            int best = -1;
+            for (int k = 0; k < t; ++k) {
+                double dx = me.x - s_spos[k].x, dy = me.y - s_spos[k].y;
+                if (dx * dx + dy * dy < s_scoi2[k]) best = k;
+            }
+            const int body = s_ord[t];
+            s_par[body] = (body == 0 || best < 0) ? 0 : s_ord[best];
+        }
+        __syncthreads();
+        // ---- rel_vel += gravity_one (:361-363): thread <-> body
+        int changed = 0;
+        if (live && t != 0) {
+            const int p = s_par[t];
+            double2 a = gravity_one_dev(s_pos[t], s_pos[p], s_mass[t], s_mass[p], gc);
+            double2 rv = s_rv[t];
+            rv.x += a.x;
+            rv.y += a.y;
+            s_rv[t] = rv;
+            changed = p != par_old;
+        }
+        if (live) s_changed[t] = changed ? par_old + 1 : 0;   // old parent + 1, 0 = unchanged
+        // ---- COI enter/leave fix-up, sequential in index order (:366-373)
+        if (__syncthreads_or(changed)) {
+            if (t == 0) {
+                for (int b = 1; b < n; ++b) {
+                    if (!s_changed[b]) continue;
+                    const int parent = s_par[b], old = s_changed[b] - 1;
+                    if (s_mass[parent] > s_mass[old]) {
+                        s_rv[b].x += s_rv[old].x;
+                        s_rv[b].y += s_rv[old].y;
+                    }
+                    if (s_mass[parent] < s_mass[old]) {
+                        s_rv[b].x -= s_rv[parent].x;
+                        s_rv[b].y -= s_rv[parent].y;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- vel compose in descending-mass order + pos += vel (:375-378)
+        double2 v = make_double2(0.0, 0.0);
+        if (live) {
+            int chain[48];
+            int depth = 0, node = t;
+            for (;;) {
+                if (s_rank[node] == 0) {
+                    v = s_vel[node];
+                    break;
+                }
+                if (depth == 48) {
+                    s_overflow = 1;
+                    break;
+                }
+                chain[depth++] = node;
+                const int p = s_par[node];
+                if (s_rank[p] < s_rank[node]) {
+                    node = p;
+                } else {
+                    v = s_vel[p];
+                    break;
+                }
+            }
+            for (int d = depth - 1; d >= 0; --d) {
+                double2 r = s_rv[chain[d]];
+                v.x = r.x + v.x;
+                v.y = r.y + v.y;
+            }
+        }
+        __syncthreads();
+        if (live) {
+            s_vel[t] = v;
+            double2 p = s_pos[t];
+            p.x += v.x;
+            p.y += v.y;
+            s_pos[t] = p;
+        }
+        __syncthreads();
+        ++ticks;
+        // ---- check_collision (:547-551): first j > i per thread, then the smallest (i,j)
+        unsigned long long key = ~0ull;
+        if (t < n - 1) {
+            const double2 me = s_pos[t];
+            const double ri = s_rad[t];
+            for (int j = t + 1; j < n; ++j) {
+                double dx = me.x - s_pos[j].x, dy = me.y - s_pos[j].y;
+                double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                if (d <= __dadd_rn(ri, s_rad[j])) {
+                    key = ((unsigned long long)t << 32) | (unsigned)j;
+                    break;
+                }
+            }
+        }
+        key = warp_min_u64(key);
+        if ((t & 31) == 0) s_key[t >> 5] = key;
+        __syncthreads();
+        if (t < 32) {
+            key = t < (int)(blockDim.x >> 5) ? s_key[t] : ~0ull;
+            key = warp_min_u64(key);
+            if (t == 0) s_key[0] = key;
+        }
+        __syncthreads();
+        key = s_key[0];
+        __syncthreads();
+        if (key != ~0ull) {
+            const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
+            if (s_mass[i] <= s_mass[j]) {
+                hit_del = i;
+                hit_add = j;
+            } else {
+                hit_del = j;
+                hit_add = i;
+            }
+            break;
+        }
+    }
+
+    if (live) {
+        g_pos[t] = s_pos[t];
+        g_vel[t] = s_vel[t];
+        g_rel_vel[t] = s_rv[t];
+        g_parents[t] = s_par[t];
+        if (do_kepler_basic && hit_del < 0 && ticks == max_ticks) {
+            if (t == 0) {
+                g_focus[0] = 0.0;
+                g_ecc_v[0] = make_double2(0.0, 0.0);
+                g_semi_major[0] = 0.0;
+                g_semi_minor[0] = 0.0;
+                g_periapsis_arg[0] = 0.0;
+                g_coi[0] = 0.0;
+            } else {
+                const int p = s_par[t];
+                kb_out o = kepler_basic_one_dev(s_pos[t], s_pos[p], s_vel[t], s_vel[p], s_mass[t],
+                                                s_mass[p], gc, coi_coef);
+                g_focus[t] = o.focus;
+                g_ecc_v[t] = o.ecc_v;
+                g_semi_major[t] = o.semi_major;
+                g_semi_minor[t] = o.semi_minor;
+                g_periapsis_arg[t] = o.periapsis_arg;
+                g_coi[t] = o.coi;
+            }
+        }
+    }
+    if (t == 0) {
+        hdr[0] = ticks;
+        hdr[1] = hit_del;
+        hdr[2] = hit_add;
+        hdr[3] = s_overflow;
+    }
+}
+
+// gather several body fields into one contiguous staging buffer (one D2H copy per frame)
+struct pack_desc {
+    const double *src[16];
+    int width[16];
+    int count;
+};
+
+__global__ void pack_fields_kernel(pack_desc d, int64_t n, double *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t off = 0;
+    for (int f = 0; f < d.count; ++f) {
+        const int64_t words = n * d.width[f];
+        if (i < words) out[off + i] = d.src[f][i];
+        off += words;
+    }
+}
+
 body_arrays arrays_of(vsb_ctx *c)
 {
     body_arrays A;
@@ -598,6 +839,50 @@ int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double 
     editor_curve_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(
         n, P, (const double2 *)c->ecc_v, c->semi_major, c->semi_minor, c->focus, c->periapsis_arg,
         c->parents, (const double2 *)c->pos, d_tabs, d_out);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
+
+// Fused small-N frame; hdr (4 x int64) lands in c->scratch.p.  n <= 1024 only.
+int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order,
+                                  int max_ticks, int do_kepler_basic)
+{
+    const int n = (int)c->n;
+    VSB_CHECK(n >= 1 && n <= FR_MAX, VSB_ERR_ARG, "editor_frame_small: n=%d", n);
+    VSB_TRY(vsb_buf_reserve(c->scratch, 64));
+    const size_t smem = (size_t)n * (4 * sizeof(double2) + 3 * sizeof(double) + 4 * sizeof(int));
+    if (smem > 48 * 1024)
+        VSB_CUDA(cudaFuncSetAttribute(editor_frame_small_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = (n + 31) / 32 * 32;
+    editor_frame_small_kernel<<<1, threads, smem, c->stream>>>(
+        n, max_ticks, gc, coi_coef, do_kepler_basic, d_order, c->mass, (double2 *)c->pos,
+        (double2 *)c->vel, (double2 *)c->rel_vel, c->coi, c->rad, c->parents, c->focus,
+        (double2 *)c->ecc_v, c->semi_major, c->semi_minor, c->periapsis_arg,
+        (int64_t *)c->scratch.p);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
+
+// Packs `nfields` body fields (ids of enum vsb_body_field) into d_out, concatenated.
+int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptrs,
+                           const int *widths, int nfields, double *d_out, int64_t *words_out)
+{
+    (void)fields;
+    pack_desc d;
+    d.count = nfields;
+    int64_t maxw = 0, total = 0;
+    for (int f = 0; f < nfields; ++f) {
+        d.src[f] = (const double *)ptrs[f];
+        d.width[f] = widths[f];
+        total += c->n * widths[f];
+        if (c->n * widths[f] > maxw) maxw = c->n * widths[f];
+    }
+    *words_out = total;
+    if (maxw == 0) return VSB_OK;
+    pack_fields_kernel<<<(unsigned)((maxw + 255) / 256), 256, 0, c->stream>>>(d, c->n, d_out);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;

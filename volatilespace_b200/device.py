@@ -129,6 +129,28 @@ class Device:
     def allpairs_tick_async(self, gc):
         check(self.L.vsb_allpairs_tick_async(self.h, float(gc)))
 
+    def editor_ticks(self, gc, coi_coef, order, max_ticks, do_kepler_basic=True):
+        """-> (ticks_done, body_del | None, body_add | None)"""
+        order = i64(order)
+        t, d, a = C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.L.vsb_editor_ticks(self.h, float(gc), float(coi_coef), ptr(order),
+                                      int(max_ticks), 1 if do_kepler_basic else 0, C.byref(t),
+                                      C.byref(d), C.byref(a)))
+        if d.value < 0:
+            return t.value, None, None
+        return t.value, d.value, a.value
+
+    def get_many(self, fields, out=None):
+        """One D2H copy for several fields; returns the packed float64 buffer (parents'
+        int64 words are bit-cast: use .view(np.int64) on that slice)."""
+        n = self.bodies_count()
+        words = sum(n * _lib.BODY_FIELD_WIDTH[f] for f in fields)
+        if out is None:
+            out = np.empty(words)
+        arr = (C.c_int * len(fields))(*fields)
+        check(self.L.vsb_bodies_get_many(self.h, arr, len(fields), ptr(out)))
+        return out
+
     def kepler_basic(self, gc, coi_coef):
         check(self.L.vsb_kepler_basic(self.h, float(gc), float(coi_coef)))
 

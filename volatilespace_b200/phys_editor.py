@@ -108,6 +108,8 @@ class Physics(_DeviceBodies):
         self.min_mass = DEFAULT_CONF["min_planet_mass"]
         self.largest = 0
         self.names = np.array([])
+        self._order_cache = None
+        self._rad_dirty = True
         self._alloc_host(0)
         self.reload_settings(curve_points)
 
@@ -139,6 +141,7 @@ class Physics(_DeviceBodies):
         self.pos[:] = body_orb_data["pos"]
         self.vel[:] = body_orb_data["vel"]
         self._stale.clear()
+        self._mass_changed()
         self.dev.bodies_resize(n)
         self._push()
         self.simplified_orbit_coi()
@@ -150,26 +153,28 @@ class Physics(_DeviceBodies):
 
     # phys_editor.py:325-346
     def simplified_orbit_coi(self):
-        self.largest = self.dev.simplified_orbit_coi(self.gc, self.coi_coef,
-                                                     mass_order(self.mass))
+        self.largest = self.dev.simplified_orbit_coi(self.gc, self.coi_coef, self._order())
         self._touched("coi")
 
     # phys_editor.py:350-354
     def find_parents(self):
-        self.dev.find_parents(mass_order(self.mass), want=False)
+        self.dev.find_parents(self._order(), want=False)
         self._touched("parents")
 
     # phys_editor.py:357-378
     def gravity(self):
-        self.dev.gravity_ref(self.gc, mass_order(self.mass))
+        self.dev.gravity_ref(self.gc, self._order())
         self._touched("parents", "rel_vel", "vel", "pos")
 
     # phys_editor.py:577-599 (radius; the thermal/atmosphere part is UI data, out of scope)
     def body(self):
+        if not self._rad_dirty:          # rad depends on mass and den only
+            return
         rad = body_radius(self.mass, self.den, self.rad_mult)
         if not np.array_equal(rad, self.rad):
             self.rad[:] = rad
             self._push("rad")
+        self._rad_dirty = False
 
     # phys_editor.py:547-551
     def check_collision(self):
@@ -188,19 +193,34 @@ class Physics(_DeviceBodies):
     def inelastic_collision(self):
         body_del, body_add = self.check_collision()
         if body_del is not None:
-            mass_r = self.mass[body_del] + self.mass[body_add]
-            mom1 = self._row("vel", body_add) * self.mass[body_add]
-            mom2 = self._row("vel", body_del) * self.mass[body_del]
-            velr = (mom1 + mom2) / mass_r
-            parent = int(self._row("parents", body_add))
-            self._set_row("rel_vel", body_add, velr - self._row("rel_vel", parent))
-            self.set_body_mass(body_add, mass_r)
-            self.del_body(body_del)
+            self._merge(body_del, body_add)
         return body_del
+
+    def _merge(self, body_del, body_add):
+        """:556-564 for an already detected pair."""
+        mass_r = self.mass[body_del] + self.mass[body_add]
+        mom1 = self._row("vel", body_add) * self.mass[body_add]
+        mom2 = self._row("vel", body_del) * self.mass[body_del]
+        velr = (mom1 + mom2) / mass_r
+        parent = int(self._row("parents", body_add))
+        self._set_row("rel_vel", body_add, velr - self._row("rel_vel", parent))
+        self.set_body_mass(body_add, mass_r)
+        self.del_body(body_del)
+
+    def _order(self):
+        """argsort(mass)[-1::-1], recomputed only when the masses changed."""
+        if self._order_cache is None or len(self._order_cache) != len(self.mass):
+            self._order_cache = mass_order(self.mass)
+        return self._order_cache
+
+    def _mass_changed(self):
+        self._order_cache = None
+        self._rad_dirty = True
 
     # phys_editor.py:844-857
     def set_body_mass(self, body, mass):
         self._set_row("mass", body, mass)
+        self._mass_changed()
         old_largest = int(self.largest)
         self.find_parents()
         self.simplified_orbit_coi()
@@ -223,6 +243,7 @@ class Physics(_DeviceBodies):
         for name in ("mass", "den", "rad"):
             arr = getattr(self, name)
             arr[0], arr[body] = arr[body], arr[0]
+        self._mass_changed()
         if len(self.names) > body:
             self.names[0], self.names[body] = self.names[body], self.names[0]
         self._touched("pos", "vel", "rel_vel", "parents")
@@ -236,6 +257,7 @@ class Physics(_DeviceBodies):
             self.pull()                      # bring every mirror up to date, then drop the row
             self.dev.delete_row(delete)
             self._delete_host_row(delete)
+            self._mass_changed()
             if len(self.names) > delete:
                 self.names = np.delete(self.names, delete)
             self.simplified_orbit_coi()
@@ -265,6 +287,7 @@ class Physics(_DeviceBodies):
         self.den[-1] = data["density"]
         self.rad[:] = body_radius(self.mass, self.den, self.rad_mult)
         self.pos[-1] = data["position"]
+        self._mass_changed()
         self.dev.bodies_resize(n)
         self._push()
         self.simplified_orbit_coi()
@@ -281,6 +304,7 @@ class Physics(_DeviceBodies):
     # phys_editor.py:860-880 (mutators used by the editor UI)
     def set_body_den(self, body, density):
         self._set_row("den", body, max(density, 0.05))
+        self._rad_dirty = True
         self.simplified_orbit_coi()
 
     def set_body_pos(self, body, position):
@@ -302,8 +326,8 @@ class Physics(_DeviceBodies):
         self.pull()
         return self.semi_major, self.semi_minor, self.coi, self.parents
 
-    def frame(self, warp=1):
-        """One editor frame exactly as editor.py:1503-1523 sequences it."""
+    def frame_calls(self, warp=1):
+        """One editor frame as the individual method calls of editor.py:1503-1523."""
         deleted = []
         for _ in range(warp):
             self.gravity()
@@ -313,6 +337,50 @@ class Physics(_DeviceBodies):
                 deleted.append(int(d))
         self.kepler_basic()
         return deleted
+
+    _FRAME_FIELDS = ("pos", "vel", "rel_vel", "parents", "focus", "ecc_v", "semi_major",
+                     "semi_minor", "periapsis_arg", "coi")
+
+    def frame(self, warp=1):
+        """The same frame through the fused driver (vsb_editor_ticks): the warp loop, the
+        collision checks and kepler_basic run on the device without host round trips (one
+        kernel launch and one 32-byte read-back for up to 1024 bodies); the host only steps
+        in to apply a merge.  Bit-identical to frame_calls().  Returns the deleted indices."""
+        deleted = []
+        left = int(warp)
+        while True:
+            self.body()          # editor.py:1505 -- rad only changes after a merge
+            done, body_del, body_add = self.dev.editor_ticks(
+                self.gc, self.coi_coef, self._order(), left, do_kepler_basic=True)
+            left -= done
+            self._stale.update(("parents", "rel_vel", "vel", "pos"))
+            if body_del is None:
+                break
+            self._merge(body_del, body_add)
+            deleted.append(int(body_del))
+            if left == 0:
+                self.kepler_basic()
+                break
+        self._stale.update(("focus", "ecc_v", "semi_major", "semi_minor", "periapsis_arg", "coi"))
+        if self.sync == "eager":
+            self._pull_frame()
+        return deleted
+
+    def _pull_frame(self):
+        """All per-frame outputs with one device->host copy."""
+        n = len(self.mass)
+        buf = self.dev.get_many([_FIELDS[k] for k in self._FRAME_FIELDS])
+        off = 0
+        for k in self._FRAME_FIELDS:
+            w = 2 if k in _WIDE else 1
+            chunk = buf[off:off + n * w]
+            off += n * w
+            dst = getattr(self, k)
+            if k == "parents":
+                dst[:] = chunk.view(np.int64)
+            else:
+                dst[...] = chunk.reshape(dst.shape)
+            self._stale.discard(k)
 
 
 class AllPairsPhysics(_DeviceBodies):
