@@ -119,8 +119,8 @@ def cpu_pairs_per_s(s, budget_s, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     L = orc.lib()
-    if threads:
-        L.vso_set_num_threads(int(threads))
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override)
+    L.vso_set_num_threads(int(threads) if threads else len(os.sched_getaffinity(0)))
     cores = L.vso_num_threads()
     n = len(s["mass"])
     rows = max(cores * 4, 32)

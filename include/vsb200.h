@@ -121,10 +121,14 @@ int vsb_allpairs_accel_async(vsb_ctx *ctx, double gc);
  * *body_add_out) is that tick's pair ((-1,-1): none).  When every tick ran undisturbed and
  * do_kepler_basic != 0, kepler_basic (phys_editor.py:381-384) runs at the end.  Up to 1024
  * bodies the whole call is ONE kernel launch (one CTA, state in shared memory) and one
- * 32-byte read-back; results are bit-identical to the per-call path. */
+ * 32-byte read-back; results are bit-identical to the per-call path.
+ * order_desc_mass may be NULL to reuse the order uploaded by the previous call.  frame_out
+ * (optional) receives the frame record in one copy: 4 int64 {ticks_done, del, add, 0} followed
+ * by pos, vel, rel_vel (2n each), parents (n, int64), focus (n), ecc_v (2n), semi_major,
+ * semi_minor, periapsis_arg, coi (n each) -- (4 + 14 n) 8-byte words. */
 int vsb_editor_ticks(vsb_ctx *ctx, double gc, double coi_coef, const int64_t *order_desc_mass,
                      int64_t max_ticks, int do_kepler_basic, int64_t *ticks_done,
-                     int64_t *body_del_out, int64_t *body_add_out);
+                     int64_t *body_del_out, int64_t *body_add_out, void *frame_out);
 /* Download several fields with one device->host copy: dst receives the fields concatenated
  * in the order given (each n x width 8-byte words; VSB_F_PARENTS as int64). */
 int vsb_bodies_get_many(vsb_ctx *ctx, const int *fields, int nfields, void *dst);

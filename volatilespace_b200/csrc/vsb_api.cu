@@ -339,11 +339,19 @@ static int need_bodies(vsb_ctx *c, const char *who)
     return VSB_OK;
 }
 
+// order == NULL reuses the order uploaded by the previous call (valid while n is unchanged)
 static int upload_order(vsb_ctx *c, const char *who, const int64_t *order)
 {
-    VSB_CHECK(order, VSB_ERR_ARG, "%s: null order", who);
+    if (!order) {
+        VSB_CHECK(c->order_n == c->n && c->order.p, VSB_ERR_STATE,
+                  "%s: no order resident for %lld bodies", who, (long long)c->n);
+        return VSB_OK;
+    }
     VSB_TRY(vsb_buf_reserve(c->order, sizeof(int64_t) * (size_t)c->npad));
-    return h2d(c, c->order.p, order, sizeof(int64_t) * (size_t)c->n);
+    c->order_n = -1;
+    VSB_TRY(h2d(c, c->order.p, order, sizeof(int64_t) * (size_t)c->n));
+    c->order_n = c->n;
+    return VSB_OK;
 }
 
 extern "C" int vsb_find_parents(vsb_ctx *c, const int64_t *order, int64_t *parents_out)
@@ -417,9 +425,25 @@ extern "C" int vsb_allpairs_step(vsb_ctx *c, double gc, int64_t nsteps)
     return VSB_OK;
 }
 
+static const int k_frame_fields[10] = {VSB_F_POS, VSB_F_VEL, VSB_F_REL_VEL, VSB_F_PARENTS,
+                                       VSB_F_FOCUS, VSB_F_ECC_V, VSB_F_SEMI_MAJOR,
+                                       VSB_F_SEMI_MINOR, VSB_F_PERIAPSIS_ARG, VSB_F_COI};
+
+static int pack_frame(vsb_ctx *c, double *d_dst)
+{
+    const void *ptrs[10];
+    int widths[10];
+    for (int f = 0; f < 10; ++f) {
+        ptrs[f] = field_ptr(c, k_frame_fields[f]);
+        widths[f] = k_fields[k_frame_fields[f]].width;
+    }
+    int64_t total = 0;
+    return vsb_launch_pack_fields(c, k_frame_fields, ptrs, widths, 10, d_dst, &total);
+}
+
 extern "C" int vsb_editor_ticks(vsb_ctx *c, double gc, double coi_coef, const int64_t *order,
                                 int64_t max_ticks, int do_kepler_basic, int64_t *ticks_done,
-                                int64_t *del_out, int64_t *add_out)
+                                int64_t *del_out, int64_t *add_out, void *frame_out)
 {
     CTX(c);
     VSB_CHECK(ticks_done && del_out && add_out && max_ticks >= 0, VSB_ERR_ARG,
@@ -430,35 +454,53 @@ extern "C" int vsb_editor_ticks(vsb_ctx *c, double gc, double coi_coef, const in
     *ticks_done = 0;
     *del_out = -1;
     *add_out = -1;
+    const size_t rec_words = 4 + 14 * (size_t)c->n;
     int64_t *h = (int64_t *)c->h_key;
     if (c->n <= 1024 && !getenv("VSB_NO_FUSED_FRAME")) {
         VSB_CHECK(max_ticks < (1ll << 30), VSB_ERR_ARG, "vsb_editor_ticks: max_ticks too large");
+        double *d_packed = nullptr;
+        if (frame_out) {
+            VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * rec_words));
+            d_packed = (double *)c->host_stage.p;
+        }
         VSB_TRY(vsb_launch_editor_frame_small(c, gc, coi_coef, d_order, (int)max_ticks,
-                                              do_kepler_basic));
-        VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                 c->stream));
-        VSB_CUDA(cudaStreamSynchronize(c->stream));
+                                              do_kepler_basic, d_packed));
+        if (frame_out) {
+            VSB_TRY(d2h(c, frame_out, d_packed, 8 * rec_words));
+            h = (int64_t *)frame_out;
+        } else {
+            VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 4 * sizeof(int64_t),
+                                     cudaMemcpyDeviceToHost, c->stream));
+            VSB_CUDA(cudaStreamSynchronize(c->stream));
+        }
         VSB_CHECK(h[3] == 0, VSB_ERR_STATE, "vsb_editor_ticks: parent chain deeper than 48 levels");
         *ticks_done = h[0];
         *del_out = h[1];
         *add_out = h[2];
         return VSB_OK;
     }
+    int64_t d = -1, a = -1;
     for (int64_t t = 0; t < max_ticks; ++t) {
         VSB_TRY(vsb_launch_gravity_ref(c, gc, d_order));
         *ticks_done = t + 1;
-        int64_t d, a;
         VSB_TRY(vsb_check_collision(c, &d, &a));
-        if (d >= 0) {
-            *del_out = d;
-            *add_out = a;
-            return VSB_OK;
-        }
+        if (d >= 0) break;
     }
-    if (do_kepler_basic) {
-        VSB_TRY(vsb_launch_kepler_basic(c, gc, coi_coef));
-        VSB_CUDA(cudaStreamSynchronize(c->stream));
+    *del_out = d;
+    *add_out = a;
+    if (do_kepler_basic && d < 0) VSB_TRY(vsb_launch_kepler_basic(c, gc, coi_coef));
+    if (frame_out) {
+        VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * rec_words));
+        double *d_packed = (double *)c->host_stage.p;
+        VSB_TRY(pack_frame(c, d_packed + 4));
+        VSB_TRY(d2h(c, (char *)frame_out + 32, d_packed + 4, 8 * (rec_words - 4)));
+        int64_t *fh = (int64_t *)frame_out;
+        fh[0] = *ticks_done;
+        fh[1] = d;
+        fh[2] = a;
+        fh[3] = 0;
     }
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
     return VSB_OK;
 }
 

@@ -87,6 +87,7 @@ struct vsb_ctx {
     // scratch
     vsb_buf part;        // all-pairs partial sums [C][rows][2]
     vsb_buf order;       // int64 order (descending mass) + rank
+    int64_t order_n = -1; // number of valid entries uploaded to `order`
     vsb_buf sorted;      // sorted-source staging for find_parents
     vsb_buf scratch;     // generic
     vsb_buf host_stage;  // device staging for the stateless host-buffer calls
@@ -209,7 +210,7 @@ int vsb_launch_swap_rows(vsb_ctx *c, int64_t a, int64_t b);
 int vsb_launch_translate(vsb_ctx *c, int64_t ref_row);
 int vsb_launch_pad_tail(vsb_ctx *c);
 int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order,
-                                  int max_ticks, int do_kepler_basic);
+                                  int max_ticks, int do_kepler_basic, double *d_packed);
 int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptrs,
                            const int *widths, int nfields, double *d_out, int64_t *words_out);
 int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double *d_out);

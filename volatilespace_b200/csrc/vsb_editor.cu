@@ -480,7 +480,7 @@ editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int 
                           double2 *g_pos, double2 *g_vel, double2 *g_rel_vel, double *g_coi,
                           const double *__restrict__ g_rad, int64_t *g_parents, double *g_focus,
                           double2 *g_ecc_v, double *g_semi_major, double *g_semi_minor,
-                          double *g_periapsis_arg, int64_t *hdr)
+                          double *g_periapsis_arg, int64_t *hdr, double *packed)
 {
     extern __shared__ double2 fr_smem[];
     double2 *s_pos = fr_smem, *s_vel = s_pos + n, *s_rv = s_vel + n, *s_spos = s_rv + n;
@@ -638,25 +638,44 @@ editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int 
         g_vel[t] = s_vel[t];
         g_rel_vel[t] = s_rv[t];
         g_parents[t] = s_par[t];
+        kb_out o;
         if (do_kepler_basic && hit_del < 0 && ticks == max_ticks) {
             if (t == 0) {
-                g_focus[0] = 0.0;
-                g_ecc_v[0] = make_double2(0.0, 0.0);
-                g_semi_major[0] = 0.0;
-                g_semi_minor[0] = 0.0;
-                g_periapsis_arg[0] = 0.0;
-                g_coi[0] = 0.0;
+                o.focus = o.semi_major = o.semi_minor = o.periapsis_arg = o.coi = 0.0;
+                o.ecc_v = make_double2(0.0, 0.0);
             } else {
                 const int p = s_par[t];
-                kb_out o = kepler_basic_one_dev(s_pos[t], s_pos[p], s_vel[t], s_vel[p], s_mass[t],
-                                                s_mass[p], gc, coi_coef);
-                g_focus[t] = o.focus;
-                g_ecc_v[t] = o.ecc_v;
-                g_semi_major[t] = o.semi_major;
-                g_semi_minor[t] = o.semi_minor;
-                g_periapsis_arg[t] = o.periapsis_arg;
-                g_coi[t] = o.coi;
+                o = kepler_basic_one_dev(s_pos[t], s_pos[p], s_vel[t], s_vel[p], s_mass[t],
+                                         s_mass[p], gc, coi_coef);
             }
+            g_focus[t] = o.focus;
+            g_ecc_v[t] = o.ecc_v;
+            g_semi_major[t] = o.semi_major;
+            g_semi_minor[t] = o.semi_minor;
+            g_periapsis_arg[t] = o.periapsis_arg;
+            g_coi[t] = o.coi;
+        } else {
+            o.focus = g_focus[t];
+            o.ecc_v = g_ecc_v[t];
+            o.semi_major = g_semi_major[t];
+            o.semi_minor = g_semi_minor[t];
+            o.periapsis_arg = g_periapsis_arg[t];
+            o.coi = g_coi[t];
+        }
+        if (packed) {
+            // frame record after the 4-word header: pos vel rel_vel parents focus ecc_v
+            // semi_major semi_minor periapsis_arg coi  (14 n words)
+            double *q = packed + 4;
+            ((double2 *)q)[t] = s_pos[t];
+            ((double2 *)(q + 2 * n))[t] = s_vel[t];
+            ((double2 *)(q + 4 * n))[t] = s_rv[t];
+            ((long long *)(q + 6 * n))[t] = s_par[t];
+            (q + 7 * n)[t] = o.focus;
+            ((double2 *)(q + 8 * n))[t] = o.ecc_v;
+            (q + 10 * n)[t] = o.semi_major;
+            (q + 11 * n)[t] = o.semi_minor;
+            (q + 12 * n)[t] = o.periapsis_arg;
+            (q + 13 * n)[t] = o.coi;
         }
     }
     if (t == 0) {
@@ -664,6 +683,13 @@ editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int 
         hdr[1] = hit_del;
         hdr[2] = hit_add;
         hdr[3] = s_overflow;
+        if (packed) {
+            long long *ph = (long long *)packed;
+            ph[0] = ticks;
+            ph[1] = hit_del;
+            ph[2] = hit_add;
+            ph[3] = s_overflow;
+        }
     }
 }
 
@@ -846,7 +872,7 @@ int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double 
 
 // Fused small-N frame; hdr (4 x int64) lands in c->scratch.p.  n <= 1024 only.
 int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order,
-                                  int max_ticks, int do_kepler_basic)
+                                  int max_ticks, int do_kepler_basic, double *d_packed)
 {
     const int n = (int)c->n;
     VSB_CHECK(n >= 1 && n <= FR_MAX, VSB_ERR_ARG, "editor_frame_small: n=%d", n);
@@ -860,7 +886,7 @@ int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const 
         n, max_ticks, gc, coi_coef, do_kepler_basic, d_order, c->mass, (double2 *)c->pos,
         (double2 *)c->vel, (double2 *)c->rel_vel, c->coi, c->rad, c->parents, c->focus,
         (double2 *)c->ecc_v, c->semi_major, c->semi_minor, c->periapsis_arg,
-        (int64_t *)c->scratch.p);
+        (int64_t *)c->scratch.p, d_packed);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;

@@ -129,13 +129,15 @@ class Device:
     def allpairs_tick_async(self, gc):
         check(self.L.vsb_allpairs_tick_async(self.h, float(gc)))
 
-    def editor_ticks(self, gc, coi_coef, order, max_ticks, do_kepler_basic=True):
-        """-> (ticks_done, body_del | None, body_add | None)"""
-        order = i64(order)
+    def editor_ticks(self, gc, coi_coef, order, max_ticks, do_kepler_basic=True, frame_out=None):
+        """-> (ticks_done, body_del | None, body_add | None).  order=None reuses the order
+        uploaded by the previous call; frame_out: float64 array of 4 + 14 n words that
+        receives the frame record (see include/vsb200.h)."""
+        order = None if order is None else i64(order)
         t, d, a = C.c_int64(), C.c_int64(), C.c_int64()
         check(self.L.vsb_editor_ticks(self.h, float(gc), float(coi_coef), ptr(order),
                                       int(max_ticks), 1 if do_kepler_basic else 0, C.byref(t),
-                                      C.byref(d), C.byref(a)))
+                                      C.byref(d), C.byref(a), ptr(frame_out)))
         if d.value < 0:
             return t.value, None, None
         return t.value, d.value, a.value

@@ -109,6 +109,7 @@ class Physics(_DeviceBodies):
         self.largest = 0
         self.names = np.array([])
         self._order_cache = None
+        self._order_on_device = False
         self._rad_dirty = True
         self._alloc_host(0)
         self.reload_settings(curve_points)
@@ -215,6 +216,7 @@ class Physics(_DeviceBodies):
 
     def _mass_changed(self):
         self._order_cache = None
+        self._order_on_device = False
         self._rad_dirty = True
 
     # phys_editor.py:844-857
@@ -348,32 +350,39 @@ class Physics(_DeviceBodies):
         in to apply a merge.  Bit-identical to frame_calls().  Returns the deleted indices."""
         deleted = []
         left = int(warp)
+        eager = self.sync == "eager"
         while True:
             self.body()          # editor.py:1505 -- rad only changes after a merge
+            n = len(self.mass)
+            rec = np.empty(4 + 14 * n) if eager else None
+            order = None if self._order_on_device else self._order()
             done, body_del, body_add = self.dev.editor_ticks(
-                self.gc, self.coi_coef, self._order(), left, do_kepler_basic=True)
+                self.gc, self.coi_coef, order, left, do_kepler_basic=True, frame_out=rec)
+            self._order_on_device = True
             left -= done
-            self._stale.update(("parents", "rel_vel", "vel", "pos"))
             if body_del is None:
+                if eager:
+                    self._unpack_frame(rec)
+                else:
+                    self._stale.update(self._FRAME_FIELDS)
                 break
+            self._stale.update(("parents", "rel_vel", "vel", "pos"))
             self._merge(body_del, body_add)
             deleted.append(int(body_del))
             if left == 0:
                 self.kepler_basic()
+                if eager:
+                    self.pull()
                 break
-        self._stale.update(("focus", "ecc_v", "semi_major", "semi_minor", "periapsis_arg", "coi"))
-        if self.sync == "eager":
-            self._pull_frame()
         return deleted
 
-    def _pull_frame(self):
-        """All per-frame outputs with one device->host copy."""
+    def _unpack_frame(self, rec):
+        """Frame record of vsb_editor_ticks -> host mirrors (in place)."""
         n = len(self.mass)
-        buf = self.dev.get_many([_FIELDS[k] for k in self._FRAME_FIELDS])
-        off = 0
+        off = 4
         for k in self._FRAME_FIELDS:
             w = 2 if k in _WIDE else 1
-            chunk = buf[off:off + n * w]
+            chunk = rec[off:off + n * w]
             off += n * w
             dst = getattr(self, k)
             if k == "parents":
