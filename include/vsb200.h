@@ -114,6 +114,18 @@ int vsb_allpairs_step(vsb_ctx *ctx, double gc, int64_t nsteps);
 int vsb_allpairs_tick_async(vsb_ctx *ctx, double gc);
 /* Acceleration only (accel + reduce into VSB_F_ACC), enqueued without a host sync. */
 int vsb_allpairs_accel_async(vsb_ctx *ctx, double gc);
+/* Kernel choice for the all-pairs entry points when the context owns every row:
+ * 0 = row kernel (13 FP64 instr per directed pair; bit-identical under any row sharding),
+ * 1 = symmetric kernel (each unordered pair evaluated once and applied to both bodies,
+ *     8 FP64 instr per directed pair; deterministic run to run, last-bit differences from
+ *     mode 0).  Sharded rows always use the row kernel. */
+int vsb_set_gravity_mode(vsb_ctx *ctx, int mode);
+/* Multi-GPU form of the symmetric kernel: rank `rank` of `world` evaluates its share of the
+ * unordered block pairs and leaves its PARTIAL accelerations for all bodies in VSB_F_ACC
+ * (asynchronous); the caller all-reduces (sum) VSB_F_ACC over the ranks and then calls
+ * vsb_allpairs_integrate_async on every rank (all rows owned). */
+int vsb_allpairs_sym_partial_async(vsb_ctx *ctx, double gc, int rank, int world);
+int vsb_allpairs_integrate_async(vsb_ctx *ctx);
 
 /* Editor frame driver, editor.py:1503-1523: up to max_ticks x (gravity(); check_collision())
  * -- body() only changes `rad` after a merge, which the host applies -- stopping after the

@@ -22,7 +22,7 @@ def test_partition_covers_rows_once():
             for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
                 assert a1 == b0 and a0 <= a1
             assert all(r1 - r0 <= rpr for r0, r1 in ranges)
-            npad = (n + 1023) // 1024 * 1024
+            npad = (n + 2047) // 2048 * 2048
             assert world * rpr <= npad          # the padded device array can hold the gather
 
 
@@ -43,7 +43,7 @@ def _worker(rank, world, port, n, steps, q):
     vel = rng.uniform(-1, 1, (n, 2))
     rpr, ranges = partition(n, world)
     r0, r1 = ranges[rank]
-    npad = (n + 1023) // 1024 * 1024
+    npad = (n + 2047) // 2048 * 2048
     full = torch.zeros((npad, 2), dtype=torch.float64)
     full[:n] = torch.from_numpy(pos)
     v = vel[r0:r1].copy()

@@ -43,14 +43,22 @@ def row_rel_err(got, want):
 
 
 # ------------------------------------------------------------------ A4 all-pairs
-def test_allpairs_accel_golden(dev):
+@pytest.fixture(params=["rows", "sym"])
+def gravity_mode(request, monkeypatch):
+    """Both all-pairs kernels: the row kernel (vsb_gravity.cu) and the symmetric one that
+    evaluates every unordered pair once (vsb_gravity_sym.cu)."""
+    monkeypatch.setenv("VSB_GRAVITY", request.param)
+    return request.param
+
+
+def test_allpairs_accel_golden(dev, gravity_mode):
     g = golden("allpairs_small")
     acc = dev.host_allpairs_accel(g["mass"], g["pos0"], float(g["gc"]))
     assert row_rel_err(acc, g["acc0"]) < 1e-12
 
 
 @pytest.mark.parametrize("n", [1, 2, 15, 127, 128, 129, 1000, 1024, 1025, 4096, 5000])
-def test_allpairs_accel_vs_oracle(dev, oracle, n):
+def test_allpairs_accel_vs_oracle(dev, oracle, n, gravity_mode):
     mass, pos, _ = small_cloud(n, 100 + n)
     acc = dev.host_allpairs_accel(mass, pos, 0.75)
     want = oracle.allpairs_accel(mass, pos, 0.75)
@@ -62,7 +70,7 @@ def test_allpairs_accel_vs_oracle(dev, oracle, n):
         assert row_rel_err(acc, want) < 1e-12
 
 
-def test_allpairs_plummer_sampled_rows(dev, oracle):
+def test_allpairs_plummer_sampled_rows(dev, oracle, gravity_mode):
     """64k-body config: acceleration parity on 256 sampled target rows."""
     from volatilespace_b200 import synth
     s = synth.plummer2d(65536)
@@ -74,7 +82,7 @@ def test_allpairs_plummer_sampled_rows(dev, oracle):
         assert err < 1e-11, (r, err)
 
 
-def test_allpairs_steps_vs_oracle_and_golden(dev, oracle):
+def test_allpairs_steps_vs_oracle_and_golden(dev, oracle, gravity_mode):
     g = golden("allpairs_small")
     pos, vel = g["pos0"].copy(), g["vel0"].copy()
     dev.host_allpairs_step(g["mass"], pos, vel, float(g["gc"]), 16)
@@ -106,7 +114,7 @@ def test_allpairs_deterministic_and_shard_invariant(dev):
     dev.set_rows(0, 6000)
 
 
-def test_allpairs_momentum_conservation(dev):
+def test_allpairs_momentum_conservation(dev, gravity_mode):
     """Size-independent property at a larger N: sum_i m_i a_i = 0 for pairwise forces."""
     from volatilespace_b200 import synth
     s = synth.plummer2d(32768, seed=3)
@@ -114,6 +122,47 @@ def test_allpairs_momentum_conservation(dev):
     f = (acc * s["mass"][:, None])
     scale = np.abs(f).sum(axis=0)
     assert np.all(np.abs(f.sum(axis=0)) < 1e-11 * scale)
+
+
+def test_allpairs_sym_matches_rows_and_is_deterministic(dev, monkeypatch):
+    """The symmetric kernel against the row kernel on several sizes (one and several
+    macro-blocks, ragged tails): <= 1e-13 of the row's acceleration, bit-identical run to run."""
+    from volatilespace_b200._lib import F_ACC
+    for n in (3, 1000, 1024, 2049, 5000, 20000):
+        mass, pos, vel = small_cloud(n, 900 + n, extent=2.0e4)
+        dev.upload_bodies(mass, pos, vel)
+        monkeypatch.setenv("VSB_GRAVITY", "rows")
+        dev.allpairs_accel(1.0)
+        rows = dev.get(F_ACC)
+        monkeypatch.setenv("VSB_GRAVITY", "sym")
+        dev.allpairs_accel(1.0)
+        sym = dev.get(F_ACC)
+        dev.allpairs_accel(1.0)
+        assert np.array_equal(sym, dev.get(F_ACC)), n
+        assert row_rel_err(sym, rows) < 1e-13, n
+
+
+def test_allpairs_sym_multi_rank_partials_sum_to_full(dev, monkeypatch):
+    """Multi-GPU form of the symmetric kernel, ranks emulated by separate contexts on one
+    GPU: the ranks' partial accelerations add up to the single-rank result."""
+    from volatilespace_b200._lib import F_ACC
+    from volatilespace_b200.device import Device
+    n = 9000
+    mass, pos, vel = small_cloud(n, 4242, extent=3.0e4)
+    monkeypatch.setenv("VSB_GRAVITY", "sym")
+    dev.upload_bodies(mass, pos, vel)
+    dev.allpairs_accel(0.5)
+    full = dev.get(F_ACC)
+    for world in (2, 3, 8):
+        total = np.zeros_like(full)
+        for rank in range(world):
+            d = Device(0)
+            d.upload_bodies(mass, pos, vel)
+            d.allpairs_sym_partial_async(0.5, rank, world)
+            d.sync()
+            total += d.get(F_ACC)
+            d.close()
+        assert row_rel_err(total, full) < 1e-14, world
 
 
 # ------------------------------------------------------------------ A1 find_parents

@@ -62,6 +62,9 @@ SIGNATURES = {
     "vsb_allpairs_step": [_ctx, _f64, _i64],
     "vsb_allpairs_tick_async": [_ctx, _f64],
     "vsb_allpairs_accel_async": [_ctx, _f64],
+    "vsb_set_gravity_mode": [_ctx, C.c_int],
+    "vsb_allpairs_sym_partial_async": [_ctx, _f64, C.c_int, C.c_int],
+    "vsb_allpairs_integrate_async": [_ctx],
     "vsb_editor_ticks": [_ctx, _f64, _f64, _pv, _i64, C.c_int, _pi, _pi, _pi, _pv],
     "vsb_bodies_get_many": [_ctx, C.POINTER(C.c_int), C.c_int, _pv],
     "vsb_kepler_basic": [_ctx, _f64, _f64],

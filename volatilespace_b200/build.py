@@ -23,6 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "--extended-lambda", "-Xcompiler", "
 SOURCES = {
     "vsb_api.cu": [],
     "vsb_gravity.cu": [],
+    "vsb_gravity_sym.cu": [],
     "vsb_pairs.cu": ["-fmad=false"],
     "vsb_broadphase.cu": ["-fmad=false"],
     "vsb_editor.cu": ["-fmad=false"],

@@ -149,6 +149,7 @@ extern "C" int vsb_ctx_destroy(vsb_ctx *c)
     free_kepler(c->kep[0]);
     free_kepler(c->kep[1]);
     vsb_buf_free(c->part);
+    vsb_buf_free(c->sym_tab);
     vsb_buf_free(c->order);
     vsb_buf_free(c->sorted);
     vsb_buf_free(c->scratch);
@@ -373,12 +374,53 @@ extern "C" int vsb_gravity_ref(vsb_ctx *c, double gc, const int64_t *order)
     return vsb_launch_gravity_ref(c, gc, (const int64_t *)c->order.p);
 }
 
+// Which all-pairs kernel runs: the symmetric one only when this context owns every row
+// (the row kernel is the one that shards); VSB_GRAVITY=rows|sym overrides the context mode.
+static bool use_sym(vsb_ctx *c)
+{
+    if (c->row0 != 0 || c->row1 != c->n) return false;
+    const char *env = getenv("VSB_GRAVITY");
+    if (env && env[0] == 'r') return false;
+    if (env && env[0] == 's') return true;
+    return c->gravity_mode == 1;
+}
+
+// one acceleration pass (+ integrator) with whichever kernel applies; asynchronous
+static int accel_pass(vsb_ctx *c, double gc, int integrate)
+{
+    if (use_sym(c)) return vsb_launch_allpairs_sym(c, gc, 0, 1, integrate);
+    VSB_TRY(vsb_launch_allpairs_accel(c, gc));
+    return vsb_launch_allpairs_reduce(c, gc, integrate);
+}
+
+extern "C" int vsb_set_gravity_mode(vsb_ctx *c, int mode)
+{
+    VSB_CHECK(c && (mode == 0 || mode == 1), VSB_ERR_ARG, "vsb_set_gravity_mode: bad argument");
+    c->gravity_mode = mode;
+    return VSB_OK;
+}
+
+extern "C" int vsb_allpairs_sym_partial_async(vsb_ctx *c, double gc, int rank, int world)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_allpairs_sym_partial_async"));
+    VSB_CHECK(world >= 1 && rank >= 0 && rank < world, VSB_ERR_ARG,
+              "vsb_allpairs_sym_partial_async: rank %d of %d", rank, world);
+    return vsb_launch_allpairs_sym(c, gc, rank, world, 0);
+}
+
+extern "C" int vsb_allpairs_integrate_async(vsb_ctx *c)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_allpairs_integrate_async"));
+    return vsb_launch_allpairs_integrate(c);
+}
+
 extern "C" int vsb_allpairs_accel(vsb_ctx *c, double gc)
 {
     CTX(c);
     VSB_TRY(need_bodies(c, "vsb_allpairs_accel"));
-    VSB_TRY(vsb_launch_allpairs_accel(c, gc));
-    VSB_TRY(vsb_launch_allpairs_reduce(c, gc, 0));
+    VSB_TRY(accel_pass(c, gc, 0));
     VSB_CUDA(cudaStreamSynchronize(c->stream));
     return VSB_OK;
 }
@@ -397,16 +439,14 @@ extern "C" int vsb_allpairs_tick_async(vsb_ctx *c, double gc)
 {
     CTX(c);
     VSB_TRY(need_bodies(c, "vsb_allpairs_tick_async"));
-    VSB_TRY(vsb_launch_allpairs_accel(c, gc));
-    return vsb_launch_allpairs_reduce(c, gc, 1);
+    return accel_pass(c, gc, 1);
 }
 
 extern "C" int vsb_allpairs_accel_async(vsb_ctx *c, double gc)
 {
     CTX(c);
     VSB_TRY(need_bodies(c, "vsb_allpairs_accel_async"));
-    VSB_TRY(vsb_launch_allpairs_accel(c, gc));
-    return vsb_launch_allpairs_reduce(c, gc, 0);
+    return accel_pass(c, gc, 0);
 }
 
 extern "C" int vsb_allpairs_step(vsb_ctx *c, double gc, int64_t nsteps)
@@ -655,10 +695,7 @@ extern "C" int vsb_host_allpairs_step(vsb_ctx *c, int64_t n, const double *mass,
     VSB_CUDA(cudaMemcpyAsync(c->mass, mass, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VSB_CUDA(cudaMemcpyAsync(c->pos, pos, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VSB_CUDA(cudaMemcpyAsync(c->vel, vel, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    for (int64_t s = 0; s < nsteps; ++s) {
-        VSB_TRY(vsb_launch_allpairs_accel(c, gc));
-        VSB_TRY(vsb_launch_allpairs_reduce(c, gc, 1));
-    }
+    for (int64_t s = 0; s < nsteps; ++s) VSB_TRY(accel_pass(c, gc, 1));
     VSB_CUDA(cudaMemcpyAsync(pos, c->pos, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     VSB_CUDA(cudaMemcpyAsync(vel, c->vel, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     VSB_CUDA(cudaStreamSynchronize(c->stream));
@@ -673,8 +710,7 @@ extern "C" int vsb_host_allpairs_accel(vsb_ctx *c, int64_t n, const double *mass
     VSB_TRY(stage_bodies(c, n));
     VSB_CUDA(cudaMemcpyAsync(c->mass, mass, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VSB_CUDA(cudaMemcpyAsync(c->pos, pos, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    VSB_TRY(vsb_launch_allpairs_accel(c, gc));
-    VSB_TRY(vsb_launch_allpairs_reduce(c, gc, 0));
+    VSB_TRY(accel_pass(c, gc, 0));
     return d2h(c, acc_out, c->acc, 16 * (size_t)n);
 }
 

@@ -41,7 +41,7 @@ void vsb_set_error(const char *fmt, ...);
 // ---------------------------------------------------------------- context
 // All body arrays are padded to a multiple of VSB_PAD entries; padding rows hold
 // mass 0 and a far-away position so pair kernels can run whole tiles unmasked.
-#define VSB_PAD 1024
+#define VSB_PAD 2048
 #define VSB_FAR 3.0e150
 
 struct vsb_buf {
@@ -85,7 +85,12 @@ struct vsb_ctx {
            *periapsis_arg = nullptr;
 
     // scratch
-    vsb_buf part;        // all-pairs partial sums [C][rows][2]
+    vsb_buf part;        // all-pairs partial sums [C][rows][2] (or the symmetric kernel's slabs)
+    vsb_buf sym_tab;     // symmetric kernel: task table + Q-slab index
+    int64_t sym_tasks_n = -1, sym_qf_off = 0;
+    int sym_world = 0, sym_rank = 0, sym_ntasks = 0, sym_nslots = 0;
+    void *sym_zeroed = nullptr;
+    int gravity_mode = 0;   // 0: row kernel (vsb_gravity.cu), 1: symmetric (vsb_gravity_sym.cu)
     vsb_buf order;       // int64 order (descending mass) + rank
     int64_t order_n = -1; // number of valid entries uploaded to `order`
     vsb_buf sorted;      // sorted-source staging for find_parents
@@ -195,6 +200,8 @@ int vsb_launch_allpairs_integrate(vsb_ctx *c);
 int vsb_launch_allpairs_reduce(vsb_ctx *c, double gc, int integrate);
 int vsb_launch_dfma_peak(vsb_ctx *c, int iters, int blocks, float *ms_out);
 int vsb_allpairs_chunks(int64_t n, int64_t *chunk_out);
+// symmetric kernel (vsb_gravity_sym.cu)
+int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int integrate);
 // pair predicates (vsb_pairs.cu)
 int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order);
 int vsb_launch_check_collision(vsb_ctx *c);

@@ -1,0 +1,296 @@
+// vsb_gravity_sym.cu -- all-pairs gravity exploiting Newton's third
+// law: every UNORDERED pair is evaluated once and applied to both bodies.
+//
+// Same model and pair arithmetic as vsb_gravity.cu (m_j r^-3 from the MUFU.RSQ64H seed
+// with one cubic correction); the shared part of a pair costs 10 FP64-pipe instructions
+// and each side 3 more, so a directed interaction costs 8 instead of 13.
+//
+// Decomposition: bodies are cut into macro-blocks of S = WARPS*128.  A CTA task is one
+// block Q (positions, masses AND its accumulators resident in shared memory) against a
+// range of blocks P <= Q.  Warp w keeps P's sub-block w in registers (4 targets per
+// lane, stride 32) and in sub-round rho works on Q's sub-block (w + rho) % WARPS, so in
+// any sub-round every Q sub-block is touched by exactly one warp; inside a sub-block
+// lane l works in step k on source group (l + k) % 32, so every shared accumulator has a
+// single writer at any time -- no atomics anywhere.  The diagonal task (P == Q) runs
+// the directed formula with the i == j mask and writes only target-side sums.
+//
+// Determinism: the schedule above is fixed, target-side sums of every (P,Q) pair and
+// source-side sums of every task go to their own slab, and allpairs_sym_reduce_kernel
+// adds the slabs in block order: bit-identical run to run.  (Across different GPU
+// counts the result differs in the last bits -- use vsb_gravity.cu when shard
+// invariance matters.)
+#include <stdlib.h>
+
+#include "vsb_common.cuh"
+
+namespace {
+
+struct sym_task {
+    int q, p0, p1, qslot;  // block Q, blocks P in [p0, p1), slab index of the Q-side sums
+};
+
+__device__ __forceinline__ double inv_r3(double dx, double dy, double &r2_out)
+{
+    double r2 = fma(dx, dx, dy * dy);
+    double y = rsqrt_seed(r2);
+    double t = y * y;
+    double e = fma(-r2, t, 1.0);
+    double y3 = t * y;
+    double p = fma(1.875, e, 1.5);
+    double q = e * p;
+    r2_out = r2;
+    return fma(y3, q, y3);
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 16) ? 1 : 2)
+allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ mass,
+                    const sym_task *__restrict__ tasks, double2 *__restrict__ part_p,
+                    double2 *__restrict__ part_q)
+{
+    constexpr int S = WARPS * 128;
+    extern __shared__ __align__(128) unsigned char sym_smem[];
+    double2 *sxy = (double2 *)sym_smem;          // S
+    double2 *sacc = sxy + S;                     // S
+    double *sm = (double *)(sacc + S);           // S
+    __shared__ alignas(8) uint64_t bar;
+
+    const sym_task task = tasks[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t qbase = (int64_t)task.q * S;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, S * (sizeof(double2) + sizeof(double)));
+        tma_bulk_g2s(sxy, pos + qbase, S * sizeof(double2), &bar);
+        tma_bulk_g2s(sm, mass + qbase, S * sizeof(double), &bar);
+    }
+    for (int i = tid; i < S; i += WARPS * 32) sacc[i] = make_double2(0.0, 0.0);
+    mbar_wait(&bar, 0);
+    __syncthreads();
+
+    for (int P = task.p0; P < task.p1; ++P) {
+        // targets of this lane: rows pbase + w*128 + k*32 + lane
+        const int64_t pbase = (int64_t)P * S + w * 128 + lane;
+        double xi[4], yi[4], mi[4], ax[4], ay[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double2 p = pos[pbase + k * 32];
+            xi[k] = p.x;
+            yi[k] = p.y;
+            mi[k] = -mass[pbase + k * 32];   // negated: the source side gets -m_i w d
+            ax[k] = ay[k] = 0.0;
+        }
+        if (P == task.q) {
+            // diagonal block: directed, masked, target side only
+            for (int qs = 0; qs < WARPS; ++qs) {
+                const int sb = qs * 128;
+#pragma unroll 1
+                for (int j = 0; j < 128; ++j) {
+                    const double2 pj = sxy[sb + j];
+                    const double mj = sm[sb + j];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double dx = pj.x - xi[k], dy = pj.y - yi[k];
+                        double r2 = fma(dx, dx, dy * dy);
+                        double y = rsqrt_seed(r2);
+                        int hi = __double2hiint(r2);
+                        y = __hiloint2double(hi < 0x00100000 ? 0 : __double2hiint(y), 0);
+                        double t = y * y;
+                        double e = fma(-r2, t, 1.0);
+                        double ym = y * mj;
+                        double y3m = t * ym;
+                        double p = fma(1.875, e, 1.5);
+                        double q = e * p;
+                        double s = fma(y3m, q, y3m);
+                        ax[k] = fma(s, dx, ax[k]);
+                        ay[k] = fma(s, dy, ay[k]);
+                    }
+                }
+            }
+        } else {
+            for (int rho = 0; rho < WARPS; ++rho) {
+                const int sb = ((w + rho) & (WARPS - 1)) * 128;
+#pragma unroll 1
+                for (int step = 0; step < 32; ++step) {
+                    const int g = (lane + step) & 31;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const int idx = sb + s * 32 + g;
+                        const double2 pj = sxy[idx];
+                        const double mj = sm[idx];
+                        double2 aj = sacc[idx];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            double dx = pj.x - xi[k], dy = pj.y - yi[k];
+                            double r2;
+                            double wv = inv_r3(dx, dy, r2);
+                            double wi = wv * mj;
+                            ax[k] = fma(wi, dx, ax[k]);
+                            ay[k] = fma(wi, dy, ay[k]);
+                            double wj = wv * mi[k];
+                            aj.x = fma(wj, dx, aj.x);
+                            aj.y = fma(wj, dy, aj.y);
+                        }
+                        sacc[idx] = aj;
+                    }
+                    __syncwarp();   // the group moves on to the next lane
+                }
+                __syncthreads();    // the sub-block moves on to the next warp
+            }
+        }
+        // target-side sums of the pair (P, Q): slab q(q+1)/2 + P
+        const int64_t slab = (int64_t)task.q * (task.q + 1) / 2 + P;
+        double2 *out = part_p + slab * S + w * 128 + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[k * 32] = make_double2(ax[k], ay[k]);
+    }
+    __syncthreads();
+    double2 *qo = part_q + (int64_t)task.qslot * S;
+    for (int i = tid; i < S; i += WARPS * 32) qo[i] = sacc[i];
+}
+
+// acc[i] = gc * ( sum of Q-side slabs of block X (tasks in P order) + sum over Q >= X of the
+// P-side slab of (X, Q) ), fixed order; optional integrator v += a ; P += v.
+__global__ void __launch_bounds__(256)
+allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__restrict__ part_q,
+                           const int *__restrict__ qslot_first, int S, int M, int64_t n,
+                           double gc, double2 *__restrict__ acc, double2 *__restrict__ vel,
+                           double2 *__restrict__ pos, int integrate, int add_into)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int X = (int)(i / S);
+    const int r = (int)(i - (int64_t)X * S);
+    double sx = 0.0, sy = 0.0;
+    for (int sl = qslot_first[X]; sl < qslot_first[X + 1]; ++sl) {
+        double2 v = part_q[(int64_t)sl * S + r];
+        sx += v.x;
+        sy += v.y;
+    }
+    for (int Q = X; Q < M; ++Q) {
+        const int64_t slab = (int64_t)Q * (Q + 1) / 2 + X;
+        double2 v = part_p[slab * S + r];
+        sx += v.x;
+        sy += v.y;
+    }
+    sx *= gc;
+    sy *= gc;
+    (void)add_into;
+    acc[i] = make_double2(sx, sy);
+    if (integrate) {
+        double2 v = vel[i];
+        v.x += sx;
+        v.y += sy;
+        vel[i] = v;
+        double2 p = pos[i];
+        p.x += v.x;
+        p.y += v.y;
+        pos[i] = p;
+    }
+}
+
+}  // namespace
+
+// Symmetric all-pairs acceleration for rank `rank` of `world` (tasks dealt round-robin in
+// descending cost order).  world == 1: acc is the full result (integrate allowed).
+// world > 1: acc holds this rank's partial sum for ALL bodies (zero where it has no task
+// touching the block); the caller all-reduces VSB_F_ACC and then integrates.
+int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int integrate)
+{
+    const int64_t n = c->n, npad = c->npad;
+    if (n <= 0) return VSB_OK;
+    const int warps = (npad >= 262144 * 2) ? 16 : 8;
+    const int S = warps * 128;
+    VSB_CHECK(npad % S == 0, VSB_ERR_STATE, "allpairs_sym: padded size %lld not a multiple of %d",
+              (long long)npad, S);
+    const int M = (int)(npad / S);
+    const int64_t pairs = (int64_t)M * (M + 1) / 2;
+    // P-range chunk: enough tasks to fill the machine ~6x over
+    int64_t want_tasks = (int64_t)c->sm_count * (warps == 16 ? 6 : 12) * world;
+    int chunk = (int)(pairs / want_tasks);
+    if (chunk < 1) chunk = 1;
+    // host-side task table (cached per n / world / rank)
+    if (c->sym_tasks_n != n || c->sym_world != world || c->sym_rank != rank) {
+        struct T { sym_task t; int cost; };
+        T *all = (T *)malloc(sizeof(T) * (size_t)(pairs + M));
+        int *qfirst = (int *)malloc(sizeof(int) * (size_t)(M + 1));
+        VSB_CHECK(all && qfirst, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
+        int nt = 0, slot = 0;
+        for (int q = 0; q < M; ++q) {
+            qfirst[q] = slot;
+            for (int p0 = 0; p0 <= q; p0 += chunk) {
+                int p1 = p0 + chunk > q + 1 ? q + 1 : p0 + chunk;
+                all[nt].t = sym_task{q, p0, p1, slot++};
+                all[nt].cost = 2 * (p1 - p0) - (p1 == q + 1 ? 1 : 0);
+                ++nt;
+            }
+        }
+        qfirst[M] = slot;
+        // descending cost (stable counting order), then deal round-robin to ranks
+        int maxc = 2 * chunk;
+        sym_task *mine = (sym_task *)malloc(sizeof(sym_task) * (size_t)(nt + 1));
+        int nm = 0, dealt = 0;
+        for (int cst = maxc; cst >= 0; --cst)
+            for (int i = 0; i < nt; ++i)
+                if (all[i].cost == cst) {
+                    if (dealt % world == rank) mine[nm++] = all[i].t;
+                    ++dealt;
+                }
+        VSB_TRY(vsb_buf_reserve(c->sym_tab, sizeof(sym_task) * (size_t)(nm + 1) +
+                                                sizeof(int) * (size_t)(M + 1) + 256));
+        VSB_CUDA(cudaMemcpyAsync(c->sym_tab.p, mine, sizeof(sym_task) * (size_t)nm,
+                                 cudaMemcpyHostToDevice, c->stream));
+        char *qf = (char *)c->sym_tab.p + (sizeof(sym_task) * (size_t)(nm + 1) + 255) / 256 * 256;
+        VSB_CUDA(cudaMemcpyAsync(qf, qfirst, sizeof(int) * (size_t)(M + 1), cudaMemcpyHostToDevice,
+                                 c->stream));
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        free(all);
+        free(qfirst);
+        free(mine);
+        c->sym_tasks_n = n;
+        c->sym_world = world;
+        c->sym_rank = rank;
+        c->sym_ntasks = nm;
+        c->sym_nslots = slot;
+        c->sym_qf_off = (int64_t)(qf - (char *)c->sym_tab.p);
+        c->sym_zeroed = nullptr;
+    }
+    const size_t slab = sizeof(double2) * (size_t)S;
+    const size_t bytes_p = slab * (size_t)pairs, bytes_q = slab * (size_t)c->sym_nslots;
+    VSB_TRY(vsb_buf_reserve(c->part, bytes_p + bytes_q));
+    double2 *part_p = (double2 *)c->part.p;
+    double2 *part_q = (double2 *)((char *)c->part.p + bytes_p);
+    if (world > 1 && c->sym_zeroed != c->part.p) {
+        // slabs of tasks owned by other ranks must read as zero in this rank's reduction
+        VSB_CUDA(cudaMemsetAsync(c->part.p, 0, bytes_p + bytes_q, c->stream));
+        c->sym_zeroed = c->part.p;
+    }
+    const sym_task *d_tasks = (const sym_task *)c->sym_tab.p;
+    const int *d_qf = (const int *)((char *)c->sym_tab.p + c->sym_qf_off);
+    const size_t smem = (size_t)S * (2 * sizeof(double2) + sizeof(double));
+    if (c->sym_ntasks > 0) {
+        if (warps == 16) {
+            VSB_CUDA(cudaFuncSetAttribute(allpairs_sym_kernel<16>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            allpairs_sym_kernel<16><<<c->sym_ntasks, 512, smem, c->stream>>>(
+                (const double2 *)c->pos, c->mass, d_tasks, part_p, part_q);
+        } else {
+            VSB_CUDA(cudaFuncSetAttribute(allpairs_sym_kernel<8>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            allpairs_sym_kernel<8><<<c->sym_ntasks, 256, smem, c->stream>>>(
+                (const double2 *)c->pos, c->mass, d_tasks, part_p, part_q);
+        }
+        c->launches += 1;
+    }
+    allpairs_sym_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        part_p, part_q, d_qf, S, M, n, gc, (double2 *)c->acc, (double2 *)c->vel,
+        (double2 *)c->pos, (world == 1 && integrate) ? 1 : 0, 0);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}

@@ -126,6 +126,17 @@ class Device:
     def allpairs_step(self, gc, nsteps=1):
         check(self.L.vsb_allpairs_step(self.h, float(gc), int(nsteps)))
 
+    def set_gravity_mode(self, mode):
+        """0 / "rows": row kernel, 1 / "sym": symmetric kernel (see include/vsb200.h)."""
+        mode = {"rows": 0, "sym": 1}.get(mode, mode)
+        check(self.L.vsb_set_gravity_mode(self.h, int(mode)))
+
+    def allpairs_sym_partial_async(self, gc, rank, world):
+        check(self.L.vsb_allpairs_sym_partial_async(self.h, float(gc), int(rank), int(world)))
+
+    def allpairs_integrate_async(self):
+        check(self.L.vsb_allpairs_integrate_async(self.h))
+
     def allpairs_tick_async(self, gc):
         check(self.L.vsb_allpairs_tick_async(self.h, float(gc)))
 

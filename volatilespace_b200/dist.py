@@ -66,7 +66,7 @@ class ShardedAllPairs:
         self._pos_t = None
         if world > 1:
             import torch
-            npad = (max(self.n, 1) + 1023) // 1024 * 1024
+            npad = (max(self.n, 1) + 2047) // 2048 * 2048     # VSB_PAD of the library
             assert world * self.rpr <= npad
             self._pos_t = device_tensor(dev, F_POS, npad)
             self._stream = torch.cuda.ExternalStream(dev.stream_handle(),
@@ -110,3 +110,55 @@ class ShardedAllPairs:
     def velocities_own(self):
         self.dev.sync()
         return self.dev.get(F_VEL, first=self.row0, count=self.row1 - self.row0)
+
+
+class ShardedAllPairsSym:
+    """MODE_ALLPAIRS with the symmetric kernel (every unordered pair once) over `world`
+    ranks: each rank evaluates its share of the unordered block pairs, the partial
+    accelerations are summed with one NCCL all-reduce (16 B/body), and every rank integrates
+    all bodies (the all-reduce result is identical on all ranks, so the replicas stay in
+    lock-step).  Deterministic run to run for a given world size."""
+
+    def __init__(self, dev, mass, pos, vel, gc, rank=0, world=1, group=None):
+        self.dev, self.gc, self.rank, self.world, self.group = dev, float(gc), rank, world, group
+        self.n = len(mass)
+        self.row0, self.row1 = 0, self.n
+        dev.upload_bodies(mass, pos, vel)
+        dev.set_gravity_mode("sym")
+        self._stream = None
+        if world > 1:
+            import torch
+            from ._lib import F_ACC
+            self._acc_t = device_tensor(dev, F_ACC, self.n)
+            self._stream = torch.cuda.ExternalStream(dev.stream_handle(),
+                                                     device="cuda:%d" % dev.index)
+
+    def tick(self):
+        if self.world == 1:
+            self.dev.allpairs_tick_async(self.gc)
+            return
+        import torch
+        import torch.distributed as dist
+        self.dev.allpairs_sym_partial_async(self.gc, self.rank, self.world)
+        with torch.cuda.stream(self._stream):
+            dist.all_reduce(self._acc_t, group=self.group)
+        self.dev.allpairs_integrate_async()
+
+    def tick_host(self, mass, pos, vel):
+        """End-to-end tick over host buffers; every rank holds (and returns) the full state."""
+        d = self.dev
+        d.set(F_MASS, mass)
+        d.set(F_POS, pos)
+        d.set(F_VEL, vel)
+        self.tick()
+        if self.world > 1:
+            self._stream.synchronize()
+        d.get(F_POS, out=pos)
+        d.get(F_VEL, out=vel)
+
+    def host_bytes_per_tick(self):
+        return self.n * (8 + 16 + 16), self.n * 32
+
+    def positions(self):
+        self.dev.sync()
+        return self.dev.get(F_POS)
