@@ -28,7 +28,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_PAIR = 13          # FP64-pipe instructions per directed pair
+# FP64-pipe instructions per directed pair: row kernel 13; symmetric kernel 8
+# (16 per unordered pair: 10 shared + 3 per side)
+OPS_PER_PAIR = {"rows": 13, "sym": 8}
+FLOPS_PER_PAIR = 13
 METRIC = "body-pair interactions/sec (FP64)"
 UNIT = "pairs/s"
 
@@ -221,16 +224,21 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
         out["solar_system_editor"] = res
     except Exception as e:
         out["solar_system_editor"] = {"error": str(e)[:200]}
-    # config 2: 64k Plummer
+    # config 2: 64k Plummer, both all-pairs kernels
     s = synth.plummer2d(65536)
     dev.upload_bodies(s["mass"], s["pos"], s["vel"])
-    for _ in range(3):
-        dev.allpairs_tick_async(s["gc"])
-    ms = time_ticks(torch, stream, lambda: dev.allpairs_tick_async(s["gc"]), 16, nobar) / 16
     pairs = 65536 * 65535
-    out["plummer64k"] = {"pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms,
-                         "fp64_pipe_frac_at_1965mhz": pairs * FLOPS_PER_PAIR / (ms * 1e-3) /
-                         (148 * 64 * 1965e6)}
+    out["plummer64k"] = {}
+    for mode in ("sym", "rows"):
+        dev.set_gravity_mode(mode)
+        for _ in range(3):
+            dev.allpairs_tick_async(s["gc"])
+        ms = time_ticks(torch, stream, lambda: dev.allpairs_tick_async(s["gc"]), 16, nobar) / 16
+        out["plummer64k"][mode] = {
+            "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms,
+            "fp64_pipe_frac_at_1965mhz": pairs * OPS_PER_PAIR[mode] / (ms * 1e-3) /
+            (148 * 64 * 1965e6)}
+    dev.set_gravity_mode("auto")
     # config 5: collision detection at 256k bodies, first tick of the collapsing cluster and a
     # no-hit variant (radii / 100: worst case for the exhaustive scan)
     s = synth.collapsing_cluster(262144)
@@ -274,7 +282,7 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
     return out
 
 
-def roofline(ops, fp64_flops_microbench, clocks, dev, ms_accel, my_pairs):
+def roofline(ops, fp64_flops_microbench, clocks, dev, ms_accel, my_pairs, ops_per_pair, kernel):
     """FP64-pipe roofline of the gravity kernel.  MEASURED_PEAKS.json has no FP64 figure, so the
     denominator is the pipe's issue peak -- 64 FP64 lanes/SM/clk (what ncu's
     sm__inst_executed_pipe_fp64 pct_of_peak is normalised to) x SMs x the SM clock observed
@@ -286,14 +294,15 @@ def roofline(ops, fp64_flops_microbench, clocks, dev, ms_accel, my_pairs):
     peak = max(nominal, fp64_flops_microbench)
     return {
         "bound": "fp64", "achieved": ops * 2 / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
-        "frac": ops * 2 / peak, "traffic": None, "kernel": "allpairs_accel_kernel",
+        "frac": ops * 2 / peak, "traffic": None,
+        "kernel": "allpairs_sym_kernel" if kernel == "sym" else "allpairs_accel_kernel",
         "ms_per_launch": ms_accel,
         "peak_source": "64 FP64 lanes/SM/clk x 148 SMs x %.0f MHz observed x 2 (issue peak of the "
                        "FP64 pipe; not in MEASURED_PEAKS.json)" % sm_clock,
         "dfma_microbench_tflops": fp64_flops_microbench / 1e12,
         "frac_of_dfma_microbench": ops * 2 / fp64_flops_microbench,
-        "note": "achieved = 13 FP64-pipe instructions per directed pair x pairs/s, each counted "
-                "as one DFMA slot (2 flop)",
+        "note": "achieved = %d FP64-pipe instructions per directed pair x pairs/s, each counted "
+                "as one DFMA slot (2 flop)" % ops_per_pair,
         "flops13_convention_tflops": my_pairs * 13 / (ms_accel * 1e-3) / 1e12,
     }
 
@@ -315,7 +324,7 @@ def run_b200(args):
         barrier = lambda: None
 
     from volatilespace_b200.device import Device
-    from volatilespace_b200.dist import ShardedAllPairs
+    from volatilespace_b200.dist import ShardedAllPairs, ShardedAllPairsSym
     dev = Device(local)
     stream = torch.cuda.ExternalStream(dev.stream_handle(), device="cuda:%d" % local)
     peaks, peaks_src = load_peaks()
@@ -324,7 +333,12 @@ def run_b200(args):
     s, label = make_workload(args.workload)
     n = len(s["mass"])
     pairs = n * (n - 1)
-    sim = ShardedAllPairs(dev, s["mass"], s["pos"], s["vel"], s["gc"], rank, world)
+    if args.gravity == "sym":
+        sim = ShardedAllPairsSym(dev, s["mass"], s["pos"], s["vel"], s["gc"], rank, world)
+    else:
+        dev.set_gravity_mode("rows")
+        sim = ShardedAllPairs(dev, s["mass"], s["pos"], s["vel"], s["gc"], rank, world)
+    ops_per_pair = OPS_PER_PAIR[args.gravity]
     for _ in range(args.warmup):
         sim.tick()
     sampler = ClockSampler(local)
@@ -347,12 +361,15 @@ def run_b200(args):
     torch.cuda.synchronize()
     ev[0].record(stream)
     for _ in range(reps):
-        _lib.check(dev.L.vsb_allpairs_accel_async(dev.h, float(s["gc"])))
+        if args.gravity == "sym" and world > 1:
+            dev.allpairs_sym_partial_async(s["gc"], rank, world)
+        else:
+            _lib.check(dev.L.vsb_allpairs_accel_async(dev.h, float(s["gc"])))
     ev[1].record(stream)
     ev[1].synchronize()
     ms_accel = ev[0].elapsed_time(ev[1]) / reps
-    my_pairs = (sim.row1 - sim.row0) * (n - 1)
-    ops = my_pairs * FLOPS_PER_PAIR / (ms_accel * 1e-3)
+    my_pairs = pairs / world if args.gravity == "sym" else (sim.row1 - sim.row0) * (n - 1)
+    ops = my_pairs * ops_per_pair / (ms_accel * 1e-3)
 
     # end-to-end through the host-buffer path (pinned numpy buffers)
     hp, _k1 = pinned_copy(s["pos"])
@@ -372,8 +389,8 @@ def run_b200(args):
     h2d, d2h = sim.host_bytes_per_tick()
     e2e = {"value": pairs / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": float(dt.item()) * 1e3,
-           "path": "ShardedAllPairs.tick_host -> vsb_bodies_set / vsb_allpairs_tick_async / "
-                   "vsb_bodies_get (pinned host buffers, per rank)"}
+           "path": "%s.tick_host -> vsb_bodies_set / all-pairs tick / vsb_bodies_get (pinned host "
+                   "buffers, per rank)" % type(sim).__name__}
 
     if rank != 0:
         if world > 1:
@@ -386,14 +403,20 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": label, "bodies": n, "pairs_per_step": pairs,
-                   "parallelism": "rows/%d + NCCL all-gather(pos)" % world if world > 1 else "1 GPU",
+                   "kernel": "symmetric (unordered pairs, 8 FP64 instr per directed pair)"
+                   if args.gravity == "sym" else "rows (13 FP64 instr per directed pair)",
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   "unordered block pairs/%d + NCCL all-reduce(acc)" % world
+                                   if args.gravity == "sym" else
+                                   "rows/%d + NCCL all-gather(pos)" % world),
                    "l2": "inputs are streamed tiles of a 24 MiB working set re-read from L2 by "
                          "design (compute-bound kernel); each step rewrites every position"},
         "steps_per_s": 1e3 / ms_step,
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": roofline(ops, fp64_flops_peak, clocks, dev, ms_accel, my_pairs),
+        "roofline": roofline(ops, fp64_flops_peak, clocks, dev, ms_accel, my_pairs, ops_per_pair,
+                             args.gravity),
         "peaks_source": peaks_src,
     }
     if not args.no_extra and world == 1:
@@ -416,6 +439,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="disk1m", choices=["disk1m", "plummer64k"])
+    ap.add_argument("--gravity", default="sym", choices=["sym", "rows"],
+                    help="all-pairs kernel: symmetric (default) or the shard-invariant row kernel")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -115,6 +115,7 @@ int vsb_allpairs_tick_async(vsb_ctx *ctx, double gc);
 /* Acceleration only (accel + reduce into VSB_F_ACC), enqueued without a host sync. */
 int vsb_allpairs_accel_async(vsb_ctx *ctx, double gc);
 /* Kernel choice for the all-pairs entry points when the context owns every row:
+ * -1 = automatic (default: symmetric from 8192 bodies up),
  * 0 = row kernel (13 FP64 instr per directed pair; bit-identical under any row sharding),
  * 1 = symmetric kernel (each unordered pair evaluated once and applied to both bodies,
  *     8 FP64 instr per directed pair; deterministic run to run, last-bit differences from

@@ -29,6 +29,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     s = synth.plummer2d(n, seed=11)
     dev = Device(local)
+    dev.set_gravity_mode("rows")      # the row kernel is the shard-invariant one
     sim = ShardedAllPairs(dev, s["mass"], s["pos"], s["vel"], s["gc"], rank, world)
     for _ in range(ticks):
         sim.tick()
@@ -50,14 +51,29 @@ def main():
         sim2.tick_host(s["mass"], hp, hv)
     ok_host = np.array_equal(hp, pos_single) and np.array_equal(
         hv[sim2.row0:sim2.row1], vel_single[sim2.row0:sim2.row1])
-    flag = torch.tensor([int(ok), int(ok_host)], device="cuda")
+    # symmetric kernel over the ranks (all-reduce of partial accelerations): tolerance parity
+    # with the row kernel, and identical replicas on every rank
+    from volatilespace_b200.dist import ShardedAllPairsSym
+    sym = ShardedAllPairsSym(dev, s["mass"], s["pos"], s["vel"], s["gc"], rank, world)
+    for _ in range(ticks):
+        sym.tick()
+    if world > 1:
+        sym._stream.synchronize()
+    pos_sym = sym.positions()
+    ok_sym = np.allclose(pos_sym, pos_single, rtol=1e-11, atol=1e-9)
+    t = torch.from_numpy(pos_sym).cuda()
+    t0 = t.clone()
+    dist.broadcast(t0, src=0)
+    ok_rep = bool(torch.equal(t, t0))
+    flag = torch.tensor([int(ok), int(ok_host), int(ok_sym), int(ok_rep)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("multigpu_check n=%d world=%d ticks=%d: sharded==single %s, host path %s" %
-              (n, world, ticks, bool(flag[0].item()), bool(flag[1].item())))
+        print("multigpu_check n=%d world=%d ticks=%d: sharded==single %s, host path %s, "
+              "sym within tolerance %s, sym replicas identical %s" %
+              (n, world, ticks, *[bool(x) for x in flag.tolist()]))
     dist.barrier()
     dist.destroy_process_group()
-    if not (flag[0].item() and flag[1].item()):
+    if not all(flag.tolist()):
         sys.exit(1)
 
 

@@ -382,7 +382,8 @@ static bool use_sym(vsb_ctx *c)
     const char *env = getenv("VSB_GRAVITY");
     if (env && env[0] == 'r') return false;
     if (env && env[0] == 's') return true;
-    return c->gravity_mode == 1;
+    if (c->gravity_mode >= 0) return c->gravity_mode == 1;
+    return c->n >= 8192;   // auto: below that the row kernel's finer grid wins
 }
 
 // one acceleration pass (+ integrator) with whichever kernel applies; asynchronous
@@ -395,7 +396,7 @@ static int accel_pass(vsb_ctx *c, double gc, int integrate)
 
 extern "C" int vsb_set_gravity_mode(vsb_ctx *c, int mode)
 {
-    VSB_CHECK(c && (mode == 0 || mode == 1), VSB_ERR_ARG, "vsb_set_gravity_mode: bad argument");
+    VSB_CHECK(c && mode >= -1 && mode <= 1, VSB_ERR_ARG, "vsb_set_gravity_mode: bad argument");
     c->gravity_mode = mode;
     return VSB_OK;
 }

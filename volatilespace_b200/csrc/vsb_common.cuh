@@ -90,7 +90,7 @@ struct vsb_ctx {
     int64_t sym_tasks_n = -1, sym_qf_off = 0;
     int sym_world = 0, sym_rank = 0, sym_ntasks = 0, sym_nslots = 0;
     void *sym_zeroed = nullptr;
-    int gravity_mode = 0;   // 0: row kernel (vsb_gravity.cu), 1: symmetric (vsb_gravity_sym.cu)
+    int gravity_mode = -1;  // -1: auto, 0: row kernel (vsb_gravity.cu), 1: symmetric (vsb_gravity_sym.cu)
     vsb_buf order;       // int64 order (descending mass) + rank
     int64_t order_n = -1; // number of valid entries uploaded to `order`
     vsb_buf sorted;      // sorted-source staging for find_parents

@@ -210,8 +210,8 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
               (long long)npad, S);
     const int M = (int)(npad / S);
     const int64_t pairs = (int64_t)M * (M + 1) / 2;
-    // P-range chunk: enough tasks to fill the machine ~6x over
-    int64_t want_tasks = (int64_t)c->sm_count * (warps == 16 ? 6 : 12) * world;
+    // P-range chunk: enough tasks that the heaviest one is a small fraction of an SM's share
+    int64_t want_tasks = (int64_t)c->sm_count * 32 * world;
     int chunk = (int)(pairs / want_tasks);
     if (chunk < 1) chunk = 1;
     // host-side task table (cached per n / world / rank)

@@ -127,8 +127,8 @@ class Device:
         check(self.L.vsb_allpairs_step(self.h, float(gc), int(nsteps)))
 
     def set_gravity_mode(self, mode):
-        """0 / "rows": row kernel, 1 / "sym": symmetric kernel (see include/vsb200.h)."""
-        mode = {"rows": 0, "sym": 1}.get(mode, mode)
+        """-1 / "auto", 0 / "rows": row kernel, 1 / "sym": symmetric kernel (include/vsb200.h)."""
+        mode = {"auto": -1, "rows": 0, "sym": 1}.get(mode, mode)
         check(self.L.vsb_set_gravity_mode(self.h, int(mode)))
 
     def allpairs_sym_partial_async(self, gc, rank, world):
