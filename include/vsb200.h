@@ -253,6 +253,28 @@ int vsb_kepler_free(vsb_ctx *ctx, int kind);
 int vsb_kepler_curves_get(vsb_ctx *ctx, int kind, int64_t first, int64_t count, double *out);
 int vsb_kepler_curves_device_ptr(vsb_ctx *ctx, int kind, void **dptr_out);
 
+/* --------------------------------------------- culling + visible subset */
+/* phys_shared.culling, phys_shared.py:224-231, over host arrays: mask_out[i] = 1 if the
+ * object is on screen.  screen_bounds = the 2x2 array [[x0,y0],[x1,y1]] flattened. */
+int vsb_host_culling(vsb_ctx *ctx, int64_t n, const double *coords, const double *radius,
+                     const double *screen_bounds, double zoom, unsigned char *mask_out);
+/* The same predicate on the device-resident positions of the Kepler state; returns the visible
+ * indices in ascending order (np.arange(n)[truth], phys_body.py:208-210, phys_vessel.py:264-265).
+ * radius: host array (n) or NULL for zeros; idx_out needs room for n entries. */
+int vsb_kepler_culling(vsb_ctx *ctx, int kind, const double *radius, const double *screen_bounds,
+                       double zoom, int64_t *idx_out, int64_t *count_out);
+/* visible_orbits of phys_body.py:212-216 / phys_vessel.py:267-271:
+ * ((ref_visible[ref] && ref_coi[ref] > 8/zoom) || ref == 0) && size*zoom < screen_x*15, with
+ * size = a (bodies) or pe_d (vessels); ascending indices. */
+int vsb_kepler_visible_orbits(vsb_ctx *ctx, int kind, int64_t nref,
+                              const unsigned char *ref_visible, const double *ref_coi,
+                              const double *size, double zoom, double screen_x, int64_t *idx_out,
+                              int64_t *count_out);
+/* Gather the moved curves of the listed objects into out (count,P,2) with one copy: only
+ * visible curves are drawn (game.py:1403-1407). */
+int vsb_kepler_curves_gather(vsb_ctx *ctx, int kind, const int64_t *idx, int64_t count,
+                             double *out);
+
 #ifdef __cplusplus
 }
 #endif

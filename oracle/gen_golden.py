@@ -324,6 +324,65 @@ def gen_game(ns, conf, bd, bod):
     save("game_mode", **out)
 
 
+def gen_culling(ns, conf, bd, bod):
+    """N3: phys_shared.culling (jitted) on random clouds, phys_body / phys_vessel culling on the
+    Solar System game state + synthetic vessels."""
+    import copy
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    from volatilespace.physics import convert
+    sys.path.remove(rh.REFERENCE_ROOT)
+    rng = np.random.default_rng(20240616)
+    out = {}
+    n = 500
+    coords = rng.uniform(-2000, 2000, (n, 2))
+    radius = rng.uniform(0, 60, n)
+    cases = []
+    for k in range(12):
+        c = rng.uniform(-1500, 1500, 2)
+        half = rng.uniform(50, 1500, 2)
+        zoom = float(rng.choice([0.05, 0.3, 1.0, 4.0]))
+        sb = np.array([[c[0] - half[0], c[1] + half[1]], [c[0] + half[0], c[1] - half[1]]])
+        if k == 0:   # touch a bound exactly
+            sb[0, 0] = coords[7, 0] + radius[7] + 2 / zoom
+        cases.append((sb, zoom, ns.phys_shared.culling(coords, radius, sb, zoom)))
+    out.update(c_coords=coords, c_radius=radius, c_sb=np.array([c[0] for c in cases]),
+               c_zoom=np.array([c[1] for c in cases]), c_mask=np.array([c[2] for c in cases]))
+    # body culling on the Solar System (game state after initial)
+    korb = convert.to_kepler(bd["mass"], copy.deepcopy(bod), conf["gc"], conf["coi_coef"])
+    pb = ns.phys_body.Physics()
+    rh.set_curve_points(ns, pb, 16)
+    pb.load(conf, copy.deepcopy(bd), copy.deepcopy(korb))
+    body_data, body_orb, pos, ma, ea, cm = pb.initial(1)
+    out.update(b_pos=pos.copy(), b_radius=pb.radius.copy(), b_atm_h=pb.atm_h.copy(),
+               b_coi=pb.coi.copy(), b_ref=np.array(pb.ref), b_a=pb.a.copy(),
+               b_screen_x=float(pb.screen_x))
+    nv = 300
+    pv = ns.phys_vessel.Physics()
+    pv.names = np.array(["v%d" % i for i in range(nv)])
+    pv.pos = pos[rng.integers(0, len(pos), nv)] + rng.uniform(-300, 300, (nv, 2))
+    pv.ref = rng.integers(0, len(pos), nv)
+    pv.pe_d = rng.uniform(10, 40000, nv)
+    pv.body_dr = np.ones(len(pos))
+    pv.body_coi = pb.coi.copy()
+    out.update(v_pos=pv.pos.copy(), v_ref=pv.ref.copy(), v_pe_d=pv.pe_d.copy())
+    bcases = []
+    for k in range(8):
+        centre = pos[int(rng.integers(0, len(pos)))] if k % 2 else np.zeros(2)
+        half = np.array([683.0, 384.0]) / [0.02, 0.1, 0.5, 2.0][k % 4]
+        zoom = [0.02, 0.1, 0.5, 2.0][k % 4]
+        sb = np.array([[centre[0] - half[0], centre[1] + half[1]],
+                       [centre[0] + half[0], centre[1] - half[1]]])
+        vb, vc, vo = pb.culling(sb, zoom)
+        vv, vvo = pv.culling(sb, zoom, vc)
+        bcases.append((sb, zoom, vb, vc, vo, np.array(vv), np.array(vvo)))
+    out["b_sb"] = np.array([c[0] for c in bcases])
+    out["b_zoom"] = np.array([c[1] for c in bcases])
+    for k, c in enumerate(bcases):
+        out.update({"b%d_bodies" % k: c[2], "b%d_coi" % k: c[3], "b%d_orbits" % k: c[4],
+                    "b%d_vessels" % k: c[5], "b%d_vorbits" % k: c[6]})
+    save("culling", **out)
+
+
 def main():
     ns = rh.load()
     conf, bd, bod = gen_solar(ns)
@@ -332,6 +391,7 @@ def main():
     gen_allpairs(ns)
     gen_kepler_solvers(ns)
     gen_game(ns, conf, bd, bod)
+    gen_culling(ns, conf, bd, bod)
 
 
 if __name__ == "__main__":

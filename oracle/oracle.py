@@ -232,6 +232,39 @@ def editor_curve(ecc_v, semi_major, semi_minor, focus, periapsis_arg, parents, p
     return out
 
 
+def culling(coords, radius, screen_bounds, zoom):
+    """phys_shared.culling, phys_shared.py:224-231 (numpy restatement, same expressions)."""
+    coords, radius, sb = _f(coords), _f(radius), _f(screen_bounds).reshape(2, 2)
+    min_dim = (coords.T + radius).T + 2 / zoom > np.array([sb[0, 0], sb[1, 1]])
+    max_dim = (coords.T - radius).T + 2 / zoom < np.array([sb[1, 0], sb[0, 1]])
+    return np.logical_and(np.logical_and(min_dim[:, 0], min_dim[:, 1]),
+                          np.logical_and(max_dim[:, 0], max_dim[:, 1]))
+
+
+def body_culling(pos, radius, atm_h, coi, ref, a, sim_screen, zoom, screen_x):
+    """phys_body.Physics.culling, phys_body.py:201-218."""
+    n = len(coi)
+    visible_bodies = np.arange(n)[culling(pos, (radius + atm_h) * zoom, sim_screen, zoom)]
+    coi_truth = culling(pos, coi, sim_screen, zoom)
+    visible_coi = np.concatenate(([0], np.arange(n)[coi_truth]))
+    t = np.logical_and(coi_truth[ref], coi[ref] > 8 / zoom)
+    t = np.logical_or(t, ref == 0)
+    t = np.logical_and(t, a * zoom < screen_x * 15)
+    return visible_bodies, visible_coi, np.arange(n)[t]
+
+
+def vessel_culling(pos, ref, pe_d, body_coi, visible_coi, sim_screen, zoom, screen_x):
+    """phys_vessel.Physics.culling, phys_vessel.py:258-273."""
+    n = len(ref)
+    visible_vessels = np.arange(n)[culling(pos, np.array([10] * n) / zoom, sim_screen, zoom)]
+    coi_truth = np.array([False] * len(body_coi))
+    coi_truth[visible_coi] = True
+    t = np.logical_and(coi_truth[ref], body_coi[ref] > 8 / zoom)
+    t = np.logical_or(t, ref == 0)
+    t = np.logical_and(t, pe_d * zoom < screen_x * 15)
+    return visible_vessels, np.arange(n)[t]
+
+
 def body_radius(mass, den, rad_mult):
     """A5 radius only, phys_editor.py:580-581 (host numpy on both sides)."""
     volume = mass / den

@@ -220,6 +220,60 @@ def test_kepler_full_size_properties(dev):
     dev.kepler_free(KIND_VESSEL)
 
 
+def test_culling_golden(dev):
+    """N3: phys_shared.culling mask and the body / vessel visible lists, bit-exact."""
+    from volatilespace_b200._lib import KIND_BODY, KIND_VESSEL, K_POS
+    g = golden("culling")
+    for sb, zoom, mask in zip(g["c_sb"], g["c_zoom"], g["c_mask"]):
+        got = dev.host_culling(g["c_coords"], g["c_radius"], sb, float(zoom))
+        assert np.array_equal(got, mask)
+    from volatilespace_b200.phys_body import Physics as BodyPhysics
+    from volatilespace_b200.phys_vessel import Physics as VesselPhysics
+    nb, nv = len(g["b_coi"]), len(g["v_ref"])
+    z = np.zeros(nb)
+    dev.kepler_load(KIND_BODY, 8, g["b_a"], z, z, z, z, z, z, z, z, g["b_ref"])
+    dev.kepler_set(KIND_BODY, K_POS, g["b_pos"])
+    zv = np.zeros(nv)
+    dev.kepler_load(KIND_VESSEL, 8, zv, zv, zv, zv, zv, zv, zv, zv, zv, g["v_ref"])
+    dev.kepler_set(KIND_VESSEL, K_POS, g["v_pos"])
+    pb = BodyPhysics(dev, curve_points=8)
+    pb.n_bodies, pb.coi, pb.a = nb, g["b_coi"], g["b_a"]
+    pv = VesselPhysics(dev, curve_points=8)
+    pv.n_vessels, pv.pe_d = nv, g["v_pe_d"]
+    sx = float(g["b_screen_x"])
+    for k, (sb, zoom) in enumerate(zip(g["b_sb"], g["b_zoom"])):
+        vb, vc, vo = pb.culling(sb, float(zoom), g["b_radius"], g["b_atm_h"], sx)
+        assert np.array_equal(vb, g["b%d_bodies" % k])
+        assert np.array_equal(vc, g["b%d_coi" % k])
+        assert np.array_equal(vo, g["b%d_orbits" % k])
+        vv, vvo = pv.culling(sb, float(zoom), vc, g["b_coi"], sx)
+        assert np.array_equal(vv, g["b%d_vessels" % k])
+        assert np.array_equal(vvo, g["b%d_vorbits" % k])
+
+
+def test_culling_and_gather_at_scale(dev, oracle):
+    """1M resident objects: visible list equals the oracle's, gathered curves equal the slices."""
+    from volatilespace_b200 import synth
+    from volatilespace_b200._lib import KIND_VESSEL, K_POS
+    n, P = 1 << 20, 64
+    s = synth.kepler_objects(n, seed=77)
+    dev.kepler_load(KIND_VESSEL, P, s["a"], s["b"], s["f"], s["ecc"], s["pea"], s["n"], s["dr"],
+                    s["ma"], s["ea"], s["ref"])
+    dev.kepler_tick(KIND_VESSEL, 1.0, s["body_pos"])
+    pos = dev.kepler_get(KIND_VESSEL, K_POS, n)
+    sb = np.array([[-2.0e4, 3.0e4], [5.0e4, -1.0e4]])
+    rad = np.full(n, 25.0)
+    idx = dev.kepler_culling(KIND_VESSEL, n, rad, sb, 0.01)
+    want = np.nonzero(oracle.culling(pos, rad, sb, 0.01))[0]
+    assert np.array_equal(idx, want) and 100 < len(idx) < n
+    pick = idx[:: max(1, len(idx) // 500)]
+    got = dev.kepler_curves_gather(KIND_VESSEL, pick, P)
+    for k in (0, len(pick) // 2, len(pick) - 1):
+        assert np.array_equal(got[k], dev.kepler_curves_get(KIND_VESSEL, int(pick[k]), 1, P)[0])
+    assert len(dev.kepler_culling(KIND_VESSEL, n, None, np.array([[1e9, 2e9], [2e9, 1e9]]), 1.0)) == 0
+    dev.kepler_free(KIND_VESSEL)
+
+
 def test_kepler_errors(dev):
     from volatilespace_b200._lib import VsbError, KIND_BODY, KIND_VESSEL
     dev.kepler_free(KIND_BODY)

@@ -227,3 +227,21 @@ def test_game_vessel_path(oracle):
     assert_close(curves, g["v_curves"], rtol=1e-12, atol=1e-9)
     assert_close(oracle.curve_move_to(curves, g["v_body_pos"], g["v_ref"], orb["f"], g["v_pea"]),
                  g["v_curves_mov"], rtol=1e-12, atol=1e-9)
+
+
+# ------------------------------------------------------------- N3 culling
+def test_culling(oracle):
+    g = golden("culling")
+    for sb, zoom, mask in zip(g["c_sb"], g["c_zoom"], g["c_mask"]):
+        assert np.array_equal(oracle.culling(g["c_coords"], g["c_radius"], sb, float(zoom)), mask)
+    for k, (sb, zoom) in enumerate(zip(g["b_sb"], g["b_zoom"])):
+        vb, vc, vo = oracle.body_culling(g["b_pos"], g["b_radius"], g["b_atm_h"], g["b_coi"],
+                                         g["b_ref"], g["b_a"], sb, float(zoom),
+                                         float(g["b_screen_x"]))
+        assert np.array_equal(vb, g["b%d_bodies" % k])
+        assert np.array_equal(vc, g["b%d_coi" % k])
+        assert np.array_equal(vo, g["b%d_orbits" % k])
+        vv, vvo = oracle.vessel_culling(g["v_pos"], g["v_ref"], g["v_pe_d"], g["b_coi"], vc, sb,
+                                        float(zoom), float(g["b_screen_x"]))
+        assert np.array_equal(vv, g["b%d_vessels" % k])
+        assert np.array_equal(vvo, g["b%d_vorbits" % k])

@@ -28,6 +28,7 @@ SOURCES = {
     "vsb_broadphase.cu": ["-fmad=false"],
     "vsb_editor.cu": ["-fmad=false"],
     "vsb_kepler.cu": ["-fmad=false"],
+    "vsb_visible.cu": ["-fmad=false"],
 }
 
 

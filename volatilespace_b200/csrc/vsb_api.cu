@@ -1127,6 +1127,129 @@ extern "C" int vsb_kepler_curves_device_ptr(vsb_ctx *c, int kind, void **out)
     return VSB_OK;
 }
 
+// ---------------------------------------------------------------- N3: culling / visible subset
+// staging layout in host_stage: flags[n] | radius/size[n] | idx[n] | counts[ceil(n/256)] | total
+struct vis_stage {
+    unsigned char *flags;
+    double *vals;
+    int64_t *idx;
+    int *counts;
+    int64_t *total;
+    unsigned char *ref_vis;
+    double *ref_coi;
+};
+
+static int vis_reserve(vsb_ctx *c, int64_t n, int64_t nref, vis_stage *st)
+{
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t o_flags = 0, o_vals = al((size_t)n), o_idx = o_vals + al(8 * (size_t)n),
+                 o_cnt = o_idx + al(8 * (size_t)n), o_tot = o_cnt + al(4 * (size_t)(n / 256 + 2)),
+                 o_rv = o_tot + 256, o_rc = o_rv + al((size_t)nref),
+                 total = o_rc + al(8 * (size_t)nref);
+    VSB_TRY(vsb_buf_reserve(c->host_stage, total));
+    char *b = (char *)c->host_stage.p;
+    st->flags = (unsigned char *)(b + o_flags);
+    st->vals = (double *)(b + o_vals);
+    st->idx = (int64_t *)(b + o_idx);
+    st->counts = (int *)(b + o_cnt);
+    st->total = (int64_t *)(b + o_tot);
+    st->ref_vis = (unsigned char *)(b + o_rv);
+    st->ref_coi = (double *)(b + o_rc);
+    return VSB_OK;
+}
+
+static int vis_finish(vsb_ctx *c, vis_stage &st, int64_t n, int64_t *idx_out, int64_t *count_out)
+{
+    VSB_TRY(vsb_launch_compact(c, st.flags, n, st.counts, st.total, st.idx));
+    int64_t count = 0;
+    VSB_TRY(d2h(c, &count, st.total, sizeof(int64_t)));
+    *count_out = count;
+    if (count > 0 && idx_out) VSB_TRY(d2h(c, idx_out, st.idx, 8 * (size_t)count));
+    return VSB_OK;
+}
+
+extern "C" int vsb_host_culling(vsb_ctx *c, int64_t n, const double *coords, const double *radius,
+                                const double *screen_bounds, double zoom, unsigned char *mask_out)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && (n == 0 || (coords && radius && screen_bounds && mask_out)) && zoom != 0.0,
+              VSB_ERR_ARG, "vsb_host_culling: bad argument");
+    if (n == 0) return VSB_OK;
+    vis_stage st;
+    VSB_TRY(vis_reserve(c, 3 * n, 0, &st));   // idx area doubles as the coords staging (16n bytes)
+    double *d_pos = (double *)st.idx;
+    VSB_CUDA(cudaMemcpyAsync(d_pos, coords, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(st.vals, radius, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_culling_flags(c, d_pos, st.vals, n, screen_bounds, zoom, st.flags));
+    return d2h(c, mask_out, st.flags, (size_t)n);
+}
+
+extern "C" int vsb_kepler_culling(vsb_ctx *c, int kind, const double *radius,
+                                  const double *screen_bounds, double zoom, int64_t *idx_out,
+                                  int64_t *count_out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_culling", kind, &k));
+    VSB_CHECK(k->n > 0, VSB_ERR_STATE, "vsb_kepler_culling: no state loaded for this kind");
+    VSB_CHECK(screen_bounds && count_out && zoom != 0.0, VSB_ERR_ARG,
+              "vsb_kepler_culling: bad argument");
+    vis_stage st;
+    VSB_TRY(vis_reserve(c, k->n, 0, &st));
+    if (radius)
+        VSB_CUDA(cudaMemcpyAsync(st.vals, radius, 8 * (size_t)k->n, cudaMemcpyHostToDevice,
+                                 c->stream));
+    VSB_TRY(vsb_launch_culling_flags(c, k->pos, radius ? st.vals : nullptr, k->n, screen_bounds,
+                                     zoom, st.flags));
+    return vis_finish(c, st, k->n, idx_out, count_out);
+}
+
+extern "C" int vsb_kepler_visible_orbits(vsb_ctx *c, int kind, int64_t nref,
+                                         const unsigned char *ref_visible, const double *ref_coi,
+                                         const double *size, double zoom, double screen_x,
+                                         int64_t *idx_out, int64_t *count_out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_visible_orbits", kind, &k));
+    VSB_CHECK(k->n > 0, VSB_ERR_STATE, "vsb_kepler_visible_orbits: no state loaded for this kind");
+    VSB_CHECK(nref > 0 && ref_visible && ref_coi && size && count_out && zoom != 0.0, VSB_ERR_ARG,
+              "vsb_kepler_visible_orbits: bad argument");
+    vis_stage st;
+    VSB_TRY(vis_reserve(c, k->n, nref, &st));
+    VSB_CUDA(cudaMemcpyAsync(st.vals, size, 8 * (size_t)k->n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(st.ref_vis, ref_visible, (size_t)nref, cudaMemcpyHostToDevice,
+                             c->stream));
+    VSB_CUDA(cudaMemcpyAsync(st.ref_coi, ref_coi, 8 * (size_t)nref, cudaMemcpyHostToDevice,
+                             c->stream));
+    VSB_TRY(vsb_launch_orbit_flags(c, k->ref, st.vals, k->n, st.ref_vis, st.ref_coi, zoom, screen_x,
+                                   st.flags));
+    return vis_finish(c, st, k->n, idx_out, count_out);
+}
+
+extern "C" int vsb_kepler_curves_gather(vsb_ctx *c, int kind, const int64_t *idx, int64_t count,
+                                        double *out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_curves_gather", kind, &k));
+    VSB_CHECK(k->n > 0 && k->curves.p, VSB_ERR_STATE,
+              "vsb_kepler_curves_gather: no curves generated yet");
+    VSB_CHECK(count >= 0 && (count == 0 || (idx && out)), VSB_ERR_ARG,
+              "vsb_kepler_curves_gather: bad argument");
+    if (count == 0) return VSB_OK;
+    for (int64_t i = 0; i < count; ++i)
+        VSB_CHECK(idx[i] >= 0 && idx[i] < k->n, VSB_ERR_ARG,
+                  "vsb_kepler_curves_gather: index %lld out of range", (long long)idx[i]);
+    const size_t bytes = 16 * (size_t)count * (size_t)k->P;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, bytes + 8 * (size_t)count + 256));
+    double *d_out = (double *)c->host_stage.p;
+    int64_t *d_idx = (int64_t *)((char *)c->host_stage.p + (bytes + 255) / 256 * 256);
+    VSB_CUDA(cudaMemcpyAsync(d_idx, idx, 8 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_curves_gather(c, (const double *)k->curves.p, d_idx, count, k->P, d_out));
+    return d2h(c, out, d_out, bytes);
+}
+
 extern "C" int vsb_kepler_free(vsb_ctx *c, int kind)
 {
     CTX(c);

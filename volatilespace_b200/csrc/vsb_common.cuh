@@ -221,6 +221,16 @@ int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const 
 int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptrs,
                            const int *widths, int nfields, double *d_out, int64_t *words_out);
 int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double *d_out);
+// culling / visible subset (vsb_visible.cu)
+int vsb_launch_culling_flags(vsb_ctx *c, const double *d_pos, const double *d_radius, int64_t n,
+                             const double *sb4, double zoom, unsigned char *d_flags);
+int vsb_launch_orbit_flags(vsb_ctx *c, const int64_t *d_ref, const double *d_size, int64_t n,
+                           const unsigned char *d_ref_visible, const double *d_ref_coi, double zoom,
+                           double screen_x, unsigned char *d_flags);
+int vsb_launch_compact(vsb_ctx *c, const unsigned char *d_flags, int64_t n, int *d_counts,
+                       int64_t *d_total, int64_t *d_idx);
+int vsb_launch_curves_gather(vsb_ctx *c, const double *d_curves, const int64_t *d_idx,
+                             int64_t count, int64_t P, double *d_out);
 // kepler (vsb_kepler.cu)
 int vsb_launch_kepler_move(vsb_ctx *c, vsb_kepler_state &k, double warp);
 int vsb_launch_kepler_curves(vsb_ctx *c, vsb_kepler_state &k, int64_t first, int64_t count,

@@ -306,6 +306,38 @@ class Device:
         check(self.L.vsb_kepler_curves_get(self.h, kind, int(first), int(count), ptr(out)))
         return out
 
+    def host_culling(self, coords, radius, screen_bounds, zoom):
+        coords, radius, sb = f64(coords), f64(radius), f64(screen_bounds)
+        mask = np.empty(len(radius), dtype=np.uint8)
+        check(self.L.vsb_host_culling(self.h, len(radius), ptr(coords), ptr(radius), ptr(sb),
+                                      float(zoom), ptr(mask)))
+        return mask.astype(bool)
+
+    def kepler_culling(self, kind, n, radius, screen_bounds, zoom):
+        radius = None if radius is None else f64(radius)
+        sb = f64(screen_bounds)
+        idx = np.empty(n, dtype=np.int64)
+        cnt = C.c_int64()
+        check(self.L.vsb_kepler_culling(self.h, kind, ptr(radius), ptr(sb), float(zoom), ptr(idx),
+                                        C.byref(cnt)))
+        return idx[:cnt.value].copy()
+
+    def kepler_visible_orbits(self, kind, n, ref_visible, ref_coi, size, zoom, screen_x):
+        rv = np.ascontiguousarray(ref_visible, dtype=np.uint8)
+        rc, size = f64(ref_coi), f64(size)
+        idx = np.empty(n, dtype=np.int64)
+        cnt = C.c_int64()
+        check(self.L.vsb_kepler_visible_orbits(self.h, kind, len(rv), ptr(rv), ptr(rc), ptr(size),
+                                               float(zoom), float(screen_x), ptr(idx),
+                                               C.byref(cnt)))
+        return idx[:cnt.value].copy()
+
+    def kepler_curves_gather(self, kind, idx, P):
+        idx = i64(idx)
+        out = np.empty((len(idx), int(P), 2))
+        check(self.L.vsb_kepler_curves_gather(self.h, kind, ptr(idx), len(idx), ptr(out)))
+        return out
+
     def kepler_free(self, kind):
         check(self.L.vsb_kepler_free(self.h, kind))
 

@@ -91,5 +91,21 @@ class Physics:
         self.dev.kepler_curves(KIND_BODY)
         if visible is None:
             return self.dev.kepler_curves_get(KIND_BODY, 0, self.n_bodies, self.curve_points)
-        return {int(i): self.dev.kepler_curves_get(KIND_BODY, int(i), 1, self.curve_points)[0]
-                for i in visible}
+        got = self.dev.kepler_curves_gather(KIND_BODY, visible, self.curve_points)
+        return {int(i): got[k] for k, i in enumerate(visible)}
+
+    # phys_body.py:201-218; radius / atm_h are the caller's body data (UI side)
+    def culling(self, sim_screen, zoom, radius=None, atm_h=None, screen_x=1366):
+        n = self.n_bodies
+        radius = np.zeros(n) if radius is None else np.asarray(radius, dtype=np.float64)
+        atm_h = np.zeros(n) if atm_h is None else np.asarray(atm_h, dtype=np.float64)
+        dev = self.dev
+        visible_bodies = dev.kepler_culling(KIND_BODY, n, (radius + atm_h) * zoom, sim_screen, zoom)
+        coi_idx = dev.kepler_culling(KIND_BODY, n, self.coi, sim_screen, zoom)
+        visible_coi = np.concatenate(([0], coi_idx))
+        coi_truth = np.zeros(n, dtype=np.uint8)
+        coi_truth[coi_idx] = 1
+        self.visible_coi_truth = coi_truth
+        visible_orbits = dev.kepler_visible_orbits(KIND_BODY, n, coi_truth, self.coi, self.a, zoom,
+                                                   screen_x)
+        return visible_bodies, visible_coi, visible_orbits

@@ -21,3 +21,8 @@ def curve_points(ecc, a, b, pea, t):
 def curve_move_to(curves, body_pos, ref, f, pea):
     """phys_shared.py:219-222."""
     return default_device().host_curve_move_to(curves, body_pos, ref, f, pea)
+
+
+def culling(coords, radius, screen_bounds, zoom):
+    """phys_shared.py:224-231: boolean mask of the objects that are on screen."""
+    return default_device().host_culling(coords, radius, screen_bounds, zoom)

@@ -67,8 +67,21 @@ class Physics:
         self.dev.kepler_curves(KIND_VESSEL)
         if visible is None:
             return self.dev.kepler_curves_get(KIND_VESSEL, 0, self.n_vessels, self.curve_points)
-        return {int(i): self.dev.kepler_curves_get(KIND_VESSEL, int(i), 1, self.curve_points)[0]
-                for i in visible}
+        got = self.dev.kepler_curves_gather(KIND_VESSEL, visible, self.curve_points)
+        return {int(i): got[k] for k, i in enumerate(visible)}
+
+    # phys_vessel.py:258-273
+    def culling(self, sim_screen, zoom, visible_coi, body_coi, screen_x=1366):
+        n = self.n_vessels
+        dev = self.dev
+        self.visible_vessels = dev.kepler_culling(KIND_VESSEL, n, np.full(n, 10.0) / zoom,
+                                                  sim_screen, zoom)
+        body_coi = np.asarray(body_coi, dtype=np.float64)
+        coi_truth = np.zeros(len(body_coi), dtype=np.uint8)
+        coi_truth[np.asarray(visible_coi, dtype=np.int64)] = 1
+        self.visible_orbits = dev.kepler_visible_orbits(KIND_VESSEL, n, coi_truth, body_coi,
+                                                        self.pe_d, zoom, screen_x)
+        return self.visible_vessels, self.visible_orbits
 
     def tick(self, warp, body_pos):
         """move + curve_move in one fused kernel (results stay on the device)."""
