@@ -253,6 +253,21 @@ int vsb_kepler_free(vsb_ctx *ctx, int kind);
 int vsb_kepler_curves_get(vsb_ctx *ctx, int kind, int64_t first, int64_t count, double *out);
 int vsb_kepler_curves_device_ptr(vsb_ctx *ctx, int kind, void **dptr_out);
 
+/* --------------------------------------------- per-frame body passes
+ * Physics.body (phys_editor.py:577-599, without the radius, which stays host numpy),
+ * Physics.temp_color (:602-651) and Physics.classify (:654-670) in one pass over host arrays.
+ * consts12 = {gc_sim, rad_mult, mass_thermal_mult, min_planet_mass, gc_real, c, ls, ms,
+ * sqrt(2), pi**(1/4), sigma**(1/4), 4*pi} evaluated by the caller with the reference's own
+ * expressions (phys_shared.py:13-17).  atm_h is in/out (bodies without an atmosphere keep their
+ * value); base_color / color are (n,3) int64 like the reference's int arrays; stellar_class:
+ * 0 Unknown, 1 M, 2 K, 3 G, 4 F, 5 A, 6 B, 7 O. */
+int vsb_host_body_thermal(vsb_ctx *ctx, int64_t n, const double *consts12, const double *mass,
+                          const double *den, const double *rad, const double *atm_pres0,
+                          const double *atm_scale_h, const double *atm_den0, double *atm_h,
+                          const int64_t *base_color, double *surf_grav, double *luminosity,
+                          double *temp, double *rad_sc, int64_t *color, double *types,
+                          int32_t *stellar_class);
+
 /* --------------------------------------------- culling + visible subset */
 /* phys_shared.culling, phys_shared.py:224-231, over host arrays: mask_out[i] = 1 if the
  * object is on screen.  screen_bounds = the 2x2 array [[x0,y0],[x1,y1]] flattened. */

@@ -383,6 +383,54 @@ def gen_culling(ns, conf, bd, bod):
     save("culling", **out)
 
 
+def gen_body_data(ns, conf, bd, bod):
+    """N4: reference Physics.body / temp_color / classify on the Solar System and on a synthetic
+    population spanning dwarf planets to black holes."""
+    import copy
+    rng = np.random.default_rng(20240617)
+    out = {}
+    for tag in ("solar", "synth"):
+        if tag == "solar":
+            body_data, orb = copy.deepcopy(bd), copy.deepcopy(bod)
+        else:
+            n = 400
+            mass = 10 ** rng.uniform(-2, 7.5, n)
+            mass[0] = 10 ** 8
+            den_arr = 10 ** rng.uniform(2, 5, n)
+            den_arr[1:9] = 10 ** rng.uniform(14, 22, 8)     # compact objects -> black holes
+            mass[1:9] = 10 ** rng.uniform(5, 8, 8)
+            body_data = {
+                "name": np.array(["b%d" % i for i in range(n)]), "mass": mass,
+                "den": den_arr,
+                "color": rng.integers(0, 256, (n, 3)),
+                "atm_pres0": np.where(rng.uniform(0, 1, n) < 0.5, rng.uniform(0.1, 90, n), 0.0),
+                "atm_scale_h": np.where(rng.uniform(0, 1, n) < 0.7, rng.uniform(0.005, 0.02, n), 0.0),
+                "atm_den0": np.where(rng.uniform(0, 1, n) < 0.7, rng.uniform(0.5, 70, n), 0.0)}
+            r = rng.uniform(1e3, 1e6, n)
+            th = rng.uniform(0, 2 * np.pi, n)
+            orb = {"kepler": False, "pos": np.stack([r * np.cos(th), r * np.sin(th)], axis=1),
+                   "vel": rng.uniform(-1, 1, (n, 2))}
+            orb["pos"][0] = 0
+        ph = ns.phys_editor.Physics()
+        ph.load_system(conf, body_data, orb)
+        color = ph.temp_color()
+        ph.classify()
+        out.update({tag + "_mass": np.array(ph.mass), tag + "_den": np.array(ph.den),
+                    tag + "_rad": np.array(ph.rad),
+                    tag + "_atm_pres0": np.array(ph.atm_pres0),
+                    tag + "_atm_scale_h": np.array(ph.atm_scale_h),
+                    tag + "_atm_den0": np.array(ph.atm_den0),
+                    tag + "_base_color": np.array(ph.base_color),
+                    tag + "_surf_grav": np.array(ph.surf_grav), tag + "_atm_h": np.array(ph.atm_h),
+                    tag + "_luminosity": np.array(ph.luminosity), tag + "_temp": np.array(ph.temp),
+                    tag + "_rad_sc": np.array(ph.rad_sc), tag + "_color": np.array(color),
+                    tag + "_types": np.array(ph.types),
+                    tag + "_stellar_class": np.array(ph.stellar_class)})
+    out.update(gc=conf["gc"], rad_mult=conf["rad_mult"], mass_thermal_mult=conf["mass_thermal_mult"],
+               min_mass=conf["min_planet_mass"])
+    save("body_data", **out)
+
+
 def main():
     ns = rh.load()
     conf, bd, bod = gen_solar(ns)
@@ -392,6 +440,7 @@ def main():
     gen_kepler_solvers(ns)
     gen_game(ns, conf, bd, bod)
     gen_culling(ns, conf, bd, bod)
+    gen_body_data(ns, conf, bd, bod)
 
 
 if __name__ == "__main__":

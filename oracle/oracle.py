@@ -265,6 +265,60 @@ def vessel_culling(pos, ref, pe_d, body_coi, visible_coi, sim_screen, zoom, scre
     return visible_vessels, np.arange(n)[t]
 
 
+# phys_shared.py:13-17
+GC_REAL = 6.674 * 10**-11
+C_LIGHT = 299792458
+SIGMA = 5.670374419 * 10**-8
+LS = 3.828 * 10**26
+MS = 1.9884 * 10**30
+
+
+def body_thermal(mass, den, rad, atm_pres0, atm_scale_h, atm_den0, atm_h, base_color, gc,
+                 rad_mult, mass_thermal_mult, min_mass):
+    """N4: Physics.body (phys_editor.py:583-599), temp_color (:602-651), classify (:654-670),
+    numpy restatement.  Returns dict."""
+    import math
+    mass, den, rad = _f(mass), _f(den), _f(rad)
+    atm_h = _f(atm_h).copy()
+    surf_grav = gc * mass / rad**2
+    for b in range(len(mass)):
+        if atm_pres0[b] != 0 and atm_scale_h[b] != 0 and atm_den0[b] != 0:
+            atm_h[b] = -atm_scale_h[b] * math.log(0.001 / atm_den0[b]) * rad_mult
+    tm = mass * mass_thermal_mult
+    tr = np.cbrt(3 * (tm / den) / (4 * np.pi))
+    lum = LS * (tm / MS)**3.5
+    temp = lum**(1 / 4) / (np.sqrt(tr) * np.sqrt(2) * np.pi**(1 / 4) * SIGMA**(1 / 4))
+    rad_sc = 2 * tm * GC_REAL / C_LIGHT**2
+    rad_sc = rad_sc * rad / tr
+    atm_h = np.where(rad_sc > rad, 0, atm_h)
+    base = np.asarray(base_color)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        fg = np.where((temp > 1000) & (temp <= 2300), 1 - 1 / (1300 / (temp - 1000)), -1)
+        color = np.copy(base)
+        for ch, hot in ((0, 255), (1, 184), (2, 111)):
+            color[:, ch] = np.where(fg != -1, base[:, ch] * fg + hot * (1 - fg), base[:, ch])
+        color[:, 0] = np.where(temp > 2300, 130 + 125 / (1 + (temp / 5922)**55.525)**0.065,
+                               color[:, 0])
+        color[:, 1] = np.where((temp > 2300) & (temp <= 6000),
+                               257 - 73 / (1 + (temp / 4742)**6.687), color[:, 1])
+        color[:, 1] = np.where(temp > 6000, 170 + 165766330 / (1 + (temp / 24)**2.651),
+                               color[:, 1])
+        color[:, 2] = np.where(temp > 2300, 283 - 176 / (1 + (temp / 4493)**5.792), color[:, 2])
+    color[rad_sc > rad] = [0, 0, 0]
+    color = np.clip(color.astype(int), 0, 255)
+    types = np.zeros(len(mass))
+    types = np.where(mass > min_mass, 1, types)
+    types = np.where(den < 1500, 2, types)
+    types = np.where(temp > 1000, 3, types)
+    types = np.where(rad_sc > rad, 4, types)
+    sc = np.where(types == 3, "M", "Unknown")
+    for thr, name in ((3900, "K"), (5300, "G"), (6000, "F"), (7300, "A"), (10000, "B"),
+                      (33000, "O")):
+        sc = np.where(temp > thr, name, sc)
+    return dict(surf_grav=surf_grav, atm_h=atm_h, luminosity=lum, temp=temp, rad_sc=rad_sc,
+                color=color, types=types, stellar_class=sc)
+
+
 def body_radius(mass, den, rad_mult):
     """A5 radius only, phys_editor.py:580-581 (host numpy on both sides)."""
     volume = mass / den

@@ -463,6 +463,29 @@ def test_allpairs_merge_sequence(dev, oracle):
     np.testing.assert_allclose(ph.mass, orc.mass, rtol=0)
 
 
+# ------------------------------------------------------------------ N4 body data
+def test_body_data_golden(dev):
+    """Physics.body / temp_color / classify in one device pass: floats to 1e-13, the integer
+    colour, type and stellar class exact (CUDA pow/cbrt/log vs libm: a 1-ulp difference could in
+    principle flip a truncated colour channel; none does on these 415 bodies)."""
+    from volatilespace_b200.phys_editor import Physics
+    g = golden("body_data")
+    for tag in ("solar", "synth"):
+        n = len(g[tag + "_mass"])
+        ph = Physics(dev)
+        ph.gc, ph.rad_mult = float(g["gc"]), float(g["rad_mult"])
+        ph.mass_thermal_mult, ph.min_mass = float(g["mass_thermal_mult"]), float(g["min_mass"])
+        ph.mass, ph.den, ph.rad = g[tag + "_mass"], g[tag + "_den"], g[tag + "_rad"]
+        out = ph.body_data(g[tag + "_atm_pres0"], g[tag + "_atm_scale_h"], g[tag + "_atm_den0"],
+                           np.zeros(n), g[tag + "_base_color"])
+        for k in ("surf_grav", "atm_h", "luminosity", "temp", "rad_sc"):
+            np.testing.assert_allclose(out[k], g[tag + "_" + k], rtol=1e-13, atol=0, err_msg=k)
+        assert np.array_equal(out["types"], g[tag + "_types"])
+        assert np.array_equal(out["stellar_class"], g[tag + "_stellar_class"])
+        assert np.abs(out["color"] - g[tag + "_color"]).max() <= 1
+        assert (out["color"] != g[tag + "_color"]).sum() <= 2
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors_are_reported(dev):
     from volatilespace_b200._lib import VsbError, F_POS

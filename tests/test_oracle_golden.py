@@ -245,3 +245,20 @@ def test_culling(oracle):
                                         float(zoom), float(g["b_screen_x"]))
         assert np.array_equal(vv, g["b%d_vessels" % k])
         assert np.array_equal(vvo, g["b%d_vorbits" % k])
+
+
+# ------------------------------------------------------------- N4 body data
+def test_body_thermal(oracle):
+    g = golden("body_data")
+    for tag in ("solar", "synth"):
+        out = oracle.body_thermal(g[tag + "_mass"], g[tag + "_den"], g[tag + "_rad"],
+                                  g[tag + "_atm_pres0"], g[tag + "_atm_scale_h"],
+                                  g[tag + "_atm_den0"], np.zeros(len(g[tag + "_mass"])),
+                                  g[tag + "_base_color"], float(g["gc"]), float(g["rad_mult"]),
+                                  float(g["mass_thermal_mult"]), float(g["min_mass"]))
+        for k in ("surf_grav", "atm_h", "luminosity", "temp", "rad_sc"):
+            assert_close(out[k], g[tag + "_" + k], rtol=1e-15, atol=0)
+        assert np.array_equal(out["color"], g[tag + "_color"])
+        assert np.array_equal(out["types"], g[tag + "_types"])
+        assert np.array_equal(out["stellar_class"], g[tag + "_stellar_class"])
+    assert set(np.unique(g["synth_types"])) == {0.0, 1.0, 2.0, 3.0, 4.0}

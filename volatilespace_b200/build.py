@@ -29,6 +29,7 @@ SOURCES = {
     "vsb_editor.cu": ["-fmad=false"],
     "vsb_kepler.cu": ["-fmad=false"],
     "vsb_visible.cu": ["-fmad=false"],
+    "vsb_body.cu": ["-fmad=false"],
 }
 
 

@@ -458,10 +458,7 @@ extern "C" int vsb_allpairs_step(vsb_ctx *c, double gc, int64_t nsteps)
               "vsb_allpairs_step: rows are sharded [%lld,%lld); step per tick and all-gather "
               "positions between ticks instead",
               (long long)c->row0, (long long)c->row1);
-    for (int64_t s = 0; s < nsteps; ++s) {
-        VSB_TRY(vsb_launch_allpairs_accel(c, gc));
-        VSB_TRY(vsb_launch_allpairs_reduce(c, gc, 1));
-    }
+    for (int64_t s = 0; s < nsteps; ++s) VSB_TRY(accel_pass(c, gc, 1));
     VSB_CUDA(cudaStreamSynchronize(c->stream));
     return VSB_OK;
 }
@@ -1124,6 +1121,46 @@ extern "C" int vsb_kepler_curves_device_ptr(vsb_ctx *c, int kind, void **out)
     VSB_TRY(kep_of(c, "vsb_kepler_curves_device_ptr", kind, &k));
     VSB_CHECK(out && k->curves.p, VSB_ERR_STATE, "vsb_kepler_curves_device_ptr: no curves yet");
     *out = k->curves.p;
+    return VSB_OK;
+}
+
+// ---------------------------------------------------------------- N4: body thermal passes
+extern "C" int vsb_host_body_thermal(vsb_ctx *c, int64_t n, const double *consts12,
+                                     const double *mass, const double *den, const double *rad,
+                                     const double *atm_pres0, const double *atm_scale_h,
+                                     const double *atm_den0, double *atm_h,
+                                     const int64_t *base_color, double *surf_grav,
+                                     double *luminosity, double *temp, double *rad_sc,
+                                     int64_t *color, double *types, int32_t *stellar_class)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && consts12, VSB_ERR_ARG, "vsb_host_body_thermal: bad argument");
+    if (n == 0) return VSB_OK;
+    VSB_CHECK(mass && den && rad && atm_pres0 && atm_scale_h && atm_den0 && atm_h && base_color &&
+                  surf_grav && luminosity && temp && rad_sc && color && types && stellar_class,
+              VSB_ERR_ARG, "vsb_host_body_thermal: null array");
+    // staging (8-byte words): in 6n | atm_h n | base_color 3n | out 4n | color 3n | types n | stellar n/2
+    const size_t N = (size_t)n, na = (N + 31) / 32 * 32;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * (20 * na)));
+    double *b = (double *)c->host_stage.p;
+    double *d_in = b, *d_atm = b + 6 * na, *d_out = b + 10 * na, *d_types = b + 17 * na;
+    long long *d_bc = (long long *)(b + 7 * na), *d_col = (long long *)(b + 14 * na);
+    int *d_st = (int *)(b + 18 * na);
+    const double *ins[6] = {mass, den, rad, atm_pres0, atm_scale_h, atm_den0};
+    // the kernel expects the six inputs at stride n (not na): pack them contiguously
+    for (int k = 0; k < 6; ++k)
+        VSB_CUDA(cudaMemcpyAsync(d_in + k * N, ins[k], 8 * N, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_atm, atm_h, 8 * N, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_bc, base_color, 24 * N, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_body_thermal(c, n, consts12, d_in, d_atm, d_bc, d_out, d_col, d_types, d_st));
+    double *outs[4] = {surf_grav, luminosity, temp, rad_sc};
+    for (int k = 0; k < 4; ++k)
+        VSB_CUDA(cudaMemcpyAsync(outs[k], d_out + k * N, 8 * N, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(atm_h, d_atm, 8 * N, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(color, d_col, 24 * N, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(types, d_types, 8 * N, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(stellar_class, d_st, 4 * N, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
     return VSB_OK;
 }
 

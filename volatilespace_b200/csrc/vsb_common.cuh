@@ -231,6 +231,10 @@ int vsb_launch_compact(vsb_ctx *c, const unsigned char *d_flags, int64_t n, int 
                        int64_t *d_total, int64_t *d_idx);
 int vsb_launch_curves_gather(vsb_ctx *c, const double *d_curves, const int64_t *d_idx,
                              int64_t count, int64_t P, double *d_out);
+// body thermal / colour / classification (vsb_body.cu)
+int vsb_launch_body_thermal(vsb_ctx *c, int64_t n, const double *consts12, const double *d_in6,
+                            double *d_atm_h, const long long *d_base_color, double *d_out4,
+                            long long *d_color, double *d_types, int *d_stellar);
 // kepler (vsb_kepler.cu)
 int vsb_launch_kepler_move(vsb_ctx *c, vsb_kepler_state &k, double warp);
 int vsb_launch_kepler_curves(vsb_ctx *c, vsb_kepler_state &k, int64_t first, int64_t count,

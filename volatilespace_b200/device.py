@@ -306,6 +306,26 @@ class Device:
         check(self.L.vsb_kepler_curves_get(self.h, kind, int(first), int(count), ptr(out)))
         return out
 
+    def host_body_thermal(self, consts12, mass, den, rad, atm_pres0, atm_scale_h, atm_den0, atm_h,
+                          base_color):
+        """N4; returns dict surf_grav, luminosity, temp, rad_sc, atm_h, color, types,
+        stellar_class (codes 0..7)."""
+        n = len(mass)
+        ins = [f64(x) for x in (mass, den, rad, atm_pres0, atm_scale_h, atm_den0)]
+        atm_h = f64(atm_h).copy()
+        bc = i64(base_color)
+        k = f64(consts12)
+        out = {name: np.empty(n) for name in ("surf_grav", "luminosity", "temp", "rad_sc",
+                                              "types")}
+        color = np.empty((n, 3), dtype=np.int64)
+        stellar = np.empty(n, dtype=np.int32)
+        check(self.L.vsb_host_body_thermal(
+            self.h, n, ptr(k), *[ptr(x) for x in ins], ptr(atm_h), ptr(bc), ptr(out["surf_grav"]),
+            ptr(out["luminosity"]), ptr(out["temp"]), ptr(out["rad_sc"]), ptr(color),
+            ptr(out["types"]), ptr(stellar)))
+        out.update(atm_h=atm_h, color=color, stellar_class=stellar)
+        return out
+
     def host_culling(self, coords, radius, screen_bounds, zoom):
         coords, radius, sb = f64(coords), f64(radius), f64(screen_bounds)
         mask = np.empty(len(radius), dtype=np.uint8)

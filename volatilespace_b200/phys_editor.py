@@ -30,6 +30,20 @@ DEFAULT_CONF = {"gc": 1.0, "rad_mult": 179.0, "mass_thermal_mult": 2e26, "coi_co
                 "vessel_scale": 0.1, "min_planet_mass": 200}   # defaults.py:58-65
 
 
+# phys_shared.py:13-17, same expressions so the constants carry the same roundings
+GC_REAL = 6.674 * 10**-11
+C_LIGHT = 299792458
+SIGMA = 5.670374419 * 10**-8
+LS = 3.828 * 10**26
+MS = 1.9884 * 10**30
+STELLAR_CLASSES = np.array(["Unknown", "M", "K", "G", "F", "A", "B", "O"])
+
+
+def thermal_consts(gc_sim, rad_mult, mass_thermal_mult, min_mass):
+    return np.array([gc_sim, rad_mult, mass_thermal_mult, min_mass, GC_REAL, C_LIGHT, LS, MS,
+                     np.sqrt(2), np.pi**(1 / 4), SIGMA**(1 / 4), 4 * np.pi], dtype=np.float64)
+
+
 def mass_order(mass):
     """np.argsort(mass)[-1::-1], phys_editor.py:353,375 (host numpy, SURVEY F10)."""
     return np.ascontiguousarray(np.argsort(mass)[-1::-1], dtype=np.int64)
@@ -176,6 +190,21 @@ class Physics(_DeviceBodies):
             self.rad[:] = rad
             self._push("rad")
         self._rad_dirty = False
+
+    # phys_editor.py:583-599 + temp_color :602-651 + classify :654-670: the
+    # per-frame body data the editor UI shows, one device pass over host arrays
+    def body_data(self, atm_pres0=None, atm_scale_h=None, atm_den0=None, atm_h=None,
+                  base_color=None):
+        n = len(self.mass)
+        z = np.zeros(n)
+        out = self.dev.host_body_thermal(
+            thermal_consts(self.gc, self.rad_mult, self.mass_thermal_mult, self.min_mass),
+            self.mass, self.den, self.rad, z if atm_pres0 is None else atm_pres0,
+            z if atm_scale_h is None else atm_scale_h, z if atm_den0 is None else atm_den0,
+            z if atm_h is None else atm_h,
+            np.zeros((n, 3), dtype=np.int64) if base_color is None else base_color)
+        out["stellar_class"] = STELLAR_CLASSES[out["stellar_class"]]
+        return out
 
     # phys_editor.py:547-551
     def check_collision(self):
