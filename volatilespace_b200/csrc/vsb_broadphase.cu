@@ -81,15 +81,33 @@ bp_stats1_kernel(const double2 *__restrict__ pos, const double *__restrict__ rad
     if (threadIdx.x < 5) partial[blockIdx.x * 5 + threadIdx.x] = sh[threadIdx.x][0];
 }
 
-__global__ void bp_stats2_kernel(const double *__restrict__ partial, int nblocks, int64_t n,
-                                 unsigned mask, bp_params *P, unsigned long long *key)
+__global__ void __launch_bounds__(256)
+bp_stats2_kernel(const double *__restrict__ partial, int nblocks, int64_t n, unsigned mask,
+                 bp_params *P, unsigned long long *key)
 {
+    // fixed-shape tree reduction of the per-CTA partials: deterministic r_cut
+    __shared__ double sh[5][256];
     double s = 0, x0 = 1e308, y0 = 1e308, x1 = -1e308, y1 = -1e308;
-    for (int b = 0; b < nblocks; ++b) {  // fixed order: deterministic r_cut
+    for (int b = threadIdx.x; b < nblocks; b += 256) {
         s += partial[b * 5];
         x0 = fmin(x0, partial[b * 5 + 1]); y0 = fmin(y0, partial[b * 5 + 2]);
         x1 = fmax(x1, partial[b * 5 + 3]); y1 = fmax(y1, partial[b * 5 + 4]);
     }
+    sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = x0; sh[2][threadIdx.x] = y0;
+    sh[3][threadIdx.x] = x1; sh[4][threadIdx.x] = y1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] = fmin(sh[1][threadIdx.x], sh[1][threadIdx.x + o]);
+            sh[2][threadIdx.x] = fmin(sh[2][threadIdx.x], sh[2][threadIdx.x + o]);
+            sh[3][threadIdx.x] = fmax(sh[3][threadIdx.x], sh[3][threadIdx.x + o]);
+            sh[4][threadIdx.x] = fmax(sh[4][threadIdx.x], sh[4][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    s = sh[0][0]; x0 = sh[1][0]; y0 = sh[2][0]; x1 = sh[3][0]; y1 = sh[4][0];
     double rcut = 2.0 * (s / (double)n);
     double h = 2.0 * rcut * (1.0 + 1e-6);
     P->xmin = x0;
@@ -349,7 +367,7 @@ int vsb_launch_broadphase(vsb_ctx *c)
 
     VSB_CUDA(cudaMemsetAsync(counts, 0, 4 * (size_t)M, c->stream));
     bp_stats1_kernel<<<sblocks, 256, 0, c->stream>>>(pos, c->rad, n, partial);
-    bp_stats2_kernel<<<1, 1, 0, c->stream>>>(partial, sblocks, n, M - 1, P, c->d_key);
+    bp_stats2_kernel<<<1, 256, 0, c->stream>>>(partial, sblocks, n, M - 1, P, c->d_key);
     bp_count_kernel<<<g, 256, 0, c->stream>>>(pos, c->rad, n, P, bucket, counts, large);
     bp_scan_reduce_kernel<<<nchunks, 256, 0, c->stream>>>(counts, chunk);
     bp_scan_chunks_kernel<<<1, 1024, 0, c->stream>>>(chunk, nchunks);
