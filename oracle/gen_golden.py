@@ -431,6 +431,46 @@ def gen_body_data(ns, conf, bd, bod):
     save("body_data", **out)
 
 
+def gen_editor_edits(ns):
+    """Boundary mutators of phys_editor.Physics: add_body (light, and heavier than
+    the root -> re-root), set_body_mass (incl. root change), set_body_pos/vel/den, del_body
+    (ordinary and root), each followed by a few frames; snapshots after every step."""
+    rng = np.random.default_rng(20240618)
+    n = 24
+    mass, den, pos, vel = cloud(rng, n, 3.0e4, central_mass=2.0e4)
+    mass[1:5] = rng.uniform(100, 900, 4)
+    den[:] = 3.0e7
+    ph = rh.editor_from_arrays(ns, mass, den, pos, vel)
+    out = dict(mass=mass, den=den, pos0=pos, vel0=vel)
+    steps = []
+
+    def snap_step(tag):
+        ph.kepler_basic(); ph.temp_color(); ph.classify()
+        for _ in range(3):
+            rh.editor_frame(ph)
+        out.update(snap(ph, "s%d_" % len(steps)))
+        out["s%d_largest" % len(steps)] = int(ph.largest)
+        steps.append(tag)
+
+    def new_body(m, p, v):
+        return {"name": "new", "mass": m, "density": 3.0e7, "position": np.array(p, float),
+                "velocity": np.array(v, float), "color": (1, 2, 3), "atm_pres0": 0.0,
+                "atm_scale_h": 0.0, "atm_den0": 0.0}
+
+    snap_step("load")
+    ph.add_body(new_body(3.0, [9000.0, 2000.0], [0.1, 1.2])); snap_step("add_light")
+    ph.set_body_mass(7, 1500.0); snap_step("set_mass")
+    ph.set_body_pos(9, np.array([-4000.0, 7000.0])); snap_step("set_pos")
+    ph.set_body_vel(9, np.array([0.9, 0.4])); snap_step("set_vel")
+    ph.set_body_den(3, 0.01); snap_step("set_den")
+    ph.del_body(5); snap_step("del_ordinary")
+    ph.add_body(new_body(9.0e4, [15000.0, -8000.0], [0.0, 0.3])); snap_step("add_new_root")
+    ph.set_body_mass(4, 5.0e5); snap_step("set_mass_new_root")
+    ph.del_body(0); snap_step("del_root")
+    out["steps"] = np.array(steps)
+    save("editor_edits", **out)
+
+
 def main():
     ns = rh.load()
     conf, bd, bod = gen_solar(ns)
@@ -441,6 +481,7 @@ def main():
     gen_game(ns, conf, bd, bod)
     gen_culling(ns, conf, bd, bod)
     gen_body_data(ns, conf, bd, bod)
+    gen_editor_edits(ns)
 
 
 if __name__ == "__main__":

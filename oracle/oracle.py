@@ -449,6 +449,45 @@ class EditorOracle:
             return 0
         return 1
 
+    # phys_editor.py:204-247
+    def add_body(self, data):
+        old_largest = int(self.largest)
+        self.mass = np.append(self.mass, data["mass"])
+        self.den = np.append(self.den, data["density"])
+        self.rad = body_radius(self.mass, self.den, self.rad_mult)
+        self.pos = np.vstack((self.pos, data["position"]))
+        self.vel = np.vstack((self.vel, [0, 0]))
+        self.parents = np.append(self.parents, 0)
+        self.simplified_orbit_coi()
+        self.find_parents()
+        self.rel_vel = np.vstack((self.rel_vel, data["velocity"]))
+        for name in ("focus", "semi_major", "semi_minor", "periapsis_arg"):
+            setattr(self, name, np.append(getattr(self, name), 0))
+        self.ecc_v = np.vstack((self.ecc_v, [0, 0]))
+        if data["mass"] > self.mass[old_largest]:
+            self.largest = len(self.mass) - 1
+            diff = self.pos[self.largest].copy()
+            self.pos -= diff
+            self.rel_vel[old_largest] = self.rel_vel[self.largest] * -1
+            self.vel[self.largest] = [0, 0]
+            if self.largest != 0:
+                self.set_root(self.largest)
+        for body in mass_order(self.mass):
+            self.vel[body] = self.rel_vel[body] + self.vel[self.parents[body]]
+
+    # phys_editor.py:860-876
+    def set_body_den(self, body, density):
+        self.den[body] = max(density, 0.05)
+        self.simplified_orbit_coi()
+
+    def set_body_pos(self, body, position):
+        self.pos[body] = position
+        self.simplified_orbit_coi()
+
+    def set_body_vel(self, body, velocity):
+        self.rel_vel[body] = velocity - self.vel[self.parents[body]]
+        self.simplified_orbit_coi()
+
     # editor.py:1503-1523
     def frame(self, warp=1):
         deleted = []

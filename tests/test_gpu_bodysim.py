@@ -8,7 +8,7 @@ velocities within the relative FP64 tolerance written at each assert.
 import numpy as np
 import pytest
 
-from conftest import golden
+from conftest import EDIT_STEPS, apply_edit, golden
 
 pytestmark = pytest.mark.gpu
 
@@ -461,6 +461,20 @@ def test_allpairs_merge_sequence(dev, oracle):
     ph.pull("pos", "vel")
     np.testing.assert_allclose(ph.pos, orc.pos, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(ph.mass, orc.mass, rtol=0)
+
+
+def test_editor_mutators_golden(dev, frame_fn):
+    """add_body (light / new root), set_body_mass (incl. root change),
+    set_body_pos / vel / den, del_body (ordinary / root) against the live reference."""
+    g = golden("editor_edits")
+    ph = make_editor(dev, g["mass"], g["den"], g["pos0"], g["vel0"])
+    for k in range(len(EDIT_STEPS)):
+        apply_edit(ph, k)
+        ph.kepler_basic()
+        for _ in range(3):
+            assert frame_fn(ph) == []
+        assert ph.largest == int(g["s%d_largest" % k]), EDIT_STEPS[k]
+        check_snapshot(ph, g, "s%d_" % k, 1e-9)
 
 
 # ------------------------------------------------------------------ N4 body data

@@ -8,7 +8,7 @@ BLAS 2x2 rotation in phys_editor.curve) rel 1e-12.
 import numpy as np
 import pytest
 
-from conftest import golden
+from conftest import EDIT_STEPS, apply_edit, golden
 
 
 def rel_err(a, b):
@@ -262,3 +262,17 @@ def test_body_thermal(oracle):
         assert np.array_equal(out["types"], g[tag + "_types"])
         assert np.array_equal(out["stellar_class"], g[tag + "_stellar_class"])
     assert set(np.unique(g["synth_types"])) == {0.0, 1.0, 2.0, 3.0, 4.0}
+
+
+# ------------------------------------------------------------- boundary mutators
+def test_editor_mutators(oracle):
+    g = golden("editor_edits")
+    assert list(g["steps"]) == EDIT_STEPS
+    ed = oracle.EditorOracle(g["mass"], g["den"], g["pos0"], g["vel0"])
+    for k in range(len(EDIT_STEPS)):
+        apply_edit(ed, k)
+        ed.kepler_basic()
+        for _ in range(3):
+            assert ed.frame() == []
+        assert ed.largest == int(g["s%d_largest" % k]), EDIT_STEPS[k]
+        check_snapshot(ed, g, "s%d_" % k, 1e-12)
