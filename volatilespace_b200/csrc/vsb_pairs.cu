@@ -173,8 +173,15 @@ cc_scan_kernel(const double2 *__restrict__ pos, const double *__restrict__ rad,
     const int64_t tmin = (i0 + 1) / PB_TJ;
     if (t0 < tmin) t0 = tmin;
     if (t0 >= t1) return;
-    // a smaller row already collided: nothing this CTA finds can win
-    if ((*(volatile unsigned long long *)key >> 32) < (unsigned long long)i0) return;
+    // a smaller row already collided: nothing this CTA finds can win.  The decision must be
+    // CTA-uniform (one thread reads the key): the key changes under our feet, and a CTA that
+    // lost only some of its threads -- thread 0 among them -- would wait on mbarriers nobody
+    // initialised.
+    __shared__ int s_skip;
+    if (threadIdx.x == 0)
+        s_skip = (*(volatile unsigned long long *)key >> 32) < (unsigned long long)i0 ? 1 : 0;
+    __syncthreads();
+    if (s_skip) return;
 
     const bool live = i < n - 1;
     const double2 me = pos[live ? i : 0];
