@@ -260,6 +260,24 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
     os.environ.pop("VSB_COLLISION", None)
     coll["timing"] = "host wall clock per vsb_check_collision call incl. result read-back"
     out["cluster256k_collision"] = coll
+    # config 5 end to end: gravity(); body(); inelastic_collision() ticks with merges applied
+    from volatilespace_b200.phys_editor import AllPairsPhysics
+    ph = AllPairsPhysics(dev)
+    ph.load_system({"gc": s["gc"], "rad_mult": s["rad_mult"]}, {"mass": s["mass"], "den": s["den"]},
+                   {"pos": s["pos"], "vel": s["vel"]})
+    merges = []
+    ph.tick()
+    t0 = time.perf_counter()
+    nt = 12
+    for t in range(nt):
+        m = ph.tick()
+        if m is not None:
+            merges.append([t + 1, int(m[0]), int(m[1])])
+    dt = (time.perf_counter() - t0) / nt
+    out["cluster256k_ticks"] = {"ms_per_tick": dt * 1e3, "body_ticks_per_s": len(ph.mass) / dt,
+                                "merges_in_%d_ticks" % nt: len(merges), "first_merges": merges[:4],
+                                "note": "AllPairsPhysics.tick: all-pairs gravity + integrator, "
+                                        "host np.cbrt radius, collision check, merge + compaction"}
     # config 4: 4M Kepler objects + 512-point curves (fused vessel tick), HBM roofline
     n, P = 4194304, 512
     try:

@@ -291,6 +291,29 @@ def test_collision_full_size_property(dev, oracle):
     assert got == ((i2, j2) if mass[i2] <= mass[j2] else (j2, i2))
 
 
+def test_collapsing_cluster_full_size_merges_teacher_forced(dev, oracle):
+    """Config 5 at full size (262 144 bodies): run the real ticks on the GPU and, every tick,
+    hand the GPU's own pos / rad / mass to the oracle's exhaustive check_collision -- the
+    (del, add) pair must be identical (teacher-forced)."""
+    from volatilespace_b200 import synth
+    from volatilespace_b200.phys_editor import AllPairsPhysics
+    s = synth.collapsing_cluster(262144)
+    ph = AllPairsPhysics(dev)
+    ph.load_system({"gc": s["gc"], "rad_mult": s["rad_mult"]}, {"mass": s["mass"], "den": s["den"]},
+                   {"pos": s["pos"], "vel": s["vel"]})
+    hits = 0
+    for tick in range(3):
+        ph.gravity()
+        ph.body()
+        ph.pull("pos")
+        want = oracle.check_collision(ph.mass, ph.pos, ph.rad)
+        got = ph.inelastic_collision()
+        assert (got if got is not None else (None, None)) == want, tick
+        hits += got is not None
+    assert hits >= 1
+    assert len(ph.mass) == 262144 - hits
+
+
 # ------------------------------------------------------------------ editor frames (MODE_REF)
 KEYS = ("mass", "rad", "pos", "vel", "rel_vel", "coi", "parents", "focus", "ecc_v",
         "semi_major", "semi_minor", "periapsis_arg")
