@@ -253,6 +253,21 @@ int vsb_kepler_free(vsb_ctx *ctx, int kind);
 int vsb_kepler_curves_get(vsb_ctx *ctx, int kind, int64_t first, int64_t count, double *out);
 int vsb_kepler_curves_device_ptr(vsb_ctx *ctx, int kind, void **dptr_out);
 
+/* --------------------------------------------- Newton <-> Kepler conversion
+ * convert.to_kepler, convert.py:193-261 (opening a Newtonian map in game mode, game.py:318-319)
+ * and convert.to_newton, convert.py:132-190 with kepler_to_velocity :20-64 (opening a Keplerian
+ * save in the editor, editor.py:295-296), over host arrays; the reference's index quirks are
+ * reproduced (see vsb_convert.cu).  to_newton reports the reference's ValueError for hyperbolic
+ * bodies as VSB_ERR_ARG "math domain error". */
+int vsb_host_to_kepler(vsb_ctx *ctx, int64_t n, const int64_t *order_desc_mass, const double *mass,
+                       const double *pos, const double *vel, double gc, double coi_coef,
+                       int64_t *ref_out, double *a_out, double *ecc_out, double *pe_arg_out,
+                       double *ma_out, double *dir_out);
+int vsb_host_to_newton(vsb_ctx *ctx, int64_t n, const double *mass, const double *a,
+                       const double *ecc, const double *pe_arg, const double *ma,
+                       const int64_t *ref, const double *dir, double gc, double *pos_out,
+                       double *vel_out);
+
 /* --------------------------------------------- per-frame body passes
  * Physics.body (phys_editor.py:577-599, without the radius, which stays host numpy),
  * Physics.temp_color (:602-651) and Physics.classify (:654-670) in one pass over host arrays.

@@ -471,6 +471,57 @@ def gen_editor_edits(ns):
     save("editor_edits", **out)
 
 
+def gen_convert(ns, conf, bd, bod):
+    """N1: convert.to_kepler / to_newton on the Solar System and on hierarchical clouds whose
+    index order differs from their mass order (the reference's index quirks matter there)."""
+    import copy
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    from volatilespace.physics import convert
+    sys.path.remove(rh.REFERENCE_ROOT)
+    rng = np.random.default_rng(20240619)
+    out = {}
+    cases = {"solar": (bd["mass"].copy(), bod["pos"].copy(), bod["vel"].copy())}
+    for tag, n in (("c60", 60), ("c1500", 1500)):
+        mass, den, pos, vel = cloud(rng, n, 3.0e4, central_mass=2.0e4)
+        npl = 6 if n == 60 else 40
+        mass[1:1 + npl] = rng.uniform(50, 900, npl)
+        for k in range(1 + npl, 1 + 3 * npl):          # moons inside planet COIs
+            p = 1 + (k % npl)
+            d = rng.uniform(30, 90)
+            th = rng.uniform(0, 2 * np.pi)
+            pos[k] = pos[p] + d * np.array([np.cos(th), np.sin(th)])
+            vel[k] = vel[p] + np.sqrt(mass[p] / d) * np.array([-np.sin(th), np.cos(th)])
+            mass[k] = rng.uniform(0.01, 0.4)
+        perm = np.concatenate(([0], 1 + rng.permutation(n - 1)))   # scramble all but the root
+        cases[tag] = (mass[perm], pos[perm], vel[perm])
+    for tag, (mass, pos, vel) in cases.items():
+        k = convert.to_kepler(mass, {"pos": pos.copy(), "vel": vel.copy()}, conf["gc"],
+                              conf["coi_coef"])
+        out.update({tag + "_mass": mass, tag + "_pos": pos, tag + "_vel": vel})
+        for key in ("a", "ecc", "pe_arg", "ma", "ref", "dir"):
+            out[tag + "_k_" + key] = np.array(k[key])
+        if np.all(k["ecc"] < 1):
+            nw = convert.to_newton(mass, copy.deepcopy(k), conf["gc"], conf["coi_coef"])
+            out[tag + "_n_pos"] = nw["pos"]
+            out[tag + "_n_vel"] = nw["vel"]
+    # to_newton on synthetic elliptic elements with arbitrary refs (incl. ref >= body)
+    n = 300
+    mass = rng.uniform(0.5, 50.0, n)
+    mass[0] = 2.0e4
+    kn = {"kepler": True, "a": rng.uniform(200, 2.0e4, n), "ecc": rng.uniform(0, 0.9, n),
+          "pe_arg": rng.uniform(0, 2 * np.pi, n), "ma": rng.uniform(0, 2 * np.pi, n),
+          "ref": rng.integers(0, n, n), "dir": rng.choice([-1.0, 1.0], n)}
+    kn["ecc"][[5, 17]] = 0.0
+    kn["ref"][:40] = 0
+    kn["ref"][0] = 0
+    nw = convert.to_newton(mass, copy.deepcopy(kn), conf["gc"], conf["coi_coef"])
+    out.update(kn_mass=mass, kn_n_pos=nw["pos"], kn_n_vel=nw["vel"])
+    for key in ("a", "ecc", "pe_arg", "ma", "ref", "dir"):
+        out["kn_k_" + key] = np.array(kn[key])
+    out.update(gc=conf["gc"], coi_coef=conf["coi_coef"])
+    save("convert", **out)
+
+
 def main():
     ns = rh.load()
     conf, bd, bod = gen_solar(ns)
@@ -482,6 +533,7 @@ def main():
     gen_culling(ns, conf, bd, bod)
     gen_body_data(ns, conf, bd, bod)
     gen_editor_edits(ns)
+    gen_convert(ns, conf, bd, bod)
 
 
 if __name__ == "__main__":

@@ -63,6 +63,10 @@ def lib():
         "vso_curve_points": (None, [f64, f64, f64, f64, _f64p, i64, _f64p]),
         "vso_curves_all": (None, [i64, _f64p, _f64p, _f64p, _f64p, _f64p, i64, _f64p]),
         "vso_curve_move_to": (None, [i64, i64, _f64p, _f64p, _i64p, _f64p, _f64p, _f64p]),
+        "vso_to_kepler": (None, [i64, _i64p, _f64p, _f64p, _f64p, f64, f64, _i64p, _f64p, _f64p,
+                                 _f64p, _f64p, _f64p]),
+        "vso_to_newton": (C.c_int, [i64, _f64p, _f64p, _f64p, _f64p, _f64p, _i64p, _f64p, f64,
+                                    _f64p, _f64p]),
         "vso_editor_curve": (None, [i64, i64, _f64p, _f64p, _f64p, _f64p, _f64p, _i64p,
                                     _f64p, _f64p, _f64p, _f64p]),
     }
@@ -263,6 +267,27 @@ def vessel_culling(pos, ref, pe_d, body_coi, visible_coi, sim_screen, zoom, scre
     t = np.logical_or(t, ref == 0)
     t = np.logical_and(t, pe_d * zoom < screen_x * 15)
     return visible_vessels, np.arange(n)[t]
+
+
+def to_kepler(mass, pos, vel, gc, coi_coef):
+    """N1: convert.to_kepler, convert.py:193-261 -> dict like the reference's return value."""
+    n = len(mass)
+    ref = np.zeros(n, dtype=np.int64)
+    a, ecc, pe, ma, dr = (np.zeros(n) for _ in range(5))
+    lib().vso_to_kepler(n, mass_order(mass), _f(mass), _f(pos), _f(vel), float(gc),
+                        float(coi_coef), ref, a, ecc, pe, ma, dr)
+    return {"kepler": True, "a": a, "ecc": ecc, "pe_arg": pe, "ma": ma, "ref": ref, "dir": dr}
+
+
+def to_newton(mass, orb, gc, coi_coef):
+    """N1: convert.to_newton, convert.py:132-190 (ValueError for hyperbolic bodies, as there)."""
+    n = len(mass)
+    pos, vel = np.zeros((n, 2)), np.zeros((n, 2))
+    rc = lib().vso_to_newton(n, _f(mass), _f(orb["a"]), _f(orb["ecc"]), _f(orb["pe_arg"]),
+                             _f(orb["ma"]), _i(orb["ref"]), _f(orb["dir"]), float(gc), pos, vel)
+    if rc != 0:
+        raise ValueError("math domain error")
+    return {"kepler": False, "pos": pos, "vel": vel}
 
 
 # phys_shared.py:13-17

@@ -552,3 +552,126 @@ void vso_editor_curve(int64_t n, int64_t P, const double *ecc_v, const double *s
         }
     }
 }
+
+/* ------------------------------------------------------------------ */
+/* N1 -- Newton <-> Kepler conversion at load/save        */
+/* ------------------------------------------------------------------ */
+
+/* convert.to_kepler, convert.py:193-261, including its index quirks: the first loop walks the
+ * bodies in INDEX order, and after the parent search it uses the body's mass RANK `body` as an
+ * index into pos / vel / mass / coi (:219-225).  order = argsort(mass)[::-1] from the caller. */
+void vso_to_kepler(int64_t n, const int64_t *order, const double *mass, const double *pos,
+                   const double *vel, double gc, double coi_coef, int64_t *ref_l, double *a_l,
+                   double *ecc_l, double *pe_l, double *ma_l, double *dir_l)
+{
+    int64_t *rank = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    double *coi = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    for (int64_t k = 0; k < n; ++k) rank[order[k]] = k;
+    for (int64_t s = 0; s < n; ++s) {
+        int64_t body = rank[s], ref = 0;
+        for (int64_t l = 0; l < body; ++l) {
+            int64_t pp = order[l];
+            double rx = pos[2 * s] - pos[2 * pp], ry = pos[2 * s + 1] - pos[2 * pp + 1];
+            if (rx * rx + ry * ry < coi[pp] * coi[pp]) ref = pp;
+        }
+        ref_l[s] = ref;
+        double rpx = pos[2 * ref] - pos[2 * body], rpy = pos[2 * ref + 1] - pos[2 * body + 1];
+        double rvx = vel[2 * ref] - vel[2 * body], rvy = vel[2 * ref + 1] - vel[2 * body + 1];
+        double u = gc * mass[ref];
+        double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / sqrt(rpx * rpx + rpy * rpy)));
+        coi[body] = a > 0 ? a * pow(mass[body] / mass[ref], coi_coef) : 0.0;
+    }
+    for (int64_t b = 0; b < n; ++b) {
+        a_l[b] = ecc_l[b] = pe_l[b] = ma_l[b] = dir_l[b] = 0.0;
+        if (!b) continue;
+        int64_t ref = ref_l[b];
+        double rpx = pos[2 * b] - pos[2 * ref], rpy = pos[2 * b + 1] - pos[2 * ref + 1];
+        double rvx = vel[2 * b] - vel[2 * ref], rvy = vel[2 * b + 1] - vel[2 * ref + 1];
+        double u = gc * mass[ref];
+        double magp = sqrt(rpx * rpx + rpy * rpy);
+        double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / magp));
+        double momentum = rpx * rvy - rpy * rvx;
+        double sx = rvy, sy = -rvx;
+        double ex = (sx * momentum / u) - rpx / magp, ey = (sy * momentum / u) - rpy / magp;
+        double ecc = sqrt(ex * ex + ey * ey);
+        double pe = py_mod((3 * VSO_PI / 2) + atan2(-ex, ey), 2 * VSO_PI);
+        double dir = copysign(1.0, momentum);
+        double ta = py_mod(pe - (atan2(rpy, rpx) - VSO_PI), 2 * VSO_PI);
+        if (dir == -1) ta = 2 * VSO_PI - ta;
+        double ea, ma;
+        if (ecc < 1) {
+            ea = acos((ecc + cos(ta)) / (1 + (ecc * cos(ta))));
+            if (VSO_PI < ta && ta < 2 * VSO_PI) ea = 2 * VSO_PI - ea;
+            ma = py_mod(ea - ecc * sin(ea), 2 * VSO_PI);
+        } else {
+            ea = acosh((ecc + cos(ta)) / (1 + (ecc * cos(ta))));
+            ma = ecc * sinh(ea) - ea;
+        }
+        a_l[b] = a; ecc_l[b] = ecc; pe_l[b] = pe; ma_l[b] = ma; dir_l[b] = dir;
+    }
+    free(rank);
+    free(coi);
+}
+
+/* rot_ellipse_by_y, phys_shared.py:133-144 */
+static double rot_ellipse_by_y(double x, double a, double b, double p)
+{
+    double sin_p = sin(p), cos_p = cos(p);
+    double a2 = a * a, b2 = b * b, x2 = x * x, sin_p2 = sin_p * sin_p, cos_p2 = cos_p * cos_p;
+    double c4 = cos_p2 * cos_p2, s4 = sin_p2 * sin_p2; /* cos_p**4, sin_p**4 */
+    return (a * b * sqrt(-x2 * (c4 + s4) - 2 * x2 * cos_p2 * sin_p2 + b2 * sin_p2 + a2 * cos_p2) +
+            a2 * x * sin_p * cos_p - b2 * x * sin_p * cos_p) / (a2 * cos_p2 + b2 * sin_p2);
+}
+
+/* impl_derivative_rot_ell, phys_shared.py:160-171 */
+static double impl_derivative_rot_ell(double px, double py, double a, double b, double p)
+{
+    double sin_p = sin(p), cos_p = cos(p);
+    double a2 = a * a, b2 = b * b, sc = sin_p * cos_p, sin_p2 = sin_p * sin_p, cos_p2 = cos_p * cos_p;
+    return atan(-(b2 * px * cos_p2 + a2 * px * sin_p2 + b2 * py * sc - a2 * py * sc) /
+                (a2 * py * cos_p2 + b2 * py * sin_p2 + b2 * px * sc - a2 * px * sc));
+}
+
+/* convert.to_newton, convert.py:132-190 with kepler_to_velocity :20-64 (ellipse branch; the
+ * reference raises ValueError at :170 for ecc > 1, reported here as return value -1).  Its
+ * loop variable `body` is the position inside bodies_sorted, i.e. it visits the bodies in
+ * INDEX order, whatever the COI sort says (:158-160). */
+int vso_to_newton(int64_t n, const double *mass, const double *a_l, const double *ecc_l,
+                  const double *pe_l, const double *ma_l, const int64_t *ref_l,
+                  const double *dir_l, double gc, double *pos, double *vel)
+{
+    for (int64_t i = 0; i < 2 * n; ++i) pos[i] = vel[i] = 0.0;
+    for (int64_t body = 1; body < n; ++body) {
+        double a = a_l[body], ecc = ecc_l[body], pe = pe_l[body], ma = ma_l[body], dr = dir_l[body];
+        int64_t ref = ref_l[body];
+        double u = gc * mass[ref];
+        if (dr > 0) ma = -ma;
+        if (ecc == 0) ecc = 0.00001;
+        if (ecc == 1) ecc = 1.00001;
+        if (1 - ecc * ecc < 0) return -1;
+        double b = a * sqrt(1 - ecc * ecc);
+        double f = sqrt(a * a - b * b);
+        double ea = vso_solve_kepler_ell(ecc, ma, 1e-10);
+        double rx = a * cos(ea) - f, ry = b * sin(ea);
+        double ang = pe - VSO_PI;
+        double px = rx * cos(ang) - ry * sin(ang), py = rx * sin(ang) + ry * cos(ang);
+        /* kepler_to_velocity(rel_pos, a, ecc, pe_arg, u, dr), ellipse */
+        double frx = f * cos(pe), fry = f * sin(pe);
+        double qx = px - f * cos(pe), qy = py - f * sin(pe);
+        double angle = impl_derivative_rot_ell(qx, qy, a, b, pe);
+        double arg = a * a * cos(2 * pe) + a * a - b * b * cos(2 * pe) + b * b;
+        if (arg < 0) return -2;
+        double x_max = sqrt(arg) / sqrt(2.0) - 1e-06;
+        double y_max = rot_ellipse_by_y(x_max, a, b, pe);
+        double x1 = x_max + frx, y1 = y_max + fry, x2 = -x_max + frx, y2 = -y_max + fry;
+        if (((x2 - x1) * (py - y1)) - ((y2 - y1) * (px - x1)) < 0) angle += VSO_PI;
+        angle = py_mod(angle, 2 * VSO_PI);
+        double distance = sqrt(px * px + py * py);
+        double speed = dr * sqrt(u * ((2 / distance) - (1 / a)));
+        pos[2 * body] = pos[2 * ref] + px;
+        pos[2 * body + 1] = pos[2 * ref + 1] + py;
+        vel[2 * body] = vel[2 * ref] + speed * cos(angle);
+        vel[2 * body + 1] = vel[2 * ref + 1] + speed * sin(angle);
+    }
+    return 0;
+}

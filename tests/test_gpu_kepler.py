@@ -274,6 +274,55 @@ def test_culling_and_gather_at_scale(dev, oracle):
     dev.kepler_free(KIND_VESSEL)
 
 
+def test_convert_golden(dev):
+    """N1: convert.to_kepler / to_newton against the live reference (index quirks included):
+    refs bit-exact, elements and state vectors within 1e-11."""
+    from volatilespace_b200 import convert
+    g = golden("convert")
+    gc, cc = float(g["gc"]), float(g["coi_coef"])
+    for tag in ("solar", "c60", "c1500"):
+        k = convert.to_kepler(g[tag + "_mass"], {"pos": g[tag + "_pos"], "vel": g[tag + "_vel"]},
+                              gc, cc, device=dev)
+        assert np.array_equal(k["ref"], g[tag + "_k_ref"]), tag
+        for key in ("a", "ecc", "pe_arg", "ma", "dir"):
+            np.testing.assert_allclose(k[key], g[tag + "_k_" + key], rtol=1e-11, atol=1e-12,
+                                       equal_nan=True, err_msg=tag + key)
+    for tag in ("solar", "kn"):
+        orb = {key: g[tag + "_k_" + key] for key in ("a", "ecc", "pe_arg", "ma", "ref", "dir")}
+        nw = convert.to_newton(g[tag + "_mass"], orb, gc, cc, device=dev)
+        np.testing.assert_allclose(nw["pos"], g[tag + "_n_pos"], rtol=1e-10, atol=1e-7)
+        np.testing.assert_allclose(nw["vel"], g[tag + "_n_vel"], rtol=1e-10, atol=1e-10)
+    orb = {key: g["c60_k_" + key] for key in ("a", "ecc", "pe_arg", "ma", "ref", "dir")}
+    with pytest.raises(ValueError):
+        convert.to_newton(g["c60_mass"], orb, gc, cc, device=dev)
+
+
+def test_to_kepler_multi_slab_vs_oracle(dev, oracle):
+    """to_kepler's sequential first loop across several 1024-step slabs, scrambled index order."""
+    from volatilespace_b200 import convert
+    rng = np.random.default_rng(99)
+    n = 5000
+    mass = rng.uniform(0.5, 2.0, n)
+    mass[0] = 5.0e4
+    mass[1:60] = rng.uniform(100, 3000, 59)
+    r = rng.uniform(0.05, 1.0, n) * 6.0e4
+    th = rng.uniform(0, 2 * np.pi, n)
+    pos = np.stack([r * np.cos(th), r * np.sin(th)], axis=1)
+    sp = np.sqrt(mass[0] / r) * rng.normal(1.0, 0.05, n)
+    vel = np.stack([-sp * np.sin(th), sp * np.cos(th)], axis=1)
+    pos[0] = 0
+    vel[0] = 0
+    perm = np.concatenate(([0], 1 + rng.permutation(n - 1)))
+    mass, pos, vel = mass[perm], np.ascontiguousarray(pos[perm]), np.ascontiguousarray(vel[perm])
+    got = convert.to_kepler(mass, {"pos": pos, "vel": vel}, 1.0, 0.7, device=dev)
+    want = oracle.to_kepler(mass, pos, vel, 1.0, 0.7)
+    assert np.array_equal(got["ref"], want["ref"])
+    assert (want["ref"] != 0).sum() > 20
+    for key in ("a", "ecc", "pe_arg", "ma", "dir"):
+        np.testing.assert_allclose(got[key], want[key], rtol=1e-10, atol=1e-11, equal_nan=True,
+                                   err_msg=key)
+
+
 def test_kepler_errors(dev):
     from volatilespace_b200._lib import VsbError, KIND_BODY, KIND_VESSEL
     dev.kepler_free(KIND_BODY)

@@ -276,3 +276,24 @@ def test_editor_mutators(oracle):
             assert ed.frame() == []
         assert ed.largest == int(g["s%d_largest" % k]), EDIT_STEPS[k]
         check_snapshot(ed, g, "s%d_" % k, 1e-12)
+
+
+# ------------------------------------------------------------- N1 convert
+def test_convert(oracle):
+    g = golden("convert")
+    gc, cc = float(g["gc"]), float(g["coi_coef"])
+    for tag in ("solar", "c60", "c1500"):
+        k = oracle.to_kepler(g[tag + "_mass"], g[tag + "_pos"], g[tag + "_vel"], gc, cc)
+        assert np.array_equal(k["ref"], g[tag + "_k_ref"])
+        for key in ("a", "ecc", "pe_arg", "ma", "dir"):
+            np.testing.assert_allclose(k[key], g[tag + "_k_" + key], rtol=1e-14, atol=0,
+                                       equal_nan=True, err_msg=tag + key)
+    assert (g["c1500_k_ref"] != 0).sum() > 30
+    for tag in ("solar", "kn"):
+        orb = {key: g[tag + "_k_" + key] for key in ("a", "ecc", "pe_arg", "ma", "ref", "dir")}
+        nw = oracle.to_newton(g[tag + "_mass"], orb, gc, cc)
+        np.testing.assert_allclose(nw["pos"], g[tag + "_n_pos"], rtol=1e-13, atol=1e-9)
+        np.testing.assert_allclose(nw["vel"], g[tag + "_n_vel"], rtol=1e-13, atol=1e-12)
+    orb = {key: g["c60_k_" + key] for key in ("a", "ecc", "pe_arg", "ma", "ref", "dir")}
+    with pytest.raises(ValueError):          # hyperbolic bodies: the reference raises too
+        oracle.to_newton(g["c60_mass"], orb, gc, cc)

@@ -94,6 +94,8 @@ SIGNATURES = {
     "vsb_kepler_free": [_ctx, C.c_int],
     "vsb_kepler_curves_get": [_ctx, C.c_int, _i64, _i64, _pv],
     "vsb_kepler_curves_device_ptr": [_ctx, C.c_int, C.POINTER(C.c_void_p)],
+    "vsb_host_to_kepler": [_ctx, _i64, _pv, _pv, _pv, _pv, _f64, _f64] + [_pv] * 6,
+    "vsb_host_to_newton": [_ctx, _i64] + [_pv] * 7 + [_f64, _pv, _pv],
     "vsb_host_body_thermal": [_ctx, _i64] + [_pv] * 16,
     "vsb_host_culling": [_ctx, _i64, _pv, _pv, _pv, _f64, _pv],
     "vsb_kepler_culling": [_ctx, C.c_int, _pv, _pv, _f64, _pv, _pi],

@@ -30,6 +30,7 @@ SOURCES = {
     "vsb_kepler.cu": ["-fmad=false"],
     "vsb_visible.cu": ["-fmad=false"],
     "vsb_body.cu": ["-fmad=false"],
+    "vsb_convert.cu": ["-fmad=false"],
 }
 
 

@@ -1124,6 +1124,62 @@ extern "C" int vsb_kepler_curves_device_ptr(vsb_ctx *c, int kind, void **out)
     return VSB_OK;
 }
 
+// ---------------------------------------------------------------- N1: Newton <-> Kepler
+extern "C" int vsb_host_to_kepler(vsb_ctx *c, int64_t n, const int64_t *order, const double *mass,
+                                  const double *pos, const double *vel, double gc, double coi_coef,
+                                  int64_t *ref_out, double *a_out, double *ecc_out,
+                                  double *pe_arg_out, double *ma_out, double *dir_out)
+{
+    CTX(c);
+    VSB_CHECK(n > 0 && order && mass && pos && vel && ref_out && a_out && ecc_out && pe_arg_out &&
+                  ma_out && dir_out,
+              VSB_ERR_ARG, "vsb_host_to_kepler: bad argument");
+    VSB_TRY(stage_bodies(c, n));
+    VSB_CUDA(cudaMemcpyAsync(c->mass, mass, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(c->pos, pos, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(c->vel, vel, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(upload_order(c, "vsb_host_to_kepler", order));
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 48 * (size_t)c->npad));
+    int64_t *d_ref = (int64_t *)c->host_stage.p;
+    double *d_el = (double *)c->host_stage.p + c->npad;
+    VSB_TRY(vsb_launch_to_kepler(c, (const int64_t *)c->order.p, gc, coi_coef, d_ref, d_el));
+    double *outs[5] = {a_out, ecc_out, pe_arg_out, ma_out, dir_out};
+    for (int k = 0; k < 5; ++k)
+        VSB_CUDA(cudaMemcpyAsync(outs[k], d_el + (size_t)k * n, 8 * (size_t)n,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    return d2h(c, ref_out, d_ref, 8 * (size_t)n);
+}
+
+extern "C" int vsb_host_to_newton(vsb_ctx *c, int64_t n, const double *mass, const double *a,
+                                  const double *ecc, const double *pe_arg, const double *ma,
+                                  const int64_t *ref, const double *dir, double gc,
+                                  double *pos_out, double *vel_out)
+{
+    CTX(c);
+    VSB_CHECK(n > 0 && mass && a && ecc && pe_arg && ma && ref && dir && pos_out && vel_out,
+              VSB_ERR_ARG, "vsb_host_to_newton: bad argument");
+    for (int64_t i = 0; i < n; ++i)
+        VSB_CHECK(ref[i] >= 0 && ref[i] < n, VSB_ERR_ARG, "vsb_host_to_newton: ref[%lld] out of range",
+                  (long long)i);
+    VSB_TRY(stage_bodies(c, n));
+    VSB_CUDA(cudaMemcpyAsync(c->mass, mass, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 48 * (size_t)c->npad));
+    int64_t *d_ref = (int64_t *)c->host_stage.p;
+    double *d_el = (double *)c->host_stage.p + c->npad;
+    const double *ins[5] = {a, ecc, pe_arg, ma, dir};
+    for (int k = 0; k < 5; ++k)
+        VSB_CUDA(cudaMemcpyAsync(d_el + (size_t)k * n, ins[k], 8 * (size_t)n,
+                                 cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_ref, ref, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    int err = 0;
+    VSB_TRY(vsb_launch_to_newton(c, d_el, d_ref, gc, &err));
+    VSB_CHECK(err != 3, VSB_ERR_ARG, "vsb_host_to_newton: ref hierarchy deeper than 64 levels");
+    // the reference raises ValueError (math domain error) for hyperbolic bodies, convert.py:170
+    VSB_CHECK(err == 0, VSB_ERR_ARG, "vsb_host_to_newton: math domain error");
+    VSB_CUDA(cudaMemcpyAsync(pos_out, c->pos, 16 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    return d2h(c, vel_out, c->vel, 16 * (size_t)n);
+}
+
 // ---------------------------------------------------------------- N4: body thermal passes
 extern "C" int vsb_host_body_thermal(vsb_ctx *c, int64_t n, const double *consts12,
                                      const double *mass, const double *den, const double *rad,

@@ -191,6 +191,65 @@ __device__ __forceinline__ long long warp_max_i64(long long v)
     return v;
 }
 
+// ---- shared tile streamer of the O(N^2) predicate scans (vsb_pairs.cu, vsb_convert.cu)
+constexpr int PB_BLOCK = 128;
+constexpr int PB_TJ = 512;
+constexpr int PB_STAGES = 2;
+
+// Streams tiles [t0, t1) of (pos2[], val[]) through shared memory and calls
+// body(sp, sv, first_source_index_of_tile) for each; all threads of the CTA must call it.
+template <typename F>
+__device__ __forceinline__ void stream_tiles(const double2 *__restrict__ gpos,
+                                             const double *__restrict__ gval, int64_t t0,
+                                             int64_t t1, F body)
+{
+    __shared__ alignas(128) double2 spos[PB_STAGES][PB_TJ];
+    __shared__ alignas(128) double sval[PB_STAGES][PB_TJ];
+    __shared__ alignas(8) uint64_t full[PB_STAGES];
+    constexpr uint32_t TILE_BYTES = PB_TJ * (sizeof(double2) + sizeof(double));
+    const int tid = threadIdx.x;
+    const int ntiles = (int)(t1 - t0);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < PB_STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < PB_STAGES; ++s)
+            if (s < ntiles) {
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                tma_bulk_g2s(spos[s], gpos + (t0 + s) * PB_TJ, PB_TJ * sizeof(double2), &full[s]);
+                tma_bulk_g2s(sval[s], gval + (t0 + s) * PB_TJ, PB_TJ * sizeof(double), &full[s]);
+            }
+    }
+    int consumed = 0;
+    int issued = ntiles < PB_STAGES ? ntiles : PB_STAGES;
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % PB_STAGES;
+        mbar_wait(&full[s], (uint32_t)(t / PB_STAGES) & 1u);
+        consumed = t + 1;
+        const bool keep_going = body(spos[s], sval[s], (t0 + t) * PB_TJ);
+        const int go = __syncthreads_or(keep_going ? 1 : 0);  // also: everyone is done with stage s
+        if (!go) break;
+        if (t + PB_STAGES < ntiles) {
+            issued = t + PB_STAGES + 1;
+            if (tid == 0) {
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                tma_bulk_g2s(spos[s], gpos + (t0 + t + PB_STAGES) * PB_TJ,
+                             PB_TJ * sizeof(double2), &full[s]);
+                tma_bulk_g2s(sval[s], gval + (t0 + t + PB_STAGES) * PB_TJ, PB_TJ * sizeof(double),
+                             &full[s]);
+            }
+        }
+    }
+    // early exit: bulk copies already in flight must land before the CTA may retire
+    for (int t = consumed; t < issued; ++t)
+        mbar_wait(&full[t % PB_STAGES], (uint32_t)(t / PB_STAGES) & 1u);
+}
+
+
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------- internal launchers
@@ -235,6 +294,11 @@ int vsb_launch_curves_gather(vsb_ctx *c, const double *d_curves, const int64_t *
 int vsb_launch_body_thermal(vsb_ctx *c, int64_t n, const double *consts12, const double *d_in6,
                             double *d_atm_h, const long long *d_base_color, double *d_out4,
                             long long *d_color, double *d_types, int *d_stellar);
+// Newton <-> Kepler conversion (vsb_convert.cu)
+int vsb_launch_to_kepler(vsb_ctx *c, const int64_t *d_order, double gc, double coi_coef,
+                         int64_t *d_ref, double *d_el);
+int vsb_launch_to_newton(vsb_ctx *c, const double *d_el, const int64_t *d_ref, double gc,
+                         int *err_out);
 // kepler (vsb_kepler.cu)
 int vsb_launch_kepler_move(vsb_ctx *c, vsb_kepler_state &k, double warp);
 int vsb_launch_kepler_curves(vsb_ctx *c, vsb_kepler_state &k, int64_t first, int64_t count,

@@ -1,0 +1,371 @@
+// vsb_convert.cu -- SURVEY 8f row N1: Newton <-> Kepler conversion at load/save (sm_100a).
+//   convert.to_kepler   convert.py:193-261   (game.py:318-319 when a Newtonian map is opened)
+//   convert.to_newton   convert.py:132-190   (editor.py:295-296 when a Keplerian save is opened)
+//   kepler_to_velocity  convert.py:20-64, rot_ellipse_by_y / impl_derivative_rot_ell
+//                       phys_shared.py:133-171
+// The reference's index quirks are part of its behaviour and are reproduced: to_kepler's first
+// loop walks the bodies in INDEX order and, after the parent search, uses the body's mass rank
+// as an index into pos / vel / mass / coi (convert.py:219-225); to_newton visits the bodies in
+// index order whatever its COI sort says (:158-160).
+//
+// to_kepler's O(N^2) first loop is a sequential recurrence (step s reads the COIs written by
+// steps s' < s).  It runs as a left-looking blocked sweep over 1024-step slabs: a grid-wide scan
+// tests the slab's bodies against every COI finished before the slab (mass-sorted sources
+// streamed through shared memory by TMA bulk copies, "last match in mass order" = max rank),
+// then one CTA resolves the slab's internal dependencies step by step.  Everything else is one
+// thread per body.  Compiled with -fmad=false.
+#include "vsb_common.cuh"
+
+namespace {
+
+constexpr double PI_D = 3.141592653589793;
+constexpr int CV_T = 1024;
+
+__device__ __forceinline__ double py_mod(double a, double b)
+{
+    double r = fmod(a, b);
+    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+    return r;
+}
+
+// sorted staging: spos[l] = pos[order[l]], w2[l] = -1 (COI of that index not written yet),
+// rank[order[l]] = l, best[s] = -1, coi[] = 0
+__global__ void tk_init_kernel(const int64_t *__restrict__ order, const double2 *__restrict__ pos,
+                               int64_t n, int64_t npad, double2 *__restrict__ spos,
+                               double *__restrict__ w2, int *__restrict__ rank,
+                               int *__restrict__ best, double *__restrict__ coi)
+{
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= npad) return;
+    if (l < n) {
+        int64_t pp = order[l];
+        spos[l] = pos[pp];
+        rank[pp] = (int)l;
+        best[l] = -1;
+        coi[l] = 0.0;
+    } else {
+        spos[l] = make_double2(VSB_FAR, VSB_FAR);
+    }
+    w2[l] = -1.0;
+}
+
+// phase A: slab bodies s in [s0, s0+cnt) against every finished source rank l < rank[s]
+__global__ void __launch_bounds__(PB_BLOCK)
+tk_scan_kernel(const double2 *__restrict__ spos, const double *__restrict__ w2,
+               const double2 *__restrict__ pos, const int *__restrict__ rank, int64_t s0, int cnt,
+               int64_t chunk_tiles, int64_t ntiles, int *__restrict__ best)
+{
+    const int64_t s = s0 + (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x;
+    const bool live = s < s0 + cnt;
+    int64_t t0 = (int64_t)blockIdx.y * chunk_tiles, t1 = t0 + chunk_tiles;
+    if (t1 > ntiles) t1 = ntiles;
+    if (t0 >= t1) return;
+    const double2 me = pos[live ? s : 0];
+    const int lim_all = live ? rank[s] : 0;
+    int found = -1;
+    stream_tiles(spos, w2, t0, t1, [&](const double2 *sp, const double *sv, int64_t base) {
+        const int lim = (int)((lim_all - base) < PB_TJ ? (lim_all - base) : PB_TJ);
+#pragma unroll 4
+        for (int j = 0; j < PB_TJ; ++j) {
+            double dx = me.x - sp[j].x, dy = me.y - sp[j].y;
+            double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d2 < sv[j] && j < lim) found = (int)base + j;
+        }
+        return true;
+    });
+    if (live && found >= 0) atomicMax(&best[s], found);
+}
+
+// phase B: one CTA resolves slab [s0, s0+cnt) sequentially (convert.py:208-225)
+__global__ void __launch_bounds__(CV_T)
+tk_slab_kernel(int64_t n, int64_t s0, int cnt, const int64_t *__restrict__ order,
+               const int *__restrict__ rank, const double *__restrict__ mass,
+               const double2 *__restrict__ pos, const double2 *__restrict__ vel, double gc,
+               double coi_coef, int *__restrict__ best, double *__restrict__ coi,
+               double *__restrict__ w2, int64_t *__restrict__ ref_l)
+{
+    __shared__ double2 s_pos[CV_T];
+    __shared__ double s_w2[CV_T];
+    __shared__ int s_l[CV_T];
+    const int t = threadIdx.x;
+    const int64_t s = s0 + t;
+    const bool live = t < cnt;
+    const double2 me = live ? pos[s] : make_double2(VSB_FAR, VSB_FAR);
+    const int my_rank = live ? rank[s] : 0;
+    int my_best = live ? best[s] : -1;
+    for (int q = 0; q < cnt; ++q) {
+        if (t == q) {
+            const int64_t ref = my_best < 0 ? 0 : order[my_best];
+            ref_l[s] = ref;
+            // quirk: the mass rank `body` is used as an index from here on (:219-225)
+            const int64_t body = my_rank;
+            const double2 pr = pos[ref], pb = pos[body], vr = vel[ref], vb = vel[body];
+            const double rpx = pr.x - pb.x, rpy = pr.y - pb.y;
+            const double rvx = vr.x - vb.x, rvy = vr.y - vb.y;
+            const double u = gc * mass[ref];
+            const double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / sqrt(rpx * rpx + rpy * rpy)));
+            const double c = a > 0 ? a * pow(mass[body] / mass[ref], coi_coef) : 0.0;
+            coi[body] = c;
+            s_pos[q] = pb;            // a later step tests against pos[pot_parent = body]
+            s_w2[q] = c * c;
+            s_l[q] = rank[body];      // where index `body` sits in the mass order
+            w2[rank[body]] = c * c;   // visible to the next slabs' scans
+        }
+        __syncthreads();
+        if (live && t > q) {
+            const int l = s_l[q];
+            if (l < my_rank && l > my_best) {
+                double dx = me.x - s_pos[q].x, dy = me.y - s_pos[q].y;
+                if (dx * dx + dy * dy < s_w2[q]) my_best = l;
+            }
+        }
+    }
+}
+
+// second loop of to_kepler (:227-259), one thread per body
+__global__ void tk_elements_kernel(int64_t n, const int64_t *__restrict__ ref_l,
+                                   const double *__restrict__ mass,
+                                   const double2 *__restrict__ pos,
+                                   const double2 *__restrict__ vel, double gc,
+                                   double *__restrict__ a_l, double *__restrict__ ecc_l,
+                                   double *__restrict__ pe_l, double *__restrict__ ma_l,
+                                   double *__restrict__ dir_l)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    if (b == 0) {
+        a_l[0] = ecc_l[0] = pe_l[0] = ma_l[0] = dir_l[0] = 0.0;
+        return;
+    }
+    const int64_t ref = ref_l[b];
+    const double2 pb = pos[b], pr = pos[ref], vb = vel[b], vr = vel[ref];
+    const double rpx = pb.x - pr.x, rpy = pb.y - pr.y;
+    const double rvx = vb.x - vr.x, rvy = vb.y - vr.y;
+    const double u = gc * mass[ref];
+    const double magp = sqrt(rpx * rpx + rpy * rpy);
+    const double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / magp));
+    const double momentum = rpx * rvy - rpy * rvx;
+    const double sx = rvy, sy = -rvx;
+    const double ex = (sx * momentum / u) - rpx / magp, ey = (sy * momentum / u) - rpy / magp;
+    const double ecc = sqrt(ex * ex + ey * ey);
+    const double pe = py_mod((3 * PI_D / 2) + atan2(-ex, ey), 2 * PI_D);
+    const double dir = copysign(1.0, momentum);
+    double ta = py_mod(pe - (atan2(rpy, rpx) - PI_D), 2 * PI_D);
+    if (dir == -1) ta = 2 * PI_D - ta;
+    double ea, ma;
+    if (ecc < 1) {
+        ea = acos((ecc + cos(ta)) / (1 + (ecc * cos(ta))));
+        if (PI_D < ta && ta < 2 * PI_D) ea = 2 * PI_D - ea;
+        ma = py_mod(ea - ecc * sin(ea), 2 * PI_D);
+    } else {
+        ea = acosh((ecc + cos(ta)) / (1 + (ecc * cos(ta))));
+        ma = ecc * sinh(ea) - ea;
+    }
+    a_l[b] = a;
+    ecc_l[b] = ecc;
+    pe_l[b] = pe;
+    ma_l[b] = ma;
+    dir_l[b] = dir;
+}
+
+// ---- to_newton --------------------------------------------------------------------------
+__device__ double tn_solve_kepler_ell(double ecc, double ma, double tol)
+{
+    // enhanced_kepler_solver.py:18-69 (same restatement as vsb_kepler.cu)
+    double mr = ma, flip;
+    if (mr > PI_D) {
+        mr = 2 * PI_D - mr;
+        flip = 1;
+    } else {
+        flip = -1;
+    }
+    if (ecc > 0.99 && mr < 0.0045) {
+        double al = tol / 1e7, be = tol / 0.3, fp = 2.7 * mr, fpp = 0.301, f = 0.154;
+        for (int i = 0; i < 2; ++i) {
+            if ((fpp - fp) <= (al + be * f)) break;
+            if ((f - ecc * sin(f) - mr) > 0) fpp = f;
+            else fp = f;
+        }
+        f = 0.5 * (fp + fpp);
+        return ma + flip * (mr - f);
+    }
+    double tol2s = 2 * tol / (ecc + 2.2e-16);
+    double eapp = mr + 0.999999 * mr * (PI_D - mr) /
+                           (2. * mr + ecc - PI_D + 2.4674011002723395 / (ecc + 2.2e-16));
+    double fpp = ecc * sin(eapp), fppp = ecc * cos(eapp);
+    double fp = 1 - fppp, f = eapp - fpp - mr;
+    double delta = -f / fp;
+    double fp3 = fp * fp * fp, ffpfpp = f * fp * fpp, f2fppp = f * f * fppp;
+    delta = delta * (fp3 - 0.5 * ffpfpp + f2fppp / 3) / (fp3 - ffpfpp + 0.5 * f2fppp);
+    for (int i = 0; i < 30; ++i) {
+        if (delta * delta < fp * tol2s) break;
+        eapp = eapp + delta;
+        fp = 1 - ecc * cos(eapp);
+        delta = (mr - eapp + ecc * sin(eapp)) / fp;
+    }
+    eapp = eapp + delta;
+    return ma + flip * (mr - eapp);
+}
+
+// per body: rel_pos (:176-177) and rel_vel = kepler_to_velocity (:20-64, ellipse); err != 0
+// where the reference would raise ValueError (hyperbola at :170, sqrt domain at :37-38)
+__global__ void tn_relative_kernel(int64_t n, const double *__restrict__ mass,
+                                   const double *__restrict__ a_l, const double *__restrict__ ecc_l,
+                                   const double *__restrict__ pe_l, const double *__restrict__ ma_l,
+                                   const int64_t *__restrict__ ref_l,
+                                   const double *__restrict__ dir_l, double gc,
+                                   double2 *__restrict__ rel_pos, double2 *__restrict__ rel_vel,
+                                   int *err)
+{
+    int64_t body = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (body >= n) return;
+    if (body == 0) {
+        rel_pos[0] = rel_vel[0] = make_double2(0.0, 0.0);
+        return;
+    }
+    double a = a_l[body], ecc = ecc_l[body], pe = pe_l[body], ma = ma_l[body], dr = dir_l[body];
+    const double u = gc * mass[ref_l[body]];
+    if (dr > 0) ma = -ma;
+    if (ecc == 0) ecc = 0.00001;
+    if (ecc == 1) ecc = 1.00001;
+    if (1 - ecc * ecc < 0) {
+        atomicExch(err, 1);
+        return;
+    }
+    const double b = a * sqrt(1 - ecc * ecc);
+    const double f = sqrt(a * a - b * b);
+    const double ea = tn_solve_kepler_ell(ecc, ma, 1e-10);
+    const double rx = a * cos(ea) - f, ry = b * sin(ea);
+    const double ang = pe - PI_D;
+    const double px = rx * cos(ang) - ry * sin(ang), py = rx * sin(ang) + ry * cos(ang);
+    // kepler_to_velocity, ellipse branch
+    const double sin_p = sin(pe), cos_p = cos(pe);
+    const double frx = f * cos_p, fry = f * sin_p;
+    const double qx = px - f * cos_p, qy = py - f * sin_p;
+    const double a2 = a * a, b2 = b * b, sc = sin_p * cos_p, sin_p2 = sin_p * sin_p,
+                 cos_p2 = cos_p * cos_p;
+    double angle = atan(-(b2 * qx * cos_p2 + a2 * qx * sin_p2 + b2 * qy * sc - a2 * qy * sc) /
+                        (a2 * qy * cos_p2 + b2 * qy * sin_p2 + b2 * qx * sc - a2 * qx * sc));
+    const double arg = a * a * cos(2 * pe) + a * a - b * b * cos(2 * pe) + b * b;
+    if (arg < 0) {
+        atomicExch(err, 2);
+        return;
+    }
+    const double x_max = sqrt(arg) / sqrt(2.0) - 1e-06;
+    const double x2 = x_max * x_max, c4 = cos_p2 * cos_p2, s4 = sin_p2 * sin_p2;
+    const double y_max = (a * b * sqrt(-x2 * (c4 + s4) - 2 * x2 * cos_p2 * sin_p2 + b2 * sin_p2 + a2 * cos_p2) +
+                          a2 * x_max * sin_p * cos_p - b2 * x_max * sin_p * cos_p) /
+                         (a2 * cos_p2 + b2 * sin_p2);
+    const double x1 = x_max + frx, y1 = y_max + fry, xx2 = -x_max + frx, y2 = -y_max + fry;
+    if (((xx2 - x1) * (py - y1)) - ((y2 - y1) * (px - x1)) < 0) angle += PI_D;
+    angle = py_mod(angle, 2 * PI_D);
+    const double distance = sqrt(px * px + py * py);
+    const double speed = dr * sqrt(u * ((2 / distance) - (1 / a)));
+    rel_pos[body] = make_double2(px, py);
+    rel_vel[body] = make_double2(speed * cos(angle), speed * sin(angle));
+}
+
+// pos[body] = pos[ref] + rel_pos in INDEX order: a ref with a larger (or equal) index still
+// holds zeros when the body is visited.  Every thread folds its own chain top-down.
+__global__ void tn_compose_kernel(int64_t n, const int64_t *__restrict__ ref_l,
+                                  const double2 *__restrict__ rel_pos,
+                                  const double2 *__restrict__ rel_vel, double2 *__restrict__ pos,
+                                  double2 *__restrict__ vel, int *err)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    constexpr int MAXD = 64;
+    int64_t chain[MAXD];
+    int depth = 0;
+    int64_t node = b;
+    while (node != 0) {
+        if (depth == MAXD) {
+            atomicExch(err, 3);
+            return;
+        }
+        chain[depth++] = node;
+        const int64_t r = ref_l[node];
+        if (r >= node) break;   // not visited yet: contributes (0,0)
+        node = r;
+    }
+    double2 p = make_double2(0.0, 0.0), v = make_double2(0.0, 0.0);
+    for (int d = depth - 1; d >= 0; --d) {
+        const double2 rp = rel_pos[chain[d]], rv = rel_vel[chain[d]];
+        p.x = p.x + rp.x;
+        p.y = p.y + rp.y;
+        v.x = v.x + rv.x;
+        v.y = v.y + rv.y;
+    }
+    pos[b] = p;
+    vel[b] = v;
+}
+
+}  // namespace
+
+// Inputs already on the device in the body arrays (mass, pos, vel) + d_order.  Outputs:
+// d_ref (n int64) and d_el (5n doubles: a | ecc | pe_arg | ma | dir).
+int vsb_launch_to_kepler(vsb_ctx *c, const int64_t *d_order, double gc, double coi_coef,
+                         int64_t *d_ref, double *d_el)
+{
+    const int64_t n = c->n, npad = c->npad;
+    if (n <= 0) return VSB_OK;
+    VSB_TRY(vsb_buf_reserve(c->sorted, (size_t)npad * (16 + 8 + 4 + 4 + 8)));
+    char *base = (char *)c->sorted.p;
+    double2 *spos = (double2 *)base;
+    double *w2 = (double *)(base + (size_t)npad * 16);
+    double *coi = (double *)(base + (size_t)npad * 24);
+    int *rank = (int *)(base + (size_t)npad * 32);
+    int *best = (int *)(base + (size_t)npad * 36);
+    const double2 *pos = (const double2 *)c->pos, *vel = (const double2 *)c->vel;
+    tk_init_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(d_order, pos, n, npad,
+                                                                         spos, w2, rank, best, coi);
+    c->launches += 1;
+    const int64_t ntiles = npad / PB_TJ;
+    for (int64_t s0 = 0; s0 < n; s0 += CV_T) {
+        const int cnt = (int)((n - s0) < CV_T ? (n - s0) : CV_T);
+        if (s0 > 0) {   // nothing is finished before the first slab
+            const int rb = (cnt + PB_BLOCK - 1) / PB_BLOCK;
+            int64_t want = ((int64_t)c->sm_count * 16 + rb - 1) / rb;
+            if (want > ntiles) want = ntiles;
+            if (want < 1) want = 1;
+            const int64_t ct = (ntiles + want - 1) / want;
+            dim3 grid((unsigned)rb, (unsigned)((ntiles + ct - 1) / ct));
+            tk_scan_kernel<<<grid, PB_BLOCK, 0, c->stream>>>(spos, w2, pos, rank, s0, cnt, ct,
+                                                             ntiles, best);
+            c->launches += 1;
+        }
+        tk_slab_kernel<<<1, CV_T, 0, c->stream>>>(n, s0, cnt, d_order, rank, c->mass, pos, vel, gc,
+                                                  coi_coef, best, coi, w2, d_ref);
+        c->launches += 1;
+    }
+    tk_elements_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        n, d_ref, c->mass, pos, vel, gc, d_el, d_el + n, d_el + 2 * n, d_el + 3 * n, d_el + 4 * n);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
+
+// d_el: 5n doubles (a | ecc | pe_arg | ma | dir), d_ref n int64, masses in c->mass.
+// Writes c->pos / c->vel; *err_out: 0 ok, 1/2 reference ValueError, 3 hierarchy too deep.
+int vsb_launch_to_newton(vsb_ctx *c, const double *d_el, const int64_t *d_ref, double gc,
+                         int *err_out)
+{
+    const int64_t n = c->n;
+    if (n <= 0) return VSB_OK;
+    VSB_TRY(vsb_buf_reserve(c->scratch, 64 + 32 * (size_t)c->npad));
+    int *d_err = (int *)c->scratch.p;
+    double2 *rel_pos = (double2 *)((char *)c->scratch.p + 64);
+    double2 *rel_vel = rel_pos + c->npad;
+    VSB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
+    const unsigned g = (unsigned)((n + 255) / 256);
+    tn_relative_kernel<<<g, 256, 0, c->stream>>>(n, c->mass, d_el, d_el + n, d_el + 2 * n,
+                                                 d_el + 3 * n, d_ref, d_el + 4 * n, gc, rel_pos,
+                                                 rel_vel, d_err);
+    tn_compose_kernel<<<g, 256, 0, c->stream>>>(n, d_ref, rel_pos, rel_vel, (double2 *)c->pos,
+                                                (double2 *)c->vel, d_err);
+    c->launches += 2;
+    VSB_CUDA(cudaGetLastError());
+    VSB_CUDA(cudaMemcpyAsync(err_out, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}

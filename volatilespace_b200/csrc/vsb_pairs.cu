@@ -13,63 +13,6 @@
 
 namespace {
 
-constexpr int PB_BLOCK = 128;
-constexpr int PB_TJ = 512;
-constexpr int PB_STAGES = 2;
-
-// Streams tiles [t0, t1) of (pos2[], val[]) through shared memory and calls
-// body(sp, sv, first_source_index_of_tile) for each; all threads of the CTA must call it.
-template <typename F>
-__device__ __forceinline__ void stream_tiles(const double2 *__restrict__ gpos,
-                                             const double *__restrict__ gval, int64_t t0,
-                                             int64_t t1, F body)
-{
-    __shared__ alignas(128) double2 spos[PB_STAGES][PB_TJ];
-    __shared__ alignas(128) double sval[PB_STAGES][PB_TJ];
-    __shared__ alignas(8) uint64_t full[PB_STAGES];
-    constexpr uint32_t TILE_BYTES = PB_TJ * (sizeof(double2) + sizeof(double));
-    const int tid = threadIdx.x;
-    const int ntiles = (int)(t1 - t0);
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < PB_STAGES; ++s) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < PB_STAGES; ++s)
-            if (s < ntiles) {
-                mbar_expect_tx(&full[s], TILE_BYTES);
-                tma_bulk_g2s(spos[s], gpos + (t0 + s) * PB_TJ, PB_TJ * sizeof(double2), &full[s]);
-                tma_bulk_g2s(sval[s], gval + (t0 + s) * PB_TJ, PB_TJ * sizeof(double), &full[s]);
-            }
-    }
-    int consumed = 0;
-    int issued = ntiles < PB_STAGES ? ntiles : PB_STAGES;
-    for (int t = 0; t < ntiles; ++t) {
-        const int s = t % PB_STAGES;
-        mbar_wait(&full[s], (uint32_t)(t / PB_STAGES) & 1u);
-        consumed = t + 1;
-        const bool keep_going = body(spos[s], sval[s], (t0 + t) * PB_TJ);
-        const int go = __syncthreads_or(keep_going ? 1 : 0);  // also: everyone is done with stage s
-        if (!go) break;
-        if (t + PB_STAGES < ntiles) {
-            issued = t + PB_STAGES + 1;
-            if (tid == 0) {
-                mbar_expect_tx(&full[s], TILE_BYTES);
-                tma_bulk_g2s(spos[s], gpos + (t0 + t + PB_STAGES) * PB_TJ,
-                             PB_TJ * sizeof(double2), &full[s]);
-                tma_bulk_g2s(sval[s], gval + (t0 + t + PB_STAGES) * PB_TJ, PB_TJ * sizeof(double),
-                             &full[s]);
-            }
-        }
-    }
-    // early exit: bulk copies already in flight must land before the CTA may retire
-    for (int t = consumed; t < issued; ++t)
-        mbar_wait(&full[t % PB_STAGES], (uint32_t)(t / PB_STAGES) & 1u);
-}
-
 // ------------------------------------------------------------------ A1 find_parents
 // Stage sources in descending-mass order: sorted_pos[k] = pos[order[k]],
 // sorted_coi2[k] = coi*coi (un-fused), rank[order[k]] = k, best[k] = -1.
