@@ -268,6 +268,23 @@ int vsb_host_to_newton(vsb_ctx *ctx, int64_t n, const double *mass, const double
                        const int64_t *ref, const double *dir, double gc, double *pos_out,
                        double *vel_out);
 
+/* --------------------------------------------- COI-crossing numeric kernels
+ * Batched forms (one item per row) of the numeric routines under phys_vessel.points
+ * (phys_vessel.py:372-474); the branchy per-vessel bookkeeping around them stays host side.
+ * solve_quartic: quartic_solver.py:57-93, coef5 = (n,5) a,b,c,d,e -> roots8 = (n,4) complex as
+ *   interleaved re,im.
+ * ell_hyp_intersect_circle: orbit_intersect.py:17-52, in6 = (n,6) a,b,ecc,c_x,c_y,r ->
+ *   ea4_out (n,4) eccentric anomalies NaN-padded, count_out (n) (0 = the reference's [nan]).
+ * predict_enter_coi: orbit_intersect.py:125-174, vessel_data10 = (n,10) a,b,f,ecc,ma,ea,pea,
+ *   period,n,dr; body_data10 = (n,10) a,b,f,ecc,ma,ea,pea,n,dr,coi -> out5 (n,5) ea,b_ea,ma,
+ *   b_ma,t (all NaN when the vessel does not enter the COI within one period). */
+int vsb_host_solve_quartic(vsb_ctx *ctx, int64_t n, const double *coef5, double *roots8);
+int vsb_host_ell_hyp_intersect_circle(vsb_ctx *ctx, int64_t n, const double *in6,
+                                      double *ea4_out, int64_t *count_out);
+int vsb_host_predict_enter_coi(vsb_ctx *ctx, int64_t n, const double *vessel_data10,
+                               const double *body_data10, double tol, int64_t steps_limit,
+                               double *out5);
+
 /* --------------------------------------------- per-frame body passes
  * Physics.body (phys_editor.py:577-599, without the radius, which stays host numpy),
  * Physics.temp_color (:602-651) and Physics.classify (:654-670) in one pass over host arrays.

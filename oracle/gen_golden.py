@@ -522,6 +522,68 @@ def gen_convert(ns, conf, bd, bod):
     save("convert", **out)
 
 
+def gen_intersect(ns):
+    """N2 numeric kernels: solve_quartic, ell_hyp_intersect_circle, predict_enter_coi (jitted)."""
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    os.chdir(rh._WORKDIR)
+    from volatilespace.physics import orbit_intersect, quartic_solver
+    sys.path.remove(rh.REFERENCE_ROOT)
+    rng = np.random.default_rng(20240620)
+    out = {}
+    coef = rng.uniform(-10, 10, (300, 5))
+    coef[:, 0] = rng.uniform(0.5, 5, 300) * rng.choice([-1, 1], 300)
+    coef[:40, 1] = 0.0
+    coef[:40, 3] = 0.0                       # biquadratics
+    roots = np.array([quartic_solver.solve_quartic(*c) for c in coef])
+    out.update(q_coef=coef, q_roots_re=roots.real, q_roots_im=roots.imag)
+    # orbit / circle intersections: ellipses and hyperbolas, circle centred on the focus
+    n = 400
+    hyp = rng.uniform(0, 1, n) < 0.4
+    ecc = np.where(hyp, rng.uniform(1.05, 3.0, n), rng.uniform(0.0, 0.95, n))
+    a = rng.uniform(100, 5000, n) * np.where(hyp, -1, 1)
+    f = a * ecc
+    b = np.sqrt(np.abs(f**2 - a**2))
+    cx = f.copy()
+    cy = np.where(rng.uniform(0, 1, n) < 0.8, 0.0, rng.uniform(-200, 200, n))
+    r = np.abs(a) * rng.uniform(0.05, 2.5, n)
+    eas = np.full((n, 4), np.nan)
+    cnt = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        e = orbit_intersect.ell_hyp_intersect_circle(a[i], b[i], ecc[i], cx[i], cy[i], r[i])
+        if not (len(e) == 1 and np.isnan(e[0])):
+            cnt[i] = len(e)
+            eas[i, :len(e)] = e
+    out.update(i_a=a, i_b=b, i_ecc=ecc, i_cx=cx, i_cy=cy, i_r=r, i_ea=eas, i_cnt=cnt)
+    # predict_enter_coi: vessels and bodies around the same reference
+    m = 120
+    u = 1.0e4
+    res = np.zeros((m, 5))
+    vds, bds = np.zeros((m, 10)), np.zeros((m, 10))
+    for i in range(m):
+        va = rng.uniform(2000, 9000)
+        vecc = rng.uniform(0.0, 0.7)
+        vf = va * vecc
+        vb = np.sqrt(abs(vf**2 - va**2))
+        vper = 2 * np.pi * np.sqrt(va**3 / u)
+        vn = 2 * np.pi / vper
+        ba = rng.uniform(3000, 8000)
+        becc = rng.uniform(0.0, 0.3)
+        bf = ba * becc
+        bb = np.sqrt(abs(bf**2 - ba**2))
+        bn = np.sqrt(u / ba**3)
+        vd = (va, vb, vf, vecc, rng.uniform(0, 2 * np.pi), 0.0, rng.uniform(0, 2 * np.pi),
+              vper if i % 10 else 0.0, vn, float(rng.choice([-1, 1])))
+        vd = vd[:5] + (ns.enhanced_kepler_solver.solve_kepler_ell(vecc, vd[4], 1e-10),) + vd[6:]
+        bma = rng.uniform(0, 2 * np.pi)
+        bd = (ba, bb, bf, becc, bma, ns.enhanced_kepler_solver.solve_kepler_ell(becc, bma, 1e-10),
+              rng.uniform(0, 2 * np.pi), bn, float(rng.choice([-1, 1])),
+              rng.uniform(600, 3000) if i % 7 else 0.0)
+        res[i] = orbit_intersect.predict_enter_coi(vd, bd, 1e-5, 300)
+        vds[i], bds[i] = vd, bd
+    out.update(p_vd=vds, p_bd=bds, p_out=res)
+    save("intersect", **out)
+
+
 def main():
     ns = rh.load()
     conf, bd, bod = gen_solar(ns)
@@ -534,6 +596,7 @@ def main():
     gen_body_data(ns, conf, bd, bod)
     gen_editor_edits(ns)
     gen_convert(ns, conf, bd, bod)
+    gen_intersect(ns)
 
 
 if __name__ == "__main__":

@@ -67,6 +67,9 @@ def lib():
                                  _f64p, _f64p, _f64p]),
         "vso_to_newton": (C.c_int, [i64, _f64p, _f64p, _f64p, _f64p, _f64p, _i64p, _f64p, f64,
                                     _f64p, _f64p]),
+        "vso_solve_quartic": (None, [f64, f64, f64, f64, f64, _f64p]),
+        "vso_ell_hyp_intersect_circle": (C.c_int, [f64, f64, f64, f64, f64, f64, _f64p]),
+        "vso_predict_enter_coi": (None, [_f64p, _f64p, f64, C.c_int, _f64p]),
         "vso_editor_curve": (None, [i64, i64, _f64p, _f64p, _f64p, _f64p, _f64p, _i64p,
                                     _f64p, _f64p, _f64p, _f64p]),
     }
@@ -267,6 +270,28 @@ def vessel_culling(pos, ref, pe_d, body_coi, visible_coi, sim_screen, zoom, scre
     t = np.logical_or(t, ref == 0)
     t = np.logical_and(t, pe_d * zoom < screen_x * 15)
     return visible_vessels, np.arange(n)[t]
+
+
+def solve_quartic(a, b, c, d, e):
+    """quartic_solver.solve_quartic, quartic_solver.py:57-93 -> 4 complex roots."""
+    r = np.zeros(8)
+    lib().vso_solve_quartic(float(a), float(b), float(c), float(d), float(e), r)
+    return r[0::2] + 1j * r[1::2]
+
+
+def ell_hyp_intersect_circle(a, b, ecc, c_x, c_y, r):
+    """orbit_intersect.py:17-52 -> array of eccentric anomalies ([nan] when there is none)."""
+    ea = np.full(4, np.nan)
+    cnt = lib().vso_ell_hyp_intersect_circle(float(a), float(b), float(ecc), float(c_x),
+                                             float(c_y), float(r), ea)
+    return ea[:cnt].copy() if cnt else np.array([np.nan])
+
+
+def predict_enter_coi(vessel_data, body_data, tol, steps_limit):
+    """orbit_intersect.py:125-174 -> (ea, b_ea, ma, b_ma, t)."""
+    out = np.zeros(5)
+    lib().vso_predict_enter_coi(_f(vessel_data), _f(body_data), float(tol), int(steps_limit), out)
+    return tuple(out)
 
 
 def to_kepler(mass, pos, vel, gc, coi_coef):

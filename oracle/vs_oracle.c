@@ -675,3 +675,185 @@ int vso_to_newton(int64_t n, const double *mass, const double *a_l, const double
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ */
+/* N2 -- numeric kernels of the vessel COI-crossing machinery          */
+/* ------------------------------------------------------------------ */
+
+/* solve_cubic_one, quartic_solver.py:28-54 */
+static double solve_cubic_one(double a, double b, double c)
+{
+    double q = b / 3 - a * a / 9;
+    double r = (b * a - 3 * c) / 6 - a * a * a / 27;
+    double rq = r * r + q * q * q;
+    double z1;
+    if (rq > 0) {
+        double aa = pow(fabs(r) + sqrt(rq), 1.0 / 3);
+        double t = r >= 0 ? aa - q / aa : q / aa - aa;
+        z1 = t - a / 3;
+    } else {
+        double theta = 0;
+        if (q < 0) theta = acos(r / pow(-q, 3.0 / 2));
+        double fi = theta / 3;
+        z1 = 2 * sqrt(-q) * cos(fi) - a / 3;
+    }
+    return z1;
+}
+
+/* complex square root of a REAL argument (every cmath.sqrt in solve_quartic gets one) */
+static void csqrt_real(double x, double *re, double *im)
+{
+    if (x != x) { *re = x; *im = x; }
+    else if (x >= 0) { *re = sqrt(x); *im = 0.0; }
+    else { *re = 0.0; *im = sqrt(-x); }
+}
+
+/* solve_quartic, quartic_solver.py:57-93: roots8 = re,im of z1..z4 */
+void vso_solve_quartic(double a, double b, double c, double d, double e, double *roots8)
+{
+    double a3 = b / a, a2 = c / a, a1 = d / a, a0 = e / a;
+    double cc = a3 / 4;
+    double cc2 = cc * cc;
+    double b2 = a2 - 6 * cc2;
+    double b1 = a1 - 2 * a2 * cc + 8 * (cc * cc2);
+    double b0 = a0 - a1 * cc + a2 * cc2 - 3 * (cc2 * cc2);
+    double y = solve_cubic_one(b2, b2 * b2 / 4 - b0, -(b1 * b1) / 8);
+    if (0 > y) y = 0;
+    double s = y * y + b2 * y + b2 * b2 / 4 - b0;
+    double r;
+    if (s > 0) r = b1 < 0 ? -sqrt(s) : sqrt(s);
+    else r = NAN;
+    double pr, pi_, dummy;
+    csqrt_real(y / 2, &pr, &pi_);
+    double p_re = pr - cc, p_im = pi_;
+    double p1_re = -pr - cc, p1_im = -pi_;
+    (void)dummy;
+    double q = -y / 2 - b2 / 2;
+    double s1r, s1i, s2r, s2i;
+    csqrt_real(q - r, &s1r, &s1i);
+    csqrt_real(q + r, &s2r, &s2i);
+    roots8[0] = p_re + s1r;  roots8[1] = p_im + s1i;
+    roots8[2] = p_re - s1r;  roots8[3] = p_im - s1i;
+    roots8[4] = p1_re + s2r; roots8[5] = p1_im + s2i;
+    roots8[6] = p1_re - s2r; roots8[7] = p1_im - s2i;
+}
+
+/* ell_hyp_intersect_circle, orbit_intersect.py:17-52.  Returns the number of values written
+ * to ea4 (0 stands for the reference's [nan]). */
+int vso_ell_hyp_intersect_circle(double a, double b, double ecc, double c_x, double c_y, double r,
+                                 double *ea4)
+{
+    double roots[8], rr[4];
+    int cnt = 0, any = 0;
+    if (ecc < 1) {
+        double a_0 = a * a - 2 * a * c_x + c_x * c_x + c_y * c_y - r * r;
+        double a_1 = -4 * b * c_y;
+        double a_2 = -2 * (a * a) + 4 * (b * b) + 2 * (c_x * c_x) + 2 * (c_y * c_y) - 2 * (r * r);
+        double a_3 = -4 * b * c_y;
+        double a_4 = a * a + 2 * a * c_x + c_x * c_x + c_y * c_y - r * r;
+        vso_solve_quartic(a_4, a_3, a_2, a_1, a_0, roots);
+        for (int k = 0; k < 4; ++k)
+            if (roots[2 * k + 1] == 0.0) { rr[cnt++] = roots[2 * k]; }
+        for (int k = 0; k < cnt; ++k) if (rr[k] != 0.0) any = 1;
+        if (!any) return 0;
+        for (int k = 0; k < cnt; ++k)
+            ea4[k] = py_mod(atan2(2 * rr[k], 1.0 - rr[k] * rr[k]), 2 * VSO_PI);
+        return cnt;
+    }
+    double a_0 = -(a * a) * (c_y * c_y + b * b) + b * b * ((c_x + r) * (c_x + r));
+    double a_1 = -4 * (a * a) * r * c_y;
+    double a_2 = -2 * (a * a * (c_y * c_y + b * b + 2 * (r * r)) + b * b * (r * r - c_x * c_x));
+    double a_3 = -4 * (a * a) * r * c_y;
+    double a_4 = -(a * a) * (c_y * c_y + b * b) + b * b * ((c_x - r) * (c_x - r));
+    vso_solve_quartic(a_4, a_3, a_2, a_1, a_0, roots);
+    for (int k = 0; k < 4; ++k)
+        if (roots[2 * k + 1] == 0.0) { rr[cnt++] = roots[2 * k]; }
+    for (int k = 0; k < cnt; ++k) if (rr[k] != 0.0) any = 1;
+    if (!any) return 0;
+    for (int k = 0; k < cnt; ++k) {
+        double x = c_x + r * (1 - rr[k] * rr[k]) / (1 + rr[k] * rr[k]);
+        double y = c_y + r * 2 * rr[k] / (1 + rr[k] * rr[k]);
+        double ta = atan2(y, x - (a * ecc));
+        double ea = acosh((ecc + cos(ta)) / (1 + (ecc * cos(ta))));
+        ea4[k] = rr[k] < 0 ? -ea : ea;
+    }
+    return cnt;
+}
+
+static void oi_orb2xy(double a, double b, double f, double ecc, double pea, double ea, double *x,
+                      double *y)
+{ /* orbit_intersect.py:95-105 */
+    double xn, yn;
+    if (ecc < 1) { xn = a * cos(ea) - f; yn = b * sin(ea); }
+    else { xn = a * cosh(ea) - f; yn = b * sinh(ea); }
+    *x = xn * cos(pea - VSO_PI) - yn * sin(pea - VSO_PI);
+    *y = xn * sin(pea - VSO_PI) + yn * cos(pea - VSO_PI);
+}
+
+static void oi_move(double *ma, double ecc, double dr, double n, double *prev_ea, double dt,
+                    double *ea)
+{ /* orbit_intersect.py:108-121 (the two wrap statements there are no-ops) */
+    if (ecc < 1) {
+        *ma += dr * n * dt;
+        *ea = vso_solve_kepler_ell(ecc, *ma, 1e-10);
+    } else {
+        *ma += dr * n * -1 * dt;
+        *ea = vso_newton_root_kepler_hyp(ecc, *ma, *prev_ea);
+        *prev_ea = *ea;
+    }
+}
+
+static double oi_wrap(double angle)
+{
+    if (angle >= 2 * VSO_PI) return angle - 2 * VSO_PI;
+    if (angle < 0) return angle + 2 * VSO_PI;
+    return angle;
+}
+
+/* predict_enter_coi, orbit_intersect.py:125-174.  vd = a,b,f,ecc,ma,ea,pea,period,n,dr;
+ * bd = a,b,f,ecc,ma,ea,pea,n,dr,coi; out5 = ea, b_ea, ma, b_ma, t (NaN x5 when nothing). */
+void vso_predict_enter_coi(const double *vd, const double *bd, double tol, int steps_limit,
+                           double *out5)
+{
+    double a = vd[0], b = vd[1], f = vd[2], ecc = vd[3], ma = vd[4], ea = vd[5], pea = vd[6],
+           period = vd[7], n = vd[8], dr = vd[9];
+    double b_a = bd[0], b_b = bd[1], b_f = bd[2], b_ecc = bd[3], b_ma = bd[4], b_ea = bd[5],
+           b_pea = bd[6], b_n = bd[7], b_dr = bd[8], b_coi = bd[9];
+    double prev_ea = ea, b_prev_ea = b_ea;
+    for (int k = 0; k < 5; ++k) out5[k] = NAN;
+    if (period == 0 || b_coi == 0) return;
+    double t = 0;
+    double c1 = period / b_coi * 5, c2 = period / 2, c3 = period / 30;
+    double m1 = c2 < c1 ? c2 : c1;              /* min(c1, c2) */
+    double m2 = c3 > m1 ? c3 : m1;              /* max(m1, c3) */
+    long long steps = (long long)m2;
+    if (steps_limit > steps) steps = steps_limit;
+    double dt = period / (double)steps;
+    double t_end = period;
+    while (t < t_end) {
+        oi_move(&ma, ecc, dr, n, &prev_ea, dt, &ea);
+        oi_move(&b_ma, b_ecc, b_dr, b_n, &b_prev_ea, dt, &b_ea);
+        double rvx, rvy, rbx, rby;
+        oi_orb2xy(a, b, f, ecc, pea, ea, &rvx, &rvy);
+        oi_orb2xy(b_a, b_b, b_f, b_ecc, b_pea, b_ea, &rbx, &rby);
+        double dx = rvx - rbx, dy = rvy - rby;
+        double d = pow(dx * dx + dy * dy, 0.5);
+        if (d < b_coi) {
+            for (int it = 0; it < 30; ++it) {
+                dt = fabs(dt) / 2 * (d < b_coi ? -1 : 1);
+                t += dt;
+                oi_move(&ma, ecc, dr, n, &prev_ea, dt, &ea);
+                oi_move(&b_ma, b_ecc, b_dr, b_n, &b_prev_ea, dt, &b_ea);
+                oi_orb2xy(a, b, f, ecc, pea, ea, &rvx, &rvy);
+                oi_orb2xy(b_a, b_b, b_f, b_ecc, b_pea, b_ea, &rbx, &rby);
+                dx = rvx - rbx; dy = rvy - rby;
+                d = pow(dx * dx + dy * dy, 0.5);
+                if (fabs(d - b_coi) < tol) break;
+            }
+            out5[0] = oi_wrap(ea); out5[1] = oi_wrap(b_ea); out5[2] = oi_wrap(ma);
+            out5[3] = oi_wrap(b_ma); out5[4] = t;
+            return;
+        }
+        t += dt;
+    }
+}

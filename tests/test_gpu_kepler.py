@@ -323,6 +323,34 @@ def test_to_kepler_multi_slab_vs_oracle(dev, oracle):
                                    err_msg=key)
 
 
+def test_intersect_kernels_golden(dev):
+    """N2: batched solve_quartic / ell_hyp_intersect_circle / predict_enter_coi against the
+    live reference's jitted functions."""
+    from volatilespace_b200 import orbit_intersect as oi
+    g = golden("intersect")
+    c = g["q_coef"]
+    z = oi.solve_quartic(c[:, 0], c[:, 1], c[:, 2], c[:, 3], c[:, 4], device=dev)
+    scale = np.maximum(1.0, np.abs(g["q_roots_re"]) + np.abs(g["q_roots_im"]))
+    ok = np.isfinite(g["q_roots_re"]) & np.isfinite(g["q_roots_im"])
+    assert np.all(np.abs(z.real - g["q_roots_re"])[ok] <= 1e-9 * scale[ok])
+    assert np.all(np.abs(z.imag - g["q_roots_im"])[ok] <= 1e-9 * scale[ok])
+    assert np.array_equal(np.isnan(z.real), np.isnan(g["q_roots_re"]))
+    ea, cnt = oi.ell_hyp_intersect_circle(g["i_a"], g["i_b"], g["i_ecc"], g["i_cx"], g["i_cy"],
+                                          g["i_r"], device=dev)
+    assert (cnt == g["i_cnt"]).mean() > 0.99          # exact-zero imaginary parts: ulp-sensitive
+    same = cnt == g["i_cnt"]
+    np.testing.assert_allclose(ea[same], g["i_ea"][same], rtol=1e-8, atol=1e-8, equal_nan=True)
+    one = oi.ell_hyp_intersect_circle(g["i_a"][3], g["i_b"][3], g["i_ecc"][3], g["i_cx"][3],
+                                      g["i_cy"][3], g["i_r"][3], device=dev)
+    assert len(one) == max(1, int(g["i_cnt"][3]))
+    out = oi.predict_enter_coi(g["p_vd"], g["p_bd"], 1e-5, 300, device=dev)
+    want = g["p_out"]
+    assert np.array_equal(np.isnan(out[:, 0]), np.isnan(want[:, 0]))
+    hit = ~np.isnan(want[:, 0])
+    np.testing.assert_allclose(out[hit], want[hit], rtol=1e-6, atol=1e-6)
+    assert hit.sum() >= 20
+
+
 def test_kepler_errors(dev):
     from volatilespace_b200._lib import VsbError, KIND_BODY, KIND_VESSEL
     dev.kepler_free(KIND_BODY)

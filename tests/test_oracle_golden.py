@@ -297,3 +297,23 @@ def test_convert(oracle):
     orb = {key: g["c60_k_" + key] for key in ("a", "ecc", "pe_arg", "ma", "ref", "dir")}
     with pytest.raises(ValueError):          # hyperbolic bodies: the reference raises too
         oracle.to_newton(g["c60_mass"], orb, gc, cc)
+
+
+# ------------------------------------------------------------- N2 COI-crossing kernels
+def test_intersect_kernels(oracle):
+    g = golden("intersect")
+    for c, re, im in zip(g["q_coef"], g["q_roots_re"], g["q_roots_im"]):
+        z = oracle.solve_quartic(*c)
+        np.testing.assert_allclose(z.real, re, rtol=1e-13, atol=1e-13, equal_nan=True)
+        np.testing.assert_allclose(z.imag, im, rtol=1e-13, atol=1e-13, equal_nan=True)
+    for i in range(len(g["i_a"])):
+        e = oracle.ell_hyp_intersect_circle(g["i_a"][i], g["i_b"][i], g["i_ecc"][i], g["i_cx"][i],
+                                            g["i_cy"][i], g["i_r"][i])
+        cnt = 0 if (len(e) == 1 and np.isnan(e[0])) else len(e)
+        assert cnt == g["i_cnt"][i]
+        if cnt:
+            np.testing.assert_allclose(e, g["i_ea"][i, :cnt], rtol=1e-12, atol=1e-12)
+    for vd, bd, want in zip(g["p_vd"], g["p_bd"], g["p_out"]):
+        got = oracle.predict_enter_coi(vd, bd, 1e-5, 300)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, equal_nan=True)
+    assert (~np.isnan(g["p_out"][:, 0])).sum() >= 20

@@ -96,6 +96,9 @@ SIGNATURES = {
     "vsb_kepler_curves_device_ptr": [_ctx, C.c_int, C.POINTER(C.c_void_p)],
     "vsb_host_to_kepler": [_ctx, _i64, _pv, _pv, _pv, _pv, _f64, _f64] + [_pv] * 6,
     "vsb_host_to_newton": [_ctx, _i64] + [_pv] * 7 + [_f64, _pv, _pv],
+    "vsb_host_solve_quartic": [_ctx, _i64, _pv, _pv],
+    "vsb_host_ell_hyp_intersect_circle": [_ctx, _i64, _pv, _pv, _pv],
+    "vsb_host_predict_enter_coi": [_ctx, _i64, _pv, _pv, _f64, _i64, _pv],
     "vsb_host_body_thermal": [_ctx, _i64] + [_pv] * 16,
     "vsb_host_culling": [_ctx, _i64, _pv, _pv, _pv, _f64, _pv],
     "vsb_kepler_culling": [_ctx, C.c_int, _pv, _pv, _f64, _pv, _pi],

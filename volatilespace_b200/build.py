@@ -31,6 +31,7 @@ SOURCES = {
     "vsb_visible.cu": ["-fmad=false"],
     "vsb_body.cu": ["-fmad=false"],
     "vsb_convert.cu": ["-fmad=false"],
+    "vsb_intersect.cu": ["-fmad=false"],
 }
 
 

@@ -1180,6 +1180,53 @@ extern "C" int vsb_host_to_newton(vsb_ctx *c, int64_t n, const double *mass, con
     return d2h(c, vel_out, c->vel, 16 * (size_t)n);
 }
 
+// ---------------------------------------------------------------- N2: COI-crossing numeric kernels
+extern "C" int vsb_host_solve_quartic(vsb_ctx *c, int64_t n, const double *coef5, double *roots8)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && (n == 0 || (coef5 && roots8)), VSB_ERR_ARG,
+              "vsb_host_solve_quartic: bad argument");
+    if (n == 0) return VSB_OK;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * 13 * (size_t)n));
+    double *d_in = (double *)c->host_stage.p, *d_out = d_in + 5 * n;
+    VSB_CUDA(cudaMemcpyAsync(d_in, coef5, 40 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_quartic(c, n, d_in, d_out));
+    return d2h(c, roots8, d_out, 64 * (size_t)n);
+}
+
+extern "C" int vsb_host_ell_hyp_intersect_circle(vsb_ctx *c, int64_t n, const double *in6,
+                                                 double *ea4_out, int64_t *count_out)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && (n == 0 || (in6 && ea4_out && count_out)), VSB_ERR_ARG,
+              "vsb_host_ell_hyp_intersect_circle: bad argument");
+    if (n == 0) return VSB_OK;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * 11 * (size_t)n));
+    double *d_in = (double *)c->host_stage.p, *d_ea = d_in + 6 * n;
+    int64_t *d_cnt = (int64_t *)(d_ea + 4 * n);
+    VSB_CUDA(cudaMemcpyAsync(d_in, in6, 48 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_intersect(c, n, d_in, d_ea, d_cnt));
+    VSB_CUDA(cudaMemcpyAsync(ea4_out, d_ea, 32 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    return d2h(c, count_out, d_cnt, 8 * (size_t)n);
+}
+
+extern "C" int vsb_host_predict_enter_coi(vsb_ctx *c, int64_t n, const double *vessel_data10,
+                                          const double *body_data10, double tol,
+                                          int64_t steps_limit, double *out5)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && steps_limit > 0 && steps_limit < (1ll << 31) &&
+                  (n == 0 || (vessel_data10 && body_data10 && out5)),
+              VSB_ERR_ARG, "vsb_host_predict_enter_coi: bad argument");
+    if (n == 0) return VSB_OK;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * 25 * (size_t)n));
+    double *d_vd = (double *)c->host_stage.p, *d_bd = d_vd + 10 * n, *d_out = d_bd + 10 * n;
+    VSB_CUDA(cudaMemcpyAsync(d_vd, vessel_data10, 80 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_bd, body_data10, 80 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_predict_enter_coi(c, n, d_vd, d_bd, tol, (int)steps_limit, d_out));
+    return d2h(c, out5, d_out, 40 * (size_t)n);
+}
+
 // ---------------------------------------------------------------- N4: body thermal passes
 extern "C" int vsb_host_body_thermal(vsb_ctx *c, int64_t n, const double *consts12,
                                      const double *mass, const double *den, const double *rad,

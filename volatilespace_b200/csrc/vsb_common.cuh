@@ -299,6 +299,11 @@ int vsb_launch_to_kepler(vsb_ctx *c, const int64_t *d_order, double gc, double c
                          int64_t *d_ref, double *d_el);
 int vsb_launch_to_newton(vsb_ctx *c, const double *d_el, const int64_t *d_ref, double gc,
                          int *err_out);
+// COI-crossing numeric kernels (vsb_intersect.cu)
+int vsb_launch_quartic(vsb_ctx *c, int64_t n, const double *d_coef, double *d_roots);
+int vsb_launch_intersect(vsb_ctx *c, int64_t n, const double *d_in6, double *d_ea, int64_t *d_cnt);
+int vsb_launch_predict_enter_coi(vsb_ctx *c, int64_t n, const double *d_vd, const double *d_bd,
+                                 double tol, int steps_limit, double *d_out5);
 // kepler (vsb_kepler.cu)
 int vsb_launch_kepler_move(vsb_ctx *c, vsb_kepler_state &k, double warp);
 int vsb_launch_kepler_curves(vsb_ctx *c, vsb_kepler_state &k, int64_t first, int64_t count,
