@@ -82,6 +82,26 @@ def test_allpairs_plummer_sampled_rows(dev, oracle, gravity_mode):
         assert err < 1e-11, (r, err)
 
 
+def test_allpairs_disk1m_sampled_rows(dev, oracle):
+    """The headline workload itself (1M-body rotating disk, symmetric kernel): accelerations of
+    48 sampled target rows against the oracle (each row is 1M reference pair evaluations)."""
+    from volatilespace_b200 import synth
+    from volatilespace_b200._lib import F_ACC
+    s = synth.rotating_disk(1048576)
+    dev.upload_bodies(s["mass"], s["pos"], s["vel"])
+    dev.set_gravity_mode("sym")
+    dev.allpairs_accel(s["gc"])
+    dev.set_gravity_mode("auto")
+    acc = dev.get(F_ACC)
+    assert np.all(np.isfinite(acc))
+    rows = np.concatenate(([1, 2047, 2048, 1048575],
+                           np.random.default_rng(3).choice(1048576, 44, replace=False)))
+    for r in rows:
+        want = oracle.allpairs_accel(s["mass"], s["pos"], s["gc"], int(r), int(r) + 1)[0]
+        err = np.linalg.norm(acc[r] - want) / np.linalg.norm(want)
+        assert err < 1e-11, (r, err)
+
+
 def test_allpairs_steps_vs_oracle_and_golden(dev, oracle, gravity_mode):
     g = golden("allpairs_small")
     pos, vel = g["pos0"].copy(), g["vel0"].copy()

@@ -219,7 +219,13 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
         struct T { sym_task t; int cost; };
         T *all = (T *)malloc(sizeof(T) * (size_t)(pairs + M));
         int *qfirst = (int *)malloc(sizeof(int) * (size_t)(M + 1));
-        VSB_CHECK(all && qfirst, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
+        sym_task *mine = (sym_task *)malloc(sizeof(sym_task) * (size_t)(pairs + M + 1));
+        if (!all || !qfirst || !mine) {
+            free(all);
+            free(qfirst);
+            free(mine);
+            VSB_CHECK(false, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
+        }
         int nt = 0, slot = 0;
         for (int q = 0; q < M; ++q) {
             qfirst[q] = slot;
@@ -233,7 +239,6 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
         qfirst[M] = slot;
         // descending cost (stable counting order), then deal round-robin to ranks
         int maxc = 2 * chunk;
-        sym_task *mine = (sym_task *)malloc(sizeof(sym_task) * (size_t)(nt + 1));
         int nm = 0, dealt = 0;
         for (int cst = maxc; cst >= 0; --cst)
             for (int i = 0; i < nt; ++i)
@@ -241,17 +246,24 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
                     if (dealt % world == rank) mine[nm++] = all[i].t;
                     ++dealt;
                 }
-        VSB_TRY(vsb_buf_reserve(c->sym_tab, sizeof(sym_task) * (size_t)(nm + 1) +
-                                                sizeof(int) * (size_t)(M + 1) + 256));
-        VSB_CUDA(cudaMemcpyAsync(c->sym_tab.p, mine, sizeof(sym_task) * (size_t)nm,
-                                 cudaMemcpyHostToDevice, c->stream));
-        char *qf = (char *)c->sym_tab.p + (sizeof(sym_task) * (size_t)(nm + 1) + 255) / 256 * 256;
-        VSB_CUDA(cudaMemcpyAsync(qf, qfirst, sizeof(int) * (size_t)(M + 1), cudaMemcpyHostToDevice,
-                                 c->stream));
-        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        int rc = vsb_buf_reserve(c->sym_tab, sizeof(sym_task) * (size_t)(nm + 1) +
+                                                 sizeof(int) * (size_t)(M + 1) + 512);
+        char *qf = nullptr;
+        cudaError_t ce = cudaSuccess;
+        if (rc == VSB_OK) {
+            qf = (char *)c->sym_tab.p + (sizeof(sym_task) * (size_t)(nm + 1) + 255) / 256 * 256;
+            ce = cudaMemcpyAsync(c->sym_tab.p, mine, sizeof(sym_task) * (size_t)nm,
+                                 cudaMemcpyHostToDevice, c->stream);
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(qf, qfirst, sizeof(int) * (size_t)(M + 1),
+                                     cudaMemcpyHostToDevice, c->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+        }
         free(all);
         free(qfirst);
         free(mine);
+        VSB_TRY(rc);
+        VSB_CUDA(ce);
         c->sym_tasks_n = n;
         c->sym_world = world;
         c->sym_rank = rank;
