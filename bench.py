@@ -184,6 +184,7 @@ def flush_l2(torch, stream):
 def time_ticks(torch, stream, fn, steps, barrier):
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
+    flush_l2(torch, stream)     # untimed: allocates the buffer, loads torch's fill kernel
     barrier()
     torch.cuda.synchronize()
     ev0.record(stream)
