@@ -98,7 +98,8 @@ int vsb_bodies_set_rows(vsb_ctx *ctx, int64_t row0, int64_t row1);
 int vsb_find_parents(vsb_ctx *ctx, const int64_t *order_desc_mass, int64_t *parents_out);
 
 /* A3  Physics.gravity, phys_editor.py:357-378: one tick of the parent/COI model
- * (find_parents, gravity_one :51-60, rel_vel fix-up, vel compose, pos += vel). */
+ * (find_parents, gravity_one :51-60, rel_vel fix-up, vel compose, pos += vel).
+ * order_desc_mass may be NULL to reuse the order uploaded by the previous call. */
 int vsb_gravity_ref(vsb_ctx *ctx, double gc, const int64_t *order_desc_mass);
 
 /* A4  documented all-pairs model, documentation/orbital-physics/

@@ -371,6 +371,17 @@ extern "C" int vsb_gravity_ref(vsb_ctx *c, double gc, const int64_t *order)
     CTX(c);
     VSB_TRY(need_bodies(c, "vsb_gravity_ref"));
     VSB_TRY(upload_order(c, "vsb_gravity_ref", order));
+    if (c->n <= 1024 && !getenv("VSB_NO_FUSED_FRAME")) {
+        // small systems: the whole tick in one single-CTA launch (bit-identical results)
+        VSB_TRY(vsb_launch_editor_frame_small(c, gc, 0.0, (const int64_t *)c->order.p, 1, 0, 0,
+                                              nullptr));
+        int64_t *h = (int64_t *)c->h_key;
+        VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                 c->stream));
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        VSB_CHECK(h[3] == 0, VSB_ERR_STATE, "vsb_gravity_ref: parent chain deeper than 48 levels");
+        return VSB_OK;
+    }
     return vsb_launch_gravity_ref(c, gc, (const int64_t *)c->order.p);
 }
 
@@ -502,7 +513,7 @@ extern "C" int vsb_editor_ticks(vsb_ctx *c, double gc, double coi_coef, const in
             d_packed = (double *)c->host_stage.p;
         }
         VSB_TRY(vsb_launch_editor_frame_small(c, gc, coi_coef, d_order, (int)max_ticks,
-                                              do_kepler_basic, d_packed));
+                                              do_kepler_basic, 1, d_packed));
         if (frame_out) {
             VSB_TRY(d2h(c, frame_out, d_packed, 8 * rec_words));
             h = (int64_t *)frame_out;

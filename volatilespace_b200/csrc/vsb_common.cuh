@@ -276,7 +276,8 @@ int vsb_launch_swap_rows(vsb_ctx *c, int64_t a, int64_t b);
 int vsb_launch_translate(vsb_ctx *c, int64_t ref_row);
 int vsb_launch_pad_tail(vsb_ctx *c);
 int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order,
-                                  int max_ticks, int do_kepler_basic, double *d_packed);
+                                  int max_ticks, int do_kepler_basic, int do_collision,
+                                  double *d_packed);
 int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptrs,
                            const int *widths, int nfields, double *d_out, int64_t *words_out);
 int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double *d_out);

@@ -476,7 +476,7 @@ constexpr int FR_MAX = 1024;
 
 __global__ void __launch_bounds__(FR_MAX)
 editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int do_kepler_basic,
-                          const int64_t *__restrict__ order, const double *__restrict__ g_mass,
+                          int do_collision, const int64_t *__restrict__ order, const double *__restrict__ g_mass,
                           double2 *g_pos, double2 *g_vel, double2 *g_rel_vel, double *g_coi,
                           const double *__restrict__ g_rad, int64_t *g_parents, double *g_focus,
                           double2 *g_ecc_v, double *g_semi_major, double *g_semi_minor,
@@ -595,6 +595,7 @@ editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int 
         }
         __syncthreads();
         ++ticks;
+        if (!do_collision) continue;   // plain Physics.gravity(): no collision phase
         // ---- check_collision (:547-551): first j > i per thread, then the smallest (i,j)
         unsigned long long key = ~0ull;
         if (t < n - 1) {
@@ -872,7 +873,8 @@ int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double 
 
 // Fused small-N frame; hdr (4 x int64) lands in c->scratch.p.  n <= 1024 only.
 int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order,
-                                  int max_ticks, int do_kepler_basic, double *d_packed)
+                                  int max_ticks, int do_kepler_basic, int do_collision,
+                                  double *d_packed)
 {
     const int n = (int)c->n;
     VSB_CHECK(n >= 1 && n <= FR_MAX, VSB_ERR_ARG, "editor_frame_small: n=%d", n);
@@ -883,7 +885,8 @@ int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const 
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = (n + 31) / 32 * 32;
     editor_frame_small_kernel<<<1, threads, smem, c->stream>>>(
-        n, max_ticks, gc, coi_coef, do_kepler_basic, d_order, c->mass, (double2 *)c->pos,
+        n, max_ticks, gc, coi_coef, do_kepler_basic, do_collision, d_order, c->mass,
+        (double2 *)c->pos,
         (double2 *)c->vel, (double2 *)c->rel_vel, c->coi, c->rad, c->parents, c->focus,
         (double2 *)c->ecc_v, c->semi_major, c->semi_minor, c->periapsis_arg,
         (int64_t *)c->scratch.p, d_packed);

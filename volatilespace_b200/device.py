@@ -114,7 +114,7 @@ class Device:
         return out
 
     def gravity_ref(self, gc, order):
-        order = i64(order)
+        order = None if order is None else i64(order)
         check(self.L.vsb_gravity_ref(self.h, float(gc), ptr(order)))
 
     def allpairs_accel(self, gc):

@@ -82,8 +82,24 @@ class _DeviceBodies:
             self._stale.discard(name)
 
     def pull(self, *names):
-        """Refresh host mirrors in place from the device."""
-        for name in names or tuple(self._stale):
+        """Refresh host mirrors in place from the device (one copy for several fields)."""
+        names = names or tuple(self._stale)
+        if len(names) > 1:
+            n = len(self.mass)
+            buf = self.dev.get_many([_FIELDS[k] for k in names])
+            off = 0
+            for k in names:
+                w = 2 if k in _WIDE else 1
+                chunk = buf[off:off + n * w]
+                off += n * w
+                dst = getattr(self, k)
+                if k == "parents":
+                    dst[:] = chunk.view(np.int64)
+                else:
+                    dst[...] = chunk.reshape(dst.shape)
+                self._stale.discard(k)
+            return
+        for name in names:
             self.dev.get(_FIELDS[name], out=getattr(self, name))
             self._stale.discard(name)
 
@@ -178,7 +194,9 @@ class Physics(_DeviceBodies):
 
     # phys_editor.py:357-378
     def gravity(self):
-        self.dev.gravity_ref(self.gc, self._order())
+        order = None if self._order_on_device else self._order()
+        self.dev.gravity_ref(self.gc, order)
+        self._order_on_device = True
         self._touched("parents", "rel_vel", "vel", "pos")
 
     # phys_editor.py:577-599 (radius; the thermal/atmosphere part is UI data, out of scope)
