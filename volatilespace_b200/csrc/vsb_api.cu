@@ -876,6 +876,12 @@ extern "C" int vsb_kepler_load(vsb_ctx *c, int kind, int64_t n, int64_t P, const
               VSB_ERR_ARG, "vsb_kepler_load: bad argument");
     VSB_CUDA(cudaStreamSynchronize(c->stream));
     free_kepler(*kp);
+    if (kind == VSB_KIND_BODY && c->kep[VSB_KIND_VESSEL].ref_pos_borrowed) {
+        // the vessel state was borrowing the old BODY positions: drop the alias
+        c->kep[VSB_KIND_VESSEL].ref_pos = nullptr;
+        c->kep[VSB_KIND_VESSEL].ref_pos_borrowed = 0;
+        c->kep[VSB_KIND_VESSEL].nref = 0;
+    }
     vsb_kepler_state &k = *kp;
     // slab (8-byte words): 9 element arrays + pos(2) + pr(2) + ref + lvl_idx = 15n, tab 4P, t P;
     // every array starts on a 256-byte boundary (double2 / 128-bit accesses)
@@ -1408,5 +1414,10 @@ extern "C" int vsb_kepler_free(vsb_ctx *c, int kind)
     VSB_TRY(kep_of(c, "vsb_kepler_free", kind, &k));
     VSB_CUDA(cudaStreamSynchronize(c->stream));
     free_kepler(*k);
+    if (kind == VSB_KIND_BODY && c->kep[VSB_KIND_VESSEL].ref_pos_borrowed) {
+        c->kep[VSB_KIND_VESSEL].ref_pos = nullptr;
+        c->kep[VSB_KIND_VESSEL].ref_pos_borrowed = 0;
+        c->kep[VSB_KIND_VESSEL].nref = 0;
+    }
     return VSB_OK;
 }
