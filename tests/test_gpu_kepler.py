@@ -131,6 +131,44 @@ def test_game_vessel_path_golden(dev):
     assert np.all(np.abs(cm - g["v_curves_mov"]) <= 1e-12 * scale)
 
 
+def test_vessel_borrows_resident_body_positions(dev):
+    """vessel move with body_pos=None uses the device-resident BODY positions (no host round
+    trip): identical to passing the same positions from the host, also after a BODY reload."""
+    from volatilespace_b200._lib import KIND_BODY, KIND_VESSEL, K_POS, K_EA
+    from volatilespace_b200.phys_body import Physics as BodyPhysics
+    from volatilespace_b200.synth import calc_orb
+    g = golden("game_mode")
+    P = int(g["P"])
+    conf = {"gc": float(g["gc"]), "coi_coef": float(g["coi_coef"])}
+    orbd = {"a": g["a"], "ecc": g["ecc"], "pe_arg": g["pea"], "ma": g["ma0"], "ref": g["ref"],
+            "dir": g["dr"]}
+    nv = len(g["v_a"])
+    orb = calc_orb("vessel", g["v_ref"], g["mass"], None, conf["gc"], 0.0, g["v_a"], g["v_ecc"])
+
+    def load_vessels():
+        dev.kepler_load(KIND_VESSEL, P, g["v_a"], orb["b"], orb["f"], g["v_ecc"], g["v_pea"],
+                        orb["n"], g["v_dr"], g["v_ma0"], g["v_ea0"], g["v_ref"])
+    res = []
+    for mode in ("resident", "host"):
+        pb = BodyPhysics(dev, curve_points=P)
+        pb.load(conf, {"mass": g["mass"]}, orbd)
+        pb.initial(1)
+        load_vessels()
+        for _ in range(5):
+            pos, _, _ = pb.move(2)
+            dev.kepler_move(KIND_VESSEL, 2, None if mode == "resident" else pos)
+        dev.kepler_curves(KIND_VESSEL)
+        res.append((dev.kepler_get(KIND_VESSEL, K_POS, nv), dev.kepler_get(KIND_VESSEL, K_EA, nv),
+                    dev.kepler_curves_get(KIND_VESSEL, 0, nv, P)))
+        if mode == "resident":      # reload the BODY state while the vessel state borrows it
+            pb2 = BodyPhysics(dev, curve_points=P)
+            pb2.load(conf, {"mass": g["mass"]}, orbd)
+            pb2.initial(1)
+            dev.kepler_move(KIND_VESSEL, 0, None)      # re-borrows, must not touch freed memory
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+
+
 def test_vessel_tick_fused_equals_split_and_oracle(dev, oracle):
     """Config-4 shaped input at a size the oracle finishes in seconds: the fused
     move+curves kernel must equal move followed by curves bit for bit, and match the
