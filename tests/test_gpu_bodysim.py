@@ -582,6 +582,36 @@ def test_body_data_golden(dev):
         assert (out["color"] != g[tag + "_color"]).sum() <= 2
 
 
+def test_editor_get_bodies_matches_reference_tuple(dev):
+    """editor.py:1517-1523: get_bodies / get_atmosphere / get_base_color / temp_color / classify
+    after load_system, against the reference's arrays for the Solar System."""
+    from volatilespace_b200.phys_editor import Physics
+    g = golden("body_data")
+    s = golden("solar_editor")
+    ph = Physics(dev)
+    conf = {"gc": float(g["gc"]), "rad_mult": float(g["rad_mult"]), "coi_coef": 0.7,
+            "mass_thermal_mult": float(g["mass_thermal_mult"]),
+            "min_planet_mass": float(g["min_mass"])}
+    ph.load_system(conf, {"mass": g["solar_mass"], "den": g["solar_den"],
+                          "color": g["solar_base_color"], "atm_pres0": g["solar_atm_pres0"],
+                          "atm_scale_h": g["solar_atm_scale_h"], "atm_den0": g["solar_atm_den0"]},
+                   {"pos": s["pos0"], "vel": s["vel0"]})
+    color = ph.temp_color()
+    ph.classify()
+    (names, types, mass, den, temp, lum, sclass, pos, vel, color2, rad, rad_sc,
+     surf_grav) = ph.get_bodies()
+    assert color is color2 and len(names) == 15
+    np.testing.assert_allclose(temp, g["solar_temp"], rtol=1e-13)
+    np.testing.assert_allclose(lum, g["solar_luminosity"], rtol=1e-13)
+    np.testing.assert_allclose(rad_sc, g["solar_rad_sc"], rtol=1e-13)
+    np.testing.assert_allclose(surf_grav, g["solar_surf_grav"], rtol=1e-13)
+    assert np.array_equal(rad, g["solar_rad"]) and np.array_equal(types, g["solar_types"])
+    assert np.array_equal(sclass, g["solar_stellar_class"])
+    assert np.abs(color - g["solar_color"]).max() <= 1
+    np.testing.assert_allclose(ph.get_atmosphere()[3], g["solar_atm_h"], rtol=1e-13)
+    assert np.array_equal(ph.get_base_color(), g["solar_base_color"])
+
+
 # ------------------------------------------------------------------ error behaviour
 def test_errors_are_reported(dev):
     from volatilespace_b200._lib import VsbError, F_POS

@@ -81,7 +81,9 @@ def test_game_body_path_golden(dev):
     pb.load({"gc": float(g["gc"]), "coi_coef": float(g["coi_coef"])}, {"mass": g["mass"]},
             {"a": g["a"], "ecc": g["ecc"], "pe_arg": g["pea"], "ma": g["ma0"], "ref": g["ref"],
              "dir": g["dr"]})
-    body_orb, pos, ma, ea, cm = pb.initial(1)
+    body_data, body_orb, pos, ma, ea, cm = pb.initial(1)
+    assert set(body_data) >= {"name", "type", "mass", "den", "temp", "lum", "class", "color_b",
+                              "color", "radius", "rad_sc", "surf_grav", "atm_h"}
     for k, gk in (("b", "orb_b"), ("f", "orb_f"), ("coi", "orb_coi"), ("n", "orb_n"),
                   ("per", "orb_per"), ("u", "orb_u"), ("pe_d", "orb_pe_d"), ("ap_d", "orb_ap_d")):
         np.testing.assert_allclose(body_orb[k], g[gk], rtol=1e-14, err_msg=k)
@@ -276,15 +278,16 @@ def test_culling_golden(dev):
     dev.kepler_set(KIND_VESSEL, K_POS, g["v_pos"])
     pb = BodyPhysics(dev, curve_points=8)
     pb.n_bodies, pb.coi, pb.a = nb, g["b_coi"], g["b_a"]
+    pb.radius, pb.atm_h, pb.screen_x = g["b_radius"], g["b_atm_h"], float(g["b_screen_x"])
     pv = VesselPhysics(dev, curve_points=8)
-    pv.n_vessels, pv.pe_d = nv, g["v_pe_d"]
-    sx = float(g["b_screen_x"])
+    pv.n_vessels, pv.pe_d, pv.body_coi = nv, g["v_pe_d"], g["b_coi"]
+    pv.screen_x = float(g["b_screen_x"])
     for k, (sb, zoom) in enumerate(zip(g["b_sb"], g["b_zoom"])):
-        vb, vc, vo = pb.culling(sb, float(zoom), g["b_radius"], g["b_atm_h"], sx)
+        vb, vc, vo = pb.culling(sb, float(zoom))
         assert np.array_equal(vb, g["b%d_bodies" % k])
         assert np.array_equal(vc, g["b%d_coi" % k])
         assert np.array_equal(vo, g["b%d_orbits" % k])
-        vv, vvo = pv.culling(sb, float(zoom), vc, g["b_coi"], sx)
+        vv, vvo = pv.culling(sb, float(zoom), vc)
         assert np.array_equal(vv, g["b%d_vessels" % k])
         assert np.array_equal(vvo, g["b%d_vorbits" % k])
 

@@ -1,16 +1,16 @@
 """Drop-in for the hot path of volatilespace/physics/phys_body.py on a B200.
 
-`Physics.load / initial / move / curve / curve_move` keep the reference's names,
-argument meaning and return shapes (phys_body.py:177-198, 221-346, 405-411); the
-Kepler solve, position compose and curve generation run in libvsb200.so.  The
-body-data part of `initial()` (radius, thermal, colour, classification --
-phys_body.py:227-282) is UI data and stays with the caller.
+`Physics.load / initial / move / curve / curve_move / culling` keep the reference's names,
+argument meaning and return shapes (phys_body.py:177-346, 405-411); the Kepler solve, position
+compose, curve generation, culling and the body-data pass of `initial()` (thermal, colour,
+classification -- phys_body.py:227-282) run in libvsb200.so.
 """
 import numpy as np
 
 from . import _lib
 from ._lib import KIND_BODY, K_EA, K_MA, K_POS
 from .device import Device, default_device
+from .phys_editor import STELLAR_CLASSES, body_radius, thermal_consts
 from .synth import calc_orb
 
 
@@ -23,6 +23,8 @@ class Physics:
         self.curve_points = int(curve_points)
         self.t = np.linspace(-np.pi, np.pi, self.curve_points)   # phys_body.py:165
         self.gc, self.coi_coef = 1.0, 0.7
+        self.rad_mult, self.mass_thermal_mult, self.min_mass = 179.0, 2e26, 200
+        self.screen_x, self.screen_y = 1366, 768       # pygame surface size in the reference
         self.n_bodies = 0
 
     def reload_settings(self, curve_points=None):
@@ -35,11 +37,22 @@ class Physics:
     def load_conf(self, conf):
         self.gc = conf["gc"]
         self.coi_coef = conf["coi_coef"]
+        self.rad_mult = conf.get("rad_mult", self.rad_mult)
+        self.mass_thermal_mult = conf.get("mass_thermal_mult", self.mass_thermal_mult)
+        self.min_mass = conf.get("min_planet_mass", self.min_mass)
 
     # phys_body.py:177-198
     def load(self, conf, body_data, body_orb_data):
         self.load_conf(conf)
         self.mass = np.array(body_data["mass"], dtype=np.float64)
+        n = len(self.mass)
+        self.names = body_data.get("name", np.array(["body%d" % i for i in range(n)]))
+        self.den = np.array(body_data.get("den", np.full(n, 1000.0)), dtype=np.float64)
+        self.base_color = np.array(body_data.get("color", np.zeros((n, 3), int)),
+                                   dtype=int).reshape(n, 3)
+        self.atm_pres0 = np.array(body_data.get("atm_pres0", np.zeros(n)), dtype=np.float64)
+        self.atm_scale_h = np.array(body_data.get("atm_scale_h", np.zeros(n)), dtype=np.float64)
+        self.atm_den0 = np.array(body_data.get("atm_den0", np.zeros(n)), dtype=np.float64)
         self.a = np.array(body_orb_data["a"], dtype=np.float64)
         self.ecc = np.array(body_orb_data["ecc"], dtype=np.float64)
         self.pea = np.array(body_orb_data["pe_arg"], dtype=np.float64)
@@ -56,8 +69,24 @@ class Physics:
         self.dev.kepler_set(KIND_BODY, K_POS, self.pos)
         self.dev.kepler_set_order(np.argsort(self.coi)[-1::-1])    # phys_body.py:328
 
-    # phys_body.py:221-312 (orbit part)
+    # phys_body.py:221-312 -> (body_data, body_orb, pos, ma, ea, curves_mov)
     def initial(self, warp):
+        # body data, :227-282: radius on the host (np.cbrt), the rest in one device pass.  The
+        # game-mode formulas equal the editor's with gc = 1 in surf_grav and atm_h starting at 0.
+        n = self.n_bodies
+        self.radius = body_radius(self.mass, self.den, self.rad_mult)
+        th = self.dev.host_body_thermal(
+            thermal_consts(1.0, self.rad_mult, self.mass_thermal_mult, self.min_mass), self.mass,
+            self.den, self.radius, self.atm_pres0, self.atm_scale_h, self.atm_den0, np.zeros(n),
+            self.base_color)
+        self.atm_h, self.types = th["atm_h"], th["types"]
+        body_data = {"name": self.names, "type": self.types, "mass": self.mass, "den": self.den,
+                     "temp": th["temp"], "lum": th["luminosity"],
+                     "class": STELLAR_CLASSES[th["stellar_class"]], "color_b": self.base_color,
+                     "color": th["color"], "radius": self.radius, "rad_sc": th["rad_sc"],
+                     "surf_grav": th["surf_grav"], "atm_pres0": self.atm_pres0,
+                     "atm_scale_h": self.atm_scale_h, "atm_den0": self.atm_den0,
+                     "atm_h": self.atm_h}
         orb = calc_orb("body", self.ref, self.mass, self.mass, self.gc, self.coi_coef, self.a,
                        self.ecc)
         self.b, self.f, self.coi, self.pe_d, self.ap_d, self.period, self.n, self.u = (
@@ -68,7 +97,7 @@ class Physics:
         self._upload()
         self.move(warp)
         curves_mov = self.curve_move()
-        return body_orb, self.pos, self.ma, self.ea, curves_mov
+        return body_data, body_orb, self.pos, self.ma, self.ea, curves_mov
 
     # phys_body.py:323-346 -> (pos (N,2), ma (N,), ea (N,)), refreshed in place
     def move(self, warp):
@@ -94,18 +123,16 @@ class Physics:
         got = self.dev.kepler_curves_gather(KIND_BODY, visible, self.curve_points)
         return {int(i): got[k] for k, i in enumerate(visible)}
 
-    # phys_body.py:201-218; radius / atm_h are the caller's body data (UI side)
-    def culling(self, sim_screen, zoom, radius=None, atm_h=None, screen_x=1366):
+    # phys_body.py:201-218
+    def culling(self, sim_screen, zoom):
         n = self.n_bodies
-        radius = np.zeros(n) if radius is None else np.asarray(radius, dtype=np.float64)
-        atm_h = np.zeros(n) if atm_h is None else np.asarray(atm_h, dtype=np.float64)
         dev = self.dev
-        visible_bodies = dev.kepler_culling(KIND_BODY, n, (radius + atm_h) * zoom, sim_screen, zoom)
+        visible_bodies = dev.kepler_culling(KIND_BODY, n, (self.radius + self.atm_h) * zoom,
+                                            sim_screen, zoom)
         coi_idx = dev.kepler_culling(KIND_BODY, n, self.coi, sim_screen, zoom)
         visible_coi = np.concatenate(([0], coi_idx))
         coi_truth = np.zeros(n, dtype=np.uint8)
         coi_truth[coi_idx] = 1
-        self.visible_coi_truth = coi_truth
         visible_orbits = dev.kepler_visible_orbits(KIND_BODY, n, coi_truth, self.coi, self.a, zoom,
-                                                   screen_x)
+                                                   self.screen_x)
         return visible_bodies, visible_coi, visible_orbits

@@ -126,6 +126,16 @@ class _DeviceBodies:
             setattr(self, name, np.delete(getattr(self, name), i, axis=0))
 
 
+# host-only per-body data of phys_editor.Physics (:114-131) that the editor UI reads; they follow
+# the structural operations exactly like there (set_root :293-313 swaps only _AUX_SWAPPED)
+_AUX = ("temp", "luminosity", "stellar_class", "color", "base_color", "atm_h", "types", "rad_sc",
+        "surf_grav", "atm_pres0", "atm_scale_h", "atm_den0")
+_AUX_SWAPPED = ("temp", "luminosity", "stellar_class", "color", "base_color", "atm_h", "types",
+                "rad_sc")
+_AUX_DELETED = ("temp", "luminosity", "stellar_class", "color", "base_color", "atm_h", "types",
+                "rad_sc", "atm_pres0", "atm_scale_h", "atm_den0")
+
+
 class Physics(_DeviceBodies):
     """Editor physics class (MODE_REF: the reference's parent/COI model)."""
 
@@ -142,7 +152,24 @@ class Physics(_DeviceBodies):
         self._order_on_device = False
         self._rad_dirty = True
         self._alloc_host(0)
+        self._alloc_aux(0)
         self.reload_settings(curve_points)
+
+    def _alloc_aux(self, n, body_data=None):
+        """UI-side arrays, phys_editor.py:169-201."""
+        bd = body_data or {}
+        self.temp = np.zeros(n)
+        self.luminosity = np.zeros(n)
+        self.stellar_class = np.array(["Unknown"] * n)
+        self.color = np.zeros((n, 3), int)
+        self.base_color = np.array(bd.get("color", np.zeros((n, 3), int)), dtype=int).reshape(n, 3)
+        self.atm_pres0 = np.array(bd.get("atm_pres0", np.zeros(n)), dtype=np.float64)
+        self.atm_scale_h = np.array(bd.get("atm_scale_h", np.zeros(n)), dtype=np.float64)
+        self.atm_den0 = np.array(bd.get("atm_den0", np.zeros(n)), dtype=np.float64)
+        self.atm_h = np.zeros(n)
+        self.types = np.zeros(n)
+        self.rad_sc = np.zeros(n)
+        self.surf_grav = np.zeros(n)
 
     # phys_editor.py:152-157
     def reload_settings(self, curve_points=None):
@@ -166,6 +193,7 @@ class Physics(_DeviceBodies):
         n = len(mass)
         self.names = body_data.get("name", np.array(["body%d" % i for i in range(n)]))
         self._alloc_host(n)
+        self._alloc_aux(n, body_data)
         self.mass[:] = mass
         self.den[:] = body_data["den"]
         self.rad[:] = body_radius(self.mass, self.den, self.rad_mult)
@@ -199,15 +227,35 @@ class Physics(_DeviceBodies):
         self._order_on_device = True
         self._touched("parents", "rel_vel", "vel", "pos")
 
-    # phys_editor.py:577-599 (radius; the thermal/atmosphere part is UI data, out of scope)
+    # phys_editor.py:577-599.  Everything here depends on mass, den and the atmosphere parameters
+    # only, so it is recomputed when one of those changed (the reference recomputes it every tick)
     def body(self):
-        if not self._rad_dirty:          # rad depends on mass and den only
+        if not self._rad_dirty:
             return
         rad = body_radius(self.mass, self.den, self.rad_mult)
         if not np.array_equal(rad, self.rad):
             self.rad[:] = rad
             self._push("rad")
+        if len(self.mass):
+            out = self.body_data(self.atm_pres0, self.atm_scale_h, self.atm_den0, self.atm_h,
+                                 self.base_color)
+            self.surf_grav, self.atm_h = out["surf_grav"], out["atm_h"]
+            self.luminosity, self.temp, self.rad_sc = out["luminosity"], out["temp"], out["rad_sc"]
+            self._color, self._types, self._stellar = (out["color"], out["types"],
+                                                       out["stellar_class"])
         self._rad_dirty = False
+
+    # phys_editor.py:602-651
+    def temp_color(self):
+        self.body()
+        self.color = self._color
+        return self.color
+
+    # phys_editor.py:654-670
+    def classify(self):
+        self.body()
+        self.types = self._types
+        self.stellar_class = self._stellar
 
     # phys_editor.py:583-599 + temp_color :602-651 + classify :654-670: the
     # per-frame body data the editor UI shows, one device pass over host arrays
@@ -295,6 +343,13 @@ class Physics(_DeviceBodies):
         self._mass_changed()
         if len(self.names) > body:
             self.names[0], self.names[body] = self.names[body], self.names[0]
+        for name in _AUX_SWAPPED:
+            arr = getattr(self, name)
+            if len(arr) > body:
+                if arr.ndim == 1:
+                    arr[0], arr[body] = arr[body], arr[0]
+                else:
+                    arr[[0, body]] = arr[[body, 0]]
         self._touched("pos", "vel", "rel_vel", "parents")
         self.simplified_orbit_coi()
         self.find_parents()
@@ -309,6 +364,10 @@ class Physics(_DeviceBodies):
             self._mass_changed()
             if len(self.names) > delete:
                 self.names = np.delete(self.names, delete)
+            for name in _AUX_DELETED:
+                arr = getattr(self, name)
+                if len(arr) > delete:
+                    setattr(self, name, np.delete(arr, delete, axis=0))
             self.simplified_orbit_coi()
             self.find_parents()
             if self.largest == delete:
@@ -332,6 +391,17 @@ class Physics(_DeviceBodies):
         for name, arr in old.items():
             getattr(self, name)[:n - 1] = arr
         self.names = np.append(self.names, data.get("name", "body%d" % (n - 1)))
+        self.temp = np.append(self.temp, 0)
+        self.luminosity = np.append(self.luminosity, 0)
+        self.stellar_class = np.append(self.stellar_class, "Unknown")
+        self.color = np.vstack((self.color, (0, 0, 0)))
+        self.base_color = np.vstack((self.base_color, data.get("color", (0, 0, 0))))
+        self.atm_h = np.append(self.atm_h, 0)
+        self.types = np.append(self.types, 0)
+        self.rad_sc = np.append(self.rad_sc, 0)
+        self.atm_pres0 = np.append(self.atm_pres0, data.get("atm_pres0", 0.0))
+        self.atm_scale_h = np.append(self.atm_scale_h, data.get("atm_scale_h", 0.0))
+        self.atm_den0 = np.append(self.atm_den0, data.get("atm_den0", 0.0))
         self.mass[-1] = data["mass"]
         self.den[-1] = data["density"]
         self.rad[:] = body_radius(self.mass, self.den, self.rad_mult)
@@ -366,14 +436,37 @@ class Physics(_DeviceBodies):
                       np.asarray(velocity, dtype=np.float64) - self._row("vel", parent))
         self.simplified_orbit_coi()
 
-    # phys_editor.py:819-841
+    # phys_editor.py:819-836
     def get_bodies(self):
         self.pull()
-        return self.names, self.mass, self.den, self.pos, self.vel, self.rad
+        return (self.names, self.types, self.mass, self.den, self.temp, self.luminosity,
+                self.stellar_class, self.pos, self.vel, self.color, self.rad, self.rad_sc,
+                self.surf_grav)
+
+    def get_atmosphere(self):
+        return self.atm_pres0, self.atm_scale_h, self.atm_den0, self.atm_h
+
+    def get_base_color(self):
+        return self.base_color
 
     def get_body_orbits(self):
         self.pull()
         return self.semi_major, self.semi_minor, self.coi, self.parents
+
+    # phys_editor.py:839-841, 883-897
+    def set_body_name(self, body, name):
+        self.names[body] = name
+
+    def set_body_base_color(self, body, color):
+        self.base_color[body] = color
+        self._rad_dirty = True
+
+    def set_body_atmos(self, body, atm_pres0, atm_scale_h, atm_den0):
+        pick = lambda v: v[body] if isinstance(v, (list, np.ndarray)) else v
+        self.atm_pres0[body] = pick(atm_pres0)
+        self.atm_scale_h[body] = pick(atm_scale_h)
+        self.atm_den0[body] = pick(atm_den0)
+        self._rad_dirty = True
 
     def frame_calls(self, warp=1):
         """One editor frame as the individual method calls of editor.py:1503-1523."""
