@@ -49,8 +49,17 @@ def main():
     sim2 = ShardedAllPairs(dev, s["mass"], s["pos"], s["vel"], s["gc"], rank, world)
     for _ in range(ticks):
         sim2.tick_host(s["mass"], hp, hv)
-    ok_host = np.array_equal(hp, pos_single) and np.array_equal(
-        hv[sim2.row0:sim2.row1], vel_single[sim2.row0:sim2.row1])
+    ok_host = np.array_equal(hp[sim2.row0:sim2.row1], pos_single[sim2.row0:sim2.row1]) and \
+        np.array_equal(hv[sim2.row0:sim2.row1], vel_single[sim2.row0:sim2.row1])
+    # the symmetric driver's host path: own slices only
+    from volatilespace_b200.dist import ShardedAllPairsSym
+    hp2, hv2 = s["pos"].copy(), s["vel"].copy()
+    sym_h = ShardedAllPairsSym(dev, s["mass"], s["pos"], s["vel"], s["gc"], rank, world)
+    for _ in range(ticks):
+        sym_h.tick_host(s["mass"], hp2, hv2)
+    ok_host = ok_host and np.allclose(hp2[sym_h.row0:sym_h.row1],
+                                      pos_single[sym_h.row0:sym_h.row1], rtol=1e-11, atol=1e-9)
+    dev.set_gravity_mode("rows")
     # symmetric kernel over the ranks (all-reduce of partial accelerations): tolerance parity
     # with the row kernel, and identical replicas on every rank
     from volatilespace_b200.dist import ShardedAllPairsSym

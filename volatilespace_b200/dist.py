@@ -69,6 +69,7 @@ class ShardedAllPairs:
             npad = (max(self.n, 1) + 2047) // 2048 * 2048     # VSB_PAD of the library
             assert world * self.rpr <= npad
             self._pos_t = device_tensor(dev, F_POS, npad)
+            self._mass_t = device_tensor(dev, F_MASS, npad, width=1)
             self._stream = torch.cuda.ExternalStream(dev.stream_handle(),
                                                      device="cuda:%d" % dev.index)
 
@@ -81,27 +82,29 @@ class ShardedAllPairs:
                 gather_rows(self._pos_t, self.rpr, self.rank, self.world, self.group)
 
     def tick_host(self, mass, pos, vel):
-        """End-to-end tick over HOST buffers (the drop-in path): upload the replicas and
-        this rank's velocities, tick, download the gathered positions and own velocities.
-        pos (n,2) / vel (n,2) are updated in place (vel: own rows)."""
-        d = self.dev
-        d.set(F_MASS, mass)
-        d.set(F_POS, pos)
-        if self.row1 > self.row0:
-            d.set(F_VEL, vel[self.row0:self.row1], first=self.row0)
+        """End-to-end tick over HOST buffers: each rank uploads ITS rows of mass / pos / vel,
+        the replicas of mass and pos are completed by NCCL all-gathers over NVLink, and the rank
+        downloads its own rows of pos / vel (updated in place)."""
+        d, r0, r1 = self.dev, self.row0, self.row1
+        if r1 > r0:
+            d.set(F_MASS, mass[r0:r1], first=r0)
+            d.set(F_POS, pos[r0:r1], first=r0)
+            d.set(F_VEL, vel[r0:r1], first=r0)
+        if self.world > 1:
+            import torch
+            with torch.cuda.stream(self._stream):
+                gather_rows(self._mass_t, self.rpr, self.rank, self.world, self.group)
+                gather_rows(self._pos_t, self.rpr, self.rank, self.world, self.group)
         self.tick()
         if self.world > 1:
             self._stream.synchronize()
-        d.get(F_POS, out=pos)
-        if self.row1 > self.row0:
-            d.get(F_VEL, first=self.row0, count=self.row1 - self.row0,
-                  out=vel[self.row0:self.row1])
+        if r1 > r0:
+            d.get(F_POS, first=r0, count=r1 - r0, out=pos[r0:r1])
+            d.get(F_VEL, first=r0, count=r1 - r0, out=vel[r0:r1])
 
     def host_bytes_per_tick(self):
         rows = self.row1 - self.row0
-        h2d = self.n * (8 + 16) + rows * 16
-        d2h = self.n * 16 + rows * 16
-        return h2d, d2h
+        return rows * (8 + 16 + 16), rows * 32
 
     def positions(self):
         self.dev.sync()
@@ -122,14 +125,20 @@ class ShardedAllPairsSym:
     def __init__(self, dev, mass, pos, vel, gc, rank=0, world=1, group=None):
         self.dev, self.gc, self.rank, self.world, self.group = dev, float(gc), rank, world, group
         self.n = len(mass)
-        self.row0, self.row1 = 0, self.n
+        self.rpr, self.ranges = partition(self.n, world)
+        self.row0, self.row1 = self.ranges[rank]       # the slice of HOST data this rank owns
         dev.upload_bodies(mass, pos, vel)
         dev.set_gravity_mode("sym")
         self._stream = None
         if world > 1:
             import torch
             from ._lib import F_ACC
+            npad = (max(self.n, 1) + 2047) // 2048 * 2048     # VSB_PAD of the library
+            assert world * self.rpr <= npad
             self._acc_t = device_tensor(dev, F_ACC, self.n)
+            self._pos_t = device_tensor(dev, F_POS, npad)
+            self._vel_t = device_tensor(dev, F_VEL, npad)
+            self._mass_t = device_tensor(dev, F_MASS, npad, width=1)
             self._stream = torch.cuda.ExternalStream(dev.stream_handle(),
                                                      device="cuda:%d" % dev.index)
 
@@ -145,19 +154,29 @@ class ShardedAllPairsSym:
         self.dev.allpairs_integrate_async()
 
     def tick_host(self, mass, pos, vel):
-        """End-to-end tick over host buffers; every rank holds (and returns) the full state."""
-        d = self.dev
-        d.set(F_MASS, mass)
-        d.set(F_POS, pos)
-        d.set(F_VEL, vel)
+        """End-to-end tick over host buffers.  Each rank moves only ITS slice of the host
+        arrays over PCIe (rows [row0,row1) of mass / pos / vel up, of pos / vel down); the
+        device replicas are completed by NCCL all-gathers over NVLink."""
+        d, r0, r1 = self.dev, self.row0, self.row1
+        if r1 > r0:
+            d.set(F_MASS, mass[r0:r1], first=r0)
+            d.set(F_POS, pos[r0:r1], first=r0)
+            d.set(F_VEL, vel[r0:r1], first=r0)
+        if self.world > 1:
+            import torch
+            with torch.cuda.stream(self._stream):
+                for t in (self._mass_t, self._pos_t, self._vel_t):
+                    gather_rows(t, self.rpr, self.rank, self.world, self.group)
         self.tick()
         if self.world > 1:
             self._stream.synchronize()
-        d.get(F_POS, out=pos)
-        d.get(F_VEL, out=vel)
+        if r1 > r0:
+            d.get(F_POS, first=r0, count=r1 - r0, out=pos[r0:r1])
+            d.get(F_VEL, first=r0, count=r1 - r0, out=vel[r0:r1])
 
     def host_bytes_per_tick(self):
-        return self.n * (8 + 16 + 16), self.n * 32
+        rows = self.row1 - self.row0
+        return rows * (8 + 16 + 16), rows * 32
 
     def positions(self):
         self.dev.sync()
