@@ -329,6 +329,42 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
         dev.kepler_free(KIND_VESSEL)
     except Exception as e:   # e.g. not enough free HBM on a shared device
         out["kepler4m"] = {"error": str(e)[:200]}
+
+    # phys_vessel.Physics.points for the 160 vessels of the live-reference fixture
+    # (the reference itself: ~110 s for this call sequence, dominated by four vessels whose serial
+    # COI-entry march runs ~1e8 steps); CPU port timed on the short-march vessels only
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "vessel_points.npz"))
+        v12, b12 = g["vessel12"], g["body12"]
+        nv = len(v12)
+        res = [np.full((nv, w), np.nan) for w in (2, 2, 2, 6)]
+        args = (v12, g["v_ref"], b12, g["body_ref"])
+        dev.host_vessel_points(*args, *res, steps_limit=300)
+        t0 = time.perf_counter()
+        dev.host_vessel_points(*args, *res, steps_limit=300)
+        t_all = time.perf_counter() - t0
+        chunks, rerun, serial = dev.march_stats()
+        per = np.where(v12[:, 3] < 1, v12[:, 11], np.inf)
+        kids = [np.flatnonzero((g["body_ref"] == r) & (np.arange(len(b12)) != 0)) for r in g["v_ref"]]
+        cost = np.array([sum(max(min(5 * p / b12[k, 9], p / 2), p / 30) for k in ks) if len(ks) else 0.0
+                         for p, ks in zip(per, kids)])
+        sel = np.flatnonzero(cost < 2e5)
+        t0 = time.perf_counter()
+        dev.host_vessel_points(*args, *res, sel=sel, steps_limit=300)
+        t_sel = time.perf_counter() - t0
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as orc            # cpu_baseline leg only
+        t0 = time.perf_counter()
+        orc.vessel_points(*args, sel=sel, steps_limit=300)
+        t_cpu = time.perf_counter() - t0
+        out["vessel_points160"] = {
+            "gpu_ms_all_vessels": t_all * 1e3, "march_chunks": chunks, "march_chunks_rerun": rerun,
+            "serial_fallbacks": serial, "short_march_vessels": int(len(sel)),
+            "gpu_ms_short": t_sel * 1e3, "cpu_port_ms_short": t_cpu * 1e3, "cpu_cores": 1,
+            "note": "host arrays in and out (vsb_host_vessel_points); the C port needs ~100 s for "
+                    "all 160 vessels on one core, the reference ~110 s"}
+    except Exception as e:
+        out["vessel_points160"] = {"error": str(e)[:200]}
     return out
 
 

@@ -286,6 +286,39 @@ int vsb_host_predict_enter_coi(vsb_ctx *ctx, int64_t n, const double *vessel_dat
                                const double *body_data10, double tol, int64_t steps_limit,
                                double *out5);
 
+/* phys_vessel.Physics.points(vessel, only_enter_coi), phys_vessel.py:372-474, for the vessels
+ * listed in sel (nsel entries; NULL = all nv vessels -- the loop of initial(), :300-302), with
+ * next_point / sort_intersect_indices (orbit_intersect.py:55-79) and orbit_time_to
+ * (phys_shared.py:58-64).
+ *   vessel12 (nv,12) = a b f ecc ma ea pea n dr pe_d ap_d period ; v_ref (nv)
+ *   body12   (nb,12) = a b f ecc ma ea pea n dr coi size atm_h   ; body_ref (nb)
+ *   entered_coi / left_coi / left_coi_prev_ref: the attributes of the same names (-1 = None)
+ *   steps_limit: [game] predict_coi_limit (phys_vessel.py:181)
+ * In/out host arrays, rows of the selected vessels rewritten, all other rows untouched:
+ *   body_impact (nv,2), body_enter_atm (nv,2), coi_leave (nv,2) (read by only_enter_coi, :441),
+ *   coi_enter (nv,6) = body index, ea, b_ea, ma, b_ma, t (all NaN when nothing is entered).
+ * Every (vessel, candidate body) pair is marched by one thread block (see vsb_intersect.cu). */
+int vsb_host_vessel_points(vsb_ctx *ctx, int64_t nv, int64_t nb, const double *vessel12,
+                           const int64_t *v_ref, const double *body12, const int64_t *body_ref,
+                           int64_t nsel, const int64_t *sel, int64_t entered_coi, int64_t left_coi,
+                           int64_t left_coi_prev_ref, int only_enter_coi, int64_t steps_limit,
+                           double *body_impact, double *body_enter_atm, double *coi_leave,
+                           double *coi_enter);
+/* Diagnostics of the COI-entry march used by the two calls above.  sequential != 0 selects the
+ * reference's own serial loop, one thread per pair (cross-check of the parallel march; the
+ * results must be bit-identical).  out3 = chunks marched, chunks re-run after a failed
+ * speculation, pairs that fell back to the serial loop -- of the last call. */
+int vsb_set_march_mode(vsb_ctx *ctx, int sequential);
+/* The closed form the parallel march uses for the reference's running sums (`t += dt`,
+ * `ma += dr * n * dt`, orbit_intersect.py:108-121,170): xs[i] = x_{ks[i]} of
+ * x_k = fl(x_{k-1} + c), x_0 = x0, with exactly the bits of the serial loop.  K_out = kmax, or
+ * (bounded) the trip count of `while x < bound`.  Pure host code, no device needed: it exists so
+ * that the closed form can be tested against the plain loop.  VSB_ERR_STATE when no closed form
+ * exists (more than 288 segments, or a bounded sum that stops growing below its bound). */
+int vsb_host_running_sum(double x0, double c, int64_t kmax, int bounded, double bound, int64_t nq,
+                         const int64_t *ks, double *xs, int64_t *K_out, int64_t *nseg_out);
+int vsb_march_stats(vsb_ctx *ctx, uint64_t *out3);
+
 /* --------------------------------------------- per-frame body passes
  * Physics.body (phys_editor.py:577-599, without the radius, which stays host numpy),
  * Physics.temp_color (:602-651) and Physics.classify (:654-670) in one pass over host arrays.

@@ -49,6 +49,11 @@ def snap(ph, prefix):
              "semi_major", "semi_minor", "periapsis_arg")}
 
 
+def gen_solar_inputs(ns):
+    gd, conf, bd, bod, vd, vod = ns.peripherals.load_file(ns.solar_system_ini)
+    return conf, bd, bod
+
+
 def gen_solar(ns):
     gd, conf, bd, bod, vd, vod = ns.peripherals.load_file(ns.solar_system_ini)
     out = dict(mass=bd["mass"].copy(), den=bd["den"].copy(), pos0=bod["pos"].copy(),
@@ -584,19 +589,110 @@ def gen_intersect(ns):
     save("intersect", **out)
 
 
+def gen_vessel_points(ns, conf, bd, bod):
+    """N2 bookkeeping: phys_vessel.Physics.points via load() + initial() of the live reference on
+    the Solar System with synthetic vessels (elliptic and hyperbolic, around the Sun, planets with
+    moons and moons), then single-vessel points() calls with the entered_coi / left_coi /
+    left_coi_prev_ref / only_enter_coi variants."""
+    import copy
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    from volatilespace.physics import convert
+    sys.path.remove(rh.REFERENCE_ROOT)
+    P = 8
+    korb = convert.to_kepler(bd["mass"], copy.deepcopy(bod), conf["gc"], conf["coi_coef"])
+    pb = ns.phys_body.Physics()
+    rh.set_curve_points(ns, pb, P)
+    pb.load(conf, copy.deepcopy(bd), copy.deepcopy(korb))
+    body_data, body_orb, bpos, bma, bea, _ = pb.initial(1)
+    nb = len(bd["mass"])
+    rng = np.random.default_rng(20240622)
+    nv = 160
+    coi = np.array(body_orb["coi"], dtype=float)
+    size = np.array(body_data["radius"], dtype=float)
+    bref = np.array(body_orb["ref"])
+    ba = np.array(body_orb["a"], dtype=float)
+    parents = np.unique(bref[1:])                  # bodies that have satellites
+    v_ref = np.where(rng.uniform(0, 1, nv) < 0.7, rng.choice(parents, nv), rng.integers(0, nb, nv))
+    v_ref[:40] = 0
+    hypm = rng.uniform(0, 1, nv) < 0.35
+    v_ecc = np.where(hypm, rng.uniform(1.05, 2.5, nv), rng.uniform(0.0, 0.9, nv))
+    v_ecc[40:44] = [0.0, 0.3, 1.6, 0.95]
+    hypm = v_ecc >= 1
+    # scale of each orbit: between the parent's surface and its COI (the Sun: out to the planets)
+    span = np.where(v_ref == 0, ba.max() * 1.2, coi[v_ref])
+    lo = size[v_ref] * 0.8
+    pe = lo + (span * 0.9 - lo) * rng.uniform(0, 1, nv) ** 2
+    v_a = np.where(hypm, -pe / (v_ecc - 1), pe / (1 - np.minimum(v_ecc, 0.9999)))
+    v_pea = rng.uniform(0, 2 * np.pi, nv)
+    v_ma = np.where(hypm, rng.uniform(-1.5, 0.5, nv), rng.uniform(0, 2 * np.pi, nv))
+    v_dr = rng.choice([-1.0, 1.0], nv)
+    vessel_data = {"name": np.array(["v%d" % i for i in range(nv)]), "mass": np.ones(nv),
+                   "rot_angle": np.zeros(nv), "rot_acc": np.zeros(nv)}
+    vessel_orb = {"a": v_a.copy(), "ecc": v_ecc.copy(), "pe_arg": v_pea.copy(), "ma": v_ma.copy(),
+                  "ref": v_ref.copy(), "dir": v_dr.copy()}
+    pv = ns.phys_vessel.Physics()
+    rh.set_curve_points(ns, pv, P)
+    pv.load(conf, body_data, body_orb, vessel_data, vessel_orb)
+    pv.initial(1, bpos, bma, bea)
+
+    def vessel12():
+        return np.stack([pv.a, pv.b, pv.f, pv.ecc, pv.ma, pv.ea, pv.pea, pv.n, pv.dr, pv.pe_d,
+                         pv.ap_d, pv.period], axis=1).astype(np.float64)
+
+    body12 = np.stack([pv.body_a, pv.body_b, pv.body_f, pv.body_ecc, pv.body_ma, pv.body_ea,
+                       pv.body_pea, pv.body_n, pv.body_dr, pv.body_coi, pv.body_size,
+                       pv.body_atm], axis=1).astype(np.float64)
+    out = dict(vessel12=vessel12(), v_ref=np.array(pv.ref, dtype=np.int64), body12=body12,
+               body_ref=np.array(pv.body_ref, dtype=np.int64),
+               steps_limit=pv.predict_coi_limit,
+               body_impact=pv.body_impact.copy(), body_enter_atm=pv.body_enter_atm.copy(),
+               coi_leave=pv.coi_leave.copy(), coi_enter=pv.coi_enter.copy())
+    # single-vessel variants (attributes the reference's cross_coi sets before calling points)
+    var = []
+    cand = [v for v in range(nv) if not np.isnan(pv.coi_enter[v, 0])][:6] + list(range(44, 52))
+    for k, v in enumerate(cand):
+        mode = k % 4
+        pv.entered_coi = v if mode == 0 else None
+        pv.left_coi = v if mode in (1, 2) else None
+        prev = None
+        if mode == 2:
+            sib = np.where(np.array(pv.body_ref) == pv.ref[v])[0]
+            sib = sib[sib != 0]
+            prev = int(sib[0]) if len(sib) else None
+        pv.left_coi_prev_ref = prev
+        before = pv.coi_leave.copy()
+        pv.points(v, only_enter_coi=(mode == 3))
+        var.append([v, -1 if pv.entered_coi is None else pv.entered_coi,
+                    -1 if pv.left_coi is None else pv.left_coi, -1 if prev is None else prev,
+                    int(mode == 3)])
+        out["var%d_coi_leave_in" % k] = before
+        out["var%d_rows" % k] = np.concatenate([pv.body_impact[v], pv.body_enter_atm[v],
+                                                pv.coi_leave[v], pv.coi_enter[v]])
+    pv.entered_coi = pv.left_coi = pv.left_coi_prev_ref = None
+    out["variants"] = np.array(var, dtype=np.int64)
+    save("vessel_points", **out)
+    print("  vessel_points: impact %d  atm %d  leave %d  enter %d of %d vessels" % (
+        np.sum(~np.isnan(pv.body_impact[:, 0])), np.sum(~np.isnan(pv.body_enter_atm[:, 0])),
+        np.sum(~np.isnan(pv.coi_leave[:, 0])), np.sum(~np.isnan(pv.coi_enter[:, 0])), nv))
+
+
 def main():
+    """All fixtures, or only the ones named on the command line (e.g. `vessel_points`)."""
     ns = rh.load()
-    conf, bd, bod = gen_solar(ns)
-    gen_editor_clouds(ns)
-    gen_pair_kernels(ns)
-    gen_allpairs(ns)
-    gen_kepler_solvers(ns)
-    gen_game(ns, conf, bd, bod)
-    gen_culling(ns, conf, bd, bod)
-    gen_body_data(ns, conf, bd, bod)
-    gen_editor_edits(ns)
-    gen_convert(ns, conf, bd, bod)
-    gen_intersect(ns)
+    only = set(sys.argv[1:])
+    want = lambda name: not only or name in only
+    conf, bd, bod = gen_solar(ns) if want("solar") else gen_solar_inputs(ns)
+    if want("editor_clouds"): gen_editor_clouds(ns)
+    if want("pair_kernels"): gen_pair_kernels(ns)
+    if want("allpairs"): gen_allpairs(ns)
+    if want("kepler_solvers"): gen_kepler_solvers(ns)
+    if want("game"): gen_game(ns, conf, bd, bod)
+    if want("culling"): gen_culling(ns, conf, bd, bod)
+    if want("body_data"): gen_body_data(ns, conf, bd, bod)
+    if want("editor_edits"): gen_editor_edits(ns)
+    if want("convert"): gen_convert(ns, conf, bd, bod)
+    if want("intersect"): gen_intersect(ns)
+    if want("vessel_points"): gen_vessel_points(ns, conf, bd, bod)
 
 
 if __name__ == "__main__":

@@ -70,6 +70,8 @@ def lib():
         "vso_solve_quartic": (None, [f64, f64, f64, f64, f64, _f64p]),
         "vso_ell_hyp_intersect_circle": (C.c_int, [f64, f64, f64, f64, f64, f64, _f64p]),
         "vso_predict_enter_coi": (None, [_f64p, _f64p, f64, C.c_int, _f64p]),
+        "vso_vessel_points": (None, [i64, _i64p, i64, _f64p, _i64p, _f64p, _i64p, i64, i64, i64,
+                                     C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p]),
         "vso_editor_curve": (None, [i64, i64, _f64p, _f64p, _f64p, _f64p, _f64p, _i64p,
                                     _f64p, _f64p, _f64p, _f64p]),
     }
@@ -292,6 +294,24 @@ def predict_enter_coi(vessel_data, body_data, tol, steps_limit):
     out = np.zeros(5)
     lib().vso_predict_enter_coi(_f(vessel_data), _f(body_data), float(tol), int(steps_limit), out)
     return tuple(out)
+
+
+def vessel_points(vessel12, v_ref, body12, body_ref, sel=None, entered_coi=None, left_coi=None,
+                  left_coi_prev_ref=None, only_enter_coi=False, steps_limit=300, coi_leave=None):
+    """phys_vessel.Physics.points (phys_vessel.py:372-474) for the vessels in `sel` (all when
+    None) -> body_impact (nv,2), body_enter_atm (nv,2), coi_leave (nv,2), coi_enter (nv,6);
+    rows of vessels outside `sel` are NaN (coi_leave: the array passed in)."""
+    vessel12, body12 = _f(vessel12), _f(body12)
+    nv = len(vessel12)
+    sel = np.arange(nv, dtype=np.int64) if sel is None else _i(sel)
+    none = lambda x: -1 if x is None else int(x)
+    bi, ba = np.full((nv, 2), np.nan), np.full((nv, 2), np.nan)
+    cl = np.full((nv, 2), np.nan) if coi_leave is None else _f(coi_leave).copy()
+    ce = np.full((nv, 6), np.nan)
+    lib().vso_vessel_points(len(sel), sel, len(body12), vessel12, _i(v_ref), body12, _i(body_ref),
+                            none(entered_coi), none(left_coi), none(left_coi_prev_ref),
+                            int(bool(only_enter_coi)), int(steps_limit), bi, ba, cl, ce)
+    return bi, ba, cl, ce
 
 
 def to_kepler(mass, pos, vel, gc, coi_coef):

@@ -857,3 +857,147 @@ void vso_predict_enter_coi(const double *vd, const double *bd, double tol, int s
         t += dt;
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * N2 bookkeeping: phys_vessel.Physics.points, phys_vessel.py:372-474, with next_point
+ * (orbit_intersect.py:55-65), sort_intersect_indices (:68-79) and orbit_time_to
+ * (phys_shared.py:58-64).
+ * vessel12 (nv,12) = a b f ecc ma ea pea n dr pe_d ap_d period; body12 (nb,12) = a b f ecc ma ea
+ * pea n dr coi size atm.  sel lists the vessels to process (the reference calls points(vessel)
+ * one vessel at a time); entered_coi / left_coi / left_coi_prev_ref are the reference's
+ * attributes of the same names (-1 = None).  coi_leave is in/out (only_enter_coi reads the
+ * stored value, :441). */
+static void next_point(double ea_vessel, const double *pts, int cnt, double dir, double *out2)
+{
+    out2[0] = out2[1] = NAN;
+    if (cnt == 0) return;                       /* the reference's [nan] */
+    for (int k = 0; k < cnt; ++k) if (isnan(pts[k])) return;
+    double ang[4];
+    int idx[4];
+    for (int k = 0; k < cnt; ++k) {
+        double a = fabs(ea_vessel - pts[k]);
+        if (ea_vessel > pts[k]) a = 2 * VSO_PI - a;
+        if (dir < 0) a = VSO_PI * 2 - a;
+        ang[k] = a;
+        idx[k] = k;
+    }
+    for (int i = 1; i < cnt; ++i) {             /* stable insertion argsort */
+        int t = idx[i], j = i - 1;
+        while (j >= 0 && ang[idx[j]] > ang[t]) { idx[j + 1] = idx[j]; --j; }
+        idx[j + 1] = t;
+    }
+    out2[0] = pts[idx[0]];
+    out2[1] = pts[idx[cnt - 1]];
+}
+
+static double orbit_time_to(double src, double dst, double ecc, double dr, double n)
+{
+    if (ecc >= 1) {
+        double v = -dr * (dst - src) / n;
+        return (0.0 > v) ? 0.0 : v;             /* python max(v, 0.0): NaN stays NaN */
+    }
+    if (dr < 0) return py_mod(src - dst, 2 * VSO_PI) / n;
+    return py_mod(dst - src, 2 * VSO_PI) / n;
+}
+
+static void advance_ea(double ecc, double ma, double ea, double n, double dr, double *next_ea)
+{ /* :411-418 / :432-439 */
+    if (ecc < 1) *next_ea = vso_solve_kepler_ell(ecc, ma + n * dr, 1e-10);
+    else *next_ea = vso_newton_root_kepler_hyp(ecc, ma + n * dr * -1, ea);
+}
+
+void vso_vessel_points(int64_t nsel, const int64_t *sel, int64_t nb, const double *vessel12,
+                       const int64_t *v_ref, const double *body12, const int64_t *body_ref,
+                       int64_t entered_coi, int64_t left_coi, int64_t left_coi_prev_ref,
+                       int only_enter_coi, int steps_limit, double *body_impact,
+                       double *body_enter_atm, double *coi_leave, double *coi_enter)
+{
+    for (int64_t s = 0; s < nsel; ++s) {
+        const int64_t v = sel[s];
+        const double *V = vessel12 + 12 * v;
+        const double a = V[0], b = V[1], f = V[2], ecc = V[3], ma = V[4], pea = V[6], n = V[7],
+                     dr = V[8], pe_d = V[9], ap_d = V[10];
+        double ea = V[5];
+        const int ell = ecc < 1;
+        const int64_t ref = v_ref[v];
+        const double *R = body12 + 12 * ref;
+        const double xc = f, yc = 0;
+        double pts[4];
+        int cnt;
+        if (!only_enter_coi) {
+            cnt = (ell && pe_d > R[10]) ? 0 : vso_ell_hyp_intersect_circle(a, b, ecc, xc, yc, R[10], pts);
+            next_point(ea, pts, cnt, dr, body_impact + 2 * v);
+            cnt = (ell && pe_d > R[10] + R[11]) ? 0
+                      : vso_ell_hyp_intersect_circle(a, b, ecc, xc, yc, R[10] + R[11], pts);
+            next_point(ea, pts, cnt, dr, body_enter_atm + 2 * v);
+            if (ell && ap_d < R[9]) {
+                coi_leave[2 * v] = coi_leave[2 * v + 1] = NAN;
+            } else {
+                cnt = vso_ell_hyp_intersect_circle(a, b, ecc, xc, yc, R[9], pts);
+                double e2 = ea;
+                if (entered_coi == v) advance_ea(ecc, ma, ea, n, dr, &e2);
+                next_point(e2, pts, cnt, dr, coi_leave + 2 * v);
+            }
+        }
+        /* enter_coi */
+        if (left_coi == v) advance_ea(ecc, ma, ea, n, dr, &ea);
+        double best_ang = 0;
+        int64_t best = -1, rows = 0;
+        double best_row[5];
+        for (int64_t body = 0; body < nb; ++body) {
+            if (body_ref[body] != ref || body == 0 || body == left_coi_prev_ref) continue;
+            const double *B = body12 + 12 * body;
+            double b_ma = B[4];
+            if (left_coi == v) {
+                if (ell) b_ma += B[7] * B[8];
+                else b_ma += +B[7] * B[8] * -1;
+            }
+            double period;
+            if (ecc < 1) {
+                period = V[11];
+            } else {
+                double ea_leave;
+                if (ref == 0) {
+                    double lp[2];
+                    cnt = vso_ell_hyp_intersect_circle(a, b, ecc, xc, yc, B[0] + B[9], pts);
+                    next_point(ea, pts, cnt, dr, lp);
+                    ea_leave = lp[0];
+                    if (isnan(ea_leave)) continue;      /* row dropped: see the index quirk below */
+                } else {
+                    ea_leave = coi_leave[2 * v];
+                }
+                double ma_leave = (ecc * sinh(ea_leave) - ea_leave) * -1;
+                period = orbit_time_to(ma, ma_leave, ecc, dr, n);
+            }
+            double vd[10] = {a, b, f, ecc, ma, ea, pea, period, n, dr};
+            double bd[10] = {B[0], B[1], B[2], B[3], b_ma, B[5], B[6], B[7], B[8], B[9]};
+            double row[5];
+            vso_predict_enter_coi(vd, bd, 1e-5, steps_limit, row);
+            if (!isnan(row[0])) {
+                double ang = fabs(ea - row[0]);
+                if (ea > row[0]) ang = 2 * VSO_PI - ang;
+                if (dr < 0) ang = VSO_PI * 2 - ang;
+                if (best < 0 || ang < best_ang) {
+                    best = rows;
+                    best_ang = ang;
+                    for (int k = 0; k < 5; ++k) best_row[k] = row[k];
+                }
+            }
+            ++rows;
+        }
+        double *ce = coi_enter + 6 * v;
+        for (int k = 0; k < 6; ++k) ce[k] = NAN;
+        if (best >= 0) {
+            /* check_bodies[first_enter]: first_enter indexes the rows that were NOT dropped by the
+             * `continue` above, but is applied to the full candidate list (:470-472). */
+            int64_t seen = 0, bid = -1;
+            for (int64_t body = 0; body < nb; ++body) {
+                if (body_ref[body] != ref || body == 0 || body == left_coi_prev_ref) continue;
+                if (seen == best) { bid = body; break; }
+                ++seen;
+            }
+            ce[0] = (double)bid;
+            for (int k = 0; k < 5; ++k) ce[1 + k] = best_row[k];
+        }
+    }
+}

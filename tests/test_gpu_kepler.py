@@ -413,3 +413,162 @@ def test_kepler_errors(dev):
         dev.kepler_move(KIND_BODY, 1.0)
     with pytest.raises(VsbError):
         dev.kepler_curves_get(KIND_VESSEL, 0, 1, 8)
+
+
+# ------------------------------------------------------------- N2 vessel orbit points
+def _points_inputs(g):
+    nv = len(g["vessel12"])
+    nan = lambda w: np.full((nv, w), np.nan)
+    return nan(2), nan(2), nan(2), nan(6)
+
+
+def _assert_points(got, want, what, nan_slack=0, frac=0.0):
+    """Orbit points against the live-reference fixture.  Two reference properties bound what can
+    be asked of a different libm (CUDA's vs glibc's sin/cos/pow/acos, <= 1-2 ulp apart):
+    * every circle of points() is centred on the focus, so its quartic is an exact biquadratic,
+      the degenerate case of the reference's Ferrari solver: the roots carry sqrt(rounding residue)
+      (~1e-8 relative) and a residue of the wrong sign turns a found intersection into [nan]
+      (quartic_solver.py:76-80).  -> values to 2e-7, `nan_slack` rows may flip found/not-found;
+    * ea / ma / t come out of a 1e-5 bisection whose exit can move by one halving."""
+    flips = np.isnan(got) != np.isnan(want)
+    assert flips.any(axis=-1).sum() <= nan_slack, what
+    ok = ~np.isnan(want) & ~np.isnan(got)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=2e-7, atol=2e-7, err_msg=what)
+    if frac:
+        assert np.isclose(got[ok], want[ok], rtol=1e-11, atol=1e-11).mean() > frac, what
+
+
+def _robust(v12):
+    """Vessels whose COI-entry march is well conditioned in the reference.  predict_enter_coi
+    never wraps the mean anomaly (the two wrap statements of orbit_intersect.move are no-ops), so
+    over one period it leaves [0, 2 pi]; for e >= 0.8 the ENRKE starter then fails at isolated
+    steps and the capped Newton loop returns garbage (|ea| up to 1e7 in the reference itself,
+    see DESIGN.md): whether such a step lands inside a COI is decided by the last ulp of sin/cos."""
+    ecc = v12[:, 3]
+    return ~((ecc >= 0.8) & (ecc < 1))
+
+
+def test_vessel_points_golden(dev):
+    """phys_vessel.Physics.points for all 160 vessels of the live-reference fixture (incl. the
+    four whose serial march takes ~20-30 s each in the reference: 110 s there, < 1 s here) and
+    the single-vessel variants (entered_coi / left_coi / left_coi_prev_ref / only_enter_coi)."""
+    g = golden("vessel_points")
+    bi, ba, cl, ce = _points_inputs(g)
+    dev.host_vessel_points(g["vessel12"], g["v_ref"], g["body12"], g["body_ref"], bi, ba, cl, ce,
+                           steps_limit=int(g["steps_limit"]))
+    chunks, rerun, serial = dev.march_stats()
+    assert serial == 0 and chunks > 0
+    assert rerun <= 0.02 * chunks            # speculation on the hyperbolic chains mostly holds
+    _assert_points(bi, g["body_impact"], "body_impact", nan_slack=1, frac=0.5)
+    _assert_points(ba, g["body_enter_atm"], "body_enter_atm", nan_slack=1, frac=0.5)
+    _assert_points(cl, g["coi_leave"], "coi_leave", nan_slack=2, frac=0.5)
+    rob = _robust(g["vessel12"]) & ~(np.isnan(cl[:, 0]) != np.isnan(g["coi_leave"][:, 0]))
+    want = g["coi_enter"]
+    assert (~np.isnan(want[rob, 0])).sum() >= 12
+    assert np.array_equal(ce[rob, 0], want[rob, 0], equal_nan=True)           # entered body
+    _assert_points(ce[rob], want[rob], "coi_enter", frac=0.85)
+    ill = ~rob & ~np.isnan(want[:, 0])
+    assert (ce[ill, 0] == want[ill, 0]).sum() >= 1       # and even there most still agree
+    opt = lambda x: None if x < 0 else int(x)
+    for k, (v, ent, lft, prev, only) in enumerate(g["variants"]):
+        bi2, ba2, _, ce2 = _points_inputs(g)
+        cl2 = g["var%d_coi_leave_in" % k].copy()
+        before = cl2.copy()
+        dev.host_vessel_points(g["vessel12"], g["v_ref"], g["body12"], g["body_ref"], bi2, ba2, cl2,
+                               ce2, sel=[int(v)], entered_coi=opt(ent), left_coi=opt(lft),
+                               left_coi_prev_ref=opt(prev), only_enter_coi=bool(only),
+                               steps_limit=int(g["steps_limit"]))
+        others = np.arange(len(cl2)) != v
+        assert np.array_equal(cl2[others], before[others], equal_nan=True)    # untouched rows
+        if not _robust(g["vessel12"])[v]:
+            continue
+        got = np.concatenate([bi2[v], ba2[v], cl2[v], ce2[v]])
+        want_v = g["var%d_rows" % k]
+        lo = 4 if only else 0
+        _assert_points(got[lo:], want_v[lo:], "variant %d" % k)
+
+
+def test_march_parallel_is_bit_identical_to_serial(dev):
+    """The CTA-parallel COI-entry march (closed-form running sums + speculated Newton chains)
+    against the one-thread-per-pair serial loop on the same device: identical bits."""
+    rng = np.random.default_rng(77)
+    g = golden("vessel_points")
+    m = 400
+    u = 1.0e4
+    hyp = rng.uniform(0, 1, m) < 0.5
+    ecc = np.where(hyp, rng.uniform(1.05, 2.5, m), rng.uniform(0, 0.8, m))
+    pe = rng.uniform(500, 4000, m)
+    a = np.where(hyp, -pe / (ecc - 1), pe / (1 - ecc))
+    f = a * ecc
+    b = np.sqrt(np.abs(f ** 2 - a ** 2))
+    n = np.sqrt(u / np.abs(a) ** 3)
+    dr = rng.choice([-1.0, 1.0], m)
+    ea = np.where(hyp, -dr * rng.uniform(0.2, 2.0, m), rng.uniform(0, 2 * np.pi, m))
+    ma = np.where(hyp, -(ecc * np.sinh(ea) - ea), ea - ecc * np.sin(ea))
+    period = np.where(hyp, rng.uniform(2e3, 6e4, m), 2 * np.pi / n)
+    period[::17] = rng.uniform(2e5, 6e5, len(period[::17]))      # long marches
+    vd = np.stack([a, b, f, ecc, ma, ea, rng.uniform(0, 2 * np.pi, m), period, n, dr], axis=1)
+    bhyp = rng.uniform(0, 1, m) < 0.15
+    becc = np.where(bhyp, rng.uniform(1.1, 1.6, m), rng.uniform(0, 0.3, m))
+    bpe = rng.uniform(800, 5000, m)
+    ba_ = np.where(bhyp, -bpe / (becc - 1), bpe / (1 - becc))
+    bf = ba_ * becc
+    bb = np.sqrt(np.abs(bf ** 2 - ba_ ** 2))
+    bn = np.sqrt(u / np.abs(ba_) ** 3)
+    bea = np.where(bhyp, rng.uniform(-1.5, 1.5, m), rng.uniform(0, 2 * np.pi, m))
+    bma = np.where(bhyp, -(becc * np.sinh(bea) - bea), bea - becc * np.sin(bea))
+    coi = rng.uniform(20, 600, m)
+    coi[::23] = 0.0
+    bd = np.stack([ba_, bb, bf, becc, bma, bea, rng.uniform(0, 2 * np.pi, m), bn,
+                   rng.choice([-1.0, 1.0], m), coi], axis=1)
+    from volatilespace_b200 import orbit_intersect as oi
+    dev.set_march_mode(True)
+    try:
+        serial = oi.predict_enter_coi(vd, bd, 1e-5, 300, device=dev)
+    finally:
+        dev.set_march_mode(False)
+    par = oi.predict_enter_coi(vd, bd, 1e-5, 300, device=dev)
+    chunks, rerun, fell_back = dev.march_stats()
+    assert fell_back == 0
+    assert np.array_equal(par.view(np.uint64), serial.view(np.uint64))
+    hit = ~np.isnan(serial[:, 0])
+    assert 20 < hit.sum() < m - 20
+    assert rerun <= 0.05 * chunks
+    # and on the golden elliptic cases
+    gi = golden("intersect")
+    dev.set_march_mode(True)
+    try:
+        s2 = oi.predict_enter_coi(gi["p_vd"], gi["p_bd"], 1e-5, 300, device=dev)
+    finally:
+        dev.set_march_mode(False)
+    p2 = oi.predict_enter_coi(gi["p_vd"], gi["p_bd"], 1e-5, 300, device=dev)
+    assert np.array_equal(p2.view(np.uint64), s2.view(np.uint64))
+
+
+def test_vessel_points_through_the_class(dev):
+    """phys_vessel.Physics.load / initial / points with the reference's dict layout."""
+    from volatilespace_b200 import phys_vessel
+    g = golden("vessel_points")
+    v12, b12 = g["vessel12"], g["body12"]
+    nb = len(b12)
+    sub = np.flatnonzero(v12[:, 3] < 1)[:60]                     # elliptic vessels, quick marches
+    body_data = {"mass": np.ones(nb), "radius": b12[:, 10], "atm_h": b12[:, 11]}
+    body_orb = {"ref": g["body_ref"], "a": b12[:, 0], "b": b12[:, 1], "f": b12[:, 2],
+                "ecc": b12[:, 3], "pea": b12[:, 6], "n": b12[:, 7], "dir": b12[:, 8],
+                "coi": b12[:, 9]}
+    vorb = {"a": v12[sub, 0], "ecc": v12[sub, 3], "pe_arg": v12[sub, 6], "ma": v12[sub, 4],
+            "ref": g["v_ref"][sub], "dir": v12[sub, 8], "ea": v12[sub, 5]}
+    pv = phys_vessel.Physics(device=dev, curve_points=8)
+    pv.load({"gc": 1.0}, body_data, body_orb, {"name": ["v%d" % i for i in sub]}, vorb)
+    # derived elements straight from the fixture (initial() would recompute them from body_mass)
+    pv.b, pv.f, pv.n, pv.pe_d, pv.ap_d, pv.period = (v12[sub, k] for k in (1, 2, 7, 9, 10, 11))
+    pv.body_ma, pv.body_ea = b12[:, 4].copy(), b12[:, 5].copy()
+    pv.predict_coi_limit = int(g["steps_limit"])
+    pv.points()
+    rob = _robust(v12[sub])
+    _assert_points(pv.coi_leave, g["coi_leave"][sub], "coi_leave", nan_slack=1)
+    _assert_points(pv.coi_enter[rob], g["coi_enter"][sub][rob], "coi_enter")
+    _assert_points(pv.body_impact, g["body_impact"][sub], "body_impact", nan_slack=1)
+    keep = pv.coi_enter.copy()
+    pv.points(vessel=3, only_enter_coi=True)
+    assert np.array_equal(pv.coi_enter, keep, equal_nan=True)

@@ -317,3 +317,43 @@ def test_intersect_kernels(oracle):
         got = oracle.predict_enter_coi(vd, bd, 1e-5, 300)
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, equal_nan=True)
     assert (~np.isnan(g["p_out"][:, 0])).sum() >= 20
+
+
+def _points_variant_args(row):
+    v, ent, lft, prev, only = (int(x) for x in row)
+    opt = lambda x: None if x < 0 else x
+    return v, dict(entered_coi=opt(ent), left_coi=opt(lft), left_coi_prev_ref=opt(prev),
+                   only_enter_coi=bool(only))
+
+
+def test_vessel_points(oracle):
+    """N2 bookkeeping: phys_vessel.Physics.points.  The serial time march makes a few vessels
+    cost tens of seconds (in the reference too), so the CPU suite checks the ones whose pairs are
+    short; the GPU suite checks all of them against the same fixture."""
+    g = golden("vessel_points")
+    v12, b12 = g["vessel12"], g["body12"]
+    # cost proxy: steps of the march, max(min(5 period / coi, period / 2), period / 30), per pair
+    per = np.where(v12[:, 3] < 1, v12[:, 11], np.inf)
+    kids = [np.flatnonzero((g["body_ref"] == r) & (np.arange(len(b12)) != 0)) for r in g["v_ref"]]
+    cost = np.array([sum(max(min(5 * p / b12[k, 9], p / 2), p / 30) for k in ks) if len(ks) else 0.0
+                     for p, ks in zip(per, kids)])
+    sel = np.flatnonzero(cost < 2e5)
+    assert len(sel) > 80
+    bi, ba, cl, ce = oracle.vessel_points(v12, g["v_ref"], b12, g["body_ref"], sel=sel,
+                                          steps_limit=int(g["steps_limit"]))
+    for got, key in ((bi, "body_impact"), (ba, "body_enter_atm"), (cl, "coi_leave"),
+                     (ce, "coi_enter")):
+        assert np.array_equal(got[sel], g[key][sel], equal_nan=True), key
+    assert (~np.isnan(g["coi_enter"][sel, 0])).sum() >= 5
+    assert (~np.isnan(g["coi_leave"][sel, 0])).sum() >= 10
+    for k, row in enumerate(g["variants"]):
+        v, kw = _points_variant_args(row)
+        if v not in sel:
+            continue
+        bi, ba, cl, ce = oracle.vessel_points(v12, g["v_ref"], b12, g["body_ref"], sel=[v],
+                                              steps_limit=int(g["steps_limit"]),
+                                              coi_leave=g["var%d_coi_leave_in" % k], **kw)
+        got = np.concatenate([bi[v], ba[v], cl[v], ce[v]])
+        want = g["var%d_rows" % k]
+        lo = 4 if kw["only_enter_coi"] else 0       # only_enter_coi leaves the first two alone
+        assert np.array_equal(got[lo:], want[lo:], equal_nan=True), (k, row)

@@ -99,6 +99,11 @@ SIGNATURES = {
     "vsb_host_solve_quartic": [_ctx, _i64, _pv, _pv],
     "vsb_host_ell_hyp_intersect_circle": [_ctx, _i64, _pv, _pv, _pv],
     "vsb_host_predict_enter_coi": [_ctx, _i64, _pv, _pv, _f64, _i64, _pv],
+    "vsb_host_vessel_points": [_ctx, _i64, _i64, _pv, _pv, _pv, _pv, _i64, _pv, _i64, _i64, _i64,
+                               C.c_int, _i64, _pv, _pv, _pv, _pv],
+    "vsb_set_march_mode": [_ctx, C.c_int],
+    "vsb_host_running_sum": [_f64, _f64, _i64, C.c_int, _f64, _i64, _pv, _pv, _pv, _pv],
+    "vsb_march_stats": [_ctx, _pv],
     "vsb_host_body_thermal": [_ctx, _i64] + [_pv] * 16,
     "vsb_host_culling": [_ctx, _i64, _pv, _pv, _pv, _f64, _pv],
     "vsb_kepler_culling": [_ctx, C.c_int, _pv, _pv, _f64, _pv, _pi],

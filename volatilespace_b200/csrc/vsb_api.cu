@@ -6,6 +6,7 @@
 #include <new>
 
 #include "vsb_common.cuh"
+#include <vector>
 
 int vsb_kepler_tables(vsb_ctx *c, vsb_kepler_state &k, const double *d_t);
 int vsb_launch_vessel_tick(vsb_ctx *c, vsb_kepler_state &k, double warp, double *d_out);
@@ -154,6 +155,7 @@ extern "C" int vsb_ctx_destroy(vsb_ctx *c)
     vsb_buf_free(c->sorted);
     vsb_buf_free(c->scratch);
     vsb_buf_free(c->host_stage);
+    vsb_buf_free(c->march_stats);
     if (c->d_key) cudaFree(c->d_key);
     if (c->h_key) cudaFreeHost(c->h_key);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1227,6 +1229,13 @@ extern "C" int vsb_host_ell_hyp_intersect_circle(vsb_ctx *c, int64_t n, const do
     return d2h(c, count_out, d_cnt, 8 * (size_t)n);
 }
 
+static int march_stats_reset(vsb_ctx *c)
+{
+    VSB_TRY(vsb_buf_reserve(c->march_stats, 32));
+    VSB_CUDA(cudaMemsetAsync(c->march_stats.p, 0, 32, c->stream));
+    return VSB_OK;
+}
+
 extern "C" int vsb_host_predict_enter_coi(vsb_ctx *c, int64_t n, const double *vessel_data10,
                                           const double *body_data10, double tol,
                                           int64_t steps_limit, double *out5)
@@ -1236,12 +1245,149 @@ extern "C" int vsb_host_predict_enter_coi(vsb_ctx *c, int64_t n, const double *v
                   (n == 0 || (vessel_data10 && body_data10 && out5)),
               VSB_ERR_ARG, "vsb_host_predict_enter_coi: bad argument");
     if (n == 0) return VSB_OK;
+    VSB_TRY(march_stats_reset(c));
     VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * 25 * (size_t)n));
     double *d_vd = (double *)c->host_stage.p, *d_bd = d_vd + 10 * n, *d_out = d_bd + 10 * n;
     VSB_CUDA(cudaMemcpyAsync(d_vd, vessel_data10, 80 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VSB_CUDA(cudaMemcpyAsync(d_bd, body_data10, 80 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    VSB_TRY(vsb_launch_predict_enter_coi(c, n, d_vd, d_bd, tol, (int)steps_limit, d_out));
+    VSB_TRY(vsb_launch_predict_enter_coi(c, n, d_vd, d_bd, nullptr, tol, (int)steps_limit, d_out,
+                                         (unsigned long long *)c->march_stats.p,
+                                         c->march_sequential));
     return d2h(c, out5, d_out, 40 * (size_t)n);
+}
+
+extern "C" int vsb_march_stats(vsb_ctx *c, uint64_t *out3)
+{
+    CTX(c);
+    VSB_CHECK(out3 != nullptr, VSB_ERR_ARG, "vsb_march_stats: null output");
+    out3[0] = out3[1] = out3[2] = 0;
+    if (!c->march_stats.p) return VSB_OK;
+    return d2h(c, out3, c->march_stats.p, 24);
+}
+
+extern "C" int vsb_host_running_sum(double x0, double c, int64_t kmax, int bounded, double bound,
+                                    int64_t nq, const int64_t *ks, double *xs, int64_t *K_out,
+                                    int64_t *nseg_out)
+{
+    VSB_CHECK(kmax >= 0 && nq >= 0 && (nq == 0 || (ks && xs)), VSB_ERR_ARG,
+              "vsb_host_running_sum: bad argument");
+    const int rc = vsb_march_walk_host(x0, c, kmax, bounded, bound, nq, ks, xs, K_out, nseg_out);
+    VSB_CHECK(rc >= 0, VSB_ERR_ARG, "vsb_host_running_sum: step index out of range");
+    VSB_CHECK(rc == 0, VSB_ERR_STATE, "vsb_host_running_sum: no closed form (code %d)", rc);
+    return VSB_OK;
+}
+
+extern "C" int vsb_set_march_mode(vsb_ctx *c, int sequential)
+{
+    CTX(c);
+    c->march_sequential = sequential ? 1 : 0;
+    return VSB_OK;
+}
+
+// phys_vessel.Physics.points for the vessels in sel (NULL = all), phys_vessel.py:372-474
+extern "C" int vsb_host_vessel_points(vsb_ctx *c, int64_t nv, int64_t nb, const double *vessel12,
+                                      const int64_t *v_ref, const double *body12,
+                                      const int64_t *body_ref, int64_t nsel, const int64_t *sel,
+                                      int64_t entered_coi, int64_t left_coi,
+                                      int64_t left_coi_prev_ref, int only_enter_coi,
+                                      int64_t steps_limit, double *body_impact,
+                                      double *body_enter_atm, double *coi_leave, double *coi_enter)
+{
+    CTX(c);
+    VSB_CHECK(nv >= 0 && nb >= 0 && nsel >= 0 && steps_limit > 0 && steps_limit < (1ll << 31),
+              VSB_ERR_ARG, "vsb_host_vessel_points: bad argument");
+    if (nv == 0) return VSB_OK;
+    VSB_CHECK(vessel12 && v_ref && body12 && body_ref && body_impact && body_enter_atm && coi_leave &&
+                  coi_enter && nb > 0,
+              VSB_ERR_ARG, "vsb_host_vessel_points: null array");
+    std::vector<int64_t> h_sel;
+    if (sel) {
+        h_sel.assign(sel, sel + nsel);
+    } else {
+        h_sel.resize((size_t)nv);
+        for (int64_t i = 0; i < nv; ++i) h_sel[(size_t)i] = i;
+    }
+    nsel = (int64_t)h_sel.size();
+    if (nsel == 0) return VSB_OK;
+    for (int64_t v : h_sel)
+        VSB_CHECK(v >= 0 && v < nv, VSB_ERR_ARG, "vsb_host_vessel_points: vessel %lld out of range",
+                  (long long)v);
+    for (int64_t i = 0; i < nv; ++i)
+        VSB_CHECK(v_ref[i] >= 0 && v_ref[i] < nb, VSB_ERR_ARG,
+                  "vsb_host_vessel_points: ref of vessel %lld out of range", (long long)i);
+    // check_bodies = np.where(body_ref == ref)[0] minus body 0 and left_coi_prev_ref (:423-424):
+    // children lists by counting sort (ascending body index inside each list)
+    std::vector<int64_t> cstart((size_t)nb + 1, 0), child((size_t)nb);
+    for (int64_t b = 0; b < nb; ++b)
+        if (body_ref[b] >= 0 && body_ref[b] < nb) ++cstart[(size_t)body_ref[b] + 1];
+    for (int64_t r = 0; r < nb; ++r) cstart[(size_t)r + 1] += cstart[(size_t)r];
+    {
+        std::vector<int64_t> fill(cstart.begin(), cstart.end() - 1);
+        for (int64_t b = 0; b < nb; ++b)
+            if (body_ref[b] >= 0 && body_ref[b] < nb) child[(size_t)fill[(size_t)body_ref[b]]++] = b;
+    }
+    std::vector<int64_t> offsets((size_t)nsel + 1, 0), pair_s, pair_body;
+    for (int64_t s = 0; s < nsel; ++s) {
+        const int64_t ref = v_ref[h_sel[(size_t)s]];
+        for (int64_t k = cstart[(size_t)ref]; k < cstart[(size_t)ref + 1]; ++k) {
+            const int64_t b = child[(size_t)k];
+            if (b == 0 || b == left_coi_prev_ref) continue;
+            pair_s.push_back(s);
+            pair_body.push_back(b);
+        }
+        offsets[(size_t)s + 1] = (int64_t)pair_s.size();
+    }
+    const int64_t np_ = (int64_t)pair_s.size();
+    // staging layout (8-byte words, every array 32-word aligned)
+    auto al = [](size_t w) { return (w + 31) / 32 * 32; };
+    const size_t NV = (size_t)nv, NB = (size_t)nb, NS = (size_t)nsel, NP = (size_t)np_;
+    size_t w = 0;
+    auto take = [&](size_t words) { size_t o = w; w += al(words); return o; };
+    const size_t o_v12 = take(12 * NV), o_vref = take(NV), o_b12 = take(12 * NB), o_sel = take(NS),
+                 o_off = take(NS + 1), o_ps = take(NP), o_pb = take(NP), o_imp = take(2 * NV),
+                 o_atm = take(2 * NV), o_lv = take(2 * NV), o_en = take(6 * NV), o_eaeff = take(NS),
+                 o_vd = take(10 * NP), o_bd = take(10 * NP), o_out = take(5 * NP),
+                 o_valid = take((NP + 7) / 8);
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * w));
+    VSB_TRY(march_stats_reset(c));
+    double *base = (double *)c->host_stage.p;
+    auto up = [&](size_t off, const void *src, size_t words) -> int {
+        if (words == 0) return VSB_OK;
+        VSB_CUDA(cudaMemcpyAsync(base + off, src, 8 * words, cudaMemcpyHostToDevice, c->stream));
+        return VSB_OK;
+    };
+    VSB_TRY(up(o_v12, vessel12, 12 * NV));
+    VSB_TRY(up(o_vref, v_ref, NV));
+    VSB_TRY(up(o_b12, body12, 12 * NB));
+    VSB_TRY(up(o_sel, h_sel.data(), NS));
+    VSB_TRY(up(o_off, offsets.data(), NS + 1));
+    VSB_TRY(up(o_ps, pair_s.data(), NP));
+    VSB_TRY(up(o_pb, pair_body.data(), NP));
+    VSB_TRY(up(o_imp, body_impact, 2 * NV));
+    VSB_TRY(up(o_atm, body_enter_atm, 2 * NV));
+    VSB_TRY(up(o_lv, coi_leave, 2 * NV));
+    VSB_TRY(up(o_en, coi_enter, 6 * NV));
+    const int64_t *d_sel = (const int64_t *)(base + o_sel), *d_vref = (const int64_t *)(base + o_vref);
+    VSB_TRY(vsb_launch_points_vessel(c, nsel, d_sel, base + o_v12, d_vref, base + o_b12, entered_coi,
+                                     left_coi, only_enter_coi, base + o_imp, base + o_atm,
+                                     base + o_lv, base + o_eaeff));
+    VSB_TRY(vsb_launch_points_pairs(c, np_, (const int64_t *)(base + o_ps),
+                                    (const int64_t *)(base + o_pb), d_sel, base + o_v12, d_vref,
+                                    base + o_b12, left_coi, base + o_lv, base + o_eaeff, base + o_vd,
+                                    base + o_bd, (unsigned char *)(base + o_valid)));
+    VSB_TRY(vsb_launch_predict_enter_coi(c, np_, base + o_vd, base + o_bd,
+                                         (const unsigned char *)(base + o_valid), 1e-5,
+                                         (int)steps_limit, base + o_out,
+                                         (unsigned long long *)c->march_stats.p,
+                                         c->march_sequential));
+    VSB_TRY(vsb_launch_points_select(c, nsel, d_sel, (const int64_t *)(base + o_off),
+                                     (const int64_t *)(base + o_pb),
+                                     (const unsigned char *)(base + o_valid), base + o_out,
+                                     base + o_eaeff, base + o_v12, base + o_en));
+    VSB_CUDA(cudaMemcpyAsync(body_impact, base + o_imp, 16 * NV, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(body_enter_atm, base + o_atm, 16 * NV, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(coi_leave, base + o_lv, 16 * NV, cudaMemcpyDeviceToHost, c->stream));
+    return d2h(c, coi_enter, base + o_en, 48 * NV);
 }
 
 // ---------------------------------------------------------------- N4: body thermal passes

@@ -96,6 +96,8 @@ struct vsb_ctx {
     vsb_buf sorted;      // sorted-source staging for find_parents
     vsb_buf scratch;     // generic
     vsb_buf host_stage;  // device staging for the stateless host-buffer calls
+    vsb_buf march_stats; // 4 x u64 counters of the parallel COI-entry march (vsb_intersect.cu)
+    int march_sequential = 0;  // VSB_ENTER_COI=seq: the one-thread-per-pair serial march
     unsigned long long *d_key = nullptr;   // collision key (device)
     unsigned long long *h_key = nullptr;   // pinned mirror
     double *h_pin = nullptr;               // pinned scratch (small)
@@ -304,7 +306,23 @@ int vsb_launch_to_newton(vsb_ctx *c, const double *d_el, const int64_t *d_ref, d
 int vsb_launch_quartic(vsb_ctx *c, int64_t n, const double *d_coef, double *d_roots);
 int vsb_launch_intersect(vsb_ctx *c, int64_t n, const double *d_in6, double *d_ea, int64_t *d_cnt);
 int vsb_launch_predict_enter_coi(vsb_ctx *c, int64_t n, const double *d_vd, const double *d_bd,
-                                 double tol, int steps_limit, double *d_out5);
+                                 const unsigned char *d_valid, double tol, int steps_limit,
+                                 double *d_out5, unsigned long long *d_stats4, int sequential);
+int vsb_march_walk_host(double x0, double c, int64_t kmax, int bounded, double bound, int64_t nq,
+                        const int64_t *ks, double *xs, int64_t *K_out, int64_t *nseg_out);
+int vsb_launch_points_vessel(vsb_ctx *c, int64_t nsel, const int64_t *d_sel, const double *d_vessel12,
+                             const int64_t *d_vref, const double *d_body12, int64_t entered_coi,
+                             int64_t left_coi, int only_enter_coi, double *d_impact, double *d_atm,
+                             double *d_leave, double *d_ea_eff);
+int vsb_launch_points_pairs(vsb_ctx *c, int64_t npairs, const int64_t *d_pair_s,
+                            const int64_t *d_pair_body, const int64_t *d_sel,
+                            const double *d_vessel12, const int64_t *d_vref, const double *d_body12,
+                            int64_t left_coi, const double *d_leave, const double *d_ea_eff,
+                            double *d_vd10, double *d_bd10, unsigned char *d_valid);
+int vsb_launch_points_select(vsb_ctx *c, int64_t nsel, const int64_t *d_sel, const int64_t *d_offsets,
+                             const int64_t *d_pair_body, const unsigned char *d_valid,
+                             const double *d_out5, const double *d_ea_eff, const double *d_vessel12,
+                             double *d_enter);
 // kepler (vsb_kepler.cu)
 int vsb_launch_kepler_move(vsb_ctx *c, vsb_kepler_state &k, double warp);
 int vsb_launch_kepler_curves(vsb_ctx *c, vsb_kepler_state &k, int64_t first, int64_t count,

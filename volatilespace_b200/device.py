@@ -326,6 +326,34 @@ class Device:
         out.update(atm_h=atm_h, color=color, stellar_class=stellar)
         return out
 
+    def host_vessel_points(self, vessel12, v_ref, body12, body_ref, body_impact, body_enter_atm,
+                           coi_leave, coi_enter, sel=None, entered_coi=None, left_coi=None,
+                           left_coi_prev_ref=None, only_enter_coi=False, steps_limit=300):
+        """phys_vessel.Physics.points (phys_vessel.py:372-474) for the vessels in `sel` (all when
+        None); the four (nv,.) result arrays are updated in place."""
+        vessel12, body12 = f64(vessel12), f64(body12)
+        v_ref, body_ref = i64(v_ref), i64(body_ref)
+        nv, nb = len(vessel12), len(body12)
+        assert vessel12.shape == (nv, 12) and body12.shape == (nb, 12)
+        for arr, w in ((body_impact, 2), (body_enter_atm, 2), (coi_leave, 2), (coi_enter, 6)):
+            assert arr.dtype == np.float64 and arr.flags.c_contiguous and arr.shape == (nv, w)
+        sel_arr = None if sel is None else i64(np.atleast_1d(sel))
+        none = lambda x: -1 if x is None else int(x)
+        check(self.L.vsb_host_vessel_points(
+            self.h, nv, nb, ptr(vessel12), ptr(v_ref), ptr(body12), ptr(body_ref),
+            0 if sel_arr is None else len(sel_arr), None if sel_arr is None else ptr(sel_arr),
+            none(entered_coi), none(left_coi), none(left_coi_prev_ref), int(bool(only_enter_coi)),
+            int(steps_limit), ptr(body_impact), ptr(body_enter_atm), ptr(coi_leave), ptr(coi_enter)))
+
+    def set_march_mode(self, sequential):
+        check(self.L.vsb_set_march_mode(self.h, int(bool(sequential))))
+
+    def march_stats(self):
+        """(chunks marched, chunks re-run, serial fallbacks) of the last COI-entry march."""
+        out = np.zeros(3, dtype=np.uint64)
+        check(self.L.vsb_march_stats(self.h, ptr(out)))
+        return tuple(int(x) for x in out)
+
     def host_culling(self, coords, radius, screen_bounds, zoom):
         coords, radius, sb = f64(coords), f64(radius), f64(screen_bounds)
         mask = np.empty(len(radius), dtype=np.uint8)

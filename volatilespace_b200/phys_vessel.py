@@ -1,7 +1,9 @@
-"""Drop-in for the hot path of volatilespace/physics/phys_vessel.py on a B200:
-`Physics.move / curve / curve_move` (phys_vessel.py:477-503, 364-369).  The
-COI-crossing prediction, warp checks and curve segmentation of that class are
-per-vessel game logic and out of scope.
+"""Drop-in for the physics of volatilespace/physics/phys_vessel.py on a B200:
+`Physics.move / curve / curve_move` (phys_vessel.py:477-503, 364-369) and the orbit
+points `Physics.points` (:372-474: body impact, atmosphere entry, COI leave, COI enter
+-- SURVEY 8f N2), batched over all vessels.  The event handling built on those points
+(check_warp, cross_coi, predict_next_orbit, curve_segments) is per-vessel game logic and
+stays with the caller.
 """
 import numpy as np
 
@@ -27,7 +29,17 @@ class Physics:
         self.gc = conf["gc"]
         self.body_mass = np.array(body_data["mass"], dtype=np.float64)
         body_orb = body_orb or {}
-        self.body_coi = np.array(body_orb.get("coi", np.zeros(len(self.body_mass))), dtype=np.float64)
+        nb = len(self.body_mass)
+        self.body_coi = np.array(body_orb.get("coi", np.zeros(nb)), dtype=np.float64)
+        # what points() needs of the bodies (phys_vessel.py:200-213); absent keys -> zeros
+        col = lambda d, k: np.array((d or {}).get(k, np.zeros(nb)), dtype=np.float64)
+        self.body_size = col(body_data, "radius")
+        self.body_atm = col(body_data, "atm_h")
+        self.body_ref = np.array(body_orb.get("ref", np.zeros(nb)), dtype=np.int64)
+        self.body_a, self.body_b, self.body_f, self.body_ecc, self.body_pea, self.body_n, \
+            self.body_dr = (col(body_orb, k) for k in ("a", "b", "f", "ecc", "pea", "n", "dir"))
+        self.predict_coi_limit = 300                   # [game] predict_coi_limit, :181
+        self.entered_coi = self.left_coi = self.left_coi_prev_ref = None
         self.names = np.array((vessel_data or {}).get("name", []))
         self.a = np.array(vessel_orb_data["a"], dtype=np.float64)
         self.ecc = np.array(vessel_orb_data["ecc"], dtype=np.float64)
@@ -38,6 +50,9 @@ class Physics:
         self.n_vessels = len(self.a)
         self.pos = np.zeros((self.n_vessels, 2))
         self.ea = np.array(vessel_orb_data.get("ea", np.zeros(self.n_vessels)), dtype=np.float64)
+        nan = lambda w: np.full((self.n_vessels, w), np.nan)
+        self.body_impact, self.body_enter_atm, self.coi_leave, self.coi_enter = (
+            nan(2), nan(2), nan(2), nan(6))            # :231-234
 
     # phys_vessel.py:276-303 (orbit part) -> (vessel_orb, pos, ma, curves_mov)
     def initial(self, warp, body_pos, body_ma=None, body_ea=None):
@@ -49,11 +64,18 @@ class Physics:
         self.dev.kepler_load(KIND_VESSEL, self.curve_points, self.a, self.b, self.f, self.ecc,
                              self.pea, self.n, self.dr, self.ma, self.ea, self.ref, self.t)
         self.move(warp, body_pos, body_ma, body_ea)
-        return vessel_orb, self.pos, self.ma, self.curve_move()
+        curves_mov = self.curve_move()
+        if body_ma is not None and body_ea is not None and self.n_vessels:
+            self.points()                              # :300-302, all vessels in one batch
+        return vessel_orb, self.pos, self.ma, curves_mov
 
     # phys_vessel.py:477-494 -> (pos (Nv,2), ma (Nv,)), refreshed in place
     def move(self, warp, body_pos, body_ma=None, body_ea=None):
         self.body_pos = body_pos
+        if body_ma is not None:
+            self.body_ma = np.asarray(body_ma, dtype=np.float64)
+        if body_ea is not None:
+            self.body_ea = np.asarray(body_ea, dtype=np.float64)
         self.prev_ea = np.array(self.ea)
         self.dev.kepler_move(KIND_VESSEL, warp, body_pos)
         n = self.n_vessels
@@ -61,6 +83,22 @@ class Physics:
         self.dev.kepler_get(KIND_VESSEL, K_MA, n, out=self.ma)
         self.dev.kepler_get(KIND_VESSEL, K_EA, n, out=self.ea)
         return self.pos, self.ma
+
+    # phys_vessel.py:372-474; vessel=None processes every vessel (the loop of initial())
+    def points(self, vessel=None, only_enter_coi=False):
+        """Characteristic points of the vessel orbits: body_impact, body_enter_atm, coi_leave
+        (each (Nv,2): next / previous eccentric anomaly) and coi_enter (Nv,6), updated in place."""
+        vessel12 = np.stack([self.a, self.b, self.f, self.ecc, self.ma, self.ea, self.pea, self.n,
+                             self.dr, self.pe_d, self.ap_d, self.period], axis=1)
+        body12 = np.stack([self.body_a, self.body_b, self.body_f, self.body_ecc, self.body_ma,
+                           self.body_ea, self.body_pea, self.body_n, self.body_dr, self.body_coi,
+                           self.body_size, self.body_atm], axis=1)
+        self.dev.host_vessel_points(
+            vessel12, self.ref, body12, self.body_ref, self.body_impact, self.body_enter_atm,
+            self.coi_leave, self.coi_enter, sel=None if vessel is None else [vessel],
+            entered_coi=self.entered_coi, left_coi=self.left_coi,
+            left_coi_prev_ref=self.left_coi_prev_ref, only_enter_coi=only_enter_coi,
+            steps_limit=self.predict_coi_limit)
 
     # phys_vessel.py:364-369
     def curve(self, vessel):
