@@ -362,7 +362,8 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
             "serial_fallbacks": serial, "short_march_vessels": int(len(sel)),
             "gpu_ms_short": t_sel * 1e3, "cpu_port_ms_short": t_cpu * 1e3, "cpu_cores": 1,
             "note": "host arrays in and out (vsb_host_vessel_points); the C port needs ~100 s for "
-                    "all 160 vessels on one core, the reference ~110 s"}
+                    "all 160 vessels on one core, the reference ~110 s (oracle/gen_golden.py "
+                    "vessel_points, dev container)"}
     except Exception as e:
         out["vessel_points160"] = {"error": str(e)[:200]}
     return out

@@ -1,6 +1,6 @@
 """Small fixed workloads for ncu captures (see profiles/README.md).
 
-    python tools/profile_run.py gravity64k | kepler1m | collision256k | parents64k | editor15
+    python tools/profile_run.py gravity64k | kepler1m | collision256k | parents64k | points160
 """
 import os
 import sys
@@ -42,6 +42,13 @@ def main():
         order = np.argsort(s["mass"])[-1::-1]
         for _ in range(4):
             dev.find_parents(order, want=False)
+    elif mode == "points160":
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden",
+                                 "vessel_points.npz"))
+        nv = len(g["vessel12"])
+        res = [np.full((nv, w), np.nan) for w in (2, 2, 2, 6)]
+        dev.host_vessel_points(g["vessel12"], g["v_ref"], g["body12"], g["body_ref"], *res)
+        print("march stats", dev.march_stats())
     else:
         raise SystemExit("unknown mode")
     dev.sync()

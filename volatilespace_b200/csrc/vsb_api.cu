@@ -1229,11 +1229,9 @@ extern "C" int vsb_host_ell_hyp_intersect_circle(vsb_ctx *c, int64_t n, const do
     return d2h(c, count_out, d_cnt, 8 * (size_t)n);
 }
 
-static int march_stats_reset(vsb_ctx *c)
+static int march_work_reserve(vsb_ctx *c, int64_t n)
 {
-    VSB_TRY(vsb_buf_reserve(c->march_stats, 32));
-    VSB_CUDA(cudaMemsetAsync(c->march_stats.p, 0, 32, c->stream));
-    return VSB_OK;
+    return vsb_buf_reserve(c->march_stats, vsb_march_work_bytes(n));
 }
 
 extern "C" int vsb_host_predict_enter_coi(vsb_ctx *c, int64_t n, const double *vessel_data10,
@@ -1245,14 +1243,13 @@ extern "C" int vsb_host_predict_enter_coi(vsb_ctx *c, int64_t n, const double *v
                   (n == 0 || (vessel_data10 && body_data10 && out5)),
               VSB_ERR_ARG, "vsb_host_predict_enter_coi: bad argument");
     if (n == 0) return VSB_OK;
-    VSB_TRY(march_stats_reset(c));
+    VSB_TRY(march_work_reserve(c, n));
     VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * 25 * (size_t)n));
     double *d_vd = (double *)c->host_stage.p, *d_bd = d_vd + 10 * n, *d_out = d_bd + 10 * n;
     VSB_CUDA(cudaMemcpyAsync(d_vd, vessel_data10, 80 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VSB_CUDA(cudaMemcpyAsync(d_bd, body_data10, 80 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VSB_TRY(vsb_launch_predict_enter_coi(c, n, d_vd, d_bd, nullptr, tol, (int)steps_limit, d_out,
-                                         (unsigned long long *)c->march_stats.p,
-                                         c->march_sequential));
+                                         c->march_stats.p, c->march_sequential));
     return d2h(c, out5, d_out, 40 * (size_t)n);
 }
 
@@ -1349,7 +1346,8 @@ extern "C" int vsb_host_vessel_points(vsb_ctx *c, int64_t nv, int64_t nb, const 
                  o_vd = take(10 * NP), o_bd = take(10 * NP), o_out = take(5 * NP),
                  o_valid = take((NP + 7) / 8);
     VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * w));
-    VSB_TRY(march_stats_reset(c));
+    VSB_TRY(march_work_reserve(c, np_ > 0 ? np_ : 1));
+    VSB_CUDA(cudaMemsetAsync(c->march_stats.p, 0, 32, c->stream));
     double *base = (double *)c->host_stage.p;
     auto up = [&](size_t off, const void *src, size_t words) -> int {
         if (words == 0) return VSB_OK;
@@ -1377,8 +1375,7 @@ extern "C" int vsb_host_vessel_points(vsb_ctx *c, int64_t nv, int64_t nb, const 
                                     base + o_bd, (unsigned char *)(base + o_valid)));
     VSB_TRY(vsb_launch_predict_enter_coi(c, np_, base + o_vd, base + o_bd,
                                          (const unsigned char *)(base + o_valid), 1e-5,
-                                         (int)steps_limit, base + o_out,
-                                         (unsigned long long *)c->march_stats.p,
+                                         (int)steps_limit, base + o_out, c->march_stats.p,
                                          c->march_sequential));
     VSB_TRY(vsb_launch_points_select(c, nsel, d_sel, (const int64_t *)(base + o_off),
                                      (const int64_t *)(base + o_pb),

@@ -96,7 +96,7 @@ struct vsb_ctx {
     vsb_buf sorted;      // sorted-source staging for find_parents
     vsb_buf scratch;     // generic
     vsb_buf host_stage;  // device staging for the stateless host-buffer calls
-    vsb_buf march_stats; // 4 x u64 counters of the parallel COI-entry march (vsb_intersect.cu)
+    vsb_buf march_stats; // work area of the parallel COI-entry march; starts with 4 x u64 counters
     int march_sequential = 0;  // VSB_ENTER_COI=seq: the one-thread-per-pair serial march
     unsigned long long *d_key = nullptr;   // collision key (device)
     unsigned long long *h_key = nullptr;   // pinned mirror
@@ -307,7 +307,8 @@ int vsb_launch_quartic(vsb_ctx *c, int64_t n, const double *d_coef, double *d_ro
 int vsb_launch_intersect(vsb_ctx *c, int64_t n, const double *d_in6, double *d_ea, int64_t *d_cnt);
 int vsb_launch_predict_enter_coi(vsb_ctx *c, int64_t n, const double *d_vd, const double *d_bd,
                                  const unsigned char *d_valid, double tol, int steps_limit,
-                                 double *d_out5, unsigned long long *d_stats4, int sequential);
+                                 double *d_out5, void *d_work, int sequential);
+size_t vsb_march_work_bytes(int64_t n);
 int vsb_march_walk_host(double x0, double c, int64_t kmax, int bounded, double bound, int64_t nq,
                         const int64_t *ks, double *xs, int64_t *K_out, int64_t *nseg_out);
 int vsb_launch_points_vessel(vsb_ctx *c, int64_t nsel, const int64_t *d_sel, const double *d_vessel12,

@@ -464,20 +464,124 @@ __device__ __forceinline__ double hyp_guess(double ecc, double ma)
     return m < 0 ? -h : h;
 }
 
+// Per-pair constants of the march, computed identically by every thread of the CTA.
+struct msetup {
+    morbit v, b;
+    double dt, period, b_coi;
+    double v_ma0, v_ea0, v_pea, v_n, v_dr, b_ma0, b_ea0, b_pea, b_n, b_dr, cv, cb;
+    bool chained;
+};
+
+__device__ __forceinline__ msetup march_setup(const double *V, const double *B, int steps_limit)
+{
+    msetup m;
+    m.period = V[7];
+    m.b_coi = B[9];
+    const double c1 = m.period / m.b_coi * 5, c2 = m.period / 2, c3 = m.period / 30;
+    const double m1 = c2 < c1 ? c2 : c1;
+    const double m2 = c3 > m1 ? c3 : m1;
+    long long steps = (long long)m2;
+    if (steps_limit > steps) steps = steps_limit;
+    m.dt = m.period / (double)steps;
+    m.v = morbit{V[0], V[1], V[2], V[3], cos(V[6] - PI_D), sin(V[6] - PI_D), !(V[3] < 1)};
+    m.b = morbit{B[0], B[1], B[2], B[3], cos(B[6] - PI_D), sin(B[6] - PI_D), !(B[3] < 1)};
+    m.v_ma0 = V[4]; m.v_ea0 = V[5]; m.v_pea = V[6]; m.v_n = V[8]; m.v_dr = V[9];
+    m.b_ma0 = B[4]; m.b_ea0 = B[5]; m.b_pea = B[6]; m.b_n = B[7]; m.b_dr = B[8];
+    m.cv = m.v.hyp ? m.v_dr * m.v_n * -1 * m.dt : m.v_dr * m.v_n * m.dt;
+    m.cb = m.b.hyp ? m.b_dr * m.b_n * -1 * m.dt : m.b_dr * m.b_n * m.dt;
+    m.chained = m.v.hyp || m.b.hyp;
+    return m;
+}
+
+struct mshared {
+    mseg seg_t[MSEG_CAP], seg_v[MSEG_CAP], seg_b[MSEG_CAP];
+    int ns[3], fail[3];
+    long long K;
+};
+
+// CTA-collective: the three segment lists of one pair.  Returns 0 = ready, 1 = the reference
+// would never return (t stops growing): answer NaN, 2 = no closed form: serial fallback.
+__device__ int march_segments(const msetup &m, mshared &sh)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        long long K;
+        march_walk(0.0, m.dt, 1ll << 60, true, m.period, sh.seg_t, &sh.ns[0], &K, &sh.fail[0]);
+        sh.K = K;
+    }
+    __syncthreads();
+    const long long K = sh.K;
+    if (tid == 32) {
+        long long kk;
+        march_walk(m.v_ma0, m.cv, K, false, 0.0, sh.seg_v, &sh.ns[1], &kk, &sh.fail[1]);
+    }
+    if (tid == 64) {
+        long long kk;
+        march_walk(m.b_ma0, m.cb, K, false, 0.0, sh.seg_b, &sh.ns[2], &kk, &sh.fail[2]);
+    }
+    __syncthreads();
+    if (sh.fail[0] == 2) return 1;
+    if (sh.fail[0] | sh.fail[1] | sh.fail[2]) return 2;
+    return 0;
+}
+
+// the 30-step refinement of the reference (orbit_intersect.py:151-168) from the exact state at
+// the first step inside the COI
+__device__ void march_refine(const msetup &m, const mshared &sh, const mchunk &r, double tol,
+                             double *o)
+{
+    orbit ov{m.v.a, m.v.b, m.v.f, m.v.ecc, r.hv_ma, r.hv_ea, m.v_pea, m.v_n, m.v_dr,
+             m.v.hyp ? r.hv_ea : m.v_ea0};
+    orbit ob{m.b.a, m.b.b, m.b.f, m.b.ecc, r.hb_ma, r.hb_ea, m.b_pea, m.b_n, m.b_dr,
+             m.b.hyp ? r.hb_ea : m.b_ea0};
+    double t = 0, d = r.hd, dtt = m.dt;
+    if (r.hit > 1) {
+        int it_ = march_find(sh.seg_t, sh.ns[0], r.hit - 1);
+        t = march_at(sh.seg_t, it_, r.hit - 1);
+    }
+    for (int it = 0; it < 30; ++it) {
+        dtt = fabs(dtt) / 2 * (d < m.b_coi ? -1 : 1);
+        t += dtt;
+        oi_move(ov, dtt);
+        oi_move(ob, dtt);
+        d = oi_dist(ov, ob);
+        if (fabs(d - m.b_coi) < tol) break;
+    }
+    o[0] = oi_wrap(ov.ea);
+    o[1] = oi_wrap(ob.ea);
+    o[2] = oi_wrap(ov.ma);
+    o[3] = oi_wrap(ob.ma);
+    o[4] = t;
+}
+
+// Long elliptic-elliptic pairs are split over a team of CTAs (team kernel below).
+constexpr long long TEAM_MIN_STEPS = 64 * MARCH_T;    // below: one CTA marches the whole pair
+constexpr int TEAM_MAX = 256;                         // parts per pair
+constexpr int TEAM_TASK_CAP = 1 << 16;
+struct mtask {
+    long long item;
+    int part, parts;
+};
+struct mteam {          // device-global bookkeeping of one launch pair
+    unsigned long long stats[4];      // chunks, re-runs, serial fallbacks, item counter
+    unsigned long long ntasks, next_task;
+};
+
 // stats[0] += chunks marched, stats[1] += chunks re-run after a failed speculation,
 // stats[2] += items that fell back to the serial march, stats[3] = work counter (zero at launch)
 __global__ void __launch_bounds__(MARCH_T)
 enter_coi_march_kernel(int64_t n, const double *__restrict__ vd, const double *__restrict__ bd,
                        const unsigned char *__restrict__ valid, double tol, int steps_limit,
-                       double *__restrict__ out5, unsigned long long *__restrict__ stats)
+                       double *__restrict__ out5, mteam *__restrict__ team,
+                       mtask *__restrict__ tasks, unsigned long long *__restrict__ best_hit,
+                       unsigned int *__restrict__ parts_done)
 {
-    __shared__ mseg seg_t[MSEG_CAP], seg_v[MSEG_CAP], seg_b[MSEG_CAP];
-    __shared__ int ns_sh[3], fail_sh[3];
-    __shared__ long long K_sh;
+    __shared__ mshared sh;
     __shared__ double end_v[MARCH_T], end_b[MARCH_T], carry[2];
-    __shared__ unsigned long long hit_sh, item_sh;
+    __shared__ unsigned long long hit_sh, item_sh, slot_sh;
     const int tid = threadIdx.x;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    unsigned long long *stats = team->stats;
 
     for (;;) {
         __syncthreads();                       // shared state of the previous item is dead
@@ -487,52 +591,53 @@ enter_coi_march_kernel(int64_t n, const double *__restrict__ vd, const double *_
         if (item >= n) break;
         const double *V = vd + 10 * item, *B = bd + 10 * item;
         double *o = out5 + 5 * item;
-        const double period = V[7], b_coi = B[9];
-        if ((valid && !valid[item]) || period == 0 || b_coi == 0) {
+        if ((valid && !valid[item]) || V[7] == 0 || B[9] == 0) {
             if (tid < 5) o[tid] = nan;
             continue;
         }
-        const double c1 = period / b_coi * 5, c2 = period / 2, c3 = period / 30;
-        const double m1 = c2 < c1 ? c2 : c1;
-        const double m2 = c3 > m1 ? c3 : m1;
-        long long steps = (long long)m2;
-        if (steps_limit > steps) steps = steps_limit;
-        const double dt = period / (double)steps;
-        morbit v{V[0], V[1], V[2], V[3], cos(V[6] - PI_D), sin(V[6] - PI_D), !(V[3] < 1)};
-        morbit b{B[0], B[1], B[2], B[3], cos(B[6] - PI_D), sin(B[6] - PI_D), !(B[3] < 1)};
-        const double v_ma0 = V[4], v_ea0 = V[5], v_n = V[8], v_dr = V[9];
-        const double b_ma0 = B[4], b_ea0 = B[5], b_n = B[7], b_dr = B[8];
-        const double cv = v.hyp ? v_dr * v_n * -1 * dt : v_dr * v_n * dt;
-        const double cb = b.hyp ? b_dr * b_n * -1 * dt : b_dr * b_n * dt;
-
-        if (tid == 0) {
-            long long K;
-            march_walk(0.0, dt, 1ll << 60, true, period, seg_t, &ns_sh[0], &K, &fail_sh[0]);
-            K_sh = K;
-        }
-        __syncthreads();
-        const long long K = K_sh;
-        if (tid == 32) {
-            long long kk;
-            march_walk(v_ma0, cv, K, false, 0.0, seg_v, &ns_sh[1], &kk, &fail_sh[1]);
-        }
-        if (tid == 64) {
-            long long kk;
-            march_walk(b_ma0, cb, K, false, 0.0, seg_b, &ns_sh[2], &kk, &fail_sh[2]);
-        }
-        __syncthreads();
-        if (fail_sh[0] == 2) {       // t stops growing below t_end: the reference never returns
+        const msetup m = march_setup(V, B, steps_limit);
+        const int st = march_segments(m, sh);
+        if (st == 1) {                          // CTA-uniform
             if (tid < 5) o[tid] = nan;
             continue;
         }
-        if (fail_sh[0] | fail_sh[1] | fail_sh[2]) {      // CTA-uniform
+        if (st == 2) {
             if (tid == 0) {
                 march_sequential(V, B, tol, steps_limit, o);
                 atomicAdd(&stats[2], 1ull);
             }
             continue;
         }
-        const bool chained = v.hyp || b.hyp;
+        const long long K = sh.K;
+        const morbit &v = m.v, &b = m.b;
+        const double b_coi = m.b_coi;
+        const bool chained = m.chained;
+        if (!chained && K > TEAM_MIN_STEPS && tasks) {
+            // hand the pair to a team: `parts` CTAs of the team kernel take its waves round-robin
+            long long parts = (K + TEAM_MIN_STEPS - 1) / TEAM_MIN_STEPS;
+            if (parts > TEAM_MAX) parts = TEAM_MAX;
+            if (tid == 0) {
+                unsigned long long slot = *(volatile unsigned long long *)&team->ntasks;
+                for (;;) {                      // reserve `parts` consecutive task slots
+                    if (slot + parts > TEAM_TASK_CAP) {
+                        slot = ~0ull;
+                        break;
+                    }
+                    const unsigned long long seen = atomicCAS(&team->ntasks, slot, slot + parts);
+                    if (seen == slot) break;
+                    slot = seen;
+                }
+                if (slot != ~0ull) {
+                    best_hit[item] = ~0ull;
+                    parts_done[item] = 0;
+                    for (int j = 0; j < (int)parts; ++j)
+                        tasks[slot + j] = mtask{(long long)item, j, (int)parts};
+                }
+                slot_sh = slot;
+            }
+            __syncthreads();
+            if (slot_sh != ~0ull) continue;     // otherwise: no room, march it here
+        }
         const int C = chained ? MARCH_C : 1;
         bool done = false;
         unsigned long long n_chunks = 0, n_rerun = 0;
@@ -540,7 +645,7 @@ enter_coi_march_kernel(int64_t n, const double *__restrict__ vd, const double *_
             const long long s = base + (long long)tid * C + 1;
             const long long e = s + C - 1 < K ? s + C - 1 : K;
             const bool active = s <= K;
-            double sv = v_ea0, sb = b_ea0;
+            double sv = m.v_ea0, sb = m.b_ea0;
             int iv = 0, ib = 0;
             mchunk r;
             r.hit = -1;
@@ -555,20 +660,20 @@ enter_coi_march_kernel(int64_t n, const double *__restrict__ vd, const double *_
                     } else {
                         // speculate the chain value at step s-1: warm up from step w0
                         const long long w0 = s - MARCH_W > 1 ? s - MARCH_W : 1;
-                        int jv = march_find(seg_v, ns_sh[1], w0), jb = march_find(seg_b, ns_sh[2], w0);
+                        int jv = march_find(sh.seg_v, sh.ns[1], w0), jb = march_find(sh.seg_b, sh.ns[2], w0);
                         if (w0 > 1) {
-                            if (v.hyp) sv = hyp_guess(v.ecc, march_at(seg_v, jv, w0));
-                            if (b.hyp) sb = hyp_guess(b.ecc, march_at(seg_b, jb, w0));
+                            if (v.hyp) sv = hyp_guess(v.ecc, march_at(sh.seg_v, jv, w0));
+                            if (b.hyp) sb = hyp_guess(b.ecc, march_at(sh.seg_b, jb, w0));
                         }
                         for (long long k = w0; k < s; ++k) {
-                            if (v.hyp) sv = pe_newton_hyp(v.ecc, march_at(seg_v, jv, k), sv);
-                            if (b.hyp) sb = pe_newton_hyp(b.ecc, march_at(seg_b, jb, k), sb);
+                            if (v.hyp) sv = pe_newton_hyp(v.ecc, march_at(sh.seg_v, jv, k), sv);
+                            if (b.hyp) sb = pe_newton_hyp(b.ecc, march_at(sh.seg_b, jb, k), sb);
                         }
                     }
                 }
-                iv = march_find(seg_v, ns_sh[1], s);
-                ib = march_find(seg_b, ns_sh[2], s);
-                march_chunk(v, b, seg_v, seg_b, iv, ib, s, e, sv, sb, b_coi, r);
+                iv = march_find(sh.seg_v, sh.ns[1], s);
+                ib = march_find(sh.seg_b, sh.ns[2], s);
+                march_chunk(v, b, sh.seg_v, sh.seg_b, iv, ib, s, e, sv, sb, b_coi, r);
                 ++n_chunks;
             }
             if (chained) {
@@ -588,7 +693,7 @@ enter_coi_march_kernel(int64_t n, const double *__restrict__ vd, const double *_
                     if (mism) {
                         sv = tv;
                         sb = tb;
-                        march_chunk(v, b, seg_v, seg_b, iv, ib, s, e, sv, sb, b_coi, r);
+                        march_chunk(v, b, sh.seg_v, sh.seg_b, iv, ib, s, e, sv, sb, b_coi, r);
                         ++n_rerun;
                         end_v[tid] = r.v_end;
                         end_b[tid] = r.b_end;
@@ -602,32 +707,7 @@ enter_coi_march_kernel(int64_t n, const double *__restrict__ vd, const double *_
             __syncthreads();
             const unsigned long long hit = hit_sh;
             if (hit != ~0ull) {
-                if (r.hit >= 0 && (unsigned long long)r.hit == hit) {
-                    // the 30-step refinement of the reference, from the exact state at the hit
-                    orbit ov{v.a, v.b, v.f, v.ecc, r.hv_ma, r.hv_ea, V[6], v_n, v_dr,
-                             v.hyp ? r.hv_ea : v_ea0};
-                    orbit ob{b.a, b.b, b.f, b.ecc, r.hb_ma, r.hb_ea, B[6], b_n, b_dr,
-                             b.hyp ? r.hb_ea : b_ea0};
-                    int it_ = 0;
-                    double t = 0, d = r.hd, dtt = dt;
-                    if (r.hit > 1) {
-                        it_ = march_find(seg_t, ns_sh[0], r.hit - 1);
-                        t = march_at(seg_t, it_, r.hit - 1);
-                    }
-                    for (int it = 0; it < 30; ++it) {
-                        dtt = fabs(dtt) / 2 * (d < b_coi ? -1 : 1);
-                        t += dtt;
-                        oi_move(ov, dtt);
-                        oi_move(ob, dtt);
-                        d = oi_dist(ov, ob);
-                        if (fabs(d - b_coi) < tol) break;
-                    }
-                    o[0] = oi_wrap(ov.ea);
-                    o[1] = oi_wrap(ob.ea);
-                    o[2] = oi_wrap(ov.ma);
-                    o[3] = oi_wrap(ob.ma);
-                    o[4] = t;
-                }
+                if (r.hit >= 0 && (unsigned long long)r.hit == hit) march_refine(m, sh, r, tol, o);
                 done = true;
             } else if (chained && tid == MARCH_T - 1) {
                 carry[0] = r.v_end;
@@ -638,6 +718,81 @@ enter_coi_march_kernel(int64_t n, const double *__restrict__ vd, const double *_
         if (!done && tid < 5) o[tid] = nan;
         if (n_chunks) atomicAdd(&stats[0], n_chunks);
         if (n_rerun) atomicAdd(&stats[1], n_rerun);
+    }
+}
+
+// Team kernel: the long elliptic-elliptic pairs queued by the kernel above.  Part j of a pair
+// marches the waves j, j+parts, ... in increasing order and stops as soon as its next wave lies
+// beyond the best hit known so far (a device-wide atomicMin); the last part to finish recomputes
+// the state at the winning step (stateless for elliptic orbits) and runs the refinement.
+__global__ void __launch_bounds__(MARCH_T)
+enter_coi_team_kernel(const double *__restrict__ vd, const double *__restrict__ bd, double tol,
+                      int steps_limit, double *__restrict__ out5, mteam *__restrict__ team,
+                      const mtask *__restrict__ tasks, unsigned long long *__restrict__ best_hit,
+                      unsigned int *__restrict__ parts_done)
+{
+    __shared__ mshared sh;
+    __shared__ unsigned long long hit_sh, task_sh;
+    __shared__ unsigned int ticket_sh;
+    const int tid = threadIdx.x;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const unsigned long long ntasks = team->ntasks;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) task_sh = atomicAdd(&team->next_task, 1ull);
+        __syncthreads();
+        if (task_sh >= ntasks) break;
+        const mtask tk = tasks[task_sh];
+        const double *V = vd + 10 * tk.item, *B = bd + 10 * tk.item;
+        double *o = out5 + 5 * tk.item;
+        const msetup m = march_setup(V, B, steps_limit);
+        march_segments(m, sh);                  // cannot fail: the first kernel walked the same sums
+        const long long K = sh.K;
+        unsigned long long n_chunks = 0;
+        volatile unsigned long long *best = best_hit + tk.item;
+        for (long long base = (long long)tk.part * MARCH_T; base < K;
+             base += (long long)tk.parts * MARCH_T) {
+            if (tid == 0) hit_sh = *best;
+            __syncthreads();
+            if (hit_sh < (unsigned long long)(base + 1)) break;     // CTA-uniform
+            __syncthreads();
+            if (tid == 0) hit_sh = ~0ull;
+            __syncthreads();
+            const long long s = base + tid + 1;
+            if (s <= K) {
+                mchunk r;
+                const int iv = march_find(sh.seg_v, sh.ns[1], s), ib = march_find(sh.seg_b, sh.ns[2], s);
+                march_chunk(m.v, m.b, sh.seg_v, sh.seg_b, iv, ib, s, s, 0.0, 0.0, m.b_coi, r);
+                ++n_chunks;
+                if (r.hit >= 0) atomicMin(&hit_sh, (unsigned long long)r.hit);
+            }
+            __syncthreads();
+            if (hit_sh != ~0ull) {
+                if (tid == 0) atomicMin(best_hit + tk.item, hit_sh);
+                break;                                               // later waves are farther
+            }
+        }
+        if (n_chunks) atomicAdd(&team->stats[0], n_chunks);
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            ticket_sh = atomicAdd(parts_done + tk.item, 1u);
+        }
+        __syncthreads();
+        if (ticket_sh == (unsigned)tk.parts - 1) {                   // last part of the pair
+            __threadfence();
+            const unsigned long long k = *best;
+            if (k == ~0ull) {
+                if (tid < 5) o[tid] = nan;
+            } else if (tid == 0) {
+                mchunk r;
+                const int iv = march_find(sh.seg_v, sh.ns[1], (long long)k),
+                          ib = march_find(sh.seg_b, sh.ns[2], (long long)k);
+                march_chunk(m.v, m.b, sh.seg_v, sh.seg_b, iv, ib, (long long)k, (long long)k, 0.0, 0.0,
+                            m.b_coi, r);
+                march_refine(m, sh, r, tol, o);
+            }
+        }
     }
 }
 
@@ -826,21 +981,36 @@ int vsb_launch_intersect(vsb_ctx *c, int64_t n, const double *d_in6, double *d_e
     return VSB_OK;
 }
 
+// d_work: mteam header | mtask[TEAM_TASK_CAP] | best_hit[n] (u64) | parts_done[n] (u32)
+size_t vsb_march_work_bytes(int64_t n)
+{
+    return sizeof(mteam) + sizeof(mtask) * (size_t)TEAM_TASK_CAP + 8 * (size_t)n +
+           4 * (size_t)((n + 1) / 2 * 2) + 64;
+}
+
 int vsb_launch_predict_enter_coi(vsb_ctx *c, int64_t n, const double *d_vd, const double *d_bd,
                                  const unsigned char *d_valid, double tol, int steps_limit,
-                                 double *d_out5, unsigned long long *d_stats4, int sequential)
+                                 double *d_out5, void *d_work, int sequential)
 {
     if (n <= 0) return VSB_OK;
+    mteam *team = (mteam *)d_work;
+    VSB_CUDA(cudaMemsetAsync(team, 0, sizeof(mteam), c->stream));
     if (sequential) {
         predict_enter_coi_seq_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
             n, d_vd, d_bd, d_valid, tol, steps_limit, d_out5);
-    } else {
-        VSB_CUDA(cudaMemsetAsync(d_stats4 + 3, 0, 8, c->stream));
-        const int64_t cap = (int64_t)c->sm_count * 4;
-        enter_coi_march_kernel<<<(unsigned)(n < cap ? n : cap), MARCH_T, 0, c->stream>>>(
-            n, d_vd, d_bd, d_valid, tol, steps_limit, d_out5, d_stats4);
+        c->launches += 1;
+        VSB_CUDA(cudaGetLastError());
+        return VSB_OK;
     }
-    c->launches += 1;
+    mtask *tasks = (mtask *)(team + 1);
+    unsigned long long *best = (unsigned long long *)(tasks + TEAM_TASK_CAP);
+    unsigned int *done = (unsigned int *)(best + n);
+    const int64_t cap = (int64_t)c->sm_count * 2;
+    enter_coi_march_kernel<<<(unsigned)(n < cap ? n : cap), MARCH_T, 0, c->stream>>>(
+        n, d_vd, d_bd, d_valid, tol, steps_limit, d_out5, team, tasks, best, done);
+    enter_coi_team_kernel<<<(unsigned)cap, MARCH_T, 0, c->stream>>>(
+        d_vd, d_bd, tol, steps_limit, d_out5, team, tasks, best, done);
+    c->launches += 2;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;
 }
