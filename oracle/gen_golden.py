@@ -676,6 +676,148 @@ def gen_vessel_points(ns, conf, bd, bod):
         np.sum(~np.isnan(pv.coi_leave[:, 0])), np.sum(~np.isnan(pv.coi_enter[:, 0])), nv))
 
 
+def gen_vessel_events(ns, conf, bd, bod):
+    """N2 per-tick vessel events: the physics loop of game.py:1165-1265 (check_warp,
+    predict_enter_coi_service, body/vessel move, cross_coi, change_vessel) run on the live
+    reference for the Solar System + the synthetic vessels of `vessel_points`; function-level
+    snapshots (inputs and outputs of each call) at the ticks where something happens and at a few
+    quiet ones."""
+    import copy
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    from volatilespace.physics import convert
+    sys.path.remove(rh.REFERENCE_ROOT)
+    g = np.load(os.path.join(OUT, "vessel_points.npz"))
+    P = 8
+    korb = convert.to_kepler(bd["mass"], copy.deepcopy(bod), conf["gc"], conf["coi_coef"])
+    pb = ns.phys_body.Physics()
+    rh.set_curve_points(ns, pb, P)
+    pb.load(conf, copy.deepcopy(bd), copy.deepcopy(korb))
+    body_data, body_orb, bpos, bma, bea, _ = pb.initial(1)
+    v12 = g["vessel12"]
+    # leave out the high-eccentricity ellipses (their COI-entry march is chaotic in the reference,
+    # see DESIGN.md) and the four vessels whose march takes tens of seconds per call
+    keep = np.flatnonzero(~((v12[:, 3] >= 0.8) & (v12[:, 3] < 1)))
+    keep = keep[~np.isin(keep, [2, 5])]
+    nv = len(keep)
+    vessel_data = {"name": np.array(["v%d" % i for i in keep]), "mass": np.ones(nv),
+                   "rot_angle": np.zeros(nv), "rot_acc": np.zeros(nv)}
+    ma0 = v12[keep, 4].copy()
+    vessel_orb = {"a": v12[keep, 0].copy(), "ecc": v12[keep, 3].copy(), "pe_arg": v12[keep, 6].copy(),
+                  "ma": ma0, "ref": g["v_ref"][keep].copy(), "dir": v12[keep, 8].copy()}
+    pv = ns.phys_vessel.Physics()
+    rh.set_curve_points(ns, pv, P)
+    pv.load(conf, body_data, body_orb, vessel_data, vessel_orb)
+    # initial() moves once by `warp`; start from the fixture's pre-move anomalies
+    hyp = np.where(pv.ecc > 1, -1, 1)
+    pv.ma = pv.ma - 0.0
+    pv.initial(1, bpos, bma, bea)
+    out = dict(keep=keep, gc=conf["gc"], body_mass=np.array(pv.body_mass, dtype=float),
+               body_ref=np.array(pv.body_ref, dtype=np.int64),
+               body_static=np.stack([pv.body_a, pv.body_b, pv.body_f, pv.body_ecc, pv.body_pea,
+                                     pv.body_n, pv.body_dr, pv.body_coi, pv.body_size,
+                                     pv.body_atm], axis=1).astype(float),
+               steps_limit=pv.predict_coi_limit, P=P)
+
+    def vstate():
+        return np.stack([pv.a, pv.b, pv.f, pv.ecc, pv.pea, pv.n, pv.dr, pv.ma, pv.ea, pv.prev_ea,
+                         pv.u, pv.pe_d, pv.ap_d, pv.period], axis=1).astype(float)
+
+    def pts():
+        return np.concatenate([pv.body_impact, pv.body_enter_atm, pv.coi_leave, pv.coi_enter], axis=1)
+
+    def hold_mask():
+        m = np.zeros(nv, dtype=np.uint8)
+        m[np.asarray(pv.physical_hold, dtype=int)] = 1
+        return m
+
+    opt = lambda x: -1 if x is None else int(x)
+    service_calls = []
+    orig_points = pv.points
+
+    def logged_points(vessel, only_enter_coi=False):
+        if only_enter_coi:
+            service_calls.append(vessel)
+        return orig_points(vessel, only_enter_coi)
+
+    pv.points = logged_points
+    cw, sv, cx, cv = [], [], [], []
+    warp_cycle = [1, 5, 25, 100]
+    T = 6000
+    phase_len = 250
+    cap = dict(cw=24, sv=16, cx=28, cv=16)          # fixture size: ~20 KB per snapshot
+    per_phase = dict(cw=2, sv=1, cx=2, cv=1)
+    seen = {}
+
+    def room(kind, lst, tick):
+        key = (kind, tick // phase_len)
+        if len(lst) >= cap[kind] or seen.get(key, 0) >= per_phase[kind]:
+            return False
+        seen[key] = seen.get(key, 0) + 1
+        return True
+
+    for tick in range(T):
+        warp = warp_cycle[(tick // phase_len) % len(warp_cycle)]
+        # --- check_warp
+        pre = (vstate(), pts(), hold_mask())
+        situation, alarm, nhold = pv.check_warp(warp)
+        if situation is not None or tick % 1500 == 0 or not np.array_equal(pre[2], hold_mask()):
+            if room("cw", cw, tick):
+                k = len(cw)
+                out.update({"cw%d_v" % k: pre[0], "cw%d_p" % k: pre[1], "cw%d_hold_in" % k: pre[2],
+                            "cw%d_hold_out" % k: hold_mask(),
+                            "cw%d_out" % k: np.array([opt(situation), opt(alarm), nhold, warp])})
+                cw.append(tick)
+        # --- predict_enter_coi_service
+        del service_calls[:]
+        pre = (vstate(), pts())
+        flags_in = np.array([opt(pv.entered_coi), opt(pv.left_coi), opt(pv.left_coi_prev_ref)])
+        pv.predict_enter_coi_service()
+        if (service_calls or tick % 1500 == 0) and room("sv", sv, tick):
+            k = len(sv)
+            calls = np.array(sorted(set(service_calls)), dtype=np.int64)
+            out.update({"sv%d_v" % k: pre[0], "sv%d_p" % k: pre[1], "sv%d_flags" % k: flags_in,
+                        "sv%d_calls" % k: calls, "sv%d_bma" % k: np.array(pv.body_ma, dtype=float),
+                        "sv%d_bea" % k: np.array(pv.body_ea, dtype=float),
+                        "sv%d_ref" % k: np.array(pv.ref, dtype=np.int64),
+                        "sv%d_p_out_rows" % k: pts()[calls]})
+            sv.append(tick)
+        # --- move
+        bpos, bma, bea = pb.move(warp)
+        pv.move(warp, bpos, bma, bea)
+        # --- cross_coi
+        pre = (vstate(), pts(), np.array(pv.ref, dtype=np.int64), np.array(bpos, dtype=float),
+               np.array([opt(pv.entered_coi), opt(pv.left_coi), opt(pv.left_coi_prev_ref)]))
+        changed = pv.cross_coi()
+        if (changed is not None or tick % 1500 == 750) and room("cx", cx, tick):
+            k = len(cx)
+            out.update({"cx%d_v" % k: pre[0], "cx%d_p" % k: pre[1], "cx%d_ref" % k: pre[2],
+                        "cx%d_bpos" % k: pre[3], "cx%d_flags_in" % k: pre[4],
+                        "cx%d_flags_out" % k: np.array([opt(pv.entered_coi), opt(pv.left_coi),
+                                                        opt(pv.left_coi_prev_ref)]),
+                        "cx%d_ret" % k: np.array([opt(changed)]),
+                        "cx%d_row_out" % k: vstate()[max(opt(changed), 0)],
+                        "cx%d_ref_out" % k: np.array([pv.ref[max(opt(changed), 0)]], dtype=np.int64)})
+            cx.append(tick)
+        # --- change_vessel
+        if changed is not None:
+            pre = (vstate(), pts(), np.array(pv.ref, dtype=np.int64),
+                   np.array([opt(pv.entered_coi), opt(pv.left_coi), opt(pv.left_coi_prev_ref)]),
+                   np.array(pv.body_ma, dtype=float), np.array(pv.body_ea, dtype=float))
+            pv.change_vessel(changed)
+            if room("cv", cv, tick):
+                k = len(cv)
+                out.update({"cv%d_v" % k: pre[0], "cv%d_p" % k: pre[1], "cv%d_ref" % k: pre[2],
+                            "cv%d_flags" % k: pre[3], "cv%d_bma" % k: pre[4], "cv%d_bea" % k: pre[5],
+                            "cv%d_vessel" % k: np.array([changed]),
+                            "cv%d_row_out" % k: vstate()[changed], "cv%d_p_row_out" % k: pts()[changed],
+                            "cv%d_curve" % k: pv.curves[changed].copy()})
+                cv.append(tick)
+    out.update(n_cw=len(cw), n_sv=len(sv), n_cx=len(cx), n_cv=len(cv))
+    save("vessel_events", **out)
+    print("  vessel_events: %d vessels, %d check_warp, %d service, %d cross_coi, %d change_vessel "
+          "snapshots" % (nv, len(cw), len(sv), len(cx), len(cv)))
+
+
 def main():
     """All fixtures, or only the ones named on the command line (e.g. `vessel_points`)."""
     ns = rh.load()
@@ -693,6 +835,7 @@ def main():
     if want("convert"): gen_convert(ns, conf, bd, bod)
     if want("intersect"): gen_intersect(ns)
     if want("vessel_points"): gen_vessel_points(ns, conf, bd, bod)
+    if want("vessel_events"): gen_vessel_events(ns, conf, bd, bod)
 
 
 if __name__ == "__main__":

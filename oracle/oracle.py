@@ -39,6 +39,7 @@ def lib():
         build()
     L = C.CDLL(_LIB_PATH)
     i64, f64 = C.c_int64, C.c_double
+    _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
     sigs = {
         "vso_num_threads": (C.c_int, []),
         "vso_set_num_threads": (None, [C.c_int]),
@@ -70,6 +71,13 @@ def lib():
         "vso_solve_quartic": (None, [f64, f64, f64, f64, f64, _f64p]),
         "vso_ell_hyp_intersect_circle": (C.c_int, [f64, f64, f64, f64, f64, f64, _f64p]),
         "vso_predict_enter_coi": (None, [_f64p, _f64p, f64, C.c_int, _f64p]),
+        "vso_point_between": (C.c_int, [f64, f64, f64, f64]),
+        "vso_check_warp": (None, [i64] + [_f64p] * 9 + [f64, _u8p, _i64p]),
+        "vso_enter_coi_service": (None, [i64, _f64p, _f64p, _f64p, _f64p, C.c_int, _u8p]),
+        "vso_cross_scan": (None, [i64] + [_f64p] * 7 + [_i64p]),
+        "vso_kepler_to_velocity": (None, [_f64p, f64, f64, f64, f64, f64, _f64p]),
+        "vso_velocity_to_kepler": (None, [_f64p, _f64p, f64, C.c_int, _f64p]),
+        "vso_cross_apply": (C.c_int, [C.c_int, _f64p, i64, i64, _f64p, f64, _f64p]),
         "vso_vessel_points": (None, [i64, _i64p, i64, _f64p, _i64p, _f64p, _i64p, i64, i64, i64,
                                      C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p]),
         "vso_editor_curve": (None, [i64, i64, _f64p, _f64p, _f64p, _f64p, _f64p, _i64p,
@@ -312,6 +320,56 @@ def vessel_points(vessel12, v_ref, body12, body_ref, sel=None, entered_coi=None,
                             none(entered_coi), none(left_coi), none(left_coi_prev_ref),
                             int(bool(only_enter_coi)), int(steps_limit), bi, ba, cl, ce)
     return bi, ba, cl, ce
+
+
+def check_warp(ecc, dr, ea, ma, n, body_impact, body_enter_atm, coi_leave, coi_enter, warp, hold):
+    """phys_vessel.Physics.check_warp (phys_vessel.py:506-560) -> (situation, alarm_vessel,
+    len(physical_hold)) with None as in the reference, and the new hold mask."""
+    hold = np.ascontiguousarray(hold, dtype=np.uint8).copy()
+    out = np.zeros(3, dtype=np.int64)
+    lib().vso_check_warp(len(ecc), _f(ecc), _f(dr), _f(ea), _f(ma), _f(n), _f(body_impact),
+                         _f(body_enter_atm), _f(coi_leave), _f(coi_enter), float(warp), hold, out)
+    opt = lambda x: None if x < 0 else int(x)
+    return (opt(out[0]), opt(out[1]), int(out[2])), hold
+
+
+def enter_coi_service(dr, prev_ea, ea, coi_enter, entered_coi=None, left_coi=None):
+    """predict_enter_coi_service (phys_vessel.py:744-758): the vessels it calls points(v, True) on."""
+    flags = np.zeros(len(dr), dtype=np.uint8)
+    lib().vso_enter_coi_service(len(dr), _f(dr), _f(prev_ea), _f(ea), _f(coi_enter),
+                                int(entered_coi is not None or left_coi is not None), flags)
+    return np.flatnonzero(flags)
+
+
+def cross_scan(ecc, dr, prev_ea, ea, body_impact, coi_leave, coi_enter):
+    """cross_coi (phys_vessel.py:563-632), detection: (vessel, kind) of the first crossing, kind
+    1 = enter, 2 = leave; (None, 0) when nothing crosses."""
+    out = np.zeros(2, dtype=np.int64)
+    lib().vso_cross_scan(len(ecc), _f(ecc), _f(dr), _f(prev_ea), _f(ea), _f(body_impact),
+                         _f(coi_leave), _f(coi_enter), out)
+    return (None if out[0] < 0 else int(out[0])), int(out[1])
+
+
+def cross_apply(kind, vessel8, ref, new_ref, body7, gc):
+    """cross_coi, the orbit change (phys_vessel.py:585-629) -> (a, ecc, pea, ma, dr, new_ref) or
+    None where the reference returns None."""
+    out = np.zeros(6)
+    rc = lib().vso_cross_apply(int(kind), _f(vessel8), int(ref), int(new_ref), _f(body7), float(gc),
+                               out)
+    return None if rc else out
+
+
+def kepler_to_velocity(rel_pos, a, ecc, pe_arg, u, dr):
+    out = np.zeros(2)
+    lib().vso_kepler_to_velocity(_f(rel_pos), float(a), float(ecc), float(pe_arg), float(u),
+                                 float(dr), out)
+    return out
+
+
+def velocity_to_kepler(rel_pos, rel_vel, u, failsafe=0):
+    out = np.zeros(5)
+    lib().vso_velocity_to_kepler(_f(rel_pos), _f(rel_vel), float(u), int(failsafe), out)
+    return out
 
 
 def to_kepler(mass, pos, vel, gc, coi_coef):

@@ -393,7 +393,7 @@ void vso_calc_orb_one(int with_coi, int64_t body, int64_t ref, const double *mas
     if (ecc != 0) {
         pe_d = a * (1 - ecc);
         if (ecc < 1) {
-            period = 2 * VSO_PI * sqrt(a * a * a / u);
+            period = 2 * VSO_PI * sqrt(pow(a, 3.0) / u);   /* a**3: libm pow, as CPython */
             ap_d = a * (1 + ecc);
             n = 2 * VSO_PI / period;
         } else {
@@ -401,11 +401,10 @@ void vso_calc_orb_one(int with_coi, int64_t body, int64_t ref, const double *mas
             else pe_d = a;
             period = 0;
             ap_d = 0;
-            double aa = fabs(a);
-            n = sqrt(u / (aa * aa * aa));
+            n = sqrt(u / pow(fabs(a), 3.0));
         }
     } else {
-        period = (2 * VSO_PI * sqrt(a * a * a / u)) / 10;
+        period = (2 * VSO_PI * sqrt(pow(a, 3.0) / u)) / 10;
         pe_d = a * (1 - ecc);
         ap_d = 0;
         n = 2 * VSO_PI / period;
@@ -1000,4 +999,267 @@ void vso_vessel_points(int64_t nsel, const int64_t *sel, int64_t nb, const doubl
             for (int k = 0; k < 5; ++k) ce[1 + k] = best_row[k];
         }
     }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * N2 per-tick vessel events: phys_vessel.Physics.check_warp (:506-560), predict_enter_coi_service
+ * (:744-758, which vessels it re-predicts) and cross_coi (:563-632) with convert.kepler_to_velocity
+ * (convert.py:20-64), convert.velocity_to_kepler (:67-131), phys_shared.point_between (:67-80),
+ * compare_coord (:35-55) and orb2xy (:187-199). */
+int vso_point_between(double n, double a, double b, double dir)
+{
+    n = py_mod(n, 2 * VSO_PI);
+    a = py_mod(a, 2 * VSO_PI);
+    b = py_mod(b, 2 * VSO_PI);
+    if (dir < 0) { double t = a; a = b; b = t; }
+    if (a == b) return a == n;
+    if (a < b) return a <= n && n <= b;
+    return a <= n || n <= b;
+}
+
+/* sort_intersect_indices(ea, pts, dir)[0]: index of the nearest non-NaN point, -1 when all NaN */
+static int first_intersect(double ea_vessel, const double *pts, int cnt, double dir)
+{
+    int best = -1;
+    double best_ang = 0;
+    for (int k = 0; k < cnt; ++k) {
+        if (isnan(pts[k])) continue;
+        double ang = fabs(ea_vessel - pts[k]);
+        if (ea_vessel > pts[k]) ang = 2 * VSO_PI - ang;
+        if (dir < 0) ang = VSO_PI * 2 - ang;
+        if (best < 0 || ang < best_ang) { best = k; best_ang = ang; }
+    }
+    return best;
+}
+
+/* check_warp: hold (nv bytes) is the membership mask of physical_hold, updated in place.
+ * out3 = situation (-1 = None), alarm_vessel (-1 = None), len(physical_hold). */
+void vso_check_warp(int64_t nv, const double *ecc, const double *dr, const double *ea,
+                    const double *ma, const double *n, const double *body_impact,
+                    const double *body_enter_atm, const double *coi_leave, const double *coi_enter,
+                    double warp, unsigned char *hold, int64_t *out3)
+{
+    int64_t situation = -1, alarm = -1, cnt = 0;
+    for (int64_t v = 0; v < nv; ++v) {
+        const double all[5] = {body_impact[2 * v], body_enter_atm[2 * v], body_enter_atm[2 * v + 1],
+                               coi_enter[6 * v + 1], coi_leave[2 * v]};
+        const int nx = first_intersect(ea[v], all, 5, dr[v]);
+        if (nx >= 0) {
+            double ea2;
+            if (ecc[v] < 1) ea2 = vso_solve_kepler_ell(ecc[v], ma[v] + n[v] * warp * dr[v] * 2, 1e-10);
+            else ea2 = vso_newton_root_kepler_hyp(ecc[v], ma[v] + n[v] * warp * dr[v] * -1 * 2, ea[v]);
+            if (vso_point_between(all[nx], ea[v], ea2, dr[v])) {
+                alarm = v;
+                if (nx <= 1) { hold[v] = 1; situation = nx; }
+                else if (nx == 2) { hold[v] = 0; situation = 2; }
+                else situation = 3;
+            } else {
+                hold[v] = 0;
+            }
+        } else {
+            hold[v] = 0;
+        }
+        cnt += hold[v];
+    }
+    out3[0] = situation; out3[1] = alarm; out3[2] = cnt;
+}
+
+/* predict_enter_coi_service: flags[v] = 1 where points(v, True) is re-run */
+void vso_enter_coi_service(int64_t nv, const double *dr, const double *prev_ea, const double *ea,
+                           const double *coi_enter, int any_crossing_pending, unsigned char *flags)
+{
+    for (int64_t v = 0; v < nv; ++v) {
+        flags[v] = 0;
+        if (!isnan(coi_enter[6 * v]) || any_crossing_pending) continue;
+        if (vso_point_between(0.0, prev_ea[v], ea[v], dr[v]) ||
+            vso_point_between(VSO_PI, prev_ea[v], ea[v], dr[v])) flags[v] = 1;
+    }
+}
+
+/* cross_coi, detection part: first vessel whose next point is a COI crossing passed this tick.
+ * out2 = vessel (-1 = none), kind (1 = enter, 2 = leave). */
+void vso_cross_scan(int64_t nv, const double *ecc, const double *dr, const double *prev_ea,
+                    const double *ea, const double *body_impact, const double *coi_leave,
+                    const double *coi_enter, int64_t *out2)
+{
+    out2[0] = -1; out2[1] = 0;
+    for (int64_t v = 0; v < nv; ++v) {
+        const int ell = ecc[v] < 1;
+        const double all[3] = {body_impact[2 * v + (ell ? 0 : 1)], coi_enter[6 * v + 1],
+                               coi_leave[2 * v]};
+        const int nx = first_intersect(prev_ea[v], all, 3, dr[v]);
+        if (nx == 2 && vso_point_between(all[2], prev_ea[v], ea[v], dr[v])) {
+            out2[0] = v; out2[1] = 2; return;
+        }
+        if (nx == 1 && vso_point_between(all[1], prev_ea[v], ea[v], dr[v])) {
+            out2[0] = v; out2[1] = 1; return;
+        }
+    }
+}
+
+static void ps_orb2xy(double a, double b, double f, double ecc, double pea, double rx, double ry,
+                      double ea, double *out)
+{ /* phys_shared.py:187-199; ea == 0 gives (0, 0) WITHOUT the reference position */
+    if (ea == 0) { out[0] = 0; out[1] = 0; return; }
+    double xn, yn;
+    if (ecc < 1) { xn = a * cos(ea) - f; yn = b * sin(ea); }
+    else { xn = a * cosh(ea) - f; yn = b * sinh(ea); }
+    out[0] = (xn * cos(pea - VSO_PI) - yn * sin(pea - VSO_PI)) + rx;
+    out[1] = (xn * sin(pea - VSO_PI) + yn * cos(pea - VSO_PI)) + ry;
+}
+
+static double ps_compare(double a, double b)
+{
+    if (a == b) return 0.0;
+    if (a == 0 || b == 0) return 100.0;
+    if ((a > 0 && b > 0) || (a < 0 && b < 0)) {
+        a = fabs(a); b = fabs(b);
+        return fabs(a - b) / (a > b ? a : b) * 100;
+    }
+    return 100;
+}
+
+void vso_kepler_to_velocity(const double *rel_pos, double a, double ecc, double pe_arg, double u,
+                            double dr, double *out2)
+{
+    const double sin_p = sin(pe_arg), cos_p = cos(pe_arg), sc = sin_p * cos_p,
+                 sin_p2 = sin_p * sin_p, cos_p2 = cos_p * cos_p;
+    double angle;
+    if (ecc < 1) {
+        const double b = a * sqrt(1 - ecc * ecc), f = sqrt(a * a - b * b);
+        const double a2 = a * a, b2 = b * b;
+        const double frx = f * cos_p, fry = f * sin_p;
+        const double px = rel_pos[0] - f * cos_p, py = rel_pos[1] - f * sin_p;
+        angle = atan(-(b2 * px * cos_p2 + a2 * px * sin_p2 + b2 * py * sc - a2 * py * sc) /
+                     (a2 * py * cos_p2 + b2 * py * sin_p2 + b2 * px * sc - a2 * px * sc));
+        const double x_max = sqrt(a2 * cos(2 * pe_arg) + a2 - b2 * cos(2 * pe_arg) + b2) / sqrt(2.0) - 1e-06;
+        const double x2 = x_max * x_max, c4 = cos_p2 * cos_p2, s4 = sin_p2 * sin_p2;
+        const double y_max = (a * b * sqrt(-x2 * (c4 + s4) - 2 * x2 * cos_p2 * sin_p2 + b2 * sin_p2 + a2 * cos_p2) +
+                              a2 * x_max * sin_p * cos_p - b2 * x_max * sin_p * cos_p) /
+                             (a2 * cos_p2 + b2 * sin_p2);
+        const double x1 = x_max + frx, y1 = y_max + fry, xx2 = -x_max + frx, y2 = -y_max + fry;
+        if (((xx2 - x1) * (rel_pos[1] - y1)) - ((y2 - y1) * (rel_pos[0] - x1)) < 0) angle += VSO_PI;
+    } else {
+        const double f = a * ecc, b = sqrt(f * f - a * a), a2 = a * a, b2 = b * b;
+        const double frx = f * cos_p, fry = f * sin_p;
+        const double px = rel_pos[0] - f * cosh(pe_arg), py = rel_pos[1] - f * sinh(pe_arg);
+        angle = atan(-(b2 * px * cos_p2 - a2 * px * sin_p2 + b2 * py * sc + a2 * py * sc) /
+                     (-a2 * py * cos_p2 + b2 * py * sin_p2 + b2 * px * sc + a2 * px * sc));
+        const double arg = a2 * cos(2 * pe_arg) + a2 + b2 * cos(2 * pe_arg) - b2;
+        if (arg >= 0) {
+            const double x_max = sqrt(arg) / sqrt(2.0) - 1e-06;
+            const double x2 = x_max * x_max, c4 = cos_p2 * cos_p2, s4 = sin_p2 * sin_p2;
+            const double y_max = -((a * b * sqrt(-x2 * (c4 + s4) + 2 * x2 * cos_p2 * sin_p2 + b2 * sin_p2 - a2 * cos_p2) +
+                                    a2 * x_max * sin_p * cos_p + b2 * x_max * sin_p * cos_p) /
+                                   (-a2 * cos_p2 + b2 * sin_p2));
+            const double x1 = x_max + frx, y1 = y_max + fry, xx2 = -x_max + frx, y2 = -y_max + fry;
+            if (((xx2 - x1) * (rel_pos[1] - y1)) - ((y2 - y1) * (rel_pos[0] - x1)) < 0) angle += VSO_PI;
+        } else if (VSO_PI <= pe_arg && pe_arg < 2 * VSO_PI) {   /* except ValueError */
+            angle += VSO_PI;
+        }
+    }
+    angle = py_mod(angle, 2 * VSO_PI);
+    const double distance = sqrt(rel_pos[0] * rel_pos[0] + rel_pos[1] * rel_pos[1]);
+    const double speed = dr * sqrt(u * ((2 / distance) - (1 / a)));
+    out2[0] = speed * cos(angle);
+    out2[1] = speed * sin(angle);
+}
+
+/* out5 = a, ecc, pe_arg, ma, dr */
+void vso_velocity_to_kepler(const double *rel_pos, const double *rel_vel_in, double u, int failsafe,
+                            double *out5)
+{
+    const double px = rel_pos[0], py = rel_pos[1];
+    double vx = rel_vel_in[0], vy = rel_vel_in[1];
+    const double mp = sqrt(px * px + py * py);
+    const double a = -1 * u / (2 * ((vx * vx + vy * vy) / 2 - u / mp));
+    const double mom = px * vy - py * vx;
+    { double t = vx; vx = vy; vy = -t; }                 /* rel_vel[0], rel_vel[1] = rel_vel[1], -rel_vel[0] */
+    const double ex = (vx * mom / u) - px / mp, ey = (vy * mom / u) - py / mp;
+    const double ecc = sqrt(ex * ex + ey * ey);
+    double pe_arg = py_mod((3 * VSO_PI / 2) + atan2(-ex, ey), 2 * VSO_PI);
+    const double dr = copysign(1.0, mom);
+    double ta = py_mod(pe_arg - (atan2(py, px) - VSO_PI), 2 * VSO_PI);
+    if (dr > 0) ta = 2 * VSO_PI - ta;
+    double ea, ma, f = 0, b = 0, np_[2];
+    if (ecc < 1) {
+        ea = acos((ecc + cos(ta)) / (1 + (ecc * cos(ta))));
+        if (VSO_PI < ta && ta < 2 * VSO_PI) ea = 2 * VSO_PI - ea;
+        ma = py_mod(ea - ecc * sin(ea), 2 * VSO_PI);
+        if (failsafe) {
+            const double new_ea = vso_solve_kepler_ell(ecc, ma, 1e-10);
+            f = a * ecc;
+            b = sqrt(fabs(f * f - a * a));
+            ps_orb2xy(a, b, f, ecc, pe_arg, 0, 0, new_ea, np_);
+            if ((ps_compare(px, np_[0]) + ps_compare(py, np_[1])) / 2 > 1) {
+                ea = 2 * VSO_PI - ea;
+                ma = py_mod(ea - ecc * sin(ea), 2 * VSO_PI);
+            }
+        }
+    } else {
+        ea = acosh((ecc + cos(ta)) / (1 + (ecc * cos(ta))));
+        ma = ecc * sinh(ea) - ea;
+        if (failsafe) {
+            const double new_ea = vso_newton_root_kepler_hyp(ecc, ma, ma);
+            f = a * ecc;
+            b = sqrt(fabs(f * f - a * a));
+            ps_orb2xy(a, b, f, ecc, pe_arg, 0, 0, new_ea, np_);
+            if ((ps_compare(px, np_[0]) + ps_compare(py, np_[1])) / 2 > 1) {
+                ea = -ea;
+                ma = -ma;
+            }
+        }
+    }
+    if (failsafe == 2) {
+        { double t = vx; vx = -vy; vy = t; }             /* undo the swap */
+        const double va = py_mod(atan2(vy, vx), 2 * VSO_PI), pa = py_mod(atan2(py, px), 2 * VSO_PI);
+        if (sin(3 * VSO_PI / 2 + va - pa) < 0) {
+            if (ecc < 1) {
+                ea = 2 * VSO_PI - ea;
+                ma = py_mod(ea - ecc * sin(ea), 2 * VSO_PI);
+            } else {
+                ea = -ea;
+                ma = -ma;
+            }
+            pe_arg = py_mod(pe_arg + VSO_PI, 2 * VSO_PI);
+            ps_orb2xy(a, b, f, ecc, pe_arg, 0, 0, ea, np_);
+            const double npa = py_mod(atan2(np_[1], np_[0]), 2 * VSO_PI);
+            pe_arg = pe_arg - (npa - pa);
+        }
+    }
+    out5[0] = a; out5[1] = ecc; out5[2] = pe_arg; out5[3] = ma; out5[4] = dr;
+}
+
+/* cross_coi, the orbit change of one vessel (:585-629).  vessel8 = a b f ecc pea u dr ea_cross;
+ * body rows of body7 = a ecc pea dr mass pos_x pos_y.  kind 2 = leave (new_ref = body_ref[ref]),
+ * 1 = enter (new_ref given).  out6 = a, ecc, pea, ma, dr, new_ref; returns 0, or 1 when the
+ * reference returns None (enter with ref == new_ref). */
+int vso_cross_apply(int kind, const double *vessel8, int64_t ref, int64_t new_ref,
+                    const double *body7, double gc, double *out6)
+{
+    const double a = vessel8[0], b = vessel8[1], f = vessel8[2], ecc = vessel8[3], pea = vessel8[4],
+                 u = vessel8[5], dr = vessel8[6], eax = vessel8[7];
+    const double *R = body7 + 7 * ref, *N = body7 + 7 * new_ref;
+    if (kind == 1 && ref == new_ref) return 1;
+    const double new_u = gc * N[4];
+    double vabs[2], vrel[2], vv[2], rv[2], npos[2], nvel[2], rrel[2];
+    ps_orb2xy(a, b, f, ecc, pea, R[5], R[6], eax, vabs);
+    vrel[0] = vabs[0] - R[5]; vrel[1] = vabs[1] - R[6];
+    if (kind == 2) {
+        rrel[0] = R[5] - N[5]; rrel[1] = R[6] - N[6];
+        vso_kepler_to_velocity(vrel, a, ecc, pea, u, dr, vv);
+        vso_kepler_to_velocity(rrel, R[0], R[1], R[2], new_u, R[3], rv);
+        npos[0] = vrel[0] + rrel[0]; npos[1] = vrel[1] + rrel[1];
+        nvel[0] = vv[0] + rv[0]; nvel[1] = vv[1] + rv[1];
+        vso_velocity_to_kepler(npos, nvel, new_u, 1, out6);
+    } else {
+        rrel[0] = N[5] - R[5]; rrel[1] = N[6] - R[6];
+        vso_kepler_to_velocity(vrel, a, ecc, pea, u, dr, vv);
+        vso_kepler_to_velocity(rrel, N[0], N[1], N[2], new_u, N[3], rv);
+        npos[0] = vrel[0] - rrel[0]; npos[1] = vrel[1] - rrel[1];
+        nvel[0] = vv[0] - rv[0]; nvel[1] = vv[1] - rv[1];
+        vso_velocity_to_kepler(npos, nvel, new_u, 2, out6);
+    }
+    out6[5] = (double)new_ref;
+    return 0;
 }

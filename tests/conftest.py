@@ -55,3 +55,38 @@ def apply_edit(ph, k):
         ph.set_body_mass(4, 5.0e5)
     elif k == 9:
         ph.del_body(0)
+
+
+# ---- vessel_events fixture helpers (column layout written by oracle/gen_golden.py) ----------
+# state columns: a b f ecc pea n dr ma ea prev_ea u pe_d ap_d period
+VS = dict(a=0, b=1, f=2, ecc=3, pea=4, n=5, dr=6, ma=7, ea=8, prev_ea=9, u=10, pe_d=11, ap_d=12,
+          period=13)
+
+
+def split_points(p):
+    """(nv,12) -> body_impact (nv,2), body_enter_atm (nv,2), coi_leave (nv,2), coi_enter (nv,6)."""
+    import numpy as np
+    return tuple(np.ascontiguousarray(x) for x in (p[:, 0:2], p[:, 2:4], p[:, 4:6], p[:, 6:12]))
+
+
+def events_body7(g, bpos):
+    """Body rows of the cross_coi orbit change: a ecc pea dr mass pos_x pos_y."""
+    import numpy as np
+    bs = g["body_static"]
+    return np.stack([bs[:, 0], bs[:, 3], bs[:, 4], bs[:, 6], g["body_mass"], bpos[:, 0], bpos[:, 1]],
+                    axis=1)
+
+
+def events_body12(g, bma, bea):
+    """Body rows of points(): a b f ecc ma ea pea n dr coi size atm."""
+    import numpy as np
+    bs = g["body_static"]
+    return np.stack([bs[:, 0], bs[:, 1], bs[:, 2], bs[:, 3], bma, bea, bs[:, 4], bs[:, 5], bs[:, 6],
+                     bs[:, 7], bs[:, 8], bs[:, 9]], axis=1)
+
+
+def events_vessel12(v):
+    """State columns -> the vessel rows of points(): a b f ecc ma ea pea n dr pe_d ap_d period."""
+    import numpy as np
+    return np.stack([v[:, 0], v[:, 1], v[:, 2], v[:, 3], v[:, 7], v[:, 8], v[:, 4], v[:, 5], v[:, 6],
+                     v[:, 11], v[:, 12], v[:, 13]], axis=1)

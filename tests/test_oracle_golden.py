@@ -357,3 +357,72 @@ def test_vessel_points(oracle):
         want = g["var%d_rows" % k]
         lo = 4 if kw["only_enter_coi"] else 0       # only_enter_coi leaves the first two alone
         assert np.array_equal(got[lo:], want[lo:], equal_nan=True), (k, row)
+
+
+def test_vessel_events(oracle):
+    """N2 per-tick events: check_warp, predict_enter_coi_service, cross_coi and change_vessel
+    against snapshots of the live reference's game loop (game.py:1165-1265)."""
+    from conftest import VS, events_body7, events_body12, events_vessel12, split_points
+    g = golden("vessel_events")
+    opt = lambda x: None if x < 0 else int(x)
+    situations = set()
+    for k in range(int(g["n_cw"])):
+        v, o = g["cw%d_v" % k], g["cw%d_out" % k]
+        bi, ba, cl, ce = split_points(g["cw%d_p" % k])
+        got, hold = oracle.check_warp(v[:, VS["ecc"]], v[:, VS["dr"]], v[:, VS["ea"]], v[:, VS["ma"]],
+                                      v[:, VS["n"]], bi, ba, cl, ce, o[3], g["cw%d_hold_in" % k])
+        assert got == (opt(o[0]), opt(o[1]), int(o[2])), k
+        assert np.array_equal(hold, g["cw%d_hold_out" % k]), k
+        situations.add(got[0])
+    assert {0, 1, 2, 3, None} <= situations
+    assert len({int(g["cw%d_out" % k][3]) for k in range(int(g["n_cw"]))}) >= 3    # several warps
+    for k in range(int(g["n_sv"])):
+        v, fl = g["sv%d_v" % k], g["sv%d_flags" % k]
+        ce = split_points(g["sv%d_p" % k])[3]
+        calls = oracle.enter_coi_service(v[:, VS["dr"]], v[:, VS["prev_ea"]], v[:, VS["ea"]], ce,
+                                         opt(fl[0]), opt(fl[1]))
+        assert np.array_equal(calls, g["sv%d_calls" % k]), k
+    kinds = set()
+    for k in range(int(g["n_cx"])):
+        v, ref, ret = g["cx%d_v" % k], g["cx%d_ref" % k], int(g["cx%d_ret" % k][0])
+        bi, ba, cl, ce = split_points(g["cx%d_p" % k])
+        ves, kind = oracle.cross_scan(v[:, VS["ecc"]], v[:, VS["dr"]], v[:, VS["prev_ea"]],
+                                      v[:, VS["ea"]], bi, cl, ce)
+        res = None
+        if ves is not None:
+            r = int(ref[ves])
+            new_ref = int(g["body_ref"][r]) if kind == 2 else int(ce[ves, 0])
+            eax = cl[ves, 0] if kind == 2 else ce[ves, 1]
+            row = v[ves]
+            res = oracle.cross_apply(kind, [row[0], row[1], row[2], row[3], row[4], row[10], row[6],
+                                            eax], r, new_ref, events_body7(g, g["cx%d_bpos" % k]),
+                                     float(g["gc"]))
+            kinds.add(kind)
+        assert (-1 if res is None else ves) == ret, k
+        if ret >= 0:
+            vo = g["cx%d_row_out" % k]
+            want = np.array([vo[0], vo[3], vo[4], vo[7], vo[6], g["cx%d_ref_out" % k][0]])
+            np.testing.assert_allclose(res, want, rtol=1e-12, atol=0, err_msg=str(k))
+    assert kinds == {1, 2}
+    for k in range(int(g["n_cv"])):
+        v, ves, ref = g["cv%d_v" % k].copy(), int(g["cv%d_vessel" % k][0]), g["cv%d_ref" % k]
+        fl, vo = g["cv%d_flags" % k], g["cv%d_row_out" % k]
+        orb = oracle.calc_orb("vessel", ref[ves:ves + 1], g["body_mass"], None, float(g["gc"]), 0.0,
+                              v[ves:ves + 1, 0], v[ves:ves + 1, 3])
+        mine = np.array([orb[key][0] for key in ("b", "f", "n", "u", "pe_d", "ap_d", "period")])
+        assert np.array_equal(mine, vo[[1, 2, 5, 10, 11, 12, 13]]), k
+        ecc, ma = v[ves, 3], v[ves, 7]
+        ea = oracle.solve_kepler_ell(ecc, ma) if ecc < 1 else oracle.newton_root_kepler_hyp(ecc, ma, ma)
+        assert ea == vo[8], k
+        v[ves, [1, 2, 5, 10, 11, 12, 13]] = mine
+        v[ves, 8] = ea
+        bi, ba, cl, ce = oracle.vessel_points(
+            events_vessel12(v), ref, events_body12(g, g["cv%d_bma" % k], g["cv%d_bea" % k]),
+            g["body_ref"], sel=[ves], entered_coi=opt(fl[0]), left_coi=opt(fl[1]),
+            left_coi_prev_ref=opt(fl[2]), steps_limit=int(g["steps_limit"]),
+            coi_leave=np.ascontiguousarray(g["cv%d_p" % k][:, 4:6]))
+        got = np.concatenate([bi[ves], ba[ves], cl[ves], ce[ves]])
+        assert np.array_equal(got, g["cv%d_p_row_out" % k], equal_nan=True), k
+        t = np.linspace(-np.pi, np.pi, int(g["P"]))
+        np.testing.assert_allclose(oracle.curve_points(ecc, v[ves, 0], mine[0], v[ves, 4], t),
+                                   g["cv%d_curve" % k], rtol=1e-13, atol=1e-9, equal_nan=True)
