@@ -319,6 +319,40 @@ int vsb_host_running_sum(double x0, double c, int64_t kmax, int bounded, double 
                          const int64_t *ks, double *xs, int64_t *K_out, int64_t *nseg_out);
 int vsb_march_stats(vsb_ctx *ctx, uint64_t *out3);
 
+/* --------------------------------------------- per-tick vessel events
+ * The serial per-vessel loops of the game tick (game.py:1165-1265) as order-preserving parallel
+ * scans over host arrays of nv vessels; body_impact / body_enter_atm / coi_leave are (nv,2),
+ * coi_enter (nv,6), as filled by vsb_host_vessel_points.
+ *
+ * check_warp: phys_vessel.Physics.check_warp(warp), phys_vessel.py:506-560.  hold (nv bytes) is
+ * the membership mask of `physical_hold`, updated in place.  out3 = situation (0 impact,
+ * 1 entering atmosphere, 2 leaving atmosphere, 3 crossing COI; -1 = None), alarm_vessel (the last
+ * vessel raising one, -1 = None), len(physical_hold). */
+int vsb_host_check_warp(vsb_ctx *ctx, int64_t nv, const double *ecc, const double *dr,
+                        const double *ea, const double *ma, const double *n_motion,
+                        const double *body_impact, const double *body_enter_atm,
+                        const double *coi_leave, const double *coi_enter, double warp,
+                        uint8_t *hold, int64_t *out3);
+/* predict_enter_coi_service, phys_vessel.py:744-758: flags_out[v] = 1 for the vessels it calls
+ * points(v, True) on (feed them to vsb_host_vessel_points as `sel`); crossing_pending != 0 when
+ * entered_coi or left_coi is set (the service then does nothing). */
+int vsb_host_enter_coi_service(vsb_ctx *ctx, int64_t nv, const double *dr, const double *prev_ea,
+                               const double *ea, const double *coi_enter, int crossing_pending,
+                               uint8_t *flags_out);
+/* cross_coi, phys_vessel.py:563-632, detection: out2 = the FIRST vessel whose next orbit point is
+ * a COI crossing passed between prev_ea and ea (-1 = none), kind (1 enter, 2 leave). */
+int vsb_host_cross_scan(vsb_ctx *ctx, int64_t nv, const double *ecc, const double *dr,
+                        const double *prev_ea, const double *ea, const double *body_impact,
+                        const double *coi_leave, const double *coi_enter, int64_t *out2);
+/* cross_coi, the orbit change (:577-629) with convert.kepler_to_velocity / velocity_to_kepler
+ * (convert.py:20-131), for nev events at once.  vessel8 (nev,8) = a b f ecc pea u dr ea_cross;
+ * ref / new_ref: current and new reference body; body7 (nb,7) = a ecc pea dr mass pos_x pos_y.
+ * out6 (nev,6) = a ecc pea ma dr new_ref; status[i] = 1 where the reference returns None
+ * (entering the body the vessel already orbits). */
+int vsb_host_cross_apply(vsb_ctx *ctx, int64_t nev, const int32_t *kind, const double *vessel8,
+                         const int64_t *ref, const int64_t *new_ref, int64_t nb,
+                         const double *body7, double gc, double *out6, int32_t *status);
+
 /* --------------------------------------------- per-frame body passes
  * Physics.body (phys_editor.py:577-599, without the radius, which stays host numpy),
  * Physics.temp_color (:602-651) and Physics.classify (:654-670) in one pass over host arrays.

@@ -101,6 +101,10 @@ SIGNATURES = {
     "vsb_host_predict_enter_coi": [_ctx, _i64, _pv, _pv, _f64, _i64, _pv],
     "vsb_host_vessel_points": [_ctx, _i64, _i64, _pv, _pv, _pv, _pv, _i64, _pv, _i64, _i64, _i64,
                                C.c_int, _i64, _pv, _pv, _pv, _pv],
+    "vsb_host_check_warp": [_ctx, _i64] + [_pv] * 9 + [_f64, _pv, _pv],
+    "vsb_host_enter_coi_service": [_ctx, _i64, _pv, _pv, _pv, _pv, C.c_int, _pv],
+    "vsb_host_cross_scan": [_ctx, _i64] + [_pv] * 7 + [_pv],
+    "vsb_host_cross_apply": [_ctx, _i64, _pv, _pv, _pv, _pv, _i64, _pv, _f64, _pv, _pv],
     "vsb_set_march_mode": [_ctx, C.c_int],
     "vsb_host_running_sum": [_f64, _f64, _i64, C.c_int, _f64, _i64, _pv, _pv, _pv, _pv],
     "vsb_march_stats": [_ctx, _pv],

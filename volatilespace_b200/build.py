@@ -32,6 +32,7 @@ SOURCES = {
     "vsb_body.cu": ["-fmad=false"],
     "vsb_convert.cu": ["-fmad=false"],
     "vsb_intersect.cu": ["-fmad=false"],
+    "vsb_events.cu": ["-fmad=false"],
 }
 
 
@@ -51,7 +52,8 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "vsb_common.cuh"), INCLUDE, os.path.abspath(__file__)]
+    headers = [os.path.join(CSRC, "vsb_common.cuh"), os.path.join(CSRC, "vsb_orbit_math.cuh"), INCLUDE,
+               os.path.abspath(__file__)]
     objs, procs = [], []
     env = dict(os.environ)
     env.pop("CC", None)    # the image exports a gcc wrapper nvcc should not pick up

@@ -1387,6 +1387,164 @@ extern "C" int vsb_host_vessel_points(vsb_ctx *c, int64_t nv, int64_t nb, const 
     return d2h(c, coi_enter, base + o_en, 48 * NV);
 }
 
+// ---------------------------------------------------------------- N2: per-tick vessel events
+// staging helper: consecutive 256-byte aligned device arrays inside host_stage
+struct stage_cursor {
+    char *base;
+    size_t off = 0;
+    void *take(size_t bytes)
+    {
+        void *p = base + off;
+        off += (bytes + 255) / 256 * 256;
+        return p;
+    }
+};
+
+static int up_f64(vsb_ctx *c, double *dst, const double *src, size_t count)
+{
+    if (count == 0) return VSB_OK;
+    VSB_CUDA(cudaMemcpyAsync(dst, src, 8 * count, cudaMemcpyHostToDevice, c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_host_check_warp(vsb_ctx *c, int64_t nv, const double *ecc, const double *dr,
+                                   const double *ea, const double *ma, const double *n_motion,
+                                   const double *body_impact, const double *body_enter_atm,
+                                   const double *coi_leave, const double *coi_enter, double warp,
+                                   uint8_t *hold, int64_t *out3)
+{
+    CTX(c);
+    VSB_CHECK(nv >= 0 && out3, VSB_ERR_ARG, "vsb_host_check_warp: bad argument");
+    out3[0] = out3[1] = -1;
+    out3[2] = 0;
+    if (nv == 0) return VSB_OK;
+    VSB_CHECK(ecc && dr && ea && ma && n_motion && body_impact && body_enter_atm && coi_leave &&
+                  coi_enter && hold,
+              VSB_ERR_ARG, "vsb_host_check_warp: null array");
+    const size_t N = (size_t)nv;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * 17 * N + N + 20 * 256));
+    stage_cursor sc{(char *)c->host_stage.p};
+    double *d5[5];
+    const double *h5[5] = {ecc, dr, ea, ma, n_motion};
+    for (int k = 0; k < 5; ++k) {
+        d5[k] = (double *)sc.take(8 * N);
+        VSB_TRY(up_f64(c, d5[k], h5[k], N));
+    }
+    double *d_imp = (double *)sc.take(16 * N), *d_atm = (double *)sc.take(16 * N),
+           *d_lv = (double *)sc.take(16 * N), *d_en = (double *)sc.take(48 * N);
+    VSB_TRY(up_f64(c, d_imp, body_impact, 2 * N));
+    VSB_TRY(up_f64(c, d_atm, body_enter_atm, 2 * N));
+    VSB_TRY(up_f64(c, d_lv, coi_leave, 2 * N));
+    VSB_TRY(up_f64(c, d_en, coi_enter, 6 * N));
+    unsigned char *d_hold = (unsigned char *)sc.take(N);
+    unsigned long long *d_key = (unsigned long long *)sc.take(16);
+    VSB_CUDA(cudaMemcpyAsync(d_hold, hold, N, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_check_warp(c, nv, d5[0], d5[1], d5[2], d5[3], d5[4], d_imp, d_atm, d_lv, d_en,
+                                  warp, d_hold, d_key));
+    unsigned long long key[2];
+    VSB_CUDA(cudaMemcpyAsync(hold, d_hold, N, cudaMemcpyDeviceToHost, c->stream));
+    VSB_TRY(d2h(c, key, d_key, 16));
+    if (key[0]) {
+        out3[0] = (int64_t)(key[0] & 3);
+        out3[1] = (int64_t)(key[0] >> 2) - 1;
+    }
+    out3[2] = (int64_t)key[1];
+    return VSB_OK;
+}
+
+extern "C" int vsb_host_enter_coi_service(vsb_ctx *c, int64_t nv, const double *dr,
+                                          const double *prev_ea, const double *ea,
+                                          const double *coi_enter, int crossing_pending,
+                                          uint8_t *flags_out)
+{
+    CTX(c);
+    VSB_CHECK(nv >= 0, VSB_ERR_ARG, "vsb_host_enter_coi_service: bad argument");
+    if (nv == 0) return VSB_OK;
+    VSB_CHECK(dr && prev_ea && ea && coi_enter && flags_out, VSB_ERR_ARG,
+              "vsb_host_enter_coi_service: null array");
+    const size_t N = (size_t)nv;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * 9 * N + N + 8 * 256));
+    stage_cursor sc{(char *)c->host_stage.p};
+    double *d_dr = (double *)sc.take(8 * N), *d_pe = (double *)sc.take(8 * N),
+           *d_ea = (double *)sc.take(8 * N), *d_en = (double *)sc.take(48 * N);
+    unsigned char *d_fl = (unsigned char *)sc.take(N);
+    VSB_TRY(up_f64(c, d_dr, dr, N));
+    VSB_TRY(up_f64(c, d_pe, prev_ea, N));
+    VSB_TRY(up_f64(c, d_ea, ea, N));
+    VSB_TRY(up_f64(c, d_en, coi_enter, 6 * N));
+    VSB_TRY(vsb_launch_enter_coi_service(c, nv, d_dr, d_pe, d_ea, d_en, crossing_pending, d_fl));
+    return d2h(c, flags_out, d_fl, N);
+}
+
+extern "C" int vsb_host_cross_scan(vsb_ctx *c, int64_t nv, const double *ecc, const double *dr,
+                                   const double *prev_ea, const double *ea,
+                                   const double *body_impact, const double *coi_leave,
+                                   const double *coi_enter, int64_t *out2)
+{
+    CTX(c);
+    VSB_CHECK(nv >= 0 && out2, VSB_ERR_ARG, "vsb_host_cross_scan: bad argument");
+    out2[0] = -1;
+    out2[1] = 0;
+    if (nv == 0) return VSB_OK;
+    VSB_CHECK(ecc && dr && prev_ea && ea && body_impact && coi_leave && coi_enter, VSB_ERR_ARG,
+              "vsb_host_cross_scan: null array");
+    const size_t N = (size_t)nv;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * 14 * N + 12 * 256));
+    stage_cursor sc{(char *)c->host_stage.p};
+    double *d4[4];
+    const double *h4[4] = {ecc, dr, prev_ea, ea};
+    for (int k = 0; k < 4; ++k) {
+        d4[k] = (double *)sc.take(8 * N);
+        VSB_TRY(up_f64(c, d4[k], h4[k], N));
+    }
+    double *d_imp = (double *)sc.take(16 * N), *d_lv = (double *)sc.take(16 * N),
+           *d_en = (double *)sc.take(48 * N);
+    unsigned long long *d_key = (unsigned long long *)sc.take(8);
+    VSB_TRY(up_f64(c, d_imp, body_impact, 2 * N));
+    VSB_TRY(up_f64(c, d_lv, coi_leave, 2 * N));
+    VSB_TRY(up_f64(c, d_en, coi_enter, 6 * N));
+    VSB_TRY(vsb_launch_cross_scan(c, nv, d4[0], d4[1], d4[2], d4[3], d_imp, d_lv, d_en, d_key));
+    unsigned long long key;
+    VSB_TRY(d2h(c, &key, d_key, 8));
+    if (key != ~0ull) {
+        out2[0] = (int64_t)(key >> 2);
+        out2[1] = (int64_t)(key & 3);
+    }
+    return VSB_OK;
+}
+
+extern "C" int vsb_host_cross_apply(vsb_ctx *c, int64_t nev, const int32_t *kind,
+                                    const double *vessel8, const int64_t *ref,
+                                    const int64_t *new_ref, int64_t nb, const double *body7,
+                                    double gc, double *out6, int32_t *status)
+{
+    CTX(c);
+    VSB_CHECK(nev >= 0 && nb >= 0, VSB_ERR_ARG, "vsb_host_cross_apply: bad argument");
+    if (nev == 0) return VSB_OK;
+    VSB_CHECK(kind && vessel8 && ref && new_ref && body7 && out6 && status && nb > 0, VSB_ERR_ARG,
+              "vsb_host_cross_apply: null array");
+    for (int64_t i = 0; i < nev; ++i)
+        VSB_CHECK((kind[i] == 1 || kind[i] == 2) && ref[i] >= 0 && ref[i] < nb && new_ref[i] >= 0 &&
+                      new_ref[i] < nb,
+                  VSB_ERR_ARG, "vsb_host_cross_apply: event %lld: bad kind or body index",
+                  (long long)i);
+    const size_t E = (size_t)nev, B = (size_t)nb;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * (16 * E + 7 * B) + 8 * E + 12 * 256));
+    stage_cursor sc{(char *)c->host_stage.p};
+    double *d_v8 = (double *)sc.take(64 * E), *d_b7 = (double *)sc.take(56 * B),
+           *d_out = (double *)sc.take(48 * E);
+    int64_t *d_ref = (int64_t *)sc.take(8 * E), *d_new = (int64_t *)sc.take(8 * E);
+    int32_t *d_kind = (int32_t *)sc.take(4 * E), *d_st = (int32_t *)sc.take(4 * E);
+    VSB_TRY(up_f64(c, d_v8, vessel8, 8 * E));
+    VSB_TRY(up_f64(c, d_b7, body7, 7 * B));
+    VSB_CUDA(cudaMemcpyAsync(d_ref, ref, 8 * E, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_new, new_ref, 8 * E, cudaMemcpyHostToDevice, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(d_kind, kind, 4 * E, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_cross_apply(c, nev, d_kind, d_v8, d_ref, d_new, d_b7, gc, d_out, d_st));
+    VSB_CUDA(cudaMemcpyAsync(status, d_st, 4 * E, cudaMemcpyDeviceToHost, c->stream));
+    return d2h(c, out6, d_out, 48 * E);
+}
+
 // ---------------------------------------------------------------- N4: body thermal passes
 extern "C" int vsb_host_body_thermal(vsb_ctx *c, int64_t n, const double *consts12,
                                      const double *mass, const double *den, const double *rad,

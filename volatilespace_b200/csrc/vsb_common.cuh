@@ -309,6 +309,19 @@ int vsb_launch_predict_enter_coi(vsb_ctx *c, int64_t n, const double *d_vd, cons
                                  const unsigned char *d_valid, double tol, int steps_limit,
                                  double *d_out5, void *d_work, int sequential);
 size_t vsb_march_work_bytes(int64_t n);
+int vsb_launch_check_warp(vsb_ctx *c, int64_t nv, const double *ecc, const double *dr,
+                          const double *ea, const double *ma, const double *n, const double *impact,
+                          const double *atm, const double *leave, const double *enter, double warp,
+                          unsigned char *hold, unsigned long long *d_key2);
+int vsb_launch_enter_coi_service(vsb_ctx *c, int64_t nv, const double *dr, const double *prev_ea,
+                                 const double *ea, const double *enter, int pending,
+                                 unsigned char *flags);
+int vsb_launch_cross_scan(vsb_ctx *c, int64_t nv, const double *ecc, const double *dr,
+                          const double *prev_ea, const double *ea, const double *impact,
+                          const double *leave, const double *enter, unsigned long long *d_key);
+int vsb_launch_cross_apply(vsb_ctx *c, int64_t nev, const int32_t *kind, const double *vessel8,
+                           const int64_t *ref, const int64_t *new_ref, const double *body7,
+                           double gc, double *out6, int32_t *status);
 int vsb_march_walk_host(double x0, double c, int64_t kmax, int bounded, double bound, int64_t nq,
                         const int64_t *ks, double *xs, int64_t *K_out, int64_t *nseg_out);
 int vsb_launch_points_vessel(vsb_ctx *c, int64_t nsel, const int64_t *d_sel, const double *d_vessel12,

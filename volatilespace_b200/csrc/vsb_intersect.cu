@@ -8,18 +8,11 @@
 // one CTA marches one (vessel, body) pair in parallel and still reproduces the sequential
 // recurrences bit for bit: see "parallel march" below.  Compiled with -fmad=false.
 #include "vsb_common.cuh"
+#include "vsb_orbit_math.cuh"
 #include <vector>
 
 namespace {
 
-constexpr double PI_D = 3.141592653589793;
-
-__device__ __forceinline__ double py_mod(double a, double b)
-{
-    double r = fmod(a, b);
-    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
-    return r;
-}
 
 __device__ double solve_cubic_one(double a, double b, double c)
 {
@@ -138,53 +131,6 @@ __global__ void intersect_kernel(int64_t n, const double *__restrict__ in6,
 }
 
 // --- predict_enter_coi ---------------------------------------------------------------------
-__device__ double pe_solve_kepler_ell(double ecc, double ma, double tol)
-{
-    double mr = ma, flip;
-    if (mr > PI_D) {
-        mr = 2 * PI_D - mr;
-        flip = 1;
-    } else {
-        flip = -1;
-    }
-    if (ecc > 0.99 && mr < 0.0045) {
-        double al = tol / 1e7, be = tol / 0.3, fp = 2.7 * mr, fpp = 0.301, f = 0.154;
-        for (int i = 0; i < 2; ++i) {
-            if ((fpp - fp) <= (al + be * f)) break;
-            if ((f - ecc * sin(f) - mr) > 0) fpp = f;
-            else fp = f;
-        }
-        f = 0.5 * (fp + fpp);
-        return ma + flip * (mr - f);
-    }
-    double tol2s = 2 * tol / (ecc + 2.2e-16);
-    double eapp = mr + 0.999999 * mr * (PI_D - mr) /
-                           (2. * mr + ecc - PI_D + 2.4674011002723395 / (ecc + 2.2e-16));
-    double fpp = ecc * sin(eapp), fppp = ecc * cos(eapp);
-    double fp = 1 - fppp, f = eapp - fpp - mr;
-    double delta = -f / fp;
-    double fp3 = fp * fp * fp, ffpfpp = f * fp * fpp, f2fppp = f * f * fppp;
-    delta = delta * (fp3 - 0.5 * ffpfpp + f2fppp / 3) / (fp3 - ffpfpp + 0.5 * f2fppp);
-    for (int i = 0; i < 30; ++i) {
-        if (delta * delta < fp * tol2s) break;
-        eapp = eapp + delta;
-        fp = 1 - ecc * cos(eapp);
-        delta = (mr - eapp + ecc * sin(eapp)) / fp;
-    }
-    eapp = eapp + delta;
-    return ma + flip * (mr - eapp);
-}
-
-__device__ double pe_newton_hyp(double ecc, double ma, double ea)
-{
-    for (int i = 0; i < 50; ++i) {
-        double dx = (ea - ecc * sinh(ea) - ma) / (1.0 - ecc * cosh(ea));
-        ea -= dx;
-        if (fabs(dx) < 1e-10) return ea;
-    }
-    return ea;
-}
-
 struct orbit {
     double a, b, f, ecc, ma, ea, pea, n, dr, prev_ea;
 };

@@ -345,6 +345,49 @@ class Device:
             none(entered_coi), none(left_coi), none(left_coi_prev_ref), int(bool(only_enter_coi)),
             int(steps_limit), ptr(body_impact), ptr(body_enter_atm), ptr(coi_leave), ptr(coi_enter)))
 
+    def host_check_warp(self, ecc, dr, ea, ma, n, body_impact, body_enter_atm, coi_leave, coi_enter,
+                        warp, hold):
+        """phys_vessel.Physics.check_warp (phys_vessel.py:506-560): `hold` (uint8 mask of
+        physical_hold) is updated in place -> (situation, alarm_vessel, len(physical_hold))."""
+        assert hold.dtype == np.uint8 and hold.flags.c_contiguous and len(hold) == len(ecc)
+        out = np.zeros(3, dtype=np.int64)
+        check(self.L.vsb_host_check_warp(
+            self.h, len(ecc), ptr(f64(ecc)), ptr(f64(dr)), ptr(f64(ea)), ptr(f64(ma)), ptr(f64(n)),
+            ptr(f64(body_impact)), ptr(f64(body_enter_atm)), ptr(f64(coi_leave)),
+            ptr(f64(coi_enter)), float(warp), ptr(hold), ptr(out)))
+        none = lambda x: None if x < 0 else int(x)
+        return none(out[0]), none(out[1]), int(out[2])
+
+    def host_enter_coi_service(self, dr, prev_ea, ea, coi_enter, crossing_pending=False):
+        """predict_enter_coi_service (phys_vessel.py:744-758) -> indices it re-predicts."""
+        flags = np.zeros(len(dr), dtype=np.uint8)
+        check(self.L.vsb_host_enter_coi_service(
+            self.h, len(dr), ptr(f64(dr)), ptr(f64(prev_ea)), ptr(f64(ea)), ptr(f64(coi_enter)),
+            int(bool(crossing_pending)), ptr(flags)))
+        return np.flatnonzero(flags)
+
+    def host_cross_scan(self, ecc, dr, prev_ea, ea, body_impact, coi_leave, coi_enter):
+        """cross_coi detection (phys_vessel.py:563-632) -> (vessel | None, kind 1 enter / 2 leave)."""
+        out = np.zeros(2, dtype=np.int64)
+        check(self.L.vsb_host_cross_scan(
+            self.h, len(ecc), ptr(f64(ecc)), ptr(f64(dr)), ptr(f64(prev_ea)), ptr(f64(ea)),
+            ptr(f64(body_impact)), ptr(f64(coi_leave)), ptr(f64(coi_enter)), ptr(out)))
+        return (None if out[0] < 0 else int(out[0])), int(out[1])
+
+    def host_cross_apply(self, kind, vessel8, ref, new_ref, body7, gc):
+        """The orbit change of cross_coi for a batch of events -> (out6 (nev,6), status (nev,))."""
+        vessel8, body7 = f64(np.atleast_2d(vessel8)), f64(body7)
+        kind = np.ascontiguousarray(np.atleast_1d(kind), dtype=np.int32)
+        ref, new_ref = i64(np.atleast_1d(ref)), i64(np.atleast_1d(new_ref))
+        nev = len(kind)
+        assert vessel8.shape == (nev, 8) and body7.shape[1] == 7
+        out = np.empty((nev, 6))
+        status = np.zeros(nev, dtype=np.int32)
+        check(self.L.vsb_host_cross_apply(self.h, nev, ptr(kind), ptr(vessel8), ptr(ref),
+                                          ptr(new_ref), len(body7), ptr(body7), float(gc), ptr(out),
+                                          ptr(status)))
+        return out, status
+
     def set_march_mode(self, sequential):
         check(self.L.vsb_set_march_mode(self.h, int(bool(sequential))))
 

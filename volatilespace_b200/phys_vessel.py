@@ -1,9 +1,10 @@
 """Drop-in for the physics of volatilespace/physics/phys_vessel.py on a B200:
 `Physics.move / curve / curve_move` (phys_vessel.py:477-503, 364-369) and the orbit
 points `Physics.points` (:372-474: body impact, atmosphere entry, COI leave, COI enter
--- SURVEY 8f N2), batched over all vessels.  The event handling built on those points
-(check_warp, cross_coi, predict_next_orbit, curve_segments) is per-vessel game logic and
-stays with the caller.
+-- SURVEY 8f N2), batched over all vessels, and the per-tick event scans built on those
+points: `check_warp` (:506-560), `predict_enter_coi_service` (:744-758), `cross_coi`
+(:563-632) and `change_vessel` (:306-361).  Drawing-side helpers (predict_next_orbit,
+curve_segments, selected, rotate) stay with the caller.
 """
 import numpy as np
 
@@ -40,6 +41,7 @@ class Physics:
             self.body_dr = (col(body_orb, k) for k in ("a", "b", "f", "ecc", "pea", "n", "dir"))
         self.predict_coi_limit = 300                   # [game] predict_coi_limit, :181
         self.entered_coi = self.left_coi = self.left_coi_prev_ref = None
+        self._hold = np.zeros(0, dtype=np.uint8)       # membership mask of physical_hold
         self.names = np.array((vessel_data or {}).get("name", []))
         self.a = np.array(vessel_orb_data["a"], dtype=np.float64)
         self.ecc = np.array(vessel_orb_data["ecc"], dtype=np.float64)
@@ -50,6 +52,8 @@ class Physics:
         self.n_vessels = len(self.a)
         self.pos = np.zeros((self.n_vessels, 2))
         self.ea = np.array(vessel_orb_data.get("ea", np.zeros(self.n_vessels)), dtype=np.float64)
+        self._hold = np.zeros(self.n_vessels, dtype=np.uint8)
+        self.prev_ea = np.array(self.ea)
         nan = lambda w: np.full((self.n_vessels, w), np.nan)
         self.body_impact, self.body_enter_atm, self.coi_leave, self.coi_enter = (
             nan(2), nan(2), nan(2), nan(6))            # :231-234
@@ -88,6 +92,9 @@ class Physics:
     def points(self, vessel=None, only_enter_coi=False):
         """Characteristic points of the vessel orbits: body_impact, body_enter_atm, coi_leave
         (each (Nv,2): next / previous eccentric anomaly) and coi_enter (Nv,6), updated in place."""
+        self._points(None if vessel is None else [vessel], only_enter_coi)
+
+    def _points(self, sel, only_enter_coi=False):
         vessel12 = np.stack([self.a, self.b, self.f, self.ecc, self.ma, self.ea, self.pea, self.n,
                              self.dr, self.pe_d, self.ap_d, self.period], axis=1)
         body12 = np.stack([self.body_a, self.body_b, self.body_f, self.body_ecc, self.body_ma,
@@ -95,10 +102,89 @@ class Physics:
                            self.body_size, self.body_atm], axis=1)
         self.dev.host_vessel_points(
             vessel12, self.ref, body12, self.body_ref, self.body_impact, self.body_enter_atm,
-            self.coi_leave, self.coi_enter, sel=None if vessel is None else [vessel],
-            entered_coi=self.entered_coi, left_coi=self.left_coi,
+            self.coi_leave, self.coi_enter, sel=sel, entered_coi=self.entered_coi, left_coi=self.left_coi,
             left_coi_prev_ref=self.left_coi_prev_ref, only_enter_coi=only_enter_coi,
             steps_limit=self.predict_coi_limit)
+
+    @property
+    def physical_hold(self):
+        """Vessels held in physical warp (the reference keeps them in append order; ascending
+        here -- only membership and the count are ever used, game.py:1171-1215)."""
+        return np.flatnonzero(self._hold)
+
+    # phys_vessel.py:506-560 -> (situation, alarm_vessel, len(physical_hold))
+    def check_warp(self, warp):
+        return self.dev.host_check_warp(self.ecc, self.dr, self.ea, self.ma, self.n,
+                                        self.body_impact, self.body_enter_atm, self.coi_leave,
+                                        self.coi_enter, warp, self._hold)
+
+    # phys_vessel.py:744-758
+    def predict_enter_coi_service(self):
+        pending = self.left_coi is not None or self.entered_coi is not None
+        again = self.dev.host_enter_coi_service(self.dr, self.prev_ea, self.ea, self.coi_enter,
+                                                pending)
+        if len(again):
+            self._points(again, only_enter_coi=True)
+        return again
+
+    # phys_vessel.py:563-632 -> the vessel whose orbit changed, or None
+    def cross_coi(self):
+        ves, kind = self.dev.host_cross_scan(self.ecc, self.dr, self.prev_ea, self.ea,
+                                             self.body_impact, self.coi_leave, self.coi_enter)
+        # the reference's loop clears these flags for every vessel it visits (:579-583): up to and
+        # including the crossing one, or all of them
+        last = self.n_vessels - 1 if ves is None else ves
+        if self.entered_coi is not None and self.entered_coi <= last:
+            self.entered_coi = None
+        if self.left_coi is not None and self.left_coi <= last:
+            self.left_coi = None
+            self.left_coi_prev_ref = None
+        if ves is None:
+            return None
+        ref = int(self.ref[ves])
+        new_ref = int(self.body_ref[ref]) if kind == 2 else int(self.coi_enter[ves, 0])
+        ea_cross = self.coi_leave[ves, 0] if kind == 2 else self.coi_enter[ves, 1]
+        body7 = np.stack([self.body_a, self.body_ecc, self.body_pea, self.body_dr, self.body_mass,
+                          self.body_pos[:, 0], self.body_pos[:, 1]], axis=1)
+        row = [self.a[ves], self.b[ves], self.f[ves], self.ecc[ves], self.pea[ves], self.u[ves],
+               self.dr[ves], ea_cross]
+        out, status = self.dev.host_cross_apply(kind, row, ref, new_ref, body7, self.gc)
+        if status[0]:
+            return None                                # :609-610
+        self.a[ves], self.ecc[ves], self.pea[ves], self.ma[ves], self.dr[ves] = out[0, :5]
+        self.ref[ves] = new_ref
+        if kind == 2:
+            self.left_coi, self.left_coi_prev_ref = ves, ref
+        else:
+            self.entered_coi = ves
+        return ves
+
+    # phys_vessel.py:306-361 -> (vessel_data, vessel_orb)
+    def change_vessel(self, vessel):
+        sl = slice(vessel, vessel + 1)
+        orb = calc_orb("vessel", self.ref[sl], self.body_mass, None, self.gc, 0.0, self.a[sl],
+                       self.ecc[sl])
+        for key, arr in (("b", self.b), ("f", self.f), ("pe_d", self.pe_d), ("ap_d", self.ap_d),
+                         ("period", self.period), ("n", self.n), ("u", self.u)):
+            arr[vessel] = orb[key][0]
+        ecc, ma = self.ecc[sl], self.ma[sl]
+        if ecc[0] < 1:
+            self.ea[vessel] = self.dev.host_solve_kepler_ell(ecc, ma, 1e-10)[0]
+        else:
+            self.ea[vessel] = self.dev.host_newton_root_kepler_hyp(ecc, ma, ma)[0]
+        self.points(vessel)
+        self._push_vessel(vessel)          # curve(vessel): the device regenerates it from the elements
+        vessel_orb = [self.a[vessel], self.ref[vessel], self.ecc[vessel], self.pe_d[vessel],
+                      self.ap_d[vessel], self.pea[vessel], self.dr[vessel], self.period[vessel]]
+        return [self.names[vessel] if len(self.names) > vessel else None], vessel_orb
+
+    def _push_vessel(self, vessel):
+        """Write one vessel's (changed) elements into the device-resident vessel state."""
+        from . import _lib as L
+        for field, arr in ((L.K_A, self.a), (L.K_B, self.b), (L.K_F, self.f), (L.K_ECC, self.ecc),
+                           (L.K_PEA, self.pea), (L.K_N, self.n), (L.K_DR, self.dr), (L.K_MA, self.ma),
+                           (L.K_EA, self.ea), (L.K_REF, self.ref)):
+            self.dev.kepler_set(KIND_VESSEL, field, arr[vessel:vessel + 1], first=vessel)
 
     # phys_vessel.py:364-369
     def curve(self, vessel):
