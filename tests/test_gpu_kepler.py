@@ -697,3 +697,28 @@ def test_vessel_events_through_the_class(dev):
     o = g["cw%d_out" % k]
     assert pv.check_warp(o[3]) == (opt(o[0]), opt(o[1]), int(o[2]))
     assert np.array_equal(pv.physical_hold, np.flatnonzero(g["cw%d_hold_out" % k]))
+
+
+def test_vessel_event_argument_errors(dev):
+    from volatilespace_b200._lib import VsbError
+    z = np.zeros(3)
+    with pytest.raises(VsbError):          # event kind outside {1, 2}
+        dev.host_cross_apply(3, np.ones(8), 0, 0, np.ones((2, 7)), 1.0)
+    with pytest.raises(VsbError):          # body index out of range
+        dev.host_cross_apply(2, np.ones(8), 5, 0, np.ones((2, 7)), 1.0)
+    nan2, nan6 = np.full((3, 2), np.nan), np.full((3, 6), np.nan)
+    with pytest.raises(VsbError):          # vessel reference out of range
+        dev.host_vessel_points(np.ones((3, 12)), np.array([0, 9, 0]), np.ones((2, 12)),
+                               np.array([0, 0]), nan2.copy(), nan2.copy(), nan2.copy(), nan6.copy())
+    with pytest.raises(VsbError):          # selected vessel out of range
+        dev.host_vessel_points(np.ones((3, 12)), np.zeros(3, dtype=np.int64), np.ones((2, 12)),
+                               np.array([0, 0]), nan2.copy(), nan2.copy(), nan2.copy(), nan6.copy(),
+                               sel=[7])
+    # entering the body the vessel already orbits: the reference returns None
+    out, status = dev.host_cross_apply(1, np.ones(8), 1, 1, np.ones((2, 7)), 1.0)
+    assert status[0] == 1 and np.all(np.isnan(out))
+    # all-NaN points: nothing to do, holds are released
+    hold = np.ones(3, dtype=np.uint8)
+    assert dev.host_check_warp(z + 0.5, z + 1, z, z, z + 0.01, nan2, nan2, nan2, nan6, 1.0, hold) \
+        == (None, None, 0)
+    assert not hold.any()
