@@ -343,7 +343,7 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
         t0 = time.perf_counter()
         dev.host_vessel_points(*args, *res, steps_limit=300)
         t_all = time.perf_counter() - t0
-        chunks, rerun, serial = dev.march_stats()
+        chunks, rerun, serial, refused = dev.march_stats()
         per = np.where(v12[:, 3] < 1, v12[:, 11], np.inf)
         kids = [np.flatnonzero((g["body_ref"] == r) & (np.arange(len(b12)) != 0)) for r in g["v_ref"]]
         cost = np.array([sum(max(min(5 * p / b12[k, 9], p / 2), p / 30) for k in ks) if len(ks) else 0.0

@@ -456,7 +456,7 @@ def test_vessel_points_golden(dev):
     bi, ba, cl, ce = _points_inputs(g)
     dev.host_vessel_points(g["vessel12"], g["v_ref"], g["body12"], g["body_ref"], bi, ba, cl, ce,
                            steps_limit=int(g["steps_limit"]))
-    chunks, rerun, serial = dev.march_stats()
+    chunks, rerun, serial, refused = dev.march_stats()
     assert serial == 0 and chunks > 0
     assert rerun <= 0.02 * chunks            # speculation on the hyperbolic chains mostly holds
     _assert_points(bi, g["body_impact"], "body_impact", nan_slack=1, frac=0.5)
@@ -528,12 +528,17 @@ def test_march_parallel_is_bit_identical_to_serial(dev):
     finally:
         dev.set_march_mode(False)
     par = oi.predict_enter_coi(vd, bd, 1e-5, 300, device=dev)
-    chunks, rerun, fell_back = dev.march_stats()
+    chunks, rerun, fell_back, refused = dev.march_stats()
     assert fell_back == 0
     assert np.array_equal(par.view(np.uint64), serial.view(np.uint64))
     hit = ~np.isnan(serial[:, 0])
     assert 20 < hit.sum() < m - 20
     assert rerun <= 0.05 * chunks
+    # a march of 5e12 steps is refused (answered "no entry") instead of running for hours
+    long_vd, long_bd = vd[:1].copy(), bd[:1].copy()
+    long_vd[0, 3], long_vd[0, 7], long_bd[0, 9] = 0.3, 1.0e13, 1.0
+    assert np.all(np.isnan(oi.predict_enter_coi(long_vd, long_bd, 1e-5, 300, device=dev)))
+    assert dev.march_stats()[3] == 1
     # and on the golden elliptic cases
     gi = golden("intersect")
     dev.set_march_mode(True)

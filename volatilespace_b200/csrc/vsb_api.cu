@@ -1253,13 +1253,19 @@ extern "C" int vsb_host_predict_enter_coi(vsb_ctx *c, int64_t n, const double *v
     return d2h(c, out5, d_out, 40 * (size_t)n);
 }
 
-extern "C" int vsb_march_stats(vsb_ctx *c, uint64_t *out3)
+extern "C" int vsb_march_stats(vsb_ctx *c, uint64_t *out4)
 {
     CTX(c);
-    VSB_CHECK(out3 != nullptr, VSB_ERR_ARG, "vsb_march_stats: null output");
-    out3[0] = out3[1] = out3[2] = 0;
+    VSB_CHECK(out4 != nullptr, VSB_ERR_ARG, "vsb_march_stats: null output");
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
     if (!c->march_stats.p) return VSB_OK;
-    return d2h(c, out3, c->march_stats.p, 24);
+    uint64_t raw[7];     // mteam: stats[4], ntasks, next_task, refused
+    VSB_TRY(d2h(c, raw, c->march_stats.p, sizeof(raw)));
+    out4[0] = raw[0];
+    out4[1] = raw[1];
+    out4[2] = raw[2];
+    out4[3] = raw[6];
+    return VSB_OK;
 }
 
 extern "C" int vsb_host_running_sum(double x0, double c, int64_t kmax, int bounded, double bound,

@@ -175,6 +175,10 @@ __device__ __forceinline__ double oi_dist(const orbit &v, const orbit &b)
     return pow(dx * dx + dy * dy, 0.5);
 }
 
+// A march of more than 2^32 steps (hours of serial work in the reference) is refused: the pair is
+// answered "no entry" and counted, instead of occupying the GPU for minutes.
+constexpr long long MARCH_MAX_STEPS = 1ll << 32;
+
 // The reference's serial march, one thread per item (kept as the cross-check of the parallel
 // march and as its fallback).  vd = a b f ecc ma ea pea period n dr; bd = a b f ecc ma ea pea n dr coi
 __device__ void march_sequential(const double *V, const double *B, double tol, int steps_limit,
@@ -192,6 +196,7 @@ __device__ void march_sequential(const double *V, const double *B, double tol, i
     const double m2 = c3 > m1 ? c3 : m1;
     long long steps = (long long)m2;
     if (steps_limit > steps) steps = steps_limit;
+    if (steps > MARCH_MAX_STEPS) return;
     double dt = period / (double)steps;
     while (t < period) {
         oi_move(v, dt);
@@ -511,7 +516,9 @@ struct mtask {
 struct mteam {          // device-global bookkeeping of one launch pair
     unsigned long long stats[4];      // chunks, re-runs, serial fallbacks, item counter
     unsigned long long ntasks, next_task;
+    unsigned long long refused;       // pairs longer than MARCH_MAX_STEPS (answered NaN)
 };
+
 
 // stats[0] += chunks marched, stats[1] += chunks re-run after a failed speculation,
 // stats[2] += items that fell back to the serial march, stats[3] = work counter (zero at launch)
@@ -555,6 +562,11 @@ enter_coi_march_kernel(int64_t n, const double *__restrict__ vd, const double *_
             continue;
         }
         const long long K = sh.K;
+        if (K > MARCH_MAX_STEPS) {
+            if (tid < 5) o[tid] = nan;
+            if (tid == 0) atomicAdd(&team->refused, 1ull);
+            continue;
+        }
         const morbit &v = m.v, &b = m.b;
         const double b_coi = m.b_coi;
         const bool chained = m.chained;

@@ -392,8 +392,9 @@ class Device:
         check(self.L.vsb_set_march_mode(self.h, int(bool(sequential))))
 
     def march_stats(self):
-        """(chunks marched, chunks re-run, serial fallbacks) of the last COI-entry march."""
-        out = np.zeros(3, dtype=np.uint64)
+        """(chunks marched, chunks re-run, serial fallbacks, refused pairs) of the last COI-entry
+        march."""
+        out = np.zeros(4, dtype=np.uint64)
         check(self.L.vsb_march_stats(self.h, ptr(out)))
         return tuple(int(x) for x in out)
 
