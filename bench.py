@@ -313,17 +313,16 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
         # positions from the host, cull on screen, gather + copy only the visible curves
         from volatilespace_b200._lib import K_POS
         sb = np.array([[-6.0e4, 4.0e4], [6.0e4, -4.0e4]])
-        rad = np.full(n, 10.0)
         t0 = time.perf_counter()
         reps = 3
         for _ in range(reps):
             dev.kepler_tick(KIND_VESSEL, 1.0, k["body_pos"])
-            vis = dev.kepler_culling(KIND_VESSEL, n, rad, sb, 0.01)
+            vis = dev.kepler_culling(KIND_VESSEL, n, 10 / 0.01, sb, 0.01)
             cur = dev.kepler_curves_gather(KIND_VESSEL, vis[:2000], P)
         dt = (time.perf_counter() - t0) / reps
         out["kepler4m"]["e2e"] = {
             "object_ticks_per_s": n / dt, "ms_per_tick": dt * 1e3, "visible_objects": int(len(vis)),
-            "curves_copied": int(len(cur)), "h2d_bytes_per_tick": 16 + 8 * n,
+            "curves_copied": int(len(cur)), "h2d_bytes_per_tick": 16 * len(k["body_pos"]) + 32,
             "d2h_bytes_per_tick": int(8 * len(vis) + 16 * P * len(cur)),
             "path": "vsb_kepler_tick + vsb_kepler_culling + vsb_kepler_curves_gather (host arrays)"}
         dev.kepler_free(KIND_VESSEL)

@@ -378,6 +378,10 @@ int vsb_host_culling(vsb_ctx *ctx, int64_t n, const double *coords, const double
  * radius: host array (n) or NULL for zeros; idx_out needs room for n entries. */
 int vsb_kepler_culling(vsb_ctx *ctx, int kind, const double *radius, const double *screen_bounds,
                        double zoom, int64_t *idx_out, int64_t *count_out);
+/* Same with one radius for every object -- phys_vessel.Physics.culling's
+ * np.array([10] * n) / zoom (phys_vessel.py:264) without an n-element upload per frame. */
+int vsb_kepler_culling_uniform(vsb_ctx *ctx, int kind, double radius, const double *screen_bounds,
+                               double zoom, int64_t *idx_out, int64_t *count_out);
 /* visible_orbits of phys_body.py:212-216 / phys_vessel.py:267-271:
  * ((ref_visible[ref] && ref_coi[ref] > 8/zoom) || ref == 0) && size*zoom < screen_x*15, with
  * size = a (bodies) or pe_d (vessels); ascending indices. */

@@ -307,6 +307,7 @@ def test_culling_and_gather_at_scale(dev, oracle):
     idx = dev.kepler_culling(KIND_VESSEL, n, rad, sb, 0.01)
     want = np.nonzero(oracle.culling(pos, rad, sb, 0.01))[0]
     assert np.array_equal(idx, want) and 100 < len(idx) < n
+    assert np.array_equal(dev.kepler_culling(KIND_VESSEL, n, 25.0, sb, 0.01), want)   # one radius for all
     pick = idx[:: max(1, len(idx) // 500)]
     got = dev.kepler_curves_gather(KIND_VESSEL, pick, P)
     for k in (0, len(pick) // 2, len(pick) - 1):

@@ -111,6 +111,7 @@ SIGNATURES = {
     "vsb_host_body_thermal": [_ctx, _i64] + [_pv] * 16,
     "vsb_host_culling": [_ctx, _i64, _pv, _pv, _pv, _f64, _pv],
     "vsb_kepler_culling": [_ctx, C.c_int, _pv, _pv, _f64, _pv, _pi],
+    "vsb_kepler_culling_uniform": [_ctx, C.c_int, _f64, _pv, _f64, _pv, _pi],
     "vsb_kepler_visible_orbits": [_ctx, C.c_int, _i64, _pv, _pv, _pv, _f64, _f64, _pv, _pi],
     "vsb_kepler_curves_gather": [_ctx, C.c_int, _pv, _i64, _pv],
 }

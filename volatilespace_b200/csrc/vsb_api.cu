@@ -1644,7 +1644,7 @@ extern "C" int vsb_host_culling(vsb_ctx *c, int64_t n, const double *coords, con
     double *d_pos = (double *)st.idx;
     VSB_CUDA(cudaMemcpyAsync(d_pos, coords, 16 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     VSB_CUDA(cudaMemcpyAsync(st.vals, radius, 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    VSB_TRY(vsb_launch_culling_flags(c, d_pos, st.vals, n, screen_bounds, zoom, st.flags));
+    VSB_TRY(vsb_launch_culling_flags(c, d_pos, st.vals, 0.0, n, screen_bounds, zoom, st.flags));
     return d2h(c, mask_out, st.flags, (size_t)n);
 }
 
@@ -1663,8 +1663,25 @@ extern "C" int vsb_kepler_culling(vsb_ctx *c, int kind, const double *radius,
     if (radius)
         VSB_CUDA(cudaMemcpyAsync(st.vals, radius, 8 * (size_t)k->n, cudaMemcpyHostToDevice,
                                  c->stream));
-    VSB_TRY(vsb_launch_culling_flags(c, k->pos, radius ? st.vals : nullptr, k->n, screen_bounds,
-                                     zoom, st.flags));
+    VSB_TRY(vsb_launch_culling_flags(c, k->pos, radius ? st.vals : nullptr, 0.0, k->n,
+                                     screen_bounds, zoom, st.flags));
+    return vis_finish(c, st, k->n, idx_out, count_out);
+}
+
+extern "C" int vsb_kepler_culling_uniform(vsb_ctx *c, int kind, double radius,
+                                          const double *screen_bounds, double zoom,
+                                          int64_t *idx_out, int64_t *count_out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_culling_uniform", kind, &k));
+    VSB_CHECK(k->n > 0, VSB_ERR_STATE, "vsb_kepler_culling_uniform: no state loaded for this kind");
+    VSB_CHECK(screen_bounds && count_out && zoom != 0.0, VSB_ERR_ARG,
+              "vsb_kepler_culling_uniform: bad argument");
+    vis_stage st;
+    VSB_TRY(vis_reserve(c, k->n, 0, &st));
+    VSB_TRY(vsb_launch_culling_flags(c, k->pos, nullptr, radius, k->n, screen_bounds, zoom,
+                                     st.flags));
     return vis_finish(c, st, k->n, idx_out, count_out);
 }
 

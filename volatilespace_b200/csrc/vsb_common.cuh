@@ -284,8 +284,9 @@ int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptr
                            const int *widths, int nfields, double *d_out, int64_t *words_out);
 int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double *d_out);
 // culling / visible subset (vsb_visible.cu)
-int vsb_launch_culling_flags(vsb_ctx *c, const double *d_pos, const double *d_radius, int64_t n,
-                             const double *sb4, double zoom, unsigned char *d_flags);
+int vsb_launch_culling_flags(vsb_ctx *c, const double *d_pos, const double *d_radius,
+                             double r_uniform, int64_t n, const double *sb4, double zoom,
+                             unsigned char *d_flags);
 int vsb_launch_orbit_flags(vsb_ctx *c, const int64_t *d_ref, const double *d_size, int64_t n,
                            const unsigned char *d_ref_visible, const double *d_ref_coi, double zoom,
                            double screen_x, unsigned char *d_flags);

@@ -25,12 +25,13 @@ __device__ __forceinline__ bool culling_one(double2 p, double r, const double4 s
 }
 
 __global__ void __launch_bounds__(VC_T)
-culling_flags_kernel(const double2 *__restrict__ pos, const double *__restrict__ radius, int64_t n,
-                     double4 sb, double two_over_zoom, unsigned char *__restrict__ flags)
+culling_flags_kernel(const double2 *__restrict__ pos, const double *__restrict__ radius,
+                     double r_uniform, int64_t n, double4 sb, double two_over_zoom,
+                     unsigned char *__restrict__ flags)
 {
     int64_t i = (int64_t)blockIdx.x * VC_T + threadIdx.x;
     if (i >= n) return;
-    flags[i] = culling_one(pos[i], radius ? radius[i] : 0.0, sb, two_over_zoom) ? 1 : 0;
+    flags[i] = culling_one(pos[i], radius ? radius[i] : r_uniform, sb, two_over_zoom) ? 1 : 0;
 }
 
 // phys_body.py:212-215 / phys_vessel.py:267-270:
@@ -129,13 +130,14 @@ curves_gather_kernel(const double2 *__restrict__ curves, const int64_t *__restri
 
 }  // namespace
 
-int vsb_launch_culling_flags(vsb_ctx *c, const double *d_pos, const double *d_radius, int64_t n,
-                             const double *sb4, double zoom, unsigned char *d_flags)
+int vsb_launch_culling_flags(vsb_ctx *c, const double *d_pos, const double *d_radius,
+                             double r_uniform, int64_t n, const double *sb4, double zoom,
+                             unsigned char *d_flags)
 {
     if (n <= 0) return VSB_OK;
     double4 sb = make_double4(sb4[0], sb4[1], sb4[2], sb4[3]);
     culling_flags_kernel<<<(unsigned)((n + VC_T - 1) / VC_T), VC_T, 0, c->stream>>>(
-        (const double2 *)d_pos, d_radius, n, sb, 2.0 / zoom, d_flags);
+        (const double2 *)d_pos, d_radius, r_uniform, n, sb, 2.0 / zoom, d_flags);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;

@@ -406,12 +406,17 @@ class Device:
         return mask.astype(bool)
 
     def kepler_culling(self, kind, n, radius, screen_bounds, zoom):
-        radius = None if radius is None else f64(radius)
+        """`radius`: per-object array, None (zero), or one number for every object."""
         sb = f64(screen_bounds)
         idx = np.empty(n, dtype=np.int64)
         cnt = C.c_int64()
-        check(self.L.vsb_kepler_culling(self.h, kind, ptr(radius), ptr(sb), float(zoom), ptr(idx),
-                                        C.byref(cnt)))
+        if radius is not None and np.ndim(radius) == 0:
+            check(self.L.vsb_kepler_culling_uniform(self.h, kind, float(radius), ptr(sb),
+                                                    float(zoom), ptr(idx), C.byref(cnt)))
+        else:
+            radius = None if radius is None else f64(radius)
+            check(self.L.vsb_kepler_culling(self.h, kind, ptr(radius), ptr(sb), float(zoom),
+                                            ptr(idx), C.byref(cnt)))
         return idx[:cnt.value].copy()
 
     def kepler_visible_orbits(self, kind, n, ref_visible, ref_coi, size, zoom, screen_x):

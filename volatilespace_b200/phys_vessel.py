@@ -204,8 +204,7 @@ class Physics:
     def culling(self, sim_screen, zoom, visible_coi):
         n = self.n_vessels
         dev = self.dev
-        self.visible_vessels = dev.kepler_culling(KIND_VESSEL, n, np.full(n, 10.0) / zoom,
-                                                  sim_screen, zoom)
+        self.visible_vessels = dev.kepler_culling(KIND_VESSEL, n, 10 / zoom, sim_screen, zoom)
         coi_truth = np.zeros(len(self.body_coi), dtype=np.uint8)
         coi_truth[np.asarray(visible_coi, dtype=np.int64)] = 1
         self.visible_orbits = dev.kepler_visible_orbits(KIND_VESSEL, n, coi_truth, self.body_coi,
