@@ -160,6 +160,15 @@ int vsb_simplified_orbit_coi(vsb_ctx *ctx, double gc, double coi_coef,
  * lexicographically smallest colliding pair, returned as (body_del, body_add);
  * (-1,-1) stands for the reference's (None, None).  Bit-exact predicate. */
 int vsb_check_collision(vsb_ctx *ctx, int64_t *body_del_out, int64_t *body_add_out);
+/* The exhaustive scan split over ranks (SURVEY 8e "collision detect"): rank `part` of `parts`
+ * scans the row blocks part, part+parts, ... (asynchronous) and leaves its local minimum key
+ * (i << 32 | j; all ones = no collision) in the device word vsb_collision_key_ptr returns; the
+ * caller reduces that word with MIN over the ranks (one 64-bit all-reduce) and every rank then
+ * calls vsb_check_collision_finish, which applies the reference's del/add rule
+ * (phys_editor.py:93-97) to the winning pair. */
+int vsb_check_collision_part_async(vsb_ctx *ctx, int part, int parts);
+int vsb_collision_key_ptr(vsb_ctx *ctx, void **dptr_out);
+int vsb_check_collision_finish(vsb_ctx *ctx, int64_t *del_out, int64_t *add_out);
 
 /* B3  structural pieces of del_body :250-290 / set_root :293-313 /
  * set_body_mass :844-857 on the device arrays.

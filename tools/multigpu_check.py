@@ -6,6 +6,9 @@
 Every rank runs the row-sharded all-pairs ticks (NCCL all-gather of positions) and then the
 same ticks unsharded on its own GPU; gathered positions and own-row velocities must be
 BIT-IDENTICAL to the single-GPU result (the summation order does not depend on the sharding).
+Then: the symmetric driver (all-reduce of partial accelerations), the body-sim tick with
+collisions and merges (row-split scan + 64-bit MIN all-reduce, and the redundant candidate pass)
+against the single-GPU class, and Kepler propagation in object blocks (no collective).
 """
 import os
 import sys
@@ -74,12 +77,52 @@ def main():
     t0 = t.clone()
     dist.broadcast(t0, src=0)
     ok_rep = bool(torch.equal(t, t0))
-    flag = torch.tensor([int(ok), int(ok_host), int(ok_sym), int(ok_rep)], device="cuda")
+    # body-sim tick WITH collisions over the ranks: merge list and final state of a
+    # collapsing cluster against the single-GPU class, for both detection modes
+    from volatilespace_b200.dist import ShardedAllPairsPhysics, ShardedKepler
+    from volatilespace_b200.phys_editor import AllPairsPhysics
+    c = synth.collapsing_cluster(20000, seed=5, radius=2.5e4)
+    conf = {"gc": c["gc"], "rad_mult": c["rad_mult"]}
+    bd = {"mass": c["mass"], "den": c["den"]}
+    bo = {"pos": c["pos"], "vel": c["vel"]}
+    dev.set_gravity_mode("sym")
+    single = AllPairsPhysics(dev)
+    single.load_system(conf, bd, bo)
+    merges_single = [single.tick() for _ in range(12)]
+    pos_c = single.dev.get(F_POS)
+    ok_coll = True
+    for mode in ("rows", "grid"):
+        sh = ShardedAllPairsPhysics(dev, rank, world, collisions=mode)
+        sh.load_system(conf, bd, bo)
+        merges = [sh.tick() for _ in range(12)]
+        ok_coll = ok_coll and merges == merges_single and \
+            np.allclose(sh.dev.get(F_POS), pos_c, rtol=1e-11, atol=1e-9)
+    n_merges = sum(m is not None for m in merges_single)
+    # Kepler propagation: object blocks, no collective; each slice equals the single-GPU slice
+    from volatilespace_b200._lib import KIND_VESSEL, K_EA, K_POS
+    k = synth.kepler_objects(100003, seed=9)
+    P = 32
+    tt = np.linspace(-np.pi, np.pi, P)
+    dev.kepler_load(KIND_VESSEL, P, k["a"], k["b"], k["f"], k["ecc"], k["pea"], k["n"], k["dr"],
+                    k["ma"], k["ea"], k["ref"], tt)
+    for _ in range(3):
+        dev.kepler_tick(KIND_VESSEL, 2.0, k["body_pos"])
+    ea_all = dev.kepler_get(KIND_VESSEL, K_EA, len(k["a"]))
+    pos_all = dev.kepler_get(KIND_VESSEL, K_POS, len(k["a"]))
+    sk = ShardedKepler(dev, KIND_VESSEL, P, k, rank, world, tt)
+    for _ in range(3):
+        sk.tick(2.0, k["body_pos"])
+    ok_kep = np.array_equal(sk.get(K_EA), ea_all[sk.row0:sk.row1]) and \
+        np.array_equal(sk.get(K_POS), pos_all[sk.row0:sk.row1])
+    flag = torch.tensor([int(ok), int(ok_host), int(ok_sym), int(ok_rep), int(ok_coll), int(ok_kep)],
+                        device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("multigpu_check n=%d world=%d ticks=%d: sharded==single %s, host path %s, "
-              "sym within tolerance %s, sym replicas identical %s" %
-              (n, world, ticks, *[bool(x) for x in flag.tolist()]))
+              "sym within tolerance %s, sym replicas identical %s, collision ticks (%d merges) %s, "
+              "kepler slices %s" %
+              (n, world, ticks, *[bool(x) for x in flag.tolist()[:4]], n_merges,
+               bool(flag[4]), bool(flag[5])))
     dist.barrier()
     dist.destroy_process_group()
     if not all(flag.tolist()):

@@ -70,6 +70,9 @@ SIGNATURES = {
     "vsb_kepler_basic": [_ctx, _f64, _f64],
     "vsb_simplified_orbit_coi": [_ctx, _f64, _f64, _pv, _pi],
     "vsb_check_collision": [_ctx, _pi, _pi],
+    "vsb_check_collision_part_async": [_ctx, C.c_int, C.c_int],
+    "vsb_collision_key_ptr": [_ctx, C.POINTER(C.c_void_p)],
+    "vsb_check_collision_finish": [_ctx, _pi, _pi],
     "vsb_delete_row": [_ctx, _i64],
     "vsb_swap_rows": [_ctx, _i64, _i64],
     "vsb_translate_to": [_ctx, _i64],

@@ -636,6 +636,42 @@ extern "C" int vsb_check_collision(vsb_ctx *c, int64_t *del_out, int64_t *add_ou
     return VSB_OK;
 }
 
+// Multi-GPU form of the exhaustive scan: rank `part` of `parts` scans its row blocks
+// and leaves its local minimum (i << 32 | j, all ones = none) in the device word returned by
+// vsb_collision_key_ptr; the caller takes the minimum over ranks (one 64-bit all-reduce) and
+// calls vsb_check_collision_finish on every rank.
+extern "C" int vsb_check_collision_part_async(vsb_ctx *c, int part, int parts)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_check_collision_part_async"));
+    VSB_CHECK(parts >= 1 && part >= 0 && part < parts, VSB_ERR_ARG,
+              "vsb_check_collision_part_async: part %d of %d", part, parts);
+    return vsb_launch_check_collision_part(c, part, parts);
+}
+
+extern "C" int vsb_collision_key_ptr(vsb_ctx *c, void **dptr_out)
+{
+    CTX(c);
+    VSB_CHECK(dptr_out != nullptr, VSB_ERR_ARG, "vsb_collision_key_ptr: null output");
+    *dptr_out = c->d_key;
+    return VSB_OK;
+}
+
+extern "C" int vsb_check_collision_finish(vsb_ctx *c, int64_t *del_out, int64_t *add_out)
+{
+    CTX(c);
+    VSB_CHECK(del_out && add_out, VSB_ERR_ARG, "vsb_check_collision_finish: null output");
+    VSB_TRY(need_bodies(c, "vsb_check_collision_finish"));
+    VSB_TRY(vsb_launch_check_collision_finish(c));
+    int64_t *h = (int64_t *)c->h_key;
+    VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                             c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    *del_out = h[0];
+    *add_out = h[1];
+    return VSB_OK;
+}
+
 extern "C" int vsb_delete_row(vsb_ctx *c, int64_t row)
 {
     CTX(c);

@@ -266,6 +266,8 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
 // pair predicates (vsb_pairs.cu)
 int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order);
 int vsb_launch_check_collision(vsb_ctx *c);
+int vsb_launch_check_collision_part(vsb_ctx *c, int part, int parts);
+int vsb_launch_check_collision_finish(vsb_ctx *c);
 // sort-based candidate pass (vsb_broadphase.cu); result {del, add, fallback} in c->scratch
 int vsb_launch_broadphase(vsb_ctx *c);
 // editor step pieces (vsb_editor.cu)

@@ -104,9 +104,11 @@ __device__ __forceinline__ bool collide_exact(double2 a, double2 b, double ra, d
 __global__ void __launch_bounds__(PB_BLOCK)
 cc_scan_kernel(const double2 *__restrict__ pos, const double *__restrict__ rad,
                const double *__restrict__ radm, int64_t n, int64_t chunk_tiles,
-               unsigned long long *__restrict__ key)
+               unsigned long long *__restrict__ key, int part, int parts)
 {
-    const int64_t i0 = (int64_t)blockIdx.x * PB_BLOCK;
+    // row blocks part, part+parts, ... (multi-GPU: one part per rank; the triangular cost of the
+    // scan is balanced by dealing the blocks round-robin)
+    const int64_t i0 = ((int64_t)blockIdx.x * parts + part) * PB_BLOCK;
     const int64_t i = i0 + threadIdx.x;
     int64_t t0 = (int64_t)blockIdx.y * chunk_tiles;
     int64_t t1 = t0 + chunk_tiles;
@@ -215,8 +217,9 @@ int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order)
     return VSB_OK;
 }
 
-// Result (body_del, body_add) is written to c->scratch.p as two int64.
-int vsb_launch_check_collision(vsb_ctx *c)
+// Exhaustive scan of the row blocks of one part (part of parts); the local minimum key lands in
+// c->d_key.  parts == 1 is the whole scan.
+int vsb_launch_check_collision_part(vsb_ctx *c, int part, int parts)
 {
     const int64_t n = c->n, npad = c->npad;
     VSB_TRY(vsb_buf_reserve(c->scratch, 64));
@@ -227,15 +230,33 @@ int vsb_launch_check_collision(vsb_ctx *c)
     c->launches += 1;
     if (n >= 2) {
         const int64_t row_blocks = (n - 1 + PB_BLOCK - 1) / PB_BLOCK;
-        const int64_t tiles = (n + PB_TJ - 1) / PB_TJ;
-        const int ct = chunk_tiles_for(tiles, row_blocks, c->sm_count);
-        dim3 grid((unsigned)row_blocks, (unsigned)((tiles + ct - 1) / ct));
-        cc_scan_kernel<<<grid, PB_BLOCK, 0, c->stream>>>((const double2 *)c->pos, c->rad, radm, n,
-                                                         ct, c->d_key);
-        c->launches += 1;
+        const int64_t mine = (row_blocks - part + parts - 1) / parts;
+        if (mine > 0) {
+            const int64_t tiles = (n + PB_TJ - 1) / PB_TJ;
+            const int ct = chunk_tiles_for(tiles, mine, c->sm_count);
+            dim3 grid((unsigned)mine, (unsigned)((tiles + ct - 1) / ct));
+            cc_scan_kernel<<<grid, PB_BLOCK, 0, c->stream>>>((const double2 *)c->pos, c->rad, radm,
+                                                             n, ct, c->d_key, part, parts);
+            c->launches += 1;
+        }
     }
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
+
+// (i, j) key in c->d_key -> (body_del, body_add) in c->scratch.p as two int64
+int vsb_launch_check_collision_finish(vsb_ctx *c)
+{
+    VSB_TRY(vsb_buf_reserve(c->scratch, 64));
     cc_finalize_kernel<<<1, 1, 0, c->stream>>>(c->d_key, c->mass, (int64_t *)c->scratch.p);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;
+}
+
+// Result (body_del, body_add) is written to c->scratch.p as two int64.
+int vsb_launch_check_collision(vsb_ctx *c)
+{
+    VSB_TRY(vsb_launch_check_collision_part(c, 0, 1));
+    return vsb_launch_check_collision_finish(c);
 }

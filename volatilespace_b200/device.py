@@ -181,6 +181,23 @@ class Device:
             return None, None
         return d.value, a.value
 
+    def check_collision_part_async(self, part, parts):
+        """Exhaustive scan of this rank's row blocks (multi-GPU); the local minimum key stays in
+        the device word at collision_key_ptr()."""
+        check(self.L.vsb_check_collision_part_async(self.h, int(part), int(parts)))
+
+    def collision_key_ptr(self):
+        p = C.c_void_p()
+        check(self.L.vsb_collision_key_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def check_collision_finish(self):
+        d, a = C.c_int64(), C.c_int64()
+        check(self.L.vsb_check_collision_finish(self.h, C.byref(d), C.byref(a)))
+        if d.value < 0:
+            return None, None
+        return d.value, a.value
+
     def delete_row(self, row):
         check(self.L.vsb_delete_row(self.h, int(row)))
 
