@@ -368,6 +368,62 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
     return out
 
 
+def multi_gpu_extras(torch, dist, dev, stream, rank, world, barrier):
+    """The other two rows of SURVEY 8e at N > 1 (every rank takes part; max over ranks):
+    Kepler propagation in object blocks (no collective) and collision detection at 256k bodies
+    (row-split exhaustive scan + 64-bit MIN all-reduce, and the redundant candidate pass)."""
+    from volatilespace_b200 import synth
+    from volatilespace_b200._lib import KIND_VESSEL
+    from volatilespace_b200.dist import ShardedAllPairsPhysics, partition
+    from volatilespace_b200.phys_editor import body_radius
+    out = {}
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, P = 4194304, 512
+    rpr, ranges = partition(n, world)
+    mine = ranges[rank][1] - ranges[rank][0]
+    k = synth.kepler_objects(mine, seed=20240603 + rank)      # this rank's block of the 4M objects
+    dev.kepler_load(KIND_VESSEL, P, k["a"], k["b"], k["f"], k["ecc"], k["pea"], k["n"], k["dr"],
+                    k["ma"], k["ea"], k["ref"])
+    dev.kepler_tick(KIND_VESSEL, 1.0, k["body_pos"])
+    for _ in range(2):
+        dev.kepler_tick_async(KIND_VESSEL, 1.0)
+    ms = time_ticks(torch, stream, lambda: dev.kepler_tick_async(KIND_VESSEL, 1.0), 5, barrier) / 5
+    ms = max_over_ranks(ms)
+    out["kepler4m_sharded"] = {"ms_per_tick": ms, "object_ticks_per_s": n / (ms * 1e-3),
+                               "objects_per_rank": rpr, "collective": "none"}
+    dev.kepler_free(KIND_VESSEL)
+
+    s = synth.collapsing_cluster(262144)
+    rad = body_radius(s["mass"], s["den"], s["rad_mult"]) * 0.01           # no hit: full scan
+    coll = {}
+    for mode in ("rows", "grid"):
+        ph = ShardedAllPairsPhysics(dev, rank, world, collisions=mode)
+        ph.load_system({"gc": s["gc"], "rad_mult": s["rad_mult"]}, {"mass": s["mass"], "den": s["den"]},
+                       {"pos": s["pos"], "vel": s["vel"]})
+        ph.dev.set(_f_rad(), rad)
+        assert ph.check_collision() == (None, None)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ph.check_collision()
+        coll[mode + "_ms_per_check"] = max_over_ranks((time.perf_counter() - t0) / 5 * 1e3)
+    coll["note"] = ("262144 bodies, no hit (worst case), host-visible result per check; rows = "
+                    "exhaustive scan split by row blocks + MIN all-reduce of one 64-bit key, grid = "
+                    "sort-based candidate pass on every rank")
+    out["collision256k_sharded"] = coll
+    return out
+
+
+def _f_rad():
+    from volatilespace_b200._lib import F_RAD
+    return F_RAD
+
+
 def roofline(ops, fp64_flops_microbench, clocks, dev, ms_accel, my_pairs, ops_per_pair, kernel):
     """FP64-pipe roofline of the gravity kernel.  MEASURED_PEAKS.json has no FP64 figure, so the
     denominator is the pipe's issue peak -- 64 FP64 lanes/SM/clk (what ncu's
@@ -482,6 +538,10 @@ def run_b200(args):
            "path": "%s.tick_host -> vsb_bodies_set / all-pairs tick / vsb_bodies_get (pinned host "
                    "buffers, per rank)" % type(sim).__name__}
 
+    extra_multi = None
+    if world > 1 and not args.no_extra:
+        extra_multi = multi_gpu_extras(torch, dist, dev, stream, rank, world, barrier)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -512,6 +572,8 @@ def run_b200(args):
     }
     if not args.no_extra and world == 1:
         line["extra"] = extra_workloads(torch, dev, stream, peaks, fp64_ops_peak)
+    if extra_multi is not None:
+        line["extra"] = extra_multi
     if not args.no_cpu and world == 1:
         v, cores, rows, dtc = cpu_pairs_per_s(s, 12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
