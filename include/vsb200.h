@@ -101,6 +101,15 @@ int vsb_find_parents(vsb_ctx *ctx, const int64_t *order_desc_mass, int64_t *pare
  * (find_parents, gravity_one :51-60, rel_vel fix-up, vel compose, pos += vel).
  * order_desc_mass may be NULL to reuse the order uploaded by the previous call. */
 int vsb_gravity_ref(vsb_ctx *ctx, double gc, const int64_t *order_desc_mass);
+/* The same tick with the O(N^2) find_parents scan split over ranks: rank `part` of
+ * `parts` scans the row blocks part, part+parts, ... of the mass-sorted bodies (asynchronous);
+ * the int32 array vsb_find_parents_best_ptr returns (one entry per body in sorted order: sorted
+ * rank of the smallest enclosing COI, -1 = none; rows of other ranks hold -1) is reduced with
+ * MAX over the ranks, and every rank calls vsb_gravity_ref_finish (parents, gravity_one,
+ * integrator -- all O(N)).  order may be NULL in begin when it is already resident. */
+int vsb_gravity_ref_begin_async(vsb_ctx *ctx, const int64_t *order_desc_mass, int part, int parts);
+int vsb_find_parents_best_ptr(vsb_ctx *ctx, void **dptr_out);
+int vsb_gravity_ref_finish(vsb_ctx *ctx, double gc);
 
 /* A4  documented all-pairs model, documentation/orbital-physics/
  * 01-complex-orbit-model.txt:4-12, pair formula of gravity_one phys_editor.py:51-60.

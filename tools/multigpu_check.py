@@ -130,15 +130,37 @@ def main():
         sk.tick(2.0, k["body_pos"])
     ok_kep = np.array_equal(sk.get(K_EA), ea_all[sk.row0:sk.row1]) and \
         np.array_equal(sk.get(K_POS), pos_all[sk.row0:sk.row1])
-    flag = torch.tensor([int(ok), int(ok_host), int(ok_sym), int(ok_rep), int(ok_coll), int(ok_kep)],
-                        device="cuda")
+    # MODE_REF tick: find_parents scan split over the ranks + MAX all-reduce; bit-identical
+    from volatilespace_b200.dist import ShardedPhysics
+    from volatilespace_b200.phys_editor import Physics
+    from volatilespace_b200._lib import F_PARENTS
+    e = synth.plummer2d(30000, seed=21)
+    rng = np.random.default_rng(4)
+    econf = {"gc": e["gc"], "rad_mult": 179.0, "coi_coef": 0.7}
+    heavy = np.where(rng.uniform(0, 1, len(e["mass"])) < 0.01, 3000.0, 1.0)     # 1 % "planets" with moons
+    ebd = {"mass": e["mass"] * heavy, "den": np.full(len(e["mass"]), 3000.0)}
+    ebo = {"pos": e["pos"], "vel": e["vel"]}
+    ref_single = Physics(dev)
+    ref_single.load_system(econf, ebd, ebo)
+    ref_sh = ShardedPhysics(Device(local), rank, world)
+    ref_sh.load_system(econf, ebd, ebo)
+    for _ in range(3):
+        ref_single.gravity()
+        ref_sh.gravity()
+    par = ref_single.dev.get(F_PARENTS)
+    ok_ref = np.array_equal(par, ref_sh.dev.get(F_PARENTS)) and \
+        np.array_equal(ref_single.dev.get(F_POS), ref_sh.dev.get(F_POS)) and \
+        np.array_equal(ref_single.dev.get(F_VEL), ref_sh.dev.get(F_VEL))
+    n_children = int((par != 0).sum())
+    flag = torch.tensor([int(ok), int(ok_host), int(ok_sym), int(ok_rep), int(ok_coll), int(ok_kep),
+                         int(ok_ref)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("multigpu_check n=%d world=%d ticks=%d: sharded==single %s, host path %s, "
               "sym within tolerance %s, sym replicas identical %s, collision ticks (%d merges) %s, "
-              "kepler slices %s" %
+              "kepler slices %s, MODE_REF tick (%d bodies whose parent is not body 0) %s" %
               (n, world, ticks, *[bool(x) for x in flag.tolist()[:4]], n_merges,
-               bool(flag[4]), bool(flag[5])))
+               bool(flag[4]), bool(flag[5]), n_children, bool(flag[6])))
     dist.barrier()
     dist.destroy_process_group()
     if not all(flag.tolist()):

@@ -57,6 +57,9 @@ SIGNATURES = {
     "vsb_bodies_set_rows": [_ctx, _i64, _i64],
     "vsb_find_parents": [_ctx, _pv, _pv],
     "vsb_gravity_ref": [_ctx, _f64, _pv],
+    "vsb_gravity_ref_begin_async": [_ctx, _pv, C.c_int, C.c_int],
+    "vsb_find_parents_best_ptr": [_ctx, C.POINTER(C.c_void_p)],
+    "vsb_gravity_ref_finish": [_ctx, _f64],
     "vsb_allpairs_accel": [_ctx, _f64],
     "vsb_allpairs_integrate": [_ctx],
     "vsb_allpairs_step": [_ctx, _f64, _i64],

@@ -387,6 +387,37 @@ extern "C" int vsb_gravity_ref(vsb_ctx *c, double gc, const int64_t *order)
     return vsb_launch_gravity_ref(c, gc, (const int64_t *)c->order.p);
 }
 
+// Multi-GPU form of the MODE_REF tick (SURVEY 8e "find_parents"): rank `part` of `parts` scans its
+// row blocks of the mass-sorted bodies; the int32 array at vsb_find_parents_best_ptr (n entries,
+// -1 = no enclosing COI) is then reduced with MAX over the ranks and every rank finishes the tick.
+extern "C" int vsb_gravity_ref_begin_async(vsb_ctx *c, const int64_t *order, int part, int parts)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_gravity_ref_begin_async"));
+    VSB_CHECK(parts >= 1 && part >= 0 && part < parts, VSB_ERR_ARG,
+              "vsb_gravity_ref_begin_async: part %d of %d", part, parts);
+    VSB_TRY(upload_order(c, "vsb_gravity_ref_begin_async", order));
+    return vsb_launch_gravity_ref_begin(c, (const int64_t *)c->order.p, part, parts);
+}
+
+extern "C" int vsb_find_parents_best_ptr(vsb_ctx *c, void **dptr_out)
+{
+    CTX(c);
+    VSB_CHECK(dptr_out != nullptr, VSB_ERR_ARG, "vsb_find_parents_best_ptr: null output");
+    VSB_TRY(need_bodies(c, "vsb_find_parents_best_ptr"));
+    VSB_TRY(vsb_buf_reserve(c->sorted, (size_t)c->npad * (16 + 8 + 8 + 4)));
+    *dptr_out = (char *)c->sorted.p + (size_t)c->npad * 32;
+    return VSB_OK;
+}
+
+extern "C" int vsb_gravity_ref_finish(vsb_ctx *c, double gc)
+{
+    CTX(c);
+    VSB_TRY(need_bodies(c, "vsb_gravity_ref_finish"));
+    VSB_TRY(upload_order(c, "vsb_gravity_ref_finish", nullptr));
+    return vsb_launch_gravity_ref_finish(c, gc, (const int64_t *)c->order.p);
+}
+
 // Which all-pairs kernel runs: the symmetric one only when this context owns every row
 // (the row kernel is the one that shards); VSB_GRAVITY=rows|sym overrides the context mode.
 static bool use_sym(vsb_ctx *c)

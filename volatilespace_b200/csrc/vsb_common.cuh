@@ -265,6 +265,10 @@ int vsb_allpairs_chunks(int64_t n, int64_t *chunk_out);
 int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int integrate);
 // pair predicates (vsb_pairs.cu)
 int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order);
+int vsb_launch_find_parents_part(vsb_ctx *c, const int64_t *d_order, int part, int parts);
+int vsb_launch_find_parents_finish(vsb_ctx *c, const int64_t *d_order);
+int vsb_launch_gravity_ref_begin(vsb_ctx *c, const int64_t *d_order, int part, int parts);
+int vsb_launch_gravity_ref_finish(vsb_ctx *c, double gc, const int64_t *d_order);
 int vsb_launch_check_collision(vsb_ctx *c);
 int vsb_launch_check_collision_part(vsb_ctx *c, int part, int parts);
 int vsb_launch_check_collision_finish(vsb_ctx *c);

@@ -726,13 +726,23 @@ body_arrays arrays_of(vsb_ctx *c)
 
 }  // namespace
 
-int vsb_launch_gravity_ref(vsb_ctx *c, double gc, const int64_t *d_order)
+// The MODE_REF tick in two halves so that the find_parents scan can be split over ranks:
+//   begin : parents_old snapshot + this part's share of the scan (best[] in c->sorted)
+//   finish: best[] -> parents, gravity_one per body, chain composition, integrator
+int vsb_launch_gravity_ref_begin(vsb_ctx *c, const int64_t *d_order, int part, int parts)
 {
     const int64_t n = c->n;
     if (n <= 0) return VSB_OK;
     VSB_CUDA(cudaMemcpyAsync(c->parents_old, c->parents, sizeof(int64_t) * n,
                              cudaMemcpyDeviceToDevice, c->stream));
-    VSB_TRY(vsb_launch_find_parents(c, d_order));
+    return vsb_launch_find_parents_part(c, d_order, part, parts);
+}
+
+int vsb_launch_gravity_ref_finish(vsb_ctx *c, double gc, const int64_t *d_order)
+{
+    const int64_t n = c->n;
+    if (n <= 0) return VSB_OK;
+    VSB_TRY(vsb_launch_find_parents_finish(c, d_order));
     const unsigned g = (unsigned)((n + 255) / 256);
     ref_accel_kernel<<<g, 256, 0, c->stream>>>(n, c->mass, (const double2 *)c->pos, c->parents, gc,
                                                (double2 *)c->rel_vel);
@@ -756,6 +766,12 @@ int vsb_launch_gravity_ref(vsb_ctx *c, double gc, const int64_t *d_order)
     VSB_CUDA(cudaStreamSynchronize(c->stream));
     VSB_CHECK(h_over == 0, VSB_ERR_STATE, "gravity_ref: parent chain deeper than 48 levels");
     return VSB_OK;
+}
+
+int vsb_launch_gravity_ref(vsb_ctx *c, double gc, const int64_t *d_order)
+{
+    VSB_TRY(vsb_launch_gravity_ref_begin(c, d_order, 0, 1));
+    return vsb_launch_gravity_ref_finish(c, gc, d_order);
 }
 
 int vsb_launch_kepler_basic(vsb_ctx *c, double gc, double coi_coef)

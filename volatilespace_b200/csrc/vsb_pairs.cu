@@ -41,9 +41,10 @@ __global__ void fp_gather_kernel(const int64_t *__restrict__ order, const double
 // Thread <-> target rank r; sources are ranks k < r.  best[r] = max matching k.
 __global__ void __launch_bounds__(PB_BLOCK)
 fp_scan_kernel(const double2 *__restrict__ spos, const double *__restrict__ scoi2, int64_t n,
-               int64_t chunk_tiles, int *__restrict__ best)
+               int64_t chunk_tiles, int *__restrict__ best, int part, int parts)
 {
-    const int64_t r0 = (int64_t)blockIdx.x * PB_BLOCK;
+    // row blocks part, part+parts, ... of the mass-sorted bodies (the scan is triangular)
+    const int64_t r0 = ((int64_t)blockIdx.x * parts + part) * PB_BLOCK;
     const int64_t r = r0 + threadIdx.x;
     int64_t t0 = (int64_t)blockIdx.y * chunk_tiles;
     int64_t t1 = t0 + chunk_tiles;
@@ -191,7 +192,10 @@ int chunk_tiles_for(int64_t tiles, int64_t row_blocks, int sm_count)
 }  // namespace
 
 // d_order: device array (n) of body indices in descending-mass order.
-int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order)
+// Part `part` of `parts` of the scan: best[r] (sorted rank of the smallest enclosing COI, -1 = none)
+// for this part's row blocks; the other rows keep -1, so an elementwise MAX over the parts gives
+// the full array.  parts == 1 is the whole scan.
+int vsb_launch_find_parents_part(vsb_ctx *c, const int64_t *d_order, int part, int parts)
 {
     const int64_t n = c->n, npad = c->npad;
     if (n <= 0) return VSB_OK;
@@ -205,16 +209,37 @@ int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order)
     unsigned g = (unsigned)((npad + 255) / 256);
     fp_gather_kernel<<<g, 256, 0, c->stream>>>(d_order, (const double2 *)c->pos, c->coi, n, npad,
                                                spos, scoi2, rank, best);
+    c->launches += 1;
     const int64_t row_blocks = (n + PB_BLOCK - 1) / PB_BLOCK;
-    const int64_t tiles = npad / PB_TJ;
-    const int ct = chunk_tiles_for(tiles, row_blocks, c->sm_count);
-    dim3 grid((unsigned)row_blocks, (unsigned)((tiles + ct - 1) / ct));
-    fp_scan_kernel<<<grid, PB_BLOCK, 0, c->stream>>>(spos, scoi2, n, ct, best);
-    fp_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_order, best, n,
-                                                                          c->parents);
-    c->launches += 3;
+    const int64_t mine = (row_blocks - part + parts - 1) / parts;
+    if (mine > 0) {
+        const int64_t tiles = npad / PB_TJ;
+        const int ct = chunk_tiles_for(tiles, mine, c->sm_count);
+        dim3 grid((unsigned)mine, (unsigned)((tiles + ct - 1) / ct));
+        fp_scan_kernel<<<grid, PB_BLOCK, 0, c->stream>>>(spos, scoi2, n, ct, best, part, parts);
+        c->launches += 1;
+    }
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;
+}
+
+// best[] -> parents[] in body index space
+int vsb_launch_find_parents_finish(vsb_ctx *c, const int64_t *d_order)
+{
+    const int64_t n = c->n, npad = c->npad;
+    if (n <= 0) return VSB_OK;
+    const int *best = (const int *)((char *)c->sorted.p + (size_t)npad * 32);
+    fp_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_order, best, n,
+                                                                          c->parents);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
+
+int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order)
+{
+    VSB_TRY(vsb_launch_find_parents_part(c, d_order, 0, 1));
+    return vsb_launch_find_parents_finish(c, d_order);
 }
 
 // Exhaustive scan of the row blocks of one part (part of parts); the local minimum key lands in

@@ -117,6 +117,19 @@ class Device:
         order = None if order is None else i64(order)
         check(self.L.vsb_gravity_ref(self.h, float(gc), ptr(order)))
 
+    def gravity_ref_begin_async(self, order, part, parts):
+        """First half of the MODE_REF tick with this rank's share of the find_parents scan."""
+        order = None if order is None else i64(order)
+        check(self.L.vsb_gravity_ref_begin_async(self.h, ptr(order), int(part), int(parts)))
+
+    def find_parents_best_ptr(self):
+        p = C.c_void_p()
+        check(self.L.vsb_find_parents_best_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def gravity_ref_finish(self, gc):
+        check(self.L.vsb_gravity_ref_finish(self.h, float(gc)))
+
     def allpairs_accel(self, gc):
         check(self.L.vsb_allpairs_accel(self.h, float(gc)))
 

@@ -311,3 +311,48 @@ class ShardedKepler:
     def get(self, field):
         """This rank's slice of a state field (objects [row0, row1))."""
         return self.dev.kepler_get(self.kind, field, self.count)
+
+
+class ShardedPhysics:
+    """The MODE_REF editor tick (phys_editor.Physics.gravity, phys_editor.py:357-378) over `world`
+    ranks: the O(N^2) find_parents scan is split by row blocks of the mass-sorted
+    bodies, one MAX all-reduce of the int32 result array (4 B/body) completes it, and every rank
+    runs the O(N) remainder (gravity_one per body, chain composition, integrator) on its full
+    replica.  Integer results: bit-identical to the single-GPU tick."""
+
+    def __init__(self, device, rank=0, world=1, group=None):
+        from .phys_editor import Physics
+        self.inner = Physics(device)
+        self.dev, self.rank, self.world, self.group = self.inner.dev, rank, world, group
+        self._best_n = -1
+        self._stream = None
+
+    def __getattr__(self, name):
+        return getattr(self.inner, name)
+
+    def _best(self):
+        import torch
+        n = len(self.inner.mass)
+        if self._best_n != n:
+            view = _CudaView(self.dev.find_parents_best_ptr(), (n,), "<i4")
+            self._best_t = torch.as_tensor(view, device="cuda:%d" % self.dev.index)
+            if self._stream is None:
+                self._stream = torch.cuda.ExternalStream(self.dev.stream_handle(),
+                                                         device="cuda:%d" % self.dev.index)
+            self._best_n = n
+        return self._best_t
+
+    def gravity(self):
+        inner = self.inner
+        if self.world == 1 or len(inner.mass) <= 1024:     # small systems: the fused one-CTA tick
+            return inner.gravity()
+        import torch
+        import torch.distributed as dist
+        order = None if inner._order_on_device else inner._order()
+        best = self._best()
+        self.dev.gravity_ref_begin_async(order, self.rank, self.world)
+        with torch.cuda.stream(self._stream):
+            dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
+        self.dev.gravity_ref_finish(inner.gc)
+        inner._order_on_device = True
+        inner._touched("parents", "rel_vel", "vel", "pos")
