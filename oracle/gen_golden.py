@@ -818,6 +818,68 @@ def gen_vessel_events(ns, conf, bd, bod):
           "snapshots" % (nv, len(cw), len(sv), len(cx), len(cv)))
 
 
+def gen_mapfiles(ns, conf, bd, bod):
+    """N4 (savefile I/O): maps written by the reference's peripherals.save_file from seeded arrays
+    (Newtonian, and Keplerian with vessels) and what its load_file returns for them."""
+    rng = np.random.default_rng(20240625)
+    os.chdir(rh._WORKDIR)                       # save_file creates Maps/ and Saves/ in the CWD
+    mdir = os.path.join(OUT, "maps")
+    os.makedirs(mdir, exist_ok=True)
+    out = {}
+
+    def bodies(n):
+        atm = rng.uniform(0, 1, n) < 0.4
+        names = np.array(["Body %d" % i for i in range(n)])
+        names[3] = names[2]                     # duplicate name -> "Body 2 1" on save
+        return {"name": names, "mass": 10 ** rng.uniform(-1, 4, n), "den": rng.uniform(500, 6000, n),
+                "color": rng.integers(0, 256, (n, 3)), "atm_pres0": np.where(atm, rng.uniform(0.1, 90, n), 0.0),
+                "atm_scale_h": np.where(atm, rng.uniform(0.001, 0.1, n), 0.0),
+                "atm_den0": np.where(atm, rng.uniform(0.1, 70, n), 0.0)}
+
+    def dump(tag, res):
+        gd, cf, b, bo, v, vo = res
+        out[tag + "_game"] = np.array([gd["name"], gd["date"], str(gd["time"]), str(gd["vessel"])])
+        out[tag + "_conf_keys"] = np.array(list(cf.keys()))
+        out[tag + "_conf_vals"] = np.array([float(x) for x in cf.values()])
+        for k, a in b.items():
+            out[tag + "_b_" + k] = np.asarray(a)
+        for k, a in bo.items():
+            out[tag + "_bo_" + k] = np.asarray(a)
+        for k, a in v.items():
+            out[tag + "_v_" + k] = np.asarray(a)
+        for k, a in vo.items():
+            out[tag + "_vo_" + k] = np.asarray(a)
+
+    cfg = dict(conf)
+    # Newtonian map
+    n = 40
+    b = bodies(n)
+    bo = {"pos": rng.uniform(-1e5, 1e5, (n, 2)), "vel": rng.uniform(-3, 3, (n, 2))}
+    gd = {"name": "Newtonian test", "date": "01.01.2024 12:00", "time": 1234.5, "vessel": None}
+    path = os.path.join(mdir, "newton.ini")
+    ns.peripherals.save_file(path, gd, cfg, b, bo)
+    dump("newton", ns.peripherals.load_file(path))
+    # Keplerian savegame with vessels
+    n, nv = 30, 12
+    b = bodies(n)
+    bo = {"a": rng.uniform(1e3, 1e5, n), "ecc": rng.uniform(0, 0.9, n), "pe_arg": rng.uniform(0, 6.28, n),
+          "ma": rng.uniform(0, 6.28, n), "ref": rng.integers(0, n, n), "dir": rng.choice([-1.0, 1.0], n)}
+    v = {"name": np.array(["Vessel %d" % i for i in range(nv)]), "mass": rng.uniform(1, 50, nv),
+         "rot_angle": rng.uniform(0, 6.28, nv), "rot_acc": rng.uniform(0, 0.1, nv),
+         "sprite": np.array(["sprite%d.png" % (i % 3) for i in range(nv)])}
+    vecc = np.where(rng.uniform(0, 1, nv) < 0.4, rng.uniform(1.1, 3, nv), rng.uniform(0, 0.9, nv))
+    vo = {"a": rng.uniform(100, 5000, nv) * np.where(vecc > 1, -1, 1), "ecc": vecc,
+          "pe_arg": rng.uniform(0, 6.28, nv), "ma": rng.uniform(-3, 6, nv), "ref": rng.integers(0, n, nv),
+          "dir": rng.choice([-1.0, 1.0], nv)}
+    gd = {"name": "Kepler test", "date": "02.02.2024 08:30", "time": 99.0, "vessel": 3}
+    path = os.path.join(mdir, "kepler.ini")
+    ns.peripherals.save_file(path, gd, cfg, b, bo, v, vo)
+    dump("kepler", ns.peripherals.load_file(path))
+    # the built-in map: arrays only (the file itself stays in the reference tree)
+    dump("solar", ns.peripherals.load_file(ns.solar_system_ini))
+    save("mapfiles", **out)
+
+
 def main():
     """All fixtures, or only the ones named on the command line (e.g. `vessel_points`)."""
     ns = rh.load()
@@ -836,6 +898,7 @@ def main():
     if want("intersect"): gen_intersect(ns)
     if want("vessel_points"): gen_vessel_points(ns, conf, bd, bod)
     if want("vessel_events"): gen_vessel_events(ns, conf, bd, bod)
+    if want("mapfiles"): gen_mapfiles(ns, conf, bd, bod)
 
 
 if __name__ == "__main__":
