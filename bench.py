@@ -365,6 +365,35 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
                     "vessel_points, dev container)"}
     except Exception as e:
         out["vessel_points160"] = {"error": str(e)[:200]}
+
+    # SURVEY 8f N2, per-tick scans: check_warp + predict_enter_coi_service + cross_coi detection on
+    # one recorded state of the reference's game loop (140 vessels) and on the same state tiled to
+    # 1 M vessels, through the host-array calls (uploads included)
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "vessel_events.npz"))
+        v, p = g["cw0_v"], g["cw0_p"]
+        res = {}
+        for label, reps_tile in (("140", 1), ("1m", 7490)):
+            vv, pp = np.tile(v, (reps_tile, 1)), np.tile(p, (reps_tile, 1))
+            cols = [np.ascontiguousarray(vv[:, c]) for c in range(14)]
+            bi, ba, cl, ce = (np.ascontiguousarray(x) for x in (pp[:, 0:2], pp[:, 2:4], pp[:, 4:6], pp[:, 6:12]))
+            hold = np.zeros(len(vv), dtype=np.uint8)
+            def scans():
+                dev.host_check_warp(cols[3], cols[6], cols[8], cols[7], cols[5], bi, ba, cl, ce, 5.0, hold)
+                dev.host_enter_coi_service(cols[6], cols[9], cols[8], ce, False)
+                dev.host_cross_scan(cols[3], cols[6], cols[9], cols[8], bi, cl, ce)
+            scans()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                scans()
+            res["ms_per_tick_" + label] = (time.perf_counter() - t0) / 5 * 1e3
+            res["vessels_" + label] = int(len(vv))
+        res["note"] = ("three host-array calls per tick, uploads of the per-vessel arrays included "
+                       "(320 MB per tick at 1 M vessels: PCIe-bound); the reference's whole game tick "
+                       "ran at ~67 ms at 140 vessels while the fixture was generated")
+        out["vessel_event_scans"] = res
+    except Exception as e:
+        out["vessel_event_scans"] = {"error": str(e)[:200]}
     return out
 
 
