@@ -388,6 +388,21 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
                 scans()
             res["ms_per_tick_" + label] = (time.perf_counter() - t0) / 5 * 1e3
             res["vessels_" + label] = int(len(vv))
+        # the same three scans on device-resident state (1 M vessels): nothing per-vessel over PCIe
+        n1 = len(vv)
+        dev.kepler_load(KIND_VESSEL, 8, cols[0], cols[1], cols[2], cols[3], cols[4], cols[5],
+                        cols[6], cols[7], cols[8], np.zeros(n1, dtype=np.int64))
+        dev.vessel_events_load(cols[11], cols[12], cols[13], bi, ba, cl, ce, None, cols[9])
+        def resident():
+            dev.vessel_check_warp(5.0)
+            dev.vessel_enter_coi_service(n1, False)
+            dev.vessel_cross_scan()
+        resident()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            resident()
+        res["ms_per_tick_1m_resident"] = (time.perf_counter() - t0) / 10 * 1e3
+        dev.kepler_free(KIND_VESSEL)
         res["note"] = ("three host-array calls per tick, uploads of the per-vessel arrays included "
                        "(320 MB per tick at 1 M vessels: PCIe-bound); the reference's whole game tick "
                        "ran at ~67 ms at 140 vessels while the fixture was generated")

@@ -371,6 +371,32 @@ int vsb_host_cross_apply(vsb_ctx *ctx, int64_t nev, const int32_t *kind, const d
                          const int64_t *ref, const int64_t *new_ref, int64_t nb,
                          const double *body7, double gc, double *out6, int32_t *status);
 
+/* The same, on device-resident state (no per-vessel array crosses PCIe per tick).  The vessel
+ * elements are the KIND_VESSEL Kepler state (vsb_kepler_load / vsb_kepler_move / vsb_kepler_tick,
+ * which now also keep the previous tick's ea: self.prev_ea, phys_vessel.py:486);
+ * vsb_vessel_events_load adds the orbit points, the physical_hold mask and the derived pe_d /
+ * ap_d / period of every vessel (NULL points = NaN, NULL hold = empty, NULL prev_ea = current ea).
+ * vsb_vessel_points fills the resident points (body12 / body_ref as in vsb_host_vessel_points);
+ * vsb_vessel_check_warp / _enter_coi_service / _cross_scan are the three per-tick scans;
+ * vsb_vessel_events_get copies rows [first, first+count) back (NULL = skip an array);
+ * vsb_vessel_events_set_orbit refreshes one vessel's derived elements after change_vessel. */
+int vsb_vessel_events_load(vsb_ctx *ctx, const double *body_impact, const double *body_enter_atm,
+                           const double *coi_leave, const double *coi_enter, const uint8_t *hold,
+                           const double *prev_ea, const double *pe_d, const double *ap_d,
+                           const double *period);
+int vsb_vessel_events_set_orbit(vsb_ctx *ctx, int64_t vessel, double pe_d, double ap_d,
+                                double period);
+int vsb_vessel_events_get(vsb_ctx *ctx, int64_t first, int64_t count, double *body_impact,
+                          double *body_enter_atm, double *coi_leave, double *coi_enter,
+                          uint8_t *hold, double *prev_ea);
+int vsb_vessel_points(vsb_ctx *ctx, int64_t nb, const double *body12, const int64_t *body_ref,
+                      int64_t nsel, const int64_t *sel, int64_t entered_coi, int64_t left_coi,
+                      int64_t left_coi_prev_ref, int only_enter_coi, int64_t steps_limit);
+int vsb_vessel_check_warp(vsb_ctx *ctx, double warp, int64_t *out3);
+int vsb_vessel_enter_coi_service(vsb_ctx *ctx, int crossing_pending, int64_t *idx_out,
+                                 int64_t *count_out);
+int vsb_vessel_cross_scan(vsb_ctx *ctx, int64_t *out2);
+
 /* --------------------------------------------- per-frame body passes
  * Physics.body (phys_editor.py:577-599, without the radius, which stays host numpy),
  * Physics.temp_color (:602-651) and Physics.classify (:654-670) in one pass over host arrays.

@@ -728,3 +728,66 @@ def test_vessel_event_argument_errors(dev):
     assert dev.host_check_warp(z + 0.5, z + 1, z, z, z + 0.01, nan2, nan2, nan2, nan6, 1.0, hold) \
         == (None, None, 0)
     assert not hold.any()
+
+
+def test_resident_vessel_events(dev):
+    """The device-resident form of the vessel event state: same kernels as the host-array calls,
+    so the answers must be identical bit for bit; kepler_move keeps prev_ea."""
+    from conftest import VS, events_body12, events_vessel12, split_points
+    from volatilespace_b200._lib import KIND_VESSEL, K_EA
+    g = golden("vessel_events")
+    opt = lambda x: None if x < 0 else int(x)
+    P = 8
+    t = np.linspace(-np.pi, np.pi, P)
+
+    def load(v, p, ref, hold=None):
+        col = lambda name: np.ascontiguousarray(v[:, VS[name]])
+        dev.kepler_load(KIND_VESSEL, P, col("a"), col("b"), col("f"), col("ecc"), col("pea"),
+                        col("n"), col("dr"), col("ma"), col("ea"), ref, t)
+        bi, ba, cl, ce = split_points(p)
+        dev.vessel_events_load(col("pe_d"), col("ap_d"), col("period"), bi, ba, cl, ce, hold,
+                               col("prev_ea"))
+        return bi, ba, cl, ce
+
+    nv = len(g["cw0_v"])
+    zref = np.zeros(nv, dtype=np.int64)
+    for k in range(0, int(g["n_cw"]), 3):
+        v, o = g["cw%d_v" % k], g["cw%d_out" % k]
+        load(v, g["cw%d_p" % k], zref, g["cw%d_hold_in" % k])
+        assert dev.vessel_check_warp(o[3]) == (opt(o[0]), opt(o[1]), int(o[2])), k
+        assert np.array_equal(dev.vessel_events_get(nv)["hold"], g["cw%d_hold_out" % k]), k
+    for k in range(0, int(g["n_sv"]), 2):
+        v, fl = g["sv%d_v" % k], g["sv%d_flags" % k]
+        load(v, g["sv%d_p" % k], zref)
+        calls = dev.vessel_enter_coi_service(nv, fl[0] >= 0 or fl[1] >= 0)
+        assert np.array_equal(calls, g["sv%d_calls" % k]), k
+    for k in range(0, int(g["n_cx"]), 2):
+        v = g["cx%d_v" % k]
+        bi, ba, cl, ce = load(v, g["cx%d_p" % k], g["cx%d_ref" % k])
+        want = dev.host_cross_scan(v[:, VS["ecc"]], v[:, VS["dr"]], v[:, VS["prev_ea"]],
+                                   v[:, VS["ea"]], bi, cl, ce)
+        assert dev.vessel_cross_scan() == want, k
+    # points on resident state == points over host arrays (one change_vessel snapshot)
+    k = 0
+    v, ref, fl = g["cv%d_v" % k], g["cv%d_ref" % k], g["cv%d_flags" % k]
+    sel = np.flatnonzero(v[:, VS["ecc"]] < 0.8)[:50]
+    bi, ba, cl, ce = (x.copy() for x in load(v, g["cv%d_p" % k], ref))
+    body12 = events_body12(g, g["cv%d_bma" % k], g["cv%d_bea" % k])
+    kw = dict(sel=sel, entered_coi=opt(fl[0]), left_coi=opt(fl[1]), left_coi_prev_ref=opt(fl[2]),
+              steps_limit=int(g["steps_limit"]))
+    dev.vessel_points(body12, g["body_ref"], **kw)
+    dev.host_vessel_points(events_vessel12(v), ref, body12, g["body_ref"], bi, ba, cl, ce, **kw)
+    got = dev.vessel_events_get(nv)
+    for key, want in (("body_impact", bi), ("body_enter_atm", ba), ("coi_leave", cl),
+                      ("coi_enter", ce)):
+        assert np.array_equal(got[key], want, equal_nan=True), key
+    # kepler_move keeps the previous anomalies
+    ea_before = dev.kepler_get(KIND_VESSEL, K_EA, nv)
+    dev.kepler_move(KIND_VESSEL, 3.0, np.zeros((len(g["body_mass"]), 2)))
+    assert np.array_equal(dev.vessel_events_get(nv)["prev_ea"], ea_before)
+    assert not np.array_equal(dev.kepler_get(KIND_VESSEL, K_EA, nv), ea_before)
+    dev.vessel_events_set_orbit(5, 1.0, 2.0, 3.0)
+    from volatilespace_b200._lib import VsbError
+    dev.kepler_free(KIND_VESSEL)
+    with pytest.raises(VsbError):
+        dev.vessel_check_warp(1.0)

@@ -111,6 +111,13 @@ SIGNATURES = {
     "vsb_host_enter_coi_service": [_ctx, _i64, _pv, _pv, _pv, _pv, C.c_int, _pv],
     "vsb_host_cross_scan": [_ctx, _i64] + [_pv] * 7 + [_pv],
     "vsb_host_cross_apply": [_ctx, _i64, _pv, _pv, _pv, _pv, _i64, _pv, _f64, _pv, _pv],
+    "vsb_vessel_events_load": [_ctx] + [_pv] * 9,
+    "vsb_vessel_events_set_orbit": [_ctx, _i64, _f64, _f64, _f64],
+    "vsb_vessel_events_get": [_ctx, _i64, _i64] + [_pv] * 6,
+    "vsb_vessel_points": [_ctx, _i64, _pv, _pv, _i64, _pv, _i64, _i64, _i64, C.c_int, _i64],
+    "vsb_vessel_check_warp": [_ctx, _f64, _pv],
+    "vsb_vessel_enter_coi_service": [_ctx, C.c_int, _pv, _pi],
+    "vsb_vessel_cross_scan": [_ctx, _pv],
     "vsb_set_march_mode": [_ctx, C.c_int],
     "vsb_host_running_sum": [_f64, _f64, _i64, C.c_int, _f64, _i64, _pv, _pv, _pv, _pv],
     "vsb_march_stats": [_ctx, _pv],

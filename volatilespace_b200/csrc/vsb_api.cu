@@ -135,6 +135,7 @@ static void free_kepler(vsb_kepler_state &k)
     if (k.ref_pos && !k.ref_pos_borrowed) cudaFree(k.ref_pos);
     vsb_buf_free(k.curves);
     vsb_buf_free(k.quirk_idx);
+    vsb_buf_free(k.ev);
     free(k.h_ref);
     int kind = k.kind;
     k = vsb_kepler_state();
@@ -1116,6 +1117,16 @@ static int vessel_ref_pos(vsb_ctx *c, vsb_kepler_state &k, const double *body_po
     return VSB_OK;
 }
 
+// phys_vessel.move keeps the anomalies of the previous tick (self.prev_ea, phys_vessel.py:486);
+// the resident event state needs them for cross_coi and predict_enter_coi_service
+static int keep_prev_ea(vsb_ctx *c, vsb_kepler_state &k)
+{
+    if (k.kind == VSB_KIND_VESSEL && k.ev_n == k.n && k.ev_prev_ea)
+        VSB_CUDA(cudaMemcpyAsync(k.ev_prev_ea, k.ea, 8 * (size_t)k.n, cudaMemcpyDeviceToDevice,
+                                 c->stream));
+    return VSB_OK;
+}
+
 extern "C" int vsb_kepler_move(vsb_ctx *c, int kind, double warp, const double *body_pos,
                                int64_t nref)
 {
@@ -1124,6 +1135,7 @@ extern "C" int vsb_kepler_move(vsb_ctx *c, int kind, double warp, const double *
     VSB_TRY(kep_of(c, "vsb_kepler_move", kind, &k));
     VSB_CHECK(k->n > 0, VSB_ERR_STATE, "vsb_kepler_move: no state loaded for this kind");
     if (kind == VSB_KIND_VESSEL) VSB_TRY(vessel_ref_pos(c, *k, body_pos, nref));
+    VSB_TRY(keep_prev_ea(c, *k));
     VSB_TRY(vsb_launch_kepler_move(c, *k, warp));
     VSB_CUDA(cudaStreamSynchronize(c->stream));
     return VSB_OK;
@@ -1159,6 +1171,7 @@ extern "C" int vsb_kepler_tick(vsb_ctx *c, int kind, double warp, const double *
     VSB_TRY(reserve_curves(*k));
     if (kind == VSB_KIND_VESSEL) {
         VSB_TRY(vessel_ref_pos(c, *k, body_pos, nref));
+        VSB_TRY(keep_prev_ea(c, *k));
         VSB_TRY(vsb_launch_vessel_tick(c, *k, warp, (double *)k->curves.p));
     } else {
         VSB_TRY(vsb_launch_kepler_move(c, *k, warp));
@@ -1179,6 +1192,7 @@ extern "C" int vsb_kepler_tick_async(vsb_ctx *c, int kind, double warp)
     if (kind == VSB_KIND_VESSEL) {
         VSB_CHECK(k->ref_pos != nullptr, VSB_ERR_STATE,
                   "vsb_kepler_tick_async(VESSEL): parent positions not resident");
+        VSB_TRY(keep_prev_ea(c, *k));
         return vsb_launch_vessel_tick(c, *k, warp, (double *)k->curves.p);
     }
     VSB_TRY(vsb_launch_kepler_move(c, *k, warp));
@@ -1354,113 +1368,6 @@ extern "C" int vsb_set_march_mode(vsb_ctx *c, int sequential)
     return VSB_OK;
 }
 
-// phys_vessel.Physics.points for the vessels in sel (NULL = all), phys_vessel.py:372-474
-extern "C" int vsb_host_vessel_points(vsb_ctx *c, int64_t nv, int64_t nb, const double *vessel12,
-                                      const int64_t *v_ref, const double *body12,
-                                      const int64_t *body_ref, int64_t nsel, const int64_t *sel,
-                                      int64_t entered_coi, int64_t left_coi,
-                                      int64_t left_coi_prev_ref, int only_enter_coi,
-                                      int64_t steps_limit, double *body_impact,
-                                      double *body_enter_atm, double *coi_leave, double *coi_enter)
-{
-    CTX(c);
-    VSB_CHECK(nv >= 0 && nb >= 0 && nsel >= 0 && steps_limit > 0 && steps_limit < (1ll << 31),
-              VSB_ERR_ARG, "vsb_host_vessel_points: bad argument");
-    if (nv == 0) return VSB_OK;
-    VSB_CHECK(vessel12 && v_ref && body12 && body_ref && body_impact && body_enter_atm && coi_leave &&
-                  coi_enter && nb > 0,
-              VSB_ERR_ARG, "vsb_host_vessel_points: null array");
-    std::vector<int64_t> h_sel;
-    if (sel) {
-        h_sel.assign(sel, sel + nsel);
-    } else {
-        h_sel.resize((size_t)nv);
-        for (int64_t i = 0; i < nv; ++i) h_sel[(size_t)i] = i;
-    }
-    nsel = (int64_t)h_sel.size();
-    if (nsel == 0) return VSB_OK;
-    for (int64_t v : h_sel)
-        VSB_CHECK(v >= 0 && v < nv, VSB_ERR_ARG, "vsb_host_vessel_points: vessel %lld out of range",
-                  (long long)v);
-    for (int64_t i = 0; i < nv; ++i)
-        VSB_CHECK(v_ref[i] >= 0 && v_ref[i] < nb, VSB_ERR_ARG,
-                  "vsb_host_vessel_points: ref of vessel %lld out of range", (long long)i);
-    // check_bodies = np.where(body_ref == ref)[0] minus body 0 and left_coi_prev_ref (:423-424):
-    // children lists by counting sort (ascending body index inside each list)
-    std::vector<int64_t> cstart((size_t)nb + 1, 0), child((size_t)nb);
-    for (int64_t b = 0; b < nb; ++b)
-        if (body_ref[b] >= 0 && body_ref[b] < nb) ++cstart[(size_t)body_ref[b] + 1];
-    for (int64_t r = 0; r < nb; ++r) cstart[(size_t)r + 1] += cstart[(size_t)r];
-    {
-        std::vector<int64_t> fill(cstart.begin(), cstart.end() - 1);
-        for (int64_t b = 0; b < nb; ++b)
-            if (body_ref[b] >= 0 && body_ref[b] < nb) child[(size_t)fill[(size_t)body_ref[b]]++] = b;
-    }
-    std::vector<int64_t> offsets((size_t)nsel + 1, 0), pair_s, pair_body;
-    for (int64_t s = 0; s < nsel; ++s) {
-        const int64_t ref = v_ref[h_sel[(size_t)s]];
-        for (int64_t k = cstart[(size_t)ref]; k < cstart[(size_t)ref + 1]; ++k) {
-            const int64_t b = child[(size_t)k];
-            if (b == 0 || b == left_coi_prev_ref) continue;
-            pair_s.push_back(s);
-            pair_body.push_back(b);
-        }
-        offsets[(size_t)s + 1] = (int64_t)pair_s.size();
-    }
-    const int64_t np_ = (int64_t)pair_s.size();
-    // staging layout (8-byte words, every array 32-word aligned)
-    auto al = [](size_t w) { return (w + 31) / 32 * 32; };
-    const size_t NV = (size_t)nv, NB = (size_t)nb, NS = (size_t)nsel, NP = (size_t)np_;
-    size_t w = 0;
-    auto take = [&](size_t words) { size_t o = w; w += al(words); return o; };
-    const size_t o_v12 = take(12 * NV), o_vref = take(NV), o_b12 = take(12 * NB), o_sel = take(NS),
-                 o_off = take(NS + 1), o_ps = take(NP), o_pb = take(NP), o_imp = take(2 * NV),
-                 o_atm = take(2 * NV), o_lv = take(2 * NV), o_en = take(6 * NV), o_eaeff = take(NS),
-                 o_vd = take(10 * NP), o_bd = take(10 * NP), o_out = take(5 * NP),
-                 o_valid = take((NP + 7) / 8);
-    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * w));
-    VSB_TRY(march_work_reserve(c, np_ > 0 ? np_ : 1));
-    VSB_CUDA(cudaMemsetAsync(c->march_stats.p, 0, 32, c->stream));
-    double *base = (double *)c->host_stage.p;
-    auto up = [&](size_t off, const void *src, size_t words) -> int {
-        if (words == 0) return VSB_OK;
-        VSB_CUDA(cudaMemcpyAsync(base + off, src, 8 * words, cudaMemcpyHostToDevice, c->stream));
-        return VSB_OK;
-    };
-    VSB_TRY(up(o_v12, vessel12, 12 * NV));
-    VSB_TRY(up(o_vref, v_ref, NV));
-    VSB_TRY(up(o_b12, body12, 12 * NB));
-    VSB_TRY(up(o_sel, h_sel.data(), NS));
-    VSB_TRY(up(o_off, offsets.data(), NS + 1));
-    VSB_TRY(up(o_ps, pair_s.data(), NP));
-    VSB_TRY(up(o_pb, pair_body.data(), NP));
-    VSB_TRY(up(o_imp, body_impact, 2 * NV));
-    VSB_TRY(up(o_atm, body_enter_atm, 2 * NV));
-    VSB_TRY(up(o_lv, coi_leave, 2 * NV));
-    VSB_TRY(up(o_en, coi_enter, 6 * NV));
-    const int64_t *d_sel = (const int64_t *)(base + o_sel), *d_vref = (const int64_t *)(base + o_vref);
-    VSB_TRY(vsb_launch_points_vessel(c, nsel, d_sel, base + o_v12, d_vref, base + o_b12, entered_coi,
-                                     left_coi, only_enter_coi, base + o_imp, base + o_atm,
-                                     base + o_lv, base + o_eaeff));
-    VSB_TRY(vsb_launch_points_pairs(c, np_, (const int64_t *)(base + o_ps),
-                                    (const int64_t *)(base + o_pb), d_sel, base + o_v12, d_vref,
-                                    base + o_b12, left_coi, base + o_lv, base + o_eaeff, base + o_vd,
-                                    base + o_bd, (unsigned char *)(base + o_valid)));
-    VSB_TRY(vsb_launch_predict_enter_coi(c, np_, base + o_vd, base + o_bd,
-                                         (const unsigned char *)(base + o_valid), 1e-5,
-                                         (int)steps_limit, base + o_out, c->march_stats.p,
-                                         c->march_sequential));
-    VSB_TRY(vsb_launch_points_select(c, nsel, d_sel, (const int64_t *)(base + o_off),
-                                     (const int64_t *)(base + o_pb),
-                                     (const unsigned char *)(base + o_valid), base + o_out,
-                                     base + o_eaeff, base + o_v12, base + o_en));
-    VSB_CUDA(cudaMemcpyAsync(body_impact, base + o_imp, 16 * NV, cudaMemcpyDeviceToHost, c->stream));
-    VSB_CUDA(cudaMemcpyAsync(body_enter_atm, base + o_atm, 16 * NV, cudaMemcpyDeviceToHost, c->stream));
-    VSB_CUDA(cudaMemcpyAsync(coi_leave, base + o_lv, 16 * NV, cudaMemcpyDeviceToHost, c->stream));
-    return d2h(c, coi_enter, base + o_en, 48 * NV);
-}
-
-// ---------------------------------------------------------------- N2: per-tick vessel events
 // staging helper: consecutive 256-byte aligned device arrays inside host_stage
 struct stage_cursor {
     char *base;
@@ -1480,6 +1387,146 @@ static int up_f64(vsb_ctx *c, double *dst, const double *src, size_t count)
     return VSB_OK;
 }
 
+// ---- phys_vessel.Physics.points (phys_vessel.py:372-474): shared between the host-array call
+// and the resident vessel state.  The (vessel, candidate body) pairs are listed on the host:
+// check_bodies = np.where(body_ref == ref)[0] minus body 0 and left_coi_prev_ref (:423-424).
+struct points_plan {
+    std::vector<int64_t> sel, offsets, pair_s, pair_body;
+};
+
+static int points_plan_build(const char *who, int64_t nv, int64_t nb, const int64_t *v_ref,
+                             const int64_t *body_ref, int64_t nsel, const int64_t *sel,
+                             int64_t left_coi_prev_ref, points_plan &pl)
+{
+    if (sel) {
+        pl.sel.assign(sel, sel + nsel);
+    } else {
+        pl.sel.resize((size_t)nv);
+        for (int64_t i = 0; i < nv; ++i) pl.sel[(size_t)i] = i;
+    }
+    for (int64_t v : pl.sel)
+        VSB_CHECK(v >= 0 && v < nv, VSB_ERR_ARG, "%s: vessel %lld out of range", who, (long long)v);
+    for (int64_t i = 0; i < nv; ++i)
+        VSB_CHECK(v_ref[i] >= 0 && v_ref[i] < nb, VSB_ERR_ARG, "%s: ref of vessel %lld out of range",
+                  who, (long long)i);
+    // children lists by counting sort (ascending body index inside each list)
+    std::vector<int64_t> cstart((size_t)nb + 1, 0), child((size_t)nb);
+    for (int64_t b = 0; b < nb; ++b)
+        if (body_ref[b] >= 0 && body_ref[b] < nb) ++cstart[(size_t)body_ref[b] + 1];
+    for (int64_t r = 0; r < nb; ++r) cstart[(size_t)r + 1] += cstart[(size_t)r];
+    {
+        std::vector<int64_t> fill(cstart.begin(), cstart.end() - 1);
+        for (int64_t b = 0; b < nb; ++b)
+            if (body_ref[b] >= 0 && body_ref[b] < nb) child[(size_t)fill[(size_t)body_ref[b]]++] = b;
+    }
+    const size_t ns = pl.sel.size();
+    pl.offsets.assign(ns + 1, 0);
+    for (size_t s = 0; s < ns; ++s) {
+        const int64_t ref = v_ref[pl.sel[s]];
+        for (int64_t k = cstart[(size_t)ref]; k < cstart[(size_t)ref + 1]; ++k) {
+            const int64_t b = child[(size_t)k];
+            if (b == 0 || b == left_coi_prev_ref) continue;
+            pl.pair_s.push_back((int64_t)s);
+            pl.pair_body.push_back(b);
+        }
+        pl.offsets[s + 1] = (int64_t)pl.pair_s.size();
+    }
+    return VSB_OK;
+}
+
+static size_t al32(size_t w) { return (w + 31) / 32 * 32; }
+
+// 8-byte words of device scratch the pipeline needs for a plan
+static size_t points_scratch_words(const points_plan &pl)
+{
+    const size_t NS = pl.sel.size(), NP = pl.pair_s.size();
+    return al32(NS) + al32(NS + 1) + 2 * al32(NP) + al32(NS) + 2 * al32(10 * NP) + al32(5 * NP) +
+           al32((NP + 7) / 8);
+}
+
+// scratch: device memory of points_scratch_words(pl) words.  The four result arrays are updated
+// in place for the selected vessels.
+static int points_run(vsb_ctx *c, const points_plan &pl, double *scratch, const double *d_v12,
+                      const int64_t *d_vref, const double *d_b12, int64_t entered_coi,
+                      int64_t left_coi, int only_enter_coi, int64_t steps_limit, double *d_imp,
+                      double *d_atm, double *d_lv, double *d_en)
+{
+    const size_t NS = pl.sel.size(), NP = pl.pair_s.size();
+    if (NS == 0) return VSB_OK;
+    size_t w = 0;
+    auto take = [&](size_t words) { double *p = scratch + w; w += al32(words); return p; };
+    int64_t *d_sel = (int64_t *)take(NS), *d_off = (int64_t *)take(NS + 1),
+            *d_ps = (int64_t *)take(NP), *d_pb = (int64_t *)take(NP);
+    double *d_eaeff = take(NS), *d_vd = take(10 * NP), *d_bd = take(10 * NP), *d_out = take(5 * NP);
+    unsigned char *d_valid = (unsigned char *)take((NP + 7) / 8);
+    auto up = [&](void *dst, const void *src, size_t words) -> int {
+        if (words == 0) return VSB_OK;
+        VSB_CUDA(cudaMemcpyAsync(dst, src, 8 * words, cudaMemcpyHostToDevice, c->stream));
+        return VSB_OK;
+    };
+    VSB_TRY(up(d_sel, pl.sel.data(), NS));
+    VSB_TRY(up(d_off, pl.offsets.data(), NS + 1));
+    VSB_TRY(up(d_ps, pl.pair_s.data(), NP));
+    VSB_TRY(up(d_pb, pl.pair_body.data(), NP));
+    VSB_TRY(vsb_buf_reserve(c->march_stats, vsb_march_work_bytes(NP > 0 ? (int64_t)NP : 1)));
+    VSB_CUDA(cudaMemsetAsync(c->march_stats.p, 0, 64, c->stream));
+    VSB_TRY(vsb_launch_points_vessel(c, (int64_t)NS, d_sel, d_v12, d_vref, d_b12, entered_coi,
+                                     left_coi, only_enter_coi, d_imp, d_atm, d_lv, d_eaeff));
+    VSB_TRY(vsb_launch_points_pairs(c, (int64_t)NP, d_ps, d_pb, d_sel, d_v12, d_vref, d_b12, left_coi,
+                                    d_lv, d_eaeff, d_vd, d_bd, d_valid));
+    VSB_TRY(vsb_launch_predict_enter_coi(c, (int64_t)NP, d_vd, d_bd, d_valid, 1e-5, (int)steps_limit,
+                                         d_out, c->march_stats.p, c->march_sequential));
+    VSB_TRY(vsb_launch_points_select(c, (int64_t)NS, d_sel, d_off, d_pb, d_valid, d_out, d_eaeff,
+                                     d_v12, d_en));
+    return VSB_OK;
+}
+
+// phys_vessel.Physics.points for the vessels in sel (NULL = all), over host arrays
+extern "C" int vsb_host_vessel_points(vsb_ctx *c, int64_t nv, int64_t nb, const double *vessel12,
+                                      const int64_t *v_ref, const double *body12,
+                                      const int64_t *body_ref, int64_t nsel, const int64_t *sel,
+                                      int64_t entered_coi, int64_t left_coi,
+                                      int64_t left_coi_prev_ref, int only_enter_coi,
+                                      int64_t steps_limit, double *body_impact,
+                                      double *body_enter_atm, double *coi_leave, double *coi_enter)
+{
+    CTX(c);
+    VSB_CHECK(nv >= 0 && nb >= 0 && nsel >= 0 && steps_limit > 0 && steps_limit < (1ll << 31),
+              VSB_ERR_ARG, "vsb_host_vessel_points: bad argument");
+    if (nv == 0) return VSB_OK;
+    VSB_CHECK(vessel12 && v_ref && body12 && body_ref && body_impact && body_enter_atm && coi_leave &&
+                  coi_enter && nb > 0,
+              VSB_ERR_ARG, "vsb_host_vessel_points: null array");
+    points_plan pl;
+    VSB_TRY(points_plan_build("vsb_host_vessel_points", nv, nb, v_ref, body_ref, nsel, sel,
+                              left_coi_prev_ref, pl));
+    if (pl.sel.empty()) return VSB_OK;
+    const size_t NV = (size_t)nv, NB = (size_t)nb;
+    const size_t own = al32(12 * NV) + al32(NV) + al32(12 * NB) + 3 * al32(2 * NV) + al32(6 * NV);
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * (own + points_scratch_words(pl))));
+    double *base = (double *)c->host_stage.p;
+    size_t w = 0;
+    auto take = [&](size_t words) { double *p = base + w; w += al32(words); return p; };
+    double *d_v12 = take(12 * NV);
+    int64_t *d_vref = (int64_t *)take(NV);
+    double *d_b12 = take(12 * NB), *d_imp = take(2 * NV), *d_atm = take(2 * NV), *d_lv = take(2 * NV),
+           *d_en = take(6 * NV);
+    VSB_TRY(up_f64(c, d_v12, vessel12, 12 * NV));
+    VSB_CUDA(cudaMemcpyAsync(d_vref, v_ref, 8 * NV, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(up_f64(c, d_b12, body12, 12 * NB));
+    VSB_TRY(up_f64(c, d_imp, body_impact, 2 * NV));
+    VSB_TRY(up_f64(c, d_atm, body_enter_atm, 2 * NV));
+    VSB_TRY(up_f64(c, d_lv, coi_leave, 2 * NV));
+    VSB_TRY(up_f64(c, d_en, coi_enter, 6 * NV));
+    VSB_TRY(points_run(c, pl, base + w, d_v12, d_vref, d_b12, entered_coi, left_coi, only_enter_coi,
+                       steps_limit, d_imp, d_atm, d_lv, d_en));
+    VSB_CUDA(cudaMemcpyAsync(body_impact, d_imp, 16 * NV, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(body_enter_atm, d_atm, 16 * NV, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(coi_leave, d_lv, 16 * NV, cudaMemcpyDeviceToHost, c->stream));
+    return d2h(c, coi_enter, d_en, 48 * NV);
+}
+
+// ---------------------------------------------------------------- N2: per-tick vessel events
 extern "C" int vsb_host_check_warp(vsb_ctx *c, int64_t nv, const double *ecc, const double *dr,
                                    const double *ea, const double *ma, const double *n_motion,
                                    const double *body_impact, const double *body_enter_atm,
@@ -1618,6 +1665,173 @@ extern "C" int vsb_host_cross_apply(vsb_ctx *c, int64_t nev, const int32_t *kind
     return d2h(c, out6, d_out, 48 * E);
 }
 
+// ---------------------------------------------------------------- N2: resident vessel events
+// The orbit points and the per-tick event state of phys_vessel.Physics kept on the device next
+// to the vessel elements (KIND_VESSEL state), so that a game tick moves no per-vessel array over
+// PCIe: move -> cross_scan -> check_warp -> service all read resident data.
+static int need_vessel_events(vsb_ctx *c, const char *who, vsb_kepler_state **out)
+{
+    vsb_kepler_state &k = c->kep[VSB_KIND_VESSEL];
+    VSB_CHECK(k.n > 0, VSB_ERR_STATE, "%s: no VESSEL state loaded", who);
+    VSB_CHECK(k.ev_n == k.n && k.ev.p, VSB_ERR_STATE, "%s: call vsb_vessel_events_load first", who);
+    *out = &k;
+    return VSB_OK;
+}
+
+extern "C" int vsb_vessel_events_load(vsb_ctx *c, const double *body_impact,
+                                      const double *body_enter_atm, const double *coi_leave,
+                                      const double *coi_enter, const uint8_t *hold,
+                                      const double *prev_ea, const double *pe_d,
+                                      const double *ap_d, const double *period)
+{
+    CTX(c);
+    vsb_kepler_state &k = c->kep[VSB_KIND_VESSEL];
+    VSB_CHECK(k.n > 0, VSB_ERR_STATE, "vsb_vessel_events_load: no VESSEL state loaded");
+    VSB_CHECK(pe_d && ap_d && period, VSB_ERR_ARG,
+              "vsb_vessel_events_load: pe_d, ap_d and period are required");
+    const size_t N = (size_t)k.n, A = al32(N), A2 = al32(2 * N), A6 = al32(6 * N);
+    VSB_TRY(vsb_buf_reserve(k.ev, 8 * (3 * A2 + A6 + 4 * A) + N + 256));
+    double *b = (double *)k.ev.p;
+    k.ev_impact = b;
+    k.ev_atm = b + A2;
+    k.ev_leave = b + 2 * A2;
+    k.ev_enter = b + 3 * A2;
+    k.ev_prev_ea = b + 3 * A2 + A6;
+    k.ev_pe_d = k.ev_prev_ea + A;
+    k.ev_ap_d = k.ev_pe_d + A;
+    k.ev_period = k.ev_ap_d + A;
+    k.ev_hold = (unsigned char *)(k.ev_period + A);
+    k.ev_n = k.n;
+    // NaN = "no point" (the reference initialises these arrays with NaN, phys_vessel.py:231-234)
+    VSB_CUDA(cudaMemsetAsync(b, 0xff, 8 * (3 * A2 + A6), c->stream));
+    VSB_CUDA(cudaMemsetAsync(k.ev_hold, 0, N, c->stream));
+    if (body_impact) VSB_TRY(up_f64(c, k.ev_impact, body_impact, 2 * N));
+    if (body_enter_atm) VSB_TRY(up_f64(c, k.ev_atm, body_enter_atm, 2 * N));
+    if (coi_leave) VSB_TRY(up_f64(c, k.ev_leave, coi_leave, 2 * N));
+    if (coi_enter) VSB_TRY(up_f64(c, k.ev_enter, coi_enter, 6 * N));
+    if (hold) VSB_CUDA(cudaMemcpyAsync(k.ev_hold, hold, N, cudaMemcpyHostToDevice, c->stream));
+    if (prev_ea) VSB_TRY(up_f64(c, k.ev_prev_ea, prev_ea, N));
+    else VSB_CUDA(cudaMemcpyAsync(k.ev_prev_ea, k.ea, 8 * N, cudaMemcpyDeviceToDevice, c->stream));
+    VSB_TRY(up_f64(c, k.ev_pe_d, pe_d, N));
+    VSB_TRY(up_f64(c, k.ev_ap_d, ap_d, N));
+    VSB_TRY(up_f64(c, k.ev_period, period, N));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_vessel_events_set_orbit(vsb_ctx *c, int64_t vessel, double pe_d, double ap_d,
+                                           double period)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(need_vessel_events(c, "vsb_vessel_events_set_orbit", &k));
+    VSB_CHECK(vessel >= 0 && vessel < k->n, VSB_ERR_ARG,
+              "vsb_vessel_events_set_orbit: vessel %lld of %lld", (long long)vessel, (long long)k->n);
+    VSB_TRY(up_f64(c, k->ev_pe_d + vessel, &pe_d, 1));
+    VSB_TRY(up_f64(c, k->ev_ap_d + vessel, &ap_d, 1));
+    VSB_TRY(up_f64(c, k->ev_period + vessel, &period, 1));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_vessel_events_get(vsb_ctx *c, int64_t first, int64_t count, double *body_impact,
+                                     double *body_enter_atm, double *coi_leave, double *coi_enter,
+                                     uint8_t *hold, double *prev_ea)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(need_vessel_events(c, "vsb_vessel_events_get", &k));
+    VSB_CHECK(first >= 0 && count >= 0 && first + count <= k->n, VSB_ERR_ARG,
+              "vsb_vessel_events_get: range [%lld,+%lld) of %lld", (long long)first,
+              (long long)count, (long long)k->n);
+    const size_t F = (size_t)first, C = (size_t)count;
+    auto dn = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (dst && bytes)
+            VSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return VSB_OK;
+    };
+    VSB_TRY(dn(body_impact, k->ev_impact + 2 * F, 16 * C));
+    VSB_TRY(dn(body_enter_atm, k->ev_atm + 2 * F, 16 * C));
+    VSB_TRY(dn(coi_leave, k->ev_leave + 2 * F, 16 * C));
+    VSB_TRY(dn(coi_enter, k->ev_enter + 6 * F, 48 * C));
+    VSB_TRY(dn(hold, k->ev_hold + F, C));
+    VSB_TRY(dn(prev_ea, k->ev_prev_ea + F, 8 * C));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_vessel_points(vsb_ctx *c, int64_t nb, const double *body12,
+                                 const int64_t *body_ref, int64_t nsel, const int64_t *sel,
+                                 int64_t entered_coi, int64_t left_coi, int64_t left_coi_prev_ref,
+                                 int only_enter_coi, int64_t steps_limit)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(need_vessel_events(c, "vsb_vessel_points", &k));
+    VSB_CHECK(nb > 0 && body12 && body_ref && nsel >= 0 && steps_limit > 0 &&
+                  steps_limit < (1ll << 31),
+              VSB_ERR_ARG, "vsb_vessel_points: bad argument");
+    points_plan pl;
+    VSB_TRY(points_plan_build("vsb_vessel_points", k->n, nb, k->h_ref, body_ref, nsel, sel,
+                              left_coi_prev_ref, pl));
+    if (pl.sel.empty()) return VSB_OK;
+    const size_t NV = (size_t)k->n, NB = (size_t)nb;
+    VSB_TRY(vsb_buf_reserve(c->host_stage,
+                            8 * (al32(12 * NV) + al32(12 * NB) + points_scratch_words(pl))));
+    double *base = (double *)c->host_stage.p;
+    double *d_v12 = base, *d_b12 = base + al32(12 * NV);
+    VSB_TRY(vsb_launch_pack_vessel12(c, k->n, k->a, k->b, k->f, k->ecc, k->ma, k->ea, k->pea, k->nmot,
+                                     k->dr, k->ev_pe_d, k->ev_ap_d, k->ev_period, d_v12));
+    VSB_TRY(up_f64(c, d_b12, body12, 12 * NB));
+    VSB_TRY(points_run(c, pl, d_b12 + al32(12 * NB), d_v12, k->ref, d_b12, entered_coi, left_coi,
+                       only_enter_coi, steps_limit, k->ev_impact, k->ev_atm, k->ev_leave,
+                       k->ev_enter));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_vessel_check_warp(vsb_ctx *c, double warp, int64_t *out3)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(need_vessel_events(c, "vsb_vessel_check_warp", &k));
+    VSB_CHECK(out3 != nullptr, VSB_ERR_ARG, "vsb_vessel_check_warp: null output");
+    VSB_TRY(vsb_buf_reserve(c->scratch, 64));
+    unsigned long long *d_key = (unsigned long long *)c->scratch.p;
+    VSB_TRY(vsb_launch_check_warp(c, k->n, k->ecc, k->dr, k->ea, k->ma, k->nmot, k->ev_impact,
+                                  k->ev_atm, k->ev_leave, k->ev_enter, warp, k->ev_hold, d_key));
+    unsigned long long key[2];
+    VSB_TRY(d2h(c, key, d_key, 16));
+    out3[0] = out3[1] = -1;
+    if (key[0]) {
+        out3[0] = (int64_t)(key[0] & 3);
+        out3[1] = (int64_t)(key[0] >> 2) - 1;
+    }
+    out3[2] = (int64_t)key[1];
+    return VSB_OK;
+}
+
+extern "C" int vsb_vessel_cross_scan(vsb_ctx *c, int64_t *out2)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(need_vessel_events(c, "vsb_vessel_cross_scan", &k));
+    VSB_CHECK(out2 != nullptr, VSB_ERR_ARG, "vsb_vessel_cross_scan: null output");
+    VSB_TRY(vsb_buf_reserve(c->scratch, 64));
+    unsigned long long *d_key = (unsigned long long *)c->scratch.p;
+    VSB_TRY(vsb_launch_cross_scan(c, k->n, k->ecc, k->dr, k->ev_prev_ea, k->ea, k->ev_impact,
+                                  k->ev_leave, k->ev_enter, d_key));
+    unsigned long long key;
+    VSB_TRY(d2h(c, &key, d_key, 8));
+    out2[0] = -1;
+    out2[1] = 0;
+    if (key != ~0ull) {
+        out2[0] = (int64_t)(key >> 2);
+        out2[1] = (int64_t)(key & 3);
+    }
+    return VSB_OK;
+}
+
 // ---------------------------------------------------------------- N4: body thermal passes
 extern "C" int vsb_host_body_thermal(vsb_ctx *c, int64_t n, const double *consts12,
                                      const double *mass, const double *den, const double *rad,
@@ -1749,6 +1963,22 @@ extern "C" int vsb_kepler_culling_uniform(vsb_ctx *c, int kind, double radius,
     VSB_TRY(vis_reserve(c, k->n, 0, &st));
     VSB_TRY(vsb_launch_culling_flags(c, k->pos, nullptr, radius, k->n, screen_bounds, zoom,
                                      st.flags));
+    return vis_finish(c, st, k->n, idx_out, count_out);
+}
+
+// predict_enter_coi_service on the resident vessel state: ascending indices of the vessels to
+// re-predict (feed them to vsb_vessel_points with only_enter_coi)
+extern "C" int vsb_vessel_enter_coi_service(vsb_ctx *c, int crossing_pending, int64_t *idx_out,
+                                            int64_t *count_out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(need_vessel_events(c, "vsb_vessel_enter_coi_service", &k));
+    VSB_CHECK(count_out != nullptr, VSB_ERR_ARG, "vsb_vessel_enter_coi_service: null output");
+    vis_stage st;
+    VSB_TRY(vis_reserve(c, k->n, 0, &st));
+    VSB_TRY(vsb_launch_enter_coi_service(c, k->n, k->dr, k->ev_prev_ea, k->ea, k->ev_enter,
+                                         crossing_pending, st.flags));
     return vis_finish(c, st, k->n, idx_out, count_out);
 }
 

@@ -63,6 +63,12 @@ struct vsb_kepler_state {
     int64_t *lvl_idx = nullptr;     // body kind: bodies grouped by dependency level
     int64_t nlevels = 0;
     int64_t lvl_off[66] = {0};
+    // vessel kind: orbit points + per-tick event state, device resident (vsb_vessel_events_load)
+    vsb_buf ev;
+    int64_t ev_n = 0;
+    double *ev_impact = nullptr, *ev_atm = nullptr, *ev_leave = nullptr, *ev_enter = nullptr,
+           *ev_prev_ea = nullptr, *ev_pe_d = nullptr, *ev_ap_d = nullptr, *ev_period = nullptr;
+    unsigned char *ev_hold = nullptr;
     vsb_buf curves;                 // (n,P,2) moved curves, device resident
     vsb_buf quirk_idx;              // compacted ENRKE quirk-branch indices
     size_t bytes_alloc = 0;
@@ -329,6 +335,10 @@ int vsb_launch_cross_scan(vsb_ctx *c, int64_t nv, const double *ecc, const doubl
 int vsb_launch_cross_apply(vsb_ctx *c, int64_t nev, const int32_t *kind, const double *vessel8,
                            const int64_t *ref, const int64_t *new_ref, const double *body7,
                            double gc, double *out6, int32_t *status);
+int vsb_launch_pack_vessel12(vsb_ctx *c, int64_t n, const double *a, const double *b, const double *f,
+                             const double *ecc, const double *ma, const double *ea, const double *pea,
+                             const double *nmot, const double *dr, const double *pe_d,
+                             const double *ap_d, const double *period, double *out12);
 int vsb_march_walk_host(double x0, double c, int64_t kmax, int bounded, double bound, int64_t nq,
                         const int64_t *ks, double *xs, int64_t *K_out, int64_t *nseg_out);
 int vsb_launch_points_vessel(vsb_ctx *c, int64_t nsel, const int64_t *d_sel, const double *d_vessel12,

@@ -323,7 +323,36 @@ __global__ void cross_apply_kernel(int64_t nev, const int32_t *__restrict__ kind
     o[5] = (double)new_ref[i];
 }
 
+// SoA vessel state -> the (n,12) rows points() works on: a b f ecc ma ea pea n dr pe_d ap_d period
+__global__ void pack_vessel12_kernel(int64_t n, const double *__restrict__ a,
+                                     const double *__restrict__ b, const double *__restrict__ f,
+                                     const double *__restrict__ ecc, const double *__restrict__ ma,
+                                     const double *__restrict__ ea, const double *__restrict__ pea,
+                                     const double *__restrict__ nmot, const double *__restrict__ dr,
+                                     const double *__restrict__ pe_d, const double *__restrict__ ap_d,
+                                     const double *__restrict__ period, double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double *o = out + 12 * i;
+    o[0] = a[i]; o[1] = b[i]; o[2] = f[i]; o[3] = ecc[i]; o[4] = ma[i]; o[5] = ea[i];
+    o[6] = pea[i]; o[7] = nmot[i]; o[8] = dr[i]; o[9] = pe_d[i]; o[10] = ap_d[i]; o[11] = period[i];
+}
+
 }  // namespace
+
+int vsb_launch_pack_vessel12(vsb_ctx *c, int64_t n, const double *a, const double *b, const double *f,
+                             const double *ecc, const double *ma, const double *ea, const double *pea,
+                             const double *nmot, const double *dr, const double *pe_d,
+                             const double *ap_d, const double *period, double *out12)
+{
+    if (n <= 0) return VSB_OK;
+    pack_vessel12_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        n, a, b, f, ecc, ma, ea, pea, nmot, dr, pe_d, ap_d, period, out12);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
 
 int vsb_launch_check_warp(vsb_ctx *c, int64_t nv, const double *ecc, const double *dr,
                           const double *ea, const double *ma, const double *n, const double *impact,

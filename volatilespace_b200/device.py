@@ -418,6 +418,57 @@ class Device:
                                           ptr(status)))
         return out, status
 
+    # ---- resident vessel events (the KIND_VESSEL state must be loaded) ----
+    def vessel_events_load(self, pe_d, ap_d, period, body_impact=None, body_enter_atm=None,
+                           coi_leave=None, coi_enter=None, hold=None, prev_ea=None):
+        opt = lambda a: None if a is None else ptr(f64(a))
+        h = None if hold is None else np.ascontiguousarray(hold, dtype=np.uint8)
+        check(self.L.vsb_vessel_events_load(self.h, opt(body_impact), opt(body_enter_atm),
+                                            opt(coi_leave), opt(coi_enter), ptr(h), opt(prev_ea),
+                                            ptr(f64(pe_d)), ptr(f64(ap_d)), ptr(f64(period))))
+
+    def vessel_events_set_orbit(self, vessel, pe_d, ap_d, period):
+        check(self.L.vsb_vessel_events_set_orbit(self.h, int(vessel), float(pe_d), float(ap_d),
+                                                 float(period)))
+
+    def vessel_events_get(self, n, first=0):
+        """-> dict of the resident arrays for vessels [first, first+n)."""
+        out = {"body_impact": np.empty((n, 2)), "body_enter_atm": np.empty((n, 2)),
+               "coi_leave": np.empty((n, 2)), "coi_enter": np.empty((n, 6)),
+               "hold": np.empty(n, dtype=np.uint8), "prev_ea": np.empty(n)}
+        check(self.L.vsb_vessel_events_get(self.h, int(first), int(n), *(ptr(out[k]) for k in (
+            "body_impact", "body_enter_atm", "coi_leave", "coi_enter", "hold", "prev_ea"))))
+        return out
+
+    def vessel_points(self, body12, body_ref, sel=None, entered_coi=None, left_coi=None,
+                      left_coi_prev_ref=None, only_enter_coi=False, steps_limit=300):
+        body12, body_ref = f64(body12), i64(body_ref)
+        sel_arr = None if sel is None else i64(np.atleast_1d(sel))
+        none = lambda x: -1 if x is None else int(x)
+        check(self.L.vsb_vessel_points(
+            self.h, len(body12), ptr(body12), ptr(body_ref),
+            0 if sel_arr is None else len(sel_arr), None if sel_arr is None else ptr(sel_arr),
+            none(entered_coi), none(left_coi), none(left_coi_prev_ref), int(bool(only_enter_coi)),
+            int(steps_limit)))
+
+    def vessel_check_warp(self, warp):
+        out = np.zeros(3, dtype=np.int64)
+        check(self.L.vsb_vessel_check_warp(self.h, float(warp), ptr(out)))
+        none = lambda x: None if x < 0 else int(x)
+        return none(out[0]), none(out[1]), int(out[2])
+
+    def vessel_enter_coi_service(self, n, crossing_pending=False):
+        idx = np.empty(n, dtype=np.int64)
+        cnt = C.c_int64()
+        check(self.L.vsb_vessel_enter_coi_service(self.h, int(bool(crossing_pending)), ptr(idx),
+                                                  C.byref(cnt)))
+        return idx[:cnt.value].copy()
+
+    def vessel_cross_scan(self):
+        out = np.zeros(2, dtype=np.int64)
+        check(self.L.vsb_vessel_cross_scan(self.h, ptr(out)))
+        return (None if out[0] < 0 else int(out[0])), int(out[1])
+
     def set_march_mode(self, sequential):
         check(self.L.vsb_set_march_mode(self.h, int(bool(sequential))))
 
