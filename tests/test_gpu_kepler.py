@@ -791,3 +791,66 @@ def test_resident_vessel_events(dev):
     dev.kepler_free(KIND_VESSEL)
     with pytest.raises(VsbError):
         dev.vessel_check_warp(1.0)
+
+
+def test_game_loop_resident_equals_host_arrays():
+    """game.py's physics tick (check_warp, predict_enter_coi_service, move, cross_coi,
+    change_vessel) driven through phys_vessel.Physics twice -- event state resident on the device
+    vs shipped with every call -- must evolve identically, tick by tick."""
+    from conftest import VS
+    from volatilespace_b200 import phys_vessel
+    from volatilespace_b200.device import Device
+    g, gp = golden("vessel_events"), golden("vessel_points")
+    bs = g["body_static"]
+    keep = g["keep"]
+    v12 = gp["vessel12"][keep]
+    body_data = {"mass": g["body_mass"], "radius": bs[:, 8], "atm_h": bs[:, 9]}
+    body_orb = {"ref": g["body_ref"], "a": bs[:, 0], "b": bs[:, 1], "f": bs[:, 2], "ecc": bs[:, 3],
+                "pea": bs[:, 4], "n": bs[:, 5], "dir": bs[:, 6], "coi": bs[:, 7]}
+    bpos = g["cx0_bpos"]
+    bma, bea = gp["body12"][:, 4].copy(), gp["body12"][:, 5].copy()
+    sims = []
+    for resident in (True, False):
+        pv = phys_vessel.Physics(device=Device(0), curve_points=8)
+        pv.resident_events = resident
+        vorb = {"a": v12[:, 0].copy(), "ecc": v12[:, 3].copy(), "pe_arg": v12[:, 6].copy(),
+                "ma": v12[:, 4].copy(), "ref": gp["v_ref"][keep].copy(), "dir": v12[:, 8].copy()}
+        pv.load({"gc": float(g["gc"])}, body_data, body_orb,
+                {"name": ["v%d" % i for i in keep]}, vorb)
+        pv.predict_coi_limit = int(g["steps_limit"])
+        pv.initial(1, bpos, bma, bea)
+        sims.append(pv)
+    a, b = sims
+    assert a._resident and not b._resident
+
+    def same(what):
+        for key in ("a", "ecc", "pea", "ma", "ea", "dr", "ref", "pos", "body_impact",
+                    "body_enter_atm", "coi_leave", "coi_enter", "pe_d", "period"):
+            assert np.array_equal(getattr(a, key), getattr(b, key), equal_nan=True), (what, key)
+        assert (a.entered_coi, a.left_coi, a.left_coi_prev_ref) == \
+            (b.entered_coi, b.left_coi, b.left_coi_prev_ref), what
+        assert np.array_equal(a.physical_hold, b.physical_hold), what
+
+    same("initial")
+    assert (~np.isnan(a.coi_leave[:, 0])).sum() > 10
+    crossings = alarms = 0
+    for tick in range(400):
+        warp = (1, 5, 25, 100)[(tick // 100) % 4]
+        ra, rb = a.check_warp(warp), b.check_warp(warp)
+        assert ra == rb, tick
+        alarms += ra[0] is not None
+        assert np.array_equal(a.predict_enter_coi_service(), b.predict_enter_coi_service()), tick
+        a.move(warp, bpos, bma, bea)
+        b.move(warp, bpos, bma, bea)
+        ca, cb = a.cross_coi(), b.cross_coi()
+        assert ca == cb, tick
+        if ca is not None:
+            crossings += 1
+            a.change_vessel(ca)
+            b.change_vessel(cb)
+        if tick % 20 == 0 or ca is not None:
+            same("tick %d" % tick)
+    same("end")
+    assert crossings >= 5 and alarms >= 5
+    for pv in sims:
+        pv.dev.close()

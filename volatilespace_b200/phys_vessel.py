@@ -24,6 +24,11 @@ class Physics:
         self.gc = 1.0
         self.screen_x, self.screen_y = 1366, 768       # pygame surface size in the reference
         self.n_vessels = 0
+        # after initial() the orbit points, the hold mask and prev_ea live on the device next to
+        # the vessel elements, and the per-tick scans read them there (nothing per-vessel over
+        # PCIe); before that (or with resident_events = False) every call ships its arrays
+        self.resident_events = True
+        self._resident = False
 
     # phys_vessel.py:198-240 (orbit arrays only)
     def load(self, conf, body_data, body_orb, vessel_data, vessel_orb_data):
@@ -67,6 +72,11 @@ class Physics:
                       "ap_d": self.ap_d, "pea": self.pea, "dir": self.dr, "per": self.period}
         self.dev.kepler_load(KIND_VESSEL, self.curve_points, self.a, self.b, self.f, self.ecc,
                              self.pea, self.n, self.dr, self.ma, self.ea, self.ref, self.t)
+        self._resident = bool(self.resident_events and self.n_vessels)
+        if self._resident:
+            self.dev.vessel_events_load(self.pe_d, self.ap_d, self.period, self.body_impact,
+                                        self.body_enter_atm, self.coi_leave, self.coi_enter,
+                                        self._hold, self.prev_ea)
         self.move(warp, body_pos, body_ma, body_ea)
         curves_mov = self.curve_move()
         if body_ma is not None and body_ea is not None and self.n_vessels:
@@ -95,25 +105,35 @@ class Physics:
         self._points(None if vessel is None else [vessel], only_enter_coi)
 
     def _points(self, sel, only_enter_coi=False):
-        vessel12 = np.stack([self.a, self.b, self.f, self.ecc, self.ma, self.ea, self.pea, self.n,
-                             self.dr, self.pe_d, self.ap_d, self.period], axis=1)
         body12 = np.stack([self.body_a, self.body_b, self.body_f, self.body_ecc, self.body_ma,
                            self.body_ea, self.body_pea, self.body_n, self.body_dr, self.body_coi,
                            self.body_size, self.body_atm], axis=1)
-        self.dev.host_vessel_points(
-            vessel12, self.ref, body12, self.body_ref, self.body_impact, self.body_enter_atm,
-            self.coi_leave, self.coi_enter, sel=sel, entered_coi=self.entered_coi, left_coi=self.left_coi,
-            left_coi_prev_ref=self.left_coi_prev_ref, only_enter_coi=only_enter_coi,
-            steps_limit=self.predict_coi_limit)
+        kw = dict(sel=sel, entered_coi=self.entered_coi, left_coi=self.left_coi,
+                  left_coi_prev_ref=self.left_coi_prev_ref, only_enter_coi=only_enter_coi,
+                  steps_limit=self.predict_coi_limit)
+        if self._resident:
+            self.dev.vessel_points(body12, self.body_ref, **kw)
+            got = self.dev.vessel_events_get(self.n_vessels)
+            for key in ("body_impact", "body_enter_atm", "coi_leave", "coi_enter"):
+                getattr(self, key)[:] = got[key]       # host mirrors, refreshed in place
+            return
+        vessel12 = np.stack([self.a, self.b, self.f, self.ecc, self.ma, self.ea, self.pea, self.n,
+                             self.dr, self.pe_d, self.ap_d, self.period], axis=1)
+        self.dev.host_vessel_points(vessel12, self.ref, body12, self.body_ref, self.body_impact,
+                                    self.body_enter_atm, self.coi_leave, self.coi_enter, **kw)
 
     @property
     def physical_hold(self):
         """Vessels held in physical warp (the reference keeps them in append order; ascending
         here -- only membership and the count are ever used, game.py:1171-1215)."""
+        if self._resident:
+            self._hold[:] = self.dev.vessel_events_get(self.n_vessels)["hold"]
         return np.flatnonzero(self._hold)
 
     # phys_vessel.py:506-560 -> (situation, alarm_vessel, len(physical_hold))
     def check_warp(self, warp):
+        if self._resident:
+            return self.dev.vessel_check_warp(warp)
         return self.dev.host_check_warp(self.ecc, self.dr, self.ea, self.ma, self.n,
                                         self.body_impact, self.body_enter_atm, self.coi_leave,
                                         self.coi_enter, warp, self._hold)
@@ -121,16 +141,22 @@ class Physics:
     # phys_vessel.py:744-758
     def predict_enter_coi_service(self):
         pending = self.left_coi is not None or self.entered_coi is not None
-        again = self.dev.host_enter_coi_service(self.dr, self.prev_ea, self.ea, self.coi_enter,
-                                                pending)
+        if self._resident:
+            again = self.dev.vessel_enter_coi_service(self.n_vessels, pending)
+        else:
+            again = self.dev.host_enter_coi_service(self.dr, self.prev_ea, self.ea, self.coi_enter,
+                                                    pending)
         if len(again):
             self._points(again, only_enter_coi=True)
         return again
 
     # phys_vessel.py:563-632 -> the vessel whose orbit changed, or None
     def cross_coi(self):
-        ves, kind = self.dev.host_cross_scan(self.ecc, self.dr, self.prev_ea, self.ea,
-                                             self.body_impact, self.coi_leave, self.coi_enter)
+        if self._resident:
+            ves, kind = self.dev.vessel_cross_scan()
+        else:
+            ves, kind = self.dev.host_cross_scan(self.ecc, self.dr, self.prev_ea, self.ea,
+                                                 self.body_impact, self.coi_leave, self.coi_enter)
         # the reference's loop clears these flags for every vessel it visits (:579-583): up to and
         # including the crossing one, or all of them
         last = self.n_vessels - 1 if ves is None else ves
@@ -172,8 +198,8 @@ class Physics:
             self.ea[vessel] = self.dev.host_solve_kepler_ell(ecc, ma, 1e-10)[0]
         else:
             self.ea[vessel] = self.dev.host_newton_root_kepler_hyp(ecc, ma, ma)[0]
-        self.points(vessel)
         self._push_vessel(vessel)          # curve(vessel): the device regenerates it from the elements
+        self.points(vessel)
         vessel_orb = [self.a[vessel], self.ref[vessel], self.ecc[vessel], self.pe_d[vessel],
                       self.ap_d[vessel], self.pea[vessel], self.dr[vessel], self.period[vessel]]
         return [self.names[vessel] if len(self.names) > vessel else None], vessel_orb
@@ -185,6 +211,9 @@ class Physics:
                            (L.K_PEA, self.pea), (L.K_N, self.n), (L.K_DR, self.dr), (L.K_MA, self.ma),
                            (L.K_EA, self.ea), (L.K_REF, self.ref)):
             self.dev.kepler_set(KIND_VESSEL, field, arr[vessel:vessel + 1], first=vessel)
+        if self._resident:
+            self.dev.vessel_events_set_orbit(vessel, self.pe_d[vessel], self.ap_d[vessel],
+                                             self.period[vessel])
 
     # phys_vessel.py:364-369
     def curve(self, vessel):
