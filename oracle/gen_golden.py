@@ -472,6 +472,9 @@ def gen_editor_edits(ns):
     ph.add_body(new_body(9.0e4, [15000.0, -8000.0], [0.0, 0.3])); snap_step("add_new_root")
     ph.set_body_mass(4, 5.0e5); snap_step("set_mass_new_root")
     ph.del_body(0); snap_step("del_root")
+    ph.kepler_inverse(6, 0.3, 40.0, 2000.0, 75.0, 0.0, 0.0, 1.0); snap_step("kepler_inverse_ma")
+    ph.kepler_inverse(8, 0.5, 200.0, 1500.0, 10.0, 120.0, 5200.0, -1.0)
+    snap_step("kepler_inverse_ta_apd")
     out["steps"] = np.array(steps)
     save("editor_edits", **out)
 

@@ -616,6 +616,66 @@ class EditorOracle:
         self.rel_vel[body] = velocity - self.vel[self.parents[body]]
         self.simplified_orbit_coi()
 
+    # phys_editor.py:316-322
+    def move_parent(self, body, position):
+        movement = position - self.pos[body]
+        self.pos[body] = position
+        for child in np.where(self.parents == body)[0]:
+            self.pos[child] += movement
+
+    # phys_editor.py:453-515 (orbit edited in the side panel: elements -> state vector)
+    def kepler_inverse(self, body, ecc, omega_deg, pe_d, mean_anomaly_deg, true_anomaly_deg, ap_d,
+                       direction):
+        import math
+        parent = self.parents[body]
+        u = self.gc * self.mass[parent]
+        omega = omega_deg * np.pi / 180
+        mean_anomaly = mean_anomaly_deg * np.pi / 180
+        if direction > 0:
+            mean_anomaly = -mean_anomaly
+        if ecc == 0:
+            ecc = 0.00001
+        if ecc >= 1:
+            ecc = 0.95
+        if ap_d:
+            a = (pe_d + ap_d) / 2
+            ecc = (ap_d / a) - 1
+        else:
+            a = - pe_d / (ecc - 1)
+        b = a * math.sqrt(1 - ecc**2)
+        f = math.sqrt(a**2 - b**2)
+        if true_anomaly_deg:
+            ta = true_anomaly_deg * np.pi / 180
+            ea = math.acos((ecc + math.cos(ta)) / (1 + (ecc * math.cos(ta))))
+        else:
+            ea = solve_kepler_ell(ecc, mean_anomaly, 1e-10)
+        pr_x = a * math.cos(ea) - f
+        pr_y = b * math.sin(ea)
+        pr = np.array([pr_x * math.cos(omega - np.pi) - pr_y * math.sin(omega - np.pi),
+                       pr_x * math.sin(omega - np.pi) + pr_y * math.cos(omega - np.pi)])
+        # velocity direction: implicit derivative of the rotated ellipse, disambiguated against
+        # the chord through the curve's x-extremes (same construction as
+        # convert.kepler_to_velocity); the speed uses the expression of :506
+        so, co = math.sin(omega), math.cos(omega)
+        p_x, p_y = pr[0] - f * np.cos(omega), pr[1] - f * np.sin(omega)
+        vr_angle = np.arctan(
+            -(b**2 * p_x * co**2 + a**2 * p_x * so**2 + b**2 * p_y * so * co - a**2 * p_y * so * co)
+            / (a**2 * p_y * co**2 + b**2 * p_y * so**2 + b**2 * p_x * so * co - a**2 * p_x * so * co))
+        x_max = math.sqrt(a**2 * math.cos(2*omega) + a**2 - b**2 * math.cos(2*omega) + b**2) / math.sqrt(2) - 10**-6
+        x2, c2, s2 = x_max**2, co**2, so**2
+        y_max = (a*b*math.sqrt(-x2 * (co**4 + so**4) - 2 * x2 * c2 * s2 + b**2 * s2 + a**2 * c2)
+                 + a**2 * x_max * so * co - b**2 * x_max * so * co) / (a**2 * c2 + b**2 * s2)
+        x1, y1, xx2, yy2 = x_max + f * co, y_max + f * so, -x_max + f * co, -y_max + f * so
+        if ((xx2 - x1) * (pr[1] - y1)) - ((yy2 - y1) * (pr[0] - x1)) < 0:
+            vr_angle += np.pi
+        vr_angle = vr_angle % (2*np.pi)
+        prm = math.sqrt(pr[0]*pr[0] + pr[1]*pr[1])
+        vrm = direction * math.sqrt((2 * a * u - prm * u) / (a * prm))
+        self.move_parent(body, self.pos[parent] + pr)
+        self.rel_vel[body] = np.array([vrm * math.cos(vr_angle), vrm * math.sin(vr_angle)])
+        for body_s in np.argsort(self.mass)[-1::-1]:
+            self.vel[body_s] = self.rel_vel[body_s] + self.vel[self.parents[body_s]]
+
     # editor.py:1503-1523
     def frame(self, warp=1):
         deleted = []

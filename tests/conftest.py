@@ -27,7 +27,8 @@ def oracle():
     return orc
 
 EDIT_STEPS = ["load", "add_light", "set_mass", "set_pos", "set_vel", "set_den", "del_ordinary",
-              "add_new_root", "set_mass_new_root", "del_root"]
+              "add_new_root", "set_mass_new_root", "del_root", "kepler_inverse_ma",
+              "kepler_inverse_ta_apd"]
 
 
 def new_body(m, p, v):
@@ -55,6 +56,10 @@ def apply_edit(ph, k):
         ph.set_body_mass(4, 5.0e5)
     elif k == 9:
         ph.del_body(0)
+    elif k == 10:      # orbit typed into the editor panel: e, omega, pe_d, M (deg), no ta / ap_d
+        ph.kepler_inverse(6, 0.3, 40.0, 2000.0, 75.0, 0.0, 0.0, 1.0)
+    elif k == 11:      # true anomaly and apoapsis given, clockwise
+        ph.kepler_inverse(8, 0.5, 200.0, 1500.0, 10.0, 120.0, 5200.0, -1.0)
 
 
 # ---- vessel_events fixture helpers (column layout written by oracle/gen_golden.py) ----------

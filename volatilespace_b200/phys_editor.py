@@ -13,6 +13,8 @@ editor.py:1517) -- eagerly by default, or on `pull()` with sync="lazy".
 There is no CPU fallback: constructing a Physics without the CUDA library or
 without a GPU raises.
 """
+import math
+
 import numpy as np
 
 from . import _lib
@@ -42,6 +44,28 @@ STELLAR_CLASSES = np.array(["Unknown", "M", "K", "G", "F", "A", "B", "O"])
 def thermal_consts(gc_sim, rad_mult, mass_thermal_mult, min_mass):
     return np.array([gc_sim, rad_mult, mass_thermal_mult, min_mass, GC_REAL, C_LIGHT, LS, MS,
                      np.sqrt(2), np.pi**(1 / 4), SIGMA**(1 / 4), 4 * np.pi], dtype=np.float64)
+
+
+def _ellipse_velocity_angle(pr, a, b, f, omega):
+    """Direction of motion at the focus-relative point `pr` of an ellipse (semi-axes a, b, focus
+    distance f) rotated by omega: slope from the implicit derivative of the rotated conic, and the
+    half-plane test against the chord through the curve's x-extremes that tells the two branches
+    apart (phys_editor.py:486-503; the construction of convert.kepler_to_velocity :24-43)."""
+    so, co = math.sin(omega), math.cos(omega)
+    a2, b2 = a**2, b**2
+    cx, cy = pr[0] - f * np.cos(omega), pr[1] - f * np.sin(omega)      # relative to the centre
+    angle = np.arctan(-(b2 * cx * co**2 + a2 * cx * so**2 + b2 * cy * so * co - a2 * cy * so * co)
+                      / (a2 * cy * co**2 + b2 * cy * so**2 + b2 * cx * so * co - a2 * cx * so * co))
+    x_max = math.sqrt(a2 * math.cos(2 * omega) + a2 - b2 * math.cos(2 * omega) + b2) / math.sqrt(2) - 10**-6
+    x2, c2, s2 = x_max**2, co**2, so**2
+    c4, s4 = (co * co) * (co * co), (so * so) * (so * so)
+    y_max = (a * b * math.sqrt(-x2 * (c4 + s4) - 2 * x2 * c2 * s2 + b2 * s2 + a2 * c2)
+             + a2 * x_max * so * co - b2 * x_max * so * co) / (a2 * c2 + b2 * s2)
+    x1, y1 = x_max + f * co, y_max + f * so
+    x2_, y2_ = -x_max + f * co, -y_max + f * so
+    if ((x2_ - x1) * (pr[1] - y1)) - ((y2_ - y1) * (pr[0] - x1)) < 0:
+        angle += np.pi
+    return angle % (2 * np.pi)
 
 
 def mass_order(mass):
@@ -435,6 +459,53 @@ class Physics(_DeviceBodies):
         self._set_row("rel_vel", body,
                       np.asarray(velocity, dtype=np.float64) - self._row("vel", parent))
         self.simplified_orbit_coi()
+
+    # phys_editor.py:316-322
+    def move_parent(self, body, position):
+        """Move a body together with the bodies that orbit it."""
+        self.pull("pos", "parents")
+        shift = np.asarray(position, dtype=np.float64) - self.pos[body]
+        rows = np.flatnonzero(self.parents == body)    # the root is its own parent: moved twice, as there
+        self.pos[body] = position
+        self.pos[rows] += shift
+        self._push("pos")
+
+    # phys_editor.py:453-515: the orbit typed into the editor's side panel -> position and
+    # relative velocity of `body` (ellipses only, as the reference limits it)
+    def kepler_inverse(self, body, ecc, omega_deg, pe_d, mean_anomaly_deg, true_anomaly_deg, ap_d,
+                       direction):
+        self.pull("pos", "vel", "rel_vel", "parents")
+        parent = int(self.parents[body])
+        u = self.gc * self.mass[parent]
+        omega = omega_deg * np.pi / 180
+        mean_anomaly = mean_anomaly_deg * np.pi / 180
+        if direction > 0:
+            mean_anomaly = -mean_anomaly
+        ecc = 0.00001 if ecc == 0 else (0.95 if ecc >= 1 else ecc)
+        if ap_d:
+            a = (pe_d + ap_d) / 2
+            ecc = (ap_d / a) - 1
+        else:
+            a = - pe_d / (ecc - 1)
+        b = a * math.sqrt(1 - ecc**2)
+        f = math.sqrt(a**2 - b**2)
+        if true_anomaly_deg:
+            cos_ta = math.cos(true_anomaly_deg * np.pi / 180)
+            ea = math.acos((ecc + cos_ta) / (1 + (ecc * cos_ta)))
+        else:
+            ea = float(self.dev.host_solve_kepler_ell([ecc], [mean_anomaly], 1e-10)[0])
+        rot = omega - np.pi
+        qx, qy = a * math.cos(ea) - f, b * math.sin(ea)
+        pr = np.array([qx * math.cos(rot) - qy * math.sin(rot), qx * math.sin(rot) + qy * math.cos(rot)])
+        angle = _ellipse_velocity_angle(pr, a, b, f, omega)
+        dist = math.sqrt(pr[0] * pr[0] + pr[1] * pr[1])
+        speed = direction * math.sqrt((2 * a * u - dist * u) / (a * dist))
+        self.move_parent(body, self.pos[parent] + pr)
+        self.rel_vel[body] = (speed * math.cos(angle), speed * math.sin(angle))
+        # absolute velocities again, heaviest first, so that the edit shows at once (:512-514)
+        for i in self._order():
+            self.vel[i] = self.rel_vel[i] + self.vel[self.parents[i]]
+        self._push("rel_vel", "vel")
 
     # phys_editor.py:819-836
     def get_bodies(self):
