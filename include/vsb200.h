@@ -397,6 +397,25 @@ int vsb_vessel_enter_coi_service(vsb_ctx *ctx, int crossing_pending, int64_t *id
                                  int64_t *count_out);
 int vsb_vessel_cross_scan(vsb_ctx *ctx, int64_t *out2);
 
+/* --------------------------------------------- per-item element conversions over host arrays
+ * convert.kepler_to_velocity (convert.py:20-64; out (n,2)) and convert.velocity_to_kepler
+ * (:67-131; failsafe 0/1/2; out5 (n,5) = a, ecc, pe_arg, ma, dr); phys_shared.orb2xy
+ * (phys_shared.py:187-199, ref_pos (n,2), (0,0) where ea == 0 exactly); kepler_basic_one for every
+ * body (phys_editor.py:63-83 via kepler_basic :381-384) on host arrays instead of the resident
+ * body state.  One item per thread. */
+int vsb_host_kepler_to_velocity(vsb_ctx *ctx, int64_t n, const double *rel_pos, const double *a,
+                                const double *ecc, const double *pe_arg, const double *u,
+                                const double *dr, double *vel_out);
+int vsb_host_velocity_to_kepler(vsb_ctx *ctx, int64_t n, const double *rel_pos,
+                                const double *rel_vel, const double *u, int failsafe, double *out5);
+int vsb_host_orb2xy(vsb_ctx *ctx, int64_t n, const double *a, const double *b, const double *f,
+                    const double *ecc, const double *pea, const double *ref_pos, const double *ea,
+                    double *out);
+int vsb_host_kepler_basic(vsb_ctx *ctx, int64_t n, const int64_t *parents, const double *mass,
+                          const double *pos, const double *vel, double gc, double coi_coef,
+                          double *focus, double *ecc_v, double *semi_major, double *semi_minor,
+                          double *periapsis_arg, double *coi);
+
 /* --------------------------------------------- per-frame body passes
  * Physics.body (phys_editor.py:577-599, without the radius, which stays host numpy),
  * Physics.temp_color (:602-651) and Physics.classify (:654-670) in one pass over host arrays.

@@ -883,6 +883,49 @@ def gen_mapfiles(ns, conf, bd, bod):
     save("mapfiles", **out)
 
 
+def gen_convert_vel(ns):
+    """convert.kepler_to_velocity / velocity_to_kepler (all failsafe modes) and phys_shared.orb2xy
+    of the live reference on seeded inputs."""
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    from volatilespace.physics import convert
+    sys.path.remove(rh.REFERENCE_ROOT)
+    rng = np.random.default_rng(20240627)
+    n = 300
+    hyp = rng.uniform(0, 1, n) < 0.4
+    ecc = np.where(hyp, rng.uniform(1.05, 3.0, n), rng.uniform(0.01, 0.9, n))
+    a = rng.uniform(500, 5000, n) * np.where(hyp, -1, 1)
+    pea = rng.uniform(0, 2 * np.pi, n)
+    u = rng.uniform(1e3, 1e5, n)
+    dr = rng.choice([-1.0, 1.0], n)
+    ea = np.where(hyp, rng.uniform(-2, 2, n), rng.uniform(0, 2 * np.pi, n))
+    ea[:3] = 0.0                                   # orb2xy: (0, 0) without the reference position
+    f = a * ecc
+    b = np.sqrt(np.abs(f**2 - a**2))
+    ref_pos = rng.uniform(-1e4, 1e4, (n, 2))
+    xy = np.array([ns.phys_shared.orb2xy(a[i], b[i], f[i], ecc[i], pea[i], ref_pos[i], ea[i])
+                   for i in range(n)])
+    rel = xy - ref_pos
+    rel[:3] = rng.uniform(500, 900, (3, 2))
+    with np.errstate(all="ignore"):
+        vel = np.array([convert.kepler_to_velocity(rel[i], a[i], ecc[i], pea[i], u[i], dr[i])
+                        for i in range(n)])
+    out = dict(a=a, b=b, f=f, ecc=ecc, pea=pea, u=u, dr=dr, ea=ea, ref_pos=ref_pos, xy=xy, rel=rel,
+               vel=vel)
+    # velocity_to_kepler on random state vectors (bound and unbound), three failsafe modes
+    m = 400
+    pos = rng.uniform(-5e3, 5e3, (m, 2))
+    uu = rng.uniform(1e3, 1e5, m)
+    speed = np.sqrt(uu / np.linalg.norm(pos, axis=1)) * rng.uniform(0.3, 2.2, m)
+    ang = rng.uniform(0, 2 * np.pi, m)
+    vv = speed[:, None] * np.stack([np.cos(ang), np.sin(ang)], axis=1)
+    for fs in (0, 1, 2):
+        res = np.array([convert.velocity_to_kepler(pos[i].copy(), vv[i].copy(), uu[i], failsafe=fs)
+                        for i in range(m)], dtype=float)
+        out["v2k_fs%d" % fs] = res
+    out.update(v2k_pos=pos, v2k_vel=vv, v2k_u=uu)
+    save("convert_vel", **out)
+
+
 def main():
     """All fixtures, or only the ones named on the command line (e.g. `vessel_points`)."""
     ns = rh.load()
@@ -902,6 +945,7 @@ def main():
     if want("vessel_points"): gen_vessel_points(ns, conf, bd, bod)
     if want("vessel_events"): gen_vessel_events(ns, conf, bd, bod)
     if want("mapfiles"): gen_mapfiles(ns, conf, bd, bod)
+    if want("convert_vel"): gen_convert_vel(ns)
 
 
 if __name__ == "__main__":

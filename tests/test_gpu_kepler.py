@@ -854,3 +854,75 @@ def test_game_loop_resident_equals_host_arrays():
     assert crossings >= 5 and alarms >= 5
     for pv in sims:
         pv.dev.close()
+
+
+def test_convert_velocity_helpers_golden(dev):
+    """Batched convert.kepler_to_velocity / velocity_to_kepler and phys_shared.orb2xy against the
+    live reference: branch decisions (direction, failsafe flips) identical, values to 1e-9."""
+    from volatilespace_b200 import convert
+    from volatilespace_b200._lib import check, f64, ptr
+    g = golden("convert_vel")
+    n = len(g["a"])
+    xy = np.empty((n, 2))
+    check(dev.L.vsb_host_orb2xy(dev.h, n, *(ptr(f64(g[k])) for k in ("a", "b", "f", "ecc", "pea",
+                                                                     "ref_pos", "ea")), ptr(xy)))
+    np.testing.assert_allclose(xy, g["xy"], rtol=1e-12, atol=1e-9)
+    assert np.all(xy[:3] == 0.0)                     # ea == 0: (0, 0) without the reference position
+    vel = convert.kepler_to_velocity(g["rel"], g["a"], g["ecc"], g["pea"], g["u"], g["dr"], device=dev)
+    ok = np.isfinite(g["vel"]).all(axis=1)
+    assert np.array_equal(np.isfinite(vel).all(axis=1), ok)
+    np.testing.assert_allclose(vel[ok], g["vel"][ok], rtol=1e-9, atol=1e-9)
+    one = convert.kepler_to_velocity(g["rel"][7], g["a"][7], g["ecc"][7], g["pea"][7], g["u"][7],
+                                     g["dr"][7], device=dev)
+    assert np.array_equal(one, vel[7])
+    for fs in (0, 1, 2):
+        want = g["v2k_fs%d" % fs]
+        vin = g["v2k_vel"].copy()
+        got = convert.velocity_to_kepler(g["v2k_pos"], vin, g["v2k_u"], fs, device=dev)
+        assert np.array_equal(vin, g["v2k_vel"])     # caller's array untouched
+        assert np.array_equal(got[:, 4], want[:, 4]), fs                  # direction
+        close = np.isclose(got, want, rtol=1e-9, atol=1e-9, equal_nan=True).all(axis=1)
+        assert close.mean() > 0.99, fs               # a failsafe decision may sit on the 1 % edge
+    a, ecc, pe, ma, dr = convert.velocity_to_kepler(g["v2k_pos"][0], g["v2k_vel"][0], g["v2k_u"][0],
+                                                    1, device=dev)
+    assert isinstance(dr, int) and np.isclose(a, g["v2k_fs1"][0, 0], rtol=1e-9)
+
+
+def test_editor_free_functions_golden(dev):
+    """phys_editor.{find_parent_one, gravity_one, kepler_basic_one, check_collision_one} of the
+    shim against the live reference's jitted functions (pair_kernels fixture)."""
+    from volatilespace_b200 import phys_editor as pe
+    g = golden("pair_kernels")
+    n = len(g["fp_mass"])
+    parents = pe.find_parents_all(g["fp_order"], g["fp_pos"], g["fp_coi"], device=dev)
+    assert np.array_equal(parents, g["fp_parents"])
+    for body in (0, 1, 57, n - 1):
+        assert pe.find_parent_one(body, g["fp_order"], g["fp_pos"], g["fp_coi"], device=dev) == \
+            g["fp_parents"][body]
+    rel_pos = g["fp_pos"][parents] - g["fp_pos"]
+    for body in (0, 3, 200):
+        acc = pe.gravity_one(body, int(parents[body]), g["fp_mass"], rel_pos[body], float(g["g1_gc"]),
+                             device=dev)
+        np.testing.assert_allclose(acc, g["g1_acc"][body], rtol=1e-12, atol=1e-300)
+    f, ev, a, b, w, c = pe.kepler_basic_all(parents, g["fp_mass"], g["fp_pos"], g["kb_vel"],
+                                            float(g["g1_gc"]), 0.7, device=dev)
+    for got, key in ((f, "kb_focus"), (ev, "kb_ecc_v"), (a, "kb_semi_major"), (b, "kb_semi_minor"),
+                     (w, "kb_periapsis_arg"), (c, "kb_coi")):
+        np.testing.assert_allclose(got, g[key], rtol=1e-10, atol=1e-10, err_msg=key)
+    one = pe.kepler_basic_one(5, int(parents[5]), g["fp_mass"], g["fp_pos"], g["kb_vel"],
+                              float(g["g1_gc"]), 0.7, device=dev)
+    np.testing.assert_allclose(one[2], g["kb_semi_major"][5], rtol=1e-10)
+    np.testing.assert_allclose(one[1], g["kb_ecc_v"][5], rtol=1e-10, atol=1e-12)
+    # collisions: every case of the fixture through the per-body form
+    cm = g["cc_mass"]
+    for k in range(len(g["cc_del"])):
+        pos, rad = g["cc_pos"][k], g["cc_rad"][k]
+        d, a_ = int(g["cc_del"][k]), int(g["cc_add"][k])
+        if d < 0:
+            assert pe.check_collision_one(0, cm, pos, rad, device=dev) is None
+            continue
+        i = min(d, a_)
+        assert pe.check_collision_one(i, cm, pos, rad, device=dev) == (d, a_)
+        if i > 0:                                    # an earlier body collides with nobody
+            assert pe.check_collision_one(i - 1, cm, pos, rad, device=dev) is None
+    assert pe.check_collision_one(len(cm) - 1, cm, g["cc_pos"][0], g["cc_rad"][0], device=dev) is None

@@ -426,3 +426,18 @@ def test_vessel_events(oracle):
         t = np.linspace(-np.pi, np.pi, int(g["P"]))
         np.testing.assert_allclose(oracle.curve_points(ecc, v[ves, 0], mine[0], v[ves, 4], t),
                                    g["cv%d_curve" % k], rtol=1e-13, atol=1e-9, equal_nan=True)
+
+
+def test_convert_velocity_helpers(oracle):
+    """convert.kepler_to_velocity / velocity_to_kepler restatements against the live reference."""
+    g = golden("convert_vel")
+    for i in range(len(g["a"])):
+        v = oracle.kepler_to_velocity(g["rel"][i], g["a"][i], g["ecc"][i], g["pea"][i], g["u"][i],
+                                      g["dr"][i])
+        np.testing.assert_allclose(v, g["vel"][i], rtol=1e-12, atol=1e-12, equal_nan=True)
+    for fs in (0, 1, 2):
+        want = g["v2k_fs%d" % fs]
+        for i in range(len(want)):
+            got = oracle.velocity_to_kepler(g["v2k_pos"][i], g["v2k_vel"][i], g["v2k_u"][i], fs)
+            np.testing.assert_allclose(got, want[i], rtol=1e-11, atol=1e-11, equal_nan=True,
+                                       err_msg="failsafe %d row %d" % (fs, i))

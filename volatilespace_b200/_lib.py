@@ -118,6 +118,10 @@ SIGNATURES = {
     "vsb_vessel_check_warp": [_ctx, _f64, _pv],
     "vsb_vessel_enter_coi_service": [_ctx, C.c_int, _pv, _pi],
     "vsb_vessel_cross_scan": [_ctx, _pv],
+    "vsb_host_kepler_to_velocity": [_ctx, _i64] + [_pv] * 7,
+    "vsb_host_velocity_to_kepler": [_ctx, _i64, _pv, _pv, _pv, C.c_int, _pv],
+    "vsb_host_orb2xy": [_ctx, _i64] + [_pv] * 8,
+    "vsb_host_kepler_basic": [_ctx, _i64, _pv, _pv, _pv, _pv, _f64, _f64] + [_pv] * 6,
     "vsb_set_march_mode": [_ctx, C.c_int],
     "vsb_host_running_sum": [_f64, _f64, _i64, C.c_int, _f64, _i64, _pv, _pv, _pv, _pv],
     "vsb_march_stats": [_ctx, _pv],

@@ -41,3 +41,37 @@ def to_newton(mass, orb_data, gc, coi_coef, device=None):
             raise ValueError("math domain error") from None
         raise
     return {"kepler": False, "pos": pos, "vel": vel}
+
+
+def _rows(x, width):
+    x = np.asarray(x, dtype=np.float64)
+    return x.reshape(-1, width) if width > 1 else np.atleast_1d(x)
+
+
+def kepler_to_velocity(rel_pos, a, ecc, pe_arg, u, dr, device=None):
+    """convert.py:20-64: relative velocity at the focus-relative point `rel_pos` of a conic.
+    One orbit (2-vector + scalars -> 2-vector) or n of them ((n,2) + (n,) arrays -> (n,2))."""
+    dev = device or default_device()
+    pos = f64(_rows(rel_pos, 2))
+    n = len(pos)
+    cols = [f64(np.broadcast_to(_rows(x, 1), (n,))) for x in (a, ecc, pe_arg, u, dr)]
+    out = np.empty((n, 2))
+    check(dev.L.vsb_host_kepler_to_velocity(dev.h, n, ptr(pos), *(ptr(c) for c in cols), ptr(out)))
+    return out[0] if np.ndim(rel_pos) == 1 else out
+
+
+def velocity_to_kepler(rel_pos, rel_vel, u, failsafe=0, device=None):
+    """convert.py:67-131 -> (a, ecc, pe_arg, ma, dr) for one state vector, or an (n,5) array.
+    Unlike the reference it leaves the caller's `rel_vel` untouched (the reference rotates it in
+    place and only undoes that for failsafe == 2)."""
+    dev = device or default_device()
+    pos, vel = f64(_rows(rel_pos, 2)), f64(_rows(rel_vel, 2))
+    n = len(pos)
+    uu = f64(np.broadcast_to(_rows(u, 1), (n,)))
+    out = np.empty((n, 5))
+    check(dev.L.vsb_host_velocity_to_kepler(dev.h, n, ptr(pos), ptr(vel), ptr(uu), int(failsafe),
+                                            ptr(out)))
+    if np.ndim(rel_pos) == 1:
+        a, ecc, pe, ma, dr = out[0]
+        return a, ecc, pe, ma, int(dr)
+    return out

@@ -1832,6 +1832,107 @@ extern "C" int vsb_vessel_cross_scan(vsb_ctx *c, int64_t *out2)
     return VSB_OK;
 }
 
+// ---------------------------------------------------------------- stateless element conversions
+// generic "upload k input arrays, run, download one output" helper for per-item kernels
+struct in_arr {
+    const void *host;
+    size_t words;    // 8-byte words
+};
+
+static int stage_inputs(vsb_ctx *c, const in_arr *ins, int nin, size_t out_words, double **d_ins,
+                        double **d_out)
+{
+    size_t total = al32(out_words);
+    for (int k = 0; k < nin; ++k) total += al32(ins[k].words);
+    VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * total));
+    double *p = (double *)c->host_stage.p;
+    for (int k = 0; k < nin; ++k) {
+        d_ins[k] = p;
+        if (ins[k].words)
+            VSB_CUDA(cudaMemcpyAsync(p, ins[k].host, 8 * ins[k].words, cudaMemcpyHostToDevice,
+                                     c->stream));
+        p += al32(ins[k].words);
+    }
+    *d_out = p;
+    return VSB_OK;
+}
+
+extern "C" int vsb_host_kepler_to_velocity(vsb_ctx *c, int64_t n, const double *rel_pos,
+                                           const double *a, const double *ecc, const double *pe_arg,
+                                           const double *u, const double *dr, double *vel_out)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && (n == 0 || (rel_pos && a && ecc && pe_arg && u && dr && vel_out)),
+              VSB_ERR_ARG, "vsb_host_kepler_to_velocity: bad argument");
+    if (n == 0) return VSB_OK;
+    const size_t N = (size_t)n;
+    const in_arr ins[6] = {{rel_pos, 2 * N}, {a, N}, {ecc, N}, {pe_arg, N}, {u, N}, {dr, N}};
+    double *d[6], *d_out;
+    VSB_TRY(stage_inputs(c, ins, 6, 2 * N, d, &d_out));
+    VSB_TRY(vsb_launch_k2v(c, n, d[0], d[1], d[2], d[3], d[4], d[5], d_out));
+    return d2h(c, vel_out, d_out, 16 * N);
+}
+
+extern "C" int vsb_host_velocity_to_kepler(vsb_ctx *c, int64_t n, const double *rel_pos,
+                                           const double *rel_vel, const double *u, int failsafe,
+                                           double *out5)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && failsafe >= 0 && failsafe <= 2 &&
+                  (n == 0 || (rel_pos && rel_vel && u && out5)),
+              VSB_ERR_ARG, "vsb_host_velocity_to_kepler: bad argument");
+    if (n == 0) return VSB_OK;
+    const size_t N = (size_t)n;
+    const in_arr ins[3] = {{rel_pos, 2 * N}, {rel_vel, 2 * N}, {u, N}};
+    double *d[3], *d_out;
+    VSB_TRY(stage_inputs(c, ins, 3, 5 * N, d, &d_out));
+    VSB_TRY(vsb_launch_v2k(c, n, d[0], d[1], d[2], failsafe, d_out));
+    return d2h(c, out5, d_out, 40 * N);
+}
+
+extern "C" int vsb_host_orb2xy(vsb_ctx *c, int64_t n, const double *a, const double *b,
+                               const double *f, const double *ecc, const double *pea,
+                               const double *ref_pos, const double *ea, double *out)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && (n == 0 || (a && b && f && ecc && pea && ref_pos && ea && out)),
+              VSB_ERR_ARG, "vsb_host_orb2xy: bad argument");
+    if (n == 0) return VSB_OK;
+    const size_t N = (size_t)n;
+    const in_arr ins[7] = {{a, N}, {b, N}, {f, N}, {ecc, N}, {pea, N}, {ref_pos, 2 * N}, {ea, N}};
+    double *d[7], *d_out;
+    VSB_TRY(stage_inputs(c, ins, 7, 2 * N, d, &d_out));
+    VSB_TRY(vsb_launch_orb2xy(c, n, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d_out));
+    return d2h(c, out, d_out, 16 * N);
+}
+
+extern "C" int vsb_host_kepler_basic(vsb_ctx *c, int64_t n, const int64_t *parents,
+                                     const double *mass, const double *pos, const double *vel,
+                                     double gc, double coi_coef, double *focus, double *ecc_v,
+                                     double *semi_major, double *semi_minor, double *periapsis_arg,
+                                     double *coi)
+{
+    CTX(c);
+    VSB_CHECK(n >= 0 && (n == 0 || (parents && mass && pos && vel && focus && ecc_v && semi_major &&
+                                    semi_minor && periapsis_arg && coi)),
+              VSB_ERR_ARG, "vsb_host_kepler_basic: bad argument");
+    if (n == 0) return VSB_OK;
+    for (int64_t i = 0; i < n; ++i)
+        VSB_CHECK(parents[i] >= 0 && parents[i] < n, VSB_ERR_ARG,
+                  "vsb_host_kepler_basic: parent of body %lld out of range", (long long)i);
+    const size_t N = (size_t)n;
+    const in_arr ins[4] = {{parents, N}, {mass, N}, {pos, 2 * N}, {vel, 2 * N}};
+    double *d[4], *o;
+    VSB_TRY(stage_inputs(c, ins, 4, 7 * al32(N), d, &o));
+    const size_t A = al32(N);     // outputs: focus | semi_major | semi_minor | periapsis_arg | coi | ecc_v(2)
+    VSB_TRY(vsb_launch_kepler_basic_arrays(c, n, (const int64_t *)d[0], d[1], d[2], d[3], gc, coi_coef,
+                                           o, o + 5 * A, o + A, o + 2 * A, o + 3 * A, o + 4 * A));
+    double *outs[5] = {focus, semi_major, semi_minor, periapsis_arg, coi};
+    for (int k = 0; k < 5; ++k)
+        VSB_CUDA(cudaMemcpyAsync(outs[k], o + k * A, 8 * N, cudaMemcpyDeviceToHost, c->stream));
+    return d2h(c, ecc_v, o + 5 * A, 16 * N);
+}
+
 // ---------------------------------------------------------------- N4: body thermal passes
 extern "C" int vsb_host_body_thermal(vsb_ctx *c, int64_t n, const double *consts12,
                                      const double *mass, const double *den, const double *rad,

@@ -335,6 +335,17 @@ int vsb_launch_cross_scan(vsb_ctx *c, int64_t nv, const double *ecc, const doubl
 int vsb_launch_cross_apply(vsb_ctx *c, int64_t nev, const int32_t *kind, const double *vessel8,
                            const int64_t *ref, const int64_t *new_ref, const double *body7,
                            double gc, double *out6, int32_t *status);
+int vsb_launch_k2v(vsb_ctx *c, int64_t n, const double *rel_pos, const double *a, const double *ecc,
+                   const double *pe_arg, const double *u, const double *dr, double *out2);
+int vsb_launch_v2k(vsb_ctx *c, int64_t n, const double *rel_pos, const double *rel_vel,
+                   const double *u, int failsafe, double *out5);
+int vsb_launch_orb2xy(vsb_ctx *c, int64_t n, const double *a, const double *b, const double *f,
+                      const double *ecc, const double *pea, const double *ref_pos, const double *ea,
+                      double *out2);
+int vsb_launch_kepler_basic_arrays(vsb_ctx *c, int64_t n, const int64_t *parents, const double *mass,
+                                   const double *pos, const double *vel, double gc, double coi_coef,
+                                   double *focus, double *ecc_v, double *semi_major,
+                                   double *semi_minor, double *periapsis_arg, double *coi);
 int vsb_launch_pack_vessel12(vsb_ctx *c, int64_t n, const double *a, const double *b, const double *f,
                              const double *ecc, const double *ma, const double *ea, const double *pea,
                              const double *nmot, const double *dr, const double *pe_d,

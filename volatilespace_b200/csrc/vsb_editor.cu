@@ -786,6 +786,21 @@ int vsb_launch_kepler_basic(vsb_ctx *c, double gc, double coi_coef)
     return VSB_OK;
 }
 
+// kepler_basic over explicit device arrays (the stateless host-array call)
+int vsb_launch_kepler_basic_arrays(vsb_ctx *c, int64_t n, const int64_t *parents, const double *mass,
+                                   const double *pos, const double *vel, double gc, double coi_coef,
+                                   double *focus, double *ecc_v, double *semi_major,
+                                   double *semi_minor, double *periapsis_arg, double *coi)
+{
+    if (n <= 0) return VSB_OK;
+    kepler_basic_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        n, parents, mass, (const double2 *)pos, (const double2 *)vel, gc, coi_coef, focus,
+        (double2 *)ecc_v, semi_major, semi_minor, periapsis_arg, coi);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
+
 // largest is written to ((int64_t*)c->scratch.p)[0]
 int vsb_launch_simplified_orbit_coi(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order)
 {

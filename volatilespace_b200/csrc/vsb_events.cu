@@ -323,6 +323,35 @@ __global__ void cross_apply_kernel(int64_t nev, const int32_t *__restrict__ kind
     o[5] = (double)new_ref[i];
 }
 
+// batched convert.kepler_to_velocity / velocity_to_kepler and phys_shared.orb2xy
+__global__ void k2v_kernel(int64_t n, const double *__restrict__ rel_pos, const double *__restrict__ a,
+                           const double *__restrict__ ecc, const double *__restrict__ pe_arg,
+                           const double *__restrict__ u, const double *__restrict__ dr,
+                           double *__restrict__ out2)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) kepler_to_velocity(rel_pos + 2 * i, a[i], ecc[i], pe_arg[i], u[i], dr[i], out2 + 2 * i);
+}
+
+__global__ void v2k_kernel(int64_t n, const double *__restrict__ rel_pos,
+                           const double *__restrict__ rel_vel, const double *__restrict__ u,
+                           int failsafe, double *__restrict__ out5)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) velocity_to_kepler(rel_pos + 2 * i, rel_vel + 2 * i, u[i], failsafe, out5 + 5 * i);
+}
+
+__global__ void orb2xy_kernel(int64_t n, const double *__restrict__ a, const double *__restrict__ b,
+                              const double *__restrict__ f, const double *__restrict__ ecc,
+                              const double *__restrict__ pea, const double *__restrict__ ref_pos,
+                              const double *__restrict__ ea, double *__restrict__ out2)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        ps_orb2xy(a[i], b[i], f[i], ecc[i], pea[i], ref_pos[2 * i], ref_pos[2 * i + 1], ea[i],
+                  out2 + 2 * i);
+}
+
 // SoA vessel state -> the (n,12) rows points() works on: a b f ecc ma ea pea n dr pe_d ap_d period
 __global__ void pack_vessel12_kernel(int64_t n, const double *__restrict__ a,
                                      const double *__restrict__ b, const double *__restrict__ f,
@@ -340,6 +369,40 @@ __global__ void pack_vessel12_kernel(int64_t n, const double *__restrict__ a,
 }
 
 }  // namespace
+
+int vsb_launch_k2v(vsb_ctx *c, int64_t n, const double *rel_pos, const double *a, const double *ecc,
+                   const double *pe_arg, const double *u, const double *dr, double *out2)
+{
+    if (n <= 0) return VSB_OK;
+    k2v_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, rel_pos, a, ecc, pe_arg, u, dr,
+                                                                  out2);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
+
+int vsb_launch_v2k(vsb_ctx *c, int64_t n, const double *rel_pos, const double *rel_vel,
+                   const double *u, int failsafe, double *out5)
+{
+    if (n <= 0) return VSB_OK;
+    v2k_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, rel_pos, rel_vel, u, failsafe,
+                                                                  out5);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
+
+int vsb_launch_orb2xy(vsb_ctx *c, int64_t n, const double *a, const double *b, const double *f,
+                      const double *ecc, const double *pea, const double *ref_pos, const double *ea,
+                      double *out2)
+{
+    if (n <= 0) return VSB_OK;
+    orb2xy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, a, b, f, ecc, pea, ref_pos,
+                                                                     ea, out2);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
 
 int vsb_launch_pack_vessel12(vsb_ctx *c, int64_t n, const double *a, const double *b, const double *f,
                              const double *ecc, const double *ma, const double *ea, const double *pea,

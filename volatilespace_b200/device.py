@@ -23,6 +23,19 @@ def default_device():
     return _default
 
 
+_scratch = None
+
+
+def scratch_device():
+    """A second context on the same GPU for the stateless free functions: several `vsb_host_*`
+    calls stage their arrays in the context's body state, which must not disturb a live Physics
+    object that shares the default context."""
+    global _scratch
+    if _scratch is None:
+        _scratch = Device(default_device().index)
+    return _scratch
+
+
 class Device:
     def __init__(self, device=0):
         self.L = _lib.load()

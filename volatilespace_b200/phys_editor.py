@@ -20,7 +20,7 @@ import numpy as np
 from . import _lib
 from ._lib import (F_ACC, F_COI, F_DEN, F_ECC_V, F_FOCUS, F_MASS, F_PARENTS, F_PERIAPSIS_ARG,
                    F_POS, F_RAD, F_REL_VEL, F_SEMI_MAJOR, F_SEMI_MINOR, F_VEL)
-from .device import Device, default_device
+from .device import Device, default_device, scratch_device
 
 _FIELDS = {"mass": F_MASS, "den": F_DEN, "rad": F_RAD, "coi": F_COI, "pos": F_POS, "vel": F_VEL,
            "rel_vel": F_REL_VEL, "parents": F_PARENTS, "focus": F_FOCUS, "ecc_v": F_ECC_V,
@@ -78,6 +78,71 @@ def body_radius(mass, den, rad_mult):
     reference's np.cbrt path (it feeds the bit-exact collision predicate)."""
     volume = mass / den
     return rad_mult * np.cbrt(3 * volume / (4 * np.pi))
+
+
+# ---- the per-body free functions of the reference module (phys_editor.py:36-97), for callers
+# that import them directly.  Each evaluates the whole batch on the device; the `_one` forms pick
+# one body out of it and are meant for tests and occasional queries, not for loops.
+def find_parents_all(bodies_sorted, pos, coi, device=None):
+    """find_parent_one for every body -> parents (N,) int64."""
+    dev = device or scratch_device()
+    return dev.host_find_parents(bodies_sorted, pos, coi)
+
+
+def find_parent_one(body, bodies_sorted, pos, coi, device=None):
+    """phys_editor.py:36-48."""
+    return int(find_parents_all(bodies_sorted, pos, coi, device)[body])
+
+
+def gravity_one(body, parent, mass, rel_pos, gc, device=None):
+    """phys_editor.py:51-60: acceleration of `body` toward `parent` (rel_pos = pos[parent] -
+    pos[body]); the root (body 0) gets zeros.  Evaluated by the all-pairs kernel on the two-body
+    system {body at the origin, parent at rel_pos} -- tolerance-level agreement (rsqrt^3 instead
+    of sqrt / atan2 / cos / sin)."""
+    if not body:
+        return np.zeros(2)
+    dev = device or scratch_device()
+    pos = np.array([[0.0, 0.0], [rel_pos[0], rel_pos[1]]])
+    return dev.host_allpairs_accel(np.array([mass[body], mass[parent]], dtype=np.float64), pos, gc)[0]
+
+
+def kepler_basic_all(parents, mass, pos, vel, gc, coi_coef, device=None):
+    """kepler_basic_one for every body -> (focus, ecc_v (N,2), semi_major, semi_minor,
+    periapsis_arg, coi)."""
+    dev = device or scratch_device()
+    par = _lib.i64(parents)
+    mass, pos, vel = _lib.f64(mass), _lib.f64(pos), _lib.f64(vel)
+    n = len(mass)
+    focus, sma, smi, pea, coi = (np.empty(n) for _ in range(5))
+    ecc_v = np.empty((n, 2))
+    _lib.check(dev.L.vsb_host_kepler_basic(dev.h, n, _lib.ptr(par), _lib.ptr(mass), _lib.ptr(pos),
+                                           _lib.ptr(vel), float(gc), float(coi_coef),
+                                           _lib.ptr(focus), _lib.ptr(ecc_v), _lib.ptr(sma),
+                                           _lib.ptr(smi), _lib.ptr(pea), _lib.ptr(coi)))
+    return focus, ecc_v, sma, smi, pea, coi
+
+
+def kepler_basic_one(body, parent, mass, pos, vel, gc, coi_coef, device=None):
+    """phys_editor.py:63-83 -> (focus, ecc_v, semi_major, semi_minor, periapsis_arg, coi)."""
+    if not body:
+        return 0.0, np.zeros(2), 0.0, 0.0, 0.0, 0.0
+    # two-body system: row 0 = the parent (acts as root), row 1 = the body
+    out = kepler_basic_all([0, 0], [mass[parent], mass[body]], [pos[parent], pos[body]],
+                           [vel[parent], vel[body]], gc, coi_coef, device)
+    return tuple(o[1] for o in out)
+
+
+def check_collision_one(body1, mass, pos, rad, device=None):
+    """phys_editor.py:86-97: first body2 > body1 touching body1 -> (body_del, body_add) or None."""
+    dev = device or scratch_device()
+    mass, pos, rad = (np.asarray(x, dtype=np.float64) for x in (mass, pos, rad))
+    if body1 >= len(mass) - 1:
+        return None
+    # rows body1.. : a pair (0, j) is the lexicographic minimum whenever body1 collides at all
+    d, a = dev.host_check_collision(mass[body1:], pos[body1:], rad[body1:])
+    if d is None or min(d, a) != 0:
+        return None
+    return d + body1, a + body1
 
 
 class _DeviceBodies:
