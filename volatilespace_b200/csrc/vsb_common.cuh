@@ -171,7 +171,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
         : "memory");
 }
 
-// MUFU.RSQ64H: ~2^-22 relative seed for x^-1/2 (low word zero).
+// MUFU.RSQ64H: ~2^-22 relative seed for x^-1/2 (only the high word is significant; the gravity
+// kernels replace the zero low word, see vsb_gravity.cu).
 __device__ __forceinline__ double rsqrt_seed(double x)
 {
     double y;

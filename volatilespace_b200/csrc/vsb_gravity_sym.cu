@@ -31,8 +31,13 @@ struct sym_task {
 
 __device__ __forceinline__ double inv_r3(double dx, double dy, double &r2_out)
 {
-    double r2 = fma(dx, dx, dy * dy);
-    double y = rsqrt_seed(r2);
+    const double dy2 = dy * dy;
+    double r2 = fma(dx, dx, dy2);
+    // The seed only defines the HIGH word of y.  Instead of zeroing the low word (one more
+    // instruction on the dispatch port per pair) y takes the low word of the dead temporary
+    // dy2: a perturbation below 2^-20, absorbed by the correction below (e stays under 2^-18.6,
+    // so the first dropped term 2.19 e^3 is under 3e-17).
+    double y = __hiloint2double(__double2hiint(rsqrt_seed(r2)), __double2loint(dy2));
     double t = y * y;
     double e = fma(-r2, t, 1.0);
     double y3 = t * y;
@@ -96,10 +101,11 @@ allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ 
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         double dx = pj.x - xi[k], dy = pj.y - yi[k];
-                        double r2 = fma(dx, dx, dy * dy);
-                        double y = rsqrt_seed(r2);
-                        int hi = __double2hiint(r2);
-                        y = __hiloint2double(hi < 0x00100000 ? 0 : __double2hiint(y), 0);
+                        const double dy2 = dy * dy;
+                        double r2 = fma(dx, dx, dy2);
+                        int yh = __double2hiint(rsqrt_seed(r2));
+                        yh = __double2hiint(r2) < 0x00100000 ? 0 : yh;   // i == j: exact zero
+                        const double y = __hiloint2double(yh, __double2loint(dy2));
                         double t = y * y;
                         double e = fma(-r2, t, 1.0);
                         double ym = y * mj;
