@@ -1,6 +1,6 @@
 """Small fixed workloads for ncu captures (see profiles/README.md).
 
-    python tools/profile_run.py gravity64k | kepler1m | collision256k | parents64k | points160
+    python tools/profile_run.py gravity64k | gravity256k | kepler1m | collision256k | parents64k | points160
 """
 import os
 import sys
@@ -22,6 +22,10 @@ def main():
         s = synth.plummer2d(65536)
         dev.upload_bodies(s["mass"], s["pos"], s["vel"])
         dev.allpairs_step(s["gc"], 6)
+    elif mode == "gravity256k":
+        s = synth.rotating_disk(262144)
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"])
+        dev.allpairs_step(s["gc"], 3)
     elif mode == "kepler1m":
         k = synth.kepler_objects(1 << 20)
         dev.kepler_load(KIND_VESSEL, 512, k["a"], k["b"], k["f"], k["ecc"], k["pea"], k["n"],

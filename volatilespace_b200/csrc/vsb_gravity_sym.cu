@@ -19,6 +19,7 @@
 // adds the slabs in block order: bit-identical run to run.  (Across different GPU
 // counts the result differs in the last bits -- use vsb_gravity.cu when shard
 // invariance matters.)
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "vsb_common.cuh"
@@ -47,13 +48,20 @@ __device__ __forceinline__ double inv_r3(double dx, double dy, double &r2_out)
     return fma(y3, q, y3);
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 16) ? 1 : 2)
+// WARPS warps per CTA, T targets per lane (registers), SU = hand-over of a Q sub-block
+// between warps: 1 = CTA barrier, 2 = pairwise named barriers (warp w meets only its ring neighbours).
+// Macro-block S = WARPS * T * 32 bodies.  A Q sub-block (T*32 bodies, one per warp and
+// sub-round) is cut into NG = T*8 groups of 4 sources (members NG apart, so consecutive lanes
+// read consecutive 16-byte words); lane l works in step k on group (l + k) % NG.
+template <int WARPS, int T, int SU, int MB>
+__global__ void __launch_bounds__(WARPS * 32, MB)
 allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ mass,
                     const sym_task *__restrict__ tasks, double2 *__restrict__ part_p,
                     double2 *__restrict__ part_q)
 {
-    constexpr int S = WARPS * 128;
+    constexpr int SB = T * 32;
+    constexpr int NG = SB / 4;
+    constexpr int S = WARPS * SB;
     extern __shared__ __align__(128) unsigned char sym_smem[];
     double2 *sxy = (double2 *)sym_smem;          // S
     double2 *sacc = sxy + S;                     // S
@@ -79,11 +87,11 @@ allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ 
     __syncthreads();
 
     for (int P = task.p0; P < task.p1; ++P) {
-        // targets of this lane: rows pbase + w*128 + k*32 + lane
-        const int64_t pbase = (int64_t)P * S + w * 128 + lane;
-        double xi[4], yi[4], mi[4], ax[4], ay[4];
+        // targets of this lane: rows pbase + w*SB + k*32 + lane
+        const int64_t pbase = (int64_t)P * S + w * SB + lane;
+        double xi[T], yi[T], mi[T], ax[T], ay[T];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < T; ++k) {
             double2 p = pos[pbase + k * 32];
             xi[k] = p.x;
             yi[k] = p.y;
@@ -92,46 +100,43 @@ allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ 
         }
         if (P == task.q) {
             // diagonal block: directed, masked, target side only
-            for (int qs = 0; qs < WARPS; ++qs) {
-                const int sb = qs * 128;
 #pragma unroll 1
-                for (int j = 0; j < 128; ++j) {
-                    const double2 pj = sxy[sb + j];
-                    const double mj = sm[sb + j];
+            for (int j = 0; j < S; ++j) {
+                const double2 pj = sxy[j];
+                const double mj = sm[j];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        double dx = pj.x - xi[k], dy = pj.y - yi[k];
-                        const double dy2 = dy * dy;
-                        double r2 = fma(dx, dx, dy2);
-                        int yh = __double2hiint(rsqrt_seed(r2));
-                        yh = __double2hiint(r2) < 0x00100000 ? 0 : yh;   // i == j: exact zero
-                        const double y = __hiloint2double(yh, __double2loint(dy2));
-                        double t = y * y;
-                        double e = fma(-r2, t, 1.0);
-                        double ym = y * mj;
-                        double y3m = t * ym;
-                        double p = fma(1.875, e, 1.5);
-                        double q = e * p;
-                        double s = fma(y3m, q, y3m);
-                        ax[k] = fma(s, dx, ax[k]);
-                        ay[k] = fma(s, dy, ay[k]);
-                    }
+                for (int k = 0; k < T; ++k) {
+                    double dx = pj.x - xi[k], dy = pj.y - yi[k];
+                    const double dy2 = dy * dy;
+                    double r2 = fma(dx, dx, dy2);
+                    int yh = __double2hiint(rsqrt_seed(r2));
+                    yh = __double2hiint(r2) < 0x00100000 ? 0 : yh;   // i == j: exact zero
+                    const double y = __hiloint2double(yh, __double2loint(dy2));
+                    double t = y * y;
+                    double e = fma(-r2, t, 1.0);
+                    double ym = y * mj;
+                    double y3m = t * ym;
+                    double p = fma(1.875, e, 1.5);
+                    double q = e * p;
+                    double s = fma(y3m, q, y3m);
+                    ax[k] = fma(s, dx, ax[k]);
+                    ay[k] = fma(s, dy, ay[k]);
                 }
             }
         } else {
             for (int rho = 0; rho < WARPS; ++rho) {
-                const int sb = ((w + rho) & (WARPS - 1)) * 128;
+                const int sb = ((w + rho) & (WARPS - 1)) * SB;
 #pragma unroll 1
-                for (int step = 0; step < 32; ++step) {
-                    const int g = (lane + step) & 31;
+                for (int step = 0; step < NG; ++step) {
+                    const int g = (lane + step) & (NG - 1);
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
-                        const int idx = sb + s * 32 + g;
+                        const int idx = sb + s * NG + g;
                         const double2 pj = sxy[idx];
                         const double mj = sm[idx];
                         double2 aj = sacc[idx];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < T; ++k) {
                             double dx = pj.x - xi[k], dy = pj.y - yi[k];
                             double r2;
                             double wv = inv_r3(dx, dy, r2);
@@ -146,14 +151,25 @@ allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ 
                     }
                     __syncwarp();   // the group moves on to the next lane
                 }
-                __syncthreads();    // the sub-block moves on to the next warp
+                // the sub-block moves on to the next warp
+                if (SU == 1) {
+                    __syncthreads();
+                } else {
+                    // warp w hands its sub-block to warp w-1 and takes over the one of warp w+1:
+                    // rendezvous with each ring neighbour (even warps right first, odd warps left
+                    // first, so the ring cannot deadlock); barrier 1+x belongs to the pair (x, x+1)
+                    const int right = 1 + w, left = 1 + ((w + WARPS - 1) & (WARPS - 1));
+                    const int first = (w & 1) ? left : right, second = (w & 1) ? right : left;
+                    asm volatile("bar.sync %0, 64;" ::"r"(first) : "memory");
+                    asm volatile("bar.sync %0, 64;" ::"r"(second) : "memory");
+                }
             }
         }
         // target-side sums of the pair (P, Q): slab q(q+1)/2 + P
         const int64_t slab = (int64_t)task.q * (task.q + 1) / 2 + P;
-        double2 *out = part_p + slab * S + w * 128 + lane;
+        double2 *out = part_p + slab * S + w * SB + lane;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) out[k * 32] = make_double2(ax[k], ay[k]);
+        for (int k = 0; k < T; ++k) out[k * 32] = make_double2(ax[k], ay[k]);
     }
     __syncthreads();
     double2 *qo = part_q + (int64_t)task.qslot * S;
@@ -210,8 +226,21 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
 {
     const int64_t n = c->n, npad = c->npad;
     if (n <= 0) return VSB_OK;
-    const int warps = (npad >= 262144 * 2) ? 16 : 8;
-    const int S = warps * 128;
+    // Kernel shape (warps, targets per lane, hand-over, CTAs per SM).  8 targets per lane halve
+    // the shared-memory and loop instructions per pair (profiles/README.md: 2.6 % at 1 M bodies);
+    // the macro-block S sets the task grain (small S: better balance at small N) against the
+    // slab memory N^2/(2S) * 16 B (S = 1024: 8.6 GB at 1 M bodies, 34 GB at 2 M).
+    // VSB_SYM_SHAPE=w,t,h,c overrides (tools/sym_ab.py).
+    int warps = 4, tpl = 8, su = 2, mb = 3;
+    if (npad <= 131072) warps = 2, su = 1, mb = 6;
+    if (npad > 2097152) warps = 8, su = 1, mb = 1;
+    if (const char *env = getenv("VSB_SYM_SHAPE")) {
+        mb = 0;
+        sscanf(env, "%d,%d,%d,%d", &warps, &tpl, &su, &mb);
+        if (mb == 0) mb = (warps * tpl <= 32) ? 2 : 1;
+    }
+    VSB_CHECK(warps > 0 && tpl > 0, VSB_ERR_ARG, "allpairs_sym: bad VSB_SYM_SHAPE");
+    const int S = warps * tpl * 32;
     VSB_CHECK(npad % S == 0, VSB_ERR_STATE, "allpairs_sym: padded size %lld not a multiple of %d",
               (long long)npad, S);
     const int M = (int)(npad / S);
@@ -221,7 +250,7 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
     int chunk = (int)(pairs / want_tasks);
     if (chunk < 1) chunk = 1;
     // host-side task table (cached per n / world / rank)
-    if (c->sym_tasks_n != n || c->sym_world != world || c->sym_rank != rank) {
+    if (c->sym_tasks_n != n || c->sym_world != world || c->sym_rank != rank || c->sym_S != S) {
         struct T { sym_task t; int cost; };
         T *all = (T *)malloc(sizeof(T) * (size_t)(pairs + M));
         int *qfirst = (int *)malloc(sizeof(int) * (size_t)(M + 1));
@@ -271,6 +300,7 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
         VSB_TRY(rc);
         VSB_CUDA(ce);
         c->sym_tasks_n = n;
+        c->sym_S = S;
         c->sym_world = world;
         c->sym_rank = rank;
         c->sym_ntasks = nm;
@@ -292,17 +322,23 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
     const int *d_qf = (const int *)((char *)c->sym_tab.p + c->sym_qf_off);
     const size_t smem = (size_t)S * (2 * sizeof(double2) + sizeof(double));
     if (c->sym_ntasks > 0) {
-        if (warps == 16) {
-            VSB_CUDA(cudaFuncSetAttribute(allpairs_sym_kernel<16>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            allpairs_sym_kernel<16><<<c->sym_ntasks, 512, smem, c->stream>>>(
-                (const double2 *)c->pos, c->mass, d_tasks, part_p, part_q);
-        } else {
-            VSB_CUDA(cudaFuncSetAttribute(allpairs_sym_kernel<8>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            allpairs_sym_kernel<8><<<c->sym_ntasks, 256, smem, c->stream>>>(
-                (const double2 *)c->pos, c->mass, d_tasks, part_p, part_q);
-        }
+#define VSB_SYM_CASE(W, T, U, MB)                                                                   \
+    if (warps == W && tpl == T && su == U && mb == MB) {                                                    \
+        VSB_CUDA(cudaFuncSetAttribute(allpairs_sym_kernel<W, T, U, MB>,                           \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        allpairs_sym_kernel<W, T, U, MB><<<c->sym_ntasks, W * 32, smem, c->stream>>>(            \
+            (const double2 *)c->pos, c->mass, d_tasks, part_p, part_q);                         \
+        launched = true;                                                                        \
+    }
+        bool launched = false;
+        VSB_SYM_CASE(2, 8, 1, 6)    // S =  512, 12 warps/SM
+        VSB_SYM_CASE(4, 8, 1, 3)    // S = 1024, 12 warps/SM, CTA barrier
+        VSB_SYM_CASE(4, 8, 2, 3)    // S = 1024, 12 warps/SM, pairwise barriers
+        VSB_SYM_CASE(8, 8, 1, 1)    // S = 2048,  8 warps/SM
+        VSB_SYM_CASE(8, 4, 1, 2)    // S = 1024, 4 targets per lane (first version of the kernel)
+        VSB_SYM_CASE(16, 4, 1, 1)   // S = 2048, 4 targets per lane
+#undef VSB_SYM_CASE
+        VSB_CHECK(launched, VSB_ERR_ARG, "allpairs_sym: no kernel for shape %d,%d,%d,%d", warps, tpl, su, mb);
         c->launches += 1;
     }
     allpairs_sym_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
