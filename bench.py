@@ -482,9 +482,10 @@ def roofline(ops, fp64_flops_microbench, clocks, dev, ms_accel, my_pairs, ops_pe
         "bound": "fp64", "achieved": ops * 2 / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
         "frac": ops * 2 / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this kernel on
-        # this workload at 1 GPU (profiles/r1_gravity_sym1m_ncu_full_summary.txt); the row kernel
-        # was captured at 64k bodies only
-        "traffic": 5.093e9 if (kernel == "sym" and my_pairs > 1.0e12) else None,
+        # this workload at 1 GPU (profiles/r1_gravity_sym1m_t8_ncu_full_summary.txt: 0.683 GB read
+        # + 8.651 GB written, the per-block-pair partial-sum slabs of 1024 bodies; 1.4 ms at HBM
+        # rate = 0.26 % of the launch); the row kernel was captured at 64k bodies only
+        "traffic": 9.334e9 if (kernel == "sym" and my_pairs > 1.0e12) else None,
         "kernel": "allpairs_sym_kernel" if kernel == "sym" else "allpairs_accel_kernel",
         "ms_per_launch": ms_accel,
         "peak_source": "64 FP64 lanes/SM/clk x 148 SMs x %.0f MHz observed x 2 (issue peak of the "
