@@ -254,6 +254,29 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
             "fp64_pipe_frac_at_1965mhz": pairs * OPS_PER_PAIR[mode] / (ms * 1e-3) /
             (148 * 64 * 1965e6)}
     dev.set_gravity_mode("auto")
+    # MODE_REF (the reference's own parent/COI model) at the size of config 3: one
+    # editor gravity tick = find_parents + gravity_one per body + chain composition + integrator
+    try:
+        s = synth.rotating_disk(1048576)
+        r = np.hypot(s["pos"][:, 0], s["pos"][:, 1])
+        coi = r * (s["mass"] / s["mass"][0]) ** 0.4      # kepler_basic's COI of a circular orbit
+        coi[0] = 0.0
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"], coi=coi, rel_vel=s["vel"])
+        order = np.argsort(s["mass"], kind="stable")[-1::-1]
+        res = {"bodies": 1048576}
+        for mode, reps in (("grid", 10), ("scan", 2)):
+            os.environ["VSB_PARENTS"] = mode
+            dev.gravity_ref(s["gc"], order)
+            dev.sync()
+            ms = time_ticks(torch, stream, lambda: dev.gravity_ref(s["gc"], None), reps, nobar) / reps
+            res[mode] = {"ms_per_tick": ms, "body_ticks_per_s": 1048576 / (ms * 1e-3)}
+        os.environ.pop("VSB_PARENTS", None)
+        res["note"] = ("grid = sort-based candidate pass for find_parents (default from 4096 bodies), "
+                       "scan = the exhaustive N^2/2 point-in-COI scan; identical parents")
+        out["disk1m_mode_ref_tick"] = res
+    except Exception as e:
+        os.environ.pop("VSB_PARENTS", None)
+        out["disk1m_mode_ref_tick"] = {"error": str(e)[:200]}
     # config 5: collision detection at 256k bodies, first tick of the collapsing cluster and a
     # no-hit variant (radii / 100: worst case for the exhaustive scan)
     s = synth.collapsing_cluster(262144)

@@ -192,8 +192,16 @@ def test_find_parents_golden(dev):
     assert np.array_equal(got, g["fp_parents"])
 
 
+@pytest.fixture(params=["scan", "grid"])
+def parents_mode(request, monkeypatch):
+    """Both implementations of A1: the exhaustive N^2/2 scan and the sort-based candidate pass
+    (default from 4096 bodies up) must return the reference's parents."""
+    monkeypatch.setenv("VSB_PARENTS", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("n", [1, 2, 15, 513, 3000, 8192])
-def test_find_parents_vs_oracle(dev, oracle, n):
+def test_find_parents_vs_oracle(dev, oracle, n, parents_mode):
     rng = np.random.default_rng(n)
     mass, pos, _ = small_cloud(n, 200 + n, extent=3.0e3)
     coi = rng.uniform(0, 300, n) * (rng.uniform(0, 1, n) < 0.5)
@@ -203,6 +211,58 @@ def test_find_parents_vs_oracle(dev, oracle, n):
     assert np.array_equal(got, want)
     if n >= 513:
         assert (want != 0).sum() > 10
+
+
+def test_find_parents_grid_mixed_coi_scales(dev, oracle, monkeypatch):
+    """COIs over eight decades (nested: a star-sized disc, planet-sized ones, thousands of tiny
+    ones), bodies without a COI, coincident bodies, equal masses, a body exactly on a COI edge
+    and non-finite entries: the candidate pass returns the oracle's parents, bit for bit."""
+    rng = np.random.default_rng(77)
+    n = 30000
+    mass = rng.uniform(0.5, 2.0, n)
+    mass[:200] = np.round(mass[:200], 1)          # ties: the order array decides
+    mass[0] = 1.0e9
+    pos = rng.normal(0, 1, (n, 2)) * 3.0e4        # centrally concentrated
+    pos[0] = 0.0
+    coi = 10.0 ** rng.uniform(-2, 3.5, n) * (rng.uniform(0, 1, n) < 0.7)
+    coi[0] = 0.0
+    big = rng.choice(np.arange(1, n), 40, replace=False)
+    mass[big] = rng.uniform(1e3, 1e6, 40)
+    coi[big] = 10.0 ** rng.uniform(3.5, 5, 40)    # planet / star sized discs
+    pos[5000:5100] = pos[4000:4100]               # coincident pairs
+    pos[6000] = pos[big[0]] + np.array([coi[big[0]], 0.0])   # on the edge: strict < fails
+    pos[7000] = [np.nan, 1.0]
+    pos[7001] = [np.inf, -np.inf]
+    coi[7002] = np.nan
+    coi[7003] = np.inf
+    mass[7003] = 1.9999                           # an infinite COI high up in the mass order
+    order = np.argsort(mass, kind="stable")[-1::-1]
+    want = oracle.find_parents(mass, pos, coi, order)
+    assert len(np.unique(want)) > 500
+    for mode in ("scan", "grid"):
+        monkeypatch.setenv("VSB_PARENTS", mode)
+        got = dev.host_find_parents(order, pos, coi)
+        assert np.array_equal(got, want), mode
+
+
+def test_find_parents_grid_equals_scan_256k(dev, monkeypatch):
+    """Config-3 style disk at 262 144 bodies with the COIs kepler_basic gives them plus a few
+    thousand inflated ones: both paths agree on every parent."""
+    from volatilespace_b200 import synth
+    s = synth.rotating_disk(262144)
+    rng = np.random.default_rng(5)
+    r = np.hypot(s["pos"][:, 0], s["pos"][:, 1])
+    coi = r * (s["mass"] / s["mass"][0]) ** 0.4
+    coi[0] = 0.0
+    sel = rng.choice(np.arange(1, 262144), 3000, replace=False)
+    coi[sel] *= rng.uniform(10, 3000, 3000)
+    order = np.argsort(s["mass"], kind="stable")[-1::-1]
+    res = {}
+    for mode in ("scan", "grid"):
+        monkeypatch.setenv("VSB_PARENTS", mode)
+        res[mode] = dev.host_find_parents(order, s["pos"], coi)
+    assert np.array_equal(res["scan"], res["grid"])
+    assert (res["grid"] != 0).sum() > 1000
 
 
 # ------------------------------------------------------------------ B1 collisions

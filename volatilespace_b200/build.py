@@ -26,6 +26,7 @@ SOURCES = {
     "vsb_gravity_sym.cu": [],
     "vsb_pairs.cu": ["-fmad=false"],
     "vsb_broadphase.cu": ["-fmad=false"],
+    "vsb_parents_grid.cu": ["-fmad=false"],
     "vsb_editor.cu": ["-fmad=false"],
     "vsb_kepler.cu": ["-fmad=false"],
     "vsb_visible.cu": ["-fmad=false"],
@@ -52,7 +53,8 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "vsb_common.cuh"), os.path.join(CSRC, "vsb_orbit_math.cuh"), INCLUDE,
+    headers = [os.path.join(CSRC, "vsb_common.cuh"), os.path.join(CSRC, "vsb_orbit_math.cuh"),
+               os.path.join(CSRC, "vsb_grid.cuh"), INCLUDE,
                os.path.abspath(__file__)]
     objs, procs = [], []
     env = dict(os.environ)

@@ -154,6 +154,7 @@ extern "C" int vsb_ctx_destroy(vsb_ctx *c)
     vsb_buf_free(c->sym_tab);
     vsb_buf_free(c->order);
     vsb_buf_free(c->sorted);
+    vsb_buf_free(c->pgrid);
     vsb_buf_free(c->scratch);
     vsb_buf_free(c->host_stage);
     vsb_buf_free(c->march_stats);

@@ -100,6 +100,7 @@ struct vsb_ctx {
     vsb_buf order;       // int64 order (descending mass) + rank
     int64_t order_n = -1; // number of valid entries uploaded to `order`
     vsb_buf sorted;      // sorted-source staging for find_parents
+    vsb_buf pgrid;       // uniform grid of the find_parents candidate pass
     vsb_buf scratch;     // generic
     vsb_buf host_stage;  // device staging for the stateless host-buffer calls
     vsb_buf march_stats; // work area of the parallel COI-entry march; starts with 4 x u64 counters
@@ -274,6 +275,8 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
 int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order);
 int vsb_launch_find_parents_part(vsb_ctx *c, const int64_t *d_order, int part, int parts);
 int vsb_launch_find_parents_finish(vsb_ctx *c, const int64_t *d_order);
+// sort-based candidate pass (vsb_parents_grid.cu): best[] for all sorted ranks
+int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *scoi2, int *best);
 int vsb_launch_gravity_ref_begin(vsb_ctx *c, const int64_t *d_order, int part, int parts);
 int vsb_launch_gravity_ref_finish(vsb_ctx *c, double gc, const int64_t *d_order);
 int vsb_launch_check_collision(vsb_ctx *c);

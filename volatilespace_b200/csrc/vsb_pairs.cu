@@ -9,6 +9,8 @@
 // chunks), sources staged in shared memory by 1-D TMA bulk copies (UBLKCP) on
 // mbarriers, every lane reading the same source (LDS broadcast); results are
 // combined with order-independent max / min reductions, hence deterministic.
+#include <stdlib.h>
+
 #include "vsb_common.cuh"
 
 namespace {
@@ -210,6 +212,12 @@ int vsb_launch_find_parents_part(vsb_ctx *c, const int64_t *d_order, int part, i
     fp_gather_kernel<<<g, 256, 0, c->stream>>>(d_order, (const double2 *)c->pos, c->coi, n, npad,
                                                spos, scoi2, rank, best);
     c->launches += 1;
+    // From 4096 bodies up the sort-based candidate pass gives the same best[] in O(N); it is not
+    // split (every part computes all rows; the MAX over parts is then a no-op).
+    // VSB_PARENTS=scan|grid overrides.
+    const char *env = getenv("VSB_PARENTS");
+    const bool grid = env ? env[0] == 'g' : n >= 4096;
+    if (grid) return vsb_launch_find_parents_grid(c, spos, scoi2, best);
     const int64_t row_blocks = (n + PB_BLOCK - 1) / PB_BLOCK;
     const int64_t mine = (row_blocks - part + parts - 1) / parts;
     if (mine > 0) {

@@ -1,0 +1,285 @@
+// vsb_parents_grid.cu -- sort-based candidate pass for A1 find_parents
+// (phys_editor.py:350-354 / find_parent_one :36-48) on sm_100a.
+//
+// The reference scans, for every body, all more massive bodies in descending-mass order and
+// keeps the LAST one whose COI contains it: N^2/2 point-in-disc tests.  In sorted-rank space the
+// answer is  best[r] = max { k < r : |pos_r - pos_k|^2 < coi_k^2 },  an order-independent
+// maximum, so it can be taken over any candidate set that contains every true match:
+//   1. stats: bounding box of the (finite) positions, histogram of the binary exponents of
+//      coi^2; the cell size h is the larger of 2 * sqrt(box area / N) (about 4 bodies per cell)
+//      and the smallest power-of-two COI bound that leaves at most PG_MAX_LARGE larger discs;
+//   2. discs with coi^2 > h^2 go to the "large" list, every other disc (coi > 0) is
+//      counting-sorted into a hashed uniform grid by the cell of its centre;
+//   3. a disc of radius <= h can only contain points of its own or an adjacent cell, so each
+//      body tests the discs of its 3x3 neighbourhood and then the large list.
+// The predicate is the bit-exact one of fp_scan_kernel (vsb_pairs.cu: un-fused dx*dx + dy*dy,
+// strict <, coi*coi un-fused), evaluated on every candidate, so best[] -- and with it
+// parents[] -- is identical to the exhaustive scan's.  No input needs a fallback: non-finite
+// positions never satisfy the predicate on either path and are kept out of the bounding box;
+// a cloud collapsed into a few cells only costs time.  O(N) work, ~120 B/body of traffic.
+// Compiled with -fmad=false.
+#include "vsb_common.cuh"
+#include "vsb_grid.cuh"
+
+namespace {
+
+constexpr int PG_MAX_LARGE = 4096;
+constexpr int PG_EXP_BINS = 2048;              // biased exponent of coi^2
+constexpr double PG_MAX_CELLS = 16777216.0;    // 2^24 cells per axis
+
+struct pg_params {
+    double xmin, ymin, inv_h, hh;   // hh: discs with coi^2 <= hh are binned
+    unsigned mask;
+    int n_large;
+    int pad[2];
+};
+
+__device__ __forceinline__ int exp_bin(double v)   // v > 0
+{
+    return (int)((unsigned long long)__double_as_longlong(v) >> 52) & 0x7ff;
+}
+
+// partial[b] = {min x, min y, max x, max y} over finite coordinates; hist[e] += #discs
+__global__ void __launch_bounds__(256)
+pg_stats1_kernel(const double2 *__restrict__ spos, const double *__restrict__ scoi2, int64_t n,
+                 double *__restrict__ partial, unsigned *__restrict__ hist)
+{
+    __shared__ double sh[4][256];
+    __shared__ unsigned sh_hist[PG_EXP_BINS];
+    for (int e = threadIdx.x; e < PG_EXP_BINS; e += 256) sh_hist[e] = 0;
+    __syncthreads();
+    double x0 = 1e308, y0 = 1e308, x1 = -1e308, y1 = -1e308;
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
+        const double2 p = spos[k];
+        if (isfinite(p.x) && isfinite(p.y)) {
+            x0 = fmin(x0, p.x); y0 = fmin(y0, p.y);
+            x1 = fmax(x1, p.x); y1 = fmax(y1, p.y);
+        }
+        const double c2 = scoi2[k];
+        if (c2 > 0.0) atomicAdd(&sh_hist[exp_bin(c2)], 1u);
+    }
+    sh[0][threadIdx.x] = x0; sh[1][threadIdx.x] = y0; sh[2][threadIdx.x] = x1; sh[3][threadIdx.x] = y1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] = fmin(sh[0][threadIdx.x], sh[0][threadIdx.x + o]);
+            sh[1][threadIdx.x] = fmin(sh[1][threadIdx.x], sh[1][threadIdx.x + o]);
+            sh[2][threadIdx.x] = fmax(sh[2][threadIdx.x], sh[2][threadIdx.x + o]);
+            sh[3][threadIdx.x] = fmax(sh[3][threadIdx.x], sh[3][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) partial[blockIdx.x * 4 + threadIdx.x] = sh[threadIdx.x][0];
+    for (int e = threadIdx.x; e < PG_EXP_BINS; e += 256)
+        if (sh_hist[e]) atomicAdd(&hist[e], sh_hist[e]);
+}
+
+__global__ void __launch_bounds__(256)
+pg_stats2_kernel(const double *__restrict__ partial, int nblocks, int64_t n, unsigned mask,
+                 const unsigned *__restrict__ hist, pg_params *P)
+{
+    __shared__ double sh[4][256];
+    double x0 = 1e308, y0 = 1e308, x1 = -1e308, y1 = -1e308;
+    for (int b = threadIdx.x; b < nblocks; b += 256) {
+        x0 = fmin(x0, partial[b * 4]); y0 = fmin(y0, partial[b * 4 + 1]);
+        x1 = fmax(x1, partial[b * 4 + 2]); y1 = fmax(y1, partial[b * 4 + 3]);
+    }
+    sh[0][threadIdx.x] = x0; sh[1][threadIdx.x] = y0; sh[2][threadIdx.x] = x1; sh[3][threadIdx.x] = y1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] = fmin(sh[0][threadIdx.x], sh[0][threadIdx.x + o]);
+            sh[1][threadIdx.x] = fmin(sh[1][threadIdx.x], sh[1][threadIdx.x + o]);
+            sh[2][threadIdx.x] = fmax(sh[2][threadIdx.x], sh[2][threadIdx.x + o]);
+            sh[3][threadIdx.x] = fmax(sh[3][threadIdx.x], sh[3][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    x0 = sh[0][0]; y0 = sh[1][0]; x1 = sh[2][0]; y1 = sh[3][0];
+    if (!(x1 >= x0) || !(y1 >= y0)) x0 = y0 = x1 = y1 = 0.0;   // no finite position at all
+    const double ex = x1 - x0, ey = y1 - y0;
+    // density-based cell: about 4 bodies per cell (a degenerate box falls back to its long side)
+    double area = ex * ey;
+    double h0 = 2.0 * sqrt(area / (double)n);
+    if (!(h0 > 0.0) || !isfinite(h0)) h0 = 2.0 * fmax(ex, ey) / (double)n;
+    if (!(h0 > 0.0) || !isfinite(h0)) h0 = 1.0;
+    // smallest exponent bound with at most PG_MAX_LARGE discs above it: coi^2 < 2^(e+1-1023)
+    unsigned above = 0;
+    int e = PG_EXP_BINS - 1;
+    while (e >= 0 && above + hist[e] <= (unsigned)PG_MAX_LARGE) above += hist[e--];
+    // every disc in bins <= e is binned: hh >= 2^(e + 1 - 1023) (as a double: exponent field e+1)
+    double hh = h0 * h0;
+    if (e >= 0) {
+        const double bound = e + 1 >= 0x7ff ? 1.7e308 : __longlong_as_double((long long)(e + 1) << 52);
+        hh = fmax(hh, bound);
+    }
+    if (!isfinite(hh)) hh = 1.7e308;
+    double h = sqrt(hh) * (1.0 + 1e-6);
+    // at most 2^24 cells per axis
+    h = fmax(h, fmax(ex, ey) / PG_MAX_CELLS);
+    P->xmin = x0;
+    P->ymin = y0;
+    P->inv_h = 1.0 / h;
+    P->hh = hh;
+    P->mask = mask;
+    P->n_large = 0;
+}
+
+__device__ __forceinline__ unsigned cell_of(const pg_params *P, double2 p)
+{
+    // non-finite coordinates give an arbitrary (but valid) bucket; such bodies never match
+    double fx = floor((p.x - P->xmin) * P->inv_h), fy = floor((p.y - P->ymin) * P->inv_h);
+    long long cx = isfinite(fx) ? (long long)fx : 0, cy = isfinite(fy) ? (long long)fy : 0;
+    return cell_bucket(cx, cy, P->mask);
+}
+
+// bucket[k] = grid bucket of disc k, 0xffffffff for a large disc (appended to the list),
+// 0xfffffffe for a body that owns no disc
+__global__ void __launch_bounds__(256)
+pg_count_kernel(const double2 *__restrict__ spos, const double *__restrict__ scoi2, int64_t n,
+                pg_params *P, unsigned *__restrict__ bucket, unsigned *__restrict__ counts,
+                int *__restrict__ large)
+{
+    int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    const double c2 = scoi2[k];
+    if (!(c2 > 0.0)) {
+        bucket[k] = 0xfffffffeu;
+        return;
+    }
+    if (c2 > P->hh) {
+        int slot = atomicAdd(&P->n_large, 1);
+        large[slot] = (int)k;   // capacity n; pg_stats2_kernel keeps the list short (<= PG_MAX_LARGE
+                                // unless that many discs have an infinite COI)
+        bucket[k] = 0xffffffffu;
+        return;
+    }
+    unsigned b = cell_of(P, spos[k]);
+    bucket[k] = b;
+    atomicAdd(&counts[b], 1u);
+}
+
+__global__ void __launch_bounds__(256)
+pg_scatter_kernel(const double2 *__restrict__ spos, const double *__restrict__ scoi2, int64_t n,
+                  const unsigned *__restrict__ bucket, unsigned *__restrict__ cursor,
+                  double2 *__restrict__ epos, double *__restrict__ ecoi2, int *__restrict__ erank)
+{
+    int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    unsigned b = bucket[k];
+    if (b >= 0xfffffffeu) return;
+    unsigned slot = atomicAdd(&cursor[b], 1u);
+    epos[slot] = spos[k];
+    ecoi2[slot] = scoi2[k];
+    erank[slot] = (int)k;
+}
+
+// thread <-> sorted rank r: discs of the 3x3 neighbourhood, then the large list
+__global__ void __launch_bounds__(128)
+pg_query_kernel(const pg_params *P, const unsigned *__restrict__ starts,
+                const double2 *__restrict__ epos, const double *__restrict__ ecoi2,
+                const int *__restrict__ erank, const int *__restrict__ large,
+                const double2 *__restrict__ spos, const double *__restrict__ scoi2, int64_t n,
+                int *__restrict__ best)
+{
+    __shared__ double2 lp[128];
+    __shared__ double lc[128];
+    __shared__ int lr[128];
+    const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const bool live = r < n;
+    const double2 me = spos[live ? r : 0];
+    int found = -1;
+    if (live) {
+        const double fx = floor((me.x - P->xmin) * P->inv_h), fy = floor((me.y - P->ymin) * P->inv_h);
+        const long long cx = isfinite(fx) ? (long long)fx : 0, cy = isfinite(fy) ? (long long)fy : 0;
+        unsigned seen[9];
+        int nseen = 0;
+        for (int oy = -1; oy <= 1; ++oy)
+            for (int ox = -1; ox <= 1; ++ox) {
+                const unsigned b = cell_bucket(cx + ox, cy + oy, P->mask);
+                bool dup = false;   // two neighbour cells hashing to one bucket: scan it once
+                for (int k = 0; k < nseen; ++k) dup |= seen[k] == b;
+                if (dup) continue;
+                seen[nseen++] = b;
+                const unsigned e = starts[b + 1];
+                for (unsigned s = starts[b]; s < e; ++s) {
+                    const int k = erank[s];
+                    if (k >= r || k <= found) continue;
+                    const double2 q = epos[s];
+                    const double dx = me.x - q.x, dy = me.y - q.y;
+                    const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    if (d2 < ecoi2[s]) found = k;
+                }
+            }
+    }
+    const int nl = P->n_large;
+    for (int base = 0; base < nl; base += 128) {
+        const int cnt = nl - base < 128 ? nl - base : 128;
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            const int k = large[base + threadIdx.x];
+            lr[threadIdx.x] = k;
+            lp[threadIdx.x] = spos[k];
+            lc[threadIdx.x] = scoi2[k];
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int t = 0; t < cnt; ++t) {
+            const int k = lr[t];
+            if (k >= r || k <= found) continue;
+            const double dx = me.x - lp[t].x, dy = me.y - lp[t].y;
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d2 < lc[t]) found = k;
+        }
+    }
+    if (live) best[r] = found;
+}
+
+}  // namespace
+
+// best[r] for ALL sorted ranks from the staging arrays of fp_gather_kernel (spos, scoi2).
+int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *scoi2, int *best)
+{
+    const int64_t n = c->n;
+    unsigned M = 4096;
+    while ((int64_t)M < 2 * n) M <<= 1;
+    const int nchunks = (int)(M / 1024);
+    VSB_CHECK(nchunks <= 4096, VSB_ERR_ARG, "find_parents grid: too many bodies (%lld)", (long long)n);
+    const int sblocks = c->sm_count * 4;
+    // layout of c->pgrid: params | partial | hist | counts[M] | starts[M+4] | cursor[M] |
+    //                     chunk[4096] | bucket[n] | large[n] | epos[n] | ecoi2[n] | erank[n]
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_par = take(sizeof(pg_params)), o_part = take(sizeof(double) * 4 * sblocks),
+                 o_hist = take(4 * PG_EXP_BINS), o_cnt = take(4 * (size_t)M),
+                 o_st = take(4 * ((size_t)M + 4)), o_cur = take(4 * (size_t)M), o_chk = take(4 * 4096),
+                 o_bkt = take(4 * (size_t)n), o_lrg = take(4 * (size_t)n), o_ep = take(16 * (size_t)n),
+                 o_ec = take(8 * (size_t)n), o_er = take(4 * (size_t)n);
+    VSB_TRY(vsb_buf_reserve(c->pgrid, off));
+    char *base = (char *)c->pgrid.p;
+    pg_params *P = (pg_params *)(base + o_par);
+    double *partial = (double *)(base + o_part);
+    unsigned *hist = (unsigned *)(base + o_hist), *counts = (unsigned *)(base + o_cnt),
+             *starts = (unsigned *)(base + o_st), *cursor = (unsigned *)(base + o_cur),
+             *chunk = (unsigned *)(base + o_chk), *bucket = (unsigned *)(base + o_bkt);
+    int *large = (int *)(base + o_lrg), *erank = (int *)(base + o_er);
+    double2 *epos = (double2 *)(base + o_ep);
+    double *ecoi2 = (double *)(base + o_ec);
+    const unsigned g = (unsigned)((n + 255) / 256);
+
+    // hist and counts are adjacent: one memset
+    VSB_CUDA(cudaMemsetAsync(hist, 0, (o_cnt - o_hist) + 4 * (size_t)M, c->stream));
+    pg_stats1_kernel<<<sblocks, 256, 0, c->stream>>>(spos, scoi2, n, partial, hist);
+    pg_stats2_kernel<<<1, 256, 0, c->stream>>>(partial, sblocks, n, M - 1, hist, P);
+    pg_count_kernel<<<g, 256, 0, c->stream>>>(spos, scoi2, n, P, bucket, counts, large);
+    bp_scan_reduce_kernel<<<nchunks, 256, 0, c->stream>>>(counts, chunk);
+    bp_scan_chunks_kernel<<<1, 1024, 0, c->stream>>>(chunk, nchunks);
+    bp_scan_apply_kernel<<<nchunks, 256, 0, c->stream>>>(counts, chunk, starts, cursor, M);
+    pg_scatter_kernel<<<g, 256, 0, c->stream>>>(spos, scoi2, n, bucket, cursor, epos, ecoi2, erank);
+    pg_query_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(P, starts, epos, ecoi2, erank,
+                                                                         large, spos, scoi2, n, best);
+    c->launches += 8;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
