@@ -1,6 +1,6 @@
 """Small fixed workloads for ncu captures (see profiles/README.md).
 
-    python tools/profile_run.py gravity64k | gravity256k | kepler1m | collision256k | parents64k | points160
+    python tools/profile_run.py gravity64k | gravity256k | moderef1m | kepler1m | collision256k | parents64k | points160
 """
 import os
 import sys
@@ -26,6 +26,16 @@ def main():
         s = synth.rotating_disk(262144)
         dev.upload_bodies(s["mass"], s["pos"], s["vel"])
         dev.allpairs_step(s["gc"], 3)
+    elif mode == "moderef1m":
+        s = synth.rotating_disk(1 << 20)
+        r = np.hypot(s["pos"][:, 0], s["pos"][:, 1])
+        coi = r * (s["mass"] / s["mass"][0]) ** 0.4
+        coi[0] = 0.0
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"], coi=coi, rel_vel=s["vel"])
+        order = np.argsort(s["mass"], kind="stable")[-1::-1]
+        dev.gravity_ref(s["gc"], order)
+        for _ in range(3):
+            dev.gravity_ref(s["gc"], None)
     elif mode == "kepler1m":
         k = synth.kepler_objects(1 << 20)
         dev.kepler_load(KIND_VESSEL, 512, k["a"], k["b"], k["f"], k["ecc"], k["pea"], k["n"],

@@ -50,33 +50,54 @@ __global__ void ref_accel_kernel(int64_t n, const double *__restrict__ mass,
 }
 
 // COI enter/leave fix-up (:366-373): sequential in index order because a body may
-// read the rel_vel of a body fixed earlier in the same loop.  One CTA walks the
-// bodies in 1024-wide slabs; slabs without a parent change cost one barrier.
+// read the rel_vel of a body fixed earlier in the same loop.  A grid-wide pass flags the
+// 1024-wide slabs that contain a parent change; one CTA then walks only those, in index order.
+// slab_flag[s] = 1 if any body of the 1024-wide slab s changed its parent this tick
+__global__ void __launch_bounds__(1024)
+ref_changed_kernel(int64_t n, const int64_t *__restrict__ parents,
+                   const int64_t *__restrict__ parents_old, unsigned char *__restrict__ slab_flag)
+{
+    const int64_t b = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int ch = (b < n && b != 0 && parents[b] != parents_old[b]) ? 1 : 0;
+    const int any = __syncthreads_or(ch);
+    if (threadIdx.x == 0) slab_flag[blockIdx.x] = any ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(1024)
 ref_fixup_kernel(int64_t n, const double *__restrict__ mass, const int64_t *__restrict__ parents,
-                 const int64_t *__restrict__ parents_old, double2 *rel_vel)
+                 const int64_t *__restrict__ parents_old, double2 *rel_vel,
+                 const unsigned char *__restrict__ slab_flag, int64_t nslabs)
 {
     __shared__ int changed[1024];
-    for (int64_t base = 0; base < n; base += 1024) {
-        int64_t b = base + threadIdx.x;
-        int ch = (b < n && b != 0 && parents[b] != parents_old[b]) ? 1 : 0;
-        changed[threadIdx.x] = ch;
-        int any = __syncthreads_or(ch);
-        if (any && threadIdx.x == 0) {
-            for (int t = 0; t < 1024; ++t) {
-                if (!changed[t]) continue;
-                int64_t body = base + t;
-                int64_t parent = parents[body], old = parents_old[body];
-                volatile double *rv = (volatile double *)rel_vel;
-                if (mass[parent] > mass[old]) {  // leaving orbit
-                    rv[2 * body] += rv[2 * old];
-                    rv[2 * body + 1] += rv[2 * old + 1];
-                }
-                if (mass[parent] < mass[old]) {  // entering orbit
-                    rv[2 * body] -= rv[2 * parent];
-                    rv[2 * body + 1] -= rv[2 * parent + 1];
+    __shared__ unsigned char flagged[1024];
+    for (int64_t s0 = 0; s0 < nslabs; s0 += 1024) {
+        const int f = (s0 + threadIdx.x < nslabs) ? slab_flag[s0 + threadIdx.x] : 0;
+        if (!__syncthreads_or(f)) continue;
+        flagged[threadIdx.x] = (unsigned char)f;
+        __syncthreads();
+        for (int sl = 0; sl < 1024; ++sl) {
+            if (!flagged[sl]) continue;      // uniform: shared flag
+            const int64_t base = (s0 + sl) * 1024;
+            const int64_t b = base + threadIdx.x;
+            changed[threadIdx.x] = (b < n && b != 0 && parents[b] != parents_old[b]) ? 1 : 0;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int t = 0; t < 1024; ++t) {
+                    if (!changed[t]) continue;
+                    int64_t body = base + t;
+                    int64_t parent = parents[body], old = parents_old[body];
+                    volatile double *rv = (volatile double *)rel_vel;
+                    if (mass[parent] > mass[old]) {  // leaving orbit
+                        rv[2 * body] += rv[2 * old];
+                        rv[2 * body + 1] += rv[2 * old + 1];
+                    }
+                    if (mass[parent] < mass[old]) {  // entering orbit
+                        rv[2 * body] -= rv[2 * parent];
+                        rv[2 * body + 1] -= rv[2 * parent + 1];
+                    }
                 }
             }
+            __syncthreads();
         }
         __syncthreads();
     }
@@ -746,12 +767,16 @@ int vsb_launch_gravity_ref_finish(vsb_ctx *c, double gc, const int64_t *d_order)
     const unsigned g = (unsigned)((n + 255) / 256);
     ref_accel_kernel<<<g, 256, 0, c->stream>>>(n, c->mass, (const double2 *)c->pos, c->parents, gc,
                                                (double2 *)c->rel_vel);
-    ref_fixup_kernel<<<1, 1024, 0, c->stream>>>(n, c->mass, c->parents, c->parents_old,
-                                                (double2 *)c->rel_vel);
-    // vel_old snapshot + overflow flag live in scratch
-    VSB_TRY(vsb_buf_reserve(c->scratch, 64 + sizeof(double2) * (size_t)c->npad));
+    // vel_old snapshot, overflow flag and the slab flags of the fix-up live in scratch
+    const int64_t nslabs = (n + 1023) / 1024;
+    VSB_TRY(vsb_buf_reserve(c->scratch, 64 + sizeof(double2) * (size_t)c->npad + (size_t)nslabs));
     int *overflow = (int *)c->scratch.p;
     double2 *vel_old = (double2 *)((char *)c->scratch.p + 64);
+    unsigned char *slab_flag = (unsigned char *)c->scratch.p + 64 + sizeof(double2) * (size_t)c->npad;
+    ref_changed_kernel<<<(unsigned)nslabs, 1024, 0, c->stream>>>(n, c->parents, c->parents_old,
+                                                                 slab_flag);
+    ref_fixup_kernel<<<1, 1024, 0, c->stream>>>(n, c->mass, c->parents, c->parents_old,
+                                                (double2 *)c->rel_vel, slab_flag, nslabs);
     VSB_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), c->stream));
     VSB_CUDA(cudaMemcpyAsync(vel_old, c->vel, sizeof(double2) * n, cudaMemcpyDeviceToDevice,
                              c->stream));
@@ -759,7 +784,7 @@ int vsb_launch_gravity_ref_finish(vsb_ctx *c, double gc, const int64_t *d_order)
     ref_compose_kernel<<<g, 256, 0, c->stream>>>(n, rank, c->parents, (const double2 *)c->rel_vel,
                                                  vel_old, (double2 *)c->vel, (double2 *)c->pos,
                                                  overflow);
-    c->launches += 3;
+    c->launches += 4;
     VSB_CUDA(cudaGetLastError());
     int h_over = 0;
     VSB_CUDA(cudaMemcpyAsync(&h_over, overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

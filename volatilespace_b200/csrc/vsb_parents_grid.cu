@@ -6,7 +6,7 @@
 // answer is  best[r] = max { k < r : |pos_r - pos_k|^2 < coi_k^2 },  an order-independent
 // maximum, so it can be taken over any candidate set that contains every true match:
 //   1. stats: bounding box of the (finite) positions, histogram of the binary exponents of
-//      coi^2; the cell size h is the larger of 2 * sqrt(box area / N) (about 4 bodies per cell)
+//      coi^2; the cell size h is the larger of 1.5 * sqrt(box area / N) (2-3 bodies per cell)
 //      and the smallest power-of-two COI bound that leaves at most PG_MAX_LARGE larger discs;
 //   2. discs with coi^2 > h^2 go to the "large" list, every other disc (coi > 0) is
 //      counting-sorted into a hashed uniform grid by the cell of its centre;
@@ -26,6 +26,11 @@ namespace {
 constexpr int PG_MAX_LARGE = 4096;
 constexpr int PG_EXP_BINS = 2048;              // biased exponent of coi^2
 constexpr double PG_MAX_CELLS = 16777216.0;    // 2^24 cells per axis
+
+struct __align__(32) pg_entry {   // one disc of the grid: a single 32-byte sector per candidate
+    double x, y, coi2;
+    long long rank;
+};
 
 struct pg_params {
     double xmin, ymin, inv_h, hh;   // hh: discs with coi^2 <= hh are binned
@@ -79,6 +84,8 @@ pg_stats2_kernel(const double *__restrict__ partial, int nblocks, int64_t n, uns
                  const unsigned *__restrict__ hist, pg_params *P)
 {
     __shared__ double sh[4][256];
+    __shared__ unsigned sh_hist[PG_EXP_BINS];
+    for (int e = threadIdx.x; e < PG_EXP_BINS; e += 256) sh_hist[e] = hist[e];
     double x0 = 1e308, y0 = 1e308, x1 = -1e308, y1 = -1e308;
     for (int b = threadIdx.x; b < nblocks; b += 256) {
         x0 = fmin(x0, partial[b * 4]); y0 = fmin(y0, partial[b * 4 + 1]);
@@ -99,15 +106,15 @@ pg_stats2_kernel(const double *__restrict__ partial, int nblocks, int64_t n, uns
     x0 = sh[0][0]; y0 = sh[1][0]; x1 = sh[2][0]; y1 = sh[3][0];
     if (!(x1 >= x0) || !(y1 >= y0)) x0 = y0 = x1 = y1 = 0.0;   // no finite position at all
     const double ex = x1 - x0, ey = y1 - y0;
-    // density-based cell: about 4 bodies per cell (a degenerate box falls back to its long side)
+    // density-based cell: 2-3 bodies per cell (a degenerate box falls back to its long side)
     double area = ex * ey;
-    double h0 = 2.0 * sqrt(area / (double)n);
+    double h0 = 1.5 * sqrt(area / (double)n);
     if (!(h0 > 0.0) || !isfinite(h0)) h0 = 2.0 * fmax(ex, ey) / (double)n;
     if (!(h0 > 0.0) || !isfinite(h0)) h0 = 1.0;
     // smallest exponent bound with at most PG_MAX_LARGE discs above it: coi^2 < 2^(e+1-1023)
     unsigned above = 0;
     int e = PG_EXP_BINS - 1;
-    while (e >= 0 && above + hist[e] <= (unsigned)PG_MAX_LARGE) above += hist[e--];
+    while (e >= 0 && above + sh_hist[e] <= (unsigned)PG_MAX_LARGE) above += sh_hist[e--];
     // every disc in bins <= e is binned: hh >= 2^(e + 1 - 1023) (as a double: exponent field e+1)
     double hh = h0 * h0;
     if (e >= 0) {
@@ -163,23 +170,26 @@ pg_count_kernel(const double2 *__restrict__ spos, const double *__restrict__ sco
 __global__ void __launch_bounds__(256)
 pg_scatter_kernel(const double2 *__restrict__ spos, const double *__restrict__ scoi2, int64_t n,
                   const unsigned *__restrict__ bucket, unsigned *__restrict__ cursor,
-                  double2 *__restrict__ epos, double *__restrict__ ecoi2, int *__restrict__ erank)
+                  pg_entry *__restrict__ ent)
 {
     int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (k >= n) return;
     unsigned b = bucket[k];
     if (b >= 0xfffffffeu) return;
     unsigned slot = atomicAdd(&cursor[b], 1u);
-    epos[slot] = spos[k];
-    ecoi2[slot] = scoi2[k];
-    erank[slot] = (int)k;
+    const double2 p = spos[k];
+    pg_entry e;
+    e.x = p.x;
+    e.y = p.y;
+    e.coi2 = scoi2[k];
+    e.rank = k;
+    ent[slot] = e;
 }
 
 // thread <-> sorted rank r: discs of the 3x3 neighbourhood, then the large list
 __global__ void __launch_bounds__(128)
 pg_query_kernel(const pg_params *P, const unsigned *__restrict__ starts,
-                const double2 *__restrict__ epos, const double *__restrict__ ecoi2,
-                const int *__restrict__ erank, const int *__restrict__ large,
+                const pg_entry *__restrict__ ent, const int *__restrict__ large,
                 const double2 *__restrict__ spos, const double *__restrict__ scoi2, int64_t n,
                 int *__restrict__ best)
 {
@@ -204,12 +214,12 @@ pg_query_kernel(const pg_params *P, const unsigned *__restrict__ starts,
                 seen[nseen++] = b;
                 const unsigned e = starts[b + 1];
                 for (unsigned s = starts[b]; s < e; ++s) {
-                    const int k = erank[s];
+                    const pg_entry q = ent[s];
+                    const int k = (int)q.rank;
                     if (k >= r || k <= found) continue;
-                    const double2 q = epos[s];
                     const double dx = me.x - q.x, dy = me.y - q.y;
                     const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                    if (d2 < ecoi2[s]) found = k;
+                    if (d2 < q.coi2) found = k;
                 }
             }
     }
@@ -248,14 +258,13 @@ int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *
     VSB_CHECK(nchunks <= 4096, VSB_ERR_ARG, "find_parents grid: too many bodies (%lld)", (long long)n);
     const int sblocks = c->sm_count * 4;
     // layout of c->pgrid: params | partial | hist | counts[M] | starts[M+4] | cursor[M] |
-    //                     chunk[4096] | bucket[n] | large[n] | epos[n] | ecoi2[n] | erank[n]
+    //                     chunk[4096] | bucket[n] | large[n] | ent[n]
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_par = take(sizeof(pg_params)), o_part = take(sizeof(double) * 4 * sblocks),
                  o_hist = take(4 * PG_EXP_BINS), o_cnt = take(4 * (size_t)M),
                  o_st = take(4 * ((size_t)M + 4)), o_cur = take(4 * (size_t)M), o_chk = take(4 * 4096),
-                 o_bkt = take(4 * (size_t)n), o_lrg = take(4 * (size_t)n), o_ep = take(16 * (size_t)n),
-                 o_ec = take(8 * (size_t)n), o_er = take(4 * (size_t)n);
+                 o_bkt = take(4 * (size_t)n), o_lrg = take(4 * (size_t)n), o_ent = take(sizeof(pg_entry) * (size_t)n);
     VSB_TRY(vsb_buf_reserve(c->pgrid, off));
     char *base = (char *)c->pgrid.p;
     pg_params *P = (pg_params *)(base + o_par);
@@ -263,9 +272,8 @@ int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *
     unsigned *hist = (unsigned *)(base + o_hist), *counts = (unsigned *)(base + o_cnt),
              *starts = (unsigned *)(base + o_st), *cursor = (unsigned *)(base + o_cur),
              *chunk = (unsigned *)(base + o_chk), *bucket = (unsigned *)(base + o_bkt);
-    int *large = (int *)(base + o_lrg), *erank = (int *)(base + o_er);
-    double2 *epos = (double2 *)(base + o_ep);
-    double *ecoi2 = (double *)(base + o_ec);
+    int *large = (int *)(base + o_lrg);
+    pg_entry *ent = (pg_entry *)(base + o_ent);
     const unsigned g = (unsigned)((n + 255) / 256);
 
     // hist and counts are adjacent: one memset
@@ -276,9 +284,9 @@ int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *
     bp_scan_reduce_kernel<<<nchunks, 256, 0, c->stream>>>(counts, chunk);
     bp_scan_chunks_kernel<<<1, 1024, 0, c->stream>>>(chunk, nchunks);
     bp_scan_apply_kernel<<<nchunks, 256, 0, c->stream>>>(counts, chunk, starts, cursor, M);
-    pg_scatter_kernel<<<g, 256, 0, c->stream>>>(spos, scoi2, n, bucket, cursor, epos, ecoi2, erank);
-    pg_query_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(P, starts, epos, ecoi2, erank,
-                                                                         large, spos, scoi2, n, best);
+    pg_scatter_kernel<<<g, 256, 0, c->stream>>>(spos, scoi2, n, bucket, cursor, ent);
+    pg_query_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(P, starts, ent, large, spos,
+                                                                         scoi2, n, best);
     c->launches += 8;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;
