@@ -144,9 +144,14 @@ def main():
     ref_single.load_system(econf, ebd, ebo)
     ref_sh = ShardedPhysics(Device(local), rank, world)
     ref_sh.load_system(econf, ebd, ebo)
-    for _ in range(3):
+    for tick in range(4):
+        # ticks 0-1: the sort-based candidate pass on every rank (default at this size);
+        # ticks 2-3: the exhaustive scan, split over the ranks by row blocks
+        if tick == 2:
+            os.environ["VSB_PARENTS"] = "scan"
         ref_single.gravity()
         ref_sh.gravity()
+    os.environ.pop("VSB_PARENTS", None)
     par = ref_single.dev.get(F_PARENTS)
     ok_ref = np.array_equal(par, ref_sh.dev.get(F_PARENTS)) and \
         np.array_equal(ref_single.dev.get(F_POS), ref_sh.dev.get(F_POS)) and \
