@@ -457,6 +457,17 @@ int vsb_kepler_visible_orbits(vsb_ctx *ctx, int kind, int64_t nref,
 int vsb_kepler_curves_gather(vsb_ctx *ctx, int kind, const int64_t *idx, int64_t count,
                              double *out);
 
+/* phys_vessel.Physics.curve_segments, phys_vessel.py:828-1075 (with concat_wrap :35-79), for the
+ * listed vessels (self.visible_orbits), on the device-resident VESSEL state: elements and positions
+ * (vsb_kepler_load / _move / _tick), orbit points (vsb_vessel_events_load / vsb_vessel_points) and
+ * the moved curves (vsb_kepler_curves / _tick).  Row k of every output belongs to vessel idx[k]:
+ * light, dark (count,P,2), NaN padded -- dark is all NaN where the reference never writes it (a
+ * vessel without any orbit point); first_intersect (count,2); intersect_type (count): 0 none,
+ * 1 impact, 2 COI entry, 3 COI leave; intersect_time (count); select_range (count,2). */
+int vsb_vessel_curve_segments(vsb_ctx *ctx, const int64_t *idx, int64_t count, double *light,
+                              double *dark, double *first_intersect, int32_t *intersect_type,
+                              double *intersect_time, double *select_range);
+
 #ifdef __cplusplus
 }
 #endif

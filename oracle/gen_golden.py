@@ -821,6 +821,129 @@ def gen_vessel_events(ns, conf, bd, bod):
           "snapshots" % (nv, len(cw), len(sv), len(cx), len(cv)))
 
 
+def gen_vessel_draw(ns, conf, bd, bod):
+    """Drawing-side vessel functions of game mode (phys_vessel.py:635-741 predict_next_orbit,
+    :761-774 rotate, :777-825 selected, :828-1075 curve_segments) on the live reference: the
+    Solar System + the synthetic vessels of `vessel_points`, snapshots of the inputs and outputs of
+    each call at three ticks of the game loop."""
+    import copy
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    from volatilespace.physics import convert
+    sys.path.remove(rh.REFERENCE_ROOT)
+    g = np.load(os.path.join(OUT, "vessel_points.npz"))
+    P = 16
+    korb = convert.to_kepler(bd["mass"], copy.deepcopy(bod), conf["gc"], conf["coi_coef"])
+    pb = ns.phys_body.Physics()
+    rh.set_curve_points(ns, pb, P)
+    pb.load(conf, copy.deepcopy(bd), copy.deepcopy(korb))
+    body_data, body_orb, bpos, bma, bea, _ = pb.initial(1)
+    v12 = g["vessel12"]
+    keep = np.flatnonzero(~((v12[:, 3] >= 0.8) & (v12[:, 3] < 1)))
+    keep = keep[~np.isin(keep, [2, 5])]
+    nv = len(keep)
+    rng = np.random.default_rng(20240701)
+    vessel_data = {"name": np.array(["v%d" % i for i in keep]), "mass": np.ones(nv),
+                   "rot_angle": rng.uniform(0, 2 * np.pi, nv), "rot_acc": rng.uniform(0.001, 0.01, nv)}
+    vessel_orb = {"a": v12[keep, 0].copy(), "ecc": v12[keep, 3].copy(), "pe_arg": v12[keep, 6].copy(),
+                  "ma": v12[keep, 4].copy(), "ref": g["v_ref"][keep].copy(), "dir": v12[keep, 8].copy()}
+    pv = ns.phys_vessel.Physics()
+    rh.set_curve_points(ns, pv, P)
+    pv.load(conf, body_data, body_orb, vessel_data, vessel_orb)
+    pv.initial(1, bpos, bma, bea)
+    out = dict(keep=keep, gc=conf["gc"], P=P, body_mass=np.array(pv.body_mass, dtype=float),
+               body_ref=np.array(pv.body_ref, dtype=np.int64),
+               body_static=np.stack([pv.body_a, pv.body_b, pv.body_f, pv.body_ecc, pv.body_pea,
+                                     pv.body_n, pv.body_dr, pv.body_coi], axis=1).astype(float),
+               rot_acc=np.array(pv.rot_acc, dtype=float))
+
+    def vstate():
+        return np.stack([pv.a, pv.b, pv.f, pv.ecc, pv.pea, pv.n, pv.dr, pv.ma, pv.ea, pv.prev_ea,
+                         pv.u, pv.pe_d, pv.ap_d, pv.period], axis=1).astype(float)
+
+    def pts():
+        return np.concatenate([pv.body_impact, pv.body_enter_atm, pv.coi_leave, pv.coi_enter], axis=1)
+
+    snaps = 0
+    cover = {}
+    tick = 0
+    for stop, warp in ((0, 1), (160, 5), (420, 25)):
+        while tick < stop:
+            pv.check_warp(warp)
+            pv.predict_enter_coi_service()
+            bpos, bma, bea = pb.move(warp)
+            pv.move(warp, bpos, bma, bea)
+            changed = pv.cross_coi()
+            if changed is not None:
+                pv.change_vessel(changed)
+            tick += 1
+        k = snaps
+        cm = pv.curve_move()
+        pv.visible_orbits = list(range(nv))
+        out.update({"s%d_v" % k: vstate(), "s%d_p" % k: pts(), "s%d_ref" % k: np.array(pv.ref, dtype=np.int64),
+                    "s%d_pos" % k: np.array(pv.pos, dtype=float), "s%d_bpos" % k: np.array(bpos, dtype=float),
+                    "s%d_bma" % k: np.array(pv.body_ma, dtype=float), "s%d_curves_mov" % k: np.array(cm, dtype=float)})
+        light, dark, first, itype, itime, srange = pv.curve_segments()
+        itype = np.array(itype, dtype=np.int64)
+        # dark is np.empty garbage where the reference never writes it: no intersection at all
+        dark_valid = itype > 0
+        for v in range(nv):
+            al = np.array([pv.body_impact[v, int(pv.ecc[v] >= 1)], pv.coi_enter[v, 1],
+                           pv.coi_leave[v, int(pv.ecc[v] >= 1)]])
+            if not dark_valid[v] and not np.all(np.isnan(al)):
+                dark_valid[v] = True          # cut by a later COI leave, or the full curve
+            key = (int(itype[v]), bool(pv.ecc[v] < 1), bool(pv.dr[v] > 0))
+            cover[key] = cover.get(key, 0) + 1
+        dark = np.where(dark_valid[:, None, None], dark, np.nan)
+        out.update({"s%d_light" % k: light, "s%d_dark" % k: dark, "s%d_dark_valid" % k: dark_valid,
+                    "s%d_first" % k: first, "s%d_itype" % k: itype,
+                    "s%d_itime" % k: np.array(itime, dtype=float), "s%d_srange" % k: srange})
+        # selected(): every vessel the reference's scalar math accepts
+        sel = np.full((nv, 13), np.nan)
+        for v in range(nv):
+            try:
+                ta, pe, pe_t, ap, ap_t, dist, so, sh, sv = pv.selected(v)
+                sel[v] = [ta, pe[0], pe[1], pe_t, ap[0], ap[1], ap_t, dist, so, sh, sv, 1.0, 0.0]
+            except (ValueError, ZeroDivisionError):
+                pass
+        out["s%d_selected" % k] = sel
+        # predict_next_orbit(): vessels with a COI change ahead
+        pno_v, pno_curve, pno_sc = [], [], []
+        for v in range(nv):
+            try:
+                r = pv.predict_next_orbit(v)
+            except (ValueError, ZeroDivisionError, FloatingPointError):
+                continue
+            if r[0] is None:
+                continue
+            curve, ap, ap_d, ap_t, pe, pe_d, pe_t, new_ref, nrp, nvp, enter = r
+            pno_v.append(v)
+            pno_curve.append(np.array(curve, dtype=float))
+            pno_sc.append([ap[0], ap[1], ap_d, ap_t, pe[0], pe[1], pe_d, pe_t, float(new_ref),
+                           nrp[0], nrp[1], nvp[0], nvp[1], float(enter)])
+        out.update({"s%d_pno_v" % k: np.array(pno_v, dtype=np.int64),
+                    "s%d_pno_curve" % k: np.array(pno_curve, dtype=float).reshape(len(pno_v), P, 2),
+                    "s%d_pno_sc" % k: np.array(pno_sc, dtype=float).reshape(len(pno_v), 14)})
+        # rotate(): active vessel 3 accelerates at warp 1, everything stops at higher warp
+        r_in = (np.array(pv.rot_angle, dtype=float), np.array(pv.rot_speed, dtype=float))
+        ang1 = np.array(pv.rotate(1, 3, 1.0), dtype=float)
+        ang2 = np.array(pv.rotate(1, 3, -1.0), dtype=float)
+        sp2 = np.array(pv.rot_speed, dtype=float)
+        ang3 = np.array(pv.rotate(5, 3, 1.0), dtype=float)
+        sp3 = np.array(pv.rot_speed, dtype=float)
+        out.update({"s%d_rot_angle_in" % k: r_in[0], "s%d_rot_speed_in" % k: r_in[1],
+                    "s%d_rot_angle1" % k: ang1, "s%d_rot_angle2" % k: ang2, "s%d_rot_speed2" % k: sp2,
+                    "s%d_rot_angle3" % k: ang3, "s%d_rot_speed3" % k: sp3})
+        # keep some spin for the next snapshot
+        pv.rot_speed = np.array(pv.rot_speed, dtype=float) + rng.uniform(-0.05, 0.05, nv)
+        print("  vessel_draw snapshot %d (tick %d): types %s, %d selected, %d predict_next_orbit" % (
+            k, tick, np.bincount(itype, minlength=4).tolist(), int(np.sum(~np.isnan(sel[:, 0]))),
+            len(pno_v)))
+        snaps += 1
+    out["n_snap"] = snaps
+    save("vessel_draw", **out)
+    print("  vessel_draw coverage (type, ell, ccw): %s" % sorted(cover.items()))
+
+
 def gen_mapfiles(ns, conf, bd, bod):
     """N4 (savefile I/O): maps written by the reference's peripherals.save_file from seeded arrays
     (Newtonian, and Keplerian with vessels) and what its load_file returns for them."""
@@ -944,6 +1067,7 @@ def main():
     if want("intersect"): gen_intersect(ns)
     if want("vessel_points"): gen_vessel_points(ns, conf, bd, bod)
     if want("vessel_events"): gen_vessel_events(ns, conf, bd, bod)
+    if want("vessel_draw"): gen_vessel_draw(ns, conf, bd, bod)
     if want("mapfiles"): gen_mapfiles(ns, conf, bd, bod)
     if want("convert_vel"): gen_convert_vel(ns)
 

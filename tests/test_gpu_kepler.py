@@ -926,3 +926,82 @@ def test_editor_free_functions_golden(dev):
         if i > 0:                                    # an earlier body collides with nobody
             assert pe.check_collision_one(i - 1, cm, pos, rad, device=dev) is None
     assert pe.check_collision_one(len(cm) - 1, cm, g["cc_pos"][0], g["cc_rad"][0], device=dev) is None
+
+
+# ------------------------------------------------------------------ curve_segments
+@pytest.mark.gpu
+def test_curve_segments_golden(dev):
+    """phys_vessel.Physics.curve_segments on the resident state against the live reference:
+    intersection types, NaN pattern (= which rows each part holds) and select ranges exact;
+    coordinates to 1e-9 of the curve's scale (the curves are generated on the device)."""
+    from conftest import VS, split_points
+    from volatilespace_b200._lib import KIND_VESSEL, K_EA, K_MA, K_POS
+    g = golden("vessel_draw")
+    P, nv = int(g["P"]), len(g["keep"])
+    t = np.linspace(-np.pi, np.pi, P)
+    for k in range(int(g["n_snap"])):
+        v, p, ref, pos, bpos = (g["s%d_%s" % (k, x)] for x in ("v", "p", "ref", "pos", "bpos"))
+        col = lambda name: np.ascontiguousarray(v[:, VS[name]])
+        dev.kepler_load(KIND_VESSEL, P, col("a"), col("b"), col("f"), col("ecc"), col("pea"),
+                        col("n"), col("dr"), col("ma"), col("ea"), ref, t)
+        dev.vessel_events_load(col("pe_d"), col("ap_d"), col("period"), *split_points(p), None,
+                               col("prev_ea"))
+        dev.kepler_move(KIND_VESSEL, 0.0, bpos)          # parent positions onto the device
+        dev.kepler_set(KIND_VESSEL, K_EA, col("ea"))     # ... and the reference's exact state
+        dev.kepler_set(KIND_VESSEL, K_MA, col("ma"))
+        dev.kepler_set(KIND_VESSEL, K_POS, pos)
+        dev.kepler_curves(KIND_VESSEL)
+        cm = dev.kepler_curves_get(KIND_VESSEL, 0, nv, P)
+        scale = np.max(np.abs(g["s%d_curves_mov" % k]), axis=(1, 2))
+        assert np.all(np.abs(cm - g["s%d_curves_mov" % k]) <= 1e-12 * scale[:, None, None])
+        idx = np.arange(nv)
+        light, dark, first, itype, itime, srange = dev.vessel_curve_segments(idx, P)
+        assert np.array_equal(itype, g["s%d_itype" % k]), k
+        assert np.array_equal(srange, g["s%d_srange" % k], equal_nan=True), k
+        for got, want in ((light, g["s%d_light" % k]), (dark, g["s%d_dark" % k])):
+            assert np.array_equal(np.isnan(got), np.isnan(want)), k
+            err = np.abs(np.nan_to_num(got) - np.nan_to_num(want))
+            assert np.all(err <= 1e-9 * scale[:, None, None]), (k, float(err.max()))
+        assert np.array_equal(np.isnan(first), np.isnan(g["s%d_first" % k]))
+        assert np.all(np.abs(np.nan_to_num(first) - np.nan_to_num(g["s%d_first" % k]))
+                      <= 1e-9 * scale[:, None])
+        np.testing.assert_allclose(itime, g["s%d_itime" % k], rtol=1e-9, atol=1e-9)
+        # a subset in another order gives the same rows
+        sub = np.array([nv - 1, 3, 77, 0])
+        l2, d2, f2, t2, tm2, r2 = dev.vessel_curve_segments(sub, P)
+        assert np.array_equal(l2, light[sub], equal_nan=True)
+        assert np.array_equal(d2, dark[sub], equal_nan=True) and np.array_equal(t2, itype[sub])
+    dev.kepler_free(KIND_VESSEL)
+
+
+@pytest.mark.gpu
+def test_curve_segments_through_the_class():
+    """The shim method: full-shaped arrays like the reference, NaN rows outside visible_orbits."""
+    from conftest import VS, split_points
+    from volatilespace_b200.phys_vessel import Physics
+    g = golden("vessel_draw")
+    P, nv = int(g["P"]), len(g["keep"])
+    k = 1
+    v, p, ref, pos, bpos = (g["s%d_%s" % (k, x)] for x in ("v", "p", "ref", "pos", "bpos"))
+    nb = len(g["body_mass"])
+    ph = Physics(curve_points=P)
+    ph.load({"gc": float(g["gc"])}, {"mass": g["body_mass"]}, {"coi": g["body_static"][:, 7]},
+            {"name": ["v%d" % i for i in range(nv)]},
+            {"a": v[:, VS["a"]], "ecc": v[:, VS["ecc"]], "pe_arg": v[:, VS["pea"]],
+             "ma": v[:, VS["ma"]], "ref": ref, "dir": v[:, VS["dr"]], "ea": v[:, VS["ea"]]})
+    ph.initial(0.0, bpos)
+    bi, ba, cl, ce = split_points(p)
+    ph.body_impact[:], ph.body_enter_atm[:], ph.coi_leave[:], ph.coi_enter[:] = bi, ba, cl, ce
+    ph.dev.vessel_events_load(ph.pe_d, ph.ap_d, ph.period, bi, ba, cl, ce, None, v[:, VS["prev_ea"]])
+    ph.visible_orbits = np.arange(0, nv, 2)
+    light, dark, first, itype, itime, srange = ph.curve_segments()
+    assert light.shape == (nv, P, 2) and np.all(np.isnan(light[1::2])) and np.all(itype[1::2] == 0)
+    assert np.array_equal(itype[::2], g["s%d_itype" % k][::2])
+    scale = np.max(np.abs(g["s%d_curves_mov" % k]), axis=(1, 2))[::2, None, None]
+    want = g["s%d_light" % k][::2]
+    assert np.array_equal(np.isnan(light[::2]), np.isnan(want))
+    assert np.all(np.abs(np.nan_to_num(light[::2]) - np.nan_to_num(want)) <= 1e-7 * scale)
+    sparse = ph.curve_segments(dense=False)
+    assert sorted(sparse[0]) == list(range(0, nv, 2))
+    assert np.array_equal(sparse[0][4], light[4], equal_nan=True)
+    assert np.array_equal(ph.intersect_time, itime)

@@ -441,3 +441,76 @@ def test_convert_velocity_helpers(oracle):
             got = oracle.velocity_to_kepler(g["v2k_pos"][i], g["v2k_vel"][i], g["v2k_u"][i], fs)
             np.testing.assert_allclose(got, want[i], rtol=1e-11, atol=1e-11, equal_nan=True,
                                        err_msg="failsafe %d row %d" % (fs, i))
+
+
+# ------------------------------------------------------------- drawing-side vessel functions
+@pytest.fixture(scope="module")
+def draw(oracle):
+    import draw_oracle
+    return draw_oracle
+
+
+def _eq(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def test_vessel_draw_curve_segments(draw):
+    """curve_segments (phys_vessel.py:828-1075) of the restatement == the live reference, bit for
+    bit, at three ticks of the game loop (all intersection types x ellipse/hyperbola x direction)."""
+    g = golden("vessel_draw")
+    P, nv = int(g["P"]), len(g["keep"])
+    seen = set()
+    for k in range(int(g["n_snap"])):
+        v, p, ref, pos, bpos, cm = (g["s%d_%s" % (k, x)] for x in
+                                    ("v", "p", "ref", "pos", "bpos", "curves_mov"))
+        light, dark, dv, first, itype, itime, srange = draw.curve_segments(
+            P, v, p, pos, ref, bpos, cm, range(nv))
+        assert _eq(itype, g["s%d_itype" % k]) and _eq(dv, g["s%d_dark_valid" % k]), k
+        assert _eq(light, g["s%d_light" % k]), k
+        assert _eq(np.where(dv[:, None, None], dark, np.nan), g["s%d_dark" % k]), k
+        assert _eq(first, g["s%d_first" % k]) and _eq(itime, g["s%d_itime" % k]), k
+        assert _eq(srange, g["s%d_srange" % k]), k
+        seen |= {(int(t), bool(e < 1), bool(d > 0)) for t, e, d in zip(itype, v[:, 3], v[:, 6])}
+    assert len(seen) >= 15
+
+
+def test_vessel_draw_concat_wrap_with_nans(draw):
+    """The NaN clean-up of concat_wrap (phys_vessel.py:73-77): rows are packed to the front."""
+    rng = np.random.default_rng(3)
+    arr = rng.uniform(-1, 1, (12, 2))
+    arr[[2, 7]] = np.nan
+    out = draw.concat_wrap(arr, np.array([9.0, 9.0]), 5, 10, np.array([8.0, 8.0]))
+    want = np.vstack([[9.0, 9.0], arr[5:7], arr[8:10], [8.0, 8.0]])
+    assert _eq(out[:len(want)], want) and np.all(np.isnan(out[len(want):]))
+    out = draw.concat_wrap(arr, np.array([9.0, 9.0]), 9, 3, np.array([8.0, 8.0]))
+    want = np.vstack([[8.0, 8.0], arr[9:], arr[:2], [9.0, 9.0]])
+    assert _eq(out[:len(want)], want) and np.all(np.isnan(out[len(want):]))
+
+
+def test_vessel_draw_selected_rotate_predict_next_orbit(draw):
+    """selected (:777-825), rotate (:761-774) and predict_next_orbit (:635-741) == live reference."""
+    g = golden("vessel_draw")
+    P, nv = int(g["P"]), len(g["keep"])
+    t = np.linspace(-np.pi, np.pi, P)
+    n_pno = 0
+    for k in range(int(g["n_snap"])):
+        v, p, ref, pos, bpos = (g["s%d_%s" % (k, x)] for x in ("v", "p", "ref", "pos", "bpos"))
+        sel = g["s%d_selected" % k]
+        for i in range(nv):
+            if not np.isnan(sel[i, 0]):
+                assert _eq(draw.selected(v[i], pos[i], bpos[ref[i]]), sel[i, :11]), (k, i)
+        for j, i in enumerate(g["s%d_pno_v" % k]):
+            r = draw.predict_next_orbit(int(i), P, v, p, ref, g["body_static"], g["body_mass"],
+                                        g["body_ref"], g["s%d_bma" % k], float(g["gc"]),
+                                        g["s%d_itime" % k][i], t)
+            assert r is not None and _eq(r[0], g["s%d_pno_curve" % k][j]), (k, i)
+            assert _eq(r[1], g["s%d_pno_sc" % k][j]), (k, i)
+            n_pno += 1
+        acc = g["rot_acc"]
+        ang, spd = draw.rotate(1, 3, 1.0, g["s%d_rot_angle_in" % k], g["s%d_rot_speed_in" % k], acc)
+        assert _eq(ang, g["s%d_rot_angle1" % k])
+        ang, spd = draw.rotate(1, 3, -1.0, ang, spd, acc)
+        assert _eq(ang, g["s%d_rot_angle2" % k]) and _eq(spd, g["s%d_rot_speed2" % k])
+        ang, spd = draw.rotate(5, 3, 1.0, ang, spd, acc)
+        assert _eq(ang, g["s%d_rot_angle3" % k]) and _eq(spd, g["s%d_rot_speed3" % k])
+    assert n_pno > 100

@@ -131,6 +131,7 @@ SIGNATURES = {
     "vsb_kepler_culling_uniform": [_ctx, C.c_int, _f64, _pv, _f64, _pv, _pi],
     "vsb_kepler_visible_orbits": [_ctx, C.c_int, _i64, _pv, _pv, _pv, _f64, _f64, _pv, _pi],
     "vsb_kepler_curves_gather": [_ctx, C.c_int, _pv, _i64, _pv],
+    "vsb_vessel_curve_segments": [_ctx, _pv, _i64, _pv, _pv, _pv, _pv, _pv, _pv],
 }
 
 _lib = None

@@ -34,6 +34,7 @@ SOURCES = {
     "vsb_convert.cu": ["-fmad=false"],
     "vsb_intersect.cu": ["-fmad=false"],
     "vsb_events.cu": ["-fmad=false"],
+    "vsb_segments.cu": ["-fmad=false"],
 }
 
 

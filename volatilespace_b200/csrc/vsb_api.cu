@@ -2130,6 +2130,48 @@ extern "C" int vsb_kepler_curves_gather(vsb_ctx *c, int kind, const int64_t *idx
     return d2h(c, out, d_out, bytes);
 }
 
+extern "C" int vsb_vessel_curve_segments(vsb_ctx *c, const int64_t *idx, int64_t count,
+                                         double *light, double *dark, double *first_intersect,
+                                         int32_t *intersect_type, double *intersect_time,
+                                         double *select_range)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(need_vessel_events(c, "vsb_vessel_curve_segments", &k));
+    VSB_CHECK(k->curves.p && k->ref_pos, VSB_ERR_STATE,
+              "vsb_vessel_curve_segments: no moved curves yet (vsb_kepler_curves / vsb_kepler_tick)");
+    VSB_CHECK(count >= 0 && (count == 0 || (idx && light && dark && first_intersect &&
+                                            intersect_type && intersect_time && select_range)),
+              VSB_ERR_ARG, "vsb_vessel_curve_segments: bad argument");
+    if (count == 0) return VSB_OK;
+    for (int64_t i = 0; i < count; ++i)
+        VSB_CHECK(idx[i] >= 0 && idx[i] < k->n, VSB_ERR_ARG,
+                  "vsb_vessel_curve_segments: index %lld out of range", (long long)idx[i]);
+    // staging: light | dark | first | time | range | type | idx
+    const size_t curve_bytes = 16 * (size_t)count * (size_t)k->P;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t o_dark = al(curve_bytes), o_first = o_dark + al(curve_bytes),
+                 o_time = o_first + al(16 * (size_t)count), o_range = o_time + al(8 * (size_t)count),
+                 o_type = o_range + al(16 * (size_t)count), o_idx = o_type + al(4 * (size_t)count),
+                 total = o_idx + al(8 * (size_t)count);
+    VSB_TRY(vsb_buf_reserve(c->host_stage, total));
+    char *base = (char *)c->host_stage.p;
+    int64_t *d_idx = (int64_t *)(base + o_idx);
+    VSB_CUDA(cudaMemcpyAsync(d_idx, idx, 8 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    VSB_TRY(vsb_launch_curve_segments(c, *k, d_idx, count, (double *)base, (double *)(base + o_dark),
+                                      (double *)(base + o_first), (int *)(base + o_type),
+                                      (double *)(base + o_time), (double *)(base + o_range)));
+    VSB_CUDA(cudaMemcpyAsync(light, base, curve_bytes, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(dark, base + o_dark, curve_bytes, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(first_intersect, base + o_first, 16 * (size_t)count,
+                             cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(intersect_time, base + o_time, 8 * (size_t)count,
+                             cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(select_range, base + o_range, 16 * (size_t)count,
+                             cudaMemcpyDeviceToHost, c->stream));
+    return d2h(c, intersect_type, base + o_type, 4 * (size_t)count);
+}
+
 extern "C" int vsb_kepler_free(vsb_ctx *c, int kind)
 {
     CTX(c);

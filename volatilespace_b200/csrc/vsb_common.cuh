@@ -275,6 +275,10 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
 int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order);
 int vsb_launch_find_parents_part(vsb_ctx *c, const int64_t *d_order, int part, int parts);
 int vsb_launch_find_parents_finish(vsb_ctx *c, const int64_t *d_order);
+// phys_vessel.Physics.curve_segments for the listed vessels (vsb_segments.cu)
+int vsb_launch_curve_segments(vsb_ctx *c, const vsb_kepler_state &k, const int64_t *d_idx, int64_t count,
+                              double *light, double *dark, double *first, int *type, double *time,
+                              double *range);
 // sort-based candidate pass (vsb_parents_grid.cu): best[] for all sorted ranks
 int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *scoi2, int *best);
 int vsb_launch_gravity_ref_begin(vsb_ctx *c, const int64_t *d_order, int part, int parts);

@@ -120,25 +120,6 @@ cross_scan_kernel(int64_t nv, const double *__restrict__ ecc, const double *__re
 }
 
 // --- the orbit change of a crossing vessel ---------------------------------------------------
-__device__ void ps_orb2xy(double a, double b, double f, double ecc, double pea, double rx, double ry,
-                          double ea, double *out)
-{   // phys_shared.py:187-199; ea == 0 gives (0, 0) WITHOUT the reference position
-    if (ea == 0) {
-        out[0] = out[1] = 0;
-        return;
-    }
-    double xn, yn;
-    if (ecc < 1) {
-        xn = a * cos(ea) - f;
-        yn = b * sin(ea);
-    } else {
-        xn = a * cosh(ea) - f;
-        yn = b * sinh(ea);
-    }
-    out[0] = (xn * cos(pea - PI_D) - yn * sin(pea - PI_D)) + rx;
-    out[1] = (xn * sin(pea - PI_D) + yn * cos(pea - PI_D)) + ry;
-}
-
 __device__ double ps_compare(double a, double b)
 {   // phys_shared.py:35-48
     if (a == b) return 0.0;

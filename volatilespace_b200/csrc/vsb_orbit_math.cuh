@@ -101,4 +101,35 @@ __device__ __forceinline__ int first_intersect(double ea_vessel, const double *p
     return best;
 }
 
+// phys_shared.orb2xy
+__device__ void ps_orb2xy(double a, double b, double f, double ecc, double pea, double rx, double ry,
+                          double ea, double *out)
+{   // phys_shared.py:187-199; ea == 0 gives (0, 0) WITHOUT the reference position
+    if (ea == 0) {
+        out[0] = out[1] = 0;
+        return;
+    }
+    double xn, yn;
+    if (ecc < 1) {
+        xn = a * cos(ea) - f;
+        yn = b * sin(ea);
+    } else {
+        xn = a * cosh(ea) - f;
+        yn = b * sinh(ea);
+    }
+    out[0] = (xn * cos(pea - PI_D) - yn * sin(pea - PI_D)) + rx;
+    out[1] = (xn * sin(pea - PI_D) + yn * cos(pea - PI_D)) + ry;
+}
+
+// phys_shared.orbit_time_to, phys_shared.py:58-64 (Python's max(x, 0.0) keeps a NaN x)
+__device__ __forceinline__ double orbit_time_to(double src, double dst, double ecc, double dr, double n)
+{
+    if (ecc >= 1) {
+        const double t = -dr * (dst - src) / n;
+        return 0.0 > t ? 0.0 : t;
+    }
+    if (dr < 0) return py_mod(src - dst, 2 * PI_D) / n;
+    return py_mod(dst - src, 2 * PI_D) / n;
+}
+
 }  // namespace

@@ -529,6 +529,18 @@ class Device:
         check(self.L.vsb_kepler_curves_gather(self.h, kind, ptr(idx), len(idx), ptr(out)))
         return out
 
+    def vessel_curve_segments(self, idx, P):
+        """curve_segments for the listed vessels on the resident state -> (light, dark,
+        first_intersect, intersect_type, intersect_time, select_range), one row per index."""
+        idx = i64(idx)
+        m = len(idx)
+        light, dark = np.empty((m, int(P), 2)), np.empty((m, int(P), 2))
+        first, rng = np.empty((m, 2)), np.empty((m, 2))
+        itype, itime = np.empty(m, dtype=np.int32), np.empty(m)
+        check(self.L.vsb_vessel_curve_segments(self.h, ptr(idx), m, ptr(light), ptr(dark), ptr(first),
+                                               ptr(itype), ptr(itime), ptr(rng)))
+        return light, dark, first, itype, itime, rng
+
     def kepler_free(self, kind):
         check(self.L.vsb_kepler_free(self.h, kind))
 

@@ -3,8 +3,8 @@
 points `Physics.points` (:372-474: body impact, atmosphere entry, COI leave, COI enter
 -- SURVEY 8f N2), batched over all vessels, and the per-tick event scans built on those
 points: `check_warp` (:506-560), `predict_enter_coi_service` (:744-758), `cross_coi`
-(:563-632) and `change_vessel` (:306-361).  Drawing-side helpers (predict_next_orbit,
-curve_segments, selected, rotate) stay with the caller.
+(:563-632) and `change_vessel` (:306-361), and the drawing-side `curve_segments` (:828-1075:
+the lit / dark part of every visible orbit curve, cut on the device from the resident curves).
 """
 import numpy as np
 
@@ -239,6 +239,44 @@ class Physics:
         self.visible_orbits = dev.kepler_visible_orbits(KIND_VESSEL, n, coi_truth, self.body_coi,
                                                         self.pe_d, zoom, self.screen_x)
         return self.visible_vessels, self.visible_orbits
+
+    # phys_vessel.py:828-1075
+    def curve_segments(self, dense=None):
+        """Two segments for each curve on screen (after curve_move() and points()): returns
+        (curves_light, curves_dark, first_intersect, intersect_type, intersect_time,
+        select_range) like the reference.  Rows of vessels outside `visible_orbits` -- np.empty
+        garbage in the reference -- are NaN; `curves_dark` is also NaN for a visible vessel
+        without any orbit point (the reference leaves that row unwritten).  With dense=False (the
+        default above 65 536 vessels) the two curve sets are dicts {vessel: (P,2) array} instead of
+        (Nv,P,2) arrays, so that only visible curves ever exist on the host."""
+        n, P = self.n_vessels, self.curve_points
+        vis = np.asarray(self.visible_orbits, dtype=np.int64)
+        if not self._resident:
+            self.dev.vessel_events_load(self.pe_d, self.ap_d, self.period, self.body_impact,
+                                        self.body_enter_atm, self.coi_leave, self.coi_enter,
+                                        self._hold, self.prev_ea)
+        light, dark, first, itype, itime, srange = self.dev.vessel_curve_segments(vis, P)
+        first_intersect = np.full((n, 2), np.nan)
+        select_range = np.full((n, 2), np.nan)
+        intersect_type = np.zeros(n, dtype=np.int64)
+        intersect_time = np.zeros(n)
+        first_intersect[vis] = first
+        select_range[vis] = srange
+        intersect_type[vis] = itype
+        intersect_time[vis] = itime
+        self.intersect_time = intersect_time
+        if dense is None:
+            dense = n <= 65536
+        if dense:
+            curves_light = np.full((n, P, 2), np.nan)
+            curves_dark = np.full((n, P, 2), np.nan)
+            curves_light[vis] = light
+            curves_dark[vis] = dark
+        else:
+            curves_light = {int(v): light[k] for k, v in enumerate(vis)}
+            curves_dark = {int(v): dark[k] for k, v in enumerate(vis)}
+        return (curves_light, curves_dark, first_intersect, intersect_type, intersect_time,
+                select_range)
 
     def tick(self, warp, body_pos):
         """move + curve_move in one fused kernel (results stay on the device)."""
