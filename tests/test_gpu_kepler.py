@@ -1005,3 +1005,53 @@ def test_curve_segments_through_the_class():
     assert sorted(sparse[0]) == list(range(0, nv, 2))
     assert np.array_equal(sparse[0][4], light[4], equal_nan=True)
     assert np.array_equal(ph.intersect_time, itime)
+
+
+@pytest.mark.gpu
+def test_predict_next_orbit_through_the_class():
+    """phys_vessel.Physics.predict_next_orbit of the shim against the live reference: the same
+    vessels get an orbit, new parent / enter flag exact, scalars rel 1e-7, curve rows 1e-7 of the
+    curve's scale with the same NaN pattern (index rounding can move one row on a few)."""
+    from conftest import VS, split_points
+    from volatilespace_b200.phys_vessel import Physics
+    g = golden("vessel_draw")
+    P, nv = int(g["P"]), len(g["keep"])
+    bs = g["body_static"]
+    total = pattern_ok = 0
+    for k in range(int(g["n_snap"])):
+        v, p, ref, bpos = (g["s%d_%s" % (k, x)] for x in ("v", "p", "ref", "bpos"))
+        ph = Physics(curve_points=P)
+        ph.load({"gc": float(g["gc"])}, {"mass": g["body_mass"]},
+                {"coi": bs[:, 7], "ref": g["body_ref"], "a": bs[:, 0], "b": bs[:, 1], "f": bs[:, 2],
+                 "ecc": bs[:, 3], "pea": bs[:, 4], "n": bs[:, 5], "dir": bs[:, 6]},
+                {"name": ["v%d" % i for i in range(nv)]},
+                {"a": v[:, VS["a"]], "ecc": v[:, VS["ecc"]], "pe_arg": v[:, VS["pea"]],
+                 "ma": v[:, VS["ma"]], "ref": ref, "dir": v[:, VS["dr"]], "ea": v[:, VS["ea"]]})
+        ph.initial(0.0, bpos)
+        bi, ba, cl, ce = split_points(p)
+        ph.body_impact[:], ph.body_enter_atm[:], ph.coi_leave[:], ph.coi_enter[:] = bi, ba, cl, ce
+        ph.body_ma = g["s%d_bma" % k]
+        ph.intersect_time = g["s%d_itime" % k]
+        want_v = list(g["s%d_pno_v" % k])
+        for i in range(nv):
+            r = ph.predict_next_orbit(i)
+            if i not in want_v:
+                continue
+            j = want_v.index(i)
+            assert r[0] is not None, (k, i)
+            curve, ap, ap_d, ap_t, pe, pe_d, pe_t, new_ref, nrp, nvp, enter = r
+            sc = g["s%d_pno_sc" % k][j]
+            assert new_ref == int(sc[8]) and bool(enter) == bool(sc[13]), (k, i)
+            got = np.array([ap[0], ap[1], ap_d, ap_t, pe[0], pe[1], pe_d, pe_t, nrp[0], nrp[1],
+                            nvp[0], nvp[1]], dtype=float)
+            want = np.concatenate([sc[:8], sc[9:13]])
+            scale = max(np.max(np.abs(want)), 1.0)
+            assert np.all(np.abs(got - want) <= 1e-7 * scale), (k, i, got - want)
+            wc = g["s%d_pno_curve" % k][j]
+            total += 1
+            if np.array_equal(np.isnan(curve), np.isnan(wc)):
+                pattern_ok += 1
+                cs = np.nanmax(np.abs(wc))
+                assert np.all(np.abs(np.nan_to_num(curve) - np.nan_to_num(wc)) <= 1e-7 * cs), (k, i)
+        ph.dev.kepler_free(1)
+    assert total > 100 and pattern_ok >= total - 3

@@ -9,7 +9,7 @@ from .device import default_device
 def newton_root_kepler_hyp(ecc, ma, ea_guess):
     """phys_shared.py:114-122."""
     out = default_device().host_newton_root_kepler_hyp(ecc, ma, ea_guess)
-    return float(out) if np.ndim(ecc) == 0 and np.ndim(ma) == 0 else out
+    return float(np.ravel(out)[0]) if np.ndim(ecc) == 0 and np.ndim(ma) == 0 else out
 
 
 def orb2xy(a, b, f, ecc, pea, ref_pos, ea):

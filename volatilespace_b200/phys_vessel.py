@@ -4,12 +4,15 @@ points `Physics.points` (:372-474: body impact, atmosphere entry, COI leave, COI
 -- SURVEY 8f N2), batched over all vessels, and the per-tick event scans built on those
 points: `check_warp` (:506-560), `predict_enter_coi_service` (:744-758), `cross_coi`
 (:563-632) and `change_vessel` (:306-361), and the drawing-side `curve_segments` (:828-1075:
-the lit / dark part of every visible orbit curve, cut on the device from the resident curves).
+the lit / dark part of every visible orbit curve, cut on the device from the resident curves);
+the one-vessel-per-frame helpers `selected`, `rotate`, `predict_next_orbit` are host code
+(vessel_draw.py).
 """
 import numpy as np
 
 from ._lib import KIND_VESSEL, K_EA, K_MA, K_POS
 from .device import Device, default_device
+from . import vessel_draw
 from .synth import calc_orb
 
 
@@ -55,6 +58,11 @@ class Physics:
         self.ref = np.array(vessel_orb_data["ref"], dtype=np.int64)
         self.dr = np.array(vessel_orb_data["dir"], dtype=np.float64)
         self.n_vessels = len(self.a)
+        zeros = np.zeros(self.n_vessels)
+        self.rot_angle = np.array((vessel_data or {}).get("rot_angle", zeros), dtype=np.float64)  # :216-218
+        self.rot_acc = np.array((vessel_data or {}).get("rot_acc", zeros), dtype=np.float64)
+        self.rot_speed = np.zeros(self.n_vessels)
+        self.intersect_time = np.zeros(self.n_vessels)
         self.pos = np.zeros((self.n_vessels, 2))
         self.ea = np.array(vessel_orb_data.get("ea", np.zeros(self.n_vessels)), dtype=np.float64)
         self._hold = np.zeros(self.n_vessels, dtype=np.uint8)
@@ -277,6 +285,26 @@ class Physics:
             curves_dark = {int(v): dark[k] for k, v in enumerate(vis)}
         return (curves_light, curves_dark, first_intersect, intersect_type, intersect_time,
                 select_range)
+
+    # phys_vessel.py:777-825
+    def selected(self, vessel):
+        """Physics for the selected vessel (after move()): (ta, pe, pe_t, ap, ap_t, distance,
+        speed_orb, speed_hor, speed_vert).  One vessel per frame: host scalar math."""
+        el = {k: float(getattr(self, k)[vessel]) for k in
+              ("a", "b", "ecc", "pea", "n", "dr", "ma", "ea", "u", "pe_d", "ap_d")}
+        return vessel_draw.selected(el, self.pos[vessel], np.asarray(self.body_pos)[self.ref[vessel]])
+
+    # phys_vessel.py:761-774
+    def rotate(self, warp, vessel, direction):
+        self.rot_angle = vessel_draw.rotate(warp, vessel, direction, self.rot_angle, self.rot_speed,
+                                            self.rot_acc)
+        return self.rot_angle
+
+    # phys_vessel.py:635-741
+    def predict_next_orbit(self, vessel):
+        """Next orbit of `vessel` after its coming COI change (orbit line and ghost body): the
+        reference's 11-tuple, all None when there is nothing ahead.  Needs curve_segments()."""
+        return vessel_draw.predict_next_orbit(self, vessel)
 
     def tick(self, warp, body_pos):
         """move + curve_move in one fused kernel (results stay on the device)."""
