@@ -180,7 +180,9 @@ allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ 
 // P-side slab of (X, Q) ), fixed order; optional integrator v += a ; P += v.
 __global__ void __launch_bounds__(256)
 allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__restrict__ part_q,
-                           const int *__restrict__ qslot_first, int S, int M, int64_t n,
+                           const int *__restrict__ qslot_first,
+                           const unsigned char *__restrict__ own_p,
+                           const unsigned char *__restrict__ own_q, int S, int M, int64_t n,
                            double gc, double2 *__restrict__ acc, double2 *__restrict__ vel,
                            double2 *__restrict__ pos, int integrate, int add_into)
 {
@@ -189,13 +191,17 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
     const int X = (int)(i / S);
     const int r = (int)(i - (int64_t)X * S);
     double sx = 0.0, sy = 0.0;
+    // own_p / own_q (multi-GPU): which slabs this rank's tasks wrote -- the others are skipped
+    // instead of being read as zeros (1/world of the slab traffic per rank)
     for (int sl = qslot_first[X]; sl < qslot_first[X + 1]; ++sl) {
+        if (own_q && !own_q[sl]) continue;
         double2 v = part_q[(int64_t)sl * S + r];
         sx += v.x;
         sy += v.y;
     }
     for (int Q = X; Q < M; ++Q) {
         const int64_t slab = (int64_t)Q * (Q + 1) / 2 + X;
+        if (own_p && !own_p[slab]) continue;
         double2 v = part_p[slab * S + r];
         sx += v.x;
         sy += v.y;
@@ -281,8 +287,22 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
                     if (dealt % world == rank) mine[nm++] = all[i].t;
                     ++dealt;
                 }
+        // ownership flags of the P-side slabs (one per block pair) and Q-side slabs (one per task)
+        unsigned char *own = (unsigned char *)calloc((size_t)(pairs + slot + 1), 1);
+        if (!own) {
+            free(all);
+            free(qfirst);
+            free(mine);
+            VSB_CHECK(false, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
+        }
+        for (int i = 0; i < nm; ++i) {
+            own[pairs + mine[i].qslot] = 1;
+            for (int P = mine[i].p0; P < mine[i].p1; ++P)
+                own[(int64_t)mine[i].q * (mine[i].q + 1) / 2 + P] = 1;
+        }
+        const size_t own_bytes = (size_t)(pairs + slot);
         int rc = vsb_buf_reserve(c->sym_tab, sizeof(sym_task) * (size_t)(nm + 1) +
-                                                 sizeof(int) * (size_t)(M + 1) + 512);
+                                                 sizeof(int) * (size_t)(M + 1) + own_bytes + 1024);
         char *qf = nullptr;
         cudaError_t ce = cudaSuccess;
         if (rc == VSB_OK) {
@@ -292,8 +312,13 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
             if (ce == cudaSuccess)
                 ce = cudaMemcpyAsync(qf, qfirst, sizeof(int) * (size_t)(M + 1),
                                      cudaMemcpyHostToDevice, c->stream);
+            char *ow = qf + (sizeof(int) * (size_t)(M + 1) + 255) / 256 * 256;
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(ow, own, own_bytes, cudaMemcpyHostToDevice, c->stream);
+            c->sym_own_off = (int64_t)(ow - (char *)c->sym_tab.p);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
         }
+        free(own);
         free(all);
         free(qfirst);
         free(mine);
@@ -341,8 +366,10 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
         VSB_CHECK(launched, VSB_ERR_ARG, "allpairs_sym: no kernel for shape %d,%d,%d,%d", warps, tpl, su, mb);
         c->launches += 1;
     }
+    const unsigned char *own_p = world > 1 ? (const unsigned char *)c->sym_tab.p + c->sym_own_off : nullptr;
+    const unsigned char *own_q = world > 1 ? own_p + pairs : nullptr;
     allpairs_sym_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-        part_p, part_q, d_qf, S, M, n, gc, (double2 *)c->acc, (double2 *)c->vel,
+        part_p, part_q, d_qf, own_p, own_q, S, M, n, gc, (double2 *)c->acc, (double2 *)c->vel,
         (double2 *)c->pos, (world == 1 && integrate) ? 1 : 0, 0);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
