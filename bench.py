@@ -271,6 +271,11 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
             ms = time_ticks(torch, stream, lambda: dev.gravity_ref(s["gc"], None), reps, nobar) / reps
             res[mode] = {"ms_per_tick": ms, "body_ticks_per_s": 1048576 / (ms * 1e-3)}
         os.environ.pop("VSB_PARENTS", None)
+        # A7 simplified_orbit_coi on the same state (load / add / delete / twice per merge)
+        dev.simplified_orbit_coi(s["gc"], 0.4, order)
+        t0 = time.perf_counter()
+        dev.simplified_orbit_coi(s["gc"], 0.4, order)
+        res["simplified_orbit_coi_ms"] = (time.perf_counter() - t0) * 1e3
         res["note"] = ("grid = sort-based candidate pass for find_parents (default from 4096 bodies), "
                        "scan = the exhaustive N^2/2 point-in-COI scan; identical parents")
         out["disk1m_mode_ref_tick"] = res

@@ -562,18 +562,64 @@ def test_randomised_small_systems_vs_oracle(dev, oracle, seed):
                                    err_msg="%s seed %d" % (k, seed))
 
 
-def test_simplified_orbit_coi_multi_slab(dev, oracle):
-    """A7 across several 1024-rank slabs."""
+@pytest.mark.parametrize("coi_coef", [0.7, 0.2])
+def test_simplified_orbit_coi_multi_slab(dev, oracle, parents_mode, coi_coef):
+    """A7 across several 1024-rank slabs, with the later ranks reached by the scan or through the
+    grid; coi_coef 0.2 makes the heavy bodies' COIs larger than a grid cell (large-disc list)."""
     from volatilespace_b200._lib import F_COI
     n = 3000
     mass, pos, vel = small_cloud(n, 91, extent=2.0e4, central=1.0e6)
     mass[1:40] = np.random.default_rng(1).uniform(500, 5000, 39)
     dev.upload_bodies(mass, pos, vel)
     order = np.argsort(mass)[-1::-1]
-    largest = dev.simplified_orbit_coi(1.0, 0.7, order)
-    wl, wcoi = oracle.simplified_orbit_coi(mass, pos, vel, 1.0, 0.7, order)
+    largest = dev.simplified_orbit_coi(1.0, coi_coef, order)
+    wl, wcoi = oracle.simplified_orbit_coi(mass, pos, vel, 1.0, coi_coef, order)
     assert largest == wl
     np.testing.assert_allclose(dev.get(F_COI), wcoi, rtol=1e-13)
+
+
+def test_simplified_orbit_coi_nested_chains(dev, oracle, parents_mode):
+    """A7 where the dependency chains run INSIDE a slab: a star, planets, moons, sub-moons and
+    moonlets of neighbouring mass ranks nested in each other's COIs (each body's COI depends on
+    its parent's, resolved by fixed-point rounds in soc_slab_kernel), plus a dense field of light
+    bodies that fall into those COIs, over many slabs.  COIs equal the sequential oracle's (1e-12)."""
+    from volatilespace_b200._lib import F_COI
+    rng = np.random.default_rng(17)
+    gc = 1.0
+    mass, pos, vel = [1.0e9], [np.zeros(2)], [np.zeros(2)]
+
+    def satellites(parent, count, m_lo, m_hi, r_lo, r_hi, depth):
+        for _ in range(count):
+            m = rng.uniform(m_lo, m_hi)
+            r = rng.uniform(r_lo, r_hi)
+            th = rng.uniform(0, 2 * np.pi)
+            p = pos[parent] + r * np.array([np.cos(th), np.sin(th)])
+            v = vel[parent] + np.sqrt(gc * mass[parent] / r) * np.array([-np.sin(th), np.cos(th)])
+            mass.append(m), pos.append(p), vel.append(v)
+            me = len(mass) - 1
+            if depth:
+                coi = r * (m / mass[parent]) ** 0.4
+                satellites(me, 3, m * 1e-3, m * 3e-3, coi * 0.05, coi * 0.5, depth - 1)
+
+    satellites(0, 12, 1.0e5, 1.0e6, 1.0e6, 1.0e7, 3)      # 12 * (1 + 3 + 9 + 27) bodies, 4 levels
+    nh = len(mass)
+    n = 9000
+    mass = np.concatenate([mass, rng.uniform(1e-6, 1e-3, n - nh)])
+    pos = np.vstack([pos, np.zeros((n - nh, 2))])
+    vel = np.vstack([vel, np.zeros((n - nh, 2))])
+    # light bodies: most of them next to one of the hierarchy's bodies
+    host = rng.integers(1, nh, n - nh)
+    pos[nh:] = pos[host] + rng.normal(0, 1, (n - nh, 2)) * 2.0e4
+    vel[nh:] = vel[host] + rng.normal(0, 1, (n - nh, 2)) * 0.5
+    dev.upload_bodies(mass, pos, vel)
+    order = np.argsort(mass, kind="stable")[-1::-1]
+    largest = dev.simplified_orbit_coi(gc, 0.4, order)
+    wl, wcoi = oracle.simplified_orbit_coi(mass, pos, vel, gc, 0.4, order)
+    assert largest == wl
+    assert (wcoi[1:nh] > 0).sum() > 300
+    got = dev.get(F_COI)
+    assert np.array_equal(got > 0, wcoi > 0)
+    np.testing.assert_allclose(got, wcoi, rtol=1e-12)      # CUDA pow vs glibc pow: last ulp
 
 
 def test_allpairs_merge_sequence(dev, oracle):

@@ -281,6 +281,9 @@ int vsb_launch_curve_segments(vsb_ctx *c, const vsb_kepler_state &k, const int64
                               double *range);
 // sort-based candidate pass (vsb_parents_grid.cu): best[] for all sorted ranks
 int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *scoi2, int *best);
+// A7 on the same grid: all bodies binned once, finished discs scatter into their neighbourhood
+int vsb_launch_soc_grid_begin(vsb_ctx *c, const int64_t *d_order, int slab);
+int vsb_launch_soc_grid_update(vsb_ctx *c, int64_t r0, int cnt, int slab, const double *scoi, int *best);
 int vsb_launch_gravity_ref_begin(vsb_ctx *c, const int64_t *d_order, int part, int parts);
 int vsb_launch_gravity_ref_finish(vsb_ctx *c, double gc, const int64_t *d_order);
 int vsb_launch_check_collision(vsb_ctx *c);

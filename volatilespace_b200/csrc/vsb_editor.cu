@@ -5,6 +5,8 @@
 //   B3     del_body / set_root / re-rooting moves  phys_editor.py:250-313, 844-857
 //   C7     editor Physics.curve       phys_editor.py:519-544
 // Compiled with -fmad=false: the reference runs un-fused (numba fastmath=False).
+#include <stdlib.h>
+
 #include "vsb_common.cuh"
 
 namespace {
@@ -214,8 +216,8 @@ __global__ void kepler_basic_kernel(int64_t n, const int64_t *__restrict__ paren
 
 // ------------------------------------------------------------------ A7
 // Right-looking blocked sweep over ranks (descending mass).  For a slab of T
-// consecutive ranks: soc_slab_kernel resolves the slab sequentially inside one
-// CTA (rank s needs coi of every earlier rank), then soc_update_kernel tests all
+// consecutive ranks: soc_slab_kernel resolves the slab inside one CTA (rank s needs
+// coi of every earlier rank: fixed-point rounds, see there), then soc_update_kernel tests all
 // later ranks against the slab's T finished COIs (grid-wide, "last match wins" =
 // max rank).  best[] holds the rank of the current parent candidate (-1: none).
 constexpr int SOC_T = 1024;
@@ -239,6 +241,13 @@ __global__ void soc_init_kernel(int64_t npad, int *best, double *scoi)
     }
 }
 
+// One slab of SOC_T consecutive ranks.  The reference's loop is sequential (rank s needs the COI
+// of every earlier rank), but a COI only depends on the body's parent, and the parent only on the
+// COIs of earlier ranks: iterate "all COIs from the current parents, all parents from the current
+// COIs" to the fixed point.  After k rounds the first k ranks of every dependency chain inside
+// the slab are final (induction over the rank), so the fixed point is the sequential answer --
+// same expressions, bit-identical -- and it is reached after (longest chain inside the slab + 1)
+// rounds, typically 2-3, instead of SOC_T barrier-separated steps.
 __global__ void __launch_bounds__(SOC_T)
 soc_slab_kernel(int64_t n, int64_t r0, const int64_t *__restrict__ order, int64_t largest,
                 const double *__restrict__ mass, const double2 *__restrict__ pos,
@@ -252,30 +261,38 @@ soc_slab_kernel(int64_t n, int64_t r0, const int64_t *__restrict__ order, int64_
     const bool live = r < n;
     const int64_t body = live ? order[r] : 0;
     const double2 pb = live ? pos[body] : make_double2(VSB_FAR, VSB_FAR);
+    const double2 vb = live ? vel[body] : make_double2(0.0, 0.0);
+    const double mb = live ? mass[body] : 0.0;
     s_pos[t] = pb;
-    int my_best = live ? best[r] : -1;
-    const int cnt = (int)((n - r0) < SOC_T ? (n - r0) : SOC_T);
-    __syncthreads();
-    for (int s = 0; s < cnt; ++s) {
-        if (t == s) {
-            double c = 0.0;
-            if (r > 0) {  // rank 0 keeps coi 0 (loop starts at bodies_sorted[1:], :332)
-                int64_t parent = my_best < 0 ? largest : order[my_best];
-                c = soc_coi_of(pb, vel[body], mass[body], pos[parent], vel[parent], mass[parent],
-                               gc, coi_coef);
-            }
-            coi[body] = c;
-            scoi[r] = c;
-            s_coi2[s] = c * c;
+    const int outside = live ? best[r] : -1;   // parent candidate among the ranks before the slab
+    int my_best = outside;
+    double c = 0.0;
+    for (;;) {
+        c = 0.0;
+        if (live && r > 0) {  // rank 0 keeps coi 0 (loop starts at bodies_sorted[1:], :332)
+            const int64_t parent = my_best < 0 ? largest : order[my_best];
+            c = soc_coi_of(pb, vb, mb, pos[parent], vel[parent], mass[parent], gc, coi_coef);
         }
+        __syncthreads();          // everyone is done reading s_coi2 of the previous round
+        s_coi2[t] = live ? c * c : -1.0;
         __syncthreads();
-        if (t > s && live) {
-            // (pos[body]-pos[pot])**2 summed < coi[pot]**2  (:337)
-            double dx = pb.x - s_pos[s].x, dy = pb.y - s_pos[s].y;
-            if (dx * dx + dy * dy < s_coi2[s]) my_best = (int)(r0 + s);
+        int nb = outside;
+        if (live) {
+            for (int s = 0; s < t; ++s) {
+                // (pos[body]-pos[pot])**2 summed < coi[pot]**2  (:337); last match wins
+                double dx = pb.x - s_pos[s].x, dy = pb.y - s_pos[s].y;
+                if (dx * dx + dy * dy < s_coi2[s]) nb = (int)(r0 + s);
+            }
         }
+        const int changed = nb != my_best;
+        my_best = nb;
+        if (!__syncthreads_or(changed)) break;
     }
-    if (live) best[r] = my_best;
+    if (live) {
+        coi[body] = c;
+        scoi[r] = c;
+        best[r] = my_best;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -842,6 +859,11 @@ int vsb_launch_simplified_orbit_coi(vsb_ctx *c, double gc, double coi_coef, cons
     VSB_CUDA(cudaMemcpyAsync(&h_largest, d_largest, sizeof(int64_t), cudaMemcpyDeviceToHost,
                              c->stream));
     VSB_CUDA(cudaStreamSynchronize(c->stream));
+    // from 4096 bodies up a finished slab reaches the later ranks through a uniform grid
+    // (vsb_parents_grid.cu) instead of a scan of all of them; VSB_PARENTS=scan|grid overrides
+    const char *env = getenv("VSB_PARENTS");
+    const bool grid = env ? env[0] == 'g' : n >= 4096;
+    if (grid) VSB_TRY(vsb_launch_soc_grid_begin(c, d_order, SOC_T));
     for (int64_t r0 = 0; r0 < n; r0 += SOC_T) {
         const int cnt = (int)((n - r0) < SOC_T ? (n - r0) : SOC_T);
         soc_slab_kernel<<<1, SOC_T, 0, c->stream>>>(n, r0, d_order, h_largest, c->mass,
@@ -850,7 +872,9 @@ int vsb_launch_simplified_orbit_coi(vsb_ctx *c, double gc, double coi_coef, cons
                                                     scoi, c->coi);
         c->launches += 1;
         const int64_t rest = n - r0 - cnt;
-        if (rest > 0) {
+        if (grid) {
+            VSB_TRY(vsb_launch_soc_grid_update(c, r0, cnt, SOC_T, scoi, best));
+        } else if (rest > 0) {
             soc_update_kernel<<<(unsigned)((rest + 255) / 256), 256, 0, c->stream>>>(
                 n, r0, cnt, d_order, (const double2 *)c->pos, scoi, best);
             c->launches += 1;
