@@ -1,6 +1,6 @@
 """Small fixed workloads for ncu captures (see profiles/README.md).
 
-    python tools/profile_run.py gravity64k | gravity256k | moderef1m | kepler1m | collision256k | parents64k | points160
+    python tools/profile_run.py gravity64k | gravity256k | moderef1m | soc1m | kepler1m | collision256k | parents64k | points160
 """
 import os
 import sys
@@ -36,6 +36,14 @@ def main():
         dev.gravity_ref(s["gc"], order)
         for _ in range(3):
             dev.gravity_ref(s["gc"], None)
+    elif mode == "soc1m":
+        s = synth.rotating_disk(1 << 20)
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"])
+        order = np.argsort(s["mass"], kind="stable")[-1::-1]
+        dev.simplified_orbit_coi(s["gc"], 0.4, order)
+        t1 = time.perf_counter()
+        dev.simplified_orbit_coi(s["gc"], 0.4, order)
+        print("simplified_orbit_coi at 1M: %.1f ms" % ((time.perf_counter() - t1) * 1e3))
     elif mode == "kepler1m":
         k = synth.kepler_objects(1 << 20)
         dev.kepler_load(KIND_VESSEL, 512, k["a"], k["b"], k["f"], k["ecc"], k["pea"], k["n"],

@@ -96,6 +96,7 @@ struct vsb_ctx {
     int64_t sym_tasks_n = -1, sym_qf_off = 0, sym_own_off = 0;
     int sym_world = 0, sym_rank = 0, sym_ntasks = 0, sym_nslots = 0, sym_S = 0;
     void *sym_zeroed = nullptr;
+    int soc_rounds = 0;     // fixed-point rounds of the last simplified_orbit_coi (diagnostics)
     int gravity_mode = -1;  // -1: auto, 0: row kernel (vsb_gravity.cu), 1: symmetric (vsb_gravity_sym.cu)
     vsb_buf order;       // int64 order (descending mass) + rank
     int64_t order_n = -1; // number of valid entries uploaded to `order`
@@ -281,9 +282,9 @@ int vsb_launch_curve_segments(vsb_ctx *c, const vsb_kepler_state &k, const int64
                               double *range);
 // sort-based candidate pass (vsb_parents_grid.cu): best[] for all sorted ranks
 int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *scoi2, int *best);
-// A7 on the same grid: all bodies binned once, finished discs scatter into their neighbourhood
-int vsb_launch_soc_grid_begin(vsb_ctx *c, const int64_t *d_order, int slab);
-int vsb_launch_soc_grid_update(vsb_ctx *c, int64_t r0, int cnt, int slab, const double *scoi, int *best);
+// A7 by global fixed-point rounds over the candidate pass (vsb_parents_grid.cu)
+int vsb_launch_soc_fixed_point(vsb_ctx *c, const int64_t *d_order, int64_t largest, double gc,
+                               double coi_coef, int max_rounds, int *converged_out, int *rounds_out);
 int vsb_launch_gravity_ref_begin(vsb_ctx *c, const int64_t *d_order, int part, int parts);
 int vsb_launch_gravity_ref_finish(vsb_ctx *c, double gc, const int64_t *d_order);
 int vsb_launch_check_collision(vsb_ctx *c);

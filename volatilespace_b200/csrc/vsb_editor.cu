@@ -8,17 +8,9 @@
 #include <stdlib.h>
 
 #include "vsb_common.cuh"
+#include "vsb_orbit_math.cuh"
 
 namespace {
-
-constexpr double PI_D = 3.141592653589793;
-
-__device__ __forceinline__ double py_mod(double a, double b)
-{
-    double r = fmod(a, b);
-    if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
-    return r;
-}
 
 // ------------------------------------------------------------------ A2/A3
 // gravity_one, phys_editor.py:51-60 (body != 0): acceleration of `pi` toward `pp`.
@@ -221,16 +213,6 @@ __global__ void kepler_basic_kernel(int64_t n, const int64_t *__restrict__ paren
 // later ranks against the slab's T finished COIs (grid-wide, "last match wins" =
 // max rank).  best[] holds the rank of the current parent candidate (-1: none).
 constexpr int SOC_T = 1024;
-
-__device__ __forceinline__ double soc_coi_of(double2 pb, double2 vb, double mb, double2 pp,
-                                             double2 vp, double mp, double gc, double coi_coef)
-{
-    double rpx = pp.x - pb.x, rpy = pp.y - pb.y;
-    double rvx = vp.x - vb.x, rvy = vp.y - vb.y;
-    double u = gc * mp;
-    double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / sqrt(rpx * rpx + rpy * rpy)));
-    return a > 0 ? a * pow(mb / mp, coi_coef) : 0.0;
-}
 
 __global__ void soc_init_kernel(int64_t npad, int *best, double *scoi)
 {
@@ -859,22 +841,30 @@ int vsb_launch_simplified_orbit_coi(vsb_ctx *c, double gc, double coi_coef, cons
     VSB_CUDA(cudaMemcpyAsync(&h_largest, d_largest, sizeof(int64_t), cudaMemcpyDeviceToHost,
                              c->stream));
     VSB_CUDA(cudaStreamSynchronize(c->stream));
-    // from 4096 bodies up a finished slab reaches the later ranks through a uniform grid
-    // (vsb_parents_grid.cu) instead of a scan of all of them; VSB_PARENTS=scan|grid overrides
+    // From 4096 bodies up: global fixed-point rounds over the O(N) find_parents candidate pass
+    // (vsb_parents_grid.cu) -- the same answer as the sweep below, which stays as the path for
+    // small systems and for hierarchies nested deeper than the round limit.
+    // VSB_PARENTS=scan|grid overrides.
     const char *env = getenv("VSB_PARENTS");
     const bool grid = env ? env[0] == 'g' : n >= 4096;
-    if (grid) VSB_TRY(vsb_launch_soc_grid_begin(c, d_order, SOC_T));
+    if (grid) {
+        int converged = 0;
+        const char *lim = getenv("VSB_SOC_ROUNDS");      // tests: force the fall-back
+        VSB_TRY(vsb_launch_soc_fixed_point(c, d_order, h_largest, gc, coi_coef, lim ? atoi(lim) : 48,
+                                           &converged, &c->soc_rounds));
+        if (converged) return VSB_OK;
+        soc_init_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(npad, best, scoi);
+        c->launches += 1;
+    }
     for (int64_t r0 = 0; r0 < n; r0 += SOC_T) {
         const int cnt = (int)((n - r0) < SOC_T ? (n - r0) : SOC_T);
+        const int64_t rest = n - r0 - cnt;
         soc_slab_kernel<<<1, SOC_T, 0, c->stream>>>(n, r0, d_order, h_largest, c->mass,
                                                     (const double2 *)c->pos,
                                                     (const double2 *)c->vel, gc, coi_coef, best,
                                                     scoi, c->coi);
         c->launches += 1;
-        const int64_t rest = n - r0 - cnt;
-        if (grid) {
-            VSB_TRY(vsb_launch_soc_grid_update(c, r0, cnt, SOC_T, scoi, best));
-        } else if (rest > 0) {
+        if (rest > 0) {
             soc_update_kernel<<<(unsigned)((rest + 255) / 256), 256, 0, c->stream>>>(
                 n, r0, cnt, d_order, (const double2 *)c->pos, scoi, best);
             c->launches += 1;

@@ -132,4 +132,15 @@ __device__ __forceinline__ double orbit_time_to(double src, double dst, double e
     return py_mod(dst - src, 2 * PI_D) / n;
 }
 
+// COI of a body on its orbit around `parent` (simplified_orbit_coi, phys_editor.py:338-345)
+__device__ __forceinline__ double soc_coi_of(double2 pb, double2 vb, double mb, double2 pp,
+                                             double2 vp, double mp, double gc, double coi_coef)
+{
+    double rpx = pp.x - pb.x, rpy = pp.y - pb.y;
+    double rvx = vp.x - vb.x, rvy = vp.y - vb.y;
+    double u = gc * mp;
+    double a = -1 * u / (2 * ((rvx * rvx + rvy * rvy) / 2 - u / sqrt(rpx * rpx + rpy * rpy)));
+    return a > 0 ? a * pow(mb / mp, coi_coef) : 0.0;
+}
+
 }  // namespace

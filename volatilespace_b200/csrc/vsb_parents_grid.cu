@@ -6,8 +6,8 @@
 // answer is  best[r] = max { k < r : |pos_r - pos_k|^2 < coi_k^2 },  an order-independent
 // maximum, so it can be taken over any candidate set that contains every true match:
 //   1. stats: bounding box of the (finite) positions, histogram of the binary exponents of
-//      coi^2; the cell size h is the larger of 1.5 * sqrt(box area / N) (2-3 bodies per cell)
-//      and the smallest power-of-two COI bound that leaves at most PG_MAX_LARGE larger discs;
+//      coi^2; the cell size h is the smallest power-of-two COI bound that leaves at most
+//      PG_MAX_LARGE larger discs (1.5 * sqrt(box area / N) when that few bodies own a disc);
 //   2. discs with coi^2 > h^2 go to the "large" list, every other disc (coi > 0) is
 //      counting-sorted into a hashed uniform grid by the cell of its centre;
 //   3. a disc of radius <= h can only contain points of its own or an adjacent cell, so each
@@ -20,6 +20,7 @@
 // Compiled with -fmad=false.
 #include "vsb_common.cuh"
 #include "vsb_grid.cuh"
+#include "vsb_orbit_math.cuh"
 
 namespace {
 
@@ -116,11 +117,12 @@ pg_stats2_kernel(const double *__restrict__ partial, int nblocks, int64_t n, uns
     int e = PG_EXP_BINS - 1;
     while (e >= 0 && above + sh_hist[e] <= (unsigned)PG_MAX_LARGE) above += sh_hist[e--];
     // every disc in bins <= e is binned: hh >= 2^(e + 1 - 1023) (as a double: exponent field e+1)
+    // The cells only have to be as large as the binned discs: with hashed buckets smaller cells
+    // cost nothing (a query always reads 9 buckets) and keep dense regions cheap.  The density
+    // scale h0 is the fallback when at most PG_MAX_LARGE bodies own a disc at all.
     double hh = h0 * h0;
-    if (e >= 0) {
-        const double bound = e + 1 >= 0x7ff ? 1.7e308 : __longlong_as_double((long long)(e + 1) << 52);
-        hh = fmax(hh, bound);
-    }
+    if (e >= 0)
+        hh = e + 1 >= 0x7ff ? 1.7e308 : __longlong_as_double((long long)(e + 1) << 52);
     if (!isfinite(hh)) hh = 1.7e308;
     double h = sqrt(hh) * (1.0 + 1e-6);
     // at most 2^24 cells per axis
@@ -247,95 +249,51 @@ pg_query_kernel(const pg_params *P, const unsigned *__restrict__ starts,
 }
 
 // ------------------------------------------------------------------ A7 on the same grid
-// simplified_orbit_coi (phys_editor.py:325-346) finishes the COIs slab by slab in descending
-// mass order (vsb_editor.cu); after a slab every LATER rank inside one of its new COIs has to
-// learn about it ("last match wins" = atomicMax of the disc's rank).  With all bodies binned once
-// by position, a finished disc only visits the bodies of its 3x3 cell neighbourhood instead of
-// all N later ranks; discs larger than a cell are collected per slab and scanned by every later
-// rank (there are none in a typical system: the kernel then exits at once).
+// simplified_orbit_coi (phys_editor.py:325-346) is a sequential recurrence in descending mass:
+// a body's COI needs its parent, the parent search needs the COIs of all earlier ranks.  The
+// pair (parents, COIs) it ends with is the UNIQUE fixed point of
+//     COIs    = f(parents)   (soc_coi_of per body), and
+//     parents = g(COIs)      (find_parents: last earlier rank whose COI contains the body)
+// (induction over the rank: rank 0 is fixed, and rank r's parent only reads earlier COIs).  So
+// iterate the two maps over ALL bodies -- f is one thread per body, g is the O(N) candidate pass
+// above -- until a round changes no parent: the sequential answer with the same expressions,
+// reached after (depth of the hierarchy + ~2) rounds instead of N^2/2 tests.
 __global__ void soc_gather_kernel(const int64_t *__restrict__ order, const double2 *__restrict__ pos,
-                                  int64_t n, double2 *__restrict__ spos, double *__restrict__ dummy2)
+                                  int64_t n, int64_t npad, double2 *__restrict__ spos,
+                                  int *__restrict__ best)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    spos[k] = pos[order[k]];
-    dummy2[k] = 1.0e-300;      // every body is binned; the cell size comes from the density
+    if (k >= npad) return;
+    spos[k] = k < n ? pos[order[k]] : make_double2(VSB_FAR, VSB_FAR);
+    best[k] = -1;
 }
 
-__global__ void __launch_bounds__(128)
-soc_scatter_kernel(const pg_params *P, const unsigned *__restrict__ starts,
-                   const pg_entry *__restrict__ ent, const double2 *__restrict__ spos,
-                   const double *__restrict__ scoi, int64_t r0, int cnt, int *__restrict__ best,
-                   int *__restrict__ slab_large, int *__restrict__ slab_nlarge)
+// COIs from the current parents (best[r]: sorted rank of the parent, -1 = the largest body)
+__global__ void soc_coi_all_kernel(int64_t n, const int64_t *__restrict__ order, int64_t largest,
+                                   const double *__restrict__ mass, const double2 *__restrict__ pos,
+                                   const double2 *__restrict__ vel, double gc, double coi_coef,
+                                   const int *__restrict__ best, double *__restrict__ scoi2,
+                                   double *__restrict__ coi)
 {
-    const int s = blockIdx.x * 128 + threadIdx.x;
-    if (s >= cnt) return;
-    const int64_t k = r0 + s;
-    const double c = scoi[k];
-    const double c2 = __dmul_rn(c, c);
-    if (!(c2 > 0.0)) return;
-    if (c2 > P->hh) {
-        slab_large[atomicAdd(slab_nlarge, 1)] = (int)k;
-        return;
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t body = order[r];
+    double c = 0.0;
+    if (r > 0) {  // rank 0 keeps coi 0 (the loop starts at bodies_sorted[1:], :332)
+        const int64_t parent = best[r] < 0 ? largest : order[best[r]];
+        c = soc_coi_of(pos[body], vel[body], mass[body], pos[parent], vel[parent], mass[parent], gc,
+                       coi_coef);
     }
-    const double2 me = spos[k];
-    const double fx = floor((me.x - P->xmin) * P->inv_h), fy = floor((me.y - P->ymin) * P->inv_h);
-    const long long cx = isfinite(fx) ? (long long)fx : 0, cy = isfinite(fy) ? (long long)fy : 0;
-    const long long later = r0 + cnt;     // ranks of this slab were settled by soc_slab_kernel
-    unsigned seen[9];
-    int nseen = 0;
-    for (int oy = -1; oy <= 1; ++oy)
-        for (int ox = -1; ox <= 1; ++ox) {
-            const unsigned b = cell_bucket(cx + ox, cy + oy, P->mask);
-            bool dup = false;
-            for (int q = 0; q < nseen; ++q) dup |= seen[q] == b;
-            if (dup) continue;
-            seen[nseen++] = b;
-            const unsigned e = starts[b + 1];
-            for (unsigned t = starts[b]; t < e; ++t) {
-                const pg_entry q = ent[t];
-                if (q.rank < later) continue;
-                // (pos[body]-pos[pot])**2 summed < coi[pot]**2, phys_editor.py:337
-                const double dx = q.x - me.x, dy = q.y - me.y;
-                const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                if (d2 < c2) atomicMax(&best[q.rank], (int)k);
-            }
-        }
+    coi[body] = c;
+    scoi2[r] = __dmul_rn(c, c);
 }
 
-__global__ void __launch_bounds__(256)
-soc_large_kernel(const int *__restrict__ slab_large, const int *__restrict__ slab_nlarge,
-                 const double2 *__restrict__ spos, const double *__restrict__ scoi, int64_t first,
-                 int64_t n, int *__restrict__ best)
+__global__ void soc_diff_kernel(int64_t n, const int *__restrict__ a, const int *__restrict__ b,
+                                int *__restrict__ changed)
 {
-    const int nl = *slab_nlarge;
-    if (nl == 0) return;
-    __shared__ double2 lp[256];
-    __shared__ double lc[256];
-    __shared__ int lr[256];
-    const int64_t r = first + (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const bool live = r < n;
-    const double2 me = spos[live ? r : 0];
-    int found = -1;
-    for (int base = 0; base < nl; base += 256) {
-        const int cnt = nl - base < 256 ? nl - base : 256;
-        __syncthreads();
-        if (threadIdx.x < cnt) {
-            const int k = slab_large[base + threadIdx.x];
-            const double c = scoi[k];
-            lr[threadIdx.x] = k;
-            lp[threadIdx.x] = spos[k];
-            lc[threadIdx.x] = __dmul_rn(c, c);
-        }
-        __syncthreads();
-        if (!live) continue;
-        for (int t = 0; t < cnt; ++t) {
-            const double dx = me.x - lp[t].x, dy = me.y - lp[t].y;
-            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            if (d2 < lc[t] && lr[t] > found) found = lr[t];
-        }
-    }
-    if (live && found > best[r]) best[r] = found;
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = r < n && a[r] != b[r];
+    if (__syncthreads_or(d) && threadIdx.x == 0) atomicOr(changed, 1);
 }
 
 }  // namespace
@@ -347,13 +305,11 @@ struct pg_view {
     unsigned *starts;
     pg_entry *ent;
     int *large;
-    int *slab_large, *slab_nlarge;   // A7: large discs of the slab in flight, one counter per slab
     unsigned M;
 };
 
 // counting sort of the discs (coi^2 > 0) of the n sorted ranks into the hashed grid of c->pgrid
-int pg_build(vsb_ctx *c, const double2 *spos, const double *scoi2, int64_t n, int64_t nslabs,
-             pg_view &v)
+int pg_build(vsb_ctx *c, const double2 *spos, const double *scoi2, int64_t n, pg_view &v)
 {
     unsigned M = 4096;
     while ((int64_t)M < 2 * n) M <<= 1;
@@ -361,15 +317,14 @@ int pg_build(vsb_ctx *c, const double2 *spos, const double *scoi2, int64_t n, in
     VSB_CHECK(nchunks <= 4096, VSB_ERR_ARG, "find_parents grid: too many bodies (%lld)", (long long)n);
     const int sblocks = c->sm_count * 4;
     // layout of c->pgrid: params | partial | hist | counts[M] | starts[M+4] | cursor[M] |
-    //                     chunk[4096] | bucket[n] | large[n] | ent[n] | slab_large[1024] | slab_nlarge[]
+    //                     chunk[4096] | bucket[n] | large[n] | ent[n]
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_par = take(sizeof(pg_params)), o_part = take(sizeof(double) * 4 * sblocks),
                  o_hist = take(4 * PG_EXP_BINS), o_cnt = take(4 * (size_t)M),
                  o_st = take(4 * ((size_t)M + 4)), o_cur = take(4 * (size_t)M), o_chk = take(4 * 4096),
                  o_bkt = take(4 * (size_t)n), o_lrg = take(4 * (size_t)n),
-                 o_ent = take(sizeof(pg_entry) * (size_t)n), o_sl = take(4 * 1024),
-                 o_sn = take(4 * (size_t)(nslabs + 1));
+                 o_ent = take(sizeof(pg_entry) * (size_t)n);
     VSB_TRY(vsb_buf_reserve(c->pgrid, off));
     char *base = (char *)c->pgrid.p;
     pg_params *P = (pg_params *)(base + o_par);
@@ -383,7 +338,6 @@ int pg_build(vsb_ctx *c, const double2 *spos, const double *scoi2, int64_t n, in
 
     // hist and counts are adjacent: one memset
     VSB_CUDA(cudaMemsetAsync(hist, 0, (o_cnt - o_hist) + 4 * (size_t)M, c->stream));
-    if (nslabs > 0) VSB_CUDA(cudaMemsetAsync(base + o_sn, 0, 4 * (size_t)(nslabs + 1), c->stream));
     pg_stats1_kernel<<<sblocks, 256, 0, c->stream>>>(spos, scoi2, n, partial, hist);
     pg_stats2_kernel<<<1, 256, 0, c->stream>>>(partial, sblocks, n, M - 1, hist, P);
     pg_count_kernel<<<g, 256, 0, c->stream>>>(spos, scoi2, n, P, bucket, counts, large);
@@ -397,13 +351,9 @@ int pg_build(vsb_ctx *c, const double2 *spos, const double *scoi2, int64_t n, in
     v.starts = starts;
     v.ent = ent;
     v.large = large;
-    v.slab_large = (int *)(base + o_sl);
-    v.slab_nlarge = (int *)(base + o_sn);
     v.M = M;
     return VSB_OK;
 }
-
-pg_view soc_view;   // grid of the simplified_orbit_coi call in flight (one context per process)
 
 }  // namespace
 
@@ -412,7 +362,7 @@ int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *
 {
     const int64_t n = c->n;
     pg_view v;
-    VSB_TRY(pg_build(c, spos, scoi2, n, 0, v));
+    VSB_TRY(pg_build(c, spos, scoi2, n, v));
     pg_query_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(v.P, v.starts, v.ent, v.large,
                                                                          spos, scoi2, n, best);
     c->launches += 1;
@@ -420,34 +370,44 @@ int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *
     return VSB_OK;
 }
 
-// A7: bin all bodies (sorted ranks) once; sorted positions land in c->sorted (npad x 16 bytes)
-int vsb_launch_soc_grid_begin(vsb_ctx *c, const int64_t *d_order, int slab)
+// A7 by fixed-point rounds (see soc_coi_all_kernel).  *converged_out = 0 when max_rounds did not
+// suffice (a pathological chain of nested bodies): the caller then runs the sequential sweep.
+// Uses c->sorted (spos | scoi2 | best_a | best_b) and c->scratch (flag); writes c->coi.
+int vsb_launch_soc_fixed_point(vsb_ctx *c, const int64_t *d_order, int64_t largest, double gc,
+                               double coi_coef, int max_rounds, int *converged_out, int *rounds_out)
 {
     const int64_t n = c->n, npad = c->npad;
-    VSB_TRY(vsb_buf_reserve(c->sorted, (size_t)npad * 24));
-    double2 *spos = (double2 *)c->sorted.p;
-    double *dummy2 = (double *)((char *)c->sorted.p + (size_t)npad * 16);
-    soc_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-        d_order, (const double2 *)c->pos, n, spos, dummy2);
+    *converged_out = 0;
+    VSB_TRY(vsb_buf_reserve(c->sorted, (size_t)npad * (16 + 8 + 4 + 4)));
+    VSB_TRY(vsb_buf_reserve(c->scratch, 64));
+    char *base = (char *)c->sorted.p;
+    double2 *spos = (double2 *)base;
+    double *scoi2 = (double *)(base + (size_t)npad * 16);
+    int *best = (int *)(base + (size_t)npad * 24), *best_new = (int *)(base + (size_t)npad * 28);
+    int *d_changed = (int *)((char *)c->scratch.p + 32);   // bytes 0-7 hold the caller's argmax result
+    const unsigned g = (unsigned)((n + 255) / 256);
+    soc_gather_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(
+        d_order, (const double2 *)c->pos, n, npad, spos, best);
     c->launches += 1;
-    VSB_CHECK(slab <= 1024, VSB_ERR_ARG, "soc grid: slab of %d ranks", slab);
-    return pg_build(c, spos, dummy2, n, (n + slab - 1) / slab, soc_view);
-}
-
-// A7: the slab [r0, r0+cnt) is finished (scoi by rank): tell every later rank inside its new COIs
-int vsb_launch_soc_grid_update(vsb_ctx *c, int64_t r0, int cnt, int slab, const double *scoi, int *best)
-{
-    const int64_t n = c->n;
-    const int64_t rest = n - r0 - cnt;
-    if (rest <= 0) return VSB_OK;
-    const pg_view &v = soc_view;
-    const double2 *spos = (const double2 *)c->sorted.p;
-    int *nlarge = v.slab_nlarge + r0 / slab;
-    soc_scatter_kernel<<<(cnt + 127) / 128, 128, 0, c->stream>>>(v.P, v.starts, v.ent, spos, scoi, r0, cnt,
-                                                                 best, v.slab_large, nlarge);
-    soc_large_kernel<<<(unsigned)((rest + 255) / 256), 256, 0, c->stream>>>(v.slab_large, nlarge, spos,
-                                                                            scoi, r0 + cnt, n, best);
-    c->launches += 2;
-    VSB_CUDA(cudaGetLastError());
+    for (int round = 1; round <= max_rounds; ++round) {
+        soc_coi_all_kernel<<<g, 256, 0, c->stream>>>(n, d_order, largest, c->mass,
+                                                     (const double2 *)c->pos, (const double2 *)c->vel,
+                                                     gc, coi_coef, best, scoi2, c->coi);
+        VSB_TRY(vsb_launch_find_parents_grid(c, spos, scoi2, best_new));
+        VSB_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(int), c->stream));
+        soc_diff_kernel<<<g, 256, 0, c->stream>>>(n, best, best_new, d_changed);
+        c->launches += 2;
+        int h_changed = 0;
+        VSB_CUDA(cudaMemcpyAsync(&h_changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        if (rounds_out) *rounds_out = round;
+        if (!h_changed) {
+            *converged_out = 1;     // COIs of this round belong to parents that did not move
+            return VSB_OK;
+        }
+        int *t = best;
+        best = best_new;
+        best_new = t;
+    }
     return VSB_OK;
 }
