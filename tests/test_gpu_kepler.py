@@ -339,9 +339,16 @@ def test_convert_golden(dev):
         convert.to_newton(g["c60_mass"], orb, gc, cc, device=dev)
 
 
-def test_to_kepler_multi_slab_vs_oracle(dev, oracle):
-    """to_kepler's sequential first loop across several 1024-step slabs, scrambled index order."""
+@pytest.mark.parametrize("mode,rounds,coef", [("scan", "48", 0.7), ("grid", "48", 0.7),
+                                              ("grid", "1", 0.7), ("grid", "48", 0.25)])
+def test_to_kepler_multi_slab_vs_oracle(dev, oracle, monkeypatch, mode, rounds, coef):
+    """to_kepler's sequential first loop, scrambled index order: the blocked sweep over 1024-step
+    slabs ("scan"), the fixed-point rounds over the candidate pass ("grid", default from 4096
+    bodies), their fall-back to the sweep (round limit 1) and a COI exponent that makes the heavy
+    bodies' COIs nest and exceed a grid cell."""
     from volatilespace_b200 import convert
+    monkeypatch.setenv("VSB_PARENTS", mode)
+    monkeypatch.setenv("VSB_SOC_ROUNDS", rounds)
     rng = np.random.default_rng(99)
     n = 5000
     mass = rng.uniform(0.5, 2.0, n)
@@ -356,8 +363,8 @@ def test_to_kepler_multi_slab_vs_oracle(dev, oracle):
     vel[0] = 0
     perm = np.concatenate(([0], 1 + rng.permutation(n - 1)))
     mass, pos, vel = mass[perm], np.ascontiguousarray(pos[perm]), np.ascontiguousarray(vel[perm])
-    got = convert.to_kepler(mass, {"pos": pos, "vel": vel}, 1.0, 0.7, device=dev)
-    want = oracle.to_kepler(mass, pos, vel, 1.0, 0.7)
+    got = convert.to_kepler(mass, {"pos": pos, "vel": vel}, 1.0, coef, device=dev)
+    want = oracle.to_kepler(mass, pos, vel, 1.0, coef)
     assert np.array_equal(got["ref"], want["ref"])
     assert (want["ref"] != 0).sum() > 20
     for key in ("a", "ecc", "pe_arg", "ma", "dir"):

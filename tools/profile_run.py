@@ -1,6 +1,6 @@
 """Small fixed workloads for ncu captures (see profiles/README.md).
 
-    python tools/profile_run.py gravity64k | gravity256k | moderef1m | soc1m | kepler1m | collision256k | parents64k | points160
+    python tools/profile_run.py gravity64k | gravity256k | moderef1m | soc1m | convert1m | kepler1m | collision256k | parents64k | points160
 """
 import os
 import sys
@@ -44,6 +44,15 @@ def main():
         t1 = time.perf_counter()
         dev.simplified_orbit_coi(s["gc"], 0.4, order)
         print("simplified_orbit_coi at 1M: %.1f ms" % ((time.perf_counter() - t1) * 1e3))
+    elif mode == "convert1m":
+        from volatilespace_b200 import convert
+        s = synth.rotating_disk(1 << 20)
+        for rep in range(2):
+            t1 = time.perf_counter()
+            k = convert.to_kepler(s["mass"], {"pos": s["pos"], "vel": s["vel"]}, s["gc"], 0.4, device=dev)
+            t2 = time.perf_counter()
+            print("to_kepler at 1M: %.1f ms (host arrays in and out)" % ((t2 - t1) * 1e3))
+        print("refs != 0:", int((k["ref"] != 0).sum()))
     elif mode == "kepler1m":
         k = synth.kepler_objects(1 << 20)
         dev.kepler_load(KIND_VESSEL, 512, k["a"], k["b"], k["f"], k["ecc"], k["pea"], k["n"],

@@ -282,6 +282,9 @@ int vsb_launch_curve_segments(vsb_ctx *c, const vsb_kepler_state &k, const int64
                               double *range);
 // sort-based candidate pass (vsb_parents_grid.cu): best[] for all sorted ranks
 int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *scoi2, int *best);
+// N1: first loop of to_kepler by fixed-point rounds over the candidate pass
+int vsb_launch_to_kepler_fixed_point(vsb_ctx *c, const int64_t *d_order, double gc, double coi_coef,
+                                     int max_rounds, int64_t *d_ref, int *converged_out);
 // A7 by global fixed-point rounds over the candidate pass (vsb_parents_grid.cu)
 int vsb_launch_soc_fixed_point(vsb_ctx *c, const int64_t *d_order, int64_t largest, double gc,
                                double coi_coef, int max_rounds, int *converged_out, int *rounds_out);

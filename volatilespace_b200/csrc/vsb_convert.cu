@@ -14,6 +14,8 @@
 // streamed through shared memory by TMA bulk copies, "last match in mass order" = max rank),
 // then one CTA resolves the slab's internal dependencies step by step.  Everything else is one
 // thread per body.  Compiled with -fmad=false.
+#include <stdlib.h>
+
 #include "vsb_common.cuh"
 
 namespace {
@@ -309,6 +311,25 @@ int vsb_launch_to_kepler(vsb_ctx *c, const int64_t *d_order, double gc, double c
 {
     const int64_t n = c->n, npad = c->npad;
     if (n <= 0) return VSB_OK;
+    const double2 *pos = (const double2 *)c->pos, *vel = (const double2 *)c->vel;
+    // From 4096 bodies up the first loop runs as fixed-point rounds over the O(N) candidate pass
+    // (vsb_parents_grid.cu); the blocked sweep below stays for small maps and as the fall-back.
+    // VSB_PARENTS=scan|grid overrides, VSB_SOC_ROUNDS limits the rounds (tests).
+    const char *env = getenv("VSB_PARENTS");
+    if (env ? env[0] == 'g' : n >= 4096) {
+        const char *lim = getenv("VSB_SOC_ROUNDS");
+        int converged = 0;
+        VSB_TRY(vsb_launch_to_kepler_fixed_point(c, d_order, gc, coi_coef, lim ? atoi(lim) : 48, d_ref,
+                                                 &converged));
+        if (converged) {
+            tk_elements_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+                n, d_ref, c->mass, pos, vel, gc, d_el, d_el + n, d_el + 2 * n, d_el + 3 * n,
+                d_el + 4 * n);
+            c->launches += 1;
+            VSB_CUDA(cudaGetLastError());
+            return VSB_OK;
+        }
+    }
     VSB_TRY(vsb_buf_reserve(c->sorted, (size_t)npad * (16 + 8 + 4 + 4 + 8)));
     char *base = (char *)c->sorted.p;
     double2 *spos = (double2 *)base;
@@ -316,7 +337,6 @@ int vsb_launch_to_kepler(vsb_ctx *c, const int64_t *d_order, double gc, double c
     double *coi = (double *)(base + (size_t)npad * 24);
     int *rank = (int *)(base + (size_t)npad * 32);
     int *best = (int *)(base + (size_t)npad * 36);
-    const double2 *pos = (const double2 *)c->pos, *vel = (const double2 *)c->vel;
     tk_init_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(d_order, pos, n, npad,
                                                                          spos, w2, rank, best, coi);
     c->launches += 1;

@@ -30,7 +30,8 @@ constexpr double PG_MAX_CELLS = 16777216.0;    // 2^24 cells per axis
 
 struct __align__(32) pg_entry {   // one disc of the grid: a single 32-byte sector per candidate
     double x, y, coi2;
-    long long rank;
+    int rank;
+    int vis;      // to_kepler: the step that writes this COI (0 for find_parents: always visible)
 };
 
 struct pg_params {
@@ -172,7 +173,7 @@ pg_count_kernel(const double2 *__restrict__ spos, const double *__restrict__ sco
 __global__ void __launch_bounds__(256)
 pg_scatter_kernel(const double2 *__restrict__ spos, const double *__restrict__ scoi2, int64_t n,
                   const unsigned *__restrict__ bucket, unsigned *__restrict__ cursor,
-                  pg_entry *__restrict__ ent)
+                  const int64_t *__restrict__ vis, pg_entry *__restrict__ ent)
 {
     int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (k >= n) return;
@@ -184,7 +185,8 @@ pg_scatter_kernel(const double2 *__restrict__ spos, const double *__restrict__ s
     e.x = p.x;
     e.y = p.y;
     e.coi2 = scoi2[k];
-    e.rank = k;
+    e.rank = (int)k;
+    e.vis = vis ? (int)vis[k] : 0;
     ent[slot] = e;
 }
 
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(128)
 pg_query_kernel(const pg_params *P, const unsigned *__restrict__ starts,
                 const pg_entry *__restrict__ ent, const int *__restrict__ large,
                 const double2 *__restrict__ spos, const double *__restrict__ scoi2, int64_t n,
+                const int64_t *__restrict__ order, const int64_t *__restrict__ vis,
                 int *__restrict__ best)
 {
     __shared__ double2 lp[128];
@@ -201,6 +204,9 @@ pg_query_kernel(const pg_params *P, const unsigned *__restrict__ starts,
     const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const bool live = r < n;
     const double2 me = spos[live ? r : 0];
+    // to_kepler (vis != NULL): the body at rank r is step order[r] of the reference's loop and only
+    // sees COIs written by earlier steps; find_parents: everything is visible
+    const int mine = (vis && live) ? (int)order[r] : 0x7fffffff;
     int found = -1;
     if (live) {
         const double fx = floor((me.x - P->xmin) * P->inv_h), fy = floor((me.y - P->ymin) * P->inv_h);
@@ -217,8 +223,8 @@ pg_query_kernel(const pg_params *P, const unsigned *__restrict__ starts,
                 const unsigned e = starts[b + 1];
                 for (unsigned s = starts[b]; s < e; ++s) {
                     const pg_entry q = ent[s];
-                    const int k = (int)q.rank;
-                    if (k >= r || k <= found) continue;
+                    const int k = q.rank;
+                    if (k >= r || k <= found || q.vis >= mine) continue;
                     const double dx = me.x - q.x, dy = me.y - q.y;
                     const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                     if (d2 < q.coi2) found = k;
@@ -239,7 +245,7 @@ pg_query_kernel(const pg_params *P, const unsigned *__restrict__ starts,
         if (!live) continue;
         for (int t = 0; t < cnt; ++t) {
             const int k = lr[t];
-            if (k >= r || k <= found) continue;
+            if (k >= r || k <= found || (vis && (int)vis[k] >= mine)) continue;
             const double dx = me.x - lp[t].x, dy = me.y - lp[t].y;
             const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
             if (d2 < lc[t]) found = k;
@@ -296,6 +302,50 @@ __global__ void soc_diff_kernel(int64_t n, const int *__restrict__ a, const int 
     if (__syncthreads_or(d) && threadIdx.x == 0) atomicOr(changed, 1);
 }
 
+// ------------------------------------------------------------------ N1 to_kepler, first loop
+// convert.to_kepler (convert.py:205-225) is the same recurrence with its index quirks: step s
+// (INDEX order) looks for the last candidate among the first rank[s] bodies of the mass order whose
+// COI -- as far as it has been written -- contains pos[s], and then writes the COI of index
+// R = rank[s] (the rank used as an index, :219-225).  coi[x] is therefore written by step order[x],
+// and the candidate at sorted position l (index order[l]) is visible to step s iff
+// order[order[l]] < s.  Same fixed point argument as above, by induction over s.
+__global__ void tkf_init_kernel(const int64_t *__restrict__ order, const double2 *__restrict__ pos,
+                                int64_t n, int64_t npad, double2 *__restrict__ spos,
+                                int *__restrict__ rank, int *__restrict__ best,
+                                int64_t *__restrict__ vis)
+{
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= npad) return;
+    best[l] = -1;
+    if (l < n) {
+        const int64_t p = order[l];
+        spos[l] = pos[p];
+        rank[p] = (int)l;
+        vis[l] = order[p];
+    } else {
+        spos[l] = make_double2(VSB_FAR, VSB_FAR);
+        vis[l] = 0x7fffffff;
+    }
+}
+
+// step s with its current parent: ref_l[s] and the COI it writes (squared, by sorted position)
+__global__ void tkf_coi_kernel(int64_t n, const int64_t *__restrict__ order,
+                               const int *__restrict__ rank, const double *__restrict__ mass,
+                               const double2 *__restrict__ pos, const double2 *__restrict__ vel,
+                               double gc, double coi_coef, const int *__restrict__ best,
+                               double *__restrict__ c2, int64_t *__restrict__ ref_l)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int R = rank[s];
+    const int b = best[R];
+    const int64_t ref = b < 0 ? 0 : order[b];
+    ref_l[s] = ref;
+    // quirk: the mass rank R is used as an index from here on (:219-225)
+    const double c = soc_coi_of(pos[R], vel[R], mass[R], pos[ref], vel[ref], mass[ref], gc, coi_coef);
+    c2[rank[R]] = __dmul_rn(c, c);
+}
+
 }  // namespace
 
 namespace {
@@ -309,7 +359,8 @@ struct pg_view {
 };
 
 // counting sort of the discs (coi^2 > 0) of the n sorted ranks into the hashed grid of c->pgrid
-int pg_build(vsb_ctx *c, const double2 *spos, const double *scoi2, int64_t n, pg_view &v)
+int pg_build(vsb_ctx *c, const double2 *spos, const double *scoi2, int64_t n, const int64_t *vis,
+             pg_view &v)
 {
     unsigned M = 4096;
     while ((int64_t)M < 2 * n) M <<= 1;
@@ -344,7 +395,7 @@ int pg_build(vsb_ctx *c, const double2 *spos, const double *scoi2, int64_t n, pg
     bp_scan_reduce_kernel<<<nchunks, 256, 0, c->stream>>>(counts, chunk);
     bp_scan_chunks_kernel<<<1, 1024, 0, c->stream>>>(chunk, nchunks);
     bp_scan_apply_kernel<<<nchunks, 256, 0, c->stream>>>(counts, chunk, starts, cursor, M);
-    pg_scatter_kernel<<<g, 256, 0, c->stream>>>(spos, scoi2, n, bucket, cursor, ent);
+    pg_scatter_kernel<<<g, 256, 0, c->stream>>>(spos, scoi2, n, bucket, cursor, vis, ent);
     c->launches += 7;
     VSB_CUDA(cudaGetLastError());
     v.P = P;
@@ -362,9 +413,10 @@ int vsb_launch_find_parents_grid(vsb_ctx *c, const double2 *spos, const double *
 {
     const int64_t n = c->n;
     pg_view v;
-    VSB_TRY(pg_build(c, spos, scoi2, n, v));
+    VSB_TRY(pg_build(c, spos, scoi2, n, nullptr, v));
     pg_query_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(v.P, v.starts, v.ent, v.large,
-                                                                         spos, scoi2, n, best);
+                                                                         spos, scoi2, n, nullptr,
+                                                                         nullptr, best);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;
@@ -403,6 +455,51 @@ int vsb_launch_soc_fixed_point(vsb_ctx *c, const int64_t *d_order, int64_t large
         if (rounds_out) *rounds_out = round;
         if (!h_changed) {
             *converged_out = 1;     // COIs of this round belong to parents that did not move
+            return VSB_OK;
+        }
+        int *t = best;
+        best = best_new;
+        best_new = t;
+    }
+    return VSB_OK;
+}
+
+// N1: the first loop of to_kepler by fixed-point rounds: d_ref[s] for every body.  *converged_out
+// = 0 when max_rounds did not suffice (the caller runs the blocked sweep).  Uses c->sorted.
+int vsb_launch_to_kepler_fixed_point(vsb_ctx *c, const int64_t *d_order, double gc, double coi_coef,
+                                     int max_rounds, int64_t *d_ref, int *converged_out)
+{
+    const int64_t n = c->n, npad = c->npad;
+    *converged_out = 0;
+    VSB_TRY(vsb_buf_reserve(c->sorted, (size_t)npad * (16 + 8 + 8 + 4 + 4 + 4)));
+    VSB_TRY(vsb_buf_reserve(c->scratch, 64));
+    char *base = (char *)c->sorted.p;
+    double2 *spos = (double2 *)base;
+    double *c2 = (double *)(base + (size_t)npad * 16);
+    int64_t *vis = (int64_t *)(base + (size_t)npad * 24);
+    int *rank = (int *)(base + (size_t)npad * 32);
+    int *best = (int *)(base + (size_t)npad * 36), *best_new = (int *)(base + (size_t)npad * 40);
+    int *d_changed = (int *)((char *)c->scratch.p + 32);
+    const double2 *pos = (const double2 *)c->pos, *vel = (const double2 *)c->vel;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    tkf_init_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(d_order, pos, n, npad, spos,
+                                                                          rank, best, vis);
+    c->launches += 1;
+    for (int round = 1; round <= max_rounds; ++round) {
+        tkf_coi_kernel<<<g, 256, 0, c->stream>>>(n, d_order, rank, c->mass, pos, vel, gc, coi_coef, best,
+                                                 c2, d_ref);
+        pg_view v;
+        VSB_TRY(pg_build(c, spos, c2, n, vis, v));
+        pg_query_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
+            v.P, v.starts, v.ent, v.large, spos, c2, n, d_order, vis, best_new);
+        VSB_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(int), c->stream));
+        soc_diff_kernel<<<g, 256, 0, c->stream>>>(n, best, best_new, d_changed);
+        c->launches += 3;
+        int h_changed = 0;
+        VSB_CUDA(cudaMemcpyAsync(&h_changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        if (!h_changed) {
+            *converged_out = 1;     // d_ref of this round belongs to parents that did not move
             return VSB_OK;
         }
         int *t = best;
