@@ -237,8 +237,10 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
     // the macro-block S sets the task grain (small S: better balance at small N) against the
     // slab memory N^2/(2S) * 16 B (S = 1024: 8.6 GB at 1 M bodies, 34 GB at 2 M).
     // VSB_SYM_SHAPE=w,t,h,c overrides (tools/sym_ab.py).
+    // (measured: S = 256 wins at 32 k bodies, 512 at 64 k, 1024 from 128 k: profiles/r1_sym_shapes_ab.txt)
     int warps = 4, tpl = 8, su = 2, mb = 3;
-    if (npad <= 131072) warps = 2, su = 1, mb = 6;
+    if (npad <= 98304) warps = 2, su = 1, mb = 6;
+    if (npad <= 32768) warps = 1, su = 1, mb = 12;
     if (npad > 2097152) warps = 8, su = 1, mb = 1;
     if (const char *env = getenv("VSB_SYM_SHAPE")) {
         mb = 0;
@@ -356,6 +358,7 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
         launched = true;                                                                        \
     }
         bool launched = false;
+        VSB_SYM_CASE(1, 8, 1, 12)   // S =  256, 12 warps/SM
         VSB_SYM_CASE(2, 8, 1, 6)    // S =  512, 12 warps/SM
         VSB_SYM_CASE(4, 8, 1, 3)    // S = 1024, 12 warps/SM, CTA barrier
         VSB_SYM_CASE(4, 8, 2, 3)    // S = 1024, 12 warps/SM, pairwise barriers
