@@ -430,6 +430,20 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
         for _ in range(10):
             resident()
         res["ms_per_tick_1m_resident"] = (time.perf_counter() - t0) / 10 * 1e3
+        # curve_segments (light / dark parts of the visible orbit curves) on the same resident state:
+        # a fresh 1 M-vessel state with P = 64 curves, 16 384 visible orbits
+        P = 64
+        dev.kepler_load(KIND_VESSEL, P, cols[0], cols[1], cols[2], cols[3], cols[4], cols[5],
+                        cols[6], cols[7], cols[8], np.zeros(n1, dtype=np.int64))
+        dev.vessel_events_load(cols[11], cols[12], cols[13], bi, ba, cl, ce, None, cols[9])
+        dev.kepler_tick(KIND_VESSEL, 0.0, np.zeros((1, 2)))
+        vis = np.arange(0, n1, n1 // 16384, dtype=np.int64)[:16384]
+        seg = dev.vessel_curve_segments(vis, P)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            seg = dev.vessel_curve_segments(vis, P)
+        res["curve_segments_ms_16k_visible_p64"] = (time.perf_counter() - t0) / 10 * 1e3
+        res["curve_segments_types"] = np.bincount(seg[3], minlength=4).tolist()
         dev.kepler_free(KIND_VESSEL)
         res["note"] = ("three host-array calls per tick, uploads of the per-vessel arrays included "
                        "(320 MB per tick at 1 M vessels: PCIe-bound); the reference's whole game tick "
