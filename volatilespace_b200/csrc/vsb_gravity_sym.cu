@@ -192,19 +192,38 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
     const int r = (int)(i - (int64_t)X * S);
     double sx = 0.0, sy = 0.0;
     // own_p / own_q (multi-GPU): which slabs this rank's tasks wrote -- the others are skipped
-    // instead of being read as zeros (1/world of the slab traffic per rank)
-    for (int sl = qslot_first[X]; sl < qslot_first[X + 1]; ++sl) {
-        if (own_q && !own_q[sl]) continue;
-        double2 v = part_q[(int64_t)sl * S + r];
-        sx += v.x;
-        sy += v.y;
+    // instead of being read as zeros (1/world of the slab traffic per rank).  Flags and slabs
+    // are fetched eight at a time so that the loads of a batch are in flight together (a flag ->
+    // branch -> load chain per slab made this kernel latency-bound); the additions keep their
+    // block order.
+    for (int sl0 = qslot_first[X]; sl0 < qslot_first[X + 1]; sl0 += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int sl = sl0 + k;
+            const bool on = sl < qslot_first[X + 1] && (!own_q || own_q[sl]);
+            v[k] = on ? part_q[(int64_t)sl * S + r] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sx += v[k].x;
+            sy += v[k].y;
+        }
     }
-    for (int Q = X; Q < M; ++Q) {
-        const int64_t slab = (int64_t)Q * (Q + 1) / 2 + X;
-        if (own_p && !own_p[slab]) continue;
-        double2 v = part_p[slab * S + r];
-        sx += v.x;
-        sy += v.y;
+    for (int Q0 = X; Q0 < M; Q0 += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int Q = Q0 + k;
+            const int64_t slab = (int64_t)Q * (Q + 1) / 2 + X;
+            const bool on = Q < M && (!own_p || own_p[slab]);
+            v[k] = on ? part_p[slab * S + r] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sx += v[k].x;
+            sy += v[k].y;
+        }
     }
     sx *= gc;
     sy *= gc;
