@@ -260,10 +260,10 @@ __global__ void bp_finalize_kernel(const bp_params *P, const unsigned long long 
 int vsb_launch_broadphase(vsb_ctx *c)
 {
     const int64_t n = c->n;
+    // 2 buckets per body, at most 2^22 of them (the three-pass scan handles 4096 chunks of 1024)
     unsigned M = 4096;
-    while ((int64_t)M < 2 * n) M <<= 1;
+    while ((int64_t)M < 2 * n && M < (1u << 22)) M <<= 1;
     const int nchunks = (int)(M / 1024);
-    VSB_CHECK(nchunks <= 4096, VSB_ERR_ARG, "broadphase: too many bodies (%lld)", (long long)n);
     const int sblocks = c->sm_count * 4;
     // layout of c->sorted: params | partial | counts[M] | starts[M+4] | cursor[M] | chunk[4096] |
     //                      bucket[n] | large[4096] | spos[n] | srad[n] | sidx[n]

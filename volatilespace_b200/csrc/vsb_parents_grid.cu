@@ -362,10 +362,11 @@ struct pg_view {
 int pg_build(vsb_ctx *c, const double2 *spos, const double *scoi2, int64_t n, const int64_t *vis,
              pg_view &v)
 {
+    // 2 buckets per body, at most 2^22 of them (the three-pass scan handles 4096 chunks of 1024):
+    // beyond 2 M bodies the buckets just hold more entries
     unsigned M = 4096;
-    while ((int64_t)M < 2 * n) M <<= 1;
+    while ((int64_t)M < 2 * n && M < (1u << 22)) M <<= 1;
     const int nchunks = (int)(M / 1024);
-    VSB_CHECK(nchunks <= 4096, VSB_ERR_ARG, "find_parents grid: too many bodies (%lld)", (long long)n);
     const int sblocks = c->sm_count * 4;
     // layout of c->pgrid: params | partial | hist | counts[M] | starts[M+4] | cursor[M] |
     //                     chunk[4096] | bucket[n] | large[n] | ent[n]
