@@ -265,6 +265,28 @@ def test_find_parents_grid_equals_scan_256k(dev, monkeypatch):
     assert (res["grid"] != 0).sum() > 1000
 
 
+def test_find_parents_grid_beyond_bucket_cap(dev, monkeypatch):
+    """2.5 M bodies: more than the 2^21 bodies the hash table has two buckets each for -- the
+    buckets just fill up; parents still equal the exhaustive scan's."""
+    rng = np.random.default_rng(8)
+    n = 2500000
+    mass = rng.uniform(0.5, 2.0, n)
+    mass[0] = 1.0e9
+    pos = rng.uniform(-1, 1, (n, 2)) * 5.0e6
+    pos[0] = 0.0
+    coi = rng.uniform(0, 4000.0, n) * (rng.uniform(0, 1, n) < 0.5)
+    coi[0] = 0.0
+    coi[rng.choice(np.arange(1, n), 200, replace=False)] = rng.uniform(5e4, 5e5, 200)
+    order = np.argsort(mass, kind="stable")[-1::-1]
+    res = {}
+    for mode in ("grid", "scan"):
+        monkeypatch.setenv("VSB_PARENTS", mode)
+        res[mode] = dev.host_find_parents(order, pos, coi)
+    assert np.array_equal(res["scan"], res["grid"])
+    assert (res["grid"] != 0).sum() > 100000
+    dev.bodies_resize(16)       # give the 2.5 M-body buffers back
+
+
 # ------------------------------------------------------------------ B1 collisions
 @pytest.fixture(params=["brute", "grid"])
 def collision_mode(request, monkeypatch):
