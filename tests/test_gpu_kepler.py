@@ -735,6 +735,27 @@ def test_vessel_event_argument_errors(dev):
     assert dev.host_check_warp(z + 0.5, z + 1, z, z, z + 0.01, nan2, nan2, nan2, nan6, 1.0, hold) \
         == (None, None, 0)
     assert not hold.any()
+    # curve_segments: needs the resident event state and generated curves, indices in range
+    from volatilespace_b200._lib import KIND_VESSEL
+    dev.kepler_free(KIND_VESSEL)
+    with pytest.raises(VsbError):          # nothing loaded
+        dev.vessel_curve_segments([0], 8)
+    one = np.ones(4)
+    dev.kepler_load(KIND_VESSEL, 8, one * 100, one * 90, one * 40, one * 0.4, one, one * 0.01, one,
+                    one, one, np.zeros(4, dtype=np.int64), np.linspace(-np.pi, np.pi, 8))
+    with pytest.raises(VsbError):          # no event state yet
+        dev.vessel_curve_segments([0], 8)
+    dev.vessel_events_load(one, one, one)
+    with pytest.raises(VsbError):          # no curves / parent positions yet
+        dev.vessel_curve_segments([0], 8)
+    dev.kepler_tick(KIND_VESSEL, 1.0, np.zeros((1, 2)))
+    with pytest.raises(VsbError):          # vessel index out of range
+        dev.vessel_curve_segments([4], 8)
+    light, dark, first, itype, itime, srange = dev.vessel_curve_segments([3, 1], 8)
+    assert itype.tolist() == [0, 0] and np.all(np.isnan(dark)) and not np.isnan(light).any()
+    assert np.array_equal(light[0], dev.kepler_curves_get(KIND_VESSEL, 3, 1, 8)[0])
+    assert light.shape == (2, 8, 2) and dev.vessel_curve_segments([], 8)[0].shape == (0, 8, 2)
+    dev.kepler_free(KIND_VESSEL)
 
 
 def test_resident_vessel_events(dev):
