@@ -184,7 +184,7 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
                            const unsigned char *__restrict__ own_p,
                            const unsigned char *__restrict__ own_q, int S, int M, int64_t n,
                            double gc, double2 *__restrict__ acc, double2 *__restrict__ vel,
-                           double2 *__restrict__ pos, int integrate, int add_into)
+                           double2 *__restrict__ pos, int integrate)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -227,7 +227,6 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
     }
     sx *= gc;
     sy *= gc;
-    (void)add_into;
     acc[i] = make_double2(sx, sy);
     if (integrate) {
         double2 v = vel[i];
@@ -392,7 +391,7 @@ int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int inte
     const unsigned char *own_q = world > 1 ? own_p + pairs : nullptr;
     allpairs_sym_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
         part_p, part_q, d_qf, own_p, own_q, S, M, n, gc, (double2 *)c->acc, (double2 *)c->vel,
-        (double2 *)c->pos, (world == 1 && integrate) ? 1 : 0, 0);
+        (double2 *)c->pos, (world == 1 && integrate) ? 1 : 0);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;
