@@ -162,6 +162,28 @@ def test_allpairs_sym_matches_rows_and_is_deterministic(dev, monkeypatch):
         assert row_rel_err(sym, rows) < 1e-13, n
 
 
+def test_allpairs_sym_rescheduled_sass_is_bit_identical(dev, monkeypatch):
+    """The library holds the symmetric kernels twice: with the pair loop re-scheduled by
+    volatilespace_b200/sass_resched.py (default) and as ptxas emitted them (VSB_SYM_SCHED=ptxas).
+    The post-pass only moves instructions and sets operand-reuse flags, so every compiled shape
+    must give the same bits, on sizes with one and many macro-blocks and ragged tails."""
+    from volatilespace_b200._lib import F_ACC
+    monkeypatch.setenv("VSB_GRAVITY", "sym")
+    shapes = "16,4,1,1 8,4,1,2 8,8,1,1 4,8,1,3 4,8,2,3 2,8,1,6 1,8,1,12".split()
+    for n in (3000, 8192, 20000, 65536):
+        mass, pos, vel = small_cloud(n, 77 + n, extent=3.0e4)
+        dev.upload_bodies(mass, pos, vel)
+        for shape in shapes:
+            monkeypatch.setenv("VSB_SYM_SHAPE", shape)
+            monkeypatch.setenv("VSB_SYM_SCHED", "ptxas")
+            dev.allpairs_accel(1.0)
+            want = dev.get(F_ACC).copy()
+            monkeypatch.delenv("VSB_SYM_SCHED")
+            dev.allpairs_accel(1.0)
+            assert np.array_equal(dev.get(F_ACC), want), (n, shape)
+            assert np.all(np.isfinite(want)) and np.any(want != 0.0)
+
+
 def test_allpairs_sym_multi_rank_partials_sum_to_full(dev, monkeypatch):
     """Multi-GPU form of the symmetric kernel, ranks emulated by separate contexts on one
     GPU: the ranks' partial accelerations add up to the single-rank result."""

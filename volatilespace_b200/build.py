@@ -24,6 +24,8 @@ SOURCES = {
     "vsb_api.cu": [],
     "vsb_gravity.cu": [],
     "vsb_gravity_sym.cu": [],
+    # second object of the same source: ptxas's own schedule (reference of the SASS post-pass)
+    "vsb_gravity_sym.cu@ptxas": ["-DVSB_SYM_PTXAS_SCHEDULE"],
     "vsb_pairs.cu": ["-fmad=false"],
     "vsb_broadphase.cu": ["-fmad=false"],
     "vsb_parents_grid.cu": ["-fmad=false"],
@@ -36,6 +38,10 @@ SOURCES = {
     "vsb_events.cu": ["-fmad=false"],
     "vsb_segments.cu": ["-fmad=false"],
 }
+
+
+# objects whose pair loop is re-scheduled after ptxas (kernel name pattern)
+RESCHED = {"vsb_gravity_sym.cu": "allpairs_sym_kernel"}
 
 
 def _nvcc():
@@ -62,8 +68,8 @@ def build(force=False, verbose=False):
     env.pop("CC", None)    # the image exports a gcc wrapper nvcc should not pick up
     env.pop("CXX", None)
     for src, extra in SOURCES.items():
-        s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        s = os.path.join(CSRC, src.split("@")[0])
+        o = os.path.join(OBJ, src.replace(".cu", "").replace("@", "_") + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
             cmd = [_nvcc()] + ARCH + COMMON + extra + ["-c", s, "-o", o]
@@ -82,6 +88,19 @@ def build(force=False, verbose=False):
             sys.stderr.write("nvcc failed on %s\n" % src)
     if failed:
         raise RuntimeError("libvsb200 build failed")
+    # SASS post-pass on freshly compiled objects (sass_resched.py: same instructions, same
+    # registers, same results bit for bit -- the accumulates of the pair loop regrouped so that
+    # they ride the operand-reuse cache).  VSB_NO_RESCHED=1 keeps ptxas's own schedule.
+    for src, _ in procs:
+        if src in RESCHED and not os.environ.get("VSB_NO_RESCHED"):
+            from volatilespace_b200 import sass_resched
+            o = os.path.join(OBJ, src.replace(".cu", "").replace("@", "_") + ".o")
+            try:
+                for line in sass_resched.patch_object(o, RESCHED[src]):
+                    if verbose:
+                        print(line)
+            except Exception as e:  # noqa: BLE001 -- ptxas's schedule stays: slower, same results
+                sys.stderr.write("sass_resched skipped for %s: %s\n" % (src, e))
     if force or procs or _stale(LIB, objs):
         cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
         subprocess.check_call(cmd, env=env)

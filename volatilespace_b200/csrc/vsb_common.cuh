@@ -272,6 +272,8 @@ int vsb_launch_dfma_peak(vsb_ctx *c, int iters, int blocks, float *ms_out);
 int vsb_allpairs_chunks(int64_t n, int64_t *chunk_out);
 // symmetric kernel (vsb_gravity_sym.cu)
 int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int integrate);
+// the same kernels with ptxas's own instruction schedule (VSB_SYM_SCHED=ptxas; see vsb_gravity_sym.cu)
+int vsb_launch_allpairs_sym_ptxas(vsb_ctx *c, double gc, int rank, int world, int integrate);
 // pair predicates (vsb_pairs.cu)
 int vsb_launch_find_parents(vsb_ctx *c, const int64_t *d_order);
 int vsb_launch_find_parents_part(vsb_ctx *c, const int64_t *d_order, int part, int parts);

@@ -21,6 +21,7 @@
 // invariance matters.)
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "vsb_common.cuh"
 
@@ -246,8 +247,23 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
 // descending cost order).  world == 1: acc is the full result (integrate allowed).
 // world > 1: acc holds this rank's partial sum for ALL bodies (zero where it has no task
 // touching the block); the caller all-reduces VSB_F_ACC and then integrates.
-int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int integrate)
+//
+// This file is compiled twice (build.py): as it is, and with -DVSB_SYM_PTXAS_SCHEDULE.  The first
+// object goes through sass_resched.py (the accumulates of the pair loop regrouped so that they
+// ride the operand-reuse cache: same instructions, same registers, same bits, ~1.5 % faster);
+// the second keeps ptxas's schedule and is the reference VSB_SYM_SCHED=ptxas selects -- the GPU
+// tests compare the two bit for bit.
+#ifdef VSB_SYM_PTXAS_SCHEDULE
+#define VSB_SYM_LAUNCHER vsb_launch_allpairs_sym_ptxas
+#else
+#define VSB_SYM_LAUNCHER vsb_launch_allpairs_sym
+#endif
+int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
 {
+#ifndef VSB_SYM_PTXAS_SCHEDULE
+    if (const char *sched = getenv("VSB_SYM_SCHED"))
+        if (strcmp(sched, "ptxas") == 0) return vsb_launch_allpairs_sym_ptxas(c, gc, rank, world, integrate);
+#endif
     const int64_t n = c->n, npad = c->npad;
     if (n <= 0) return VSB_OK;
     // Kernel shape (warps, targets per lane, hand-over, CTAs per SM).  8 targets per lane halve
