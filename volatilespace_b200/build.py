@@ -96,7 +96,7 @@ def build(force=False, verbose=False):
             from volatilespace_b200 import sass_resched
             o = os.path.join(OBJ, src.replace(".cu", "").replace("@", "_") + ".o")
             try:
-                for line in sass_resched.patch_object(o, RESCHED[src]):
+                for line in sass_resched.patch_object(o, RESCHED[src], no_yield=True):
                     if verbose:
                         print(line)
             except Exception as e:  # noqa: BLE001 -- ptxas's schedule stays: slower, same results
