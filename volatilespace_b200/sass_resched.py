@@ -88,8 +88,17 @@ class Ins:
                 self.src |= span(o, 2 if ".WIDE" in self.op else 1)
 
 
+def _cuobjdump():
+    import os
+    import shutil
+    for cand in (os.environ.get("CUOBJDUMP"), shutil.which("cuobjdump"), "/usr/local/cuda/bin/cuobjdump"):
+        if cand and os.path.exists(cand):
+            return cand
+    return "cuobjdump"
+
+
 def disassemble(path):
-    txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    txt = subprocess.run([_cuobjdump(), "-sass", path], capture_output=True, text=True, check=True).stdout
     funcs, cur = {}, None
     lines = txt.split("\n")
     for i, ln in enumerate(lines):
