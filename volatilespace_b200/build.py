@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, "vsb_common.cuh"), os.path.join(CSRC, "vsb_orbit_math.cuh"),
                os.path.join(CSRC, "vsb_grid.cuh"), INCLUDE,
-               os.path.abspath(__file__)]
+               os.path.abspath(__file__), os.path.join(HERE, "sass_resched.py")]
     objs, procs = [], []
     env = dict(os.environ)
     env.pop("CC", None)    # the image exports a gcc wrapper nvcc should not pick up
