@@ -5,8 +5,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from volatilespace_b200._lib import F_ACC
-from volatilespace_b200.device import Device
+from volatilespace_b200 import synth  # noqa: E402
+from volatilespace_b200._lib import F_ACC  # noqa: E402
+from volatilespace_b200.device import Device  # noqa: E402
 dev = Device(0)
 os.environ["VSB_GRAVITY"] = "sym"
 for n in (1048576, 2200000):
