@@ -93,9 +93,8 @@ struct vsb_ctx {
     // scratch
     vsb_buf part;        // all-pairs partial sums [C][rows][2] (or the symmetric kernel's slabs)
     vsb_buf sym_tab;     // symmetric kernel: task table + Q-slab index
-    int64_t sym_tasks_n = -1, sym_qf_off = 0, sym_own_off = 0;
+    int64_t sym_tasks_n = -1, sym_qf_off = 0, sym_own_off = 0, sym_ownlist_off = 0;
     int sym_world = 0, sym_rank = 0, sym_ntasks = 0, sym_nslots = 0, sym_S = 0;
-    void *sym_zeroed = nullptr;
     int soc_rounds = 0;     // fixed-point rounds of the last simplified_orbit_coi (diagnostics)
     int gravity_mode = -1;  // -1: auto, 0: row kernel (vsb_gravity.cu), 1: symmetric (vsb_gravity_sym.cu)
     vsb_buf order;       // int64 order (descending mass) + rank

@@ -179,11 +179,14 @@ allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ 
 
 // acc[i] = gc * ( sum of Q-side slabs of block X (tasks in P order) + sum over Q >= X of the
 // P-side slab of (X, Q) ), fixed order; optional integrator v += a ; P += v.
+// One GPU: the slab addresses are arithmetic.  Several GPUs: a rank sums only the slabs its own
+// tasks wrote -- their unified indices (P-side slab s -> s, Q-side slab sl -> pairs + sl; part_q
+// follows part_p in memory) are listed per block in `own_list` (same order) -- so a rank's
+// reduction costs 1/world of the loads AND of the loop trips.
 __global__ void __launch_bounds__(256)
 allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__restrict__ part_q,
-                           const int *__restrict__ qslot_first,
-                           const unsigned char *__restrict__ own_p,
-                           const unsigned char *__restrict__ own_q, int S, int M, int64_t n,
+                           const int *__restrict__ qslot_first, const int *__restrict__ own_first,
+                           const int *__restrict__ own_list, int S, int M, int64_t n,
                            double gc, double2 *__restrict__ acc, double2 *__restrict__ vel,
                            double2 *__restrict__ pos, int integrate)
 {
@@ -192,38 +195,48 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
     const int X = (int)(i / S);
     const int r = (int)(i - (int64_t)X * S);
     double sx = 0.0, sy = 0.0;
-    // own_p / own_q (multi-GPU): which slabs this rank's tasks wrote -- the others are skipped
-    // instead of being read as zeros (1/world of the slab traffic per rank).  Flags and slabs
-    // are fetched eight at a time so that the loads of a batch are in flight together (a flag ->
-    // branch -> load chain per slab made this kernel latency-bound); the additions keep their
-    // block order.
-    for (int sl0 = qslot_first[X]; sl0 < qslot_first[X + 1]; sl0 += 8) {
-        double2 v[8];
+    // slabs are fetched eight at a time so that the loads of a batch are in flight together;
+    // the additions keep their order
+    if (own_first) {
+        const int e1 = own_first[X + 1];
+        for (int e0 = own_first[X]; e0 < e1; e0 += 8) {
+            double2 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int sl = sl0 + k;
-            const bool on = sl < qslot_first[X + 1] && (!own_q || own_q[sl]);
-            v[k] = on ? part_q[(int64_t)sl * S + r] : make_double2(0.0, 0.0);
+            for (int k = 0; k < 8; ++k)
+                v[k] = e0 + k < e1 ? part_p[(int64_t)own_list[e0 + k] * S + r] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sx += v[k].x;
+                sy += v[k].y;
+            }
         }
+    } else {
+        for (int sl0 = qslot_first[X]; sl0 < qslot_first[X + 1]; sl0 += 8) {
+            double2 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            sx += v[k].x;
-            sy += v[k].y;
+            for (int k = 0; k < 8; ++k) {
+                const int sl = sl0 + k;
+                v[k] = sl < qslot_first[X + 1] ? part_q[(int64_t)sl * S + r] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                sx += v[k].x;
+                sy += v[k].y;
+            }
         }
-    }
-    for (int Q0 = X; Q0 < M; Q0 += 8) {
-        double2 v[8];
+        for (int Q0 = X; Q0 < M; Q0 += 8) {
+            double2 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int Q = Q0 + k;
-            const int64_t slab = (int64_t)Q * (Q + 1) / 2 + X;
-            const bool on = Q < M && (!own_p || own_p[slab]);
-            v[k] = on ? part_p[slab * S + r] : make_double2(0.0, 0.0);
-        }
+            for (int k = 0; k < 8; ++k) {
+                const int Q = Q0 + k;
+                const int64_t slab = (int64_t)Q * (Q + 1) / 2 + X;
+                v[k] = Q < M ? part_p[slab * S + r] : make_double2(0.0, 0.0);
+            }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            sx += v[k].x;
-            sy += v[k].y;
+            for (int k = 0; k < 8; ++k) {
+                sx += v[k].x;
+                sy += v[k].y;
+            }
         }
     }
     sx *= gc;
@@ -323,38 +336,66 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
                     if (dealt % world == rank) mine[nm++] = all[i].t;
                     ++dealt;
                 }
-        // ownership flags of the P-side slabs (one per block pair) and Q-side slabs (one per task)
+        // several GPUs: per block X the unified indices of the slabs THIS rank's tasks write, in the
+        // order the one-GPU reduction adds them (Q-side slabs in slot order, then P-side by Q)
         unsigned char *own = (unsigned char *)calloc((size_t)(pairs + slot + 1), 1);
-        if (!own) {
+        int *own_first = (int *)malloc(sizeof(int) * (size_t)(M + 1));
+        int *own_list = nullptr;
+        int n_own = 0;
+        if (own)
+            for (int i = 0; i < nm; ++i) {
+                own[pairs + mine[i].qslot] = 1;
+                n_own += 1 + (mine[i].p1 - mine[i].p0);
+                for (int P = mine[i].p0; P < mine[i].p1; ++P)
+                    own[(int64_t)mine[i].q * (mine[i].q + 1) / 2 + P] = 1;
+            }
+        if (own) own_list = (int *)malloc(sizeof(int) * (size_t)(n_own + 1));
+        if (!own || !own_first || !own_list) {
+            free(own);
+            free(own_first);
+            free(own_list);
             free(all);
             free(qfirst);
             free(mine);
             VSB_CHECK(false, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
         }
-        for (int i = 0; i < nm; ++i) {
-            own[pairs + mine[i].qslot] = 1;
-            for (int P = mine[i].p0; P < mine[i].p1; ++P)
-                own[(int64_t)mine[i].q * (mine[i].q + 1) / 2 + P] = 1;
+        n_own = 0;
+        for (int X = 0; X < M; ++X) {
+            own_first[X] = n_own;
+            for (int sl = qfirst[X]; sl < qfirst[X + 1]; ++sl)
+                if (own[pairs + sl]) own_list[n_own++] = (int)(pairs + sl);
+            for (int Q = X; Q < M; ++Q) {
+                const int64_t sb = (int64_t)Q * (Q + 1) / 2 + X;
+                if (own[sb]) own_list[n_own++] = (int)sb;
+            }
         }
-        const size_t own_bytes = (size_t)(pairs + slot);
-        int rc = vsb_buf_reserve(c->sym_tab, sizeof(sym_task) * (size_t)(nm + 1) +
-                                                 sizeof(int) * (size_t)(M + 1) + own_bytes + 1024);
+        own_first[M] = n_own;
+        free(own);
+        const size_t tab_bytes = (sizeof(sym_task) * (size_t)(nm + 1) + 255) / 256 * 256;
+        const size_t idx_bytes = (sizeof(int) * (size_t)(M + 1) + 255) / 256 * 256;
+        int rc = vsb_buf_reserve(c->sym_tab, tab_bytes + 2 * idx_bytes + sizeof(int) * (size_t)(n_own + 1) + 1024);
         char *qf = nullptr;
         cudaError_t ce = cudaSuccess;
         if (rc == VSB_OK) {
-            qf = (char *)c->sym_tab.p + (sizeof(sym_task) * (size_t)(nm + 1) + 255) / 256 * 256;
+            qf = (char *)c->sym_tab.p + tab_bytes;
+            char *of = qf + idx_bytes, *ol = of + idx_bytes;
             ce = cudaMemcpyAsync(c->sym_tab.p, mine, sizeof(sym_task) * (size_t)nm,
                                  cudaMemcpyHostToDevice, c->stream);
             if (ce == cudaSuccess)
                 ce = cudaMemcpyAsync(qf, qfirst, sizeof(int) * (size_t)(M + 1),
                                      cudaMemcpyHostToDevice, c->stream);
-            char *ow = qf + (sizeof(int) * (size_t)(M + 1) + 255) / 256 * 256;
             if (ce == cudaSuccess)
-                ce = cudaMemcpyAsync(ow, own, own_bytes, cudaMemcpyHostToDevice, c->stream);
-            c->sym_own_off = (int64_t)(ow - (char *)c->sym_tab.p);
+                ce = cudaMemcpyAsync(of, own_first, sizeof(int) * (size_t)(M + 1),
+                                     cudaMemcpyHostToDevice, c->stream);
+            if (ce == cudaSuccess)
+                ce = cudaMemcpyAsync(ol, own_list, sizeof(int) * (size_t)n_own, cudaMemcpyHostToDevice,
+                                     c->stream);
+            c->sym_own_off = (int64_t)(of - (char *)c->sym_tab.p);
+            c->sym_ownlist_off = (int64_t)(ol - (char *)c->sym_tab.p);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
         }
-        free(own);
+        free(own_first);
+        free(own_list);
         free(all);
         free(qfirst);
         free(mine);
@@ -367,18 +408,12 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
         c->sym_ntasks = nm;
         c->sym_nslots = slot;
         c->sym_qf_off = (int64_t)(qf - (char *)c->sym_tab.p);
-        c->sym_zeroed = nullptr;
     }
     const size_t slab = sizeof(double2) * (size_t)S;
     const size_t bytes_p = slab * (size_t)pairs, bytes_q = slab * (size_t)c->sym_nslots;
     VSB_TRY(vsb_buf_reserve(c->part, bytes_p + bytes_q));
     double2 *part_p = (double2 *)c->part.p;
     double2 *part_q = (double2 *)((char *)c->part.p + bytes_p);
-    if (world > 1 && c->sym_zeroed != c->part.p) {
-        // slabs of tasks owned by other ranks must read as zero in this rank's reduction
-        VSB_CUDA(cudaMemsetAsync(c->part.p, 0, bytes_p + bytes_q, c->stream));
-        c->sym_zeroed = c->part.p;
-    }
     const sym_task *d_tasks = (const sym_task *)c->sym_tab.p;
     const int *d_qf = (const int *)((char *)c->sym_tab.p + c->sym_qf_off);
     const size_t smem = (size_t)S * (2 * sizeof(double2) + sizeof(double));
@@ -403,10 +438,11 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
         VSB_CHECK(launched, VSB_ERR_ARG, "allpairs_sym: no kernel for shape %d,%d,%d,%d", warps, tpl, su, mb);
         c->launches += 1;
     }
-    const unsigned char *own_p = world > 1 ? (const unsigned char *)c->sym_tab.p + c->sym_own_off : nullptr;
-    const unsigned char *own_q = world > 1 ? own_p + pairs : nullptr;
+    // slabs of other ranks' tasks are never read: no zeroing of the slab memory is needed
+    const int *own_first = world > 1 ? (const int *)((char *)c->sym_tab.p + c->sym_own_off) : nullptr;
+    const int *own_list = world > 1 ? (const int *)((char *)c->sym_tab.p + c->sym_ownlist_off) : nullptr;
     allpairs_sym_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
-        part_p, part_q, d_qf, own_p, own_q, S, M, n, gc, (double2 *)c->acc, (double2 *)c->vel,
+        part_p, part_q, d_qf, own_first, own_list, S, M, n, gc, (double2 *)c->acc, (double2 *)c->vel,
         (double2 *)c->pos, (world == 1 && integrate) ? 1 : 0);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
