@@ -40,6 +40,11 @@ typedef struct vsb_ctx vsb_ctx;
 /* ------------------------------------------------------------------ library */
 int vsb_abi_version(void);
 const char *vsb_last_error(void);
+/* Which instruction schedule of the symmetric pair kernel this library runs: "resched" (the SASS
+ * post-pass of volatilespace_b200/sass_resched.py was applied at build time) or "ptxas ..." with
+ * the reason in parentheses (post-pass skipped or failed at build time, or VSB_SYM_SCHED=ptxas
+ * in the environment).  Same results bit for bit either way; the string is static. */
+const char *vsb_sym_schedule(void);
 int vsb_device_count(int *count_out);
 
 /* One context per GPU (one per process under torch.distributed). */

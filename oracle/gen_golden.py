@@ -1049,6 +1049,80 @@ def gen_convert_vel(ns):
     save("convert_vel", **out)
 
 
+def bits_xor(a):
+    """Order-independent fingerprint of an array's exact bits (tests rebuild the inputs the
+    live reference saw and must prove they are the same bits)."""
+    return np.bitwise_xor.reduce(np.ascontiguousarray(a, dtype=np.float64).reshape(-1).view(np.uint64))
+
+
+def gen_fullsize(ns):
+    """Round-2 fixtures at the sizes SURVEY 8d names ("next" item 1):
+      * collision_k64: config 5 teacher-forced at N = 4096 over K = 64 ticks -- the genuine
+        reference's check_collision (phys_editor.py:547-551) on a seeded kinematic collapse
+        (synth.kinematic_collapse: pos += vel, merges by the documented rule), (del, add) per tick;
+      * editor_curve_conics: C7 (phys_editor.py:519-544) on ellipses, hyperbolas AND exact
+        ecc == 1 parabolas (:532-534);
+      * body_move_deep: C1 (phys_body.py:323-346) on a 131 072-body hierarchy of depth 3 with
+        children that come before their parent in argsort(coi)[::-1]; 4096 sampled rows kept."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from volatilespace_b200 import synth
+    from volatilespace_b200.phys_editor import body_radius
+    # ---- collision_k64
+    s = synth.kinematic_collapse()
+    ph = ns.phys_editor.Physics()
+
+    def ref_check(mass, pos, rad):
+        ph.mass, ph.pos, ph.rad = mass, pos, rad
+        return ph.check_collision()
+    pairs, fp = [], []
+    for t, mass, pos, rad, pair in synth.kinematic_collapse_run(s, 64, ref_check, body_radius):
+        pairs.append([-1, -1] if pair[0] is None else [int(pair[0]), int(pair[1])])
+        fp.append([len(mass), int(bits_xor(pos)), int(bits_xor(rad)), int(bits_xor(mass))])
+    save("collision_k64", pairs=np.array(pairs, dtype=np.int64), fingerprint=np.array(fp, dtype=np.uint64),
+         n=np.int64(len(s["mass"])), ticks=np.int64(64))
+    # ---- editor_curve_conics
+    rng = np.random.default_rng(20240607)
+    n, P = 96, 48
+    kind = np.arange(n) % 3                     # 0 ellipse, 1 hyperbola, 2 parabola
+    ang = rng.uniform(0, 2 * np.pi, n)
+    emag = np.where(kind == 0, rng.uniform(0.0, 0.95, n), rng.uniform(1.05, 3.0, n))
+    ecc_v = np.stack([emag * np.cos(ang), emag * np.sin(ang)], axis=1)
+    unit = np.array([[1.0, 0.0], [0.0, 1.0], [-1.0, 0.0], [0.0, -1.0], [0.6, 0.8], [-0.8, 0.6]])
+    par = np.flatnonzero(kind == 2)
+    ecc_v[par] = unit[np.arange(len(par)) % len(unit)]
+    assert all(ns.phys_shared.mag(ecc_v[i]) == 1.0 for i in par)
+    a = rng.uniform(500, 5e4, n) * np.where(kind == 1, -1.0, 1.0)
+    f = a * np.where(kind == 2, 1.0, emag)
+    b = np.sqrt(np.abs(f * f - a * a))
+    pe = rng.uniform(0, 2 * np.pi, n)
+    parents = rng.integers(0, n, n)
+    parents[0] = 0
+    pos = rng.uniform(-1e5, 1e5, (n, 2))
+    ph = ns.phys_editor.Physics()
+    rh.set_curve_points(ns, ph, P)
+    ph.ecc_v, ph.semi_major, ph.semi_minor, ph.focus, ph.periapsis_arg = ecc_v, a, b, f, pe
+    ph.parents, ph.pos = parents, pos
+    save("editor_curve_conics", P=np.int64(P), ecc_v=ecc_v, semi_major=a, semi_minor=b, focus=f,
+         periapsis_arg=pe, parents=parents, pos=pos, curves=ph.curve())
+    # ---- body_move_deep
+    h = synth.kepler_hierarchy()
+    n = len(h["a"])
+    pb = ns.phys_body.Physics()
+    for k in ("a", "b", "f", "ecc", "pea", "n", "coi", "ref"):
+        setattr(pb, k, h[k].copy())
+    pb.dr, pb.ma, pb.ea, pb.pos = h["dr"].copy(), h["ma"].copy(), h["ea"].copy(), h["pos"].copy()
+    sample = np.sort(np.random.default_rng(3).choice(n, 4096, replace=False))
+    out = dict(n=np.int64(n), sample=sample,
+               inputs_fp=np.array([int(bits_xor(h[k])) for k in ("a", "b", "f", "ecc", "pea", "n", "coi",
+                                                                 "dr", "ma", "ea")], dtype=np.uint64),
+               ref_fp=np.int64(np.bitwise_xor.reduce(h["ref"])))
+    for step, warp in enumerate((1, 3, 2)):
+        pos, ma, ea = pb.move(warp)
+        out.update({"pos%d" % step: pos[sample].copy(), "ma%d" % step: ma[sample].copy(),
+                    "ea%d" % step: ea[sample].copy()})
+    save("body_move_deep", **out)
+
+
 def main():
     """All fixtures, or only the ones named on the command line (e.g. `vessel_points`)."""
     ns = rh.load()
@@ -1070,6 +1144,7 @@ def main():
     if want("vessel_draw"): gen_vessel_draw(ns, conf, bd, bod)
     if want("mapfiles"): gen_mapfiles(ns, conf, bd, bod)
     if want("convert_vel"): gen_convert_vel(ns)
+    if want("fullsize"): gen_fullsize(ns)
 
 
 if __name__ == "__main__":

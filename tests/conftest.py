@@ -95,3 +95,9 @@ def events_vessel12(v):
     import numpy as np
     return np.stack([v[:, 0], v[:, 1], v[:, 2], v[:, 3], v[:, 7], v[:, 8], v[:, 4], v[:, 5], v[:, 6],
                      v[:, 11], v[:, 12], v[:, 13]], axis=1)
+
+
+def bits_xor(a):
+    """Order-independent fingerprint of an array's exact bits (oracle/gen_golden.py:bits_xor)."""
+    import numpy as np
+    return np.bitwise_xor.reduce(np.ascontiguousarray(a, dtype=np.float64).reshape(-1).view(np.uint64))

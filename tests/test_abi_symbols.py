@@ -34,8 +34,12 @@ def test_header_symbols_are_exported(lib):
 
 def test_ctypes_stub_matches_header():
     from volatilespace_b200 import _lib
-    assert sorted(list(_lib.SIGNATURES) + ["vsb_last_error"]) == declared_symbols()
+    assert sorted(list(_lib.SIGNATURES) + ["vsb_last_error", "vsb_sym_schedule"]) == declared_symbols()
     _lib.load()
+    # the SASS post-pass either ran or the library says why not (build.status() is the same string)
+    from volatilespace_b200 import build
+    assert _lib.sym_schedule().split(" ")[0] in ("resched", "ptxas")
+    assert _lib.sym_schedule().split(" ")[0] == build.status()["sym_sched"]
 
 
 def test_no_compute_without_gpu_is_loud(lib):

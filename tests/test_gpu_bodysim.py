@@ -71,15 +71,23 @@ def test_allpairs_accel_vs_oracle(dev, oracle, n, gravity_mode):
 
 
 def test_allpairs_plummer_sampled_rows(dev, oracle, gravity_mode):
-    """64k-body config: acceleration parity on 256 sampled target rows."""
+    """Config 2 (64k-body Plummer disk): acceleration parity on 4096 sampled target rows
+     -- 8 seeded blocks of 512 consecutive rows, first and last rows included --
+    rel 1e-11 per row; the share within 1e-13 is asserted too."""
     from volatilespace_b200 import synth
     s = synth.plummer2d(65536)
     acc = dev.host_allpairs_accel(s["mass"], s["pos"], s["gc"])
-    rows = np.random.default_rng(7).choice(65536, 256, replace=False)
-    for r in rows[:256]:
-        want = oracle.allpairs_accel(s["mass"], s["pos"], s["gc"], int(r), int(r) + 1)[0]
-        err = np.linalg.norm(acc[r] - want) / np.linalg.norm(want)
-        assert err < 1e-11, (r, err)
+    assert np.all(np.isfinite(acc))
+    starts = np.concatenate(([0, 65536 - 512],
+                             np.random.default_rng(7).choice(65536 - 512, 6, replace=False)))
+    errs = []
+    for r0 in starts:
+        want = oracle.allpairs_accel(s["mass"], s["pos"], s["gc"], int(r0), int(r0) + 512)
+        got = acc[r0:r0 + 512]
+        errs.append(np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1))
+    errs = np.concatenate(errs)
+    assert len(errs) == 4096 and errs.max() < 1e-11, errs.max()
+    assert (errs < 1e-13).mean() > 0.99
 
 
 def test_allpairs_disk1m_sampled_rows(dev, oracle):
@@ -416,9 +424,10 @@ def test_collision_full_size_property(dev, oracle):
 
 
 def test_collapsing_cluster_full_size_merges_teacher_forced(dev, oracle):
-    """Config 5 at full size (262 144 bodies): run the real ticks on the GPU and, every tick,
-    hand the GPU's own pos / rad / mass to the oracle's exhaustive check_collision -- the
-    (del, add) pair must be identical (teacher-forced)."""
+    """Config 5 at full size (262 144 bodies), horizon K = 64: run the real ticks on the GPU
+    (all-pairs gravity, radius, collision check, merge + compaction) and, every tick, hand the
+    GPU's own pos / rad / mass to the oracle's exhaustive check_collision -- the (tick, del, add)
+    list must be identical (teacher-forced)."""
     from volatilespace_b200 import synth
     from volatilespace_b200.phys_editor import AllPairsPhysics
     s = synth.collapsing_cluster(262144)
@@ -426,7 +435,8 @@ def test_collapsing_cluster_full_size_merges_teacher_forced(dev, oracle):
     ph.load_system({"gc": s["gc"], "rad_mult": s["rad_mult"]}, {"mass": s["mass"], "den": s["den"]},
                    {"pos": s["pos"], "vel": s["vel"]})
     hits = 0
-    for tick in range(3):
+    merges = []
+    for tick in range(64):                      # K = 64
         ph.gravity()
         ph.body()
         ph.pull("pos")
@@ -434,8 +444,11 @@ def test_collapsing_cluster_full_size_merges_teacher_forced(dev, oracle):
         got = ph.inelastic_collision()
         assert (got if got is not None else (None, None)) == want, tick
         hits += got is not None
-    assert hits >= 1
+        merges.append(got)
+    assert hits >= 32
     assert len(ph.mass) == 262144 - hits
+    # index bookkeeping: a deleted row shifts every later index, so the list is not monotone
+    assert len({m for m in merges if m is not None}) == hits
 
 
 # ------------------------------------------------------------------ editor frames (MODE_REF)

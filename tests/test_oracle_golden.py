@@ -514,3 +514,58 @@ def test_vessel_draw_selected_rotate_predict_next_orbit(draw):
         ang, spd = draw.rotate(5, 3, 1.0, ang, spd, acc)
         assert _eq(ang, g["s%d_rot_angle3" % k]) and _eq(spd, g["s%d_rot_speed3" % k])
     assert n_pno > 100
+
+
+# ------------------------------------------------------------- round-2 fixtures (gen_fullsize)
+def test_collision_k64_teacher_forced(oracle):
+    """Config 5 at the size the genuine reference runs: 4096 bodies, 64 ticks,
+    the same mass / pos / rad on both sides each tick -- (del, add) bit-exact, and the rebuilt
+    states are proven to be the bits the live reference saw."""
+    from conftest import bits_xor
+    from volatilespace_b200 import synth
+    g = golden("collision_k64")
+    s = synth.kinematic_collapse()
+    ticks = 0
+    for t, mass, pos, rad, pair in synth.kinematic_collapse_run(s, int(g["ticks"]), oracle.check_collision,
+                                                                oracle.body_radius):
+        fp = g["fingerprint"][t]
+        assert (len(mass), int(bits_xor(pos)), int(bits_xor(rad)), int(bits_xor(mass))) == tuple(
+            int(x) for x in fp), "tick %d: rebuilt state differs from the fixture's" % t
+        want = g["pairs"][t]
+        assert (pair == (None, None) and want[0] < 0) or tuple(int(x) for x in want) == pair, t
+        ticks += 1
+    assert ticks == 64 and (g["pairs"][:, 0] >= 0).sum() >= 40 and (g["pairs"][:, 0] < 0).sum() >= 5
+
+
+def test_editor_curve_conics(oracle):
+    """C7 incl. the hyperbola and the exact ecc == 1 parabola branch (phys_editor.py:528-537)."""
+    g = golden("editor_curve_conics")
+    got = oracle.editor_curve(g["ecc_v"], g["semi_major"], g["semi_minor"], g["focus"],
+                              g["periapsis_arg"], g["parents"], g["pos"], int(g["P"]))
+    scale = np.abs(g["curves"]).max(axis=(0, 2))[None, :, None]
+    assert np.all(np.abs(got - g["curves"]) <= 1e-12 * scale)
+    ecc = np.hypot(g["ecc_v"][:, 0], g["ecc_v"][:, 1])
+    assert (ecc == 1).sum() >= 30 and (ecc > 1).sum() >= 30 and (ecc < 1).sum() >= 30
+
+
+def test_body_move_deep_hierarchy(oracle):
+    """C1 on 131 072 bodies, depth 3, children ahead of their parent in argsort(coi)[::-1]."""
+    from conftest import bits_xor
+    from volatilespace_b200 import synth
+    g = golden("body_move_deep")
+    h = synth.kepler_hierarchy()
+    fp = [int(bits_xor(h[k])) for k in ("a", "b", "f", "ecc", "pea", "n", "coi", "dr", "ma", "ea")]
+    assert fp == [int(x) for x in g["inputs_fp"]] and int(np.bitwise_xor.reduce(h["ref"])) == int(g["ref_fp"])
+    order = np.argsort(h["coi"])[-1::-1]
+    rank = np.empty(len(order), dtype=np.int64)
+    rank[order] = np.arange(len(order))
+    assert ((rank[h["ref"]] > rank)[1:]).sum() > 1000          # refs that point forward
+    pos, ma, ea = h["pos"], h["ma"], h["ea"]
+    sm = g["sample"]
+    for step, warp in enumerate((1, 3, 2)):
+        pos, ma, ea = oracle.body_move(warp, h["ref"], h["coi"], h["a"], h["b"], h["f"], h["ecc"],
+                                       h["pea"], h["n"], h["dr"], ma, ea, pos)
+        assert np.array_equal(ma[sm], g["ma%d" % step])
+        assert_close(ea[sm], g["ea%d" % step], rtol=1e-13, atol=1e-15)
+        scale = np.abs(g["pos%d" % step]).max()
+        assert np.abs(pos[sm] - g["pos%d" % step]).max() <= 1e-13 * scale

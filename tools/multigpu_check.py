@@ -144,16 +144,31 @@ def main():
     ref_single.load_system(econf, ebd, ebo)
     ref_sh = ShardedPhysics(Device(local), rank, world)
     ref_sh.load_system(econf, ebd, ebo)
-    for tick in range(4):
-        # ticks 0-1: the sort-based candidate pass on every rank (default at this size);
-        # ticks 2-3: the exhaustive scan, split over the ranks by row blocks
-        if tick == 2:
+    ok_ref_merges = True
+    ref_single.body()
+    ref_sh.body()
+    n_ref_merges = 0
+    for tick in range(8):
+        # ticks 0-3: the sort-based candidate pass on every rank (default at this size);
+        # ticks 4-7: the exhaustive scan, split over the ranks by row blocks.  Collision checks,
+        # merges and mass edits run BETWEEN the gravity calls: they re-reserve the staging buffer
+        # that holds best[] (the view the MAX all-reduce runs on must follow it)
+        if tick == 4:
             os.environ["VSB_PARENTS"] = "scan"
         ref_single.gravity()
         ref_sh.gravity()
+        ref_single.body()
+        ref_sh.body()
+        m_a, m_b = ref_single.inelastic_collision(), ref_sh.inelastic_collision()
+        if m_a != m_b:
+            ok_ref_merges = False
+        n_ref_merges += m_a is not None
+        if tick in (1, 5):
+            for obj in (ref_single, ref_sh):
+                obj.set_body_mass(17 + tick, float(obj.mass[17 + tick]) * 40.0)
     os.environ.pop("VSB_PARENTS", None)
     par = ref_single.dev.get(F_PARENTS)
-    ok_ref = np.array_equal(par, ref_sh.dev.get(F_PARENTS)) and \
+    ok_ref = ok_ref_merges and np.array_equal(par, ref_sh.dev.get(F_PARENTS)) and \
         np.array_equal(ref_single.dev.get(F_POS), ref_sh.dev.get(F_POS)) and \
         np.array_equal(ref_single.dev.get(F_VEL), ref_sh.dev.get(F_VEL))
     n_children = int((par != 0).sum())
@@ -163,9 +178,10 @@ def main():
     if rank == 0:
         print("multigpu_check n=%d world=%d ticks=%d: sharded==single %s, host path %s, "
               "sym within tolerance %s, sym replicas identical %s, collision ticks (%d merges) %s, "
-              "kepler slices %s, MODE_REF tick (%d bodies whose parent is not body 0) %s" %
+              "kepler slices %s, MODE_REF ticks interleaved with %d merges and 2 mass edits (%d bodies whose "
+              "parent is not body 0) %s" %
               (n, world, ticks, *[bool(x) for x in flag.tolist()[:4]], n_merges,
-               bool(flag[4]), bool(flag[5]), n_children, bool(flag[6])))
+               bool(flag[4]), bool(flag[5]), n_ref_merges, n_children, bool(flag[6])))
     dist.barrier()
     dist.destroy_process_group()
     if not all(flag.tolist()):

@@ -153,8 +153,15 @@ def load():
         fn.restype = C.c_int
     L.vsb_last_error.argtypes = []
     L.vsb_last_error.restype = C.c_char_p
+    L.vsb_sym_schedule.argtypes = []
+    L.vsb_sym_schedule.restype = C.c_char_p
     _lib = L
     return L
+
+
+def sym_schedule():
+    """"resched" or "ptxas (<why>)": the schedule of the symmetric pair kernel in this library."""
+    return load().vsb_sym_schedule().decode("utf-8", "replace")
 
 
 def check(code):

@@ -7,6 +7,7 @@ The shared library travels to the GPU box with the gpurun snapshot; it is
 git-ignored.  nvcc cross-compiles without a GPU.
 """
 import os
+import shutil
 import subprocess
 import sys
 
@@ -58,18 +59,42 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _obj(src):
+    return os.path.join(OBJ, src.replace(".cu", "").replace("@", "_") + ".o")
+
+
+def _read(path):
+    try:
+        with open(path) as f:
+            return f.read()
+    except OSError:
+        return None
+
+
+def _write_if_changed(path, text):
+    if _read(path) != text:
+        with open(path, "w") as f:
+            f.write(text)
+
+
+def status():
+    """What the last build() did about the SASS post-pass: {"sym_sched": "resched" | "ptxas",
+    "warning": None | reason}.  The same string is compiled into the library (vsb_sym_schedule)."""
+    txt = _read(os.path.join(OBJ, "sym_sched.txt")) or "ptxas (never built)"
+    return {"sym_sched": txt.split(" ")[0], "warning": txt[txt.index("(") + 1:-1] if "(" in txt else None}
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, "vsb_common.cuh"), os.path.join(CSRC, "vsb_orbit_math.cuh"),
-               os.path.join(CSRC, "vsb_grid.cuh"), INCLUDE,
-               os.path.abspath(__file__), os.path.join(HERE, "sass_resched.py")]
+               os.path.join(CSRC, "vsb_grid.cuh"), INCLUDE, os.path.abspath(__file__)]
     objs, procs = [], []
     env = dict(os.environ)
     env.pop("CC", None)    # the image exports a gcc wrapper nvcc should not pick up
     env.pop("CXX", None)
     for src, extra in SOURCES.items():
         s = os.path.join(CSRC, src.split("@")[0])
-        o = os.path.join(OBJ, src.replace(".cu", "").replace("@", "_") + ".o")
+        o = _obj(src)
         objs.append(o)
         if force or _stale(o, [s] + headers):
             cmd = [_nvcc()] + ARCH + COMMON + extra + ["-c", s, "-o", o]
@@ -88,22 +113,54 @@ def build(force=False, verbose=False):
             sys.stderr.write("nvcc failed on %s\n" % src)
     if failed:
         raise RuntimeError("libvsb200 build failed")
-    # SASS post-pass on freshly compiled objects (sass_resched.py: same instructions, same
-    # registers, same results bit for bit -- the accumulates of the pair loop regrouped so that
-    # they ride the operand-reuse cache).  VSB_NO_RESCHED=1 keeps ptxas's own schedule.
-    for src, _ in procs:
-        if src in RESCHED and not os.environ.get("VSB_NO_RESCHED"):
-            from volatilespace_b200 import sass_resched
-            o = os.path.join(OBJ, src.replace(".cu", "").replace("@", "_") + ".o")
-            try:
-                for line in sass_resched.patch_object(o, RESCHED[src], no_yield=True):
+    # SASS post-pass (sass_resched.py: same instructions, same registers, same results bit for
+    # bit -- the accumulates of the pair loop regrouped so that they ride the operand-reuse
+    # cache).  ptxas's object is never modified: the patched code goes to a SEPARATE file
+    # (<name>_resched.o, rebuilt when ptxas's object or the tool is newer), and which of the two
+    # is linked is recorded in _build/sym_sched.txt, compiled into the library
+    # (vsb_sym_schedule()) and returned by status().  VSB_NO_RESCHED=1 links ptxas's schedule.
+    sched = "resched"
+    for src, pattern in RESCHED.items():
+        plain = _obj(src)
+        patched = plain[:-2] + "_resched.o"
+        if os.environ.get("VSB_NO_RESCHED"):
+            sched = "ptxas (VSB_NO_RESCHED set at build time)"
+            continue
+        try:
+            tool = os.path.join(HERE, "sass_resched.py")
+            if force or _stale(patched, [plain, tool]):
+                from volatilespace_b200 import sass_resched
+                tmp = patched + ".tmp"
+                shutil.copyfile(plain, tmp)
+                for line in sass_resched.patch_object(tmp, pattern, no_yield=True):
                     if verbose:
                         print(line)
-            except Exception as e:  # noqa: BLE001 -- ptxas's schedule stays: slower, same results
-                sys.stderr.write("sass_resched skipped for %s: %s\n" % (src, e))
-    if force or procs or _stale(LIB, objs):
+                os.replace(tmp, patched)
+            objs[objs.index(plain)] = patched
+        except Exception as e:  # noqa: BLE001 -- ptxas's schedule stays: slower, same results
+            sched = "ptxas (SASS post-pass failed: %s)" % str(e).replace("\n", " ")[:160]
+            sys.stderr.write("WARNING: sass_resched skipped for %s: %s\n" % (src, e))
+    _write_if_changed(os.path.join(OBJ, "sym_sched.txt"), sched)
+    info_c = os.path.join(OBJ, "vsb_build_info.c")
+    _write_if_changed(info_c, """/* generated by volatilespace_b200/build.py */
+#include <stdlib.h>
+#include <string.h>
+const char *vsb_sym_schedule(void)
+{
+    const char *e = getenv("VSB_SYM_SCHED");
+    if (e && strcmp(e, "ptxas") == 0) return "ptxas (VSB_SYM_SCHED=ptxas)";
+    return "%s";
+}
+""" % sched.replace("\\", "/").replace('"', "'"))
+    info_o = os.path.join(OBJ, "vsb_build_info.o")
+    if force or _stale(info_o, [info_c]):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-c", info_c, "-o", info_o], env=env)
+    objs.append(info_o)
+    link_txt = os.path.join(OBJ, "link.txt")
+    if force or procs or _stale(LIB, objs) or _read(link_txt) != "\n".join(objs):
         cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
         subprocess.check_call(cmd, env=env)
+        _write_if_changed(link_txt, "\n".join(objs))
     return LIB
 
 

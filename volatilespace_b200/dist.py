@@ -74,6 +74,7 @@ class ShardedAllPairs:
         self.rpr, self.ranges = partition(self.n, world)
         self.row0, self.row1 = self.ranges[rank]
         dev.upload_bodies(mass, pos, vel)
+        dev.set_gravity_mode("rows")      # the shard-invariant kernel (auto would pick sym at world 1)
         dev.set_rows(self.row0, self.row1)
         self._stream = None
         self._pos_t = None
@@ -228,17 +229,20 @@ class ShardedAllPairsPhysics:
         return getattr(self.inner, name)
 
     def _views(self):
+        """torch views of the acceleration array and the collision key word; rebuilt whenever the
+        library's addresses or the body count changed (a resize may move the body slab)."""
         import torch
         from ._lib import F_ACC
         n = len(self.inner.mass)
-        if self._views_n != n:
+        key = (self.dev.device_ptr(F_ACC), self.dev.collision_key_ptr(), n)
+        if self._views_n != key:
             self._acc_t = device_tensor(self.dev, F_ACC, n)
-            key = _CudaView(self.dev.collision_key_ptr(), (1,), "<i8")
-            self._key_t = torch.as_tensor(key, device="cuda:%d" % self.dev.index)
-            if self._stream is None:
-                self._stream = torch.cuda.ExternalStream(self.dev.stream_handle(),
-                                                         device="cuda:%d" % self.dev.index)
-            self._views_n = n
+            kview = _CudaView(key[1], (1,), "<i8")
+            self._key_t = torch.as_tensor(kview, device="cuda:%d" % self.dev.index)
+            self._views_n = key
+        if self._stream is None:
+            self._stream = torch.cuda.ExternalStream(self.dev.stream_handle(),
+                                                     device="cuda:%d" % self.dev.index)
         return self._acc_t, self._key_t
 
     def gravity(self):
@@ -324,22 +328,27 @@ class ShardedPhysics:
         from .phys_editor import Physics
         self.inner = Physics(device)
         self.dev, self.rank, self.world, self.group = self.inner.dev, rank, world, group
-        self._best_n = -1
+        self._best_key = None
         self._stream = None
 
     def __getattr__(self, name):
         return getattr(self.inner, name)
 
     def _best(self):
+        """torch view of the library's best[] array.  best[] lives in a staging buffer that other
+        passes (the collision candidate pass, simplified_orbit_coi) may re-allocate between ticks,
+        so the address is asked for on EVERY tick -- after gravity_ref_begin, which reserves the
+        buffer -- and the view is rebuilt whenever the address or the body count changed."""
         import torch
         n = len(self.inner.mass)
-        if self._best_n != n:
-            view = _CudaView(self.dev.find_parents_best_ptr(), (n,), "<i4")
+        key = (self.dev.find_parents_best_ptr(), n)
+        if self._best_key != key:
+            view = _CudaView(key[0], (n,), "<i4")
             self._best_t = torch.as_tensor(view, device="cuda:%d" % self.dev.index)
-            if self._stream is None:
-                self._stream = torch.cuda.ExternalStream(self.dev.stream_handle(),
-                                                         device="cuda:%d" % self.dev.index)
-            self._best_n = n
+            self._best_key = key
+        if self._stream is None:
+            self._stream = torch.cuda.ExternalStream(self.dev.stream_handle(),
+                                                     device="cuda:%d" % self.dev.index)
         return self._best_t
 
     def gravity(self):
@@ -349,8 +358,8 @@ class ShardedPhysics:
         import torch
         import torch.distributed as dist
         order = None if inner._order_on_device else inner._order()
-        best = self._best()
         self.dev.gravity_ref_begin_async(order, self.rank, self.world)
+        best = self._best()          # after begin: begin may have re-allocated the staging buffer
         with torch.cuda.stream(self._stream):
             dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)
         self.dev.gravity_ref_finish(inner.gc)

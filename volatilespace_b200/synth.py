@@ -121,3 +121,99 @@ def kepler_objects(n=4194304, seed=20240603, gc=1.0, central_mass=1.0e6, quirk=0
     ea = np.where(ecc >= 1, ma, 0.0)           # hyperbolic warm start (phys_vessel.py:221)
     return dict(a=a, ecc=ecc, pea=pea, ma=ma, dr=dr, ref=ref, b=orb["b"], f=orb["f"],
                 n=orb["n"], ea=ea, body_pos=body_pos, body_mass=body_mass, gc=gc)
+
+
+def kepler_bodies(n=4194304, seed=20240603, gc=1.0, central_mass=1.0e6, quirk=0, coi_coef=0.7):
+    """Config 4, body-style variant (C1, phys_body.py:323-346): the same conics as
+    kepler_objects, as BODIES of one root (index 0, all-zero elements, phys_body.py:60) with
+    ref = 0 everywhere, light masses and the `coi` that orders the reference's loop."""
+    k = kepler_objects(n, seed=seed, gc=gc, central_mass=central_mass, quirk=quirk)
+    rng = np.random.default_rng(seed + 1)
+    mass = rng.uniform(0.5, 2.0, n)
+    mass[0] = central_mass
+    a, ecc = k["a"].copy(), k["ecc"].copy()
+    a[0] = ecc[0] = 0.0
+    orb = calc_orb("body", k["ref"], mass, mass, gc, coi_coef, a, ecc)
+    ma, pea, dr = k["ma"].copy(), k["pea"].copy(), k["dr"].copy()
+    ma[0] = pea[0] = 0.0
+    ea = np.where(ecc >= 1, ma, 0.0)
+    return dict(a=a, ecc=ecc, pea=pea, ma=ma, dr=dr, ref=k["ref"], b=orb["b"], f=orb["f"],
+                n=orb["n"], coi=orb["coi"], ea=ea, mass=mass, pos=np.zeros((n, 2)), gc=gc)
+
+
+def kepler_hierarchy(n=131072, seed=20240605, gc=1.0, coi_coef=0.7):
+    """C1 on a deep hierarchy: root 0 -> planets -> moons -> moonlets (depth 3), indices
+    shuffled so that `ref` points both ways in index order, 8 % hyperbolic bodies on every
+    level.  A hyperbolic body has coi = 0 (calc_orb_one, phys_body.py:47-50), so its children
+    come BEFORE it in argsort(coi)[::-1] and are composed with its position of the previous
+    tick -- the loop-order behaviour of phys_body.py:328-345 that the device path must keep."""
+    rng = np.random.default_rng(seed)
+    n1 = max(2, n // 128)
+    n2 = max(2, n // 12)
+    n3 = n - 1 - n1 - n2
+    perm = np.concatenate(([0], 1 + rng.permutation(n - 1)))       # new index of logical body k
+    lvl = np.concatenate(([0], np.full(n1, 1), np.full(n2, 2), np.full(n3, 3)))
+    lref = np.zeros(n, dtype=np.int64)                             # logical parent
+    lref[1 + n1:1 + n1 + n2] = rng.integers(1, 1 + n1, n2)
+    lref[1 + n1 + n2:] = rng.integers(1 + n1, 1 + n1 + n2, n3)
+    scale_a = np.array([0.0, 1.0e8, 1.0e4, 30.0])[lvl]
+    scale_m = np.array([1.0e9, 1.0e4, 10.0, 0.05])[lvl]
+    hyp = rng.uniform(0, 1, n) < 0.08
+    hyp[0] = False
+    ecc_l = np.where(hyp, rng.uniform(1.05, 2.5, n), rng.uniform(0.0, 0.9, n))
+    a_l = scale_a * rng.uniform(0.1, 1.0, n) * np.where(hyp, -1.0, 1.0)
+    mass_l = scale_m * rng.uniform(0.5, 2.0, n)
+    pea_l = rng.uniform(0, 2 * np.pi, n)
+    ma_l = np.where(hyp, rng.uniform(-2.0, 2.0, n), rng.uniform(0, 2 * np.pi, n))
+    dr_l = rng.choice([-1.0, 1.0], n)
+    a_l[0] = ecc_l[0] = pea_l[0] = ma_l[0] = 0.0
+    out = {}
+    inv = np.empty(n, dtype=np.int64)
+    inv[perm] = np.arange(n)                                       # logical body at new index
+    for name, arr in (("a", a_l), ("ecc", ecc_l), ("mass", mass_l), ("pea", pea_l), ("ma", ma_l),
+                      ("dr", dr_l), ("level", lvl)):
+        out[name] = np.ascontiguousarray(arr[inv])
+    out["ref"] = np.ascontiguousarray(perm[lref[inv]])
+    orb = calc_orb("body", out["ref"], out["mass"], out["mass"], gc, coi_coef, out["a"], out["ecc"])
+    out.update(b=orb["b"], f=orb["f"], n=orb["n"], coi=orb["coi"],
+               ea=np.where(out["ecc"] >= 1, out["ma"], 0.0), pos=np.zeros((n, 2)), gc=gc)
+    return out
+
+
+def kinematic_collapse(n=4096, seed=20240606, radius=4.0e4, rad_mult=179.0):
+    """Teacher-forced collision input (config 5 at the size the genuine reference can run): a
+    uniform disk whose bodies fall radially inward at constant speed, advanced by pos += vel only
+    (elementwise IEEE adds: every machine regenerates the same bits), so that the states the
+    live reference saw while the fixture was written can be rebuilt inside the test."""
+    rng = np.random.default_rng(seed)
+    mass = rng.uniform(0.5, 2.0, n)
+    mass[0] = 200.0
+    r = radius * np.sqrt(rng.uniform(0.0, 1.0, n))
+    th = rng.uniform(0.0, 2 * np.pi, n)
+    pos = np.stack([r * np.cos(th), r * np.sin(th)], axis=1)
+    pos[0] = 0.0
+    vel = -pos * rng.uniform(0.002, 0.01, (n, 1))
+    den = np.full(n, 3000.0)
+    return dict(mass=mass, den=den, pos=np.ascontiguousarray(pos), vel=np.ascontiguousarray(vel),
+                rad_mult=rad_mult)
+
+
+def kinematic_collapse_run(s, ticks, check_collision, body_radius):
+    """Drives kinematic_collapse for `ticks` ticks: pos += vel; rad = body_radius(...);
+    (del, add) = check_collision(mass, pos, rad); documented inelastic merge
+    (documentation/orbital-physics/09-collisions.txt:3-6: mass and momentum add up, the survivor
+    keeps its position) and np.delete of the deleted row.  Yields (tick, mass, pos, rad, pair)
+    BEFORE the merge is applied; `pair` is what check_collision returned."""
+    mass, den, pos, vel = (s[k].copy() for k in ("mass", "den", "pos", "vel"))
+    for t in range(ticks):
+        pos += vel
+        rad = body_radius(mass, den, s["rad_mult"])
+        pair = check_collision(mass, pos, rad)
+        yield t, mass, pos, rad, pair
+        if pair[0] is not None:
+            d, a = int(pair[0]), int(pair[1])
+            mr = mass[d] + mass[a]
+            vel[a] = (vel[a] * mass[a] + vel[d] * mass[d]) / mr
+            mass[a] = mr
+            mass, den = np.delete(mass, d), np.delete(den, d)
+            pos, vel = np.delete(pos, d, axis=0), np.delete(vel, d, axis=0)
