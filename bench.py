@@ -198,7 +198,7 @@ def time_ticks(torch, stream, fn, steps, barrier):
     return ev0.elapsed_time(ev1)
 
 
-def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
+def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak, with_cpu=True):
     """Secondary configs of BASELINE.json, device-timed, reported under `extra`."""
     from volatilespace_b200 import synth
     from volatilespace_b200._lib import KIND_VESSEL
@@ -251,9 +251,15 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
         ms = time_ticks(torch, stream, lambda: dev.allpairs_tick_async(s["gc"]), 16, nobar) / 16
         out["plummer64k"][mode] = {
             "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms,
-            "fp64_pipe_frac_at_1965mhz": pairs * OPS_PER_PAIR[mode] / (ms * 1e-3) /
-            (148 * 64 * 1965e6)}
+            "fp64_pipe_utilisation_at_1965mhz": pairs * OPS_PER_PAIR[mode] / (ms * 1e-3) /
+            (148 * 64 * 1965e6),
+            "flops13_frac_at_1965mhz": pairs * FLOPS_PER_PAIR / (ms * 1e-3) / (148 * 64 * 2 * 1965e6)}
     dev.set_gravity_mode("auto")
+    if with_cpu:
+        v, cores, rows, dtc = cpu_pairs_per_s(s, 4.0)
+        out["plummer64k"]["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d target rows x 65536 sources (%.1f s), oracle/vs_oracle.c OpenMP" % (rows, dtc)}
     # MODE_REF (the reference's own parent/COI model) at the size of config 3: one
     # editor gravity tick = find_parents + gravity_one per body + chain composition + integrator
     try:
@@ -302,6 +308,22 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
                                         "pair": None if hit[0] is None else list(hit)}
     os.environ.pop("VSB_COLLISION", None)
     coll["timing"] = "host wall clock per vsb_check_collision call incl. result read-back"
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as orc            # cpu_baseline leg only
+        orc.lib().vso_set_num_threads(len(os.sched_getaffinity(0)))
+        cores = orc.lib().vso_num_threads()
+        cb = {"cores": cores, "kind": "port", "unit": "bodies/s",
+              "sample": "oracle check_collision (phys_editor.py:86-97, 547-551 restated, OpenMP over "
+                        "rows with the reference's early exit), one full call per variant"}
+        for label, r in (("first_tick", rad), ("no_hit", rad * 0.01)):
+            t0 = time.perf_counter()
+            hit = orc.check_collision(s["mass"], s["pos"], r)
+            dtc = time.perf_counter() - t0
+            cb[label] = {"ms_per_tick": dtc * 1e3, "bodies_per_s": 262144 / dtc,
+                         "pair": None if hit[0] is None else [int(hit[0]), int(hit[1])]}
+        cb["value"] = cb["no_hit"]["bodies_per_s"]
+        coll["cpu_baseline"] = cb
     out["cluster256k_collision"] = coll
     # config 5 end to end: gravity(); body(); inelastic_collision() ticks with merges applied
     from volatilespace_b200.phys_editor import AllPairsPhysics
@@ -336,7 +358,9 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
         out["kepler4m"] = {"object_ticks_per_s": n / (ms * 1e-3), "ms_per_tick": ms,
                            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                                        "traffic": None, "bytes_per_object_tick": bytes_per_obj}}
+                                        "traffic": (measured_traffic("vessel_tick_kernel@kepler4m") or {}).get("bytes"),
+                                        "traffic_source": (measured_traffic("vessel_tick_kernel@kepler4m") or {}).get("source"),
+                                        "bytes_per_object_tick": bytes_per_obj}}
         # end to end through the host-facing calls, as game.py uses them: tick with the parent
         # positions from the host, cull on screen, gather + copy only the visible curves
         from volatilespace_b200._lib import K_POS
@@ -346,14 +370,43 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
         for _ in range(reps):
             dev.kepler_tick(KIND_VESSEL, 1.0, k["body_pos"])
             vis = dev.kepler_culling(KIND_VESSEL, n, 10 / 0.01, sb, 0.01)
-            cur = dev.kepler_curves_gather(KIND_VESSEL, vis[:2000], P)
+            cur = dev.kepler_curves_gather(KIND_VESSEL, vis[:2000], P, reuse=True)
         dt = (time.perf_counter() - t0) / reps
         out["kepler4m"]["e2e"] = {
             "object_ticks_per_s": n / dt, "ms_per_tick": dt * 1e3, "visible_objects": int(len(vis)),
             "curves_copied": int(len(cur)), "h2d_bytes_per_tick": 16 * len(k["body_pos"]) + 32,
             "d2h_bytes_per_tick": int(8 * len(vis) + 16 * P * len(cur)),
-            "path": "vsb_kepler_tick + vsb_kepler_culling + vsb_kepler_curves_gather (host arrays)"}
+            "path": "vsb_kepler_tick + vsb_kepler_culling + vsb_kepler_curves_gather (host arrays; "
+                    "results land in the Device's page-locked staging buffers)"}
         dev.kepler_free(KIND_VESSEL)
+        if with_cpu:
+            # CPU port of the same tick (vessel_move + curve_points + curve_move_to,
+            # phys_vessel.py:477-503, phys_shared.py:202-222) on a bounded sample of the objects
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as orc            # cpu_baseline leg only
+            ns = 65536
+            sub = {key: np.ascontiguousarray(k[key][:ns]) for key in
+                   ("a", "b", "f", "ecc", "pea", "n", "dr", "ma", "ea", "ref")}
+            tt = np.linspace(-np.pi, np.pi, P)
+
+            def cpu_tick():
+                orc.vessel_move(1.0, sub["ref"], k["body_pos"], sub["a"], sub["b"], sub["f"], sub["ecc"],
+                                sub["pea"], sub["n"], sub["dr"], sub["ma"], sub["ea"])
+                cur = orc.curves_all(sub["ecc"], sub["a"], sub["b"], sub["pea"], tt)
+                orc.curve_move_to(cur, k["body_pos"], sub["ref"], sub["f"], sub["pea"])
+            cb = {"kind": "port", "unit": "object-ticks/s",
+                  "sample": "%d of the 4194304 objects x %d curve points per tick (O(N): scales "
+                            "linearly), oracle/vs_oracle.c" % (ns, P)}
+            for label, threads in (("1_thread", 1), ("all_cores", len(os.sched_getaffinity(0)))):
+                orc.lib().vso_set_num_threads(threads)
+                cpu_tick()
+                t0 = time.perf_counter()
+                cpu_tick()
+                dtc = time.perf_counter() - t0
+                cb[label] = {"object_ticks_per_s": ns / dtc, "cores": orc.lib().vso_num_threads(),
+                             "ms_per_sample_tick": dtc * 1e3}
+            cb["value"], cb["cores"] = cb["all_cores"]["object_ticks_per_s"], cb["all_cores"]["cores"]
+            out["kepler4m"]["cpu_baseline"] = cb
     except Exception as e:   # e.g. not enough free HBM on a shared device
         out["kepler4m"] = {"error": str(e)[:200]}
 
@@ -438,10 +491,10 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak):
         dev.vessel_events_load(cols[11], cols[12], cols[13], bi, ba, cl, ce, None, cols[9])
         dev.kepler_tick(KIND_VESSEL, 0.0, np.zeros((1, 2)))
         vis = np.arange(0, n1, n1 // 16384, dtype=np.int64)[:16384]
-        seg = dev.vessel_curve_segments(vis, P)
+        seg = dev.vessel_curve_segments(vis, P, reuse=True)
         t0 = time.perf_counter()
         for _ in range(10):
-            seg = dev.vessel_curve_segments(vis, P)
+            seg = dev.vessel_curve_segments(vis, P, reuse=True)
         res["curve_segments_ms_16k_visible_p64"] = (time.perf_counter() - t0) / 10 * 1e3
         res["curve_segments_types"] = np.bincount(seg[3], minlength=4).tolist()
         dev.kepler_free(KIND_VESSEL)
@@ -510,34 +563,59 @@ def _f_rad():
     return F_RAD
 
 
-def roofline(ops, fp64_flops_microbench, clocks, dev, ms_accel, my_pairs, ops_per_pair, kernel):
-    """FP64-pipe roofline of the gravity kernel.  MEASURED_PEAKS.json has no FP64 figure, so the
-    denominator is the pipe's issue peak -- 64 FP64 lanes/SM/clk (what ncu's
-    sm__inst_executed_pipe_fp64 pct_of_peak is normalised to) x SMs x the SM clock observed
-    during the timed region x 2 flop -- or the DFMA-chain microbenchmark of this run if that is
-    higher (it is not: the all-DFMA microbenchmark runs into the power cap)."""
+def measured_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel on a named workload, from
+    the committed ncu captures (profiles/traffic.json: {key: {"bytes": ..., "source": file}})."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except OSError:
+        return None
+
+
+def roofline(pairs_per_s, fp64_flops_microbench, clocks, ms_accel, ops_per_pair, kernel, traffic_key):
+    """FP64 roofline of the gravity kernel.  `achieved` / `frac` use the ALGORITHMIC count of
+    SURVEY 8d (13 flop per directed pair); the share of FP64-pipe issue slots the kernel fills
+    (what ncu's sm__inst_executed_pipe_fp64 reports, the north star's own definition) is the
+    separate key `fp64_pipe_utilisation`.  MEASURED_PEAKS.json has no FP64 figure, so the peak is
+    the pipe's issue peak: 64 FP64 lanes/SM/clk x 148 SMs x the SM clock observed during the
+    timed region x 2 flop (a DFMA per lane per clock)."""
     sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-    sms = 148
-    nominal = sms * 64 * 2 * sm_clock * 1e6
-    peak = max(nominal, fp64_flops_microbench)
+    lanes_per_s = 148 * 64 * sm_clock * 1e6
+    peak = 2 * lanes_per_s
+    tr = measured_traffic(traffic_key)
     return {
-        "bound": "fp64", "achieved": ops * 2 / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
-        "frac": ops * 2 / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this kernel on
-        # this workload at 1 GPU (profiles/r1_gravity_sym1m_t8_ncu_full_summary.txt: 0.683 GB read
-        # + 8.651 GB written, the per-block-pair partial-sum slabs of 1024 bodies; 1.4 ms at HBM
-        # rate = 0.26 % of the launch); the row kernel was captured at 64k bodies only
-        "traffic": 9.334e9 if (kernel == "sym" and my_pairs > 1.0e12) else None,
-        "kernel": "allpairs_sym_kernel" if kernel == "sym" else "allpairs_accel_kernel",
-        "ms_per_launch": ms_accel,
+        "bound": "fp64", "achieved": pairs_per_s * FLOPS_PER_PAIR / 1e12, "peak": peak / 1e12,
+        "unit": "TFLOP/s", "frac": pairs_per_s * FLOPS_PER_PAIR / peak,
+        "flops_per_pair": FLOPS_PER_PAIR,
+        "fp64_pipe_utilisation": pairs_per_s * ops_per_pair / lanes_per_s,
+        "fp64_pipe_instr_per_pair": ops_per_pair,
+        "traffic": None if tr is None else tr["bytes"],
+        "traffic_source": None if tr is None else tr["source"],
+        "kernel": kernel, "ms_per_launch": ms_accel,
         "peak_source": "64 FP64 lanes/SM/clk x 148 SMs x %.0f MHz observed x 2 (issue peak of the "
                        "FP64 pipe; not in MEASURED_PEAKS.json)" % sm_clock,
         "dfma_microbench_tflops": fp64_flops_microbench / 1e12,
-        "frac_of_dfma_microbench": ops * 2 / fp64_flops_microbench,
-        "note": "achieved = %d FP64-pipe instructions per directed pair x pairs/s, each counted "
-                "as one DFMA slot (2 flop)" % ops_per_pair,
-        "flops13_convention_tflops": my_pairs * 13 / (ms_accel * 1e-3) / 1e12,
     }
+
+
+def parity_check(dev, s, rows=64, acc=None):
+    """Accelerations of `rows` sampled target rows of the state now on the device against the
+    CPU oracle (each row: N reference pair evaluations).  Run AFTER the timed region."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc            # checker only
+    from volatilespace_b200._lib import F_ACC, F_POS
+    n = len(s["mass"])
+    pos = dev.get(F_POS)
+    if acc is None:
+        acc = dev.get(F_ACC)
+    pick = np.unique(np.concatenate(([1, n - 1], np.random.default_rng(11).choice(n, rows - 2, replace=False))))
+    worst = 0.0
+    for r in pick:
+        want = orc.allpairs_accel(s["mass"], pos, s["gc"], int(r), int(r) + 1)[0]
+        worst = max(worst, float(np.linalg.norm(acc[r] - want) / np.linalg.norm(want)))
+    return {"rows": int(len(pick)), "max_rel": worst, "tol": 1e-11, "ok": bool(worst < 1e-11),
+            "what": "acceleration of sampled target rows after the timed ticks vs oracle/vs_oracle.c"}
 
 
 def run_b200(args):
@@ -556,12 +634,20 @@ def run_b200(args):
         dist = None
         barrier = lambda: None
 
+    from volatilespace_b200 import _lib
+    from volatilespace_b200._lib import F_ACC
     from volatilespace_b200.device import Device
-    from volatilespace_b200.dist import ShardedAllPairs, ShardedAllPairsSym
+    from volatilespace_b200.dist import ShardedAllPairs, ShardedAllPairsPhysics, ShardedAllPairsSym
     dev = Device(local)
     stream = torch.cuda.ExternalStream(dev.stream_handle(), device="cuda:%d" % local)
     peaks, peaks_src = load_peaks()
     fp64_flops_peak, fp64_ops_peak = dev.fp64_peak()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     s, label = make_workload(args.workload)
     n = len(s["mass"])
@@ -569,7 +655,6 @@ def run_b200(args):
     if args.gravity == "sym":
         sim = ShardedAllPairsSym(dev, s["mass"], s["pos"], s["vel"], s["gc"], rank, world)
     else:
-        dev.set_gravity_mode("rows")
         sim = ShardedAllPairs(dev, s["mass"], s["pos"], s["vel"], s["gc"], rank, world)
     ops_per_pair = OPS_PER_PAIR[args.gravity]
     for _ in range(args.warmup):
@@ -581,17 +666,15 @@ def run_b200(args):
     ms_total = time_ticks(torch, stream, sim.tick, args.steps, barrier)
     launches = dev.kernel_launches() - l0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = max_over_ranks(ms_total) / args.steps
     value = pairs / (ms_step * 1e-3)
 
-    # kernel-only timing of the dominant kernel (accel) for the roofline, CUDA events, rank 0 rows
-    from volatilespace_b200 import _lib
+    # kernel-only timing of the dominant kernel (accel) for the roofline, CUDA events on the
+    # library's stream; max over ranks (each rank runs its share of the pairs)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     reps = max(2, min(args.steps, 4))
     torch.cuda.synchronize()
+    barrier()
     ev[0].record(stream)
     for _ in range(reps):
         if args.gravity == "sym" and world > 1:
@@ -600,30 +683,79 @@ def run_b200(args):
             _lib.check(dev.L.vsb_allpairs_accel_async(dev.h, float(s["gc"])))
     ev[1].record(stream)
     ev[1].synchronize()
-    ms_accel = ev[0].elapsed_time(ev[1]) / reps
-    my_pairs = pairs / world if args.gravity == "sym" else (sim.row1 - sim.row0) * (n - 1)
-    ops = my_pairs * ops_per_pair / (ms_accel * 1e-3)
+    ms_accel = max_over_ranks(ev[0].elapsed_time(ev[1]) / reps)
 
-    # end-to-end through the host-buffer path (pinned numpy buffers)
+    # parity, after the timed region (the bench carries its own proof): the state the
+    # timed ticks left on the device, 64 sampled rows against the oracle; at N > 1 additionally
+    # the all-reduced accelerations against the one-GPU kernel run on rank 0's replica
+    parity = None
+    if not args.no_parity:
+        if args.gravity == "sym" and world > 1:
+            dev.allpairs_sym_partial_async(s["gc"], rank, world)
+            with torch.cuda.stream(sim._stream):
+                dist.all_reduce(sim._acc_t, group=None)
+            sim._stream.synchronize()
+            acc_multi = dev.get(F_ACC)
+        else:
+            if world > 1:
+                dev.set_rows(0, n)          # every row on this rank, for the check only
+            dev.allpairs_accel(s["gc"])
+            acc_multi = dev.get(F_ACC)
+            if world > 1:
+                dev.set_rows(sim.row0, sim.row1)
+        if rank == 0:
+            parity = parity_check(dev, s, 64, acc_multi)
+            if world > 1 and args.gravity == "sym":
+                dev.allpairs_accel(s["gc"])                 # one-GPU kernel, same positions
+                one = dev.get(F_ACC)
+                rel = np.linalg.norm(acc_multi - one, axis=1) / np.maximum(np.linalg.norm(one, axis=1), 1e-300)
+                parity["vs_one_gpu_kernel_max_rel"] = float(rel.max())
+                parity["ok"] = bool(parity["ok"] and rel.max() < 1e-11)
+        barrier()
+
+    # end to end, tick_host: pinned numpy buffers, each rank moves ITS row slice over PCIe
     hp, _k1 = pinned_copy(s["pos"])
     hv, _k2 = pinned_copy(s["vel"])
     hm, _k3 = pinned_copy(s["mass"])
     e2e_steps = max(1, min(args.steps, 3))
-    sim.tick_host(hm, hp, hv)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        sim.tick_host(hm, hp, hv)
-    torch.cuda.synchronize()
-    barrier()
-    dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+
+    def wall(fn):
+        fn()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    dt_host = wall(lambda: sim.tick_host(hm, hp, hv))
     h2d, d2h = sim.host_bytes_per_tick()
-    e2e = {"value": pairs / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": float(dt.item()) * 1e3,
-           "path": "%s.tick_host -> vsb_bodies_set / all-pairs tick / vsb_bodies_get (pinned host "
-                   "buffers, per rank)" % type(sim).__name__}
+    e2e_tick_host = {"value": pairs / dt_host, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": dt_host * 1e3,
+                     "path": "%s.tick_host -> vsb_bodies_set / all-pairs tick / vsb_bodies_get "
+                             "(pinned host buffers, per-rank row slices)" % type(sim).__name__}
+    # end to end through the DROP-IN class (phys_editor.AllPairsPhysics; ShardedAllPairsPhysics at
+    # N > 1): per step the caller's mass / pos / vel go host -> device from the class's page-locked
+    # mirrors, gravity() runs the tick, pos / vel come back into the mirrors
+    e2e = e2e_tick_host
+    if args.gravity == "sym":
+        ph = ShardedAllPairsPhysics(dev, rank, world)
+        ph.load_system({"gc": s["gc"], "rad_mult": s["rad_mult"]}, {"mass": s["mass"], "den": s["den"]},
+                       {"pos": s["pos"], "vel": s["vel"]})
+
+        def dropin_step():
+            inner = ph.inner
+            inner._push("mass", "pos", "vel")
+            ph.gravity()
+            inner.pull("pos", "vel")
+        dt_cls = wall(dropin_step)
+        e2e = {"value": pairs / dt_cls, "unit": UNIT, "h2d_bytes_per_step": 40 * n,
+               "d2h_bytes_per_step": 32 * n, "ms_per_step": dt_cls * 1e3,
+               "path": "phys_editor.AllPairsPhysics%s: mirrors -> device (mass, pos, vel), gravity(), "
+                       "pull(pos, vel); page-locked mirrors, every rank moves all bodies" %
+                       ("" if world == 1 else " via dist.ShardedAllPairsPhysics")}
+        dev.set_gravity_mode("sym")
 
     extra_multi = None
     if world > 1 and not args.no_extra:
@@ -635,6 +767,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
+    kernel_name = "allpairs_sym_kernel" if args.gravity == "sym" else "allpairs_accel_kernel"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -652,13 +785,18 @@ def run_b200(args):
         "steps_per_s": 1e3 / ms_step,
         "clocks": clocks,
         "e2e": e2e,
+        "e2e_tick_host": e2e_tick_host,
         "gpu_launches": int(launches),
-        "roofline": roofline(ops, fp64_flops_peak, clocks, dev, ms_accel, my_pairs, ops_per_pair,
-                             args.gravity),
+        "parity": parity,
+        "sym_sched": _lib.sym_schedule(),
+        "roofline": roofline(pairs / (ms_accel * 1e-3), fp64_flops_peak, clocks, ms_accel, ops_per_pair,
+                             kernel_name, "%s@%s@%dgpu" % (kernel_name, args.workload, world)),
         "peaks_source": peaks_src,
     }
+    if line["sym_sched"] != "resched":
+        sys.stderr.write("bench.py: WARNING: symmetric kernel runs ptxas's schedule: %s\n" % line["sym_sched"])
     if not args.no_extra and world == 1:
-        line["extra"] = extra_workloads(torch, dev, stream, peaks, fp64_ops_peak)
+        line["extra"] = extra_workloads(torch, dev, stream, peaks, fp64_ops_peak, not args.no_cpu)
     if extra_multi is not None:
         line["extra"] = extra_multi
     if not args.no_cpu and world == 1:
@@ -683,6 +821,7 @@ def main():
                     help="all-pairs kernel: symmetric (default) or the shard-invariant row kernel")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -13,7 +13,7 @@ from volatilespace_b200._lib import F_ACC  # noqa: E402
 from volatilespace_b200.device import Device  # noqa: E402
 
 # the shapes compiled into the library (vsb_gravity_sym.cu, VSB_SYM_CASE list)
-SHAPES = os.environ.get("SYM_AB_SHAPES", "16,4,1,1 8,4,1,2 8,8,1,1 4,8,1,3 4,8,2,3 2,8,1,6").split()
+SHAPES = os.environ.get("SYM_AB_SHAPES", "8,4,1,2 8,8,1,1 4,8,1,3 4,8,2,3 2,8,1,6").split()
 sizes = [int(a) for a in sys.argv[1:]] or [65536, 1048576]
 dev = Device(0)
 for n in sizes:

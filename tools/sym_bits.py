@@ -10,7 +10,7 @@ from volatilespace_b200 import synth  # noqa: E402
 from volatilespace_b200._lib import F_ACC  # noqa: E402
 from volatilespace_b200.device import Device  # noqa: E402
 
-SHAPES = "16,4,1,1 8,4,1,2 8,8,1,1 4,8,1,3 4,8,2,3 2,8,1,6 1,8,1,12".split()
+SHAPES = "8,4,1,2 8,8,1,1 4,8,1,3 4,8,2,3 2,8,1,6 1,8,1,12".split()
 dev = Device(0)
 os.environ["VSB_GRAVITY"] = "sym"
 for n in (8192, 20000, 65536, 262144):

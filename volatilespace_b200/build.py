@@ -27,6 +27,7 @@ SOURCES = {
     "vsb_gravity_sym.cu": [],
     # second object of the same source: ptxas's own schedule (reference of the SASS post-pass)
     "vsb_gravity_sym.cu@ptxas": ["-DVSB_SYM_PTXAS_SCHEDULE"],
+    "vsb_gravity_sym_lean.cu": [],
     "vsb_pairs.cu": ["-fmad=false"],
     "vsb_broadphase.cu": ["-fmad=false"],
     "vsb_parents_grid.cu": ["-fmad=false"],

@@ -152,6 +152,7 @@ extern "C" int vsb_ctx_destroy(vsb_ctx *c)
     free_kepler(c->kep[1]);
     vsb_buf_free(c->part);
     vsb_buf_free(c->sym_tab);
+    vsb_buf_free(c->lean_tab);
     vsb_buf_free(c->order);
     vsb_buf_free(c->sorted);
     vsb_buf_free(c->pgrid);
@@ -192,14 +193,25 @@ extern "C" int vsb_ctx_kernel_launches(vsb_ctx *c, int64_t *out)
 extern "C" int vsb_host_register(void *ptr, int64_t bytes)
 {
     VSB_CHECK(ptr && bytes > 0, VSB_ERR_ARG, "vsb_host_register: bad argument");
-    VSB_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        // pinning is optional: report it, but leave no pending error for the next launch check
+        cudaGetLastError();
+        vsb_set_error("vsb_host_register: %s", cudaGetErrorString(e));
+        return VSB_ERR_CUDA;
+    }
     return VSB_OK;
 }
 
 extern "C" int vsb_host_unregister(void *ptr)
 {
     VSB_CHECK(ptr, VSB_ERR_ARG, "vsb_host_unregister: null pointer");
-    VSB_CUDA(cudaHostUnregister(ptr));
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        vsb_set_error("vsb_host_unregister: %s", cudaGetErrorString(e));
+        return VSB_ERR_CUDA;
+    }
     return VSB_OK;
 }
 

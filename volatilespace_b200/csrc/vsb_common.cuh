@@ -95,6 +95,10 @@ struct vsb_ctx {
     vsb_buf sym_tab;     // symmetric kernel: task table + Q-slab index
     int64_t sym_tasks_n = -1, sym_qf_off = 0, sym_own_off = 0, sym_ownlist_off = 0;
     int sym_world = 0, sym_rank = 0, sym_ntasks = 0, sym_nslots = 0, sym_S = 0;
+    // slab-free symmetric kernel (vsb_gravity_sym_lean.cu): ticket list | expectation table | counters
+    vsb_buf lean_tab;
+    int64_t lean_tasks_n = -1, lean_exp_off = 0, lean_ctl_off = 0, lean_ctl_bytes = 0;
+    int lean_world = 0, lean_rank = 0, lean_ntasks = 0, lean_S = 0, lean_chunk = 0;
     int soc_rounds = 0;     // fixed-point rounds of the last simplified_orbit_coi (diagnostics)
     int gravity_mode = -1;  // -1: auto, 0: row kernel (vsb_gravity.cu), 1: symmetric (vsb_gravity_sym.cu)
     vsb_buf order;       // int64 order (descending mass) + rank
@@ -271,6 +275,8 @@ int vsb_launch_dfma_peak(vsb_ctx *c, int iters, int blocks, float *ms_out);
 int vsb_allpairs_chunks(int64_t n, int64_t *chunk_out);
 // symmetric kernel (vsb_gravity_sym.cu)
 int vsb_launch_allpairs_sym(vsb_ctx *c, double gc, int rank, int world, int integrate);
+// the same pairs without partial-sum slabs (vsb_gravity_sym_lean.cu): large body counts
+int vsb_launch_allpairs_sym_lean(vsb_ctx *c, double gc, int rank, int world, int integrate);
 // the same kernels with ptxas's own instruction schedule (VSB_SYM_SCHED=ptxas; see vsb_gravity_sym.cu)
 int vsb_launch_allpairs_sym_ptxas(vsb_ctx *c, double gc, int rank, int world, int integrate);
 // pair predicates (vsb_pairs.cu)

@@ -279,6 +279,16 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
 #endif
     const int64_t n = c->n, npad = c->npad;
     if (n <= 0) return VSB_OK;
+    // The slabs take N^2/(2S) * 16 B (8.6 GB at 1 M bodies, 34 GB at 2 M with S = 1024).  Above
+    // VSB_SYM_SLAB_GB (default 16) of slab memory, or with VSB_SYM_MODE=lean, the slab-free kernel
+    // of vsb_gravity_sym_lean.cu runs instead: ~4 % slower, 48 MB of scratch, no size limit.
+    {
+        const char *mode = getenv("VSB_SYM_MODE"), *gb = getenv("VSB_SYM_SLAB_GB");
+        const double budget = (gb ? atof(gb) : 16.0) * 1073741824.0;
+        const double slab_bytes = (double)npad * (double)npad / 2048.0 * 16.0;
+        if ((mode && mode[0] == 'l') || (!(mode && mode[0] == 's') && slab_bytes > budget))
+            return vsb_launch_allpairs_sym_lean(c, gc, rank, world, integrate);
+    }
     // Kernel shape (warps, targets per lane, hand-over, CTAs per SM).  8 targets per lane halve
     // the shared-memory and loop instructions per pair (profiles/README.md: 2.6 % at 1 M bodies);
     // the macro-block S sets the task grain (small S: better balance at small N) against the
@@ -288,7 +298,6 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
     int warps = 4, tpl = 8, su = 2, mb = 3;
     if (npad <= 98304) warps = 2, su = 1, mb = 6;
     if (npad <= 32768) warps = 1, su = 1, mb = 12;
-    if (npad > 2097152) warps = 8, su = 1, mb = 1;
     if (const char *env = getenv("VSB_SYM_SHAPE")) {
         mb = 0;
         sscanf(env, "%d,%d,%d,%d", &warps, &tpl, &su, &mb);

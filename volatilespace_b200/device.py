@@ -4,6 +4,7 @@ Nothing here computes physics; every method forwards numpy buffers to
 libvsb200.so (see include/vsb200.h) and raises VsbError on failure.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -36,6 +37,29 @@ def scratch_device():
     return _scratch
 
 
+def _unregister(L, address):
+    try:
+        L.vsb_host_unregister(C.c_void_p(address))
+    except Exception:       # interpreter shutdown
+        pass
+
+
+def pinned_empty(shape, dtype=np.float64, L=None):
+    """np.empty whose memory is page-locked with vsb_host_register (cudaHostRegister), so that the
+    library's synchronous copies into / out of it run at PCIe rate instead of through the driver's
+    pageable staging (~5 GB/s).  The registration is dropped when the buffer is garbage collected.
+    Falls back to a plain array when the registration is refused (no device, locked-memory limit):
+    pinning is an optimisation, never a requirement."""
+    L = L or _lib.load()
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    raw = np.empty(max(nbytes, 1) + 64, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 64
+    if nbytes >= 65536 and L.vsb_host_register(C.c_void_p(raw.ctypes.data), raw.nbytes) == _lib.VSB_OK:
+        weakref.finalize(raw, _unregister, L, raw.ctypes.data)
+    return raw[off:off + nbytes].view(dtype).reshape(shape)
+
+
 class Device:
     def __init__(self, device=0):
         self.L = _lib.load()
@@ -43,6 +67,19 @@ class Device:
         h = C.c_void_p()
         check(self.L.vsb_ctx_create(self.index, C.byref(h)))
         self.h = h
+        self._pool = {}
+
+    def staging(self, name, shape, dtype=np.float64):
+        """Grow-only page-locked result buffer `name` of this Device, viewed as `shape`.  The view
+        is valid until the next call that asks for the same name (the `reuse=True` results below:
+        the callers of the reference consume them within the frame, game.py:1248-1296)."""
+        shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+        count = int(np.prod(shape, dtype=np.int64))
+        buf = self._pool.get(name)
+        if buf is None or buf.dtype != np.dtype(dtype) or buf.size < count:
+            buf = pinned_empty(count + count // 4 + 16, dtype, self.L)
+            self._pool[name] = buf
+        return buf[:count].reshape(shape)
 
     def close(self):
         if getattr(self, "h", None):
@@ -502,7 +539,7 @@ class Device:
     def kepler_culling(self, kind, n, radius, screen_bounds, zoom):
         """`radius`: per-object array, None (zero), or one number for every object."""
         sb = f64(screen_bounds)
-        idx = np.empty(n, dtype=np.int64)
+        idx = self.staging("cull_idx", n, np.int64)
         cnt = C.c_int64()
         if radius is not None and np.ndim(radius) == 0:
             check(self.L.vsb_kepler_culling_uniform(self.h, kind, float(radius), ptr(sb),
@@ -516,27 +553,34 @@ class Device:
     def kepler_visible_orbits(self, kind, n, ref_visible, ref_coi, size, zoom, screen_x):
         rv = np.ascontiguousarray(ref_visible, dtype=np.uint8)
         rc, size = f64(ref_coi), f64(size)
-        idx = np.empty(n, dtype=np.int64)
+        idx = self.staging("cull_idx", n, np.int64)
         cnt = C.c_int64()
         check(self.L.vsb_kepler_visible_orbits(self.h, kind, len(rv), ptr(rv), ptr(rc), ptr(size),
                                                float(zoom), float(screen_x), ptr(idx),
                                                C.byref(cnt)))
         return idx[:cnt.value].copy()
 
-    def kepler_curves_gather(self, kind, idx, P):
+    def kepler_curves_gather(self, kind, idx, P, reuse=False):
+        """(len(idx), P, 2) moved curves of the listed objects.  reuse=True: the result is a view
+        of this Device's page-locked staging buffer (valid until the next gather), which lets the
+        copy run at PCIe rate and skips a fresh 16 P len(idx)-byte allocation per frame."""
         idx = i64(idx)
-        out = np.empty((len(idx), int(P), 2))
+        shape = (len(idx), int(P), 2)
+        out = self.staging("gather", shape) if reuse else np.empty(shape)
         check(self.L.vsb_kepler_curves_gather(self.h, kind, ptr(idx), len(idx), ptr(out)))
         return out
 
-    def vessel_curve_segments(self, idx, P):
+    def vessel_curve_segments(self, idx, P, reuse=False):
         """curve_segments for the listed vessels on the resident state -> (light, dark,
-        first_intersect, intersect_type, intersect_time, select_range), one row per index."""
+        first_intersect, intersect_type, intersect_time, select_range), one row per index.
+        reuse=True: results are views of page-locked staging buffers (valid until the next call)."""
         idx = i64(idx)
         m = len(idx)
-        light, dark = np.empty((m, int(P), 2)), np.empty((m, int(P), 2))
-        first, rng = np.empty((m, 2)), np.empty((m, 2))
-        itype, itime = np.empty(m, dtype=np.int32), np.empty(m)
+        new = (lambda name, shape, dt=np.float64: self.staging("seg_" + name, shape, dt)) if reuse \
+            else (lambda name, shape, dt=np.float64: np.empty(shape, dtype=dt))
+        light, dark = new("light", (m, int(P), 2)), new("dark", (m, int(P), 2))
+        first, rng = new("first", (m, 2)), new("range", (m, 2))
+        itype, itime = new("itype", m, np.int32), new("itime", m)
         check(self.L.vsb_vessel_curve_segments(self.h, ptr(idx), m, ptr(light), ptr(dark), ptr(first),
                                                ptr(itype), ptr(itime), ptr(rng)))
         return light, dark, first, itype, itime, rng

@@ -9,7 +9,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import KIND_BODY, K_EA, K_MA, K_POS
-from .device import Device, default_device
+from .device import Device, default_device, pinned_empty
 from .phys_editor import STELLAR_CLASSES, body_radius, thermal_consts
 from .synth import calc_orb
 
@@ -56,12 +56,15 @@ class Physics:
         self.a = np.array(body_orb_data["a"], dtype=np.float64)
         self.ecc = np.array(body_orb_data["ecc"], dtype=np.float64)
         self.pea = np.array(body_orb_data["pe_arg"], dtype=np.float64)
-        self.ma = np.array(body_orb_data["ma"], dtype=np.float64)
+        self.ma = pinned_empty(len(self.mass))      # per-tick results in page-locked memory
+        self.ma[:] = body_orb_data["ma"]
         self.ref = np.array(body_orb_data["ref"], dtype=np.int64)
         self.dr = np.array(body_orb_data["dir"], dtype=np.float64)
         self.n_bodies = len(self.mass)
-        self.pos = np.zeros((self.n_bodies, 2))
-        self.ea = np.zeros(self.n_bodies)
+        self.pos = pinned_empty((self.n_bodies, 2))
+        self.pos[:] = 0.0
+        self.ea = pinned_empty(self.n_bodies)
+        self.ea[:] = 0.0
 
     def _upload(self):
         self.dev.kepler_load(KIND_BODY, self.curve_points, self.a, self.b, self.f, self.ecc,
@@ -120,7 +123,7 @@ class Physics:
         self.dev.kepler_curves(KIND_BODY)
         if visible is None:
             return self.dev.kepler_curves_get(KIND_BODY, 0, self.n_bodies, self.curve_points)
-        got = self.dev.kepler_curves_gather(KIND_BODY, visible, self.curve_points)
+        got = self.dev.kepler_curves_gather(KIND_BODY, visible, self.curve_points, reuse=True)
         return {int(i): got[k] for k, i in enumerate(visible)}
 
     # phys_body.py:201-218

@@ -20,7 +20,7 @@ import numpy as np
 from . import _lib
 from ._lib import (F_ACC, F_COI, F_DEN, F_ECC_V, F_FOCUS, F_MASS, F_PARENTS, F_PERIAPSIS_ARG,
                    F_POS, F_RAD, F_REL_VEL, F_SEMI_MAJOR, F_SEMI_MINOR, F_VEL)
-from .device import Device, default_device, scratch_device
+from .device import Device, default_device, pinned_empty, scratch_device
 
 _FIELDS = {"mass": F_MASS, "den": F_DEN, "rad": F_RAD, "coi": F_COI, "pos": F_POS, "vel": F_VEL,
            "rel_vel": F_REL_VEL, "parents": F_PARENTS, "focus": F_FOCUS, "ecc_v": F_ECC_V,
@@ -156,13 +156,12 @@ class _DeviceBodies:
         self._stale = set()        # host mirrors older than the device copy
 
     def _alloc_host(self, n):
+        """Host mirrors; from 8192 rows up they are page-locked (vsb_host_register), so that
+        pull() / _push() move them at PCIe rate."""
         for name in _FIELDS:
-            if name == "parents":
-                arr = np.zeros(n, dtype=np.int64)
-            elif name in _WIDE:
-                arr = np.zeros((n, 2))
-            else:
-                arr = np.zeros(n)
+            shape = (n, 2) if name in _WIDE else (n,)
+            arr = pinned_empty(shape, np.int64 if name == "parents" else np.float64, self.dev.L)
+            arr[...] = 0
             setattr(self, name, arr)
 
     def _push(self, *names):
@@ -173,9 +172,13 @@ class _DeviceBodies:
     def pull(self, *names):
         """Refresh host mirrors in place from the device (one copy for several fields)."""
         names = names or tuple(self._stale)
-        if len(names) > 1:
+        # small systems: one packed copy for all fields; large ones: straight into the page-locked
+        # mirrors, field by field (no second pass over the data on the host)
+        if len(names) > 1 and len(self.mass) <= 65536:
             n = len(self.mass)
-            buf = self.dev.get_many([_FIELDS[k] for k in names])
+            words = sum(n * (2 if k in _WIDE else 1) for k in names)
+            buf = self.dev.get_many([_FIELDS[k] for k in names],
+                                    out=self.dev.staging("pull", words))
             off = 0
             for k in names:
                 w = 2 if k in _WIDE else 1

@@ -11,7 +11,7 @@ the one-vessel-per-frame helpers `selected`, `rotate`, `predict_next_orbit` are 
 import numpy as np
 
 from ._lib import KIND_VESSEL, K_EA, K_MA, K_POS
-from .device import Device, default_device
+from .device import Device, default_device, pinned_empty
 from . import vessel_draw
 from .synth import calc_orb
 
@@ -54,17 +54,22 @@ class Physics:
         self.a = np.array(vessel_orb_data["a"], dtype=np.float64)
         self.ecc = np.array(vessel_orb_data["ecc"], dtype=np.float64)
         self.pea = np.array(vessel_orb_data["pe_arg"], dtype=np.float64)
-        self.ma = np.array(vessel_orb_data["ma"], dtype=np.float64)
         self.ref = np.array(vessel_orb_data["ref"], dtype=np.int64)
         self.dr = np.array(vessel_orb_data["dir"], dtype=np.float64)
         self.n_vessels = len(self.a)
+        # the per-tick results (pos, ma, ea, refreshed in place by move()) live in page-locked
+        # memory: their device -> host copies then run at PCIe rate
+        self.ma = pinned_empty(self.n_vessels)
+        self.ma[:] = vessel_orb_data["ma"]
         zeros = np.zeros(self.n_vessels)
         self.rot_angle = np.array((vessel_data or {}).get("rot_angle", zeros), dtype=np.float64)  # :216-218
         self.rot_acc = np.array((vessel_data or {}).get("rot_acc", zeros), dtype=np.float64)
         self.rot_speed = np.zeros(self.n_vessels)
         self.intersect_time = np.zeros(self.n_vessels)
-        self.pos = np.zeros((self.n_vessels, 2))
-        self.ea = np.array(vessel_orb_data.get("ea", np.zeros(self.n_vessels)), dtype=np.float64)
+        self.pos = pinned_empty((self.n_vessels, 2))
+        self.pos[:] = 0.0
+        self.ea = pinned_empty(self.n_vessels)
+        self.ea[:] = vessel_orb_data.get("ea", 0.0)
         self._hold = np.zeros(self.n_vessels, dtype=np.uint8)
         self.prev_ea = np.array(self.ea)
         nan = lambda w: np.full((self.n_vessels, w), np.nan)
@@ -234,7 +239,7 @@ class Physics:
         self.dev.kepler_curves(KIND_VESSEL)
         if visible is None:
             return self.dev.kepler_curves_get(KIND_VESSEL, 0, self.n_vessels, self.curve_points)
-        got = self.dev.kepler_curves_gather(KIND_VESSEL, visible, self.curve_points)
+        got = self.dev.kepler_curves_gather(KIND_VESSEL, visible, self.curve_points, reuse=True)
         return {int(i): got[k] for k, i in enumerate(visible)}
 
     # phys_vessel.py:258-273
@@ -263,7 +268,7 @@ class Physics:
             self.dev.vessel_events_load(self.pe_d, self.ap_d, self.period, self.body_impact,
                                         self.body_enter_atm, self.coi_leave, self.coi_enter,
                                         self._hold, self.prev_ea)
-        light, dark, first, itype, itime, srange = self.dev.vessel_curve_segments(vis, P)
+        light, dark, first, itype, itime, srange = self.dev.vessel_curve_segments(vis, P, reuse=True)
         first_intersect = np.full((n, 2), np.nan)
         select_range = np.full((n, 2), np.nan)
         intersect_type = np.zeros(n, dtype=np.int64)
