@@ -94,7 +94,7 @@ struct vsb_ctx {
     vsb_buf part;        // all-pairs partial sums [C][rows][2] (or the symmetric kernel's slabs)
     vsb_buf sym_tab;     // symmetric kernel: task table + Q-slab index
     int64_t sym_tasks_n = -1, sym_qf_off = 0, sym_own_off = 0, sym_ownlist_off = 0;
-    int sym_world = 0, sym_rank = 0, sym_ntasks = 0, sym_nslots = 0, sym_S = 0;
+    int sym_world = 0, sym_rank = 0, sym_ntasks = 0, sym_nslots = 0, sym_S = 0, sym_tail = -1;
     // slab-free symmetric kernel (vsb_gravity_sym_lean.cu): ticket list | expectation table | counters
     vsb_buf lean_tab;
     int64_t lean_tasks_n = -1, lean_exp_off = 0, lean_ctl_off = 0, lean_ctl_bytes = 0;

@@ -313,8 +313,11 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
     int64_t want_tasks = (int64_t)c->sm_count * 32 * world;
     int chunk = (int)(pairs / want_tasks);
     if (chunk < 1) chunk = 1;
-    // host-side task table (cached per n / world / rank)
-    if (c->sym_tasks_n != n || c->sym_world != world || c->sym_rank != rank || c->sym_S != S) {
+    // host-side task table (cached per n / world / rank / shape / tail setting)
+    const char *tail_env = getenv("VSB_SYM_TAIL");
+    const int tail_split = tail_env ? atoi(tail_env) : 8;
+    if (c->sym_tasks_n != n || c->sym_world != world || c->sym_rank != rank || c->sym_S != S ||
+        c->sym_tail != tail_split) {
         struct T { sym_task t; int cost; };
         T *all = (T *)malloc(sizeof(T) * (size_t)(pairs + M));
         int *qfirst = (int *)malloc(sizeof(int) * (size_t)(M + 1));
@@ -325,17 +328,57 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
             free(mine);
             VSB_CHECK(false, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
         }
-        int nt = 0, slot = 0;
-        for (int q = 0; q < M; ++q) {
-            qfirst[q] = slot;
+        // Tail: the tasks that would run in the last two waves of the resident CTAs -- the last
+        // 2 x slots x world entries of the cost-sorted list -- are cut into VSB_SYM_TAIL pieces
+        // (default 8, 0 = off), so that the ranks and the SMs finish within a small piece of each
+        // other.  A cut task keeps its P-side slabs; each piece gets its own Q-side slab.
+        unsigned char *cut = (unsigned char *)calloc((size_t)(pairs + M), 1);
+        int nt = 0;
+        for (int q = 0; q < M; ++q)
             for (int p0 = 0; p0 <= q; p0 += chunk) {
-                int p1 = p0 + chunk > q + 1 ? q + 1 : p0 + chunk;
-                all[nt].t = sym_task{q, p0, p1, slot++};
+                const int p1 = p0 + chunk > q + 1 ? q + 1 : p0 + chunk;
+                all[nt].t = sym_task{q, p0, p1, 0};
                 all[nt].cost = 2 * (p1 - p0) - (p1 == q + 1 ? 1 : 0);
                 ++nt;
             }
+        if (cut && tail_split > 1 && chunk >= 2) {
+            int64_t left = 2 * (int64_t)c->sm_count * mb * world;
+            if (left > nt / 2) left = nt / 2;
+            for (int cst = 0; cst <= 2 * chunk && left > 0; ++cst)      // cheapest first = run last
+                for (int i = nt - 1; i >= 0 && left > 0; --i)
+                    if (all[i].cost == cst) {
+                        cut[i] = 1;
+                        --left;
+                    }
         }
+        const int nplain = nt;
+        T *plain = (T *)malloc(sizeof(T) * (size_t)(nplain + 1));
+        if (!plain) {
+            free(cut);
+            free(all);
+            free(qfirst);
+            free(mine);
+            VSB_CHECK(false, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
+        }
+        memcpy(plain, all, sizeof(T) * (size_t)nplain);
+        nt = 0;
+        int slot = 0, last_q = -1;
+        for (int i = 0; i < nplain; ++i) {
+            const int q = plain[i].t.q, p0 = plain[i].t.p0, p1 = plain[i].t.p1;
+            while (last_q < q) qfirst[++last_q] = slot;
+            const int piece = (cut && cut[i] && p1 - p0 >= 2) ? (p1 - p0 + tail_split - 1) / tail_split
+                                                              : p1 - p0;
+            for (int a0 = p0; a0 < p1; a0 += piece) {
+                const int a1 = a0 + piece > p1 ? p1 : a0 + piece;
+                all[nt].t = sym_task{q, a0, a1, slot++};
+                all[nt].cost = 2 * (a1 - a0) - (a1 == q + 1 ? 1 : 0);
+                ++nt;
+            }
+        }
+        while (last_q < M - 1) qfirst[++last_q] = slot;
         qfirst[M] = slot;
+        free(plain);
+        free(cut);
         // descending cost (stable counting order), then deal round-robin to ranks
         int maxc = 2 * chunk;
         int nm = 0, dealt = 0;
@@ -411,6 +454,7 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
         VSB_TRY(rc);
         VSB_CUDA(ce);
         c->sym_tasks_n = n;
+        c->sym_tail = tail_split;
         c->sym_S = S;
         c->sym_world = world;
         c->sym_rank = rank;
