@@ -327,11 +327,16 @@ int vsb_host_vessel_points(vsb_ctx *ctx, int64_t nv, int64_t nb, const double *v
                            int64_t left_coi_prev_ref, int only_enter_coi, int64_t steps_limit,
                            double *body_impact, double *body_enter_atm, double *coi_leave,
                            double *coi_enter);
-/* Diagnostics of the COI-entry march used by the two calls above.  sequential != 0 selects the
- * reference's own serial loop, one thread per pair (cross-check of the parallel march; the
- * results must be bit-identical).  out3 = chunks marched, chunks re-run after a failed
- * speculation, pairs that fell back to the serial loop -- of the last call. */
-int vsb_set_march_mode(vsb_ctx *ctx, int sequential);
+/* Modes of the COI-entry march used by the two calls above.  mode bit 0: the reference's own
+ * serial loop, one thread per pair (cross-check of the parallel march; the results must be
+ * bit-identical).  mode bit 1: "exact trigonometry" -- the march's sin / cos are evaluated in
+ * double-double arithmetic and rounded to nearest (~20x their normal cost), which reproduces the
+ * reference's libm on the ill-conditioned marches of high-eccentricity ellipses where CUDA's
+ * 1-2 ulp routines decide differently.  Default 2 (parallel march, exact
+ * trigonometry); 0 is the fast variant.
+ * vsb_march_stats: out4 = chunks marched, chunks re-run after a failed speculation, pairs that
+ * fell back to the serial loop, pairs refused (> 2^32 steps) -- of the last call. */
+int vsb_set_march_mode(vsb_ctx *ctx, int mode);
 /* The closed form the parallel march uses for the reference's running sums (`t += dt`,
  * `ma += dr * n * dt`, orbit_intersect.py:108-121,170): xs[i] = x_{ks[i]} of
  * x_k = fl(x_{k-1} + c), x_0 = x0, with exactly the bits of the serial loop.  K_out = kmax, or

@@ -43,6 +43,7 @@ def lib():
     sigs = {
         "vso_num_threads": (C.c_int, []),
         "vso_set_num_threads": (None, [C.c_int]),
+        "vso_set_exact_trig": (None, [C.c_int]),
         "vso_find_parents": (None, [i64, _i64p, _f64p, _f64p, _i64p]),
         "vso_gravity_one": (None, [i64, i64, _f64p, f64, f64, f64, _f64p]),
         "vso_gravity_ref": (None, [i64, _i64p, _f64p, _f64p, f64, _f64p, _f64p, _f64p, _i64p]),

@@ -28,6 +28,16 @@
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
+
+/* "Exact trigonometry" experiment: sin / cos of the COI-entry march
+ * evaluated in double-double arithmetic and rounded to nearest -- the SAME routine the device path
+ * uses in its exact mode (generated header, plain C) -- instead of libm's.  Off by default: the
+ * oracle then uses the reference's own libm and matches the live fixtures bit for bit. */
+#include "../volatilespace_b200/csrc/vsb_ddtrig.h"
+static int vso_exact_trig = 0;
+void vso_set_exact_trig(int on) { vso_exact_trig = on; }
+static double t_sin(double x) { return vso_exact_trig ? vsb_dd_sin(x) : sin(x); }
+static double t_cos(double x) { return vso_exact_trig ? vsb_dd_cos(x) : cos(x); }
 #endif
 
 #define VSO_PI 3.141592653589793 /* math.pi == np.pi */
@@ -306,7 +316,7 @@ double vso_solve_kepler_ell(double ecc, double ma, double tol)
         double al = tol / 1e7, be = tol / 0.3, fp = 2.7 * mr, fpp = 0.301, f = 0.154;
         for (int i = 0; i < 1000; ++i) { /* midpoint update is outside the loop (F8b) */
             if ((fpp - fp) <= (al + be * f)) break;
-            if ((f - ecc * sin(f) - mr) > 0) fpp = f;
+            if ((f - ecc * t_sin(f) - mr) > 0) fpp = f;
             else fp = f;
         }
         f = 0.5 * (fp + fpp);
@@ -316,8 +326,8 @@ double vso_solve_kepler_ell(double ecc, double ma, double tol)
     double tol2s = 2 * tol / (ecc + 2.2e-16);
     double eapp = mr + 0.999999 * mr * (VSO_PI - mr) /
                            (2. * mr + ecc - VSO_PI + 2.4674011002723395 / (ecc + 2.2e-16));
-    double fpp = ecc * sin(eapp);
-    double fppp = ecc * cos(eapp);
+    double fpp = ecc * t_sin(eapp);
+    double fppp = ecc * t_cos(eapp);
     double fp = 1 - fppp;
     double f = eapp - fpp - mr;
     double delta = -f / fp;
@@ -328,8 +338,8 @@ double vso_solve_kepler_ell(double ecc, double ma, double tol)
     for (int i = 0; i < 30; ++i) {
         if (delta * delta < fp * tol2s) break;
         eapp = eapp + delta;
-        fp = 1 - ecc * cos(eapp);
-        delta = (mr - eapp + ecc * sin(eapp)) / fp;
+        fp = 1 - ecc * t_cos(eapp);
+        delta = (mr - eapp + ecc * t_sin(eapp)) / fp;
     }
     eapp = eapp + delta;
     return ma + flip * (mr - eapp);
@@ -783,10 +793,10 @@ static void oi_orb2xy(double a, double b, double f, double ecc, double pea, doub
                       double *y)
 { /* orbit_intersect.py:95-105 */
     double xn, yn;
-    if (ecc < 1) { xn = a * cos(ea) - f; yn = b * sin(ea); }
+    if (ecc < 1) { xn = a * t_cos(ea) - f; yn = b * t_sin(ea); }
     else { xn = a * cosh(ea) - f; yn = b * sinh(ea); }
-    *x = xn * cos(pea - VSO_PI) - yn * sin(pea - VSO_PI);
-    *y = xn * sin(pea - VSO_PI) + yn * cos(pea - VSO_PI);
+    *x = xn * t_cos(pea - VSO_PI) - yn * t_sin(pea - VSO_PI);
+    *y = xn * t_sin(pea - VSO_PI) + yn * t_cos(pea - VSO_PI);
 }
 
 static void oi_move(double *ma, double ecc, double dr, double n, double *prev_ea, double dt,

@@ -259,6 +259,38 @@ def test_allpairs_4m_bodies_on_one_gpu(dev, oracle):
     dev.bodies_resize(0)
 
 
+def test_allpairs_coincident_bodies_behaviour_is_pinned(dev, oracle, monkeypatch):
+    """Two DISTINCT bodies at the same position are outside the model: the reference's gravity_one
+    divides by zero (numba raises ZeroDivisionError, phys_editor.py:54-55).  What the kernels do is
+    pinned here so that it cannot drift silently: the i == j mask (r^2 == 0 -> exact zero) is
+    applied where a CTA meets its own rows / on the diagonal macro-block, so a coincident pair
+    inside one block contributes nothing; a coincident pair in DIFFERENT blocks is not masked and
+    both bodies' sums become non-finite -- in both kernels, and never a wrong finite number.
+    Every other body keeps a finite sum that matches the oracle."""
+    from volatilespace_b200._lib import F_ACC
+    n = 3000
+    mass, pos, vel = small_cloud(n, 31, extent=2.0e4)
+    pos[11] = pos[10]                       # same block in both kernels
+    pos[2900] = pos[700]                    # different blocks
+    dev.upload_bodies(mass, pos, vel)
+    good = np.setdiff1d(np.arange(n), [10, 11, 700, 2900])
+    sep = pos.copy()
+    sep[11] += 1.0e9                        # the oracle cannot take r = 0: move the twins far away
+    sep[2900] += 1.0e9
+    want = oracle.allpairs_accel(mass, sep, 1.0)
+    for mode in ("rows", "sym"):
+        monkeypatch.setenv("VSB_GRAVITY", mode)
+        dev.allpairs_accel(1.0)
+        acc = dev.get(F_ACC)
+        bad = np.flatnonzero(~np.isfinite(acc).all(axis=1))
+        assert set(bad.tolist()) == {700, 2900}, mode
+        assert np.all(np.isfinite(acc[[10, 11]])), mode
+        # the twins' pull on everybody else is there twice, the far-away copies' is negligible
+        twin = lambda j: mass[j, None] * (pos[j] - pos[good]) / np.linalg.norm(pos[j] - pos[good], axis=1)[:, None]**3
+        expect = want[good] + twin(11) + twin(2900)
+        assert row_rel_err(acc[good], expect) < 1e-9, mode
+
+
 def test_allpairs_sym_multi_rank_partials_sum_to_full(dev, monkeypatch):
     """Multi-GPU form of the symmetric kernel, ranks emulated by separate contexts on one
     GPU: the ranks' partial accelerations add up to the single-rank result."""

@@ -467,16 +467,55 @@ def test_vessel_points_golden(dev):
     chunks, rerun, serial, refused = dev.march_stats()
     assert serial == 0 and chunks > 0
     assert rerun <= 0.02 * chunks            # speculation on the hyperbolic chains mostly holds
-    _assert_points(bi, g["body_impact"], "body_impact", nan_slack=1, frac=0.5)
-    _assert_points(ba, g["body_enter_atm"], "body_enter_atm", nan_slack=1, frac=0.5)
-    _assert_points(cl, g["coi_leave"], "coi_leave", nan_slack=2, frac=0.5)
-    rob = _robust(g["vessel12"]) & ~(np.isnan(cl[:, 0]) != np.isnan(g["coi_leave"][:, 0]))
+    # The EXACT sets of fixture vessels that differ from the live reference (measured on the B200,
+    # tools/points_diag.py, profiles/r2_points160_diag.txt): a change in any of them is a
+    # regression -- or an improvement that must be written down here.
+    #   found / not-found flips: the sign of a rounding residue under the reference's Ferrari
+    #   sqrt (quartic_solver.py:76-80) -- one vessel, coi_leave;
+    #   coi_enter (the COI-entry march): NONE with the default exact trigonometry (sin / cos in
+    #   double-double arithmetic rounded to nearest, as the reference's libm returns them); with
+    #   CUDA's 1-2 ulp sin / cos (set_march_mode(exact_trig=False)) five of the seven
+    #   high-eccentricity ellipses (0.8 <= e < 1) with ill-conditioned marches (see _robust) differ.
+    ill = ~_robust(g["vessel12"])
     want = g["coi_enter"]
-    assert (~np.isnan(want[rob, 0])).sum() >= 12
-    assert np.array_equal(ce[rob, 0], want[rob, 0], equal_nan=True)           # entered body
-    _assert_points(ce[rob], want[rob], "coi_enter", frac=0.85)
-    ill = ~rob & ~np.isnan(want[:, 0])
-    assert (ce[ill, 0] == want[ill, 0]).sum() >= 1       # and even there most still agree
+
+    def compare(results, flips_want, off_want, label):
+        report = []
+        for name, got in zip(("body_impact", "body_enter_atm", "coi_leave", "coi_enter"), results):
+            ref = g[name]
+            flips = set(np.flatnonzero((np.isnan(got) != np.isnan(ref)).any(axis=1)).tolist())
+            ok = ~np.isnan(ref) & ~np.isnan(got)
+            rel = np.zeros_like(ref)
+            rel[ok] = np.abs(got[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1.0)
+            worst = rel.max(axis=1)
+            off = set(np.flatnonzero(worst > 2e-7).tolist())
+            loose = int((worst > 1e-11).sum())
+            keep = np.array([i not in off for i in range(len(worst))])
+            report.append("%s: %d NaN flips %s, %d beyond 2e-7 %s, %d beyond 1e-11, max %.1e elsewhere" % (
+                name, len(flips), sorted(flips), len(off), sorted(off), loose, worst[keep].max()))
+            assert flips == flips_want[name], report[-1]
+            assert off == off_want[name], report[-1]
+            # everything else: the biquadratic's sqrt(rounding residue) bounds the agreement at ~1e-8
+            assert worst[keep].max() < 2e-8, report[-1]
+            assert loose <= 12, report[-1]
+        print("\nN2 orbit points vs the live reference (160 vessels), %s:\n  " % label + "\n  ".join(report))
+
+    none = {"body_impact": set(), "body_enter_atm": set(), "coi_leave": set(), "coi_enter": set()}
+    compare((bi, ba, cl, ce), dict(none, coi_leave={79}), none, "exact trigonometry (default)")
+    assert np.array_equal(ce[:, 0], want[:, 0], equal_nan=True)           # entered body, every vessel
+    assert (~np.isnan(want[~ill, 0])).sum() >= 12 and (~np.isnan(want[ill, 0])).sum() == 5
+    # the fast variant: CUDA's own sin / cos
+    dev.set_march_mode(False, exact_trig=False)
+    try:
+        fast = _points_inputs(g)
+        dev.host_vessel_points(g["vessel12"], g["v_ref"], g["body12"], g["body_ref"], *fast,
+                               steps_limit=int(g["steps_limit"]))
+    finally:
+        dev.set_march_mode(False, exact_trig=True)
+    compare(fast, dict(none, coi_leave={79}, coi_enter={33, 34}), dict(none, coi_enter={6, 16, 43}),
+            "CUDA sin / cos")
+    assert all(ill[v] for v in (33, 34, 6, 16, 43))                       # only the e >= 0.8 ellipses
+    assert np.array_equal(fast[3][~ill, 0], want[~ill, 0], equal_nan=True)
     opt = lambda x: None if x < 0 else int(x)
     for k, (v, ent, lft, prev, only) in enumerate(g["variants"]):
         bi2, ba2, _, ce2 = _points_inputs(g)
@@ -488,8 +527,6 @@ def test_vessel_points_golden(dev):
                                steps_limit=int(g["steps_limit"]))
         others = np.arange(len(cl2)) != v
         assert np.array_equal(cl2[others], before[others], equal_nan=True)    # untouched rows
-        if not _robust(g["vessel12"])[v]:
-            continue
         got = np.concatenate([bi2[v], ba2[v], cl2[v], ce2[v]])
         want_v = g["var%d_rows" % k]
         lo = 4 if only else 0
@@ -530,15 +567,16 @@ def test_march_parallel_is_bit_identical_to_serial(dev):
     bd = np.stack([ba_, bb, bf, becc, bma, bea, rng.uniform(0, 2 * np.pi, m), bn,
                    rng.choice([-1.0, 1.0], m), coi], axis=1)
     from volatilespace_b200 import orbit_intersect as oi
-    dev.set_march_mode(True)
-    try:
-        serial = oi.predict_enter_coi(vd, bd, 1e-5, 300, device=dev)
-    finally:
-        dev.set_march_mode(False)
-    par = oi.predict_enter_coi(vd, bd, 1e-5, 300, device=dev)
-    chunks, rerun, fell_back, refused = dev.march_stats()
-    assert fell_back == 0
-    assert np.array_equal(par.view(np.uint64), serial.view(np.uint64))
+    for exact in (False, True):          # fast trigonometry, then the default (exact) mode
+        dev.set_march_mode(True, exact_trig=exact)
+        try:
+            serial = oi.predict_enter_coi(vd, bd, 1e-5, 300, device=dev)
+        finally:
+            dev.set_march_mode(False, exact_trig=exact)
+        par = oi.predict_enter_coi(vd, bd, 1e-5, 300, device=dev)
+        chunks, rerun, fell_back, refused = dev.march_stats()
+        assert fell_back == 0
+        assert np.array_equal(par.view(np.uint64), serial.view(np.uint64)), exact
     hit = ~np.isnan(serial[:, 0])
     assert 20 < hit.sum() < m - 20
     assert rerun <= 0.05 * chunks
@@ -578,9 +616,8 @@ def test_vessel_points_through_the_class(dev):
     pv.body_ma, pv.body_ea = b12[:, 4].copy(), b12[:, 5].copy()
     pv.predict_coi_limit = int(g["steps_limit"])
     pv.points()
-    rob = _robust(v12[sub])
     _assert_points(pv.coi_leave, g["coi_leave"][sub], "coi_leave", nan_slack=1)
-    _assert_points(pv.coi_enter[rob], g["coi_enter"][sub][rob], "coi_enter")
+    _assert_points(pv.coi_enter, g["coi_enter"][sub], "coi_enter")     # incl. the e >= 0.8 ellipses
     _assert_points(pv.body_impact, g["body_impact"][sub], "body_impact", nan_slack=1)
     keep = pv.coi_enter.copy()
     pv.points(vessel=3, only_enter_coi=True)
@@ -698,11 +735,10 @@ def test_vessel_events_through_the_class(dev):
         want_p = g["cv%d_p_row_out" % k]
         got_p = np.concatenate([pv.body_impact[ves], pv.body_enter_atm[ves], pv.coi_leave[ves],
                                 pv.coi_enter[ves]])
-        if not ((pv.ecc[ves] >= 0.8) & (pv.ecc[ves] < 1)):
-            flips = np.isnan(got_p) != np.isnan(want_p)
-            both = ~np.isnan(got_p) & ~np.isnan(want_p)
-            assert flips.sum() <= 2, k          # degenerate-quartic found / not-found flips
-            np.testing.assert_allclose(got_p[both], want_p[both], rtol=2e-7, atol=2e-7)
+        flips = np.isnan(got_p) != np.isnan(want_p)
+        both = ~np.isnan(got_p) & ~np.isnan(want_p)
+        assert flips.sum() <= 2, k              # degenerate-quartic found / not-found flips
+        np.testing.assert_allclose(got_p[both], want_p[both], rtol=2e-7, atol=2e-7)
     k = 0
     pv = fresh(g["cw%d_v" % k], g["cw%d_p" % k], np.zeros(len(g["cw%d_v" % k]), dtype=np.int64),
                [-1, -1, -1])

@@ -1,6 +1,6 @@
 """Small fixed workloads for ncu captures (see profiles/README.md).
 
-    python tools/profile_run.py gravity64k | gravity256k | moderef1m | soc1m | convert1m | kepler1m | collision256k | parents64k | points160
+    python tools/profile_run.py gravity64k | gravity64k_sym | gravity256k | gravity1m | gravity1m_lean | kepler4m | moderef1m | soc1m | convert1m | kepler1m | collision256k | parents64k | points160
 """
 import os
 import sys
@@ -59,6 +59,19 @@ def main():
                         k["dr"], k["ma"], k["ea"], k["ref"])
         for _ in range(5):
             dev.kepler_tick(KIND_VESSEL, 1.0, k["body_pos"])
+    elif mode == "kepler4m":
+        k = synth.kepler_objects(1 << 22)
+        dev.kepler_load(KIND_VESSEL, 512, k["a"], k["b"], k["f"], k["ecc"], k["pea"], k["n"],
+                        k["dr"], k["ma"], k["ea"], k["ref"])
+        for _ in range(4):
+            dev.kepler_tick(KIND_VESSEL, 1.0, k["body_pos"])
+    elif mode in ("gravity1m", "gravity1m_lean", "gravity64k_sym"):
+        if mode == "gravity1m_lean":
+            os.environ["VSB_SYM_MODE"] = "lean"
+        s = synth.plummer2d(65536) if mode == "gravity64k_sym" else synth.rotating_disk(1 << 20)
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"])
+        dev.set_gravity_mode("sym")
+        dev.allpairs_step(s["gc"], 3)
     elif mode == "collision256k":
         from volatilespace_b200.phys_editor import body_radius
         s = synth.collapsing_cluster(262144)

@@ -1374,10 +1374,11 @@ extern "C" int vsb_host_running_sum(double x0, double c, int64_t kmax, int bound
     return VSB_OK;
 }
 
-extern "C" int vsb_set_march_mode(vsb_ctx *c, int sequential)
+extern "C" int vsb_set_march_mode(vsb_ctx *c, int mode)
 {
     CTX(c);
-    c->march_sequential = sequential ? 1 : 0;
+    VSB_CHECK(mode >= 0 && mode <= 3, VSB_ERR_ARG, "vsb_set_march_mode: mode %d", mode);
+    c->march_sequential = mode;        // bit 0: serial loop, bit 1: exact trigonometry
     return VSB_OK;
 }
 

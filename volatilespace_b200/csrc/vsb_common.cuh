@@ -108,7 +108,7 @@ struct vsb_ctx {
     vsb_buf scratch;     // generic
     vsb_buf host_stage;  // device staging for the stateless host-buffer calls
     vsb_buf march_stats; // work area of the parallel COI-entry march; starts with 4 x u64 counters
-    int march_sequential = 0;  // vsb_set_march_mode: the one-thread-per-pair serial march
+    int march_sequential = 2;  // vsb_set_march_mode: bit 0 the one-thread-per-pair serial march, bit 1 exact trigonometry (default on)
     unsigned long long *d_key = nullptr;   // collision key (device)
     unsigned long long *h_key = nullptr;   // pinned mirror
     double *h_pin = nullptr;               // pinned scratch (small)

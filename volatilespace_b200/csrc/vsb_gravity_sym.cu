@@ -183,7 +183,7 @@ allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ 
 // tasks wrote -- their unified indices (P-side slab s -> s, Q-side slab sl -> pairs + sl; part_q
 // follows part_p in memory) are listed per block in `own_list` (same order) -- so a rank's
 // reduction costs 1/world of the loads AND of the loop trips.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__restrict__ part_q,
                            const int *__restrict__ qslot_first, const int *__restrict__ own_first,
                            const int *__restrict__ own_list, int S, int M, int64_t n,
@@ -195,45 +195,48 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
     const int X = (int)(i / S);
     const int r = (int)(i - (int64_t)X * S);
     double sx = 0.0, sy = 0.0;
-    // slabs are fetched eight at a time so that the loads of a batch are in flight together;
-    // the additions keep their order
+    // slabs are fetched RB at a time so that the loads of a batch are in flight together (the
+    // kernel is latency bound: ~2 M slabs of 16 B per body at 64 k bodies); the additions keep
+    // their order
+    constexpr int RB = 32;
     if (own_first) {
         const int e1 = own_first[X + 1];
-        for (int e0 = own_first[X]; e0 < e1; e0 += 8) {
-            double2 v[8];
+        for (int e0 = own_first[X]; e0 < e1; e0 += RB) {
+            double2 v[RB];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < RB; ++k)
                 v[k] = e0 + k < e1 ? part_p[(int64_t)own_list[e0 + k] * S + r] : make_double2(0.0, 0.0);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < RB; ++k) {
                 sx += v[k].x;
                 sy += v[k].y;
             }
         }
     } else {
-        for (int sl0 = qslot_first[X]; sl0 < qslot_first[X + 1]; sl0 += 8) {
-            double2 v[8];
+        const int sl1 = qslot_first[X + 1];
+        for (int sl0 = qslot_first[X]; sl0 < sl1; sl0 += RB) {
+            double2 v[RB];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < RB; ++k) {
                 const int sl = sl0 + k;
-                v[k] = sl < qslot_first[X + 1] ? part_q[(int64_t)sl * S + r] : make_double2(0.0, 0.0);
+                v[k] = sl < sl1 ? part_q[(int64_t)sl * S + r] : make_double2(0.0, 0.0);
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < RB; ++k) {
                 sx += v[k].x;
                 sy += v[k].y;
             }
         }
-        for (int Q0 = X; Q0 < M; Q0 += 8) {
-            double2 v[8];
+        for (int Q0 = X; Q0 < M; Q0 += RB) {
+            double2 v[RB];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < RB; ++k) {
                 const int Q = Q0 + k;
                 const int64_t slab = (int64_t)Q * (Q + 1) / 2 + X;
                 v[k] = Q < M ? part_p[slab * S + r] : make_double2(0.0, 0.0);
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < RB; ++k) {
                 sx += v[k].x;
                 sy += v[k].y;
             }
@@ -494,7 +497,7 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
     // slabs of other ranks' tasks are never read: no zeroing of the slab memory is needed
     const int *own_first = world > 1 ? (const int *)((char *)c->sym_tab.p + c->sym_own_off) : nullptr;
     const int *own_list = world > 1 ? (const int *)((char *)c->sym_tab.p + c->sym_ownlist_off) : nullptr;
-    allpairs_sym_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+    allpairs_sym_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
         part_p, part_q, d_qf, own_first, own_list, S, M, n, gc, (double2 *)c->acc, (double2 *)c->vel,
         (double2 *)c->pos, (world == 1 && integrate) ? 1 : 0);
     c->launches += 1;

@@ -151,13 +151,13 @@ __device__ __forceinline__ double2 oi_xy(const orbit &o)
 {   // orbit_intersect.py:95-105
     double xn, yn;
     if (o.ecc < 1) {
-        xn = o.a * cos(o.ea) - o.f;
-        yn = o.b * sin(o.ea);
+        xn = o.a * pe_cos(o.ea) - o.f;
+        yn = o.b * pe_sin(o.ea);
     } else {
         xn = o.a * cosh(o.ea) - o.f;
         yn = o.b * sinh(o.ea);
     }
-    const double c = cos(o.pea - PI_D), s = sin(o.pea - PI_D);
+    const double c = pe_cos(o.pea - PI_D), s = pe_sin(o.pea - PI_D);
     return make_double2(xn * c - yn * s, xn * s + yn * c);
 }
 
@@ -367,8 +367,8 @@ __device__ __forceinline__ double2 m_xy(const morbit &o, double ea)
 {
     double xn, yn;
     if (!o.hyp) {
-        xn = o.a * cos(ea) - o.f;
-        yn = o.b * sin(ea);
+        xn = o.a * pe_cos(ea) - o.f;
+        yn = o.b * pe_sin(ea);
     } else {
         xn = o.a * cosh(ea) - o.f;
         yn = o.b * sinh(ea);
@@ -434,8 +434,8 @@ __device__ __forceinline__ msetup march_setup(const double *V, const double *B, 
     long long steps = (long long)m2;
     if (steps_limit > steps) steps = steps_limit;
     m.dt = m.period / (double)steps;
-    m.v = morbit{V[0], V[1], V[2], V[3], cos(V[6] - PI_D), sin(V[6] - PI_D), !(V[3] < 1)};
-    m.b = morbit{B[0], B[1], B[2], B[3], cos(B[6] - PI_D), sin(B[6] - PI_D), !(B[3] < 1)};
+    m.v = morbit{V[0], V[1], V[2], V[3], pe_cos(V[6] - PI_D), pe_sin(V[6] - PI_D), !(V[3] < 1)};
+    m.b = morbit{B[0], B[1], B[2], B[3], pe_cos(B[6] - PI_D), pe_sin(B[6] - PI_D), !(B[3] < 1)};
     m.v_ma0 = V[4]; m.v_ea0 = V[5]; m.v_pea = V[6]; m.v_n = V[8]; m.v_dr = V[9];
     m.b_ma0 = B[4]; m.b_ea0 = B[5]; m.b_pea = B[6]; m.b_n = B[7]; m.b_dr = B[8];
     m.cv = m.v.hyp ? m.v_dr * m.v_n * -1 * m.dt : m.v_dr * m.v_n * m.dt;
@@ -951,6 +951,11 @@ int vsb_launch_predict_enter_coi(vsb_ctx *c, int64_t n, const double *d_vd, cons
                                  double *d_out5, void *d_work, int sequential)
 {
     if (n <= 0) return VSB_OK;
+    // bit 0: the serial loop, bit 1: exact trigonometry (vsb_set_march_mode)
+    const int exact = (sequential >> 1) & 1;
+    sequential &= 1;
+    VSB_CUDA(cudaMemcpyToSymbolAsync(pe_exact_trig, &exact, sizeof(int), 0, cudaMemcpyHostToDevice,
+                                     c->stream));
     mteam *team = (mteam *)d_work;
     VSB_CUDA(cudaMemsetAsync(team, 0, sizeof(mteam), c->stream));
     if (sequential) {

@@ -3,10 +3,20 @@
 // files are compiled with -fmad=false.
 #pragma once
 #include "vsb_common.cuh"
+#include "vsb_ddtrig.h"
 
 namespace {
 
 constexpr double PI_D = 3.141592653589793;
+
+// "Exact trigonometry" mode of the COI-entry march (vsb_set_march_mode bit 1):
+// sin / cos evaluated in double-double arithmetic and rounded to nearest (vsb_ddtrig.h) instead of
+// CUDA's 1-2 ulp routines.  ~20x the cost of sin / cos; off by default.  One copy per including
+// file (only vsb_intersect.cu sets it).
+__constant__ int pe_exact_trig = 0;
+
+__device__ __forceinline__ double pe_sin(double x) { return pe_exact_trig ? vsb_dd_sin(x) : sin(x); }
+__device__ __forceinline__ double pe_cos(double x) { return pe_exact_trig ? vsb_dd_cos(x) : cos(x); }
 
 // Python's float % (sign of the divisor)
 __device__ __forceinline__ double py_mod(double a, double b)
@@ -30,7 +40,7 @@ __device__ double pe_solve_kepler_ell(double ecc, double ma, double tol)
         double al = tol / 1e7, be = tol / 0.3, fp = 2.7 * mr, fpp = 0.301, f = 0.154;
         for (int i = 0; i < 2; ++i) {
             if ((fpp - fp) <= (al + be * f)) break;
-            if ((f - ecc * sin(f) - mr) > 0) fpp = f;
+            if ((f - ecc * pe_sin(f) - mr) > 0) fpp = f;
             else fp = f;
         }
         f = 0.5 * (fp + fpp);
@@ -39,7 +49,7 @@ __device__ double pe_solve_kepler_ell(double ecc, double ma, double tol)
     double tol2s = 2 * tol / (ecc + 2.2e-16);
     double eapp = mr + 0.999999 * mr * (PI_D - mr) /
                            (2. * mr + ecc - PI_D + 2.4674011002723395 / (ecc + 2.2e-16));
-    double fpp = ecc * sin(eapp), fppp = ecc * cos(eapp);
+    double fpp = ecc * pe_sin(eapp), fppp = ecc * pe_cos(eapp);
     double fp = 1 - fppp, f = eapp - fpp - mr;
     double delta = -f / fp;
     double fp3 = fp * fp * fp, ffpfpp = f * fp * fpp, f2fppp = f * f * fppp;
@@ -47,8 +57,8 @@ __device__ double pe_solve_kepler_ell(double ecc, double ma, double tol)
     for (int i = 0; i < 30; ++i) {
         if (delta * delta < fp * tol2s) break;
         eapp = eapp + delta;
-        fp = 1 - ecc * cos(eapp);
-        delta = (mr - eapp + ecc * sin(eapp)) / fp;
+        fp = 1 - ecc * pe_cos(eapp);
+        delta = (mr - eapp + ecc * pe_sin(eapp)) / fp;
     }
     eapp = eapp + delta;
     return ma + flip * (mr - eapp);

@@ -519,8 +519,10 @@ class Device:
         check(self.L.vsb_vessel_cross_scan(self.h, ptr(out)))
         return (None if out[0] < 0 else int(out[0])), int(out[1])
 
-    def set_march_mode(self, sequential):
-        check(self.L.vsb_set_march_mode(self.h, int(bool(sequential))))
+    def set_march_mode(self, sequential=False, exact_trig=True):
+        """sequential: the reference's serial loop, one thread per pair; exact_trig: the march's
+        sin / cos in double-double arithmetic, rounded to nearest (include/vsb200.h)."""
+        check(self.L.vsb_set_march_mode(self.h, int(bool(sequential)) | (int(bool(exact_trig)) << 1)))
 
     def march_stats(self):
         """(chunks marched, chunks re-run, serial fallbacks, refused pairs) of the last COI-entry
