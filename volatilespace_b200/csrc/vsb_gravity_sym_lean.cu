@@ -22,10 +22,11 @@
 // side by side then belong to one or two rows and to different P-ranges, and the contribution a
 // task has to follow (the previous row's, same blocks) comes from a task that started a wave
 // earlier: 1.5-3 % of the contributions find their predecessor late (VSB_SYM_DEBUG=s counts them).
-// Bit-identical run to run (for a given GPU count).  Measured at 1 M bodies: 546 ms per tick
-// (FP64 pipe 86.8 %; the slab kernel: 526 ms, 90.2 %), DRAM traffic 3.0 GB per launch -- staging
-// slabs evicted from L2 -- instead of 9.3 GB, 48 MB of scratch instead of 8.6 GB
-// (profiles/r2_symlean1m_ncu_full_summary.txt).
+// Bit-identical run to run (for a given GPU count).  Measured at 1 M bodies: 555 ms per tick
+// (FP64 pipe 85 %; the slab kernel: 526 ms, 90.3 %), DRAM traffic 0.80 GB per launch instead of
+// 9.5 GB -- a consumed staging slab is discarded in L2 (discard.global.L2) before it is written
+// back; 7.1 GB without that -- and 48 MB of scratch instead of 8.6 GB
+// (profiles/r2_dram_gravity1m_lean.csv).
 //
 // What was tried on the way (profiles/README.md, round 2): ticket order by diagonals of the task
 // grid (a contribution made at the END of a long task precedes those of tasks running beside it:
@@ -324,6 +325,14 @@ allpairs_symlean_kernel(const double2 *__restrict__ pos, const double *__restric
                         sum[k].x = (sum[k].x + a0[k].x) + a1[k].x;
                         sum[k].y = (sum[k].y + a0[k].y) + a1[k].y;
                     }
+                    // the two slabs are dead now: tell L2 not to write their lines back
+                    if ((lane & 7) == 0) {
+#pragma unroll
+                        for (int k = 0; k < T; ++k) {
+                            asm volatile("discard.global.L2 [%0], 128;" ::"l"(s0 + k * 32) : "memory");
+                            asm volatile("discard.global.L2 [%0], 128;" ::"l"(s1 + k * 32) : "memory");
+                        }
+                    }
                 }
                 if (j < task.row_tasks) {
                     const double2 *s0 = base + (int64_t)((task.row_t0 + j) % pool) * S;
@@ -332,6 +341,11 @@ allpairs_symlean_kernel(const double2 *__restrict__ pos, const double *__restric
                         const double2 a0 = __ldcg(s0 + k * 32);
                         sum[k].x += a0.x;
                         sum[k].y += a0.y;
+                    }
+                    if ((lane & 7) == 0) {
+#pragma unroll
+                        for (int k = 0; k < T; ++k)
+                            asm volatile("discard.global.L2 [%0], 128;" ::"l"(s0 + k * 32) : "memory");
                     }
                 }
                 ordered_add<T>(acc + (int64_t)task.q * S + w * SB + lane, sems + task.q * WARPS + w,
