@@ -281,6 +281,28 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak, with_cpu=True):
             (148 * 64 * 1965e6),
             "flops13_frac_at_1965mhz": pairs * FLOPS_PER_PAIR / (ms * 1e-3) / (148 * 64 * 2 * 1965e6)}
     dev.set_gravity_mode("auto")
+    # the slab-free symmetric kernel on the headline workload (VSB_SYM_MODE=lean; automatic above
+    # 16 GB of slabs): same pairs, 48 MB of scratch instead of 8.6 GB
+    try:
+        d1 = synth.rotating_disk(1048576)
+        dev.upload_bodies(d1["mass"], d1["pos"], d1["vel"])
+        dev.set_gravity_mode("sym")
+        os.environ["VSB_SYM_MODE"] = "lean"
+        dev.allpairs_tick_async(d1["gc"])
+        ms = time_ticks_each(torch, stream, lambda: dev.allpairs_tick_async(d1["gc"]), 3) / 3
+        p1 = 1048576 * 1048575
+        tr = measured_traffic("allpairs_symlean_kernel@disk1m@1gpu") or {}
+        out["disk1m_slab_free_kernel"] = {
+            "pairs_per_s": p1 / (ms * 1e-3), "ms_per_step": ms,
+            "fp64_pipe_utilisation_at_1965mhz": p1 * 8 / (ms * 1e-3) / (148 * 64 * 1965e6),
+            "traffic": tr.get("bytes"), "traffic_source": tr.get("source"),
+            "note": "vsb_gravity_sym_lean.cu: persistent CTAs, ordered accumulation into acc[]; "
+                    "bit-identical run to run"}
+    except Exception as e:
+        out["disk1m_slab_free_kernel"] = {"error": str(e)[:200]}
+    finally:
+        os.environ.pop("VSB_SYM_MODE", None)
+        dev.set_gravity_mode("auto")
     if with_cpu:
         v, cores, rows, dtc = cpu_pairs_per_s(s, 4.0)
         out["plummer64k"]["cpu_baseline"] = {

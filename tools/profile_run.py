@@ -72,6 +72,12 @@ def main():
         dev.upload_bodies(s["mass"], s["pos"], s["vel"])
         dev.set_gravity_mode("sym")
         dev.allpairs_step(s["gc"], 3)
+    elif mode == "gravity1m_rank0of8":
+        s = synth.rotating_disk(1 << 20)
+        dev.upload_bodies(s["mass"], s["pos"], s["vel"])
+        dev.set_gravity_mode("sym")
+        for _ in range(3):
+            dev.allpairs_sym_partial_async(s["gc"], 0, 8)
     elif mode == "collision256k":
         from volatilespace_b200.phys_editor import body_radius
         s = synth.collapsing_cluster(262144)
