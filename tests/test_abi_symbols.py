@@ -78,3 +78,17 @@ def test_sass_uses_tma_bulk_copies():
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "UBLKCP" in out.stdout and "MUFU.RSQ64H" in out.stdout and "DFMA" in out.stdout
+
+
+def test_pinned_buffers_degrade_to_plain_arrays_without_a_gpu(lib):
+    """Page-locking the shim's result arrays is an optimisation: without a device (or when the
+    registration is refused) pinned_empty returns an ordinary writable array of the asked shape and
+    leaves no pending CUDA error behind."""
+    import numpy as np
+    from volatilespace_b200.device import pinned_empty
+    for shape, dt in (((100000, 2), np.float64), (70000, np.int64), ((3, 5), np.float64), (0, np.float64)):
+        a = pinned_empty(shape, dt)
+        assert a.shape == (shape if isinstance(shape, tuple) else (shape,)) and a.dtype == dt
+        assert a.flags.c_contiguous and a.flags.writeable and a.ctypes.data % 8 == 0
+        a[...] = 7
+        assert (a == 7).all()
