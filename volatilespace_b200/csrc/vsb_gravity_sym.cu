@@ -183,6 +183,11 @@ allpairs_sym_kernel(const double2 *__restrict__ pos, const double *__restrict__ 
 // tasks wrote -- their unified indices (P-side slab s -> s, Q-side slab sl -> pairs + sl; part_q
 // follows part_p in memory) are listed per block in `own_list` (same order) -- so a rank's
 // reduction costs 1/world of the loads AND of the loop trips.
+// The kernel is latency bound (a body's ~2 M 16-byte terms sit 16 S bytes apart), so FOUR lanes
+// share a body: lane part p of 4 adds the p-th quarter of the body's slab list in order (eight
+// loads in flight at a time), and the quarters are combined as (q0 + q1) + (q2 + q3) -- a fixed
+// order, bit-identical run to run.  Lanes part*8 + j of a warp work on body j of the warp's eight,
+// so that every load instruction of a part covers 128 contiguous bytes.
 __global__ void __launch_bounds__(128)
 allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__restrict__ part_q,
                            const int *__restrict__ qslot_first, const int *__restrict__ own_first,
@@ -190,22 +195,22 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
                            double gc, double2 *__restrict__ acc, double2 *__restrict__ vel,
                            double2 *__restrict__ pos, int integrate)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int X = (int)(i / S);
-    const int r = (int)(i - (int64_t)X * S);
+    const int lane = threadIdx.x & 31, part = lane >> 3;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t i = warp * 8 + (lane & 7);
+    const bool live = i < n;
+    const int X = (int)((live ? i : n - 1) / S);
+    const int r = (int)((live ? i : n - 1) - (int64_t)X * S);
     double sx = 0.0, sy = 0.0;
-    // slabs are fetched RB at a time so that the loads of a batch are in flight together (the
-    // kernel is latency bound: ~2 M slabs of 16 B per body at 64 k bodies); the additions keep
-    // their order
-    constexpr int RB = 32;
+    constexpr int RB = 8;
     if (own_first) {
-        const int e1 = own_first[X + 1];
-        for (int e0 = own_first[X]; e0 < e1; e0 += RB) {
+        const int b0 = own_first[X], len = own_first[X + 1] - b0;
+        const int e0 = b0 + (int)((int64_t)len * part / 4), e1 = b0 + (int)((int64_t)len * (part + 1) / 4);
+        for (int e = e0; e < e1; e += RB) {
             double2 v[RB];
 #pragma unroll
             for (int k = 0; k < RB; ++k)
-                v[k] = e0 + k < e1 ? part_p[(int64_t)own_list[e0 + k] * S + r] : make_double2(0.0, 0.0);
+                v[k] = e + k < e1 ? part_p[(int64_t)own_list[e + k] * S + r] : make_double2(0.0, 0.0);
 #pragma unroll
             for (int k = 0; k < RB; ++k) {
                 sx += v[k].x;
@@ -213,27 +218,23 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
             }
         }
     } else {
-        const int sl1 = qslot_first[X + 1];
-        for (int sl0 = qslot_first[X]; sl0 < sl1; sl0 += RB) {
+        // the body's list: Q-side slabs qslot_first[X] .. qslot_first[X+1]-1, then P-side slabs of
+        // the pairs (X, Q), Q = X .. M-1
+        const int q0 = qslot_first[X], nq = qslot_first[X + 1] - q0, len = nq + (M - X);
+        const int e0 = (int)((int64_t)len * part / 4), e1 = (int)((int64_t)len * (part + 1) / 4);
+        for (int e = e0; e < e1; e += RB) {
             double2 v[RB];
 #pragma unroll
             for (int k = 0; k < RB; ++k) {
-                const int sl = sl0 + k;
-                v[k] = sl < sl1 ? part_q[(int64_t)sl * S + r] : make_double2(0.0, 0.0);
-            }
-#pragma unroll
-            for (int k = 0; k < RB; ++k) {
-                sx += v[k].x;
-                sy += v[k].y;
-            }
-        }
-        for (int Q0 = X; Q0 < M; Q0 += RB) {
-            double2 v[RB];
-#pragma unroll
-            for (int k = 0; k < RB; ++k) {
-                const int Q = Q0 + k;
-                const int64_t slab = (int64_t)Q * (Q + 1) / 2 + X;
-                v[k] = Q < M ? part_p[slab * S + r] : make_double2(0.0, 0.0);
+                const int ee = e + k;
+                if (ee >= e1) {
+                    v[k] = make_double2(0.0, 0.0);
+                } else if (ee < nq) {
+                    v[k] = part_q[(int64_t)(q0 + ee) * S + r];
+                } else {
+                    const int Q = X + (ee - nq);
+                    v[k] = part_p[((int64_t)Q * (Q + 1) / 2 + X) * S + r];
+                }
             }
 #pragma unroll
             for (int k = 0; k < RB; ++k) {
@@ -242,6 +243,12 @@ allpairs_sym_reduce_kernel(const double2 *__restrict__ part_p, const double2 *__
             }
         }
     }
+    // (q0 + q1) + (q2 + q3)
+    sx += __shfl_xor_sync(0xffffffffu, sx, 8);
+    sy += __shfl_xor_sync(0xffffffffu, sy, 8);
+    sx += __shfl_xor_sync(0xffffffffu, sx, 16);
+    sy += __shfl_xor_sync(0xffffffffu, sy, 16);
+    if (!live || part != 0) return;
     sx *= gc;
     sy *= gc;
     acc[i] = make_double2(sx, sy);
@@ -497,7 +504,7 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
     // slabs of other ranks' tasks are never read: no zeroing of the slab memory is needed
     const int *own_first = world > 1 ? (const int *)((char *)c->sym_tab.p + c->sym_own_off) : nullptr;
     const int *own_list = world > 1 ? (const int *)((char *)c->sym_tab.p + c->sym_ownlist_off) : nullptr;
-    allpairs_sym_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(
+    allpairs_sym_reduce_kernel<<<(unsigned)((n * 4 + 127) / 128), 128, 0, c->stream>>>(
         part_p, part_q, d_qf, own_first, own_list, S, M, n, gc, (double2 *)c->acc, (double2 *)c->vel,
         (double2 *)c->pos, (world == 1 && integrate) ? 1 : 0);
     c->launches += 1;
