@@ -23,6 +23,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "vsb_common.cuh"
 
 namespace {
@@ -328,141 +331,106 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
     const int tail_split = tail_env ? atoi(tail_env) : 8;
     if (c->sym_tasks_n != n || c->sym_world != world || c->sym_rank != rank || c->sym_S != S ||
         c->sym_tail != tail_split) {
-        struct T { sym_task t; int cost; };
-        T *all = (T *)malloc(sizeof(T) * (size_t)(pairs + M));
-        int *qfirst = (int *)malloc(sizeof(int) * (size_t)(M + 1));
-        sym_task *mine = (sym_task *)malloc(sizeof(sym_task) * (size_t)(pairs + M + 1));
-        if (!all || !qfirst || !mine) {
-            free(all);
-            free(qfirst);
-            free(mine);
-            VSB_CHECK(false, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
-        }
-        // Tail: the tasks that would run in the last two waves of the resident CTAs -- the last
-        // 2 x slots x world entries of the cost-sorted list -- are cut into VSB_SYM_TAIL pieces
-        // (default 8, 0 = off), so that the ranks and the SMs finish within a small piece of each
-        // other.  A cut task keeps its P-side slabs; each piece gets its own Q-side slab.
-        unsigned char *cut = (unsigned char *)calloc((size_t)(pairs + M), 1);
-        int nt = 0;
+        // cost unit: one block pair, one side (the diagonal pair runs the directed formula: 1)
+        struct item { sym_task t; int cost; };
+        std::vector<item> plain;
+        plain.reserve((size_t)(pairs / chunk + M + 1));
         for (int q = 0; q < M; ++q)
             for (int p0 = 0; p0 <= q; p0 += chunk) {
-                const int p1 = p0 + chunk > q + 1 ? q + 1 : p0 + chunk;
-                all[nt].t = sym_task{q, p0, p1, 0};
-                all[nt].cost = 2 * (p1 - p0) - (p1 == q + 1 ? 1 : 0);
-                ++nt;
+                const int p1 = std::min(p0 + chunk, q + 1);
+                plain.push_back({sym_task{q, p0, p1, 0}, 2 * (p1 - p0) - (p1 == q + 1 ? 1 : 0)});
             }
-        if (cut && tail_split > 1 && chunk >= 2) {
-            int64_t left = 2 * (int64_t)c->sm_count * mb * world;
-            if (left > nt / 2) left = nt / 2;
-            for (int cst = 0; cst <= 2 * chunk && left > 0; ++cst)      // cheapest first = run last
-                for (int i = nt - 1; i >= 0 && left > 0; --i)
-                    if (all[i].cost == cst) {
-                        cut[i] = 1;
+        // Tail: the tasks that would run in the last two waves of the resident CTAs -- the last
+        // 2 x slots x world entries of the cost-sorted list -- are cut into VSB_SYM_TAIL shorter
+        // P-ranges (default 8, 0 = off), so that the ranks and the SMs finish within a small piece
+        // of each other.  A cut task keeps its pairs' P-side slabs; each piece gets its own
+        // Q-side slab.  (Single block pairs -- the tasks of mid sizes -- are NOT cut: cutting the
+        // last two waves of them into their sub-rounds, each piece with its own slabs, was
+        // measured slower, 2.113 -> 2.190 ms at 64 k bodies and 8.37 -> 8.50 ms at 128 k,
+        // profiles/r2_midsize_subround_pieces_ab.txt: CTAs left alone on an SM run faster, and a
+        // piece pays the full Q load and two full slabs for a fraction of the pairs.)
+        std::vector<char> cut(plain.size(), 0);
+        if (tail_split > 1) {
+            int64_t left = std::min<int64_t>(2 * (int64_t)c->sm_count * mb * world, (int64_t)plain.size() / 2);
+            const int maxc = 2 * chunk;
+            for (int cst = 0; cst <= maxc && left > 0; ++cst)           // cheapest first = run last
+                for (int64_t i = (int64_t)plain.size() - 1; i >= 0 && left > 0; --i)
+                    if (plain[i].cost == cst) {
+                        const sym_task &t = plain[i].t;
+                        cut[i] = t.p1 - t.p0 >= 2;
                         --left;
                     }
         }
-        const int nplain = nt;
-        T *plain = (T *)malloc(sizeof(T) * (size_t)(nplain + 1));
-        if (!plain) {
-            free(cut);
-            free(all);
-            free(qfirst);
-            free(mine);
-            VSB_CHECK(false, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
-        }
-        memcpy(plain, all, sizeof(T) * (size_t)nplain);
-        nt = 0;
-        int slot = 0, last_q = -1;
-        for (int i = 0; i < nplain; ++i) {
-            const int q = plain[i].t.q, p0 = plain[i].t.p0, p1 = plain[i].t.p1;
-            while (last_q < q) qfirst[++last_q] = slot;
-            const int piece = (cut && cut[i] && p1 - p0 >= 2) ? (p1 - p0 + tail_split - 1) / tail_split
-                                                              : p1 - p0;
-            for (int a0 = p0; a0 < p1; a0 += piece) {
-                const int a1 = a0 + piece > p1 ? p1 : a0 + piece;
-                all[nt].t = sym_task{q, a0, a1, slot++};
-                all[nt].cost = 2 * (a1 - a0) - (a1 == q + 1 ? 1 : 0);
-                ++nt;
+        std::vector<item> all;
+        all.reserve(plain.size() + 16 * (size_t)c->sm_count * mb * world);
+        for (size_t i = 0; i < plain.size(); ++i) {
+            const sym_task &t = plain[i].t;
+            if (!cut[i]) {
+                all.push_back(plain[i]);
+                continue;
+            }
+            const int len = (t.p1 - t.p0 + tail_split - 1) / tail_split;
+            for (int a0 = t.p0; a0 < t.p1; a0 += len) {
+                const int a1 = std::min(a0 + len, t.p1);
+                all.push_back({sym_task{t.q, a0, a1, 0}, 2 * (a1 - a0) - (a1 == t.q + 1 ? 1 : 0)});
             }
         }
-        while (last_q < M - 1) qfirst[++last_q] = slot;
-        qfirst[M] = slot;
-        free(plain);
-        free(cut);
-        // descending cost (stable counting order), then deal round-robin to ranks
-        int maxc = 2 * chunk;
-        int nm = 0, dealt = 0;
-        for (int cst = maxc; cst >= 0; --cst)
-            for (int i = 0; i < nt; ++i)
-                if (all[i].cost == cst) {
-                    if (dealt % world == rank) mine[nm++] = all[i].t;
-                    ++dealt;
-                }
+        // Q-side slab slots: the tasks of block Q in creation (P) order
+        std::vector<int> qfirst((size_t)M + 1, 0);
+        {
+            int slot_run = 0, last_q = -1;
+            for (item &it : all) {
+                while (last_q < it.t.q) qfirst[++last_q] = slot_run;
+                it.t.qslot = slot_run++;
+            }
+            while (last_q < M) qfirst[++last_q] = slot_run;
+        }
+        const int slot = qfirst[M];
+        // descending cost (stable: creation order within a cost), then deal round-robin to ranks
+        std::vector<int> order(all.size());
+        for (size_t i = 0; i < all.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return all[x].cost > all[y].cost; });
+        std::vector<sym_task> mine;
+        for (size_t k = rank; k < order.size(); k += (size_t)world) mine.push_back(all[order[k]].t);
+        const int nm = (int)mine.size();
         // several GPUs: per block X the unified indices of the slabs THIS rank's tasks write, in the
-        // order the one-GPU reduction adds them (Q-side slabs in slot order, then P-side by Q)
-        unsigned char *own = (unsigned char *)calloc((size_t)(pairs + slot + 1), 1);
-        int *own_first = (int *)malloc(sizeof(int) * (size_t)(M + 1));
-        int *own_list = nullptr;
-        int n_own = 0;
-        if (own)
-            for (int i = 0; i < nm; ++i) {
-                own[pairs + mine[i].qslot] = 1;
-                n_own += 1 + (mine[i].p1 - mine[i].p0);
-                for (int P = mine[i].p0; P < mine[i].p1; ++P)
-                    own[(int64_t)mine[i].q * (mine[i].q + 1) / 2 + P] = 1;
-            }
-        if (own) own_list = (int *)malloc(sizeof(int) * (size_t)(n_own + 1));
-        if (!own || !own_first || !own_list) {
-            free(own);
-            free(own_first);
-            free(own_list);
-            free(all);
-            free(qfirst);
-            free(mine);
-            VSB_CHECK(false, VSB_ERR_NOMEM, "allpairs_sym: out of host memory");
+        // order the one-GPU reduction adds them (the block's slot list, then P-side by Q)
+        std::vector<char> own((size_t)(pairs + slot + 1), 0);
+        for (int i = 0; i < nm; ++i) {
+            own[pairs + mine[i].qslot] = 1;
+            for (int P = mine[i].p0; P < mine[i].p1; ++P)
+                own[(int64_t)mine[i].q * (mine[i].q + 1) / 2 + P] = 1;
         }
-        n_own = 0;
+        std::vector<int> own_first((size_t)M + 1, 0), own_list;
         for (int X = 0; X < M; ++X) {
-            own_first[X] = n_own;
+            own_first[X] = (int)own_list.size();
             for (int sl = qfirst[X]; sl < qfirst[X + 1]; ++sl)
-                if (own[pairs + sl]) own_list[n_own++] = (int)(pairs + sl);
+                if (own[pairs + sl]) own_list.push_back((int)(pairs + sl));
             for (int Q = X; Q < M; ++Q) {
                 const int64_t sb = (int64_t)Q * (Q + 1) / 2 + X;
-                if (own[sb]) own_list[n_own++] = (int)sb;
+                if (own[sb]) own_list.push_back((int)sb);
             }
         }
-        own_first[M] = n_own;
-        free(own);
+        own_first[M] = (int)own_list.size();
+        const int n_own = (int)own_list.size();
         const size_t tab_bytes = (sizeof(sym_task) * (size_t)(nm + 1) + 255) / 256 * 256;
         const size_t idx_bytes = (sizeof(int) * (size_t)(M + 1) + 255) / 256 * 256;
-        int rc = vsb_buf_reserve(c->sym_tab, tab_bytes + 2 * idx_bytes + sizeof(int) * (size_t)(n_own + 1) + 1024);
-        char *qf = nullptr;
-        cudaError_t ce = cudaSuccess;
-        if (rc == VSB_OK) {
-            qf = (char *)c->sym_tab.p + tab_bytes;
-            char *of = qf + idx_bytes, *ol = of + idx_bytes;
-            ce = cudaMemcpyAsync(c->sym_tab.p, mine, sizeof(sym_task) * (size_t)nm,
-                                 cudaMemcpyHostToDevice, c->stream);
-            if (ce == cudaSuccess)
-                ce = cudaMemcpyAsync(qf, qfirst, sizeof(int) * (size_t)(M + 1),
-                                     cudaMemcpyHostToDevice, c->stream);
-            if (ce == cudaSuccess)
-                ce = cudaMemcpyAsync(of, own_first, sizeof(int) * (size_t)(M + 1),
-                                     cudaMemcpyHostToDevice, c->stream);
-            if (ce == cudaSuccess)
-                ce = cudaMemcpyAsync(ol, own_list, sizeof(int) * (size_t)n_own, cudaMemcpyHostToDevice,
-                                     c->stream);
-            c->sym_own_off = (int64_t)(of - (char *)c->sym_tab.p);
-            c->sym_ownlist_off = (int64_t)(ol - (char *)c->sym_tab.p);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
-        }
-        free(own_first);
-        free(own_list);
-        free(all);
-        free(qfirst);
-        free(mine);
-        VSB_TRY(rc);
-        VSB_CUDA(ce);
+        const size_t own_bytes = (sizeof(int) * (size_t)(n_own + 1) + 255) / 256 * 256;
+        VSB_TRY(vsb_buf_reserve(c->sym_tab, tab_bytes + 2 * idx_bytes + own_bytes + 1024));
+        char *qf = (char *)c->sym_tab.p + tab_bytes;
+        char *of = qf + idx_bytes, *ol = of + idx_bytes;
+        VSB_CUDA(cudaMemcpyAsync(c->sym_tab.p, mine.data(), sizeof(sym_task) * (size_t)nm,
+                                 cudaMemcpyHostToDevice, c->stream));
+        VSB_CUDA(cudaMemcpyAsync(qf, qfirst.data(), sizeof(int) * (size_t)(M + 1), cudaMemcpyHostToDevice,
+                                 c->stream));
+        VSB_CUDA(cudaMemcpyAsync(of, own_first.data(), sizeof(int) * (size_t)(M + 1),
+                                 cudaMemcpyHostToDevice, c->stream));
+        if (n_own)
+            VSB_CUDA(cudaMemcpyAsync(ol, own_list.data(), sizeof(int) * (size_t)n_own, cudaMemcpyHostToDevice,
+                                     c->stream));
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        c->sym_own_off = (int64_t)(of - (char *)c->sym_tab.p);
+        c->sym_ownlist_off = (int64_t)(ol - (char *)c->sym_tab.p);
         c->sym_tasks_n = n;
         c->sym_tail = tail_split;
         c->sym_S = S;
