@@ -293,12 +293,20 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
     const int64_t n = c->n, npad = c->npad;
     if (n <= 0) return VSB_OK;
     // The slabs take N^2/(2S) * 16 B (8.6 GB at 1 M bodies, 34 GB at 2 M with S = 1024).  Above
-    // VSB_SYM_SLAB_GB (default 16) of slab memory, or with VSB_SYM_MODE=lean, the slab-free kernel
+    // VSB_SYM_SLAB_GB (default 16, and never more than 60 % of the free device memory) of slab
+    // memory, or with VSB_SYM_MODE=lean, the slab-free kernel
     // of vsb_gravity_sym_lean.cu runs instead: ~4 % slower, 48 MB of scratch, no size limit.
     {
         const char *mode = getenv("VSB_SYM_MODE"), *gb = getenv("VSB_SYM_SLAB_GB");
-        const double budget = (gb ? atof(gb) : 16.0) * 1073741824.0;
+        double budget = (gb ? atof(gb) : 16.0) * 1073741824.0;
         const double slab_bytes = (double)npad * (double)npad / 2048.0 * 16.0;
+        if (!gb && slab_bytes > 1073741824.0 && (double)c->part.cap < slab_bytes) {
+            // never more than 60 % of what the device can still give (the Kepler state's curves may
+            // hold tens of GB in the same context)
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+                budget = std::min(budget, 0.6 * ((double)free_b + (double)c->part.cap));
+        }
         if ((mode && mode[0] == 'l') || (!(mode && mode[0] == 's') && slab_bytes > budget))
             return vsb_launch_allpairs_sym_lean(c, gc, rank, world, integrate);
     }
