@@ -800,15 +800,15 @@ def run_b200(args):
                        {"pos": s["pos"], "vel": s["vel"]})
 
         def dropin_step():
-            inner = ph.inner
-            inner._push("mass", "pos", "vel")
+            ph.push("mass", "pos", "vel")
             ph.gravity()
-            inner.pull("pos", "vel")
+            ph.inner.pull("pos", "vel")
         dt_cls = wall(dropin_step)
-        e2e_dropin = {"value": pairs / dt_cls, "unit": UNIT, "h2d_bytes_per_step": 40 * n,
+        e2e_dropin = {"value": pairs / dt_cls, "unit": UNIT, "h2d_bytes_per_step": 40 * ((n + world - 1) // world),
                       "d2h_bytes_per_step": 32 * n, "ms_per_step": dt_cls * 1e3,
                       "path": "phys_editor.AllPairsPhysics%s: mirrors -> device (mass, pos, vel), gravity(), "
-                              "pull(pos, vel); page-locked mirrors, every rank moves all bodies" %
+                              "pull(pos, vel); page-locked mirrors; at N > 1 each rank uploads its block of rows (NCCL "
+                              "all-gather completes the replicas) and downloads all bodies" %
                               ("" if world == 1 else " via dist.ShardedAllPairsPhysics")}
         if world == 1:
             e2e = e2e_dropin

@@ -114,6 +114,13 @@ def main():
                 print("   max |dpos|", np.abs(pg - pos_c).max())
         ok_coll = ok_coll and same and close
     n_merges = sum(m is not None for m in merges_single)
+    # push(): every rank uploads its block of rows, all-gathers complete the replicas
+    sh.inner.pull("pos", "vel", "mass")
+    sh.inner.pos += 3.0
+    sh.inner.vel *= 0.5
+    sh.push("mass", "pos", "vel")
+    ok_coll = ok_coll and np.array_equal(sh.dev.get(F_POS), sh.inner.pos) and \
+        np.array_equal(sh.dev.get(F_VEL), sh.inner.vel)
     # Kepler propagation: object blocks, no collective; each slice equals the single-GPU slice
     from volatilespace_b200._lib import KIND_VESSEL, K_EA, K_POS
     k = synth.kepler_objects(100003, seed=9)

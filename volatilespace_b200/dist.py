@@ -257,6 +257,32 @@ class ShardedAllPairsPhysics:
         self.dev.allpairs_integrate_async()
         self.inner._touched("pos", "vel")
 
+    def push(self, *names):
+        """Host mirrors -> device for the named fields ("mass", "pos", "vel", ...): every rank holds
+        the full mirrors, so each uploads only ITS block of rows over PCIe and the device replicas
+        are completed by in-place NCCL all-gathers over NVLink (same result as inner._push on every
+        rank, 1/world of the PCIe traffic)."""
+        inner = self.inner
+        if self.world == 1:
+            return inner._push(*names)
+        import torch
+        from .phys_editor import _FIELDS, _WIDE
+        n = len(inner.mass)
+        rpr, ranges = partition(n, self.world)
+        r0, r1 = ranges[self.rank]
+        npad = (max(n, 1) + 2047) // 2048 * 2048
+        self._views()
+        for name in names:
+            assert name != "parents", "push() moves the float64 fields"
+            arr = getattr(inner, name)
+            if r1 > r0:
+                self.dev.set(_FIELDS[name], arr[r0:r1], first=r0)
+            view = device_tensor(self.dev, _FIELDS[name], npad, width=2 if name in _WIDE else 1)
+            with torch.cuda.stream(self._stream):
+                gather_rows(view, rpr, self.rank, self.world, self.group)
+            inner._stale.discard(name)
+        self._stream.synchronize()
+
     def body(self):
         self.inner.body()
 
