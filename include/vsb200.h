@@ -329,10 +329,11 @@ int vsb_host_vessel_points(vsb_ctx *ctx, int64_t nv, int64_t nb, const double *v
                            double *coi_enter);
 /* Modes of the COI-entry march used by the two calls above.  mode bit 0: the reference's own
  * serial loop, one thread per pair (cross-check of the parallel march; the results must be
- * bit-identical).  mode bit 1: "exact trigonometry" -- the march's sin / cos are evaluated in
- * double-double arithmetic and rounded to nearest (~20x their normal cost), which reproduces the
- * reference's libm on the ill-conditioned marches of high-eccentricity ellipses where CUDA's
- * 1-2 ulp routines decide differently.  Default 2 (parallel march, exact
+ * bit-identical).  mode bit 1: "exact libm" -- sin / cos / pow / acos / atan2 of the march and of
+ * the orbit-circle quartic are evaluated in double-double arithmetic and rounded to nearest
+ * (~20x their normal cost), which reproduces the reference's libm where CUDA's 1-2 ulp routines
+ * decide differently: the ill-conditioned marches of high-eccentricity ellipses and the degenerate
+ * Ferrari quartic.  Default 2 (parallel march, exact
  * trigonometry); 0 is the fast variant.
  * vsb_march_stats: out4 = chunks marched, chunks re-run after a failed speculation, pairs that
  * fell back to the serial loop, pairs refused (> 2^32 steps) -- of the last call. */

@@ -38,6 +38,9 @@ static int vso_exact_trig = 0;
 void vso_set_exact_trig(int on) { vso_exact_trig = on; }
 static double t_sin(double x) { return vso_exact_trig ? vsb_dd_sin(x) : sin(x); }
 static double t_cos(double x) { return vso_exact_trig ? vsb_dd_cos(x) : cos(x); }
+static double t_pow(double x, double y) { return vso_exact_trig ? vsb_dd_pow(x, y) : pow(x, y); }
+static double t_acos(double x) { return vso_exact_trig ? vsb_dd_acos(x) : acos(x); }
+static double t_atan2(double y, double x) { return vso_exact_trig ? vsb_dd_atan2(y, x) : atan2(y, x); }
 #endif
 
 #define VSO_PI 3.141592653589793 /* math.pi == np.pi */
@@ -697,14 +700,14 @@ static double solve_cubic_one(double a, double b, double c)
     double rq = r * r + q * q * q;
     double z1;
     if (rq > 0) {
-        double aa = pow(fabs(r) + sqrt(rq), 1.0 / 3);
+        double aa = t_pow(fabs(r) + sqrt(rq), 1.0 / 3);
         double t = r >= 0 ? aa - q / aa : q / aa - aa;
         z1 = t - a / 3;
     } else {
         double theta = 0;
-        if (q < 0) theta = acos(r / pow(-q, 3.0 / 2));
+        if (q < 0) theta = t_acos(r / t_pow(-q, 3.0 / 2));
         double fi = theta / 3;
-        z1 = 2 * sqrt(-q) * cos(fi) - a / 3;
+        z1 = 2 * sqrt(-q) * t_cos(fi) - a / 3;
     }
     return z1;
 }
@@ -766,7 +769,7 @@ int vso_ell_hyp_intersect_circle(double a, double b, double ecc, double c_x, dou
         for (int k = 0; k < cnt; ++k) if (rr[k] != 0.0) any = 1;
         if (!any) return 0;
         for (int k = 0; k < cnt; ++k)
-            ea4[k] = py_mod(atan2(2 * rr[k], 1.0 - rr[k] * rr[k]), 2 * VSO_PI);
+            ea4[k] = py_mod(t_atan2(2 * rr[k], 1.0 - rr[k] * rr[k]), 2 * VSO_PI);
         return cnt;
     }
     double a_0 = -(a * a) * (c_y * c_y + b * b) + b * b * ((c_x + r) * (c_x + r));
@@ -782,8 +785,8 @@ int vso_ell_hyp_intersect_circle(double a, double b, double ecc, double c_x, dou
     for (int k = 0; k < cnt; ++k) {
         double x = c_x + r * (1 - rr[k] * rr[k]) / (1 + rr[k] * rr[k]);
         double y = c_y + r * 2 * rr[k] / (1 + rr[k] * rr[k]);
-        double ta = atan2(y, x - (a * ecc));
-        double ea = acosh((ecc + cos(ta)) / (1 + (ecc * cos(ta))));
+        double ta = t_atan2(y, x - (a * ecc));
+        double ea = acosh((ecc + t_cos(ta)) / (1 + (ecc * t_cos(ta))));
         ea4[k] = rr[k] < 0 ? -ea : ea;
     }
     return cnt;

@@ -20,13 +20,13 @@ __device__ double solve_cubic_one(double a, double b, double c)
     double r = (b * a - 3 * c) / 6 - a * a * a / 27;
     double rq = r * r + q * q * q;
     if (rq > 0) {
-        double aa = pow(fabs(r) + sqrt(rq), 1.0 / 3);
+        double aa = pe_pow(fabs(r) + sqrt(rq), 1.0 / 3);
         double t = r >= 0 ? aa - q / aa : q / aa - aa;
         return t - a / 3;
     }
     double theta = 0;
-    if (q < 0) theta = acos(r / pow(-q, 3.0 / 2));
-    return 2 * sqrt(-q) * cos(theta / 3) - a / 3;
+    if (q < 0) theta = pe_acos(r / pe_pow(-q, 3.0 / 2));
+    return 2 * sqrt(-q) * pe_cos(theta / 3) - a / 3;
 }
 
 // cmath.sqrt of a real argument
@@ -105,12 +105,12 @@ __device__ int intersect_circle(double a, double b, double ecc, double c_x, doub
     if (!any) cnt = 0;
     for (int k = 0; k < cnt; ++k) {
         if (ecc < 1) {
-            out[k] = py_mod(atan2(2 * rr[k], 1.0 - rr[k] * rr[k]), 2 * PI_D);
+            out[k] = py_mod(pe_atan2(2 * rr[k], 1.0 - rr[k] * rr[k]), 2 * PI_D);
         } else {
             double x = c_x + r * (1 - rr[k] * rr[k]) / (1 + rr[k] * rr[k]);
             double y = c_y + r * 2 * rr[k] / (1 + rr[k] * rr[k]);
-            double ta = atan2(y, x - (a * ecc));
-            double ea = acosh((ecc + cos(ta)) / (1 + (ecc * cos(ta))));
+            double ta = pe_atan2(y, x - (a * ecc));
+            double ea = acosh((ecc + pe_cos(ta)) / (1 + (ecc * pe_cos(ta))));
             out[k] = rr[k] < 0 ? -ea : ea;
         }
     }
@@ -921,8 +921,24 @@ __global__ void points_select_kernel(int64_t nsel, const int64_t *__restrict__ s
 
 }  // namespace
 
+// pe_exact_trig of this file follows the context's mode (vsb_set_march_mode bit 1)
+static int set_exact_mode(vsb_ctx *c)
+{
+    static int last_of[64];                     // per device: 0 unknown, 1 + mode otherwise
+    const int exact = (c->march_sequential >> 1) & 1;
+    int &last = last_of[c->device & 63];
+    if (1 + exact != last) {
+        VSB_CUDA(cudaMemcpyToSymbolAsync(pe_exact_trig, &exact, sizeof(int), 0, cudaMemcpyHostToDevice,
+                                         c->stream));
+        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        last = 1 + exact;
+    }
+    return VSB_OK;
+}
+
 int vsb_launch_quartic(vsb_ctx *c, int64_t n, const double *d_coef, double *d_roots)
 {
+    VSB_TRY(set_exact_mode(c));
     if (n <= 0) return VSB_OK;
     quartic_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, d_coef, d_roots);
     c->launches += 1;
@@ -932,6 +948,7 @@ int vsb_launch_quartic(vsb_ctx *c, int64_t n, const double *d_coef, double *d_ro
 
 int vsb_launch_intersect(vsb_ctx *c, int64_t n, const double *d_in6, double *d_ea, int64_t *d_cnt)
 {
+    VSB_TRY(set_exact_mode(c));
     if (n <= 0) return VSB_OK;
     intersect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, d_in6, d_ea, d_cnt);
     c->launches += 1;
@@ -952,10 +969,8 @@ int vsb_launch_predict_enter_coi(vsb_ctx *c, int64_t n, const double *d_vd, cons
 {
     if (n <= 0) return VSB_OK;
     // bit 0: the serial loop, bit 1: exact trigonometry (vsb_set_march_mode)
-    const int exact = (sequential >> 1) & 1;
     sequential &= 1;
-    VSB_CUDA(cudaMemcpyToSymbolAsync(pe_exact_trig, &exact, sizeof(int), 0, cudaMemcpyHostToDevice,
-                                     c->stream));
+    VSB_TRY(set_exact_mode(c));
     mteam *team = (mteam *)d_work;
     VSB_CUDA(cudaMemsetAsync(team, 0, sizeof(mteam), c->stream));
     if (sequential) {
@@ -1007,6 +1022,7 @@ int vsb_launch_points_vessel(vsb_ctx *c, int64_t nsel, const int64_t *d_sel, con
                              int64_t left_coi, int only_enter_coi, double *d_impact, double *d_atm,
                              double *d_leave, double *d_ea_eff)
 {
+    VSB_TRY(set_exact_mode(c));
     if (nsel <= 0) return VSB_OK;
     points_vessel_kernel<<<(unsigned)((nsel + 127) / 128), 128, 0, c->stream>>>(
         nsel, d_sel, d_vessel12, d_vref, d_body12, entered_coi, left_coi, only_enter_coi, d_impact,
@@ -1022,6 +1038,7 @@ int vsb_launch_points_pairs(vsb_ctx *c, int64_t npairs, const int64_t *d_pair_s,
                             int64_t left_coi, const double *d_leave, const double *d_ea_eff,
                             double *d_vd10, double *d_bd10, unsigned char *d_valid)
 {
+    VSB_TRY(set_exact_mode(c));
     if (npairs <= 0) return VSB_OK;
     points_pair_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, c->stream>>>(
         npairs, d_pair_s, d_pair_body, d_sel, d_vessel12, d_vref, d_body12, left_coi, d_leave,
@@ -1036,6 +1053,7 @@ int vsb_launch_points_select(vsb_ctx *c, int64_t nsel, const int64_t *d_sel, con
                              const double *d_out5, const double *d_ea_eff, const double *d_vessel12,
                              double *d_enter)
 {
+    VSB_TRY(set_exact_mode(c));
     if (nsel <= 0) return VSB_OK;
     points_select_kernel<<<(unsigned)((nsel + 127) / 128), 128, 0, c->stream>>>(
         nsel, d_sel, d_offsets, d_pair_body, d_valid, d_out5, d_ea_eff, d_vessel12, d_enter);

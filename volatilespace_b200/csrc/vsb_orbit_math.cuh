@@ -11,12 +11,17 @@ constexpr double PI_D = 3.141592653589793;
 
 // "Exact trigonometry" mode of the COI-entry march (vsb_set_march_mode bit 1):
 // sin / cos evaluated in double-double arithmetic and rounded to nearest (vsb_ddtrig.h) instead of
-// CUDA's 1-2 ulp routines.  ~20x the cost of sin / cos; off by default.  One copy per including
-// file (only vsb_intersect.cu sets it).
+// CUDA's 1-2 ulp routines.  ~20x the cost of sin / cos; ON by default (vsb_set_march_mode).  One
+// copy per including file (only vsb_intersect.cu sets it, before every launch that reads it).
 __constant__ int pe_exact_trig = 0;
 
 __device__ __forceinline__ double pe_sin(double x) { return pe_exact_trig ? vsb_dd_sin(x) : sin(x); }
 __device__ __forceinline__ double pe_cos(double x) { return pe_exact_trig ? vsb_dd_cos(x) : cos(x); }
+// the same for the cubic / quartic of the orbit-circle intersections (pow, acos, atan2: one Newton
+// step in double-double from the library value, rounded to nearest)
+__device__ __forceinline__ double pe_pow(double x, double y) { return pe_exact_trig ? vsb_dd_pow(x, y) : pow(x, y); }
+__device__ __forceinline__ double pe_acos(double x) { return pe_exact_trig ? vsb_dd_acos(x) : acos(x); }
+__device__ __forceinline__ double pe_atan2(double y, double x) { return pe_exact_trig ? vsb_dd_atan2(y, x) : atan2(y, x); }
 
 // Python's float % (sign of the divisor)
 __device__ __forceinline__ double py_mod(double a, double b)
