@@ -88,7 +88,8 @@ def status():
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, "vsb_common.cuh"), os.path.join(CSRC, "vsb_orbit_math.cuh"),
-               os.path.join(CSRC, "vsb_grid.cuh"), INCLUDE, os.path.abspath(__file__)]
+               os.path.join(CSRC, "vsb_grid.cuh"), os.path.join(CSRC, "vsb_ddtrig.h"), INCLUDE,
+               os.path.abspath(__file__)]
     objs, procs = [], []
     env = dict(os.environ)
     env.pop("CC", None)    # the image exports a gcc wrapper nvcc should not pick up
