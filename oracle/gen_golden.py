@@ -1123,6 +1123,119 @@ def gen_fullsize(ns):
     save("body_move_deep", **out)
 
 
+def editor_hierarchy(n=4400, seed=20240612, coi_coef=0.7):
+    """A MODE_REF system above the 4096-body switch of the production kernels (the O(N) candidate
+    passes for find_parents / check_collision and the fixed-point rounds of simplified_orbit_coi):
+    root 0, 60 planets on exactly circular orbits, ~1500 moons inside the planets' COIs, 120
+    moonlets around heavy moons (depth 3), 400 bodies within 1.2 % of a planet's COI edge moving
+    radially (parent changes in both directions within a few frames), free bodies, and four planted
+    overlaps (free-free twice, moon-moon, planet-moon) that merge on the first frames."""
+    rng = np.random.default_rng(seed)
+    M0 = 1.0e7
+    mass = rng.uniform(0.5, 2.0, n)
+    den = np.full(n, 3.0e5)
+    pos = np.zeros((n, 2))
+    vel = np.zeros((n, 2))
+    mass[0] = M0
+
+    def circ(center, cvel, m_c, d, th, speed_mult=1.0):
+        u = np.stack([np.cos(th), np.sin(th)], axis=-1)
+        t = np.stack([-np.sin(th), np.cos(th)], axis=-1)
+        sp = np.sqrt(m_c / d) * speed_mult
+        return center + d[..., None] * u, cvel + sp[..., None] * t, u
+    npl = 60
+    pl = np.arange(1, 1 + npl)
+    mass[pl] = rng.uniform(2.0e3, 5.0e4, npl)
+    r_pl = np.sort(rng.uniform(2.0e5, 3.0e6, npl))
+    pos[pl], vel[pl], _ = circ(np.zeros(2), np.zeros(2), M0, r_pl, rng.uniform(0, 2 * np.pi, npl))
+    coi_pl = r_pl * (mass[pl] / M0) ** coi_coef
+    k = 1 + npl
+    # moons
+    nmoon = 1500
+    mo = np.arange(k, k + nmoon)
+    par = rng.integers(0, npl, nmoon)
+    d = coi_pl[par] * rng.uniform(0.05, 0.6, nmoon)
+    pos[mo], vel[mo], _ = circ(pos[pl][par], vel[pl][par], mass[pl][par], d, rng.uniform(0, 2 * np.pi, nmoon),
+                               rng.normal(1.0, 0.05, nmoon))
+    heavy = mo[:120]
+    mass[heavy] = rng.uniform(100.0, 400.0, 120)
+    k += nmoon
+    # moonlets around the heavy moons (their COI: ~d * (m / m_planet)^0.7)
+    ml = np.arange(k, k + 120)
+    d_h = np.linalg.norm(pos[heavy] - pos[pl][par[:120]], axis=1)
+    coi_h = d_h * (mass[heavy] / mass[pl][par[:120]]) ** coi_coef
+    mass[ml] = rng.uniform(0.01, 0.05, 120)
+    den[ml] = 3.0e7
+    pos[ml], vel[ml], _ = circ(pos[heavy], vel[heavy], mass[heavy], coi_h * rng.uniform(0.15, 0.5, 120),
+                               rng.uniform(0, 2 * np.pi, 120))
+    k += 120
+    # COI-edge crossers
+    ncr = 400
+    cr = np.arange(k, k + ncr)
+    cp = rng.integers(0, npl, ncr)
+    inside = rng.uniform(size=ncr) < 0.5
+    d = coi_pl[cp] * (1.0 + np.where(inside, -1.0, 1.0) * rng.uniform(0.0, 0.012, ncr))
+    pos[cr], vel[cr], u = circ(pos[pl][cp], vel[pl][cp], mass[pl][cp], d, rng.uniform(0, 2 * np.pi, ncr), 0.7)
+    vel[cr] += u * (np.where(inside, 1.0, -1.0) * coi_pl[cp] * rng.uniform(0.0008, 0.002, ncr))[:, None]
+    mass[cr] = rng.uniform(0.01, 0.5, ncr)
+    k += ncr
+    # free bodies around the root
+    fr = np.arange(k, n)
+    pos[fr], vel[fr], _ = circ(np.zeros(2), np.zeros(2), M0, rng.uniform(1.0e5, 3.5e6, len(fr)),
+                               rng.uniform(0, 2 * np.pi, len(fr)), rng.normal(1.0, 0.05, len(fr)))
+    # planted overlaps: radius = 179 cbrt(3 m / (4 pi den)) ~ 1.7 for m = 1
+    def touch(i, j, dist):
+        pos[j] = pos[i] + np.array([dist, 0.0])
+        vel[j] = vel[i]
+    touch(fr[10], fr[900], 1.0)
+    touch(fr[400], fr[77], 0.5)
+    touch(mo[700], mo[1300], 0.8)
+    touch(pl[17], mo[300], 20.0)          # planet radius ~ 60
+    return mass, den, np.ascontiguousarray(pos), np.ascontiguousarray(vel)
+
+
+def gen_editor_large(ns):
+    """MODE_REF frames of the GENUINE reference at 4400 bodies -- the size class in which the
+    library runs its O(N) candidate passes and fixed-point rounds instead of the small-system
+    kernels (phys_editor.py:325-378, 547-565, 844-857, 250-290).  Parents of every body on every
+    frame, deleted indices, body counts; the float state on sampled rows after load, after the
+    merges and at the end."""
+    import time
+    mass, den, pos, vel = editor_hierarchy()
+    n = len(mass)
+    t0 = time.time()
+    ph = rh.editor_from_arrays(ns, mass, den, pos, vel)
+    print("editor_large: load %.1f s" % (time.time() - t0))
+    out = dict(mass=mass, den=den, pos0=pos, vel0=vel, frames=np.int64(8))
+    rng = np.random.default_rng(5)
+
+    def sampled(tag):
+        m = len(ph.mass)
+        rows = np.sort(rng.choice(m, 1200, replace=False))
+        out[tag + "rows"] = rows
+        for k2, v in snap(ph, tag).items():
+            out[k2] = v if k2.endswith("parents") else v[rows]
+    sampled("f0_")
+    dels, counts = [], []
+    for fr in range(1, 9):
+        t0 = time.time()
+        d = rh.editor_frame(ph)
+        dels.append(d[0] if d else -1)
+        counts.append(len(ph.mass))
+        out["parents_f%d" % fr] = np.array(ph.parents, dtype=np.int16)
+        print("editor_large: frame %d %.1f s, deleted %s, %d bodies" % (fr, time.time() - t0, d, len(ph.mass)))
+        if fr in (4, 8):
+            sampled("f%d_" % fr)
+    out["deleted"] = np.array(dels)
+    out["counts"] = np.array(counts)
+    changes = sum(int((out["parents_f%d" % (f + 1)] != out["parents_f%d" % f]).sum())
+                  for f in range(5, 8))
+    print("editor_large: merges %d, parent changes on frames 6-8: %d, depth-2 parents %d" % (
+        (np.array(dels) >= 0).sum(), changes, int((out["f0_parents"] > 60).sum())))
+    assert n - counts[-1] >= 3 and changes >= 20 and (out["f0_parents"] > 60).sum() >= 60
+    save("editor_large", **out)
+
+
 def main():
     """All fixtures, or only the ones named on the command line (e.g. `vessel_points`)."""
     ns = rh.load()
@@ -1145,6 +1258,7 @@ def main():
     if want("mapfiles"): gen_mapfiles(ns, conf, bd, bod)
     if want("convert_vel"): gen_convert_vel(ns)
     if want("fullsize"): gen_fullsize(ns)
+    if want("editor_large"): gen_editor_large(ns)
 
 
 if __name__ == "__main__":

@@ -648,6 +648,18 @@ def test_editor_cloud_merges(dev, frame_fn):
             check_snapshot(ph, g, "B_f%d_" % fr, 1e-9)
 
 
+def test_editor_large_frames_vs_live_reference(dev, frame_fn):
+    """4400 bodies -- above the 4096-body switch, so find_parents and check_collision run their
+    sort-based candidate passes and simplified_orbit_coi its fixed-point rounds -- eight
+    free-running frames against the GENUINE reference (fixture editor_large, oracle/gen_golden.py):
+    parents of all bodies on every frame (depth-3 hierarchy, COI crossings both ways), four merges
+    incl. planet + moon, deleted indices and counts bit-exact."""
+    from test_oracle_golden import check_sampled_snapshot, run_editor_large
+    g = golden("editor_large")
+    ph = make_editor(dev, g["mass"], g["den"], g["pos0"], g["vel0"])
+    run_editor_large(ph, g, frame_fn, lambda e, gg, pre, tol: check_sampled_snapshot(e, gg, pre, tol, pull=True))
+
+
 def test_toy_collision_semantics(dev):
     g = golden("editor_clouds")
     ph = make_editor(dev, g["C_mass"], g["C_den"], g["C_pos0"], g["C_vel0"])
