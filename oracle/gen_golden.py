@@ -1236,6 +1236,39 @@ def gen_editor_large(ns):
     save("editor_large", **out)
 
 
+def gen_convert_large(ns, conf):
+    """N1 at 4400 bodies (above the 4096-body switch: the fixed-point rounds over the candidate
+    pass instead of the blocked sweep): the GENUINE convert.to_kepler (convert.py:132-261) on the
+    editor_large system with every index but the root scrambled.  refs of all bodies, elements on
+    sampled rows; the inputs are editor_large's arrays + the stored permutation."""
+    import time
+    sys.path.insert(0, rh.REFERENCE_ROOT)
+    from volatilespace.physics import convert
+    sys.path.remove(rh.REFERENCE_ROOT)
+    mass, den, pos, vel = editor_hierarchy()
+    n = len(mass)
+    # the four planted partners share their partner's velocity exactly; next to a planet that is a
+    # radial orbit on which the reference divides by zero (convert.py:252): give them a push
+    _, first, counts = np.unique(vel, axis=0, return_index=True, return_counts=True)
+    dup = np.setdiff1d(np.arange(n), first)
+    assert len(dup) == 4
+    vel = vel.copy()
+    vel[dup] += np.array([0.05, 0.3])
+    rng = np.random.default_rng(20240613)
+    perm = np.concatenate(([0], 1 + rng.permutation(n - 1)))
+    t0 = time.time()
+    k = convert.to_kepler(mass[perm], {"pos": pos[perm].copy(), "vel": vel[perm].copy()}, conf["gc"],
+                          conf["coi_coef"])
+    print("convert_large: to_kepler %.1f s, %d refs != 0" % (time.time() - t0, int((np.array(k["ref"]) != 0).sum())))
+    rows = np.sort(rng.choice(n, 1200, replace=False))
+    out = dict(perm=perm.astype(np.int16), rows=rows, pushed=dup.astype(np.int16), push=np.array([0.05, 0.3]), k_ref=np.array(k["ref"], dtype=np.int16),
+               gc=conf["gc"], coi_coef=conf["coi_coef"])
+    for key in ("a", "ecc", "pe_arg", "ma", "dir"):
+        out["k_" + key] = np.array(k[key])[rows]
+    assert (out["k_ref"] != 0).sum() > 300
+    save("convert_large", **out)
+
+
 def main():
     """All fixtures, or only the ones named on the command line (e.g. `vessel_points`)."""
     ns = rh.load()
@@ -1259,6 +1292,7 @@ def main():
     if want("convert_vel"): gen_convert_vel(ns)
     if want("fullsize"): gen_fullsize(ns)
     if want("editor_large"): gen_editor_large(ns)
+    if want("convert_large"): gen_convert_large(ns, conf)
 
 
 if __name__ == "__main__":

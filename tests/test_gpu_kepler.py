@@ -377,6 +377,19 @@ def test_to_kepler_multi_slab_vs_oracle(dev, oracle, monkeypatch, mode, rounds, 
                                    err_msg=key)
 
 
+@pytest.mark.parametrize("mode", ["grid", "scan"])
+def test_convert_large_vs_live_reference(dev, monkeypatch, mode):
+    """N1 at 4400 bodies against the GENUINE reference (fixture convert_large): the fixed-point
+    rounds over the candidate pass (default from 4096 bodies) and the blocked sweep -- refs of all
+    bodies bit-exact (index quirks included), elements of the sampled rows within 1e-10."""
+    from test_oracle_golden import check_convert_large, convert_large_inputs
+    from volatilespace_b200 import convert
+    monkeypatch.setenv("VSB_PARENTS", mode)
+    mass, pos, vel, g = convert_large_inputs()
+    k = convert.to_kepler(mass, {"pos": pos, "vel": vel}, float(g["gc"]), float(g["coi_coef"]), device=dev)
+    check_convert_large(k, g, 1e-10)
+
+
 def test_intersect_kernels_golden(dev):
     """N2: batched solve_quartic / ell_hyp_intersect_circle / predict_enter_coi against the
     live reference's jitted functions."""

@@ -344,6 +344,31 @@ def test_convert(oracle):
         oracle.to_newton(g["c60_mass"], orb, gc, cc)
 
 
+def convert_large_inputs():
+    """Inputs of the convert_large fixture: editor_large's system, the four planted partners pushed
+    off their radial orbits, every index but the root scrambled."""
+    e, g = golden("editor_large"), golden("convert_large")
+    vel = e["vel0"].copy()
+    vel[g["pushed"]] += g["push"]
+    perm = g["perm"].astype(np.int64)
+    return e["mass"][perm], np.ascontiguousarray(e["pos0"][perm]), np.ascontiguousarray(vel[perm]), g
+
+
+def check_convert_large(k, g, rtol):
+    assert np.array_equal(k["ref"], g["k_ref"])
+    assert (g["k_ref"] != 0).sum() > 300
+    for key in ("a", "ecc", "pe_arg", "ma", "dir"):
+        np.testing.assert_allclose(np.asarray(k[key])[g["rows"]], g["k_" + key], rtol=rtol, atol=1e-12,
+                                   equal_nan=True, err_msg=key)
+
+
+def test_convert_large(oracle):
+    """to_kepler of the GENUINE reference at 4400 bodies, scrambled index order (its index quirks
+    decide 772 refs): refs of all bodies bit-exact, elements of the sampled rows."""
+    mass, pos, vel, g = convert_large_inputs()
+    check_convert_large(oracle.to_kepler(mass, pos, vel, float(g["gc"]), float(g["coi_coef"])), g, 1e-13)
+
+
 # ------------------------------------------------------------- N2 COI-crossing kernels
 def test_intersect_kernels(oracle):
     g = golden("intersect")
