@@ -843,8 +843,12 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "parity": parity,
         "sym_sched": _lib.sym_schedule(),
-        "roofline": roofline(pairs / (ms_accel * 1e-3), fp64_flops_peak, clocks, ms_accel, ops_per_pair,
-                             kernel_name, "%s@%s@%dgpu" % (kernel_name, args.workload, world)),
+        # per GPU: each rank's share of the pairs over the slowest rank's kernel time, against ONE
+        # GPU's peak
+        "roofline": dict(roofline(pairs / world / (ms_accel * 1e-3), fp64_flops_peak, clocks, ms_accel,
+                                  ops_per_pair, kernel_name,
+                                  "%s@%s@%dgpu" % (kernel_name, args.workload, world)),
+                         scope="per GPU (1/%d of the pairs per launch)" % world),
         "peaks_source": peaks_src,
     }
     if line["sym_sched"] != "resched":
