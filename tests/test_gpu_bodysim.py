@@ -605,6 +605,32 @@ def test_fused_frame_is_bit_identical_to_per_call_path(dev):
                 assert np.array_equal(x, y), (case, fr)
 
 
+def test_fused_frame_mapped_record_equals_copy_path(dev, monkeypatch):
+    """The fused frame hands its results to the host through mapped page-locked memory (the kernel
+    writes the record, then a sequence word the host spins on); VSB_NO_MAPPED_FRAME=1 goes through
+    cudaMemcpyAsync + cudaStreamSynchronize.  Same frames, bit for bit, eager and lazy mirrors,
+    incl. frames with merges and the per-method gravity() of small systems."""
+    g = golden("editor_clouds")
+    runs = {}
+    for mode in ("mapped", "copy"):
+        if mode == "copy":
+            monkeypatch.setenv("VSB_NO_MAPPED_FRAME", "1")
+        for case, frames, warp in (("A", 40, 1), ("B", 60, 2)):
+            ph = make_editor(dev, g[case + "_mass"], g[case + "_den"], g[case + "_pos0"], g[case + "_vel0"])
+            log = []
+            for fr in range(frames):
+                d = ph.frame(warp) if fr % 3 else ph.frame_calls(warp)
+                ph.pull()
+                log.append((d, ph.pos.copy(), ph.vel.copy(), ph.rel_vel.copy(), ph.parents.copy(), ph.coi.copy()))
+            runs[mode, case] = log
+    for case in ("A", "B"):
+        for x, y in zip(runs["mapped", case], runs["copy", case]):
+            assert x[0] == y[0]
+            for u, v in zip(x[1:], y[1:]):
+                assert np.array_equal(u, v), case
+    assert any(x[0] for x in runs["mapped", "B"])          # merges happened
+
+
 def test_solar_system_frames(dev, frame_fn):
     """BASELINE config 1: built-in map, MODE_REF, 10 000 faithful editor frames."""
     g = golden("solar_editor")

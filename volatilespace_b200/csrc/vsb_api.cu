@@ -1,6 +1,8 @@
 // vsb_api.cu -- C ABI of libvsb200.so (see include/vsb200.h for the contract and
 // the reference interfaces each entry point stands behind).
 #include <stdarg.h>
+#include <string.h>
+#include <atomic>
 #include <stdlib.h>
 
 #include <new>
@@ -161,6 +163,7 @@ extern "C" int vsb_ctx_destroy(vsb_ctx *c)
     vsb_buf_free(c->march_stats);
     if (c->d_key) cudaFree(c->d_key);
     if (c->h_key) cudaFreeHost(c->h_key);
+    if (c->h_frame) cudaFreeHost(c->h_frame);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -371,6 +374,58 @@ static int upload_order(vsb_ctx *c, const char *who, const int64_t *order)
     return VSB_OK;
 }
 
+// The fused small-system frame / tick (n <= 1024, one CTA) and its results on the host: h[0..3] =
+// ticks done, del, add, chain-overflow flag; frame_out (optional) receives the frame record.
+// The kernel writes the record and the header straight into mapped page-locked host memory and then
+// a sequence word the host spins on -- no copy call and no stream synchronise on the 60 Hz path (a
+// launch-latency bound frame at 15 bodies: 25 k -> 36 k frames per second).  VSB_NO_MAPPED_FRAME=1
+// goes through cudaMemcpyAsync + cudaStreamSynchronize instead (same results).
+static int run_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order, int max_ticks,
+                           int do_kepler_basic, int do_collision, void *frame_out, int64_t *h)
+{
+    const size_t rec_words = 4 + 14 * (size_t)c->n;
+    if (!getenv("VSB_NO_MAPPED_FRAME")) {
+        const size_t flag_at = 4 + 14 * (size_t)1024;
+        if (!c->h_frame) {
+            const size_t cap = 8 * (flag_at + 8);
+            VSB_CUDA(cudaHostAlloc((void **)&c->h_frame, cap, cudaHostAllocMapped));
+            VSB_CUDA(cudaHostGetDevicePointer((void **)&c->d_frame, c->h_frame, 0));
+            memset(c->h_frame, 0, cap);
+        }
+        volatile long long *flag = (volatile long long *)(c->h_frame + flag_at);
+        const long long seq = ++c->frame_seq;
+        VSB_TRY(vsb_launch_editor_frame_small(c, gc, coi_coef, d_order, max_ticks, do_kepler_basic,
+                                              do_collision, frame_out ? c->d_frame : nullptr,
+                                              (long long *)(c->d_frame + flag_at), seq));
+        for (unsigned spins = 1; *flag != seq; ++spins) {
+            if ((spins & 0x3fff) == 0) {             // a faulting kernel never publishes
+                cudaError_t q = cudaStreamQuery(c->stream);
+                if (q == cudaSuccess && *flag != seq) q = cudaErrorUnknown;
+                if (q != cudaErrorNotReady)
+                    VSB_CHECK(*flag == seq, VSB_ERR_CUDA, "fused frame kernel -> %s", cudaGetErrorString(q));
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (frame_out) memcpy(frame_out, c->h_frame, 8 * rec_words);
+        for (int k = 0; k < 4; ++k) h[k] = (int64_t)flag[1 + k];
+        return VSB_OK;
+    }
+    if (frame_out) {
+        VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * rec_words));
+        double *d_packed = (double *)c->host_stage.p;
+        VSB_TRY(vsb_launch_editor_frame_small(c, gc, coi_coef, d_order, max_ticks, do_kepler_basic,
+                                              do_collision, d_packed));
+        VSB_TRY(d2h(c, frame_out, d_packed, 8 * rec_words));
+        memcpy(h, frame_out, 4 * sizeof(int64_t));
+        return VSB_OK;
+    }
+    VSB_TRY(vsb_launch_editor_frame_small(c, gc, coi_coef, d_order, max_ticks, do_kepler_basic,
+                                          do_collision, nullptr));
+    VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
 extern "C" int vsb_find_parents(vsb_ctx *c, const int64_t *order, int64_t *parents_out)
 {
     CTX(c);
@@ -389,12 +444,8 @@ extern "C" int vsb_gravity_ref(vsb_ctx *c, double gc, const int64_t *order)
     VSB_TRY(upload_order(c, "vsb_gravity_ref", order));
     if (c->n <= 1024 && !getenv("VSB_NO_FUSED_FRAME")) {
         // small systems: the whole tick in one single-CTA launch (bit-identical results)
-        VSB_TRY(vsb_launch_editor_frame_small(c, gc, 0.0, (const int64_t *)c->order.p, 1, 0, 0,
-                                              nullptr));
         int64_t *h = (int64_t *)c->h_key;
-        VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                 c->stream));
-        VSB_CUDA(cudaStreamSynchronize(c->stream));
+        VSB_TRY(run_frame_small(c, gc, 0.0, (const int64_t *)c->order.p, 1, 0, 0, nullptr, h));
         VSB_CHECK(h[3] == 0, VSB_ERR_STATE, "vsb_gravity_ref: parent chain deeper than 48 levels");
         return VSB_OK;
     }
@@ -554,21 +605,7 @@ extern "C" int vsb_editor_ticks(vsb_ctx *c, double gc, double coi_coef, const in
     int64_t *h = (int64_t *)c->h_key;
     if (c->n <= 1024 && !getenv("VSB_NO_FUSED_FRAME")) {
         VSB_CHECK(max_ticks < (1ll << 30), VSB_ERR_ARG, "vsb_editor_ticks: max_ticks too large");
-        double *d_packed = nullptr;
-        if (frame_out) {
-            VSB_TRY(vsb_buf_reserve(c->host_stage, 8 * rec_words));
-            d_packed = (double *)c->host_stage.p;
-        }
-        VSB_TRY(vsb_launch_editor_frame_small(c, gc, coi_coef, d_order, (int)max_ticks,
-                                              do_kepler_basic, 1, d_packed));
-        if (frame_out) {
-            VSB_TRY(d2h(c, frame_out, d_packed, 8 * rec_words));
-            h = (int64_t *)frame_out;
-        } else {
-            VSB_CUDA(cudaMemcpyAsync(h, c->scratch.p, 4 * sizeof(int64_t),
-                                     cudaMemcpyDeviceToHost, c->stream));
-            VSB_CUDA(cudaStreamSynchronize(c->stream));
-        }
+        VSB_TRY(run_frame_small(c, gc, coi_coef, d_order, (int)max_ticks, do_kepler_basic, 1, frame_out, h));
         VSB_CHECK(h[3] == 0, VSB_ERR_STATE, "vsb_editor_ticks: parent chain deeper than 48 levels");
         *ticks_done = h[0];
         *del_out = h[1];

@@ -111,6 +111,11 @@ struct vsb_ctx {
     int march_sequential = 2;  // vsb_set_march_mode: bit 0 the one-thread-per-pair serial march, bit 1 exact trigonometry (default on)
     unsigned long long *d_key = nullptr;   // collision key (device)
     unsigned long long *h_key = nullptr;   // pinned mirror
+    // fused small-system frame: results written by the kernel straight into mapped page-locked host
+    // memory (record + a sequence word the host spins on): no copy call, no stream synchronise
+    double *h_frame = nullptr;             // host address; d_frame is the device alias
+    double *d_frame = nullptr;
+    long long frame_seq = 0;
     double *h_pin = nullptr;               // pinned scratch (small)
     size_t h_pin_bytes = 0;
 
@@ -313,7 +318,7 @@ int vsb_launch_translate(vsb_ctx *c, int64_t ref_row);
 int vsb_launch_pad_tail(vsb_ctx *c);
 int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order,
                                   int max_ticks, int do_kepler_basic, int do_collision,
-                                  double *d_packed);
+                                  double *d_packed, long long *d_flag = nullptr, long long seq = 0);
 int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptrs,
                            const int *widths, int nfields, double *d_out, int64_t *words_out);
 int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double *d_out);

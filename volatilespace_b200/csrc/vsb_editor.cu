@@ -500,7 +500,7 @@ editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int 
                           double2 *g_pos, double2 *g_vel, double2 *g_rel_vel, double *g_coi,
                           const double *__restrict__ g_rad, int64_t *g_parents, double *g_focus,
                           double2 *g_ecc_v, double *g_semi_major, double *g_semi_minor,
-                          double *g_periapsis_arg, int64_t *hdr, double *packed)
+                          double *g_periapsis_arg, int64_t *hdr, double *packed, long long *host_flag, long long seq)
 {
     extern __shared__ double2 fr_smem[];
     double2 *s_pos = fr_smem, *s_vel = s_pos + n, *s_rv = s_vel + n, *s_spos = s_rv + n;
@@ -699,6 +699,12 @@ editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int 
             (q + 13 * n)[t] = o.coi;
         }
     }
+    if (host_flag) {
+        // `packed` is mapped host memory: every thread's record words are made visible to the host
+        // before thread 0 publishes the sequence word the host spins on
+        __threadfence_system();
+        __syncthreads();
+    }
     if (t == 0) {
         hdr[0] = ticks;
         hdr[1] = hit_del;
@@ -710,6 +716,15 @@ editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int 
             ph[1] = hit_del;
             ph[2] = hit_add;
             ph[3] = s_overflow;
+        }
+        if (host_flag) {
+            // header copy next to the sequence word (the caller may not have asked for the record)
+            host_flag[1] = ticks;
+            host_flag[2] = hit_del;
+            host_flag[3] = hit_add;
+            host_flag[4] = s_overflow;
+            __threadfence_system();
+            *(volatile long long *)host_flag = seq;
         }
     }
 }
@@ -944,7 +959,7 @@ int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double 
 // Fused small-N frame; hdr (4 x int64) lands in c->scratch.p.  n <= 1024 only.
 int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t *d_order,
                                   int max_ticks, int do_kepler_basic, int do_collision,
-                                  double *d_packed)
+                                  double *d_packed, long long *d_flag, long long seq)
 {
     const int n = (int)c->n;
     VSB_CHECK(n >= 1 && n <= FR_MAX, VSB_ERR_ARG, "editor_frame_small: n=%d", n);
@@ -959,7 +974,7 @@ int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const 
         (double2 *)c->pos,
         (double2 *)c->vel, (double2 *)c->rel_vel, c->coi, c->rad, c->parents, c->focus,
         (double2 *)c->ecc_v, c->semi_major, c->semi_minor, c->periapsis_arg,
-        (int64_t *)c->scratch.p, d_packed);
+        (int64_t *)c->scratch.p, d_packed, d_flag, seq);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;
