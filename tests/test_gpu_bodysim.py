@@ -576,10 +576,16 @@ def check_snapshot(ph, g, prefix, rtol):
             np.testing.assert_allclose(got, want, rtol=rtol, atol=1e-300, err_msg=prefix + k)
 
 
-@pytest.fixture(params=["fused", "calls"])
-def frame_fn(request):
-    """Physics.frame (fused vsb_editor_ticks driver) and Physics.frame_calls (the individual
-    gravity(); body(); inelastic_collision(); kepler_basic() calls of editor.py:1503-1523)."""
+@pytest.fixture(params=["fused", "calls", "calls_general"])
+def frame_fn(request, monkeypatch):
+    """Physics.frame (fused vsb_editor_ticks driver), Physics.frame_calls (the individual
+    gravity(); body(); inelastic_collision(); kepler_basic() calls of editor.py:1503-1523; small
+    systems: one launch of the fused kernel per call, results through mapped host memory) and the
+    same calls on the GENERAL kernels (the ones systems above 1024 bodies run: per-pass launches,
+    exhaustive scans, copy calls) forced onto the small fixtures."""
+    if request.param == "calls_general":
+        monkeypatch.setenv("VSB_NO_FUSED_FRAME", "1")
+        monkeypatch.setenv("VSB_NO_MAPPED_FRAME", "1")
     name = "frame" if request.param == "fused" else "frame_calls"
     return lambda ph, warp=1: getattr(ph, name)(warp)
 

@@ -729,6 +729,65 @@ editor_frame_small_kernel(int n, int max_ticks, double gc, double coi_coef, int 
     }
 }
 
+// check_collision (phys_editor.py:547-551) of a small system (n <= 1024) in ONE launch of one CTA:
+// thread i scans j > i in ascending order for the first touching body (the same un-fused predicate as
+// cc_scan_kernel's exact path and the fused frame), the CTA takes the smallest (i, j), the lighter
+// body is deleted (ties delete i, :93-97).  The answer goes to out2 (device) and, when host_flag is
+// given, into mapped host memory: host_flag[1..2] = (del, add), then host_flag[0] = seq.
+__global__ void __launch_bounds__(FR_MAX)
+collision_small_kernel(int n, const double2 *__restrict__ g_pos, const double *__restrict__ g_rad,
+                       const double *__restrict__ g_mass, int64_t *out2, long long *host_flag,
+                       long long seq)
+{
+    extern __shared__ double2 cs_smem[];
+    double2 *s_pos = cs_smem;
+    double *s_rad = (double *)(s_pos + n);
+    __shared__ unsigned long long s_key[32];
+    const int t = threadIdx.x;
+    if (t < n) {
+        s_pos[t] = g_pos[t];
+        s_rad[t] = g_rad[t];
+    }
+    __syncthreads();
+    unsigned long long key = ~0ull;
+    if (t < n - 1) {
+        const double2 me = s_pos[t];
+        const double ri = s_rad[t];
+        for (int j = t + 1; j < n; ++j) {
+            double dx = me.x - s_pos[j].x, dy = me.y - s_pos[j].y;
+            double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            if (d <= __dadd_rn(ri, s_rad[j])) {
+                key = ((unsigned long long)t << 32) | (unsigned)j;
+                break;
+            }
+        }
+    }
+    key = warp_min_u64(key);
+    if ((t & 31) == 0) s_key[t >> 5] = key;
+    __syncthreads();
+    if (t < 32) {
+        key = t < (int)(blockDim.x >> 5) ? s_key[t] : ~0ull;
+        key = warp_min_u64(key);
+        if (t == 0) {
+            long long del = -1, add = -1;
+            if (key != ~0ull) {
+                const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
+                const bool first = g_mass[i] <= g_mass[j];
+                del = first ? i : j;
+                add = first ? j : i;
+            }
+            out2[0] = del;
+            out2[1] = add;
+            if (host_flag) {
+                host_flag[1] = del;
+                host_flag[2] = add;
+                __threadfence_system();
+                *(volatile long long *)host_flag = seq;
+            }
+        }
+    }
+}
+
 // gather several body fields into one contiguous staging buffer (one D2H copy per frame)
 struct pack_desc {
     const double *src[16];
@@ -745,6 +804,22 @@ __global__ void pack_fields_kernel(pack_desc d, int64_t n, double *__restrict__ 
         if (i < words) out[off + i] = d.src[f][i];
         off += words;
     }
+}
+
+// the same for a small system, in one CTA, straight into mapped host memory: `out` and host_flag are
+// device aliases of page-locked host words; the sequence word is published after the data
+__global__ void __launch_bounds__(1024)
+pack_fields_small_kernel(pack_desc d, int64_t n, double *out, long long *host_flag, long long seq)
+{
+    int64_t off = 0;
+    for (int f = 0; f < d.count; ++f) {
+        const int64_t words = n * d.width[f];
+        for (int64_t i = threadIdx.x; i < words; i += blockDim.x) out[off + i] = d.src[f][i];
+        off += words;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile long long *)host_flag = seq;
 }
 
 body_arrays arrays_of(vsb_ctx *c)
@@ -980,9 +1055,25 @@ int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const 
     return VSB_OK;
 }
 
+// check_collision of a small system in one launch; (del, add) in c->scratch.p and, with d_flag, in
+// mapped host memory (see collision_small_kernel).  n <= 1024 only.
+int vsb_launch_check_collision_small(vsb_ctx *c, long long *d_flag, long long seq)
+{
+    const int n = (int)c->n;
+    VSB_CHECK(n >= 1 && n <= FR_MAX, VSB_ERR_ARG, "check_collision_small: n=%d", n);
+    VSB_TRY(vsb_buf_reserve(c->scratch, 64));
+    const int threads = (n + 31) / 32 * 32;
+    collision_small_kernel<<<1, threads, (size_t)n * (sizeof(double2) + sizeof(double)), c->stream>>>(
+        n, (const double2 *)c->pos, c->rad, c->mass, (int64_t *)c->scratch.p, d_flag, seq);
+    c->launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    return VSB_OK;
+}
+
 // Packs `nfields` body fields (ids of enum vsb_body_field) into d_out, concatenated.
 int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptrs,
-                           const int *widths, int nfields, double *d_out, int64_t *words_out)
+                           const int *widths, int nfields, double *d_out, int64_t *words_out,
+                           long long *d_flag, long long seq)
 {
     (void)fields;
     pack_desc d;
@@ -996,6 +1087,12 @@ int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptr
     }
     *words_out = total;
     if (maxw == 0) return VSB_OK;
+    if (d_flag) {
+        pack_fields_small_kernel<<<1, 1024, 0, c->stream>>>(d, c->n, d_out, d_flag, seq);
+        c->launches += 1;
+        VSB_CUDA(cudaGetLastError());
+        return VSB_OK;
+    }
     pack_fields_kernel<<<(unsigned)((maxw + 255) / 256), 256, 0, c->stream>>>(d, c->n, d_out);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());

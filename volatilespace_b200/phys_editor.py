@@ -315,9 +315,23 @@ class Physics(_DeviceBodies):
     # phys_editor.py:357-378
     def gravity(self):
         order = None if self._order_on_device else self._order()
+        if self._small_eager():
+            # one launch: the fused kernel runs the tick and leaves the frame record in mapped
+            # host memory (its collision answer is not used here)
+            rec = np.empty(4 + 14 * len(self.mass))
+            self.dev.editor_ticks(self.gc, self.coi_coef, order, 1, do_kepler_basic=False, frame_out=rec)
+            self._order_on_device = True
+            self._unpack_frame(rec, ("pos", "vel", "rel_vel", "parents"))
+            return
         self.dev.gravity_ref(self.gc, order)
         self._order_on_device = True
         self._touched("parents", "rel_vel", "vel", "pos")
+
+    def _small_eager(self):
+        """Eager host mirrors of a system the fused one-CTA kernel serves (up to 1024 bodies): the
+        per-method calls then take one launch each and read their results from mapped host memory
+        instead of a kernel + a packing kernel + a copy."""
+        return self.sync == "eager" and 0 < len(self.mass) <= 1024
 
     # phys_editor.py:577-599.  Everything here depends on mass, den and the atmosphere parameters
     # only, so it is recomputed when one of those changed (the reference recomputes it every tick)
@@ -370,6 +384,13 @@ class Physics(_DeviceBodies):
 
     # phys_editor.py:381-384
     def kepler_basic(self):
+        if self._small_eager():
+            rec = np.empty(4 + 14 * len(self.mass))
+            order = None if self._order_on_device else self._order()
+            self.dev.editor_ticks(self.gc, self.coi_coef, order, 0, do_kepler_basic=True, frame_out=rec)
+            self._order_on_device = True
+            self._unpack_frame(rec, ("focus", "ecc_v", "semi_major", "semi_minor", "periapsis_arg", "coi"))
+            return
         self.dev.kepler_basic(self.gc, self.coi_coef)
         self._touched("focus", "ecc_v", "semi_major", "semi_minor", "periapsis_arg", "coi")
 
@@ -655,14 +676,16 @@ class Physics(_DeviceBodies):
                 break
         return deleted
 
-    def _unpack_frame(self, rec):
-        """Frame record of vsb_editor_ticks -> host mirrors (in place)."""
+    def _unpack_frame(self, rec, fields=None):
+        """Frame record of vsb_editor_ticks -> host mirrors (in place); `fields`: only those."""
         n = len(self.mass)
         off = 4
         for k in self._FRAME_FIELDS:
             w = 2 if k in _WIDE else 1
             chunk = rec[off:off + n * w]
             off += n * w
+            if fields is not None and k not in fields:
+                continue
             dst = getattr(self, k)
             if k == "parents":
                 dst[:] = chunk.view(np.int64)
