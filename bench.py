@@ -260,8 +260,10 @@ def extra_workloads(torch, dev, stream, peaks, fp64_ops_peak, with_cpu=True):
             ed.frame()
         res["cpu_port_frames_per_s_1thread"] = 2000 / (time.perf_counter() - t0)
         orc.lib().vso_set_num_threads(os.cpu_count() or 1)
-        res["note"] = ("frame = fused vsb_editor_ticks driver (1 launch + 1 packed read-back), "
-                       "frame_calls = per-method calls; eager host mirrors in both")
+        res["note"] = ("frame = fused vsb_editor_ticks driver (1 launch, the frame record written by the "
+                       "kernel into mapped host memory), frame_calls = the reference's per-method calls "
+                       "(gravity / body / inelastic_collision / kepler_basic: one launch each on small "
+                       "systems); eager host mirrors in both")
         out["solar_system_editor"] = res
     except Exception as e:
         out["solar_system_editor"] = {"error": str(e)[:200]}
