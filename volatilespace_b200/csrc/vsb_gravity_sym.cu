@@ -334,10 +334,10 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
     int64_t want_tasks = (int64_t)c->sm_count * 32 * world;
     int chunk = (int)(pairs / want_tasks);
     if (chunk < 1) chunk = 1;
-    // host-side task table (cached per n / world / rank / shape / tail setting)
+    // host-side task table (cached per padded size / world / rank / shape / tail setting)
     const char *tail_env = getenv("VSB_SYM_TAIL");
     const int tail_split = tail_env ? atoi(tail_env) : 8;
-    if (c->sym_tasks_n != n || c->sym_world != world || c->sym_rank != rank || c->sym_S != S ||
+    if (c->sym_tasks_n != npad || c->sym_world != world || c->sym_rank != rank || c->sym_S != S ||
         c->sym_tail != tail_split) {
         // cost unit: one block pair, one side (the diagonal pair runs the directed formula: 1)
         struct item { sym_task t; int cost; };
@@ -439,7 +439,7 @@ int VSB_SYM_LAUNCHER(vsb_ctx *c, double gc, int rank, int world, int integrate)
         VSB_CUDA(cudaStreamSynchronize(c->stream));
         c->sym_own_off = (int64_t)(of - (char *)c->sym_tab.p);
         c->sym_ownlist_off = (int64_t)(ol - (char *)c->sym_tab.p);
-        c->sym_tasks_n = n;
+        c->sym_tasks_n = npad;   // the table depends on the padded size only (a merge rarely changes it)
         c->sym_tail = tail_split;
         c->sym_S = S;
         c->sym_world = world;

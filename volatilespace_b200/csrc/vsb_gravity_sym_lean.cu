@@ -416,7 +416,7 @@ int vsb_launch_allpairs_sym_lean(vsb_ctx *c, double gc, int rank, int world, int
     int pool = (int)((32u << 20) / (sizeof(double2) * (size_t)S));
     if (pool < 2 * M + 2 * slots) pool = 2 * M + 2 * slots;
     // host-side ticket list + expectation table (cached per n / world / rank / shape)
-    if (c->lean_tasks_n != n || c->lean_world != world || c->lean_rank != rank || c->lean_S != S ||
+    if (c->lean_tasks_n != npad || c->lean_world != world || c->lean_rank != rank || c->lean_S != S ||
         c->lean_chunk != key_chunk) {
         // Rows are dealt to the ranks whole (descending, boustrophedon: 0..w-1, w-1..0, ...), so
         // that every rank's rows are waves of its own CTAs and the loads differ by a short row.
@@ -456,7 +456,7 @@ int vsb_launch_allpairs_sym_lean(vsb_ctx *c, double gc, int rank, int world, int
         VSB_CUDA(cudaMemcpyAsync((char *)c->lean_tab.p + tab_bytes, expect.data(),
                                  sizeof(int) * expect.size(), cudaMemcpyHostToDevice, c->stream));
         VSB_CUDA(cudaStreamSynchronize(c->stream));
-        c->lean_tasks_n = n;
+        c->lean_tasks_n = npad;   // the table depends on the padded size only
         c->lean_S = S;
         c->lean_world = world;
         c->lean_rank = rank;
