@@ -261,6 +261,11 @@ int vsb_kepler_device_ptr(vsb_ctx *ctx, int kind, int field, void **dptr_out);
  *     device-resident BODY state's positions).
  * Includes C2/C3.  Results stay on the device (fetch with vsb_kepler_get). */
 int vsb_kepler_move(vsb_ctx *ctx, int kind, double warp, const double *body_pos, int64_t nref);
+/* The same move with its results handed back in the same call -- what Physics.move returns
+ * (phys_body.py:346 -> (pos, ma, ea); phys_vessel.py:494): pos_out (N,2), ma_out (N,), ea_out (N,),
+ * one wait instead of a launch + three copies (small states: through mapped page-locked memory). */
+int vsb_kepler_move_state(vsb_ctx *ctx, int kind, double warp, const double *body_pos, int64_t nref,
+                          double *pos_out, double *ma_out, double *ea_out);
 
 /* C5+C6 fused: Physics.curve(i) for all i + Physics.curve_move() (phys_body.py:315-320,
  * 405-411; phys_vessel.py:364-369,497-503): writes the moved curves (N,P,2) into the
@@ -275,6 +280,9 @@ int vsb_kepler_free(vsb_ctx *ctx, int kind);
 /* Copy curves of objects [first, first+count) to the host, layout (count,P,2);
  * only visible curves are ever consumed by the caller (game.py:1403-1407). */
 int vsb_kepler_curves_get(vsb_ctx *ctx, int kind, int64_t first, int64_t count, double *out);
+/* Physics.curve_move() (phys_body.py:405-411, phys_vessel.py:497-503) in one call: vsb_kepler_curves
+ * + the copy of all N moved curves (N,P,2) to the host, one wait. */
+int vsb_kepler_curve_move(vsb_ctx *ctx, int kind, double *out);
 int vsb_kepler_curves_device_ptr(vsb_ctx *ctx, int kind, void **dptr_out);
 
 /* --------------------------------------------- Newton <-> Kepler conversion

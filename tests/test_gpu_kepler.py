@@ -133,6 +133,40 @@ def test_game_vessel_path_golden(dev):
     assert np.all(np.abs(cm - g["v_curves_mov"]) <= 1e-12 * scale)
 
 
+@pytest.mark.parametrize("n", [200, 5000])
+def test_move_state_and_curve_move_equal_the_separate_calls(dev, monkeypatch, n):
+    """vsb_kepler_move_state / vsb_kepler_curve_move (move or curves + their results in one call,
+    one wait; small states through mapped page-locked memory) against vsb_kepler_move +
+    vsb_kepler_get x 3 and vsb_kepler_curves + vsb_kepler_curves_get: bit for bit, on 200 objects
+    (mapped path), 5000 (copies) and with the mapped path switched off."""
+    from volatilespace_b200 import synth
+    from volatilespace_b200._lib import KIND_VESSEL, K_EA, K_MA, K_POS
+    k = synth.kepler_objects(n, seed=77)
+    P = 16
+
+    def load():
+        dev.kepler_load(KIND_VESSEL, P, k["a"], k["b"], k["f"], k["ecc"], k["pea"], k["n"], k["dr"],
+                        k["ma"], k["ea"], k["ref"])
+    load()
+    want = []
+    for warp in (1.0, 3.0, 2.0):
+        dev.kepler_move(KIND_VESSEL, warp, k["body_pos"])
+        dev.kepler_curves(KIND_VESSEL)
+        want.append([dev.kepler_get(KIND_VESSEL, f, n) for f in (K_POS, K_MA, K_EA)]
+                    + [dev.kepler_curves_get(KIND_VESSEL, 0, n, P)])
+    for mapped in (True, False):
+        if not mapped:
+            monkeypatch.setenv("VSB_NO_MAPPED_FRAME", "1")
+        load()
+        pos, ma, ea = np.empty((n, 2)), np.empty(n), np.empty(n)
+        for step, warp in enumerate((1.0, 3.0, 2.0)):
+            dev.kepler_move_state(KIND_VESSEL, warp, k["body_pos"], pos, ma, ea)
+            cur = dev.kepler_curve_move(KIND_VESSEL, n, P)
+            for got, w in zip((pos, ma, ea, cur), want[step]):
+                assert np.array_equal(got, w, equal_nan=True), (mapped, step)
+    dev.kepler_free(KIND_VESSEL)
+
+
 def test_vessel_borrows_resident_body_positions(dev):
     """vessel move with body_pos=None uses the device-resident BODY positions (no host round
     trip): identical to passing the same positions from the host, also after a BODY reload."""

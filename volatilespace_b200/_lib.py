@@ -94,11 +94,13 @@ SIGNATURES = {
     "vsb_kepler_get": [_ctx, C.c_int, C.c_int, _pv, _i64, _i64],
     "vsb_kepler_device_ptr": [_ctx, C.c_int, C.c_int, C.POINTER(C.c_void_p)],
     "vsb_kepler_move": [_ctx, C.c_int, _f64, _pv, _i64],
+    "vsb_kepler_move_state": [_ctx, C.c_int, _f64, _pv, _i64, _pv, _pv, _pv],
     "vsb_kepler_curves": [_ctx, C.c_int],
     "vsb_kepler_tick": [_ctx, C.c_int, _f64, _pv, _i64],
     "vsb_kepler_tick_async": [_ctx, C.c_int, _f64],
     "vsb_kepler_free": [_ctx, C.c_int],
     "vsb_kepler_curves_get": [_ctx, C.c_int, _i64, _i64, _pv],
+    "vsb_kepler_curve_move": [_ctx, C.c_int, _pv],
     "vsb_kepler_curves_device_ptr": [_ctx, C.c_int, C.POINTER(C.c_void_p)],
     "vsb_host_to_kepler": [_ctx, _i64, _pv, _pv, _pv, _pv, _f64, _f64] + [_pv] * 6,
     "vsb_host_to_newton": [_ctx, _i64] + [_pv] * 7 + [_f64, _pv, _pv],

@@ -1238,6 +1238,43 @@ extern "C" int vsb_kepler_move(vsb_ctx *c, int kind, double warp, const double *
     return VSB_OK;
 }
 
+// C1 / C4 with the results handed back in the same call: move + (pos, ma, ea) of all objects on the
+// host with ONE wait (phys_body.Physics.move -> (pos, ma, ea), phys_body.py:346; phys_vessel's
+// :494).  Small states (up to 3 584 objects) come back through mapped page-locked memory: one CTA
+// packs the three fields there and publishes a sequence word -- no copy call, no synchronise.
+extern "C" int vsb_kepler_move_state(vsb_ctx *c, int kind, double warp, const double *body_pos,
+                                     int64_t nref, double *pos_out, double *ma_out, double *ea_out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_move_state", kind, &k));
+    VSB_CHECK(k->n > 0, VSB_ERR_STATE, "vsb_kepler_move_state: no state loaded for this kind");
+    VSB_CHECK(pos_out && ma_out && ea_out, VSB_ERR_ARG, "vsb_kepler_move_state: null output");
+    if (kind == VSB_KIND_VESSEL) VSB_TRY(vessel_ref_pos(c, *k, body_pos, nref));
+    VSB_TRY(keep_prev_ea(c, *k));
+    VSB_TRY(vsb_launch_kepler_move(c, *k, warp));
+    const size_t n = (size_t)k->n;
+    if (4 * n <= k_flag_at && !getenv("VSB_NO_MAPPED_FRAME")) {
+        VSB_TRY(mapped_area(c));
+        const void *ptrs[3] = {k->pos, k->ma, k->ea};
+        const int widths[3] = {2, 1, 1};
+        int64_t total = 0;
+        const long long seq = ++c->frame_seq;
+        VSB_TRY(vsb_launch_pack_fields(c, nullptr, ptrs, widths, 3, c->d_frame, &total,
+                                       (long long *)(c->d_frame + k_flag_at), seq, k->n));
+        VSB_TRY(mapped_wait(c, seq, "vsb_kepler_move_state"));
+        memcpy(pos_out, c->h_frame, 16 * n);
+        memcpy(ma_out, c->h_frame + 2 * n, 8 * n);
+        memcpy(ea_out, c->h_frame + 3 * n, 8 * n);
+        return VSB_OK;
+    }
+    VSB_CUDA(cudaMemcpyAsync(pos_out, k->pos, 16 * n, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(ma_out, k->ma, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaMemcpyAsync(ea_out, k->ea, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
+    return VSB_OK;
+}
+
 static int reserve_curves(vsb_kepler_state &k)
 {
     return vsb_buf_reserve(k.curves, 16 * (size_t)k.n * (size_t)k.P);
@@ -1309,6 +1346,35 @@ extern "C" int vsb_kepler_curves_get(vsb_ctx *c, int kind, int64_t first, int64_
               (long long)(first + count), (long long)k->n);
     const size_t stride = 16 * (size_t)k->P;
     return d2h(c, out, (char *)k->curves.p + stride * first, stride * count);
+}
+
+// C5 + C6 with the result handed back in the same call: vsb_kepler_curves + vsb_kepler_curves_get
+// of all objects, one wait; up to 114 KB of curves come back through mapped page-locked memory.
+extern "C" int vsb_kepler_curve_move(vsb_ctx *c, int kind, double *out)
+{
+    CTX(c);
+    vsb_kepler_state *k;
+    VSB_TRY(kep_of(c, "vsb_kepler_curve_move", kind, &k));
+    VSB_CHECK(k->n > 0 && out, VSB_ERR_STATE, "vsb_kepler_curve_move: no state loaded / null output");
+    if (kind == VSB_KIND_VESSEL)
+        VSB_CHECK(k->ref_pos != nullptr, VSB_ERR_STATE,
+                  "vsb_kepler_curve_move(VESSEL): call vsb_kepler_move first (parent positions)");
+    VSB_TRY(reserve_curves(*k));
+    VSB_TRY(vsb_launch_kepler_curves(c, *k, 0, k->n, (double *)k->curves.p, 1));
+    const size_t words = 2 * (size_t)k->n * (size_t)k->P;
+    if (words <= k_flag_at && !getenv("VSB_NO_MAPPED_FRAME")) {
+        VSB_TRY(mapped_area(c));
+        const void *ptrs[1] = {k->curves.p};
+        const int widths[1] = {1};
+        int64_t total = 0;
+        const long long seq = ++c->frame_seq;
+        VSB_TRY(vsb_launch_pack_fields(c, nullptr, ptrs, widths, 1, c->d_frame, &total,
+                                       (long long *)(c->d_frame + k_flag_at), seq, (int64_t)words));
+        VSB_TRY(mapped_wait(c, seq, "vsb_kepler_curve_move"));
+        memcpy(out, c->h_frame, 8 * words);
+        return VSB_OK;
+    }
+    return d2h(c, out, k->curves.p, 8 * words);
 }
 
 extern "C" int vsb_kepler_curves_device_ptr(vsb_ctx *c, int kind, void **out)

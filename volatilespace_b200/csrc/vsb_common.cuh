@@ -322,7 +322,7 @@ int vsb_launch_editor_frame_small(vsb_ctx *c, double gc, double coi_coef, const 
 int vsb_launch_check_collision_small(vsb_ctx *c, long long *d_flag, long long seq);
 int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptrs,
                            const int *widths, int nfields, double *d_out, int64_t *words_out,
-                           long long *d_flag = nullptr, long long seq = 0);
+                           long long *d_flag = nullptr, long long seq = 0, int64_t rows = -1);
 int vsb_launch_editor_curve(vsb_ctx *c, int64_t P, const double *d_tabs, double *d_out);
 // culling / visible subset (vsb_visible.cu)
 int vsb_launch_culling_flags(vsb_ctx *c, const double *d_pos, const double *d_radius,

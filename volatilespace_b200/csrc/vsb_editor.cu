@@ -1073,27 +1073,28 @@ int vsb_launch_check_collision_small(vsb_ctx *c, long long *d_flag, long long se
 // Packs `nfields` body fields (ids of enum vsb_body_field) into d_out, concatenated.
 int vsb_launch_pack_fields(vsb_ctx *c, const int *fields, const void *const *ptrs,
                            const int *widths, int nfields, double *d_out, int64_t *words_out,
-                           long long *d_flag, long long seq)
+                           long long *d_flag, long long seq, int64_t rows)
 {
     (void)fields;
+    const int64_t n = rows >= 0 ? rows : c->n;     // rows of every field (default: the bodies)
     pack_desc d;
     d.count = nfields;
     int64_t maxw = 0, total = 0;
     for (int f = 0; f < nfields; ++f) {
         d.src[f] = (const double *)ptrs[f];
         d.width[f] = widths[f];
-        total += c->n * widths[f];
-        if (c->n * widths[f] > maxw) maxw = c->n * widths[f];
+        total += n * widths[f];
+        if (n * widths[f] > maxw) maxw = n * widths[f];
     }
     *words_out = total;
     if (maxw == 0) return VSB_OK;
     if (d_flag) {
-        pack_fields_small_kernel<<<1, 1024, 0, c->stream>>>(d, c->n, d_out, d_flag, seq);
+        pack_fields_small_kernel<<<1, 1024, 0, c->stream>>>(d, n, d_out, d_flag, seq);
         c->launches += 1;
         VSB_CUDA(cudaGetLastError());
         return VSB_OK;
     }
-    pack_fields_kernel<<<(unsigned)((maxw + 255) / 256), 256, 0, c->stream>>>(d, c->n, d_out);
+    pack_fields_kernel<<<(unsigned)((maxw + 255) / 256), 256, 0, c->stream>>>(d, n, d_out);
     c->launches += 1;
     VSB_CUDA(cudaGetLastError());
     return VSB_OK;

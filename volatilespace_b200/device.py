@@ -369,6 +369,19 @@ class Device:
         check(self.L.vsb_kepler_move(self.h, kind, float(warp), ptr(bp),
                                      0 if bp is None else len(bp)))
 
+    def kepler_move_state(self, kind, warp, body_pos, pos, ma, ea):
+        """move + (pos, ma, ea) of all objects into the given float64 arrays, one wait."""
+        bp = None if body_pos is None else f64(body_pos)
+        check(self.L.vsb_kepler_move_state(self.h, kind, float(warp), ptr(bp), 0 if bp is None else len(bp),
+                                           ptr(pos), ptr(ma), ptr(ea)))
+
+    def kepler_curve_move(self, kind, count, P, out=None):
+        """curves of all objects + their copy to the host (count, P, 2), one wait."""
+        if out is None:
+            out = np.empty((count, P, 2))
+        check(self.L.vsb_kepler_curve_move(self.h, kind, ptr(out)))
+        return out
+
     def kepler_curves(self, kind):
         check(self.L.vsb_kepler_curves(self.h, kind))
 

@@ -104,11 +104,7 @@ class Physics:
 
     # phys_body.py:323-346 -> (pos (N,2), ma (N,), ea (N,)), refreshed in place
     def move(self, warp):
-        self.dev.kepler_move(KIND_BODY, warp)
-        n = self.n_bodies
-        self.dev.kepler_get(KIND_BODY, K_POS, n, out=self.pos)
-        self.dev.kepler_get(KIND_BODY, K_MA, n, out=self.ma)
-        self.dev.kepler_get(KIND_BODY, K_EA, n, out=self.ea)
+        self.dev.kepler_move_state(KIND_BODY, warp, None, self.pos, self.ma, self.ea)
         return self.pos, self.ma, self.ea
 
     # phys_body.py:315-320: relative curve of one body, (P,2)
@@ -120,9 +116,9 @@ class Physics:
     # phys_body.py:405-411 -> (N,P,2); `visible` limits the copy to the curves the
     # caller draws (game.py:1403-1407), the full set stays resident on the device
     def curve_move(self, visible=None):
-        self.dev.kepler_curves(KIND_BODY)
         if visible is None:
-            return self.dev.kepler_curves_get(KIND_BODY, 0, self.n_bodies, self.curve_points)
+            return self.dev.kepler_curve_move(KIND_BODY, self.n_bodies, self.curve_points)
+        self.dev.kepler_curves(KIND_BODY)
         got = self.dev.kepler_curves_gather(KIND_BODY, visible, self.curve_points, reuse=True)
         return {int(i): got[k] for k, i in enumerate(visible)}
 

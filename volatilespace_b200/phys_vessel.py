@@ -104,11 +104,7 @@ class Physics:
         if body_ea is not None:
             self.body_ea = np.asarray(body_ea, dtype=np.float64)
         self.prev_ea = np.array(self.ea)
-        self.dev.kepler_move(KIND_VESSEL, warp, body_pos)
-        n = self.n_vessels
-        self.dev.kepler_get(KIND_VESSEL, K_POS, n, out=self.pos)
-        self.dev.kepler_get(KIND_VESSEL, K_MA, n, out=self.ma)
-        self.dev.kepler_get(KIND_VESSEL, K_EA, n, out=self.ea)
+        self.dev.kepler_move_state(KIND_VESSEL, warp, body_pos, self.pos, self.ma, self.ea)
         return self.pos, self.ma
 
     # phys_vessel.py:372-474; vessel=None processes every vessel (the loop of initial())
@@ -236,9 +232,9 @@ class Physics:
 
     # phys_vessel.py:497-503
     def curve_move(self, visible=None):
-        self.dev.kepler_curves(KIND_VESSEL)
         if visible is None:
-            return self.dev.kepler_curves_get(KIND_VESSEL, 0, self.n_vessels, self.curve_points)
+            return self.dev.kepler_curve_move(KIND_VESSEL, self.n_vessels, self.curve_points)
+        self.dev.kepler_curves(KIND_VESSEL)
         got = self.dev.kepler_curves_gather(KIND_VESSEL, visible, self.curve_points, reuse=True)
         return {int(i): got[k] for k, i in enumerate(visible)}
 
