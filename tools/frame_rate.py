@@ -43,3 +43,22 @@ b, pb = rate("frame", 5000, "VSB_NO_MAPPED_FRAME")
 c, _ = rate("frame_calls", 500)
 print("fused frame, mapped host record: %.0f frames/s; through a copy call: %.0f frames/s; per-method calls: "
       "%.0f frames/s; identical positions after the same number of frames: %s" % (a, b, c, np.array_equal(pa, pb)))
+
+# the editor also asks for the orbit curves of every body on every frame (editor.py:1604)
+ph = Physics(dev, curve_points=300)
+ph.load_system({"gc": float(g["gc"]), "rad_mult": float(g["rad_mult"]), "coi_coef": float(g["coi_coef"])},
+               {"mass": g["mass"], "den": g["den"]}, {"pos": g["pos0"], "vel": g["vel0"]})
+ph.kepler_basic()
+for _ in range(100):
+    ph.frame()
+    ph.curve()
+t0 = time.perf_counter()
+for _ in range(3000):
+    ph.curve()
+t1 = time.perf_counter()
+for _ in range(3000):
+    ph.frame()
+    ph.curve()
+t2 = time.perf_counter()
+print("curve() of 15 bodies x 300 points: %.1f us per call; frame() + curve(): %.1f us = %.0f frames/s" % (
+    (t1 - t0) / 3000 * 1e6, (t2 - t1) / 3000 * 1e6, 3000 / (t2 - t1)))

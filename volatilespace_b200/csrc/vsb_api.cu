@@ -154,6 +154,7 @@ extern "C" int vsb_ctx_destroy(vsb_ctx *c)
     free_kepler(c->kep[1]);
     vsb_buf_free(c->part);
     vsb_buf_free(c->sym_tab);
+    vsb_buf_free(c->curve_tabs);
     vsb_buf_free(c->lean_tab);
     vsb_buf_free(c->order);
     vsb_buf_free(c->sorted);
@@ -164,6 +165,7 @@ extern "C" int vsb_ctx_destroy(vsb_ctx *c)
     if (c->d_key) cudaFree(c->d_key);
     if (c->h_key) cudaFreeHost(c->h_key);
     if (c->h_frame) cudaFreeHost(c->h_frame);
+    free(c->h_curve_tabs);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -842,12 +844,24 @@ extern "C" int vsb_editor_curve(vsb_ctx *c, int64_t P, const double *ell_t, cons
     VSB_TRY(need_bodies(c, "vsb_editor_curve"));
     VSB_CHECK(P > 0 && ell_t && par_t && out, VSB_ERR_ARG, "vsb_editor_curve: bad argument");
     const size_t out_bytes = sizeof(double) * 2 * (size_t)c->n * (size_t)P;
-    VSB_TRY(vsb_buf_reserve(c->host_stage, out_bytes + sizeof(double) * 2 * (size_t)P));
+    const size_t tab_bytes = sizeof(double) * 2 * (size_t)P;
+    VSB_TRY(vsb_buf_reserve(c->host_stage, out_bytes));
     double *d_out = (double *)c->host_stage.p;
-    double *d_tabs = (double *)((char *)c->host_stage.p + out_bytes);
-    VSB_TRY(h2d(c, d_tabs, ell_t, sizeof(double) * (size_t)P));
-    VSB_TRY(h2d(c, d_tabs + P, par_t, sizeof(double) * (size_t)P));
-    VSB_TRY(vsb_launch_editor_curve(c, P, d_tabs, d_out));
+    // the parameter tables change with the settings only (editor.py calls curve() every frame):
+    // they stay on the device and are re-sent when their contents differ
+    if (c->curve_tabs_P != P || !c->h_curve_tabs || memcmp(c->h_curve_tabs, ell_t, tab_bytes / 2) != 0 ||
+        memcmp(c->h_curve_tabs + P, par_t, tab_bytes / 2) != 0) {
+        c->curve_tabs_P = 0;
+        VSB_TRY(vsb_buf_reserve(c->curve_tabs, tab_bytes));
+        double *h = (double *)realloc(c->h_curve_tabs, tab_bytes);
+        VSB_CHECK(h != nullptr, VSB_ERR_NOMEM, "vsb_editor_curve: out of host memory");
+        c->h_curve_tabs = h;
+        memcpy(h, ell_t, tab_bytes / 2);
+        memcpy(h + P, par_t, tab_bytes / 2);
+        VSB_TRY(h2d(c, c->curve_tabs.p, h, tab_bytes));
+        c->curve_tabs_P = P;
+    }
+    VSB_TRY(vsb_launch_editor_curve(c, P, (const double *)c->curve_tabs.p, d_out));
     return d2h(c, out, d_out, out_bytes);
 }
 

@@ -116,6 +116,11 @@ struct vsb_ctx {
     double *h_frame = nullptr;             // host address; d_frame is the device alias
     double *d_frame = nullptr;
     long long frame_seq = 0;
+    // editor curve(): the parameter tables last uploaded (host copy + device copy), re-sent only when
+    // they change (reload_settings)
+    vsb_buf curve_tabs;
+    double *h_curve_tabs = nullptr;
+    int64_t curve_tabs_P = 0;
     double *h_pin = nullptr;               // pinned scratch (small)
     size_t h_pin_bytes = 0;
 
