@@ -166,6 +166,7 @@ extern "C" int vsb_ctx_destroy(vsb_ctx *c)
     if (c->h_key) cudaFreeHost(c->h_key);
     if (c->h_frame) cudaFreeHost(c->h_frame);
     free(c->h_curve_tabs);
+    free(c->h_small);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -410,6 +411,37 @@ static int mapped_wait(vsb_ctx *c, long long seq, const char *who)
         }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    return VSB_OK;
+}
+
+// A few small device results -> host with ONE wait: nf segments of `words[f]` 8-byte words each.
+// Up to 14 340 words in all they are packed by one CTA into mapped page-locked memory, followed by a
+// sequence word the host spins on (no copy call, no synchronise); above, or with
+// VSB_NO_MAPPED_FRAME, asynchronous copies and one synchronise.
+static int d2h_small(vsb_ctx *c, int nf, const void *const *src, const int *words, void *const *dst,
+                     const char *who)
+{
+    size_t total_words = 0;
+    for (int f = 0; f < nf; ++f) total_words += (size_t)words[f];
+    if (total_words == 0) return VSB_OK;
+    if (nf <= 16 && total_words <= k_flag_at && !getenv("VSB_NO_MAPPED_FRAME")) {
+        VSB_TRY(mapped_area(c));
+        int64_t total = 0;
+        const long long seq = ++c->frame_seq;
+        VSB_TRY(vsb_launch_pack_fields(c, nullptr, src, words, nf, c->d_frame, &total,
+                                       (long long *)(c->d_frame + k_flag_at), seq, 1));
+        VSB_TRY(mapped_wait(c, seq, who));
+        const double *h = c->h_frame;
+        for (int f = 0; f < nf; ++f) {
+            memcpy(dst[f], h, 8 * (size_t)words[f]);
+            h += words[f];
+        }
+        return VSB_OK;
+    }
+    for (int f = 0; f < nf; ++f)
+        if (words[f])
+            VSB_CUDA(cudaMemcpyAsync(dst[f], src[f], 8 * (size_t)words[f], cudaMemcpyDeviceToHost, c->stream));
+    VSB_CUDA(cudaStreamSynchronize(c->stream));
     return VSB_OK;
 }
 
@@ -1979,7 +2011,12 @@ extern "C" int vsb_vessel_check_warp(vsb_ctx *c, double warp, int64_t *out3)
     VSB_TRY(vsb_launch_check_warp(c, k->n, k->ecc, k->dr, k->ea, k->ma, k->nmot, k->ev_impact,
                                   k->ev_atm, k->ev_leave, k->ev_enter, warp, k->ev_hold, d_key));
     unsigned long long key[2];
-    VSB_TRY(d2h(c, key, d_key, 16));
+    {
+        const void *src[1] = {d_key};
+        const int words[1] = {2};
+        void *dst[1] = {key};
+        VSB_TRY(d2h_small(c, 1, src, words, dst, "vsb_vessel_check_warp"));
+    }
     out3[0] = out3[1] = -1;
     if (key[0]) {
         out3[0] = (int64_t)(key[0] & 3);
@@ -2000,7 +2037,12 @@ extern "C" int vsb_vessel_cross_scan(vsb_ctx *c, int64_t *out2)
     VSB_TRY(vsb_launch_cross_scan(c, k->n, k->ecc, k->dr, k->ev_prev_ea, k->ea, k->ev_impact,
                                   k->ev_leave, k->ev_enter, d_key));
     unsigned long long key;
-    VSB_TRY(d2h(c, &key, d_key, 8));
+    {
+        const void *src[1] = {d_key};
+        const int words[1] = {1};
+        void *dst[1] = {&key};
+        VSB_TRY(d2h_small(c, 1, src, words, dst, "vsb_vessel_cross_scan"));
+    }
     out2[0] = -1;
     out2[1] = 0;
     if (key != ~0ull) {
@@ -2186,6 +2228,22 @@ static int vis_finish(vsb_ctx *c, vis_stage &st, int64_t n, int64_t *idx_out, in
 {
     VSB_TRY(vsb_launch_compact(c, st.flags, n, st.counts, st.total, st.idx));
     int64_t count = 0;
+    if (idx_out && n + 1 <= (int64_t)k_flag_at && !getenv("VSB_NO_MAPPED_FRAME")) {
+        // small lists: the count and all n index slots in one round trip (the first `count` are valid)
+        if (c->h_small_cap < 8 * (size_t)n) {
+            void *h = realloc(c->h_small, 8 * (size_t)n);
+            VSB_CHECK(h != nullptr, VSB_ERR_NOMEM, "compaction result: out of host memory");
+            c->h_small = h;
+            c->h_small_cap = 8 * (size_t)n;
+        }
+        const void *src[2] = {st.total, st.idx};
+        const int words[2] = {1, (int)n};
+        void *dst[2] = {&count, c->h_small};
+        VSB_TRY(d2h_small(c, 2, src, words, dst, "compaction result"));
+        *count_out = count;
+        if (count > 0) memcpy(idx_out, c->h_small, 8 * (size_t)count);
+        return VSB_OK;
+    }
     VSB_TRY(d2h(c, &count, st.total, sizeof(int64_t)));
     *count_out = count;
     if (count > 0 && idx_out) VSB_TRY(d2h(c, idx_out, st.idx, 8 * (size_t)count));

@@ -119,6 +119,8 @@ struct vsb_ctx {
     // editor curve(): the parameter tables last uploaded (host copy + device copy), re-sent only when
     // they change (reload_settings)
     vsb_buf curve_tabs;
+    void *h_small = nullptr;               // plain host scratch of the small-result path
+    size_t h_small_cap = 0;
     double *h_curve_tabs = nullptr;
     int64_t curve_tabs_P = 0;
     double *h_pin = nullptr;               // pinned scratch (small)
