@@ -377,24 +377,29 @@ static int upload_order(vsb_ctx *c, const char *who, const int64_t *order)
     return VSB_OK;
 }
 
-// The fused small-system frame / tick (n <= 1024, one CTA) and its results on the host: h[0..3] =
-// ticks done, del, add, chain-overflow flag; frame_out (optional) receives the frame record.
-// The kernel writes the record and the header straight into mapped page-locked host memory and then
-// a sequence word the host spins on -- no copy call and no stream synchronise on the 60 Hz path (a
-// launch-latency bound frame at 15 bodies: 25 k -> 36 k frames per second).  VSB_NO_MAPPED_FRAME=1
-// goes through cudaMemcpyAsync + cudaStreamSynchronize instead (same results).
 // Mapped page-locked result area of the small-system kernels: [frame record: 4 + 14 * 1024 words]
 // [sequence word][4 header words][3 spare].
 static const size_t k_flag_at = 4 + 14 * (size_t)1024;
 
-static int mapped_area(vsb_ctx *c)
+// true when results may go through the mapped area: not switched off (VSB_NO_MAPPED_FRAME) and the
+// mapped page-locked allocation exists -- a refused allocation (locked-memory limit) is remembered
+// and every caller falls back to its copy path: the mapped words are an optimisation, never a
+// requirement
+static bool use_mapped(vsb_ctx *c)
 {
-    if (c->h_frame) return VSB_OK;
+    if (getenv("VSB_NO_MAPPED_FRAME") || c->mapped_refused) return false;
+    if (c->h_frame) return true;
     const size_t cap = 8 * (k_flag_at + 8);
-    VSB_CUDA(cudaHostAlloc((void **)&c->h_frame, cap, cudaHostAllocMapped));
-    VSB_CUDA(cudaHostGetDevicePointer((void **)&c->d_frame, c->h_frame, 0));
+    if (cudaHostAlloc((void **)&c->h_frame, cap, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&c->d_frame, c->h_frame, 0) != cudaSuccess) {
+        cudaGetLastError();            // clear the (non-sticky) allocation error
+        if (c->h_frame) cudaFreeHost(c->h_frame);
+        c->h_frame = nullptr;
+        c->mapped_refused = true;
+        return false;
+    }
     memset(c->h_frame, 0, cap);
-    return VSB_OK;
+    return true;
 }
 
 // spins until the kernel launched last has published `seq` (a faulting kernel never does: the
@@ -424,8 +429,7 @@ static int d2h_small(vsb_ctx *c, int nf, const void *const *src, const int *word
     size_t total_words = 0;
     for (int f = 0; f < nf; ++f) total_words += (size_t)words[f];
     if (total_words == 0) return VSB_OK;
-    if (nf <= 16 && total_words <= k_flag_at && !getenv("VSB_NO_MAPPED_FRAME")) {
-        VSB_TRY(mapped_area(c));
+    if (nf <= 16 && total_words <= k_flag_at && use_mapped(c)) {
         int64_t total = 0;
         const long long seq = ++c->frame_seq;
         VSB_TRY(vsb_launch_pack_fields(c, nullptr, src, words, nf, c->d_frame, &total,
@@ -457,8 +461,7 @@ static int run_frame_small(vsb_ctx *c, double gc, double coi_coef, const int64_t
                            int do_kepler_basic, int do_collision, void *frame_out, int64_t *h)
 {
     const size_t rec_words = 4 + 14 * (size_t)c->n;
-    if (!getenv("VSB_NO_MAPPED_FRAME")) {
-        VSB_TRY(mapped_area(c));
+    if (use_mapped(c)) {
         const long long seq = ++c->frame_seq;
         VSB_TRY(vsb_launch_editor_frame_small(c, gc, coi_coef, d_order, max_ticks, do_kepler_basic,
                                               do_collision, frame_out ? c->d_frame : nullptr,
@@ -712,10 +715,9 @@ extern "C" int vsb_bodies_get_many(vsb_ctx *c, const int *fields, int nfields, v
         words += (size_t)c->n * widths[f];
     }
     int64_t total = 0;
-    if (c->n <= 1024 && words <= k_flag_at && !getenv("VSB_NO_MAPPED_FRAME")) {
+    if (c->n <= 1024 && words <= k_flag_at && use_mapped(c)) {
         // small systems: one CTA packs the fields straight into mapped host memory and publishes a
         // sequence word (no copy call, no stream synchronise: 30 -> 12 us per pull)
-        VSB_TRY(mapped_area(c));
         const long long seq = ++c->frame_seq;
         VSB_TRY(vsb_launch_pack_fields(c, fields, ptrs, widths, nfields, c->d_frame, &total,
                                        (long long *)(c->d_frame + k_flag_at), seq));
@@ -766,10 +768,9 @@ extern "C" int vsb_check_collision(vsb_ctx *c, int64_t *del_out, int64_t *add_ou
     VSB_CHECK(del_out && add_out, VSB_ERR_ARG, "vsb_check_collision: null output");
     VSB_TRY(need_bodies(c, "vsb_check_collision"));
     int64_t *h = (int64_t *)c->h_key;
-    if (c->n >= 1 && c->n <= 1024 && !getenv("VSB_COLLISION") && !getenv("VSB_NO_MAPPED_FRAME")) {
+    if (c->n >= 1 && c->n <= 1024 && !getenv("VSB_COLLISION") && use_mapped(c)) {
         // small systems: one launch of one CTA, the answer through mapped host memory (the three
         // launches + copy + synchronise of the general path take 56 us at 15 bodies, this 12)
-        VSB_TRY(mapped_area(c));
         const long long seq = ++c->frame_seq;
         VSB_TRY(vsb_launch_check_collision_small(c, (long long *)(c->d_frame + k_flag_at), seq));
         VSB_TRY(mapped_wait(c, seq, "vsb_check_collision"));
@@ -1300,8 +1301,7 @@ extern "C" int vsb_kepler_move_state(vsb_ctx *c, int kind, double warp, const do
     VSB_TRY(keep_prev_ea(c, *k));
     VSB_TRY(vsb_launch_kepler_move(c, *k, warp));
     const size_t n = (size_t)k->n;
-    if (4 * n <= k_flag_at && !getenv("VSB_NO_MAPPED_FRAME")) {
-        VSB_TRY(mapped_area(c));
+    if (4 * n <= k_flag_at && use_mapped(c)) {
         const void *ptrs[3] = {k->pos, k->ma, k->ea};
         const int widths[3] = {2, 1, 1};
         int64_t total = 0;
@@ -1408,8 +1408,7 @@ extern "C" int vsb_kepler_curve_move(vsb_ctx *c, int kind, double *out)
     VSB_TRY(reserve_curves(*k));
     VSB_TRY(vsb_launch_kepler_curves(c, *k, 0, k->n, (double *)k->curves.p, 1));
     const size_t words = 2 * (size_t)k->n * (size_t)k->P;
-    if (words <= k_flag_at && !getenv("VSB_NO_MAPPED_FRAME")) {
-        VSB_TRY(mapped_area(c));
+    if (words <= k_flag_at && use_mapped(c)) {
         const void *ptrs[1] = {k->curves.p};
         const int widths[1] = {1};
         int64_t total = 0;
@@ -2228,7 +2227,7 @@ static int vis_finish(vsb_ctx *c, vis_stage &st, int64_t n, int64_t *idx_out, in
 {
     VSB_TRY(vsb_launch_compact(c, st.flags, n, st.counts, st.total, st.idx));
     int64_t count = 0;
-    if (idx_out && n + 1 <= (int64_t)k_flag_at && !getenv("VSB_NO_MAPPED_FRAME")) {
+    if (idx_out && n + 1 <= (int64_t)k_flag_at && use_mapped(c)) {
         // small lists: the count and all n index slots in one round trip (the first `count` are valid)
         if (c->h_small_cap < 8 * (size_t)n) {
             void *h = realloc(c->h_small, 8 * (size_t)n);

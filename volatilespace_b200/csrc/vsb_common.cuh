@@ -116,6 +116,7 @@ struct vsb_ctx {
     double *h_frame = nullptr;             // host address; d_frame is the device alias
     double *d_frame = nullptr;
     long long frame_seq = 0;
+    bool mapped_refused = false;           // the mapped allocation failed once: copy paths from then on
     // editor curve(): the parameter tables last uploaded (host copy + device copy), re-sent only when
     // they change (reload_settings)
     vsb_buf curve_tabs;
